@@ -1,0 +1,106 @@
+// oracle/amos_cpu.cpp — CPU checker for the batched special-function path.
+//
+// TEST INFRASTRUCTURE ONLY.  This translation unit compiles the scalar,
+// point-by-point TOMS-644 drivers (sciport_rs_b200/csrc/amos/spb_drivers.h)
+// for the host and exposes them through a small C ABI so that tests/ and
+// bench.py's cpu_baseline leg can (a) pin the restatement against the golden
+// vectors generated from scipy.special (the reference's own test oracle,
+// /root/reference/tests/special.rs:10-16) and (b) time a multi-threaded CPU
+// run of the same batch (the stand-in for the reference's
+// `x.mapv(|v| bessel_i(0.0, v.into()))`, /root/reference/src/special/mod.rs:10,
+// parallelised over contiguous chunks).  Nothing in the product path links it.
+#include <cstdint>
+#include <thread>
+#include <vector>
+#include <algorithm>
+#include <cmath>
+
+#include "../sciport_rs_b200/csrc/amos/spb_drivers.h"
+
+using namespace spb;
+
+namespace {
+
+enum Fn { FN_J = 0, FN_Y = 1, FN_I = 2, FN_K = 3, FN_H1 = 4, FN_H2 = 5 };
+
+inline void eval_one(int fn, int kode, double v, cplx z, cplx &out, int &ierr, int &nz) {
+    cplx cy[1];
+    cy[0] = cplx(0.0, 0.0);
+    switch (fn) {
+        case FN_J: nz = besj(z, v, kode, 1, cy, ierr); break;
+        case FN_Y: nz = besy(z, v, kode, cy, ierr); break;
+        case FN_I: nz = besi(z, v, kode, 1, cy, ierr); break;
+        case FN_K: nz = besk(z, v, kode, 1, cy, ierr); break;
+        case FN_H1: nz = besh(z, v, kode, 1, 1, cy, ierr); break;
+        case FN_H2: nz = besh(z, v, kode, 2, 1, cy, ierr); break;
+        default: ierr = 1; nz = 0;
+    }
+    out = cy[0];
+}
+
+template <class F>
+void parallel_for(int64_t n, int threads, F f) {
+    if (threads <= 1 || n < 4096) {
+        f(0, n);
+        return;
+    }
+    std::vector<std::thread> pool;
+    int64_t chunk = (n + threads - 1) / threads;
+    for (int t = 0; t < threads; ++t) {
+        int64_t lo = t * chunk, hi = std::min<int64_t>(n, lo + chunk);
+        if (lo >= hi) break;
+        pool.emplace_back([=] { f(lo, hi); });
+    }
+    for (auto &th : pool) th.join();
+}
+
+}  // namespace
+
+extern "C" {
+
+// Raw AMOS semantics: value as computed, ierr and nz per element.
+int spbo_bessel(int fn, int kode, const double *v, int64_t v_stride, const double *z /*re,im pairs*/,
+                double *out /*re,im pairs*/, int32_t *ierr, int32_t *nz, int64_t n, int threads) {
+    parallel_for(n, threads, [=](int64_t lo, int64_t hi) {
+        for (int64_t i = lo; i < hi; ++i) {
+            cplx o;
+            int ie, nzz;
+            eval_one(fn, kode, v[i * v_stride], cplx(z[2 * i], z[2 * i + 1]), o, ie, nzz);
+            out[2 * i] = o.re;
+            out[2 * i + 1] = o.im;
+            if (ierr) ierr[i] = ie;
+            if (nz) nz[i] = nzz;
+        }
+    });
+    return 0;
+}
+
+// which: 0 Ai, 1 Ai', 2 Bi, 3 Bi'
+int spbo_airy(int which, int kode, const double *z, double *out, int32_t *ierr, int32_t *nz, int64_t n,
+              int threads) {
+    parallel_for(n, threads, [=](int64_t lo, int64_t hi) {
+        for (int64_t i = lo; i < hi; ++i) {
+            cplx zz(z[2 * i], z[2 * i + 1]);
+            cplx o;
+            int ie = 0, nzz = 0;
+            if (which < 2)
+                o = airy(zz, which, kode, nzz, ie);
+            else
+                o = biry(zz, which - 2, kode, ie);
+            out[2 * i] = o.re;
+            out[2 * i + 1] = o.im;
+            if (ierr) ierr[i] = ie;
+            if (nz) nz[i] = nzz;
+        }
+    });
+    return 0;
+}
+
+int spbo_gamln(const double *x, double *out, int64_t n) {
+    for (int64_t i = 0; i < n; ++i) out[i] = gamln(x[i]);
+    return 0;
+}
+
+int spbo_hardware_threads() { return (int)std::thread::hardware_concurrency(); }
+
+}  // extern "C"

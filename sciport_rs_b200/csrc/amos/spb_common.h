@@ -1,0 +1,150 @@
+// spb_common.h — scalar/complex helpers and machine constants shared by every
+// region routine of the batched special-function engine.
+//
+// The arithmetic the reference delegates to `complex-bessel-rs 1.2.0`
+// (/root/reference/Cargo.toml:16; call sites src/special/mod.rs:10 and
+// src/special/kv.rs:19) is D. E. Amos' Algorithm 644 (ACM TOMS 12, 1986).  The
+// dependency's source is not vendored, so the routines below restate the
+// published algorithm; constants follow IEEE-754 binary64.
+//
+// Everything here is `SPB_HD` (host + device) so the same region math can be
+// driven (a) per-region by the CUDA kernels in ../kernels.cu and (b) point by
+// point by the CPU checker built from oracle/.
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define SPB_HD __host__ __device__ __forceinline__
+#define SPB_FN __host__ __device__ inline
+#else
+#define SPB_HD inline
+#define SPB_FN inline
+#endif
+
+// The scalar type can be swapped for an op-counting type on the host
+// (oracle/flopcount.cpp) to tally algorithmic flops per evaluation.
+#ifndef SPB_REAL
+#define SPB_REAL double
+#endif
+
+namespace spb {
+
+typedef SPB_REAL real;
+
+// ---- machine constants (binary64) ------------------------------------------
+// tol = eps; elim = 2.303*(1021*log10(2)-3); alim = elim - 2.303*52*log10(2)
+// rl = 1.2*dig+3, fnul = 10+6*(dig-3), dig = 52*log10(2)
+#define SPB_TOL 2.220446049250313e-16
+#define SPB_R1M5 0.30102999566398120
+#define SPB_ELIM 700.9217936944459         /* 2.303*(1021*R1M5-3) */
+#define SPB_ALIM 664.8716455337102         /* elim - 2.303*52*R1M5 */
+#define SPB_DIG 15.653559774527022         /* 52*R1M5 */
+#define SPB_RL 21.784271729432426          /* 1.2*dig+3 */
+#define SPB_FNUL 85.92135864716213         /* 10+6*(dig-3) */
+#define SPB_D1MACH1 2.2250738585072014e-308
+#define SPB_D1MACH2 1.7976931348623157e+308
+#define SPB_PI 3.14159265358979323846
+#define SPB_HPI 1.57079632679489661923
+
+struct cplx {
+    real re, im;
+    SPB_HD cplx() {}
+    SPB_HD cplx(real r, real i) : re(r), im(i) {}
+};
+
+SPB_HD cplx operator+(cplx a, cplx b) { return cplx(a.re + b.re, a.im + b.im); }
+SPB_HD cplx operator-(cplx a, cplx b) { return cplx(a.re - b.re, a.im - b.im); }
+SPB_HD cplx operator-(cplx a) { return cplx(-a.re, -a.im); }
+SPB_HD cplx operator*(cplx a, cplx b) {
+    return cplx(a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re);
+}
+SPB_HD cplx operator*(cplx a, real s) { return cplx(a.re * s, a.im * s); }
+SPB_HD cplx operator*(real s, cplx a) { return cplx(a.re * s, a.im * s); }
+SPB_HD cplx operator+(cplx a, real s) { return cplx(a.re + s, a.im); }
+SPB_HD cplx operator-(cplx a, real s) { return cplx(a.re - s, a.im); }
+SPB_HD cplx conj(cplx a) { return cplx(a.re, -a.im); }
+// multiplication by +i / -i (exact)
+SPB_HD cplx mul_i(cplx a) { return cplx(-a.im, a.re); }
+SPB_HD cplx mul_mi(cplx a) { return cplx(a.im, -a.re); }
+
+SPB_HD real rabs(real x) { return fabs(x); }
+SPB_HD real rmax(real a, real b) { return a > b ? a : b; }
+SPB_HD real rmin(real a, real b) { return a < b ? a : b; }
+
+// |z| without premature over/underflow (the ZABS of the algorithm).
+SPB_HD real cabs_(cplx z) {
+    real u = rabs(z.re), v = rabs(z.im);
+    real s = u + v;
+    // s*1.0 in the original forces a store; here we only need the zero test.
+    if (s == real(0.0)) return real(0.0);
+    if (u > v) {
+        real q = v / u;
+        return u * sqrt(real(1.0) + q * q);
+    }
+    real q = u / v;
+    return v * sqrt(real(1.0) + q * q);
+}
+
+// a / b via the modulus of b (keeps intermediate values on scale).
+SPB_HD cplx cdiv(cplx a, cplx b) {
+    real bm = real(1.0) / cabs_(b);
+    real cc = b.re * bm, cd = b.im * bm;
+    return cplx((a.re * cc + a.im * cd) * bm, (a.im * cc - a.re * cd) * bm);
+}
+// 1 / b
+SPB_HD cplx crecip(cplx b) {
+    real bm = real(1.0) / cabs_(b);
+    real cc = b.re * bm, cd = b.im * bm;
+    return cplx(cc * bm, -cd * bm);
+}
+
+// principal square root, branch cut on the negative real axis (algebraic
+// form: one modulus, one real square root, one division)
+SPB_HD cplx csqrt_(cplx a) {
+    if (a.im == real(0.0)) {
+        if (a.re >= real(0.0)) return cplx(sqrt(a.re), real(0.0));
+        return cplx(real(0.0), sqrt(-a.re));
+    }
+    real d = cabs_(a);
+    if (a.re > real(0.0)) {
+        real r = sqrt(real(0.5) * (d + a.re));
+        return cplx(r, a.im / (r + r));
+    }
+    real s = sqrt(real(0.5) * (d - a.re));
+    real r = rabs(a.im) / (s + s);
+    return cplx(r, a.im < real(0.0) ? -s : s);
+}
+
+SPB_HD cplx cexp_(cplx a) {
+    real zm = exp(a.re);
+    return cplx(zm * cos(a.im), zm * sin(a.im));
+}
+
+// principal logarithm; ierr=1 for a == 0
+SPB_HD cplx clog_(cplx a, int &ierr) {
+    ierr = 0;
+    if (a.re == real(0.0) && a.im == real(0.0)) {
+        ierr = 1;
+        return cplx(real(0.0), real(0.0));
+    }
+    return cplx(log(cabs_(a)), atan2(a.im, a.re));
+}
+SPB_HD cplx clog_(cplx a) {
+    int ie;
+    return clog_(a, ie);
+}
+
+// Underflow check of one scaled value: the smaller component is considered
+// lost when it is below ascle and tol-times smaller than the larger one.
+SPB_HD int uchk(cplx y, real ascle, real tol) {
+    real wr = rabs(y.re), wi = rabs(y.im);
+    real st = rmin(wr, wi);
+    if (st > ascle) return 0;
+    real ss = rmax(wr, wi);
+    st = st / tol;
+    return (ss < st) ? 1 : 0;
+}
+
+}  // namespace spb

@@ -1,0 +1,441 @@
+// spb_iregions.h — the four "elementary" regions of the modified Bessel
+// function I_fnu(z), Re z >= 0 (TOMS 644 region logic):
+//   seri  : ascending power series                (|z| small or order large)
+//   asyi  : large-|z| Hankel-type asymptotic      (|z| >= rl)
+//   mlri  : Miller backward recurrence, normalised by a Neumann series
+//   rati  : ratios I_{v+1}/I_v by backward continued fraction (for the
+//           Wronskian normalisation in spb_wrsk)
+// All routines fill y[0..n-1] with I_{fnu+k}(z) (kode=1) or
+// exp(-|Re z|) I_{fnu+k}(z) (kode=2) and return the AMOS "nz" convention:
+// >=0 number of underflowed leading members, <0 failure / hand-over code.
+#pragma once
+#include "spb_common.h"
+#include "spb_gamln.h"
+
+namespace spb {
+
+// ---------------------------------------------------------------------------
+// Power series.  nz = -k means: k members underflowed and |z|^2/4 exceeds the
+// remaining order, so the caller must finish with another method.
+SPB_FN int seri(cplx z, real fnu, int kode, int n, cplx *y, real tol, real elim, real alim) {
+    int nz = 0;
+    real az = cabs_(z);
+    if (az == real(0.0)) {
+        y[0] = cplx(fnu == real(0.0) ? 1.0 : 0.0, 0.0);
+        for (int i = 1; i < n; ++i) y[i] = cplx(0.0, 0.0);
+        return 0;
+    }
+    const real arm = real(1.0e3) * SPB_D1MACH1;
+    const real rtr1 = sqrt(arm);
+    real crscr = 1.0;
+    int iflag = 0;
+    if (az < arm) {
+        nz = n;
+        if (fnu == real(0.0)) nz -= 1;
+        y[0] = cplx(fnu == real(0.0) ? 1.0 : 0.0, 0.0);
+        for (int i = 1; i < n; ++i) y[i] = cplx(0.0, 0.0);
+        return nz;
+    }
+    cplx hz = z * real(0.5);
+    cplx cz(0.0, 0.0);
+    if (az > rtr1) cz = hz * hz;
+    real acz = cabs_(cz);
+    int nn = n;
+    cplx ck = clog_(hz);
+    cplx w[2];
+    real ss = 1.0, ascle = 0.0;
+    for (;;) {  // restart point after dropping an underflowed top member
+        real dfnu = fnu + real(nn - 1);
+        real fnup = dfnu + real(1.0);
+        // underflow test on the leading factor (z/2)^v / Gamma(v+1)
+        cplx ak1 = ck * dfnu;
+        real ak = gamln(fnup);
+        ak1.re -= ak;
+        if (kode == 2) ak1.re -= z.re;
+        bool underflow = !(ak1.re > -elim);
+        if (!underflow) {
+            if (!(ak1.re > -alim)) {
+                iflag = 1;
+                ss = real(1.0) / tol;
+                crscr = tol;
+                ascle = arm * ss;
+            }
+            real aa = exp(ak1.re);
+            if (iflag == 1) aa *= ss;
+            cplx coef(aa * cos(ak1.im), aa * sin(ak1.im));
+            real atol = tol * acz / fnup;
+            int il = nn < 2 ? nn : 2;
+            for (int i = 1; i <= il; ++i) {
+                dfnu = fnu + real(nn - i);
+                fnup = dfnu + real(1.0);
+                cplx s1(1.0, 0.0);
+                if (!(acz < tol * fnup)) {
+                    cplx t(1.0, 0.0);
+                    real akk = fnup + real(2.0);
+                    real s = fnup;
+                    real a2 = 2.0;
+                    do {
+                        real rs = real(1.0) / s;
+                        t = (t * cz) * rs;
+                        s1 = s1 + t;
+                        s += akk;
+                        akk += real(2.0);
+                        a2 = a2 * acz * rs;
+                    } while (a2 > atol);
+                }
+                cplx s2 = s1 * coef;
+                w[i - 1] = s2;
+                if (iflag != 0 && uchk(s2, ascle, tol) != 0) {
+                    underflow = true;
+                    break;
+                }
+                y[nn - i] = s2 * crscr;
+                if (i != il) coef = cdiv(coef, hz) * dfnu;
+            }
+        }
+        if (underflow) {
+            nz += 1;
+            y[nn - 1] = cplx(0.0, 0.0);
+            if (acz > dfnu) return -nz;
+            nn -= 1;
+            if (nn == 0) return nz;
+            continue;
+        }
+        break;
+    }
+    if (nn <= 2) return nz;
+    // backward recurrence for the remaining members of the sequence
+    int k = nn - 2;  // 1-based index of the next member to fill
+    real ak = real(k);
+    cplx rz = crecip(z) * real(2.0);
+    int ib = 3;
+    if (iflag == 1) {
+        // recur on scaled values until they are back on scale
+        cplx s1 = w[0], s2 = w[1];
+        int l;
+        bool onscale = false;
+        for (l = 3; l <= nn; ++l) {
+            cplx c = s2;
+            s2 = s1 + (rz * c) * (ak + fnu);
+            s1 = c;
+            cplx c2 = s2 * crscr;
+            y[k - 1] = c2;
+            ak -= real(1.0);
+            k -= 1;
+            if (cabs_(c2) > ascle) {
+                onscale = true;
+                break;
+            }
+        }
+        if (!onscale) return nz;
+        ib = l + 1;
+        if (ib > nn) return nz;
+    }
+    for (int i = ib; i <= nn; ++i) {
+        y[k - 1] = (rz * y[k]) * (ak + fnu) + y[k + 1];
+        ak -= real(1.0);
+        k -= 1;
+    }
+    return nz;
+}
+
+// ---------------------------------------------------------------------------
+// Large-|z| asymptotic expansion.  nz = -1 overflow, -2 no convergence.
+SPB_FN int asyi(cplx z, real fnu, int kode, int n, cplx *y, real rl, real tol, real elim, real alim) {
+    const real rtpi = 0.159154943091895336;  // 1/(2 pi)
+    real az = cabs_(z);
+    const real arm = real(1.0e3) * SPB_D1MACH1;
+    const real rtr1 = sqrt(arm);
+    int il = n < 2 ? n : 2;
+    real dfnu = fnu + real(n - il);
+    // leading factor sqrt(1/(2 pi z)) * exp(z)
+    cplx ak1 = csqrt_(crecip(z) * rtpi);
+    cplx cz = z;
+    if (kode == 2) cz.re = 0.0;
+    if (rabs(cz.re) > elim) return -1;
+    real dnu2 = dfnu + dfnu;
+    int koded = 1;
+    if (!(rabs(cz.re) > alim && n > 2)) {
+        koded = 0;
+        ak1 = ak1 * cexp_(cz);
+    }
+    real fdn = 0.0;
+    if (dnu2 > rtr1) fdn = dnu2 * dnu2;
+    cplx ez = z * real(8.0);
+    // for imaginary z the error test is made relative to the first reciprocal
+    // power, the leading term of the imaginary part
+    real aez = real(8.0) * az;
+    real s = tol / aez;
+    int jl = (int)(rl + rl) + 2;
+    cplx p1(0.0, 0.0);
+    if (z.im != real(0.0)) {
+        // exp(i pi (1/2 + fnu + n - il)) with the integer part folded out
+        int inu = (int)fnu;
+        real arg = (fnu - real(inu)) * SPB_PI;
+        inu = inu + n - il;
+        real ak = -sin(arg);
+        real bk = cos(arg);
+        if (z.im < real(0.0)) bk = -bk;
+        p1 = cplx(ak, bk);
+        if (inu % 2 != 0) p1 = -p1;
+    }
+    for (int k = 1; k <= il; ++k) {
+        real sqk = fdn - real(1.0);
+        real atol = s * rabs(sqk);
+        real sgn = 1.0;
+        cplx cs1(1.0, 0.0), cs2(1.0, 0.0), ck(1.0, 0.0);
+        real ak = 0.0, aa = 1.0, bb = aez;
+        cplx dk = ez;
+        bool conv = false;
+        for (int j = 1; j <= jl; ++j) {
+            ck = cdiv(ck, dk) * sqk;
+            cs2 = cs2 + ck;
+            sgn = -sgn;
+            cs1 = cs1 + ck * sgn;
+            dk = dk + ez;
+            aa = aa * rabs(sqk) / bb;
+            bb += aez;
+            ak += real(8.0);
+            sqk -= ak;
+            if (aa <= atol) {
+                conv = true;
+                break;
+            }
+        }
+        if (!conv) return -2;
+        cplx s2 = cs1;
+        if (z.re + z.re < elim) {
+            cplx tz = z * real(-2.0);
+            s2 = s2 + (cexp_(tz) * p1) * cs2;
+        }
+        fdn = fdn + real(8.0) * dfnu + real(4.0);
+        p1 = -p1;
+        y[n - il + k - 1] = s2 * ak1;
+    }
+    if (n <= 2) return 0;
+    int nn = n;
+    int k = nn - 2;
+    real ak = real(k);
+    cplx rz = crecip(z) * real(2.0);
+    for (int i = 3; i <= nn; ++i) {
+        y[k - 1] = (rz * y[k]) * (ak + fnu) + y[k + 1];
+        ak -= real(1.0);
+        k -= 1;
+    }
+    if (koded == 0) return 0;
+    cplx ckk = cexp_(cz);
+    for (int i = 0; i < nn; ++i) y[i] = y[i] * ckk;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Miller algorithm normalised by a Neumann series.  nz = -2: no convergence.
+SPB_FN int mlri(cplx z, real fnu, int kode, int n, cplx *y, real tol) {
+    const real scle = SPB_D1MACH1 / tol;
+    real az = cabs_(z);
+    int iaz = (int)az;
+    int ifnu = (int)fnu;
+    int inu = ifnu + n - 1;
+    real at = real(iaz) + real(1.0);
+    cplx rcz = crecip(z);
+    cplx ck = rcz * at;
+    cplx rz = rcz * real(2.0);
+    real raz = real(1.0) / az;
+    cplx p1(0.0, 0.0), p2(1.0, 0.0);
+    real ack = (at + real(1.0)) * raz;
+    real rho = ack + sqrt(ack * ack - real(1.0));
+    real rho2 = rho * rho;
+    real tst = (rho2 + rho2) / ((rho2 - real(1.0)) * (rho - real(1.0)));
+    tst = tst / tol;
+    // relative truncation error index for the series
+    real ak = at;
+    int i;
+    bool found = false;
+    for (i = 1; i <= 80; ++i) {
+        cplx pt = p2;
+        p2 = p1 - ck * pt;
+        p1 = pt;
+        ck = ck + rz;
+        real ap = cabs_(p2);
+        if (ap > tst * ak * ak) {
+            found = true;
+            break;
+        }
+        ak += real(1.0);
+    }
+    if (!found) return -2;
+    i += 1;
+    int k = 0;
+    if (inu >= iaz) {
+        // relative truncation error for the ratios
+        p1 = cplx(0.0, 0.0);
+        p2 = cplx(1.0, 0.0);
+        at = real(inu) + real(1.0);
+        ck = rcz * at;
+        ack = at * raz;
+        tst = sqrt(ack / tol);
+        int itime = 1;
+        found = false;
+        for (k = 1; k <= 80; ++k) {
+            cplx pt = p2;
+            p2 = p1 - ck * pt;
+            p1 = pt;
+            ck = ck + rz;
+            real ap = cabs_(p2);
+            if (ap < tst) continue;
+            if (itime == 2) {
+                found = true;
+                break;
+            }
+            ack = cabs_(ck);
+            real flam = ack + sqrt(ack * ack - real(1.0));
+            real fkap = ap / cabs_(p1);
+            rho = rmin(flam, fkap);
+            tst = tst * sqrt(rho / (rho * rho - real(1.0)));
+            itime = 2;
+        }
+        if (!found) return -2;
+    }
+    // backward recurrence and sum of the normalising relation
+    k += 1;
+    int kk = (i + iaz) > (k + inu) ? (i + iaz) : (k + inu);
+    real fkk = real(kk);
+    p1 = cplx(0.0, 0.0);
+    p2 = cplx(scle, 0.0);  // scaled start value
+    real fnf = fnu - real(ifnu);
+    real tfnf = fnf + fnf;
+    real bk = gamln(fkk + tfnf + real(1.0)) - gamln(fkk + real(1.0)) - gamln(tfnf + real(1.0));
+    bk = exp(bk);
+    cplx sum(0.0, 0.0);
+    int km = kk - inu;
+    for (int j = 1; j <= km; ++j) {
+        cplx pt = p2;
+        p2 = p1 + (rz * pt) * (fkk + fnf);
+        p1 = pt;
+        real a = real(1.0) - tfnf / (fkk + tfnf);
+        real ac = bk * a;
+        sum = sum + p1 * (ac + bk);
+        bk = ac;
+        fkk -= real(1.0);
+    }
+    y[n - 1] = p2;
+    for (int j = 2; j <= n; ++j) {
+        cplx pt = p2;
+        p2 = p1 + (rz * pt) * (fkk + fnf);
+        p1 = pt;
+        real a = real(1.0) - tfnf / (fkk + tfnf);
+        real ac = bk * a;
+        sum = sum + p1 * (ac + bk);
+        bk = ac;
+        fkk -= real(1.0);
+        y[n - j] = p2;
+    }
+    for (int j = 1; j <= ifnu; ++j) {
+        cplx pt = p2;
+        p2 = p1 + (rz * pt) * (fkk + fnf);
+        p1 = pt;
+        real a = real(1.0) - tfnf / (fkk + tfnf);
+        real ac = bk * a;
+        sum = sum + p1 * (ac + bk);
+        bk = ac;
+        fkk -= real(1.0);
+    }
+    cplx pt = z;
+    if (kode == 2) pt.re = 0.0;
+    cplx lrz = clog_(rz);
+    cplx q = pt - lrz * fnf;
+    real ap = gamln(real(1.0) + fnf);
+    q.re -= ap;
+    // exp(q)/(sum+p2) without squaring large magnitudes
+    p2 = p2 + sum;
+    ap = cabs_(p2);
+    real rap = real(1.0) / ap;
+    cplx e = cexp_(q) * rap;
+    cplx cnorm = e * (conj(p2) * rap);
+    for (int j = 0; j < n; ++j) y[j] = y[j] * cnorm;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Ratios cy[k] = I_{fnu+k+1}(z)/I_{fnu+k}(z), k = 0..n-1, by backward
+// recurrence started from an index chosen by a forward magnitude walk.
+SPB_FN void rati(cplx z, real fnu, int n, cplx *cy, real tol) {
+    const real rt2 = 1.41421356237309515;
+    real az = cabs_(z);
+    int inu = (int)fnu;
+    int idnu = inu + n - 1;
+    int magz = (int)az;
+    real amagz = real(magz + 1);
+    real fdnu = real(idnu);
+    real fnup = rmax(amagz, fdnu);
+    int id = idnu - magz - 1;
+    int itime = 1;
+    int k = 1;
+    cplx rz = crecip(z) * real(2.0);
+    cplx t1 = rz * fnup;
+    cplx p2 = -t1;
+    cplx p1(1.0, 0.0);
+    t1 = t1 + rz;
+    if (id > 0) id = 0;
+    real ap2 = cabs_(p2);
+    real ap1 = cabs_(p1);
+    // scale test values by ap1 so that an overflow does not occur prematurely
+    real arg = (ap2 + ap2) / (ap1 * tol);
+    real test1 = sqrt(arg);
+    real test = test1;
+    real rap1 = real(1.0) / ap1;
+    p1 = p1 * rap1;
+    p2 = p2 * rap1;
+    ap2 = ap2 * rap1;
+    for (;;) {
+        k += 1;
+        ap1 = ap2;
+        cplx pt = p2;
+        p2 = p1 - t1 * pt;
+        p1 = pt;
+        t1 = t1 + rz;
+        ap2 = cabs_(p2);
+        if (ap1 <= test) continue;
+        if (itime == 2) break;
+        real ak = cabs_(t1) * real(0.5);
+        real flam = ak + sqrt(ak * ak - real(1.0));
+        real rho = rmin(ap2 / ap1, flam);
+        test = test1 * sqrt(rho / (rho * rho - real(1.0)));
+        itime = 2;
+    }
+    int kk = k + 1 - id;
+    real ak = real(kk);
+    real t1r = ak;
+    real dfnu = fnu + real(n - 1);
+    p1 = cplx(real(1.0) / ap2, 0.0);
+    p2 = cplx(0.0, 0.0);
+    for (int i = 1; i <= kk; ++i) {
+        cplx pt = p1;
+        real rap = dfnu + t1r;
+        cplx tt = rz * rap;
+        p1 = pt * tt + p2;
+        p2 = pt;
+        t1r -= real(1.0);
+    }
+    if (p1.re == real(0.0) && p1.im == real(0.0)) p1 = cplx(tol, tol);
+    cy[n - 1] = cdiv(p2, p1);
+    if (n == 1) return;
+    k = n - 1;
+    ak = real(k);
+    t1r = ak;
+    cplx cdfnu = rz * fnu;
+    for (int i = 2; i <= n; ++i) {
+        cplx pt = cdfnu + rz * t1r + cy[k];
+        ak = cabs_(pt);
+        if (ak == real(0.0)) {
+            pt = cplx(tol, tol);
+            ak = tol * rt2;
+        }
+        real rak = real(1.0) / ak;
+        cy[k - 1] = conj(pt) * rak * rak;
+        t1r -= real(1.0);
+        k -= 1;
+    }
+}
+
+}  // namespace spb
