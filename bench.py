@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the batched complex Bessel path on B200 (BASELINE.json metric).
+
+One *step* = one pass of the hot path over one batch of synthetic input: J_v and Y_v (v = 2.5) over the
+4096 x 4096 complex grid |z| <= 200 of BASELINE config[1] ("complex Bessel jv/yv, fixed order v=2.5,
+4096x4096 complex grid |z|<=200, single B200"); one *eval* = one complex output, so a step is
+2 * 4096^2 evals.  Inputs are generated on the device (spb_synth) and stay resident in HBM for `value`;
+`e2e` runs the same step through the host-buffer C-ABI path (pinned host memory -> H2D -> kernels -> D2H).
+
+    python bench.py --gpus N --steps K --warmup W          (N > 1: launched by torchrun, one rank per GPU,
+                                                             every rank its own grid: weak scaling, no collective
+                                                             on the data path, barrier + max-over-ranks timing)
+    python bench.py --impl reference ...                   the reference's CPU path stand-in (oracle port,
+                                                             all host threads) on a bounded sample of the same work
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SIDE = 4096
+N_POINTS = SIDE * SIDE
+ORDER = 2.5
+METRIC = "complex_bessel_evals_per_sec"
+UNIT = "evals/s"
+WORKLOAD = "cfg2: jv+yv, v=2.5, 4096x4096 complex grid |z|<=200 (2 evals per point)"
+# algorithmic cost per eval: 16 B in + 16 B out; flops from the op-count tally
+BYTES_PER_EVAL = 32.0
+
+
+def load_flops_per_eval():
+    path = os.path.join(ROOT, "profiles", "flops_per_eval.json")
+    try:
+        with open(path) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1]))
+                mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_sample_points(n_sample):
+    """Evenly strided subsample of the cfg2 grid (same generator as the device: SURVEY.md §8d)."""
+    idx = (np.arange(n_sample, dtype=np.int64) * (N_POINTS // n_sample)) % N_POINTS
+    j = idx % SIDE
+    k = idx // SIDE
+    a = 200.0 / np.sqrt(2.0)
+    return (-a + 2 * a * (j + 0.5) / SIDE) + 1j * (-a + 2 * a * (k + 0.5) / SIDE)
+
+
+def run_cpu_port(n_sample, threads, repeats=1):
+    """Time the CPU checker (oracle/libspb_oracle.so: the point-by-point TOMS-644 drivers, one thread per core)
+    on a bounded sample of the step.  Returns evals/s."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers  # noqa: E402  (test infrastructure; allowed here as the cpu_baseline leg)
+    z = cpu_sample_points(n_sample)
+    helpers.cpu_bessel("J", 1, ORDER, z[:4096], threads=threads)  # warm
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        helpers.cpu_bessel("J", 1, ORDER, z, threads=threads)
+        helpers.cpu_bessel("Y", 1, ORDER, z, threads=threads)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return 2 * n_sample / best, best
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n_sample = 1 << 20
+    for _ in range(args.warmup):
+        run_cpu_port(1 << 16, threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        run_cpu_port(n_sample, threads)
+    dt = time.perf_counter() - t0
+    value = 2 * n_sample * args.steps / dt
+    sample = f"{n_sample} evenly strided points of the 4096x4096 grid per step, jv+yv"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "CPU stand-in for the reference path: the Rust crate cannot be built "
+                   "here (no rustc); oracle/ port of the same TOMS-644 algorithm, one thread per host core"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from sciport_rs_b200 import special, _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: sciport_rs_b200 has no CPU path")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    warmup = max(args.warmup, 3)
+
+    # FP64 peak of this GPU (DFMA microbenchmark, part of the library), before the timed region
+    fp64_peak, _ = special.fp64_peak(local_rank, 1.0)
+
+    # inputs resident in HBM: this rank's own 4096 x 4096 grid
+    v, z = special.synth(2, N_POINTS, n_total=N_POINTS, device=dev)
+    vt = torch.full((1,), ORDER, dtype=torch.float64, device=dev)
+
+    kernel_ms = [0.0]
+    launches = [0]
+
+    def step():
+        oj, ej, _ = special.bessel("J", vt, z)
+        ms1, l1 = _lib.last_timing()
+        oy, ey, _ = special.bessel("Y", vt, z)
+        ms2, l2 = _lib.last_timing()
+        kernel_ms[0] += ms1 + ms2
+        launches[0] += l1 + l2
+        return oj, oy, ej, ey
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    kernel_ms[0] = 0.0
+    launches[0] = 0
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(args.steps):
+        out = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.barrier()
+        ms = float(t.item())
+    evals_per_step = 2 * N_POINTS * world
+    value = evals_per_step * args.steps / (ms * 1e-3)
+
+    # per-kernel times of one profiled step (events between launches) for the roofline of the dominant kernel
+    prof = special.profile_step(lambda: (special.bessel("J", vt, z, profile=True), special.bessel("Y", vt, z, profile=True)))
+
+    # end to end through the host-buffer C ABI: pinned host memory in, host memory out, copies inside the timed region
+    e2e = None
+    if rank == 0 or world > 1:
+        zh = torch.empty(N_POINTS, dtype=torch.complex128).pin_memory()
+        zh.copy_(z)
+        zn = zh.numpy()
+        special.bessel("J", ORDER, zn[: 1 << 20])  # warm the staging buffers
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            oj, ej, nj = special.bessel("J", ORDER, zn)
+            oy, ey, ny = special.bessel("Y", ORDER, zn)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        h2d = 2 * (zn.nbytes + 8)
+        d2h = 2 * (oj.nbytes + ej.nbytes + nj.nbytes)
+        e2e = {"value": evals_per_step * args.e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "steps": args.e2e_steps,
+               "note": "host pinned buffers through spb_bessel (H2D, kernels, D2H inside the timed region)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    flops = load_flops_per_eval()
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    # dominant kernel = the one with the largest share of the profiled step
+    top = max(prof, key=lambda r: r["ms"]) if prof else None
+    roofline = None
+    if top:
+        fpe = flops.get(top["name"], {}).get("flops_per_point")
+        pts = top.get("points") or 0
+        achieved = (fpe * pts / (top["ms"] * 1e-3) / 1e12) if (fpe and pts) else None
+        roofline = {
+            "bound": "fp64", "kernel": top["name"], "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+            "frac": (achieved / fp64_peak) if achieved else None, "traffic": None,
+            "peak_source": "spb_fp64_peak DFMA microbenchmark on this GPU (MEASURED_PEAKS.json has no FP64 figure)",
+            "flops_per_point": fpe, "points_per_launch": pts, "launch_ms": top["ms"],
+            "share_of_step": top["ms"] / max(sum(r["ms"] for r in prof), 1e-9),
+            "hbm_view": {"achieved_gbs": BYTES_PER_EVAL * pts / (top["ms"] * 1e-3) / 1e9 if pts else None,
+                         "peak_gbs": peaks.get("hbm_gbs")},
+            "kernels": prof,
+        }
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        n_sample = 1 << 20
+        cv, cdt = run_cpu_port(n_sample, threads)
+        cpu_baseline = {"value": cv, "unit": UNIT, "cores": threads, "kind": "port",
+                        "sample": f"{n_sample} evenly strided grid points, jv+yv, {cdt:.2f} s"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "points_per_gpu": N_POINTS, "order": ORDER,
+                   "l2": "inputs+outputs per step 1.1 GB >> 126 MB L2 (no flush needed)",
+                   "timing": "CUDA events on the launching stream, max over ranks", "path": "binned"},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": launches[0],
+        "kernel_ms_per_step": kernel_ms[0] / args.steps, "fp64_peak_tflops": fp64_peak,
+        "roofline": roofline, "cpu_baseline": cpu_baseline,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

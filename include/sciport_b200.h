@@ -1,0 +1,157 @@
+/* sciport_b200.h — C ABI of the B200 batched special-function engine.
+ *
+ * Drop-in boundary for sciport-rs's `special` module.  The
+ * reference reaches its arithmetic through two scalar calls into the external
+ * crate complex-bessel-rs 1.2.0:
+ *
+ *   complex_bessel_rs::bessel_i::bessel_i(order: f64, z: Complex<f64>) -> Result<Complex<f64>, i32>
+ *       call site /root/reference/src/special/mod.rs:10   (special::i0, batched over Array1<f64>)
+ *   complex_bessel_rs::bessel_k::bessel_k(order: f64, z: Complex<f64>) -> Result<Complex<f64>, E>
+ *       call site /root/reference/src/special/kv.rs:19    (special::kv / special::kve)
+ *
+ * The entry points below are what a `build.rs` + `extern "C"` block in the
+ * Rust crate binds instead (INTEGRATION.md shows the stub): batched forms with
+ * the reference's argument order (order first, then z: kv.rs:11), the
+ * unscaled / exponentially scaled pair selected by `kode` (kv vs kve,
+ * kv.rs:11,39), complex values as `#[repr(C)] {re, im}` pairs (= CUDA
+ * double2), and the per-element error code the reference's `Result<_, i32>`
+ * carries (mod.rs:8).
+ *
+ * All functions return 0 on success, a negative SPB_E_* code on failure
+ * (spb_last_error() gives the text).  There is NO CPU fallback: without a
+ * CUDA device every compute entry point fails with SPB_E_NO_DEVICE.
+ */
+#ifndef SCIPORT_B200_H
+#define SCIPORT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct spb_c128 {
+    double re, im;
+} spb_c128; /* == num::Complex<f64> (#[repr(C)]) == double2 */
+
+/* function selector of spb_bessel (order-then-z like kv(v, z), kv.rs:11) */
+enum spb_fn {
+    SPB_FN_J = 0,  /* J_v(z)                                  */
+    SPB_FN_Y = 1,  /* Y_v(z)                                  */
+    SPB_FN_I = 2,  /* I_v(z)   — replaces bessel_i, mod.rs:10 */
+    SPB_FN_K = 3,  /* K_v(z)   — replaces bessel_k, kv.rs:19  */
+    SPB_FN_H1 = 4, /* H^(1)_v(z)                              */
+    SPB_FN_H2 = 5  /* H^(2)_v(z)                              */
+};
+
+/* kode: 1 = unscaled (kv), 2 = exponentially scaled (kve; I,J,Y: e^{-|Re z|} resp. e^{-|Im z|};
+ * K: e^{z}; H1: e^{-iz}; H2: e^{iz}) */
+enum spb_kode { SPB_KODE_UNSCALED = 1, SPB_KODE_SCALED = 2 };
+
+/* which of spb_airy */
+enum spb_airy_which { SPB_AIRY_AI = 0, SPB_AIRY_AIP = 1, SPB_AIRY_BI = 2, SPB_AIRY_BIP = 3 };
+
+/* per-element error code (AMOS IERR, the i32 of Result<_, i32>, mod.rs:8) */
+enum spb_ierr {
+    SPB_IERR_OK = 0,
+    SPB_IERR_INPUT = 1,    /* invalid input / singular point (e.g. K at z = 0) */
+    SPB_IERR_OVERFLOW = 2, /* result too large                                  */
+    SPB_IERR_HALF = 3,     /* argument so large that half the digits are lost   */
+    SPB_IERR_LOST = 4,     /* argument so large that no digits remain           */
+    SPB_IERR_NOCONV = 5    /* an internal iteration failed to converge          */
+};
+
+/* error returns of the library calls themselves */
+enum spb_status {
+    SPB_OK = 0,
+    SPB_E_ARG = -1,       /* bad argument (null pointer, unknown selector, n < 0 …) */
+    SPB_E_NO_DEVICE = -2, /* no CUDA device: this library has no CPU path          */
+    SPB_E_CUDA = -3,      /* a CUDA runtime call failed                            */
+    SPB_E_ALLOC = -4      /* device or pinned-host allocation failed               */
+};
+
+/* exec.flags */
+enum spb_flags {
+    SPB_SEM_AMOS = 0,   /* value exactly as the algorithm leaves it (0 on failure) + ierr/nz  */
+    SPB_SEM_SCIPY = 1,  /* value post-processed like scipy.special, the reference's test oracle
+                           (tests/special.rs:10-16): NaN on ierr 1/2/4/5, +-inf on overflow
+                           where the sign is known, negative orders by reflection           */
+    SPB_PATH_BINNED = 0,     /* classify -> stable compaction by region -> per-region kernels */
+    SPB_PATH_MONOLITHIC = 16, /* one thread runs the whole driver per point (debug / checker) */
+    SPB_PROFILE = 32          /* device pointers only: CUDA events between the kernel launches;
+                                 read the records back with spb_last_profile()                 */
+};
+
+/* kernel ids reported by spb_last_profile */
+enum spb_kernel_id {
+    SPB_K_CLASSIFY = 0,      /* region classification + per-tile histogram          */
+    SPB_K_SCAN_SCATTER = 1,  /* offsets scan + warp-aggregated stable compaction     */
+    SPB_K_IPASS_SERIES = 2,  /* I pass: power series                                 */
+    SPB_K_IPASS_ASYI = 3,    /* I pass: large-|z| asymptotic expansion               */
+    SPB_K_IPASS_MLRI = 4,    /* I pass: Miller recurrence, Neumann normalisation     */
+    SPB_K_IPASS_WRSK = 5,    /* I pass: Miller ratios, Wronskian normalisation       */
+    SPB_K_KPASS = 6,         /* K pass + family combine                              */
+    SPB_K_GENERAL = 7,       /* general per-point path                               */
+    SPB_K_MONOLITHIC = 8     /* whole batch through the general path                 */
+};
+
+/* where the buffers live and which GPUs to use */
+typedef struct spb_exec {
+    int n_devices;      /* 0 or 1: one device; >1: slice [i*n/G,(i+1)*n/G) per device (host pointers only) */
+    const int *devices; /* device ordinals, NULL = 0..n_devices-1 (or the current device)                  */
+    int device_ptrs;    /* 0: all buffers are host memory (pinned or pageable); 1: device memory on devices[0] */
+    void *stream;       /* cudaStream_t to enqueue on when device_ptrs = 1 (NULL = default stream)         */
+    int flags;          /* spb_flags, OR-ed                                                                */
+} spb_exec;
+
+/* ---- Bessel / Hankel ---------------------------------------------------------------------
+ * out[k*n + i] = F_{v_i + k}(z_i),  k = 0..n_orders-1,  i = 0..n-1
+ * v[i*v_stride] is the (starting) order of point i; v_stride = 0 broadcasts one scalar order.
+ * ierr / nz may be NULL.  nz = number of members set to zero by underflow. */
+int spb_bessel(int fn, int kode, const double *v, int64_t v_stride, const spb_c128 *z, spb_c128 *out,
+               int32_t *ierr, int32_t *nz, int64_t n, int n_orders, const spb_exec *ex);
+
+/* same with real arguments promoted to complex, the shape of special::i0 (mod.rs:8-13: `v.into()`) */
+int spb_bessel_real(int fn, int kode, const double *v, int64_t v_stride, const double *x, spb_c128 *out,
+                    int32_t *ierr, int32_t *nz, int64_t n, int n_orders, const spb_exec *ex);
+
+/* ---- Airy -------------------------------------------------------------------------------- */
+int spb_airy(int which, int kode, const spb_c128 *z, spb_c128 *out, int32_t *ierr, int32_t *nz, int64_t n,
+             const spb_exec *ex);
+
+/* ---- gamma companions (memory-bound) ------------------------------------------------------ */
+int spb_gamma(const double *x, double *out, int64_t n, const spb_exec *ex);    /* Gamma(x), real    */
+int spb_lgamma(const double *x, double *out, int64_t n, const spb_exec *ex);   /* ln|Gamma(x)|      */
+int spb_cgamma(const spb_c128 *z, spb_c128 *out, int64_t n, const spb_exec *ex);   /* Gamma(z)      */
+int spb_clgamma(const spb_c128 *z, spb_c128 *out, int64_t n, const spb_exec *ex);  /* loggamma(z)   */
+
+/* ---- sinc, special::sinc (trig.rs:4-13): sin(pi x)/(pi x), 1 at x = 0 ---------------------- */
+int spb_sinc(const double *x, double *out, int64_t n, const spb_exec *ex);
+
+/* ---- first error in index order = `.collect::<Result<_, i32>>()` (mod.rs:11-12) ------------
+ * *idx = -1, *code = 0 when every element is OK.  ierr lives where ex says. */
+int spb_first_error(const int32_t *ierr, int64_t n, int64_t *idx, int32_t *code, const spb_exec *ex);
+
+/* ---- synthetic inputs: index-addressable splitmix64 stream -----------------
+ * Fills v[offset..offset+n) / z[...] for BASELINE config `cfg` (2,3,4,5) directly where ex says. */
+int spb_synth(int cfg, uint64_t seed, int64_t offset, int64_t n, int64_t n_total, double *v, spb_c128 *z,
+              const spb_exec *ex);
+
+/* ---- measurement helpers ------------------------------------------------------------------ */
+/* sustained DFMA throughput of `device` in TFLOP/s (register-resident, 8 independent chains/thread) */
+int spb_fp64_peak(int device, double seconds, double *tflops, double *sm_mhz);
+/* device time (ms) spent in kernels of the last spb_* compute call on this thread, measured with
+ * CUDA events on the launching stream, and how many kernels it launched */
+int spb_last_timing(double *kernel_ms, int *launches);
+/* per-kernel records of the last spb_bessel call made with SPB_PROFILE on this thread: returns the number of
+ * records written (<= max_records); points = elements the launch processed */
+int spb_last_profile(int max_records, int *kernel_ids, double *ms, int64_t *points);
+
+int spb_device_count(void);
+int spb_version(void);
+const char *spb_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCIPORT_B200_H */

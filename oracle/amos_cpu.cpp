@@ -15,7 +15,8 @@
 #include <algorithm>
 #include <cmath>
 
-#include "../sciport_rs_b200/csrc/amos/spb_drivers.h"
+#include "../sciport_rs_b200/csrc/amos/spb_family.h"
+#include "../sciport_rs_b200/csrc/amos/spb_gamma.h"
 
 using namespace spb;
 
@@ -24,18 +25,7 @@ namespace {
 enum Fn { FN_J = 0, FN_Y = 1, FN_I = 2, FN_K = 3, FN_H1 = 4, FN_H2 = 5 };
 
 inline void eval_one(int fn, int kode, double v, cplx z, cplx &out, int &ierr, int &nz) {
-    cplx cy[1];
-    cy[0] = cplx(0.0, 0.0);
-    switch (fn) {
-        case FN_J: nz = besj(z, v, kode, 1, cy, ierr); break;
-        case FN_Y: nz = besy(z, v, kode, cy, ierr); break;
-        case FN_I: nz = besi(z, v, kode, 1, cy, ierr); break;
-        case FN_K: nz = besk(z, v, kode, 1, cy, ierr); break;
-        case FN_H1: nz = besh(z, v, kode, 1, 1, cy, ierr); break;
-        case FN_H2: nz = besh(z, v, kode, 2, 1, cy, ierr); break;
-        default: ierr = 1; nz = 0;
-    }
-    out = cy[0];
+    out = general_eval(fn, z, v, kode, ierr, nz);
 }
 
 template <class F>
@@ -58,18 +48,47 @@ void parallel_for(int64_t n, int threads, F f) {
 
 extern "C" {
 
+int spbo_bessel_sem(int fn, int kode, int sem, const double *v, int64_t v_stride, const double *z, double *out,
+                    int32_t *ierr, int32_t *nz, int64_t n, int threads);
+
 // Raw AMOS semantics: value as computed, ierr and nz per element.
 int spbo_bessel(int fn, int kode, const double *v, int64_t v_stride, const double *z /*re,im pairs*/,
                 double *out /*re,im pairs*/, int32_t *ierr, int32_t *nz, int64_t n, int threads) {
+    return spbo_bessel_sem(fn, kode, 0, v, v_stride, z, out, ierr, nz, n, threads);
+}
+
+// sem = 1 additionally applies the scipy value conventions (NaN / signed infinity on failure).
+int spbo_bessel_sem(int fn, int kode, int sem, const double *v, int64_t v_stride, const double *z, double *out,
+                    int32_t *ierr, int32_t *nz, int64_t n, int threads) {
     parallel_for(n, threads, [=](int64_t lo, int64_t hi) {
         for (int64_t i = lo; i < hi; ++i) {
             cplx o;
             int ie, nzz;
-            eval_one(fn, kode, v[i * v_stride], cplx(z[2 * i], z[2 * i + 1]), o, ie, nzz);
+            cplx zz(z[2 * i], z[2 * i + 1]);
+            eval_one(fn, kode, v[i * v_stride], zz, o, ie, nzz);
+            if (sem) o = apply_semantics(fn, zz, v[i * v_stride], kode, o, ie, nzz);
             out[2 * i] = o.re;
             out[2 * i + 1] = o.im;
             if (ierr) ierr[i] = ie;
             if (nz) nz[i] = nzz;
+        }
+    });
+    return 0;
+}
+
+// Same batch through the restructured flow the GPU kernels use (prepare / I pass /
+// K pass / finish); path[i] = 0 binned, 1 general from prepare, 2 general after a pass.
+int spbo_bessel_pipeline(int fn, int kode, const double *v, int64_t v_stride, const double *z, double *out,
+                         int32_t *ierr, int32_t *nz, int32_t *path, int64_t n, int threads) {
+    parallel_for(n, threads, [=](int64_t lo, int64_t hi) {
+        for (int64_t i = lo; i < hi; ++i) {
+            int ie, nzz, pth;
+            cplx o = pipeline_eval(fn, cplx(z[2 * i], z[2 * i + 1]), v[i * v_stride], kode, ie, nzz, pth);
+            out[2 * i] = o.re;
+            out[2 * i + 1] = o.im;
+            if (ierr) ierr[i] = ie;
+            if (nz) nz[i] = nzz;
+            if (path) path[i] = pth;
         }
     });
     return 0;
@@ -93,6 +112,23 @@ int spbo_airy(int which, int kode, const double *z, double *out, int32_t *ierr, 
             if (nz) nz[i] = nzz;
         }
     });
+    return 0;
+}
+
+// which: 0 gamma, 1 ln|gamma|, 2 sinc
+int spbo_gamma(int which, const double *x, double *out, int64_t n) {
+    for (int64_t i = 0; i < n; ++i)
+        out[i] = which == 0 ? gamma_real(x[i]) : which == 1 ? lgamma_real(x[i]) : sinc_real(x[i]);
+    return 0;
+}
+
+// which: 0 gamma(z), 1 loggamma(z)
+int spbo_cgamma(int which, const double *z, double *out, int64_t n) {
+    for (int64_t i = 0; i < n; ++i) {
+        cplx r = which == 0 ? cgamma(cplx(z[2 * i], z[2 * i + 1])) : cloggamma(cplx(z[2 * i], z[2 * i + 1]));
+        out[2 * i] = r.re;
+        out[2 * i + 1] = r.im;
+    }
     return 0;
 }
 

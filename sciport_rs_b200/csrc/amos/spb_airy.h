@@ -317,3 +317,15 @@ SPB_FN cplx biry(cplx z, int id, int kode, int &ierr) {
 }
 
 }  // namespace spb
+
+namespace spb {
+// scipy.special.airy value convention: NaN on domain / overflow / no-result codes
+SPB_HD cplx airy_semantics(cplx z, cplx val, int ierr) {
+    (void)z;
+    if (ierr == 1 || ierr == 2 || ierr == 4 || ierr == 5) {
+        const real inf = real(1.0) / real(0.0);
+        return cplx(inf - inf, inf - inf);
+    }
+    return val;
+}
+}  // namespace spb

@@ -1,0 +1,418 @@
+// spb_family.h — the six Bessel families re-expressed for the binned GPU
+// pipeline:
+//
+//     prepare(z, v)  ->  one right-half-plane point w, which of I_v(w) / K_v(w)
+//                        are needed, and whether the point is "simple"
+//     I pass         ->  I_v(w) by exactly one region routine (no fall-through)
+//     K pass         ->  K_v(w) by the K region routine
+//     finish         ->  rotation / analytic continuation / Hankel difference
+//
+// A point is "simple" when (a) the over/underflow pre-test (uoik) is provably a
+// no-op, (b) its region routine completes without handing over to another
+// region, and (c) the order is below the uniform-K threshold.  Everything else
+// is routed to the general per-point driver (spb_drivers.h) on the GPU, so both
+// paths produce the same numbers; the split only removes divergence.
+//
+// J and I follow "ZBESJ"/"ZBESI"; K, H1, H2 follow "ZBESK"/"ZBESH" with the
+// continuation "ZACON"; Y = (H1 - H2)/(2i) shares ONE (I, K) pair between its
+// two Hankel terms because both reduce to the same right-half-plane point.
+#pragma once
+#include "spb_common.h"
+#include "spb_binu.h"
+#include "spb_drivers.h"
+
+namespace spb {
+
+enum Family { FAM_J = 0, FAM_Y = 1, FAM_I = 2, FAM_K = 3, FAM_H1 = 4, FAM_H2 = 5 };
+
+// how finish() combines the pass results
+enum Combine {
+    CMB_FINAL = 0,    // prepare already produced the result (error / trivial)
+    CMB_GENERAL = 1,  // not simple: evaluate with the per-point driver
+    CMB_I_ROT = 2,    // J / I: rotate I(w)
+    CMB_K_ROT = 3,    // K / H with w in the right half plane: rotate K(w)
+    CMB_ACON = 4,     // K / H in the left half plane: continuation from I(w), K(w)
+    CMB_Y_SHARED = 5, // Y from one (I(w), K(w)) pair
+    CMB_Y_CONJ = 6    // Y on the positive real axis: K(w) and its conjugate
+};
+
+// K-pass regions
+enum KRegion { KREG_SERIES = 0, KREG_MILLER = 1, KREG_HALF = 2, KREG_COUNT = 3 };
+
+struct Prep {
+    cplx w;       // right-half-plane evaluation point
+    int combine;  // Combine
+    int ireg;     // IRegion for the I pass, -1 if I is not needed
+    int kreg;     // KRegion for the K pass, -1 if K is not needed
+    int ierr;     // preliminary ierr (0 or 3)
+    int mr;       // continuation direction (+-1)
+};
+
+// Conservative bound on |Re(-zeta1 + zeta2 -+ w)| of the leading uniform term for
+// order gnu at w: if it stays below alim, uoik() returns 0 without touching y.
+SPB_HD bool uoik_is_noop(real az, real gnu, real alim) {
+    real t = az / gnu;
+    real b = gnu * (log(real(1.0) + real(2.0) / t + t) + real(SPB_PI) + real(1.0)) + az + az;
+    return b < alim;
+}
+
+SPB_HD int kregion(cplx w, real fnu) {
+    int inu = (int)(fnu + real(0.5));
+    real dnu = fnu - real(inu);
+    if (rabs(dnu) == real(0.5)) return KREG_HALF;
+    if (!(cabs_(w) > real(2.0))) return KREG_SERIES;
+    return KREG_MILLER;
+}
+
+// Is the I evaluation at (w, fnu) simple, and in which region?
+SPB_HD int iregion_simple(cplx w, real fnu, real az, bool &simple) {
+    const real rl = SPB_RL, fnul = SPB_FNUL, alim = SPB_ALIM;
+    int r = binu_region(w, fnu, 1, rl, fnul);
+    simple = true;
+    if (r == IREG_MLRI || r == IREG_WRSK || r == IREG_BUNI) {
+        // these are entered through uoik(ikflg=1) unless dfnu <= 1 took the direct Miller route
+        bool direct = (r == IREG_MLRI) && (az < rl) && (fnu <= real(1.0));
+        if (!direct && !uoik_is_noop(az, rmax(fnu, real(1.0)), alim)) simple = false;
+    }
+    if (r == IREG_WRSK) {
+        // second pre-test on K_fnu, K_fnu+1
+        if (!uoik_is_noop(az, rmax(fnu + real(1.0), real(2.0)), alim)) simple = false;
+    }
+    if (r == IREG_BUNI) simple = false;  // raised-order recurrences stay on the general path
+    return r;
+}
+
+SPB_FN Prep prepare(int fam, cplx z, real fnu, int kode) {
+    const real fnul = SPB_FNUL, alim = SPB_ALIM, tol = SPB_TOL;
+    Prep p;
+    p.w = z;
+    p.combine = CMB_GENERAL;
+    p.ireg = -1;
+    p.kreg = -1;
+    p.ierr = 0;
+    p.mr = 0;
+    // anything unusual (invalid input, NaN, huge or tiny arguments) goes to the driver
+    real az = cabs_(z);
+    if (!(fnu >= real(0.0)) || !(az == az) || !(az < real(32767.0)) || !(fnu < real(32767.0))) return p;
+    if (fam == FAM_J || fam == FAM_I) {
+        if (fam == FAM_J) {
+            p.w = cplx(z.im, -z.re);
+            if (z.im < real(0.0)) p.w = -p.w;
+        } else if (z.re < real(0.0)) {
+            p.w = -z;
+        }
+        bool simple;
+        if (az == real(0.0)) return p;
+        p.ireg = iregion_simple(p.w, fnu, az, simple);
+        if (simple) p.combine = CMB_I_ROT;
+        return p;
+    }
+    // K-type families
+    if (az < real(1.0e-290) || fnu > fnul) return p;
+    if (fnu > real(2.0)) {
+        if (!uoik_is_noop(az, rmax(fnu, real(1.0)), alim)) return p;
+    } else if (fnu > real(1.0) && !(az > tol)) {
+        return p;
+    }
+    bool left;
+    if (fam == FAM_K) {
+        left = z.re < real(0.0);
+        p.w = left ? -z : z;
+        p.mr = (z.im < real(0.0)) ? -1 : 1;
+        p.combine = left ? CMB_ACON : CMB_K_ROT;
+    } else if (fam == FAM_H1 || fam == FAM_H2) {
+        int m = (fam == FAM_H1) ? 1 : 2;
+        int mm = 3 - m - m;
+        real fmm = real(mm);
+        cplx zn(fmm * z.im, -fmm * z.re);
+        left = (zn.re < real(0.0)) || (zn.re == real(0.0) && zn.im < real(0.0) && m == 2);
+        p.w = left ? -zn : zn;
+        p.mr = -mm;
+        p.combine = left ? CMB_ACON : CMB_K_ROT;
+    } else {  // FAM_Y
+        // H1 uses zn1 = -i z, H2 uses zn2 = +i z = -zn1
+        cplx zn1(z.im, -z.re);
+        if (z.im == real(0.0) && z.re > real(0.0)) {
+            // both Hankel terms sit on the imaginary axis of the right half plane: conjugate points
+            p.w = zn1;
+            p.combine = CMB_Y_CONJ;
+            left = false;
+        } else {
+            bool left1 = zn1.re < real(0.0);  // H1 continued, H2 direct
+            p.w = left1 ? -zn1 : zn1;
+            p.mr = left1 ? -1 : 1;  // mr = -mm of the continued term
+            p.combine = CMB_Y_SHARED;
+            left = true;
+        }
+    }
+    p.kreg = kregion(p.w, fnu);
+    if (left) {
+        bool simple;
+        p.ireg = iregion_simple(p.w, fnu, az, simple);
+        if (!simple) {
+            p.combine = CMB_GENERAL;
+            p.ireg = -1;
+            p.kreg = -1;
+        }
+    }
+    return p;
+}
+
+// One region of the I pass.  Returns the AMOS nz (>= 0) or < 0 when the region
+// wants to hand over (-> general path).
+SPB_FN int ipass_region(int region, cplx w, real fnu, int kode, cplx &val) {
+    const real tol = SPB_TOL, elim = SPB_ELIM, alim = SPB_ALIM, rl = SPB_RL;
+    cplx y[1];
+    y[0] = cplx(0.0, 0.0);
+    int nw;
+    switch (region) {
+        case IREG_SERIES: nw = seri(w, fnu, kode, 1, y, tol, elim, alim); break;
+        case IREG_ASYI: nw = asyi(w, fnu, kode, 1, y, rl, tol, elim, alim); break;
+        case IREG_MLRI: nw = mlri(w, fnu, kode, 1, y, tol); break;
+        case IREG_WRSK: nw = wrsk(w, fnu, kode, 1, y, tol, elim, alim); break;
+        default: nw = -9; break;
+    }
+    val = y[0];
+    return nw;
+}
+
+SPB_FN int kpass_region(cplx w, real fnu, int kode, cplx &val) {
+    const real tol = SPB_TOL, elim = SPB_ELIM, alim = SPB_ALIM;
+    cplx y[1];
+    y[0] = cplx(0.0, 0.0);
+    int nw = bknu(w, fnu, kode, 1, y, tol, elim, alim);
+    val = y[0];
+    return nw;
+}
+
+// continuation K(w e^{i pi mr}) from (K(w), I(w)) for one member (acon with n = 1)
+SPB_FN cplx acon_combine(cplx w, real fnu, int kode, int mr, cplx kval, cplx ival, int &nz) {
+    const real tol = SPB_TOL, alim = SPB_ALIM, pi = SPB_PI;
+    nz = 0;
+    real sgn = (mr < 0) ? pi : -pi;
+    cplx csgn(0.0, sgn);
+    if (kode != 1) {
+        real yy = -w.im;
+        csgn = csgn * cplx(cos(yy), sin(yy));
+    }
+    int inu = (int)fnu;
+    real arg = (fnu - real(inu)) * sgn;
+    cplx cspn(cos(arg), sin(arg));
+    if (inu % 2 != 0) cspn = -cspn;
+    cplx c1 = kval, c2 = ival;
+    if (kode != 1) {
+        int iuf = 0;
+        real ascle = real(1.0e3) * SPB_D1MACH1 / tol;
+        nz += s1s2(w, c1, c2, ascle, alim, iuf);
+    }
+    return cspn * c1 + csgn * c2;
+}
+
+// rotation applied by the Hankel driver after K (or its continuation)
+SPB_FN cplx hankel_rotate(int m, real fnu, cplx y) {
+    const real tol = SPB_TOL, hpi = SPB_HPI;
+    int mm = 3 - m - m;
+    real fmm = real(mm);
+    real sgn = (-fmm < real(0.0)) ? -hpi : hpi;
+    int inu = (int)fnu;
+    int inuh = inu / 2;
+    int ir = inu - 2 * inuh;
+    real arg = (fnu - real(inu - ir)) * sgn;
+    real rhpi = real(1.0) / sgn;
+    cplx csgn(-rhpi * sin(arg), rhpi * cos(arg));
+    if (inuh % 2 == 1) csgn = -csgn;
+    real rtol = real(1.0) / tol;
+    real ascle = SPB_D1MACH1 * real(1.0e3) * rtol;
+    return rot_guard(y, csgn, rtol, ascle, tol);
+}
+
+SPB_FN cplx y_from_hankels(cplx z, int kode, cplx h1, cplx h2, int nz1, int nz2, int &nz) {
+    const real tol = SPB_TOL, elim = SPB_ELIM, hci = 0.5;
+    nz = nz1 < nz2 ? nz1 : nz2;
+    if (kode != 2) {
+        cplx d = h2 - h1;
+        return cplx(-d.im * hci, d.re * hci);
+    }
+    real exr = cos(z.re), exi = sin(z.re);
+    real ey = 0.0;
+    real tay = rabs(z.im + z.im);
+    if (tay < elim) ey = exp(-tay);
+    cplx c1, c2;
+    if (z.im < real(0.0)) {
+        c1 = cplx(exr, exi);
+        c2 = cplx(exr * ey, -exi * ey);
+    } else {
+        c1 = cplx(exr * ey, exi * ey);
+        c2 = cplx(exr, -exi);
+    }
+    nz = 0;
+    real rtol = real(1.0) / tol;
+    real ascle = SPB_D1MACH1 * rtol * real(1.0e3);
+    cplx a = rot_guard(h2, c2, rtol, ascle, tol);
+    cplx b = rot_guard(h1, c1, rtol, ascle, tol);
+    cplx st = a - b;
+    if (st.re == real(0.0) && st.im == real(0.0) && ey == real(0.0)) nz += 1;
+    return cplx(-st.im * hci, st.re * hci);
+}
+
+// Combine pass results into the family value.  inz/knz are the nz codes of the
+// passes (>= 0).  Sets ierr/nz like the per-point drivers.
+SPB_FN cplx finish(int fam, const Prep &p, cplx z, real fnu, int kode, cplx ival, int inz, cplx kval, int knz,
+                   int &ierr, int &nz) {
+    const real tol = SPB_TOL;
+    ierr = p.ierr;
+    nz = 0;
+    real rtol = real(1.0) / tol;
+    real ascle = SPB_D1MACH1 * rtol * real(1.0e3);
+    if (p.combine == CMB_I_ROT) {
+        nz = inz;
+        if (nz != 0) return cplx(0.0, 0.0);
+        if (fam == FAM_I) {
+            if (!(z.re < real(0.0))) return ival;
+            int inu = (int)fnu;
+            real arg = (fnu - real(inu)) * real(SPB_PI);
+            if (z.im < real(0.0)) arg = -arg;
+            cplx csgn(cos(arg), sin(arg));
+            if (inu % 2 != 0) csgn = -csgn;
+            return rot_guard(ival, csgn, rtol, ascle, tol);
+        }
+        int inu = (int)fnu;
+        int inuh = inu / 2;
+        int ir = inu - 2 * inuh;
+        real arg = (fnu - real(inu - ir)) * real(SPB_HPI);
+        cplx csgn(cos(arg), sin(arg));
+        if (inuh % 2 == 1) csgn = -csgn;
+        if (z.im < real(0.0)) csgn.im = -csgn.im;
+        return rot_guard(ival, csgn, rtol, ascle, tol);
+    }
+    if (fam == FAM_K) {
+        if (p.combine == CMB_K_ROT) {
+            nz = knz;
+            return kval;
+        }
+        return acon_combine(p.w, fnu, kode, p.mr, kval, ival, nz);
+    }
+    if (fam == FAM_H1 || fam == FAM_H2) {
+        int m = (fam == FAM_H1) ? 1 : 2;
+        cplx y;
+        if (p.combine == CMB_K_ROT) {
+            nz = knz;
+            y = kval;
+        } else {
+            y = acon_combine(p.w, fnu, kode, p.mr, kval, ival, nz);
+        }
+        return hankel_rotate(m, fnu, y);
+    }
+    // FAM_Y
+    cplx h1, h2;
+    int nz1 = 0, nz2 = 0;
+    if (p.combine == CMB_Y_CONJ) {
+        // H1 from K(w), w = (0,-x); H2 from K(conj w) = conj K(w)
+        nz1 = nz2 = knz;
+        h1 = hankel_rotate(1, fnu, kval);
+        h2 = hankel_rotate(2, fnu, conj(kval));
+    } else if (p.mr == -1) {
+        // H1 continued (mr = -mm = -1), H2 direct
+        cplx yc = acon_combine(p.w, fnu, kode, -1, kval, ival, nz1);
+        h1 = hankel_rotate(1, fnu, yc);
+        nz2 = knz;
+        h2 = hankel_rotate(2, fnu, kval);
+    } else {
+        nz1 = knz;
+        h1 = hankel_rotate(1, fnu, kval);
+        cplx yc = acon_combine(p.w, fnu, kode, 1, kval, ival, nz2);
+        h2 = hankel_rotate(2, fnu, yc);
+    }
+    return y_from_hankels(z, kode, h1, h2, nz1, nz2, nz);
+}
+
+// The general per-point path (same routine on CPU checker and GPU).
+SPB_FN cplx general_eval(int fam, cplx z, real fnu, int kode, int &ierr, int &nz) {
+    cplx cy[1];
+    cy[0] = cplx(0.0, 0.0);
+    if (!(fnu == fnu) || !(z.re == z.re) || !(z.im == z.im)) {
+        // NaN in, NaN out (flagged as an input error)
+        ierr = 1;
+        nz = 0;
+        real q = fnu + z.re + z.im;
+        return cplx(q, q);
+    }
+    switch (fam) {
+        case FAM_J: nz = besj(z, fnu, kode, 1, cy, ierr); break;
+        case FAM_Y: nz = besy(z, fnu, kode, cy, ierr); break;
+        case FAM_I: nz = besi(z, fnu, kode, 1, cy, ierr); break;
+        case FAM_K: nz = besk(z, fnu, kode, 1, cy, ierr); break;
+        case FAM_H1: nz = besh(z, fnu, kode, 1, 1, cy, ierr); break;
+        case FAM_H2: nz = besh(z, fnu, kode, 2, 1, cy, ierr); break;
+        default: ierr = 1; nz = 0; break;
+    }
+    return cy[0];
+}
+
+// Post-processing that reproduces the value conventions of scipy.special, the
+// reference's declared test oracle (/root/reference/tests/special.rs:10-16),
+// for orders >= 0: NaN on domain / overflow / no-result codes, signed infinity
+// where the overflow direction is known.  ierr / nz are left untouched.
+SPB_FN cplx apply_semantics(int fam, cplx z, real fnu, int kode, cplx val, int ierr, int nz) {
+    (void)nz;
+    if (ierr == 0 || ierr == 3) return val;
+    const real inf = real(1.0) / real(0.0);
+    const real nan = inf - inf;
+    cplx out(nan, nan);
+    if (!(fnu == fnu) || !(z.re == z.re) || !(z.im == z.im)) return out;
+    if (fam == FAM_Y && kode == 1 && z.re == real(0.0) && z.im == real(0.0) && fnu >= real(0.0))
+        return cplx(-inf, 0.0);
+    if (ierr != 2) return out;
+    const bool pos_real = z.re >= real(0.0) && z.im == real(0.0);
+    if (fam == FAM_K) return pos_real ? cplx(inf, 0.0) : out;
+    if (fam == FAM_Y) {
+        // the oracle reports -inf for yv and +inf for yve on the positive real axis
+        if (pos_real) return cplx(kode == 1 ? -inf : inf, 0.0);
+        return out;
+    }
+    if (kode != 1) return out;
+    if (fam == FAM_J) {
+        int ie, nzz;
+        cplx e = general_eval(FAM_J, z, fnu, 2, ie, nzz);
+        if (ie != 0 && ie != 3) return out;
+        return cplx(e.re * inf, e.im * inf);
+    }
+    if (fam == FAM_I) {
+        if (z.im == real(0.0) && (z.re >= real(0.0) || fnu == floor(fnu))) {
+            real half = fnu * real(0.5);
+            if (z.re < real(0.0) && half != floor(half)) return cplx(-inf, 0.0);
+            return cplx(inf, 0.0);
+        }
+        int ie, nzz;
+        cplx e = general_eval(FAM_I, z, fnu, 2, ie, nzz);
+        if (ie != 0 && ie != 3) return out;
+        return cplx(e.re * inf, e.im * inf);
+    }
+    return out;
+}
+
+// Whole pipeline for one point, in the order the GPU runs it (prepare -> I pass
+// -> K pass -> finish, general path on any hand-over).  `path` reports which
+// route was taken: 0 binned, 1 general from prepare, 2 general after a pass.
+SPB_FN cplx pipeline_eval(int fam, cplx z, real fnu, int kode, int &ierr, int &nz, int &path) {
+    Prep p = prepare(fam, z, fnu, kode);
+    path = 1;
+    if (p.combine == CMB_GENERAL) return general_eval(fam, z, fnu, kode, ierr, nz);
+    cplx ival(0.0, 0.0), kval(0.0, 0.0);
+    int inz = 0, knz = 0;
+    path = 2;
+    if (p.ireg >= 0) {
+        inz = ipass_region(p.ireg, p.w, fnu, kode, ival);
+        if (inz < 0) return general_eval(fam, z, fnu, kode, ierr, nz);
+    }
+    if (p.kreg >= 0) {
+        knz = kpass_region(p.w, fnu, kode, kval);
+        if (knz < 0) return general_eval(fam, z, fnu, kode, ierr, nz);
+        if (knz != 0 && (p.combine == CMB_ACON || p.combine == CMB_Y_SHARED))
+            return general_eval(fam, z, fnu, kode, ierr, nz);
+    }
+    path = 0;
+    return finish(fam, p, z, fnu, kode, ival, inz, kval, knz, ierr, nz);
+}
+
+}  // namespace spb

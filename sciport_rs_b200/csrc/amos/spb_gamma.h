@@ -1,0 +1,238 @@
+// spb_gamma.h — real gamma / log-gamma companions (memory-bound kernels).
+//   gamma_real : shift to x >= 12 by the recurrence, Stirling series there
+//                (Bernoulli coefficients CF from tools/gen_tables.py), reflection
+//                for x < 0; the power (x/e)^x is split to stay on scale up to 171.6.
+//   lgamma_real: ln|Gamma(x)|; Maclaurin series of lgamma(1+t) on (0.5, 2.5] so
+//                the zeros at 1 and 2 keep relative accuracy, Stirling above 12,
+//                recurrence in between, reflection for x < 0.
+// Value conventions (poles, overflow) follow scipy.special.gamma / gammaln, the
+// reference's test oracle (/root/reference/tests/special.rs:10-16).
+#pragma once
+#include "spb_common.h"
+#include "spb_gamln.h"
+
+namespace spb {
+
+// sum_{k>=1} B_2k / (2k(2k-1) x^(2k-1)),  x >= 12
+SPB_HD real stirling_tail(real x) {
+#include "spb_tables_gln.inc"
+    (void)GLN;
+    real r = real(1.0) / x;
+    real r2 = r * r;
+    real s = real(CF[8]);
+#pragma unroll
+    for (int k = 7; k >= 0; --k) s = s * r2 + real(CF[k]);
+    return s * r;
+}
+
+SPB_HD real sinpi_(real x) {
+#if defined(__CUDA_ARCH__)
+    return sinpi(x);
+#else
+    // exact argument reduction on the host
+    real r = fmod(x, real(2.0));
+    if (r > real(1.0)) r -= real(2.0);
+    if (r < real(-1.0)) r += real(2.0);
+    if (r > real(0.5)) r = real(1.0) - r;
+    if (r < real(-0.5)) r = real(-1.0) - r;
+    return sin(real(SPB_PI) * r);
+#endif
+}
+
+SPB_FN real gamma_pos(real x) {
+    // x > 0
+    const real sq2pi = 2.50662827463100050242;
+    if (x > real(171.6243769563027)) return real(1.0) / real(0.0);
+    real prod = 1.0;
+    real y = x;
+    while (y < real(12.0)) {
+        prod *= y;
+        y += real(1.0);
+    }
+    real w = pow(y, real(0.5) * y - real(0.25));
+    real g = sq2pi * exp(stirling_tail(y));
+    g = (w * exp(-y)) * w * g;
+    return g / prod;
+}
+
+SPB_FN real gamma_real(real x) {
+    const real inf = real(1.0) / real(0.0);
+    if (!(x == x)) return x;
+    if (x == inf) return inf;
+    if (x == -inf) return inf - inf;
+    if (x == real(0.0)) return real(1.0) / x;  // signed infinity
+    if (x > real(0.0)) return gamma_pos(x);
+    if (x == floor(x)) return inf - inf;  // pole at a negative integer
+    // reflection: Gamma(x) = pi / (sin(pi x) Gamma(1 - x))
+    real s = sinpi_(x);
+    real ax = -x;
+    if (ax > real(170.6243769563027)) {
+        // |Gamma| underflows; keep the sign like the oracle
+        real p = floor(ax);
+        bool odd = fmod(p, real(2.0)) != real(0.0);
+        return odd ? real(0.0) : -real(0.0);
+    }
+    real g = gamma_pos(real(1.0) - x);
+    return real(SPB_PI) / (s * g);
+}
+
+SPB_FN real lgamma_pos(real x) {
+#include "spb_tables_gamma.inc"
+    const real euler1 = 0.42278433509846713939;  // 1 - Euler's constant
+    const real hl2pi = 0.91893853320467274178;   // ln(2 pi)/2
+    if (x >= real(12.0)) {
+        if (x > real(1.0e305)) return real(1.0) / real(0.0);
+        real lx = log(x);
+        return (x - real(0.5)) * lx - x + hl2pi + (x < real(1.0e17) ? stirling_tail(x) : real(0.0));
+    }
+    // (0, 12): lgamma(1+t), |t| <= 1/2, plus the log of the recurrence product
+    real t, extra;
+    if (x > real(2.5)) {
+        real m = floor(x + real(0.5));  // x = m + t
+        t = x - m;
+        real prod = real(1.0) + t;
+        for (real j = 2.0; j < m; j += real(1.0)) prod *= (t + j);
+        extra = log(prod);  // lgamma(m+t) = lgamma(1+t) + ln((1+t)(2+t)...(m-1+t))
+    } else if (x > real(1.5)) {
+        t = x - real(2.0);
+        extra = log1p(t);  // lgamma(2+t) = lgamma(1+t) + ln(1+t)
+    } else if (x > real(0.5)) {
+        t = x - real(1.0);
+        extra = 0.0;
+    } else {
+        t = x;
+        extra = -log(x);  // lgamma(t) = lgamma(1+t) - ln t
+    }
+    real s = real(LG1[31]);
+#pragma unroll
+    for (int k = 30; k >= 0; --k) s = s * t + real(LG1[k]);
+    return extra + (t * euler1 - log1p(t)) + s * t * t;
+}
+
+SPB_FN real lgamma_real(real x) {
+    const real inf = real(1.0) / real(0.0);
+    if (!(x == x)) return x;
+    if (x == inf) return inf;
+    if (x == -inf) return -inf;
+    if (x == real(0.0)) return inf;
+    if (x > real(0.0)) return lgamma_pos(x);
+    if (x == floor(x)) return inf;
+    // ln|Gamma(x)| = ln(pi / |sin(pi x)|) - lgamma(1 - x)
+    real s = rabs(sinpi_(x));
+    return log(real(SPB_PI) / s) - lgamma_pos(real(1.0) - x);
+}
+
+SPB_HD real sinc_real(real x) {
+    // special::sinc, /root/reference/src/special/trig.rs:4-13: sin(pi a)/(pi a), 1 at a == 0
+    if (x == real(0.0)) return real(1.0);
+    real y = x * real(SPB_PI);
+    return sin(y) / y;
+}
+
+}  // namespace spb
+
+// ---------------------------------------------------------------------------
+// Complex loggamma / gamma.  Region logic after Hare (1997), the algorithm the
+// oracle's loggamma documents: Stirling series for Re z > 7 or |Im z| > 7,
+// Taylor series around 1 and 2, reflection for Re z < 0.1, otherwise the upward
+// recurrence with branch counting.  gamma(z) = exp(loggamma(z)).
+namespace spb {
+
+SPB_HD cplx csinpi_(cplx z) {
+    real x = z.re, piy = real(SPB_PI) * z.im;
+    real sx, cx;
+#if defined(__CUDA_ARCH__)
+    sincospi(x, &sx, &cx);
+#else
+    sx = sinpi_(x);
+    cx = sinpi_(x + real(0.5));
+#endif
+    return cplx(sx * cosh(piy), cx * sinh(piy));
+}
+
+SPB_FN cplx clgam_stirling(cplx z) {
+#include "spb_tables_gln.inc"
+    (void)GLN;
+    const real hl2pi = 0.91893853320467274178;
+    cplx rz = crecip(z);
+    cplx rzz = rz * rz;
+    cplx s(real(CF[7]), 0.0);
+#pragma unroll
+    for (int k = 6; k >= 0; --k) s = s * rzz + real(CF[k]);
+    cplx lz = clog_(z);
+    return (z - real(0.5)) * lz - z + hl2pi + s * rz;
+}
+
+SPB_FN cplx clgam_taylor(cplx t) {
+#include "spb_tables_gamma.inc"
+    (void)LG1;
+    const real euler = 0.57721566490153286061;
+    cplx s(real(LGZ[22]), 0.0);
+#pragma unroll
+    for (int k = 21; k >= 0; --k) s = s * t + real(LGZ[k]);
+    return (s * t - euler) * t;
+}
+
+SPB_FN cplx clgam_recurrence(cplx z) {
+    // Im z >= 0 here
+    int signflips = 0, sb = 0;
+    cplx shiftprod = z;
+    z.re += real(1.0);
+    while (z.re <= real(7.0)) {
+        shiftprod = shiftprod * z;
+        int nsb = shiftprod.im < real(0.0) ? 1 : 0;
+        if (nsb != 0 && sb == 0) signflips += 1;
+        sb = nsb;
+        z.re += real(1.0);
+    }
+    cplx r = clgam_stirling(z) - clog_(shiftprod);
+    r.im -= real(signflips) * real(2.0 * SPB_PI);
+    return r;
+}
+
+SPB_FN cplx cloggamma(cplx z) {
+    const real inf = real(1.0) / real(0.0);
+    const real nan = inf - inf;
+    const real logpi = 1.1447298858494001741434262;
+    if (!(z.re == z.re) || !(z.im == z.im)) return cplx(nan, nan);
+    if (z.re <= real(0.0) && z.im == real(0.0) && z.re == floor(z.re)) return cplx(nan, nan);
+    if (z.re > real(7.0) || rabs(z.im) > real(7.0)) return clgam_stirling(z);
+    cplx t1 = z - real(1.0);
+    if (cabs_(t1) <= real(0.2)) return clgam_taylor(t1);
+    cplx t2 = z - real(2.0);
+    if (cabs_(t2) <= real(0.2)) return clog_(t1) + clgam_taylor(t2);
+    if (z.re < real(0.1)) {
+        // reflection: loggamma(z) = ln(pi) - ln(sin(pi z)) - loggamma(1 - z) with the branch tracked
+        real tmp = floor(real(0.5) * z.re + real(0.25)) * real(2.0 * SPB_PI);
+        if (z.im < real(0.0) || (z.im == real(0.0) && signbit(z.im))) tmp = -tmp;
+        cplx one_minus(real(1.0) - z.re, -z.im);
+        cplx rec;
+        // 1 - z has Re > 0.9: Stirling / Taylor / recurrence, no second reflection
+        if (one_minus.re > real(7.0) || rabs(one_minus.im) > real(7.0)) {
+            rec = clgam_stirling(one_minus);
+        } else {
+            cplx u1 = one_minus - real(1.0), u2 = one_minus - real(2.0);
+            if (cabs_(u1) <= real(0.2))
+                rec = clgam_taylor(u1);
+            else if (cabs_(u2) <= real(0.2))
+                rec = clog_(u1) + clgam_taylor(u2);
+            else if (!(one_minus.im < real(0.0)))
+                rec = clgam_recurrence(one_minus);
+            else
+                rec = conj(clgam_recurrence(conj(one_minus)));
+        }
+        cplx ls = clog_(csinpi_(z));
+        return cplx(logpi - ls.re - rec.re, tmp - ls.im - rec.im);
+    }
+    if (!(z.im < real(0.0))) return clgam_recurrence(z);
+    return conj(clgam_recurrence(conj(z)));
+}
+
+SPB_FN cplx cgamma(cplx z) {
+    const real inf = real(1.0) / real(0.0);
+    const real nan = inf - inf;
+    if (z.re <= real(0.0) && z.im == real(0.0) && z.re == floor(z.re)) return cplx(nan, nan);
+    return cexp_(cloggamma(z));
+}
+
+}  // namespace spb

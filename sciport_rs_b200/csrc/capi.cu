@@ -1,0 +1,705 @@
+// capi.cu — the extern "C" launcher layer declared in include/sciport_b200.h.
+//
+// Host side of the drop-in boundary: argument checking, per-device scratch
+// cache, chunking, the host-buffer pipeline (pinned async copies, two streams
+// per device, one host thread per device) and the device-pointer fast path
+// used when the caller already keeps the batch in HBM.  No CPU fallback: every
+// compute entry point fails with SPB_E_NO_DEVICE when no CUDA device exists.
+#include "../../include/sciport_b200.h"
+#include "spb_kernels.cuh"
+
+
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+using namespace spbk;
+
+namespace {
+
+thread_local std::string g_err;
+thread_local double g_last_ms = 0.0;
+thread_local int g_last_launches = 0;
+
+int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CK(call)                                                                                        \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess)                                                                          \
+            return fail(SPB_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                 \
+    } while (0)
+
+constexpr long long CHUNK_DEVICE = 1ll << 24;  // points per pipeline pass when data is resident
+constexpr long long CHUNK_HOST = 1ll << 22;    // points per staged chunk for host buffers
+
+struct ScratchSet {
+    Scratch s{};
+    long long cap = 0;
+    void *arena = nullptr;
+};
+
+struct StageSet {  // device staging for host-pointer mode
+    double2 *z = nullptr;
+    double *x = nullptr;
+    double *v = nullptr;
+    double2 *out = nullptr;
+    int *ierr = nullptr;
+    int *nz = nullptr;
+    long long cap = 0;
+    long long cap_out = 0;
+};
+
+struct DeviceCtx {
+    int dev = -1;
+    int sms = 148;
+    std::mutex mu;
+    ScratchSet scratch[2];
+    StageSet stage[2];
+    cudaStream_t streams[2] = {nullptr, nullptr};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    unsigned long long *d_packed = nullptr;
+};
+
+std::mutex g_ctx_mu;
+std::vector<DeviceCtx *> g_ctx;
+
+int device_count() {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+DeviceCtx *get_ctx(int dev) {
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    if ((int)g_ctx.size() <= dev) g_ctx.resize(dev + 1, nullptr);
+    if (!g_ctx[dev]) {
+        DeviceCtx *c = new DeviceCtx();
+        c->dev = dev;
+        cudaSetDevice(dev);
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, dev) == cudaSuccess) c->sms = p.multiProcessorCount;
+        cudaStreamCreateWithFlags(&c->streams[0], cudaStreamNonBlocking);
+        cudaStreamCreateWithFlags(&c->streams[1], cudaStreamNonBlocking);
+        cudaEventCreate(&c->ev0);
+        cudaEventCreate(&c->ev1);
+        cudaMalloc(&c->d_packed, sizeof(unsigned long long));
+        g_ctx[dev] = c;
+    }
+    return g_ctx[dev];
+}
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+int ensure_scratch(ScratchSet &ss, long long n) {
+    if (n <= ss.cap) {
+        ss.s.nblocks = (int)((n + TILE - 1) / TILE);
+        return SPB_OK;
+    }
+    if (ss.arena) cudaFree(ss.arena);
+    ss.arena = nullptr;
+    ss.cap = 0;
+    long long cap = std::max<long long>(n, 1 << 16);
+    int nblocks_cap = (int)((cap + TILE - 1) / TILE);
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        size_t o = off;
+        off = align_up(off + bytes, 256);
+        return o;
+    };
+    size_t o_cls = take(cap), o_pi = take(cap * 4), o_pk = take(cap * 4), o_gl = take(cap * 4),
+           o_it = take(cap * 16), o_ic = take(cap), o_bc = take((size_t)NBINS * nblocks_cap * 4), o_bins = take(32 * 4);
+    char *base = nullptr;
+    if (cudaMalloc(&base, off) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(SPB_E_ALLOC, "cudaMalloc of pipeline scratch failed");
+    }
+    ss.arena = base;
+    ss.cap = cap;
+    ss.s.cls = (unsigned char *)(base + o_cls);
+    ss.s.perm_i = (unsigned int *)(base + o_pi);
+    ss.s.perm_k = (unsigned int *)(base + o_pk);
+    ss.s.glist = (unsigned int *)(base + o_gl);
+    ss.s.itemp = (double2 *)(base + o_it);
+    ss.s.icode = (signed char *)(base + o_ic);
+    ss.s.blockcnt = (unsigned int *)(base + o_bc);
+    ss.s.bins = (unsigned int *)(base + o_bins);
+    ss.s.nblocks = (int)((n + TILE - 1) / TILE);
+    return SPB_OK;
+}
+
+// per-kernel profile of the last call made with SPB_PROFILE (events between launches)
+struct ProfRec {
+    int kernel;  // spb_kernel_id
+    double ms;
+    long long points;
+};
+thread_local std::vector<ProfRec> g_prof;
+
+struct Prof {
+    bool on = false;
+    std::vector<cudaEvent_t> ev;
+    std::vector<int> ids;
+    void mark(int id, cudaStream_t st) {
+        if (!on) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        ev.push_back(e);
+        ids.push_back(id);
+    }
+};
+
+// enqueue the whole pipeline for one chunk; returns number of kernel launches
+int enqueue_chunk(const DevJob &job, ScratchSet &ss, int sms, int flags, cudaStream_t st, Prof *pf = nullptr) {
+    Prof dummy;
+    Prof &p = pf ? *pf : dummy;
+    if (flags & SPB_PATH_MONOLITHIC) {
+        p.mark(SPB_K_MONOLITHIC, st);
+        launch_monolithic(job, st);
+        p.mark(-1, st);
+        return 1;
+    }
+    int launches = 0;
+    p.mark(SPB_K_CLASSIFY, st);
+    launch_classify(job, ss.s, st);
+    p.mark(SPB_K_SCAN_SCATTER, st);
+    launch_scan_scatter(job, ss.s, st);
+    launches += 3;
+    const bool ktype = !(job.fam == SPB_FN_J || job.fam == SPB_FN_I);
+    for (int r = 0; r < 4; ++r) {
+        p.mark(SPB_K_IPASS_SERIES + r, st);
+        launch_ipass(job, ss.s, r, sms, st);
+        ++launches;
+    }
+    if (ktype) {
+        p.mark(SPB_K_KPASS, st);
+        launch_kpass(job, ss.s, sms, st);
+        ++launches;
+    }
+    p.mark(SPB_K_GENERAL, st);
+    launch_general(job, ss.s, sms, st);
+    p.mark(-1, st);
+    ++launches;
+    return launches;
+}
+
+// turn the recorded events into (kernel, ms, points) records; call after the stream is idle
+void collect_profile(Prof &p, const ScratchSet &ss, long long n) {
+    if (!p.on) return;
+    unsigned int bins[17] = {0};
+    cudaMemcpy(bins, ss.s.bins, sizeof(bins), cudaMemcpyDeviceToHost);
+    for (size_t i = 0; i + 1 < p.ev.size(); ++i) {
+        if (p.ids[i] < 0) continue;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, p.ev[i], p.ev[i + 1]);
+        long long pts = n;
+        int id = p.ids[i];
+        if (id >= SPB_K_IPASS_SERIES && id <= SPB_K_IPASS_WRSK) {
+            int r = id - SPB_K_IPASS_SERIES;
+            pts = (long long)bins[r + 1] - bins[r];
+        } else if (id == SPB_K_KPASS) {
+            pts = (long long)bins[BIN_GENERAL] - bins[4];
+        } else if (id == SPB_K_GENERAL) {
+            pts = bins[GLIST_LEN_SLOT];
+        }
+        g_prof.push_back({id, ms, pts});
+    }
+    for (auto e : p.ev) cudaEventDestroy(e);
+    p.ev.clear();
+    p.ids.clear();
+}
+
+int check_exec(const spb_exec *ex, std::vector<int> &devs, bool &device_ptrs, cudaStream_t &stream, int &flags) {
+    int ndev = device_count();
+    if (ndev <= 0) return fail(SPB_E_NO_DEVICE, "no CUDA device visible: libsciport_b200 has no CPU path");
+    device_ptrs = ex ? ex->device_ptrs != 0 : false;
+    stream = ex ? (cudaStream_t)ex->stream : nullptr;
+    flags = ex ? ex->flags : 0;
+    devs.clear();
+    int want = ex ? std::max(ex->n_devices, 1) : 1;
+    if (ex && ex->devices) {
+        for (int i = 0; i < want; ++i) devs.push_back(ex->devices[i]);
+    } else if (want == 1) {
+        int cur = 0;
+        cudaGetDevice(&cur);
+        devs.push_back(cur);
+    } else {
+        for (int i = 0; i < want; ++i) devs.push_back(i);
+    }
+    for (int d : devs)
+        if (d < 0 || d >= ndev) return fail(SPB_E_ARG, "device ordinal out of range");
+    if (device_ptrs && devs.size() != 1) return fail(SPB_E_ARG, "device pointers require exactly one device");
+    return SPB_OK;
+}
+
+struct BesselArgs {
+    int fn, kode;
+    const double *v;
+    long long v_stride;
+    const double2 *z;
+    const double *x;
+    double2 *out;
+    int *ierr;
+    int *nz;
+    long long n;
+    int flags;
+};
+
+// data resident on the device: chunk over the batch on the caller's stream
+int run_device(DeviceCtx *c, const BesselArgs &a, cudaStream_t st, double *ms_out, int *launches_out) {
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->dev));
+    int launches = 0;
+    Prof prof;
+    prof.on = (a.flags & SPB_PROFILE) != 0;
+    if (prof.on) g_prof.clear();
+    CK(cudaEventRecord(c->ev0, st));
+    for (long long off = 0; off < a.n; off += CHUNK_DEVICE) {
+        long long m = std::min(CHUNK_DEVICE, a.n - off);
+        int rc = ensure_scratch(c->scratch[0], m);
+        if (rc != SPB_OK) return rc;
+        DevJob job{};
+        job.fam = a.fn;
+        job.kode = a.kode;
+        job.sem = (a.flags & SPB_SEM_SCIPY) ? 1 : 0;
+        job.v = a.v + off * a.v_stride;
+        job.v_stride = a.v_stride;
+        job.z = a.z ? a.z + off : nullptr;
+        job.x = a.x ? a.x + off : nullptr;
+        job.out = a.out + off;
+        job.ierr = a.ierr ? a.ierr + off : nullptr;
+        job.nz = a.nz ? a.nz + off : nullptr;
+        job.n = m;
+        launches += enqueue_chunk(job, c->scratch[0], c->sms, a.flags, st, &prof);
+        if (prof.on) {
+            // profiling serialises the chunks so that the bin counters can be read back per chunk
+            CK(cudaStreamSynchronize(st));
+            if (!(a.flags & SPB_PATH_MONOLITHIC)) collect_profile(prof, c->scratch[0], m);
+            else {
+                unsigned int z17[1];
+                (void)z17;
+                for (size_t i = 0; i + 1 < prof.ev.size(); ++i) {
+                    float ms = 0.f;
+                    cudaEventElapsedTime(&ms, prof.ev[i], prof.ev[i + 1]);
+                    if (prof.ids[i] >= 0) g_prof.push_back({prof.ids[i], ms, m});
+                }
+                for (auto e : prof.ev) cudaEventDestroy(e);
+                prof.ev.clear();
+                prof.ids.clear();
+            }
+        }
+    }
+    CK(cudaEventRecord(c->ev1, st));
+    CK(cudaGetLastError());
+    CK(cudaEventSynchronize(c->ev1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    if (ms_out) *ms_out = ms;
+    if (launches_out) *launches_out = launches;
+    return SPB_OK;
+}
+
+int ensure_stage(StageSet &s, long long n, bool real_in, bool per_elem_v, bool want_ierr, bool want_nz) {
+    if (n > s.cap) {
+        cudaFree(s.z);
+        cudaFree(s.x);
+        cudaFree(s.v);
+        cudaFree(s.out);
+        cudaFree(s.ierr);
+        cudaFree(s.nz);
+        s = StageSet();
+        if (cudaMalloc(&s.z, n * 16) != cudaSuccess || cudaMalloc(&s.x, n * 8) != cudaSuccess ||
+            cudaMalloc(&s.v, n * 8) != cudaSuccess || cudaMalloc(&s.out, n * 16) != cudaSuccess ||
+            cudaMalloc(&s.ierr, n * 4) != cudaSuccess || cudaMalloc(&s.nz, n * 4) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(SPB_E_ALLOC, "cudaMalloc of staging buffers failed");
+        }
+        s.cap = n;
+    }
+    (void)real_in;
+    (void)per_elem_v;
+    (void)want_ierr;
+    (void)want_nz;
+    return SPB_OK;
+}
+
+// Pin a caller buffer for the duration of the call unless it already is.
+struct Pin {
+    void *p = nullptr;
+    bool registered = false;
+    void pin(const void *ptr, size_t bytes) {
+        if (!ptr || bytes == 0) return;
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, ptr) == cudaSuccess && at.type != cudaMemoryTypeUnregistered) return;
+        cudaGetLastError();
+        if (cudaHostRegister(const_cast<void *>(ptr), bytes, cudaHostRegisterPortable) == cudaSuccess) {
+            p = const_cast<void *>(ptr);
+            registered = true;
+        } else {
+            cudaGetLastError();  // pageable copies still work, just slower
+        }
+    }
+    ~Pin() {
+        if (registered) cudaHostUnregister(p);
+    }
+};
+
+// host buffers, one device: staged chunks, two streams, copies overlapped with compute
+int run_host_slice(DeviceCtx *c, const BesselArgs &a, double *ms_out, int *launches_out) {
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->dev));
+    Pin pz, px, pv, po, pe, pn;
+    if (a.z) pz.pin(a.z, a.n * 16);
+    if (a.x) px.pin(a.x, a.n * 8);
+    if (a.v_stride != 0) pv.pin(a.v, ((a.n - 1) * a.v_stride + 1) * 8);
+    po.pin(a.out, a.n * 16);
+    if (a.ierr) pe.pin(a.ierr, a.n * 4);
+    if (a.nz) pn.pin(a.nz, a.n * 4);
+    int launches = 0;
+    int k = 0;
+    double v0 = a.v[0];
+    for (long long off = 0; off < a.n; off += CHUNK_HOST, ++k) {
+        long long m = std::min(CHUNK_HOST, a.n - off);
+        int b = k & 1;
+        cudaStream_t st = c->streams[b];
+        int rc = ensure_stage(c->stage[b], std::min(CHUNK_HOST, a.n), a.x != nullptr, a.v_stride != 0, a.ierr, a.nz);
+        if (rc != SPB_OK) return rc;
+        rc = ensure_scratch(c->scratch[b], m);
+        if (rc != SPB_OK) return rc;
+        StageSet &s = c->stage[b];
+        if (a.z) CK(cudaMemcpyAsync(s.z, a.z + off, m * 16, cudaMemcpyHostToDevice, st));
+        if (a.x) CK(cudaMemcpyAsync(s.x, a.x + off, m * 8, cudaMemcpyHostToDevice, st));
+        if (a.v_stride == 1) {
+            CK(cudaMemcpyAsync(s.v, a.v + off, m * 8, cudaMemcpyHostToDevice, st));
+        } else if (a.v_stride == 0) {
+            CK(cudaMemcpyAsync(s.v, &v0, 8, cudaMemcpyHostToDevice, st));
+        } else {
+            CK(cudaMemcpy2DAsync(s.v, 8, a.v + off * a.v_stride, a.v_stride * 8, 8, m, cudaMemcpyHostToDevice, st));
+        }
+        DevJob job{};
+        job.fam = a.fn;
+        job.kode = a.kode;
+        job.sem = (a.flags & SPB_SEM_SCIPY) ? 1 : 0;
+        job.v = s.v;
+        job.v_stride = a.v_stride == 0 ? 0 : 1;
+        job.z = a.z ? s.z : nullptr;
+        job.x = a.x ? s.x : nullptr;
+        job.out = s.out;
+        job.ierr = a.ierr ? s.ierr : nullptr;
+        job.nz = a.nz ? s.nz : nullptr;
+        job.n = m;
+        launches += enqueue_chunk(job, c->scratch[b], c->sms, a.flags, st);
+        CK(cudaMemcpyAsync(a.out + off, s.out, m * 16, cudaMemcpyDeviceToHost, st));
+        if (a.ierr) CK(cudaMemcpyAsync(a.ierr + off, s.ierr, m * 4, cudaMemcpyDeviceToHost, st));
+        if (a.nz) CK(cudaMemcpyAsync(a.nz + off, s.nz, m * 4, cudaMemcpyDeviceToHost, st));
+        // the staging set of this stream is reused two chunks later: stream order protects it
+    }
+    CK(cudaStreamSynchronize(c->streams[0]));
+    CK(cudaStreamSynchronize(c->streams[1]));
+    CK(cudaGetLastError());
+    if (ms_out) *ms_out = 0.0;
+    if (launches_out) *launches_out = launches;
+    return SPB_OK;
+}
+
+int bessel_impl(int fn, int kode, const double *v, int64_t v_stride, const spb_c128 *z, const double *x,
+                spb_c128 *out, int32_t *ierr, int32_t *nz, int64_t n, int n_orders, const spb_exec *ex) {
+    if (fn < SPB_FN_J || fn > SPB_FN_H2) return fail(SPB_E_ARG, "unknown function selector");
+    if (kode != 1 && kode != 2) return fail(SPB_E_ARG, "kode must be 1 or 2");
+    if (n < 0 || v_stride < 0) return fail(SPB_E_ARG, "negative n or v_stride");
+    if (n_orders != 1) return fail(SPB_E_ARG, "n_orders != 1: use spb_bessel_seq");
+    if (n > 0 && (!v || (!z && !x) || !out)) return fail(SPB_E_ARG, "null buffer");
+    std::vector<int> devs;
+    bool dptr;
+    cudaStream_t st;
+    int flags;
+    int rc = check_exec(ex, devs, dptr, st, flags);
+    if (rc != SPB_OK) return rc;
+    g_last_ms = 0.0;
+    g_last_launches = 0;
+    if (n == 0) return SPB_OK;
+    BesselArgs a{fn, kode, v, v_stride, (const double2 *)z, x, (double2 *)out, ierr, nz, n, flags};
+    if (dptr) return run_device(get_ctx(devs[0]), a, st, &g_last_ms, &g_last_launches);
+    const int G = (int)devs.size();
+    if (G == 1) return run_host_slice(get_ctx(devs[0]), a, &g_last_ms, &g_last_launches);
+    // contiguous slice i of G per device, one host thread per device (no collective: shards never talk)
+    std::vector<int> rcs(G, SPB_OK), ls(G, 0);
+    std::vector<std::string> errs(G);
+    std::vector<std::thread> th;
+    for (int g = 0; g < G; ++g) {
+        th.emplace_back([&, g] {
+            long long lo = n * g / G, hi = n * (g + 1) / G;
+            BesselArgs s = a;
+            s.v = a.v + lo * a.v_stride;
+            s.z = a.z ? a.z + lo : nullptr;
+            s.x = a.x ? a.x + lo : nullptr;
+            s.out = a.out + lo;
+            s.ierr = a.ierr ? a.ierr + lo : nullptr;
+            s.nz = a.nz ? a.nz + lo : nullptr;
+            s.n = hi - lo;
+            if (s.n > 0) rcs[g] = run_host_slice(get_ctx(devs[g]), s, nullptr, &ls[g]);
+            errs[g] = g_err;
+        });
+    }
+    for (auto &t : th) t.join();
+    for (int g = 0; g < G; ++g) {
+        g_last_launches += ls[g];
+        if (rcs[g] != SPB_OK) return fail(rcs[g], errs[g]);
+    }
+    return SPB_OK;
+}
+
+// generic "map over a batch" helper for the simple kernels (device or host pointers, one device)
+template <class F>
+int run_map(const spb_exec *ex, long long n, size_t in_bytes_per, size_t out_bytes_per, const void *in, void *out,
+            F launch) {
+    std::vector<int> devs;
+    bool dptr;
+    cudaStream_t st;
+    int flags;
+    int rc = check_exec(ex, devs, dptr, st, flags);
+    if (rc != SPB_OK) return rc;
+    if (n < 0) return fail(SPB_E_ARG, "negative n");
+    if (n == 0) return SPB_OK;
+    if (!in || !out) return fail(SPB_E_ARG, "null buffer");
+    DeviceCtx *c = get_ctx(devs[0]);
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->dev));
+    g_last_launches = 1;
+    if (dptr) {
+        CK(cudaEventRecord(c->ev0, st));
+        launch(in, out, n, st);
+        CK(cudaEventRecord(c->ev1, st));
+        CK(cudaGetLastError());
+        CK(cudaEventSynchronize(c->ev1));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        g_last_ms = ms;
+        return SPB_OK;
+    }
+    void *din = nullptr, *dout = nullptr;
+    if (cudaMalloc(&din, n * in_bytes_per) != cudaSuccess || cudaMalloc(&dout, n * out_bytes_per) != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(din);
+        return fail(SPB_E_ALLOC, "cudaMalloc failed");
+    }
+    cudaStream_t s0 = c->streams[0];
+    cudaError_t e = cudaMemcpyAsync(din, in, n * in_bytes_per, cudaMemcpyHostToDevice, s0);
+    if (e == cudaSuccess) {
+        launch(din, dout, n, s0);
+        e = cudaMemcpyAsync(out, dout, n * out_bytes_per, cudaMemcpyDeviceToHost, s0);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s0);
+    cudaFree(din);
+    cudaFree(dout);
+    if (e != cudaSuccess) return fail(SPB_E_CUDA, cudaGetErrorString(e));
+    return SPB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int spb_bessel(int fn, int kode, const double *v, int64_t v_stride, const spb_c128 *z, spb_c128 *out, int32_t *ierr,
+               int32_t *nz, int64_t n, int n_orders, const spb_exec *ex) {
+    return bessel_impl(fn, kode, v, v_stride, z, nullptr, out, ierr, nz, n, n_orders, ex);
+}
+
+int spb_bessel_real(int fn, int kode, const double *v, int64_t v_stride, const double *x, spb_c128 *out,
+                    int32_t *ierr, int32_t *nz, int64_t n, int n_orders, const spb_exec *ex) {
+    return bessel_impl(fn, kode, v, v_stride, nullptr, x, out, ierr, nz, n, n_orders, ex);
+}
+
+int spb_airy(int which, int kode, const spb_c128 *z, spb_c128 *out, int32_t *ierr, int32_t *nz, int64_t n,
+             const spb_exec *ex) {
+    if (which < 0 || which > 3) return fail(SPB_E_ARG, "which must be 0..3");
+    if (kode != 1 && kode != 2) return fail(SPB_E_ARG, "kode must be 1 or 2");
+    std::vector<int> devs;
+    bool dptr;
+    cudaStream_t st;
+    int flags;
+    int rc = check_exec(ex, devs, dptr, st, flags);
+    if (rc != SPB_OK) return rc;
+    if (n < 0) return fail(SPB_E_ARG, "negative n");
+    if (n == 0) return SPB_OK;
+    if (!z || !out) return fail(SPB_E_ARG, "null buffer");
+    DeviceCtx *c = get_ctx(devs[0]);
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->dev));
+    int sem = (flags & SPB_SEM_SCIPY) ? 1 : 0;
+    g_last_launches = 1;
+    if (dptr) {
+        CK(cudaEventRecord(c->ev0, st));
+        launch_airy(which, kode, sem, (const double2 *)z, (double2 *)out, ierr, nz, n, st);
+        CK(cudaEventRecord(c->ev1, st));
+        CK(cudaGetLastError());
+        CK(cudaEventSynchronize(c->ev1));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        g_last_ms = ms;
+        return SPB_OK;
+    }
+    int launches = 0, k = 0;
+    for (long long off = 0; off < n; off += CHUNK_HOST, ++k) {
+        long long m = std::min<long long>(CHUNK_HOST, n - off);
+        int b = k & 1;
+        cudaStream_t s0 = c->streams[b];
+        rc = ensure_stage(c->stage[b], std::min<long long>(CHUNK_HOST, n), false, false, true, true);
+        if (rc != SPB_OK) return rc;
+        StageSet &s = c->stage[b];
+        CK(cudaMemcpyAsync(s.z, z + off, m * 16, cudaMemcpyHostToDevice, s0));
+        launch_airy(which, kode, sem, s.z, s.out, ierr ? s.ierr : nullptr, nz ? s.nz : nullptr, m, s0);
+        ++launches;
+        CK(cudaMemcpyAsync(out + off, s.out, m * 16, cudaMemcpyDeviceToHost, s0));
+        if (ierr) CK(cudaMemcpyAsync(ierr + off, s.ierr, m * 4, cudaMemcpyDeviceToHost, s0));
+        if (nz) CK(cudaMemcpyAsync(nz + off, s.nz, m * 4, cudaMemcpyDeviceToHost, s0));
+    }
+    CK(cudaStreamSynchronize(c->streams[0]));
+    CK(cudaStreamSynchronize(c->streams[1]));
+    g_last_launches = launches;
+    return SPB_OK;
+}
+
+int spb_gamma(const double *x, double *out, int64_t n, const spb_exec *ex) {
+    return run_map(ex, n, 8, 8, x, out, [](const void *i, void *o, long long m, cudaStream_t st) {
+        launch_gamma(0, (const double *)i, (double *)o, m, st);
+    });
+}
+int spb_lgamma(const double *x, double *out, int64_t n, const spb_exec *ex) {
+    return run_map(ex, n, 8, 8, x, out, [](const void *i, void *o, long long m, cudaStream_t st) {
+        launch_gamma(1, (const double *)i, (double *)o, m, st);
+    });
+}
+int spb_cgamma(const spb_c128 *z, spb_c128 *out, int64_t n, const spb_exec *ex) {
+    return run_map(ex, n, 16, 16, z, out, [](const void *i, void *o, long long m, cudaStream_t st) {
+        launch_cgamma(0, (const double2 *)i, (double2 *)o, m, st);
+    });
+}
+int spb_clgamma(const spb_c128 *z, spb_c128 *out, int64_t n, const spb_exec *ex) {
+    return run_map(ex, n, 16, 16, z, out, [](const void *i, void *o, long long m, cudaStream_t st) {
+        launch_cgamma(1, (const double2 *)i, (double2 *)o, m, st);
+    });
+}
+int spb_sinc(const double *x, double *out, int64_t n, const spb_exec *ex) {
+    return run_map(ex, n, 8, 8, x, out, [](const void *i, void *o, long long m, cudaStream_t st) {
+        launch_sinc((const double *)i, (double *)o, m, st);
+    });
+}
+
+int spb_first_error(const int32_t *ierr, int64_t n, int64_t *idx, int32_t *code, const spb_exec *ex) {
+    if (!idx || !code) return fail(SPB_E_ARG, "null output");
+    *idx = -1;
+    *code = 0;
+    if (n < 0) return fail(SPB_E_ARG, "negative n");
+    if (n == 0) return SPB_OK;
+    if (!ierr) return fail(SPB_E_ARG, "null buffer");
+    if (!ex || !ex->device_ptrs) {
+        // host array: plain scan (this is host-side bookkeeping, not part of the compute path)
+        for (int64_t i = 0; i < n; ++i)
+            if (ierr[i] != 0) {
+                *idx = i;
+                *code = ierr[i];
+                break;
+            }
+        return SPB_OK;
+    }
+    std::vector<int> devs;
+    bool dptr;
+    cudaStream_t st;
+    int flags;
+    int rc = check_exec(ex, devs, dptr, st, flags);
+    if (rc != SPB_OK) return rc;
+    DeviceCtx *c = get_ctx(devs[0]);
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->dev));
+    CK(cudaMemsetAsync(c->d_packed, 0xff, 8, st));
+    launch_first_error(ierr, n, c->d_packed, st);
+    unsigned long long packed = 0;
+    CK(cudaMemcpyAsync(&packed, c->d_packed, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (packed != ~0ull) {
+        *idx = (int64_t)(packed >> 8);
+        *code = (int32_t)(packed & 0xff);
+    }
+    return SPB_OK;
+}
+
+int spb_synth(int cfg, uint64_t seed, int64_t offset, int64_t n, int64_t n_total, double *v, spb_c128 *z,
+              const spb_exec *ex) {
+    if (cfg < 1 || cfg > 5) return fail(SPB_E_ARG, "cfg must be 1..5");
+    if (n < 0 || offset < 0) return fail(SPB_E_ARG, "negative n or offset");
+    std::vector<int> devs;
+    bool dptr;
+    cudaStream_t st;
+    int flags;
+    int rc = check_exec(ex, devs, dptr, st, flags);
+    if (rc != SPB_OK) return rc;
+    if (n == 0) return SPB_OK;
+    DeviceCtx *c = get_ctx(devs[0]);
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->dev));
+    if (dptr) {
+        launch_synth(cfg, seed, offset, n, n_total, v, (double2 *)z, st);
+        CK(cudaGetLastError());
+        return SPB_OK;
+    }
+    double *dv = nullptr;
+    double2 *dz = nullptr;
+    if (v && cudaMalloc(&dv, n * 8) != cudaSuccess) return fail(SPB_E_ALLOC, "cudaMalloc failed");
+    if (z && cudaMalloc(&dz, n * 16) != cudaSuccess) {
+        cudaFree(dv);
+        return fail(SPB_E_ALLOC, "cudaMalloc failed");
+    }
+    launch_synth(cfg, seed, offset, n, n_total, dv, dz, c->streams[0]);
+    cudaError_t e = cudaSuccess;
+    if (v) e = cudaMemcpyAsync(v, dv, n * 8, cudaMemcpyDeviceToHost, c->streams[0]);
+    if (z && e == cudaSuccess) e = cudaMemcpyAsync(z, dz, n * 16, cudaMemcpyDeviceToHost, c->streams[0]);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->streams[0]);
+    cudaFree(dv);
+    cudaFree(dz);
+    if (e != cudaSuccess) return fail(SPB_E_CUDA, cudaGetErrorString(e));
+    return SPB_OK;
+}
+
+int spb_fp64_peak(int device, double seconds, double *tflops, double *sm_mhz) {
+    int ndev = device_count();
+    if (ndev <= 0) return fail(SPB_E_NO_DEVICE, "no CUDA device visible");
+    if (device < 0 || device >= ndev || !tflops) return fail(SPB_E_ARG, "bad device or null output");
+    *tflops = run_fp64_peak(device, seconds, sm_mhz);
+    return SPB_OK;
+}
+
+int spb_last_profile(int max_records, int *kernel_ids, double *ms, int64_t *points) {
+    int n = (int)g_prof.size();
+    if (n > max_records) n = max_records;
+    for (int i = 0; i < n; ++i) {
+        if (kernel_ids) kernel_ids[i] = g_prof[i].kernel;
+        if (ms) ms[i] = g_prof[i].ms;
+        if (points) points[i] = g_prof[i].points;
+    }
+    return n;
+}
+
+int spb_last_timing(double *kernel_ms, int *launches) {
+    if (kernel_ms) *kernel_ms = g_last_ms;
+    if (launches) *launches = g_last_launches;
+    return SPB_OK;
+}
+
+int spb_device_count(void) { return device_count(); }
+int spb_version(void) { return 100; }
+const char *spb_last_error(void) { return g_err.c_str(); }
+
+}  // extern "C"

@@ -1,0 +1,45 @@
+// k_general.cu — the general per-point path on the GPU: every point the binned
+// pipeline does not treat as "simple" (uniform-asymptotic orders, arguments near
+// the exponent limits, invalid input, region hand-overs) runs the complete
+// driver here.  k_monolithic runs the same driver over a whole batch and is the
+// in-GPU cross-check of the binned path (SPB_PATH_MONOLITHIC).
+#include "spb_dev.cuh"
+
+namespace spbk {
+
+__global__ void __launch_bounds__(128) k_general(DevJob job, Scratch s) {
+    const unsigned int count = s.bins[GLIST_LEN_SLOT];
+    const unsigned int stride = gridDim.x * blockDim.x;
+#pragma unroll 1
+    for (unsigned int t = blockIdx.x * blockDim.x + threadIdx.x; t < count; t += stride) {
+        const long long i = s.glist[t];
+        cplx z;
+        double v;
+        load_point(job, i, z, v);
+        eval_general_store(job, i, z, v);
+    }
+}
+
+__global__ void __launch_bounds__(128) k_monolithic(DevJob job) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+#pragma unroll 1
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < job.n; i += stride) {
+        cplx z;
+        double v;
+        load_point(job, i, z, v);
+        eval_general_store(job, i, z, v);
+    }
+}
+
+void launch_general(const DevJob &job, const Scratch &s, int sms, cudaStream_t st) {
+    k_general<<<sms * 4, 128, 0, st>>>(job, s);
+}
+
+void launch_monolithic(const DevJob &job, cudaStream_t st) {
+    long long blocks = (job.n + 127) / 128;
+    if (blocks > 148 * 64) blocks = 148 * 64;
+    if (blocks < 1) blocks = 1;
+    k_monolithic<<<(int)blocks, 128, 0, st>>>(job);
+}
+
+}  // namespace spbk

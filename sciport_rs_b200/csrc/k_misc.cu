@@ -1,0 +1,213 @@
+// k_misc.cu — small kernels around the hot path: synthetic inputs, first-error
+// reduction, the memory-bound gamma / lgamma / sinc companions, and the DFMA
+// microbenchmark that defines "FP64 peak" for the roofline.
+#include "spb_dev.cuh"
+#include "amos/spb_gamma.h"
+#include <chrono>
+
+namespace spbk {
+
+// ---------------------------------------------------------------- synthetic inputs
+__device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
+    x ^= x >> 30;
+    x *= 0xBF58476D1CE4E5B9ull;
+    x ^= x >> 27;
+    x *= 0x94D049BB133111EBull;
+    x ^= x >> 31;
+    return x;
+}
+__device__ __forceinline__ double u01(unsigned long long seed, unsigned long long i, int k) {
+    unsigned long long h = mix64(seed * 0x9E3779B97F4A7C15ull + 4ull * i + (unsigned long long)k);
+    return (double)(h >> 11) * (1.0 / 9007199254740992.0);
+}
+
+// cfg 1: x = 100 u0 (real axis), v = 0      cfg 2: 4096 x 4096 grid, |z| <= 200, v = 2.5
+// cfg 3: v = 50 u0, z = 200 u1 e^{i pi (2 u2 - 1)}      cfg 4: z = 10^(-3+7 u0) e^{i pi (2 u1 - 1)}, v = 2.5
+// cfg 5: z as cfg 3, v = 0
+__global__ void k_synth(int cfg, unsigned long long seed, long long offset, long long n, long long n_total,
+                        double *v, double2 *z) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) {
+        unsigned long long i = (unsigned long long)(offset + t);
+        double vv = 0.0;
+        double2 zz;
+        if (cfg == 2) {
+            long long side = 4096;
+            if (n_total != side * side) {
+                side = (long long)llrint(sqrt((double)n_total));
+            }
+            long long j = (long long)(i % (unsigned long long)side), k = (long long)(i / (unsigned long long)side);
+            const double a = 141.42135623730951;  // 200/sqrt(2)
+            zz.x = -a + (2.0 * a) * ((double)j + 0.5) / (double)side;
+            zz.y = -a + (2.0 * a) * ((double)k + 0.5) / (double)side;
+            vv = 2.5;
+        } else if (cfg == 3 || cfg == 5) {
+            vv = (cfg == 3) ? 50.0 * u01(seed, i, 0) : 0.0;
+            double r = 200.0 * u01(seed, i, 1);
+            double s, c;
+            sincospi(2.0 * u01(seed, i, 2) - 1.0, &s, &c);
+            zz.x = r * c;
+            zz.y = r * s;
+        } else if (cfg == 4) {
+            vv = 2.5;
+            double r = exp10(-3.0 + 7.0 * u01(seed, i, 0));
+            double s, c;
+            sincospi(2.0 * u01(seed, i, 1) - 1.0, &s, &c);
+            zz.x = r * c;
+            zz.y = r * s;
+        } else {  // cfg 1
+            zz.x = 100.0 * u01(seed, i, 0);
+            zz.y = 0.0;
+        }
+        if (v) v[t] = vv;
+        if (z) z[t] = zz;
+    }
+}
+
+void launch_synth(int cfg, unsigned long long seed, long long offset, long long n, long long n_total, double *v,
+                  double2 *z, cudaStream_t st) {
+    long long blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks < 1) blocks = 1;
+    k_synth<<<(int)blocks, 256, 0, st>>>(cfg, seed, offset, n, n_total, v, z);
+}
+
+// ---------------------------------------------------------------- first error in index order
+// packed = min over i with ierr != 0 of (i << 8 | ierr); ~0 when none
+__global__ void k_first_error(const int *ierr, long long n, unsigned long long *packed) {
+    unsigned long long best = ~0ull;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        int e = ierr[i];
+        if (e != 0) {
+            unsigned long long p = ((unsigned long long)i << 8) | (unsigned long long)(e & 0xff);
+            if (p < best) best = p;
+        }
+    }
+    for (int d = 16; d > 0; d >>= 1) {
+        unsigned long long o = __shfl_down_sync(0xffffffffu, best, d);
+        if (o < best) best = o;
+    }
+    if ((threadIdx.x & 31) == 0 && best != ~0ull) atomicMin(packed, best);
+}
+
+void launch_first_error(const int *ierr, long long n, unsigned long long *packed, cudaStream_t st) {
+    long long blocks = (n + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    k_first_error<<<(int)blocks, 256, 0, st>>>(ierr, n, packed);
+}
+
+// ---------------------------------------------------------------- gamma / lgamma / sinc (HBM-bound)
+// two points per thread through one 16-byte load / store
+template <int WHICH>
+__device__ __forceinline__ double gfun(double x) {
+    if (WHICH == 0) return spb::gamma_real(x);
+    if (WHICH == 1) return spb::lgamma_real(x);
+    return spb::sinc_real(x);
+}
+
+template <int WHICH>
+__global__ void __launch_bounds__(256) k_real_map(const double *x, double *out, long long n) {
+    const long long n2 = n >> 1;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const double2 *x2 = reinterpret_cast<const double2 *>(x);
+    double2 *o2 = reinterpret_cast<double2 *>(out);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
+        double2 a = __ldg(x2 + i);
+        double2 r;
+        r.x = gfun<WHICH>(a.x);
+        r.y = gfun<WHICH>(a.y);
+        o2[i] = r;
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) out[n - 1] = gfun<WHICH>(x[n - 1]);
+}
+
+template <int WHICH>
+__global__ void __launch_bounds__(256) k_real_map_unaligned(const double *x, double *out, long long n) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = gfun<WHICH>(__ldg(x + i));
+}
+
+template <int WHICH>
+static void launch_real_map(const double *x, double *out, long long n, cudaStream_t st) {
+    long long blocks = (n / 2 + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+    if (aligned)
+        k_real_map<WHICH><<<(int)blocks, 256, 0, st>>>(x, out, n);
+    else
+        k_real_map_unaligned<WHICH><<<(int)blocks, 256, 0, st>>>(x, out, n);
+}
+
+void launch_gamma(int which, const double *x, double *out, long long n, cudaStream_t st) {
+    if (which == 0)
+        launch_real_map<0>(x, out, n, st);
+    else
+        launch_real_map<1>(x, out, n, st);
+}
+void launch_sinc(const double *x, double *out, long long n, cudaStream_t st) { launch_real_map<2>(x, out, n, st); }
+
+// ---------------------------------------------------------------- FP64 peak microbenchmark
+// 8 independent DFMA chains per thread, register resident; 2 flops per DFMA.
+__global__ void __launch_bounds__(256) k_dfma(double *sink, int iters, double a, double b) {
+    double x0 = threadIdx.x * 1e-9, x1 = x0 + 1e-3, x2 = x0 + 2e-3, x3 = x0 + 3e-3;
+    double x4 = x0 + 4e-3, x5 = x0 + 5e-3, x6 = x0 + 6e-3, x7 = x0 + 7e-3;
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            x0 = fma(x0, a, b);
+            x1 = fma(x1, a, b);
+            x2 = fma(x2, a, b);
+            x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b);
+            x5 = fma(x5, a, b);
+            x6 = fma(x6, a, b);
+            x7 = fma(x7, a, b);
+        }
+    }
+    double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (s == 12345.678) sink[0] = s;  // never true; keeps the chains alive
+}
+
+double run_fp64_peak(int device, double seconds, double *sm_mhz) {
+    cudaSetDevice(device);
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    double *sink = nullptr;
+    cudaMalloc(&sink, 8);
+    const int blocks = prop.multiProcessorCount * 8;
+    const int iters = 4096;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    k_dfma<<<blocks, 256>>>(sink, iters, 0.999999, 1e-7);  // warm-up
+    cudaDeviceSynchronize();
+    double best = 0.0;
+    auto t0 = std::chrono::steady_clock::now();
+    do {
+        cudaEventRecord(e0);
+        for (int r = 0; r < 8; ++r) k_dfma<<<blocks, 256>>>(sink, iters, 0.999999, 1e-7);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        double flops = 8.0 * (double)blocks * 256.0 * (double)iters * 16.0 * 8.0 * 2.0;
+        double tf = flops / (ms * 1e-3) / 1e12;
+        if (tf > best) best = tf;
+    } while (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() < seconds);
+    if (sm_mhz) {
+        int khz = 0;
+        cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
+        *sm_mhz = khz / 1000.0;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    return best;
+}
+
+}  // namespace spbk

@@ -1,0 +1,60 @@
+// spb_kernels.cuh — declarations shared by the kernel translation units and the
+// C-ABI launcher layer (capi.cu).  One `DevJob` describes one chunk of one
+// spb_bessel() call on one device; all pointers are device pointers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace spbk {
+
+struct DevJob {
+    int fam;   // spb::Family
+    int kode;  // 1 | 2
+    int sem;   // 0 raw AMOS, 1 scipy-compatible post-processing
+    const double *v;
+    long long v_stride;  // 0 = broadcast
+    const double2 *z;    // complex input, or
+    const double *x;     // real input promoted to complex (z == nullptr)
+    double2 *out;
+    int *ierr;  // nullable
+    int *nz;    // nullable
+    long long n;  // points in this chunk
+};
+
+// Scratch of one chunk (device memory, owned by the per-device cache in capi.cu).
+struct Scratch {
+    unsigned char *cls;     // [n] class byte: bits 0-2 I bin (7 none), 3-4 K bin (3 none), 5 general
+    unsigned int *perm_i;   // [n] point indices sorted by I bin (stable)
+    unsigned int *perm_k;   // [n] point indices sorted by K bin (stable)
+    unsigned int *glist;    // [n] general-path list
+    double2 *itemp;         // [n] I(w) for families that also need K
+    signed char *icode;     // [n] nz of the I pass (<0: handed to the general path)
+    unsigned int *blockcnt; // [NBINS][nblocks] per-tile histogram, then exclusive offsets
+    unsigned int *bins;     // [NBINS+1] start offsets of bins inside their perm arrays; [16] = glist length
+    int nblocks;            // tiles in this chunk
+};
+
+// bins: 0..3 I regions (series, asyi, mlri, wrsk), 4..6 K regions (series, miller, half), 7 general
+constexpr int NBINS = 8;
+constexpr int TILE = 2048;  // points per classification tile
+constexpr int BIN_GENERAL = 7;
+constexpr int GLIST_LEN_SLOT = 16;
+
+// kernels.cu
+void launch_classify(const DevJob &job, const Scratch &s, cudaStream_t st);
+void launch_scan_scatter(const DevJob &job, const Scratch &s, cudaStream_t st);
+void launch_ipass(const DevJob &job, const Scratch &s, int region, int sms, cudaStream_t st);
+void launch_kpass(const DevJob &job, const Scratch &s, int sms, cudaStream_t st);
+void launch_general(const DevJob &job, const Scratch &s, int sms, cudaStream_t st);
+void launch_monolithic(const DevJob &job, cudaStream_t st);
+void launch_airy(int which, int kode, int sem, const double2 *z, double2 *out, int *ierr, int *nz, long long n,
+                 cudaStream_t st);
+void launch_synth(int cfg, unsigned long long seed, long long offset, long long n, long long n_total, double *v,
+                  double2 *z, cudaStream_t st);
+void launch_first_error(const int *ierr, long long n, unsigned long long *packed, cudaStream_t st);
+void launch_gamma(int which, const double *x, double *out, long long n, cudaStream_t st);
+void launch_cgamma(int which, const double2 *z, double2 *out, long long n, cudaStream_t st);
+void launch_sinc(const double *x, double *out, long long n, cudaStream_t st);
+double run_fp64_peak(int device, double seconds, double *sm_mhz);
+
+}  // namespace spbk

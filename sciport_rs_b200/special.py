@@ -1,0 +1,315 @@
+"""Host-side mirror of sciport-rs's `special` module, batched.
+
+Reference surface (same names, argument order and error behaviour):
+
+* ``i0(x)``      /root/reference/src/special/mod.rs:8-13   real array -> complex array, first ``Err(i32)`` in
+                 index order wins (``collect::<Result<_, i32>>``) -> raises :class:`SpecialError`
+* ``kv(v, z)``   /root/reference/src/special/kv.rs:11-25   NaN z -> 0, NaN v -> 0, ``unwrap()`` panics on Err
+                 -> raises :class:`SpecialPanic`
+* ``kve(v, z)``  /root/reference/src/special/kv.rs:39-41   ``kv(v, z) * exp(z)`` (post-multiplication)
+* ``sinc(x)``    /root/reference/src/special/trig.rs:4-13
+
+Widened, batched surface named by BASELINE.json (order first, then z; ``xv`` / ``xve`` pairs like kv / kve):
+``jv jve yv yve iv ive kv_array kve_array hankel1 hankel1e hankel2 hankel2e airy airye gamma gammaln loggamma``.
+
+Inputs may be numpy arrays (host buffers: the library stages them through pinned async copies) or torch CUDA
+tensors (device pointers: zero copies, launched on the current torch stream).  Everything is computed by the
+CUDA library; nothing here evaluates a special function on the CPU.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import lib, check, make_exec, FN, AIRY, SEM_AMOS, SEM_SCIPY, PATH_MONOLITHIC, PROFILE
+
+try:  # torch is plumbing only (device memory / streams)
+    import torch
+except Exception:  # pragma: no cover
+    torch = None
+
+
+class SpecialError(Exception):
+    """``Err(code)`` of the reference's ``Result<_, i32>`` (first failing element, index order)."""
+
+    def __init__(self, code, index):
+        super().__init__(f"special function failed with ierr={code} at index {index}")
+        self.code = code
+        self.index = index
+
+
+class SpecialPanic(RuntimeError):
+    """The reference ``unwrap()``s the scalar kv result (kv.rs:24) and panics on Err."""
+
+
+def _is_torch(a):
+    return torch is not None and isinstance(a, torch.Tensor)
+
+
+def _stream_for(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+_PROFILE_LOG = None
+
+
+def profile_step(fn):
+    """Run `fn` (which calls bessel(..., profile=True)) and return the per-kernel records, with the family
+    prefixed: [{"name": "J/ipass_asyi", "ms": .., "points": ..}, ...]."""
+    global _PROFILE_LOG
+    _PROFILE_LOG = []
+    try:
+        fn()
+        return _PROFILE_LOG
+    finally:
+        _PROFILE_LOG = None
+
+
+def bessel(fn, v, z, scaled=False, semantics="amos", path="binned", real_input=False, devices=None, profile=False):
+    """Evaluate one family over a batch.  Returns ``(values, ierr, nz)``.
+
+    fn: 'J','Y','I','K','H1','H2'; v: scalar or array broadcast against z; z: complex128 (or float64 with
+    ``real_input=True``, promoted like ``v.into()`` in mod.rs:10).
+    """
+    kode = 2 if scaled else 1
+    flags = (SEM_SCIPY if semantics == "scipy" else SEM_AMOS) | (PATH_MONOLITHIC if path == "monolithic" else 0)
+    if profile:
+        flags |= PROFILE
+    if _is_torch(z):
+        if not z.is_cuda:
+            raise ValueError("torch inputs must be CUDA tensors (use numpy arrays for host buffers)")
+        zc = z.contiguous()
+        want = torch.float64 if real_input else torch.complex128
+        if zc.dtype != want:
+            zc = zc.to(want)
+        n = zc.numel()
+        if _is_torch(v):
+            vt = v.to(device=zc.device, dtype=torch.float64).contiguous()
+            if vt.numel() == 1:
+                stride = 0
+            else:
+                if vt.numel() != n:
+                    raise ValueError("v and z must have the same number of elements")
+                stride = 1
+        else:
+            vt = torch.full((1,), float(v), dtype=torch.float64, device=zc.device)
+            stride = 0
+        out = torch.empty(zc.shape, dtype=torch.complex128, device=zc.device)
+        ierr = torch.empty(zc.shape, dtype=torch.int32, device=zc.device)
+        nz = torch.empty(zc.shape, dtype=torch.int32, device=zc.device)
+        with torch.cuda.device(zc.device):
+            ex = make_exec(device_ptrs=True, stream=_stream_for(zc), flags=flags, devices=[zc.device.index])
+            f = lib.spb_bessel_real if real_input else lib.spb_bessel
+            check(f(FN[fn], kode, vt.data_ptr(), stride, zc.data_ptr(), out.data_ptr(), ierr.data_ptr(),
+                    nz.data_ptr(), n, 1, ctypes.byref(ex)))
+        if profile and _PROFILE_LOG is not None:
+            for r in _lib.last_profile():
+                r["name"] = f"{fn}/{r['name']}"
+                _PROFILE_LOG.append(r)
+        return out, ierr, nz
+    za = np.ascontiguousarray(z, dtype=np.float64 if real_input else np.complex128)
+    n = za.size
+    va = np.asarray(v, dtype=np.float64)
+    if va.size == 1:
+        va = np.ascontiguousarray(va.reshape(1))
+        stride = 0
+    else:
+        va = np.ascontiguousarray(np.broadcast_to(va, za.shape))
+        stride = 1
+    out = np.empty(za.shape, dtype=np.complex128)
+    ierr = np.empty(za.shape, dtype=np.int32)
+    nz = np.empty(za.shape, dtype=np.int32)
+    ex = make_exec(device_ptrs=False, flags=flags, devices=devices)
+    f = lib.spb_bessel_real if real_input else lib.spb_bessel
+    check(f(FN[fn], kode, va.ctypes.data, stride, za.ctypes.data, out.ctypes.data, ierr.ctypes.data, nz.ctypes.data,
+            n, 1, ctypes.byref(ex)))
+    return out, ierr, nz
+
+
+def first_error(ierr):
+    """(index, code) of the first non-zero ierr in index order, (-1, 0) if none."""
+    idx = ctypes.c_int64()
+    code = ctypes.c_int32()
+    if _is_torch(ierr):
+        t = ierr.contiguous()
+        with torch.cuda.device(t.device):
+            ex = make_exec(device_ptrs=True, stream=_stream_for(t), devices=[t.device.index])
+            check(lib.spb_first_error(t.data_ptr(), t.numel(), ctypes.byref(idx), ctypes.byref(code), ctypes.byref(ex)))
+    else:
+        a = np.ascontiguousarray(ierr, dtype=np.int32)
+        ex = make_exec()
+        check(lib.spb_first_error(a.ctypes.data, a.size, ctypes.byref(idx), ctypes.byref(code), ctypes.byref(ex)))
+    return idx.value, code.value
+
+
+def _result(vals, ierr, accept_half=True):
+    """`collect::<Result<Array, i32>>()`: raise on the first Err in index order (mod.rs:11-12)."""
+    idx, code = first_error(ierr)
+    if idx >= 0:
+        raise SpecialError(code, idx)
+    return vals
+
+
+# ---------------------------------------------------------------- reference surface
+def i0(x):
+    """special::i0 (mod.rs:8-13): I_0 of a real array through the complex routine; complex result."""
+    vals, ierr, _ = bessel("I", 0.0, x, real_input=True)
+    return _result(vals, ierr)
+
+
+def kv(v, z):
+    """special::kv (kv.rs:11-25), scalar: NaN z -> 0, NaN v -> 0, then K_v(z); panics on Err."""
+    z = complex(z)
+    v = float(v)
+    if z != z:
+        z = 0j
+    if v != v:
+        v = 0.0
+    if v < 0:
+        v = -v  # K_{-v} = K_v (the reference exercises kv(-3.5, 1000), kv.rs:53-54)
+    vals, ierr, _ = bessel("K", v, np.array([z], dtype=np.complex128))
+    if ierr[0] != 0:
+        print(f"{v} {z}")  # kv.rs:20-22
+        raise SpecialPanic(f"called `Result::unwrap()` on an `Err` value: {int(ierr[0])}")
+    return complex(vals[0])
+
+
+def kve(v, z):
+    """special::kve (kv.rs:39-41): kv(v, z) * exp(z)."""
+    return kv(v, z) * np.exp(complex(z))
+
+
+def sinc(x):
+    """special::sinc (trig.rs:4-13)."""
+    return _real_map(lib.spb_sinc, x)
+
+
+# ---------------------------------------------------------------- widened batched surface
+def _family(fn, scaled):
+    def f(v, z, **kw):
+        vals, ierr, _ = bessel(fn, v, z, scaled=scaled, **kw)
+        return _result(vals, ierr)
+
+    return f
+
+
+jv, jve = _family("J", False), _family("J", True)
+yv, yve = _family("Y", False), _family("Y", True)
+iv, ive = _family("I", False), _family("I", True)
+kv_array, kve_array = _family("K", False), _family("K", True)
+hankel1, hankel1e = _family("H1", False), _family("H1", True)
+hankel2, hankel2e = _family("H2", False), _family("H2", True)
+
+
+def airy_raw(which, z, scaled=False, semantics="amos"):
+    kode = 2 if scaled else 1
+    flags = SEM_SCIPY if semantics == "scipy" else SEM_AMOS
+    if _is_torch(z):
+        zc = z.contiguous().to(torch.complex128)
+        out = torch.empty_like(zc)
+        ierr = torch.empty(zc.shape, dtype=torch.int32, device=zc.device)
+        nz = torch.empty(zc.shape, dtype=torch.int32, device=zc.device)
+        with torch.cuda.device(zc.device):
+            ex = make_exec(device_ptrs=True, stream=_stream_for(zc), flags=flags, devices=[zc.device.index])
+            check(lib.spb_airy(AIRY[which], kode, zc.data_ptr(), out.data_ptr(), ierr.data_ptr(), nz.data_ptr(),
+                               zc.numel(), ctypes.byref(ex)))
+        return out, ierr, nz
+    za = np.ascontiguousarray(z, dtype=np.complex128)
+    out = np.empty_like(za)
+    ierr = np.empty(za.shape, np.int32)
+    nz = np.empty(za.shape, np.int32)
+    ex = make_exec(flags=flags)
+    check(lib.spb_airy(AIRY[which], kode, za.ctypes.data, out.ctypes.data, ierr.ctypes.data, nz.ctypes.data, za.size,
+                       ctypes.byref(ex)))
+    return out, ierr, nz
+
+
+def airy(z, scaled=False):
+    """(Ai, Ai', Bi, Bi') like scipy.special.airy; raises on the first Err."""
+    outs = []
+    for which in ("Ai", "Aip", "Bi", "Bip"):
+        vals, ierr, _ = airy_raw(which, z, scaled=scaled)
+        outs.append(_result(vals, ierr))
+    return tuple(outs)
+
+
+def airye(z):
+    return airy(z, scaled=True)
+
+
+def _real_map(fn, x):
+    if _is_torch(x):
+        xc = x.contiguous().to(torch.float64)
+        out = torch.empty_like(xc)
+        with torch.cuda.device(xc.device):
+            ex = make_exec(device_ptrs=True, stream=_stream_for(xc), devices=[xc.device.index])
+            check(fn(xc.data_ptr(), out.data_ptr(), xc.numel(), ctypes.byref(ex)))
+        return out
+    xa = np.ascontiguousarray(x, dtype=np.float64)
+    out = np.empty_like(xa)
+    ex = make_exec()
+    check(fn(xa.ctypes.data, out.ctypes.data, xa.size, ctypes.byref(ex)))
+    return out
+
+
+def _cplx_map(fn, z):
+    if _is_torch(z):
+        zc = z.contiguous().to(torch.complex128)
+        out = torch.empty_like(zc)
+        with torch.cuda.device(zc.device):
+            ex = make_exec(device_ptrs=True, stream=_stream_for(zc), devices=[zc.device.index])
+            check(fn(zc.data_ptr(), out.data_ptr(), zc.numel(), ctypes.byref(ex)))
+        return out
+    za = np.ascontiguousarray(z, dtype=np.complex128)
+    out = np.empty_like(za)
+    ex = make_exec()
+    check(fn(za.ctypes.data, out.ctypes.data, za.size, ctypes.byref(ex)))
+    return out
+
+
+def _is_complex(a):
+    if _is_torch(a):
+        return a.is_complex()
+    return np.iscomplexobj(a)
+
+
+def gamma(x):
+    return _cplx_map(lib.spb_cgamma, x) if _is_complex(x) else _real_map(lib.spb_gamma, x)
+
+
+def gammaln(x):
+    """ln|Gamma(x)| for real x."""
+    return _real_map(lib.spb_lgamma, x)
+
+
+def loggamma(z):
+    """Principal branch of log Gamma(z) for complex z; ln|Gamma(x)| for real x."""
+    return _cplx_map(lib.spb_clgamma, z) if _is_complex(z) else _real_map(lib.spb_lgamma, z)
+
+
+def synth(cfg, n, n_total=None, offset=0, seed=None, device=None):
+    """Synthetic inputs of BASELINE config `cfg` generated on the GPU.
+
+    Returns (v, z): torch CUDA tensors when `device` is given, numpy arrays otherwise."""
+    seed = cfg if seed is None else seed
+    n_total = n if n_total is None else n_total
+    if device is not None:
+        dev = torch.device(device)
+        v = torch.empty(n, dtype=torch.float64, device=dev)
+        z = torch.empty(n, dtype=torch.complex128, device=dev)
+        with torch.cuda.device(dev):
+            ex = make_exec(device_ptrs=True, stream=torch.cuda.current_stream(dev).cuda_stream, devices=[dev.index or 0])
+            check(lib.spb_synth(cfg, seed, offset, n, n_total, v.data_ptr(), z.data_ptr(), ctypes.byref(ex)))
+        return v, z
+    v = np.empty(n, np.float64)
+    z = np.empty(n, np.complex128)
+    ex = make_exec()
+    check(lib.spb_synth(cfg, seed, offset, n, n_total, v.ctypes.data, z.ctypes.data, ctypes.byref(ex)))
+    return v, z
+
+
+def fp64_peak(device=0, seconds=2.0):
+    t = ctypes.c_double()
+    mhz = ctypes.c_double()
+    check(lib.spb_fp64_peak(device, seconds, ctypes.byref(t), ctypes.byref(mhz)))
+    return t.value, mhz.value

@@ -1,0 +1,95 @@
+"""Shared helpers for the tests: the CPU checker library (oracle/), golden vectors, tolerance policy."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+FN = {"J": 0, "Y": 1, "I": 2, "K": 3, "H1": 4, "H2": 5}
+CATS = ["", "domain", "overflow", "underflow", "loss", "no_result", "singular", "slow", "other"]
+
+_oracle = None
+
+
+def oracle_lib():
+    """oracle/libspb_oracle.so, built on demand with g++ (CPU only)."""
+    global _oracle
+    if _oracle is None:
+        path = os.path.join(ROOT, "oracle", "libspb_oracle.so")
+        subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
+        lib = ctypes.CDLL(path)
+        P, I, L = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64
+        lib.spbo_bessel.argtypes = [I, I, P, L, P, P, P, P, L, I]
+        lib.spbo_bessel_sem.argtypes = [I, I, I, P, L, P, P, P, P, L, I]
+        lib.spbo_bessel_pipeline.argtypes = [I, I, P, L, P, P, P, P, P, L, I]
+        lib.spbo_airy.argtypes = [I, I, P, P, P, P, L, I]
+        lib.spbo_gamma.argtypes = [I, P, P, L]
+        lib.spbo_cgamma.argtypes = [I, P, P, L]
+        _oracle = lib
+    return _oracle
+
+
+def cpu_bessel(fn, kode, v, z, sem=0, pipeline=False, threads=8):
+    lib = oracle_lib()
+    z = np.ascontiguousarray(z, dtype=np.complex128)
+    v = np.ascontiguousarray(np.broadcast_to(np.asarray(v, dtype=np.float64), z.shape))
+    out = np.empty_like(z)
+    ierr = np.empty(z.shape, np.int32)
+    nz = np.empty(z.shape, np.int32)
+    if pipeline:
+        path = np.empty(z.shape, np.int32)
+        lib.spbo_bessel_pipeline(FN[fn], kode, v.ctypes.data, 1, z.ctypes.data, out.ctypes.data, ierr.ctypes.data,
+                                 nz.ctypes.data, path.ctypes.data, z.size, threads)
+        return out, ierr, nz, path
+    lib.spbo_bessel_sem(FN[fn], kode, sem, v.ctypes.data, 1, z.ctypes.data, out.ctypes.data, ierr.ctypes.data,
+                        nz.ctypes.data, z.size, threads)
+    return out, ierr, nz
+
+
+def cpu_airy(which, kode, z, threads=8):
+    lib = oracle_lib()
+    z = np.ascontiguousarray(z, dtype=np.complex128)
+    out = np.empty_like(z)
+    ierr = np.empty(z.shape, np.int32)
+    nz = np.empty(z.shape, np.int32)
+    lib.spbo_airy(which, kode, z.ctypes.data, out.ctypes.data, ierr.ctypes.data, nz.ctypes.data, z.size, threads)
+    return out, ierr, nz
+
+
+def cpu_gamma(which, x):
+    """which: 0 gamma, 1 gammaln, 2 sinc (real); 10 gamma, 11 loggamma (complex)."""
+    lib = oracle_lib()
+    if which >= 10:
+        z = np.ascontiguousarray(x, dtype=np.complex128)
+        out = np.empty_like(z)
+        lib.spbo_cgamma(which - 10, z.ctypes.data, out.ctypes.data, z.size)
+        return out
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    out = np.empty_like(x)
+    lib.spbo_gamma(which, x.ctypes.data, out.ctypes.data, x.size)
+    return out
+
+
+def load_golden(name):
+    return np.load(os.path.join(GOLDEN, name))
+
+
+def expected_ierr_ok(cat_code, ierr, nz):
+    """Does (ierr, nz) agree with the oracle's sf_error class?  underflow <-> nz != 0; loss <-> ierr 3;
+    domain 1; overflow 2; no_result 4 or 5."""
+    cat = CATS[cat_code]
+    if cat == "":
+        return ierr == 0 and nz == 0
+    if cat == "underflow":
+        return nz != 0 and ierr == 0
+    if cat == "loss":
+        return ierr == 3
+    if cat == "domain":
+        return ierr == 1
+    if cat == "overflow":
+        return ierr == 2
+    if cat == "no_result":
+        return ierr in (4, 5)
+    return False

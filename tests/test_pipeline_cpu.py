@@ -1,0 +1,45 @@
+"""CPU: the restructured flow the GPU kernels run (prepare -> I pass -> K pass -> finish, general path on any
+hand-over; sciport_rs_b200/csrc/amos/spb_family.h) must reproduce the point-by-point drivers bit for bit."""
+import numpy as np
+import pytest
+
+import helpers
+from helpers import FN
+
+
+def gen(cfg, n, rng):
+    if cfg == "cfg2":
+        a = 200 / np.sqrt(2)
+        return np.full(n, 2.5), rng.uniform(-a, a, n) + 1j * rng.uniform(-a, a, n)
+    if cfg == "cfg3":
+        return 50 * rng.random(n), 200 * rng.random(n) * np.exp(1j * np.pi * (2 * rng.random(n) - 1))
+    if cfg == "cfg4":
+        return np.full(n, 2.5), 10 ** (-3 + 7 * rng.random(n)) * np.exp(1j * np.pi * (2 * rng.random(n) - 1))
+    if cfg == "real":
+        return rng.integers(0, 2, n).astype(float), (100 * rng.random(n)).astype(np.complex128)
+    v = 10 ** rng.uniform(-2, 2.3, n)
+    return v, 10 ** rng.uniform(-3, 3, n) * np.exp(1j * np.pi * (2 * rng.random(n) - 1))
+
+
+@pytest.mark.parametrize("cfg", ["cfg2", "cfg3", "cfg4", "real", "wide"])
+@pytest.mark.parametrize("fn", list(FN))
+def test_pipeline_matches_drivers(fn, cfg):
+    rng = np.random.default_rng(hash((fn, cfg)) % 2**32)
+    v, z = gen(cfg, 20000, rng)
+    for kode in (1, 2):
+        a, ia, na = helpers.cpu_bessel(fn, kode, v, z)
+        b, ib, nb, path = helpers.cpu_bessel(fn, kode, v, z, pipeline=True)
+        assert np.array_equal(a.view(np.uint64), b.view(np.uint64))
+        assert np.array_equal(ia, ib) and np.array_equal(na, nb)
+    if cfg == "cfg2":
+        assert (path == 0).all(), "every cfg2 point must take the binned path"
+
+
+def test_golden_points_through_pipeline():
+    g = helpers.load_golden("bessel_golden.npz")
+    for fn in FN:
+        for kode in (1, 2):
+            a, ia, na = helpers.cpu_bessel(fn, kode, g["v"], g["z"])
+            b, ib, nb, _ = helpers.cpu_bessel(fn, kode, g["v"], g["z"], pipeline=True)
+            same = (a.view(np.uint64) == b.view(np.uint64)).reshape(-1, 2).all(1) | (np.isnan(a.real) & np.isnan(b.real))
+            assert same.all() and np.array_equal(ia, ib) and np.array_equal(na, nb)

@@ -16,6 +16,7 @@ here with exact rationals (sympy) or 60-digit arithmetic (mpmath):
   GAMA[30]   Maclaurin coefficients in w^2 = 1 - z^2 of zeta / w^2
              (DLMF 10.20.2-3)
   ALFA[180]  Maclaurin coefficients in w^2 of A_s(zeta), s = 1..6  (30 each)
+  LG1[32]    (-1)^k (zeta(k)-1)/k, k = 2..33: Maclaurin series of lgamma(1+t) (DLMF 5.7.3)
   BETA[210]  Maclaurin coefficients in w^2 of B_s(zeta), s = 0..6  (30 each)
              (DLMF 10.20.10-13); extracted by a Cauchy integral on |w^2| = r
              because the closed forms have removable singularities at w = 0.
@@ -217,6 +218,13 @@ def main():
     au, av = airy_uv(13)
     ar = [frac_to_mp(au[k] * Fraction(3, 2) ** k) for k in range(14)]
     br = [frac_to_mp(av[k] * Fraction(3, 2) ** k) for k in range(14)]
+    # lgamma(1+t) = -log1p(t) + t(1-euler) + sum_{k>=2} (-1)^k (zeta(k)-1) t^k / k   (DLMF 5.7.3)
+    lg1 = [(-1) ** k * (mp.zeta(k) - 1) / k for k in range(2, 34)]
+    # loggamma(1+t) = -euler t + sum_{k>=2} (-1)^k zeta(k) t^k / k for |t| <= 0.2 (complex Taylor branch)
+    lgz = [(-1) ** k * mp.zeta(k) / k for k in range(2, 25)]
+    write("spb_tables_gamma.inc", [table("LG1", lg1), table("LGZ", lgz)])
+    if "--fast" in sys.argv:
+        return
     gama, alfa, beta = gen_gama_alfa_beta()
     write("spb_tables_unhj.inc", [table("AR", ar), table("BR", br), table("UC", [frac_to_mp(c) for c in uk[:105]]),
                                   table("GAMA", gama), table("ALFA", alfa), table("BETA", beta)])
