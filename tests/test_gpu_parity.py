@@ -1,0 +1,221 @@
+"""GPU: parity of the CUDA path (through the C ABI, libsciport_b200.so) with the oracle.
+
+Checkers: (1) the committed golden vectors from scipy.special; (2) the CPU oracle restatement on seeded samples
+of every BASELINE config; (3) size-independent properties at full config size.  Tolerance policy as in
+tests/test_oracle_golden.py (1e-13 normalised, conditioning-aware beyond 1e+-49, absolute near zeros)."""
+import numpy as np
+import pytest
+
+import helpers
+from helpers import FN, CATS
+from oracle import scipy_oracle as so
+from test_oracle_golden import scipy_kode2_defect, sem_ok
+from test_pipeline_cpu import gen
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def special():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from sciport_rs_b200 import special as sp
+    return sp
+
+
+def to_np(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.mark.parametrize("kode", [1, 2])
+@pytest.mark.parametrize("fn", list(FN))
+def test_golden_device_pointers(special, fn, kode):
+    g = helpers.load_golden("bessel_golden.npz")
+    v, z = g["v"], g["z"]
+    want, cats = g[f"{fn}_{kode}"], g[f"{fn}_{kode}_err"]
+    zt = torch.from_numpy(z).cuda()
+    vt = torch.from_numpy(v).cuda()
+    got, ierr, nz = special.bessel(fn, vt, zt, scaled=(kode == 2), semantics="scipy")
+    got, ierr, nz = to_np(got), to_np(ierr), to_np(nz)
+    err = so.mismatch(got, want, so.scale_near_zeros(fn, kode, v, z, want))
+    skip = scipy_kode2_defect(fn, kode, v) | (cats == CATS.index("loss"))
+    bad = (err > so.tolerance(want)) & ~skip
+    assert not bad.any(), f"{bad.sum()} mismatches, first v={v[bad][0]} z={z[bad][0]} err={err[bad][0]:.2e}"
+    ok = np.array([sem_ok(c, e, n, zz) for c, e, n, zz in zip(cats, ierr, nz, z)]) | skip
+    assert ok.all(), f"{(~ok).sum()} ierr/nz mismatches, first v={v[~ok][0]} z={z[~ok][0]}"
+
+
+@pytest.mark.parametrize("cfg", ["cfg2", "cfg3", "cfg4", "real", "wide"])
+@pytest.mark.parametrize("fn", list(FN))
+def test_vs_cpu_oracle_and_monolithic(special, fn, cfg):
+    """Binned CUDA path vs CPU oracle (tolerance) and vs the monolithic CUDA path (bit-identical)."""
+    rng = np.random.default_rng(abs(hash((fn, cfg, "gpu"))) % 2**32)
+    v, z = gen(cfg, 200000, rng)
+    zt, vt = torch.from_numpy(z).cuda(), torch.from_numpy(v).cuda()
+    for kode in (1, 2):
+        got, ierr, nz = special.bessel(fn, vt, zt, scaled=(kode == 2))
+        mono, ierr_m, nz_m = special.bessel(fn, vt, zt, scaled=(kode == 2), path="monolithic")
+        g, m = to_np(got), to_np(mono)
+        same = (g.view(np.uint64) == m.view(np.uint64)).reshape(-1, 2).all(1) | (np.isnan(g.real) & np.isnan(m.real))
+        assert same.all(), f"binned != monolithic at {np.nonzero(~same)[0][:5]}"
+        assert torch.equal(ierr, ierr_m) and torch.equal(nz, nz_m)
+        want, ierr_c, nz_c = helpers.cpu_bessel(fn, kode, v, z)
+        comp = helpers.cpu_bessel(so.COMPANION[fn], kode, v, z)[0]
+        scale = np.maximum(np.abs(want), np.where(np.isfinite(np.abs(comp)), np.abs(comp), 0) *
+                           {"J": 1, "Y": 1, "I": 1 / np.pi, "K": np.pi, "H1": 0, "H2": 0}[fn])
+        err = so.mismatch(g, want, scale)
+        okv = (ierr_c == 0) & (nz_c == 0)
+        bad = okv & (err > so.tolerance(want))
+        assert not bad.any(), f"kode={kode}: {bad.sum()} mismatches, first v={v[bad][0]} z={z[bad][0]} err={err[bad][0]:.2e}"
+        # error classes: identical up to points sitting exactly on an over/underflow threshold
+        ie = to_np(ierr)
+        diff = (ie != ierr_c) | (to_np(nz) != nz_c)
+        assert diff.sum() <= 2, f"{diff.sum()} ierr/nz differences vs CPU oracle"
+
+
+def test_host_pointer_path_matches_device_path(special):
+    rng = np.random.default_rng(11)
+    v, z = gen("cfg3", 300000, rng)
+    for fn in ("J", "K", "Y"):
+        a, ia, na = special.bessel(fn, v, z)  # numpy in: staged through pinned copies inside the library
+        b, ib, nb = special.bessel(fn, torch.from_numpy(v).cuda(), torch.from_numpy(z).cuda())
+        assert np.array_equal(a.view(np.uint64), to_np(b).view(np.uint64))
+        assert np.array_equal(ia, to_np(ib)) and np.array_equal(na, to_np(nb))
+    # scalar order broadcast (v_stride = 0) and a ragged length
+    a, _, _ = special.bessel("I", 0.75, z[:12345])
+    b, _, _ = special.bessel("I", np.full(12345, 0.75), z[:12345])
+    assert np.array_equal(a.view(np.uint64), b.view(np.uint64))
+
+
+def test_empty_and_tiny_batches(special):
+    out, ierr, nz = special.bessel("J", 2.5, np.zeros(0, np.complex128))
+    assert out.size == 0
+    out, ierr, nz = special.bessel("J", 2.5, np.array([3 + 4j]))
+    assert abs(out[0] - (3.967307975128131 + 4.355646112647439j)) < 1e-13 * abs(out[0])
+
+
+def test_reference_surface_i0_kv_kve_sinc(special):
+    """special::i0 / kv / kve / sinc with the reference's conventions (mod.rs:8-13, kv.rs:11-41, trig.rs:4-13)."""
+    import scipy.special as sc
+    rng = np.random.default_rng(5)
+    # tests/special.rs:23-46: |i0(x)| vs scipy.special.i0, x in [0,1), epsilon 1e-14
+    for _ in range(20):
+        x = rng.random(rng.integers(2, 100))
+        got = np.abs(special.i0(x))
+        assert np.allclose(got, sc.i0(x), rtol=1e-14, atol=1e-14)
+    x = 30 * rng.random(1000)  # Kaiser-window range (fir_filter_design_windows.rs:247)
+    assert np.allclose(np.abs(special.i0(x)), sc.i0(x), rtol=1e-14, atol=0)
+    # kv.rs doctest: kve(1,1) == kv(1,1) * exp(1) exactly
+    assert special.kve(1.0, 1.0) == special.kv(1.0, 1.0) * np.exp(1.0 + 0j)
+    # kv.rs:51-58 smoke inputs
+    assert special.kv(-3.5, 1000.0) == 0
+    z3 = 1.0 / complex(1.2, 0.3)
+    assert abs(special.kve(3.5, z3) - sc.kve(3.5, z3)) < 5e-13 * abs(sc.kve(3.5, z3))
+    # NaN z is mapped to 0 (kv.rs:12-14) where K is singular -> Err -> unwrap panics (kv.rs:24)
+    with pytest.raises(special.SpecialPanic):
+        special.kv(2.5, complex(np.nan, 0))
+    assert special.kv(np.nan, 1.0) == special.kv(0.0, 1.0)  # NaN v -> 0 (kv.rs:16-18)
+    # first Err in index order wins (mod.rs:11-12)
+    with pytest.raises(special.SpecialError) as e:
+        special.iv(2.5, np.array([1.0, 800.0, 1.0, 900.0], dtype=complex))
+    assert e.value.index == 1 and e.value.code == 2
+    xs = np.concatenate([[0.0], rng.uniform(-20, 20, 1000)])
+    assert np.allclose(special.sinc(xs), np.sinc(xs), rtol=1e-15, atol=1e-17)
+    # besselap poles: kve at half-integer orders in the left half plane (bessel.rs:121-142), 1e-6 in the reference
+    g = helpers.load_golden("bessel_golden.npz")
+    sel = (g["z"].real < 0) & (np.abs(g["v"] % 1 - 0.5) < 1e-12) & (g["v"] < 51)
+    got, ierr, _ = special.bessel("K", g["v"][sel], g["z"][sel], scaled=True)
+    ref = sc.kve(g["v"][sel], g["z"][sel])
+    scale = np.maximum(np.abs(ref), np.pi * np.abs(sc.ive(g["v"][sel], g["z"][sel])))
+    assert np.all(np.abs(got - ref) <= 1e-13 * scale)
+
+
+@pytest.mark.parametrize("kode", [1, 2])
+@pytest.mark.parametrize("which", ["Ai", "Aip", "Bi", "Bip"])
+def test_airy_golden(special, which, kode):
+    g = helpers.load_golden("airy_golden.npz")
+    z = g["z"]
+    want = g[f"{which}_{kode}"]
+    got, ierr, nz = special.airy_raw(which, torch.from_numpy(z).cuda(), scaled=(kode == 2), semantics="scipy")
+    got, ierr = to_np(got), to_np(ierr)
+    w = ("Ai", "Aip", "Bi", "Bip").index(which)
+    cpu, ierr_c, _ = helpers.cpu_airy(w, kode, z)
+    assert np.array_equal(ierr, ierr_c)
+    nanw = np.isnan(want.real)
+    assert np.all(np.isnan(got.real[nanw]))
+    ok = ~nanw & (ierr == 0)
+    zeta = np.abs(2.0 / 3.0 * z * np.sqrt(z))
+    tol = 1e-13 + 4 * so.EPS * zeta
+    comp = g[f"{('Bi', 'Bip', 'Ai', 'Aip')[w]}_{kode}"]
+    scale = np.maximum(np.abs(want), np.where((z.real < 0) & np.isfinite(np.abs(comp)), np.abs(comp), 0))
+    err = so.mismatch(got, want, scale)
+    assert np.all(err[ok] <= tol[ok]), f"{np.max((err - tol)[ok]):.2e}"
+
+
+def test_gamma_family(special):
+    g = helpers.load_golden("gamma_golden.npz")
+    x = g["x"]
+    got = to_np(special.gamma(torch.from_numpy(x).cuda()))
+    want = g["gamma"]
+    with np.errstate(all="ignore"):
+        err = np.abs(got - want) / np.abs(want)
+    err[(got == want) | (np.isnan(got) & np.isnan(want))] = 0
+    assert np.all(err <= 1e-13 + np.where(x < 0, 4 * so.EPS * np.pi * np.abs(x), 0.0))
+    got = special.gammaln(x)  # host pointers
+    want = g["gammaln"]
+    with np.errstate(all="ignore"):
+        err = np.abs(got - want) / np.maximum(np.abs(want), 1.0)
+    err[(got == want) | (np.isnan(got) & np.isnan(want))] = 0
+    assert np.all(err[np.abs(x) >= 1e-300] <= 1e-13)
+    zc = g["zc"]
+    got = to_np(special.loggamma(torch.from_numpy(zc).cuda()))
+    want = g["cloggamma"]
+    d = got - want
+    d = d.real + 1j * np.remainder(d.imag + np.pi, 2 * np.pi) - 1j * np.pi  # modulo 2 pi i (branch bookkeeping)
+    err = np.abs(d) / np.maximum(np.abs(want), 1.0)
+    err[np.isnan(want.real) & np.isnan(got.real)] = 0
+    assert np.all(err <= 1e-13)
+    got = to_np(special.gamma(torch.from_numpy(zc).cuda()))
+    want = g["cgamma"]
+    with np.errstate(all="ignore"):
+        err = np.abs(got - want) / np.abs(want)
+    err[(got == want) | (np.isnan(want.real) & np.isnan(got.real))] = 0
+    bound = 1e-13 + 4 * so.EPS * np.abs(g["cloggamma"])
+    bound[~np.isfinite(bound)] = 1e-13
+    assert np.all(err <= bound)
+
+
+def test_first_error_and_synth(special):
+    ierr = torch.zeros(1 << 20, dtype=torch.int32, device="cuda")
+    assert special.first_error(ierr) == (-1, 0)
+    ierr[777777] = 3
+    ierr[12345] = 2
+    assert special.first_error(ierr) == (12345, 2)
+    v1, z1 = special.synth(3, 1 << 16, n_total=1 << 20, offset=4096, device="cuda:0")
+    v2, z2 = special.synth(3, 1 << 20, n_total=1 << 20, offset=0, device="cuda:0")
+    assert torch.equal(z1, z2[4096:4096 + (1 << 16)]) and torch.equal(v1, v2[4096:4096 + (1 << 16)])
+    assert float(z2.abs().max()) <= 200.0 and float(v2.max()) <= 50.0
+    vh, zh = special.synth(3, 1000, n_total=1 << 20, offset=4096)  # host buffers
+    assert np.array_equal(zh, to_np(z1[:1000]))
+
+
+def test_full_size_cfg2_properties(special):
+    """BASELINE config[1] at full size (4096 x 4096): properties that need no oracle.
+    (a) conjugate symmetry f(conj z) = conj f(z): the grid is symmetric under im -> -im;
+    (b) no element fails; (c) a strided sample agrees with the CPU oracle."""
+    side = 4096
+    n = side * side
+    v, z = special.synth(2, n, n_total=n, device="cuda:0")
+    for fn in ("J", "Y"):
+        out, ierr, nz = special.bessel(fn, 2.5, z)
+        assert special.first_error(ierr) == (-1, 0)
+        grid = out.view(side, side)
+        mirrored = torch.flip(grid, dims=[0]).conj()
+        rel = (grid - mirrored).abs() / grid.abs()
+        assert float(rel.max()) <= 1e-13, float(rel.max())
+        idx = torch.arange(0, n, 4099, device="cuda:0")
+        zs = to_np(z[idx])
+        want, _, _ = helpers.cpu_bessel(fn, 1, 2.5, zs)
+        comp, _, _ = helpers.cpu_bessel("Y" if fn == "J" else "J", 1, 2.5, zs)
+        err = so.mismatch(to_np(out[idx]), want, np.maximum(np.abs(want), np.abs(comp)))
+        assert np.all(err <= 1e-13), err.max()
