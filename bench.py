@@ -234,14 +234,18 @@ def main():
         zh = torch.empty(N_POINTS, dtype=torch.complex128).pin_memory()
         zh.copy_(z)
         zn = zh.numpy()
+        # result buffers in pinned host memory, one set per function (the caller owns all buffers: SURVEY §8b)
+        res = {fn: (torch.empty(N_POINTS, dtype=torch.complex128).pin_memory().numpy(),
+                    torch.empty(N_POINTS, dtype=torch.int32).pin_memory().numpy(),
+                    torch.empty(N_POINTS, dtype=torch.int32).pin_memory().numpy()) for fn in ("J", "Y")}
         special.bessel("J", ORDER, zn[: 1 << 20])  # warm the staging buffers
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
-            oj, ej, nj = special.bessel("J", ORDER, zn)
-            oy, ey, ny = special.bessel("Y", ORDER, zn)
+            oj, ej, nj = special.bessel("J", ORDER, zn, out=res["J"][0], ierr=res["J"][1], nz=res["J"][2])
+            oy, ey, ny = special.bessel("Y", ORDER, zn, out=res["Y"][0], ierr=res["Y"][1], nz=res["Y"][2])
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         if world > 1:

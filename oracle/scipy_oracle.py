@@ -95,14 +95,20 @@ def scale_near_zeros(fn, kode, v, z, want):
     return comp("J", 1.0, z.imag > 0)
 
 
-def tolerance(want, rtol=RTOL):
-    """Per-element bound on the normalised error: `rtol` (1e-13, BASELINE.json north_star) for values on
-    scale; for |f| beyond 1e+-49 the result is exp(x) with |x| > 112 and one rounding of x already moves it by
-    eps*|x|, so the bound grows as 4 eps |ln|f|| ("away from ... overflow" in the north star)."""
+def tolerance(want, z=None, rtol=RTOL):
+    """Per-element bound on the normalised error: `rtol` (1e-13, BASELINE.json north_star) for values on scale
+    and |z| <= 200 (the range of the BASELINE configs).  Two conditioning terms widen it outside that box:
+    * |f| beyond 1e+-49: the result is exp(x) with |x| > 112 and one rounding of x already moves it by eps |x|,
+      so the bound grows as 4 eps |ln|f|| ("away from ... overflow" in the north star);
+    * |z| > 200: the phase of every oscillatory factor is known to eps |z| only, so the bound grows as
+      rtol |z| / 200."""
     with np.errstate(all="ignore"):
         lf = np.abs(np.log(np.abs(want)))
     lf = np.where(np.isfinite(lf), lf, 0.0)
-    return np.maximum(rtol, 4 * EPS * lf)
+    tol = np.maximum(rtol, 4 * EPS * lf)
+    if z is not None:
+        tol = tol * np.maximum(1.0, np.abs(z) / 200.0)
+    return tol
 
 
 def mismatch(got, want, scale=None):

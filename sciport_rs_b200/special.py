@@ -65,11 +65,13 @@ def profile_step(fn):
         _PROFILE_LOG = None
 
 
-def bessel(fn, v, z, scaled=False, semantics="amos", path="binned", real_input=False, devices=None, profile=False):
+def bessel(fn, v, z, scaled=False, semantics="amos", path="binned", real_input=False, devices=None, profile=False,
+           out=None, ierr=None, nz=None):
     """Evaluate one family over a batch.  Returns ``(values, ierr, nz)``.
 
     fn: 'J','Y','I','K','H1','H2'; v: scalar or array broadcast against z; z: complex128 (or float64 with
-    ``real_input=True``, promoted like ``v.into()`` in mod.rs:10).
+    ``real_input=True``, promoted like ``v.into()`` in mod.rs:10).  Host (numpy) calls may pass preallocated
+    ``out`` / ``ierr`` / ``nz`` arrays (pinned memory avoids the per-call page registration).
     """
     kode = 2 if scaled else 1
     flags = (SEM_SCIPY if semantics == "scipy" else SEM_AMOS) | (PATH_MONOLITHIC if path == "monolithic" else 0)
@@ -116,9 +118,12 @@ def bessel(fn, v, z, scaled=False, semantics="amos", path="binned", real_input=F
     else:
         va = np.ascontiguousarray(np.broadcast_to(va, za.shape))
         stride = 1
-    out = np.empty(za.shape, dtype=np.complex128)
-    ierr = np.empty(za.shape, dtype=np.int32)
-    nz = np.empty(za.shape, dtype=np.int32)
+    # caller-provided (e.g. pinned) result buffers are filled in place, like the C ABI
+    out = np.empty(za.shape, dtype=np.complex128) if out is None else out
+    ierr = np.empty(za.shape, dtype=np.int32) if ierr is None else ierr
+    nz = np.empty(za.shape, dtype=np.int32) if nz is None else nz
+    assert out.dtype == np.complex128 and ierr.dtype == np.int32 and nz.dtype == np.int32
+    assert out.size == n and ierr.size == n and nz.size == n and out.flags.c_contiguous
     ex = make_exec(device_ptrs=False, flags=flags, devices=devices)
     f = lib.spb_bessel_real if real_input else lib.spb_bessel
     check(f(FN[fn], kode, va.ctypes.data, stride, za.ctypes.data, out.ctypes.data, ierr.ctypes.data, nz.ctypes.data,
