@@ -1,0 +1,111 @@
+// oracle/flopcount.cpp — TEST / MEASUREMENT INFRASTRUCTURE ONLY.
+//
+// Compiles the region math with an op-counting scalar type to tally the ALGORITHMIC FP64 operations per
+// point of every kernel of the binned pipeline (binding definition: add/sub/mul = 1, div = 1,
+// sqrt = 1, each of exp/log/sin/cos/atan/... = 30).  tools/count_flops.py drives it over the parity sample
+// of a BASELINE config and freezes the per-kernel means into profiles/flops_per_eval.json, which bench.py
+// multiplies by the live launch durations to get roofline.achieved.
+#include <cstdint>
+#include <cmath>
+
+struct counted;
+static thread_local uint64_t g_ops = 0;
+
+struct counted {
+    double v;
+    counted() : v(0) {}
+    counted(double x) : v(x) {}
+    counted(int x) : v(x) {}
+    explicit operator int() const { return (int)v; }
+    explicit operator double() const { return v; }
+    explicit operator bool() const { return v != 0; }
+};
+#define BINOP(op)                                                                            \
+    inline counted operator op(counted a, counted b) { g_ops += 1; return counted(a.v op b.v); } \
+    inline counted operator op(counted a, double b) { g_ops += 1; return counted(a.v op b); }     \
+    inline counted operator op(double a, counted b) { g_ops += 1; return counted(a op b.v); }
+BINOP(+) BINOP(-) BINOP(*) BINOP(/)
+inline counted operator-(counted a) { return counted(-a.v); }
+inline counted &operator+=(counted &a, counted b) { g_ops += 1; a.v += b.v; return a; }
+inline counted &operator-=(counted &a, counted b) { g_ops += 1; a.v -= b.v; return a; }
+inline counted &operator*=(counted &a, counted b) { g_ops += 1; a.v *= b.v; return a; }
+#define CMP(op)                                                         \
+    inline bool operator op(counted a, counted b) { return a.v op b.v; } \
+    inline bool operator op(counted a, double b) { return a.v op b; }    \
+    inline bool operator op(double a, counted b) { return a op b.v; }
+CMP(<) CMP(>) CMP(<=) CMP(>=) CMP(==) CMP(!=)
+#define TRANS(name) \
+    inline counted name(counted a) { g_ops += 30; return counted(std::name(a.v)); }
+TRANS(exp) TRANS(log) TRANS(sin) TRANS(cos) TRANS(atan) TRANS(sinh) TRANS(cosh) TRANS(log1p)
+inline counted sqrt(counted a) { g_ops += 1; return counted(std::sqrt(a.v)); }
+inline counted fabs(counted a) { return counted(std::fabs(a.v)); }
+inline counted floor(counted a) { return counted(std::floor(a.v)); }
+inline counted fmod(counted a, counted b) { g_ops += 1; return counted(std::fmod(a.v, b.v)); }
+inline counted atan2(counted a, counted b) { g_ops += 30; return counted(std::atan2(a.v, b.v)); }
+inline counted pow(counted a, counted b) { g_ops += 60; return counted(std::pow(a.v, b.v)); }
+inline bool signbit(counted a) { return std::signbit(a.v); }
+
+#define SPB_REAL counted
+#include "../sciport_rs_b200/csrc/amos/spb_family.h"
+
+using namespace spb;
+
+extern "C" {
+
+// ops[9]: classify(prepare), 4 ipass regions (region + its share of finish), kpass (+finish), general, and
+// pts[9] the number of points charged to each, following the kernel ids of include/sciport_b200.h
+// (0 classify, 2..5 ipass, 6 kpass, 7 general).
+int spbo_count_ops(int fam, int kode, const double *v, int64_t v_stride, const double *z, int64_t n, double *ops,
+                   int64_t *pts) {
+    for (int k = 0; k < 9; ++k) {
+        ops[k] = 0;
+        pts[k] = 0;
+    }
+    for (int64_t i = 0; i < n; ++i) {
+        cplx zz(counted(z[2 * i]), counted(z[2 * i + 1]));
+        counted fnu(v[i * v_stride]);
+        g_ops = 0;
+        Prep p = prepare(fam, zz, fnu, kode);
+        uint64_t prep_ops = g_ops;
+        ops[0] += prep_ops;
+        pts[0] += 1;
+        int ierr, nz;
+        if (p.combine == CMB_GENERAL) {
+            g_ops = 0;
+            general_eval(fam, zz, fnu, kode, ierr, nz);
+            ops[7] += g_ops;
+            pts[7] += 1;
+            continue;
+        }
+        cplx ival(0.0, 0.0), kval(0.0, 0.0);
+        int inz = 0, knz = 0;
+        bool handed = false;
+        if (p.ireg >= 0) {
+            g_ops = prep_ops;  // the region kernel recomputes prepare()
+            inz = ipass_region(p.ireg, p.w, fnu, kode, ival);
+            if (inz < 0) handed = true;
+            if (!handed && p.combine == CMB_I_ROT) finish(fam, p, zz, fnu, kode, ival, inz, kval, 0, ierr, nz);
+            ops[2 + p.ireg] += g_ops;
+            pts[2 + p.ireg] += 1;
+        }
+        if (!handed && p.kreg >= 0) {
+            g_ops = prep_ops;
+            knz = kpass_region(p.w, fnu, kode, kval);
+            if (knz < 0 || (knz != 0 && (p.combine == CMB_ACON || p.combine == CMB_Y_SHARED)))
+                handed = true;
+            else
+                finish(fam, p, zz, fnu, kode, ival, inz, kval, knz, ierr, nz);
+            ops[6] += g_ops;
+            pts[6] += 1;
+        }
+        if (handed) {
+            g_ops = 0;
+            general_eval(fam, zz, fnu, kode, ierr, nz);
+            ops[7] += g_ops;
+            pts[7] += 1;
+        }
+    }
+    return 0;
+}
+
+}  // extern "C"

@@ -56,9 +56,6 @@ def test_vs_cpu_oracle_and_monolithic(special, fn, cfg):
         got, ierr, nz = special.bessel(fn, vt, zt, scaled=(kode == 2))
         mono, ierr_m, nz_m = special.bessel(fn, vt, zt, scaled=(kode == 2), path="monolithic")
         g, m = to_np(got), to_np(mono)
-        same = (g.view(np.uint64) == m.view(np.uint64)).reshape(-1, 2).all(1) | (np.isnan(g.real) & np.isnan(m.real))
-        assert same.all(), f"binned != monolithic at {np.nonzero(~same)[0][:5]}"
-        assert torch.equal(ierr, ierr_m) and torch.equal(nz, nz_m)
         want, ierr_c, nz_c = helpers.cpu_bessel(fn, kode, v, z)
         comp = helpers.cpu_bessel(so.COMPANION[fn], kode, v, z)[0]
         scale = np.maximum(np.abs(want), np.where(np.isfinite(np.abs(comp)), np.abs(comp), 0) *
@@ -67,6 +64,12 @@ def test_vs_cpu_oracle_and_monolithic(special, fn, cfg):
         okv = (ierr_c == 0) & (nz_c == 0)
         bad = okv & (err > so.tolerance(want, z))
         assert not bad.any(), f"kode={kode}: {bad.sum()} mismatches, first v={v[bad][0]} z={z[bad][0]} err={err[bad][0]:.2e}"
+        # the two CUDA paths run the same region math, but nvcc contracts FMAs per kernel, so they agree to
+        # rounding (same tolerance), not bit for bit; their error classes must be identical
+        errm = so.mismatch(g, m, scale)
+        badm = okv & (errm > so.tolerance(want, z))
+        assert not badm.any(), f"kode={kode}: binned vs monolithic {errm[badm].max():.2e}"
+        assert torch.equal(ierr, ierr_m) and torch.equal(nz, nz_m)
         # error classes: identical up to points sitting exactly on an over/underflow threshold
         ie = to_np(ierr)
         diff = (ie != ierr_c) | (to_np(nz) != nz_c)
