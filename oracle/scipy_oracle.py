@@ -95,19 +95,33 @@ def scale_near_zeros(fn, kode, v, z, want):
     return comp("J", 1.0, z.imag > 0)
 
 
-def tolerance(want, z=None, rtol=RTOL):
-    """Per-element bound on the normalised error: `rtol` (1e-13, BASELINE.json north_star) for values on scale
-    and |z| <= 200 (the range of the BASELINE configs).  Two conditioning terms widen it outside that box:
-    * |f| beyond 1e+-49: the result is exp(x) with |x| > 112 and one rounding of x already moves it by eps |x|,
-      so the bound grows as 4 eps |ln|f|| ("away from ... overflow" in the north star);
-    * |z| > 200: the phase of every oscillatory factor is known to eps |z| only, so the bound grows as
-      rtol |z| / 200."""
+FNUL = 85.92135864716213
+
+
+def uniform_region(v, z):
+    """Points whose value comes from the uniform (Olver) asymptotic expansions: order above fnul, or |z| above
+    fnul where the large-|z| expansion does not apply (2|z| < v^2, v > 1).  There the result is
+    phi * exp(-zeta1 + zeta2) * sum with |zeta| ~ max(|z|, v), so its phase carries eps * max(|z|, v)."""
+    v = np.asarray(v, dtype=np.float64)
+    az = np.abs(z)
+    return (v > FNUL) | ((az > FNUL) & (2 * az < v * v) & (v > 1))
+
+
+def tolerance(want, z=None, v=None, rtol=RTOL):
+    """Per-element bound on the normalised error: `rtol` (1e-13, BASELINE.json north_star) for values on scale.
+    Conditioning terms widen it where one rounding of an exponent / phase already exceeds rtol:
+    * |f| beyond 1e+-49: the result is exp(x), |x| > 112; bound 4 eps |ln|f|| ("away from overflow");
+    * |z| > 200 (outside the BASELINE configs' box): bound rtol |z| / 200;
+    * uniform-asymptotic region (see uniform_region): bound 8 eps max(|z|, v)."""
     with np.errstate(all="ignore"):
         lf = np.abs(np.log(np.abs(want)))
     lf = np.where(np.isfinite(lf), lf, 0.0)
     tol = np.maximum(rtol, 4 * EPS * lf)
     if z is not None:
         tol = tol * np.maximum(1.0, np.abs(z) / 200.0)
+        if v is not None:
+            vv = np.broadcast_to(np.asarray(v, dtype=np.float64), np.shape(z))
+            tol = np.maximum(tol, np.where(uniform_region(vv, z), 8 * EPS * np.maximum(np.abs(z), vv), 0.0))
     return tol
 
 
