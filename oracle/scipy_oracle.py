@@ -122,6 +122,7 @@ def tolerance(want, z=None, v=None, rtol=RTOL):
         if v is not None:
             vv = np.broadcast_to(np.asarray(v, dtype=np.float64), np.shape(z))
             tol = np.maximum(tol, np.where(uniform_region(vv, z), 8 * EPS * np.maximum(np.abs(z), vv), 0.0))
+            tol = np.maximum(tol, 8 * EPS * vv)  # order recurrences accumulate ~v roundings (matters above v = 56)
     return tol
 
 

@@ -117,9 +117,21 @@ SPB_HD cplx csqrt_(cplx a) {
     return cplx(r, a.im < real(0.0) ? -s : s);
 }
 
+// sin and cos of the same argument in one call on the device
+SPB_HD void sincos_(real x, real &s, real &c) {
+#if defined(__CUDA_ARCH__)
+    sincos(x, &s, &c);
+#else
+    s = sin(x);
+    c = cos(x);
+#endif
+}
+
 SPB_HD cplx cexp_(cplx a) {
     real zm = exp(a.re);
-    return cplx(zm * cos(a.im), zm * sin(a.im));
+    real s, c;
+    sincos_(a.im, s, c);
+    return cplx(zm * c, zm * s);
 }
 
 // principal logarithm; ierr=1 for a == 0

@@ -141,15 +141,36 @@ SPB_FN int seri(cplx z, real fnu, int kode, int n, cplx *y, real tol, real elim,
 
 // ---------------------------------------------------------------------------
 // Large-|z| asymptotic expansion.  nz = -1 overflow, -2 no convergence.
+//
+// The term ratio of the Hankel series is (4 v^2 - (2j-1)^2) / (j * 8z); the
+// reciprocal 1/(8z) is formed once and the integer reciprocals 1/j come from a
+// table, so the inner loop is one complex multiply and two real multiplies per
+// term (no division, no modulus).  The second exponential exp(-2z) is below
+// half an ulp of the leading sum once 2 Re z > 80 and is skipped there.
 SPB_FN int asyi(cplx z, real fnu, int kode, int n, cplx *y, real rl, real tol, real elim, real alim) {
+    static const double RJ[48] = {
+        0.0, 1.0, 1.0 / 2, 1.0 / 3, 1.0 / 4, 1.0 / 5, 1.0 / 6, 1.0 / 7, 1.0 / 8, 1.0 / 9, 1.0 / 10, 1.0 / 11,
+        1.0 / 12, 1.0 / 13, 1.0 / 14, 1.0 / 15, 1.0 / 16, 1.0 / 17, 1.0 / 18, 1.0 / 19, 1.0 / 20, 1.0 / 21,
+        1.0 / 22, 1.0 / 23, 1.0 / 24, 1.0 / 25, 1.0 / 26, 1.0 / 27, 1.0 / 28, 1.0 / 29, 1.0 / 30, 1.0 / 31,
+        1.0 / 32, 1.0 / 33, 1.0 / 34, 1.0 / 35, 1.0 / 36, 1.0 / 37, 1.0 / 38, 1.0 / 39, 1.0 / 40, 1.0 / 41,
+        1.0 / 42, 1.0 / 43, 1.0 / 44, 1.0 / 45, 1.0 / 46, 1.0 / 47};
     const real rtpi = 0.159154943091895336;  // 1/(2 pi)
     real az = cabs_(z);
     const real arm = real(1.0e3) * SPB_D1MACH1;
     const real rtr1 = sqrt(arm);
     int il = n < 2 ? n : 2;
     real dfnu = fnu + real(n - il);
-    // leading factor sqrt(1/(2 pi z)) * exp(z)
-    cplx ak1 = csqrt_(crecip(z) * rtpi);
+    // 1/z through the modulus (on scale for any |z| >= rl)
+    real raz = real(1.0) / az;
+    cplx rcz = cplx(z.re * raz, -z.im * raz) * raz;
+    // leading factor sqrt(1/(2 pi z)) * exp(z); Re(1/z) >= 0, modulus known
+    cplx ak1;
+    {
+        cplx a = rcz * rtpi;
+        real d = rtpi * raz;
+        real r = sqrt(real(0.5) * (d + a.re));
+        ak1 = cplx(r, a.im / (r + r));
+    }
     cplx cz = z;
     if (kode == 2) cz.re = 0.0;
     if (rabs(cz.re) > elim) return -1;
@@ -161,40 +182,44 @@ SPB_FN int asyi(cplx z, real fnu, int kode, int n, cplx *y, real rl, real tol, r
     }
     real fdn = 0.0;
     if (dnu2 > rtr1) fdn = dnu2 * dnu2;
-    cplx ez = z * real(8.0);
     // for imaginary z the error test is made relative to the first reciprocal
     // power, the leading term of the imaginary part
     real aez = real(8.0) * az;
+    real raez = real(0.125) * raz;
+    cplx rez = rcz * real(0.125);  // 1/(8z)
     real s = tol / aez;
     int jl = (int)(rl + rl) + 2;
     cplx p1(0.0, 0.0);
+    const bool second = (z.im != real(0.0)) && (z.re + z.re < real(80.0));
+    cplx e2(0.0, 0.0);
     if (z.im != real(0.0)) {
         // exp(i pi (1/2 + fnu + n - il)) with the integer part folded out
         int inu = (int)fnu;
         real arg = (fnu - real(inu)) * SPB_PI;
         inu = inu + n - il;
-        real ak = -sin(arg);
-        real bk = cos(arg);
+        real sn, cs;
+        sincos_(arg, sn, cs);
+        real ak = -sn;
+        real bk = cs;
         if (z.im < real(0.0)) bk = -bk;
         p1 = cplx(ak, bk);
         if (inu % 2 != 0) p1 = -p1;
+        if (second) e2 = cexp_(z * real(-2.0));
     }
     for (int k = 1; k <= il; ++k) {
         real sqk = fdn - real(1.0);
         real atol = s * rabs(sqk);
         real sgn = 1.0;
         cplx cs1(1.0, 0.0), cs2(1.0, 0.0), ck(1.0, 0.0);
-        real ak = 0.0, aa = 1.0, bb = aez;
-        cplx dk = ez;
+        real ak = 0.0, aa = 1.0;
         bool conv = false;
         for (int j = 1; j <= jl; ++j) {
-            ck = cdiv(ck, dk) * sqk;
+            real t = sqk * real(RJ[j]);
+            ck = (ck * rez) * t;
             cs2 = cs2 + ck;
             sgn = -sgn;
             cs1 = cs1 + ck * sgn;
-            dk = dk + ez;
-            aa = aa * rabs(sqk) / bb;
-            bb += aez;
+            aa = aa * (rabs(t) * raez);
             ak += real(8.0);
             sqk -= ak;
             if (aa <= atol) {
@@ -204,10 +229,7 @@ SPB_FN int asyi(cplx z, real fnu, int kode, int n, cplx *y, real rl, real tol, r
         }
         if (!conv) return -2;
         cplx s2 = cs1;
-        if (z.re + z.re < elim) {
-            cplx tz = z * real(-2.0);
-            s2 = s2 + (cexp_(tz) * p1) * cs2;
-        }
+        if (second) s2 = s2 + (e2 * p1) * cs2;
         fdn = fdn + real(8.0) * dfnu + real(4.0);
         p1 = -p1;
         y[n - il + k - 1] = s2 * ak1;
@@ -216,7 +238,7 @@ SPB_FN int asyi(cplx z, real fnu, int kode, int n, cplx *y, real rl, real tol, r
     int nn = n;
     int k = nn - 2;
     real ak = real(k);
-    cplx rz = crecip(z) * real(2.0);
+    cplx rz = rcz * real(2.0);
     for (int i = 3; i <= nn; ++i) {
         y[k - 1] = (rz * y[k]) * (ak + fnu) + y[k + 1];
         ak -= real(1.0);

@@ -32,14 +32,11 @@ __global__ void __launch_bounds__(128) k_monolithic(DevJob job) {
 }
 
 void launch_general(const DevJob &job, const Scratch &s, int sms, cudaStream_t st) {
-    k_general<<<sms * 4, 128, 0, st>>>(job, s);
+    k_general<<<resident_grid(k_general, 128, sms), 128, 0, st>>>(job, s);
 }
 
 void launch_monolithic(const DevJob &job, cudaStream_t st) {
-    long long blocks = (job.n + 127) / 128;
-    if (blocks > 148 * 64) blocks = 148 * 64;
-    if (blocks < 1) blocks = 1;
-    k_monolithic<<<(int)blocks, 128, 0, st>>>(job);
+    k_monolithic<<<resident_grid(k_monolithic, 128, 148), 128, 0, st>>>(job);
 }
 
 }  // namespace spbk

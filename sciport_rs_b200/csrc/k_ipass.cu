@@ -40,13 +40,20 @@ __global__ void __launch_bounds__(128) k_ipass(DevJob job, Scratch s) {
 }
 
 void launch_ipass(const DevJob &job, const Scratch &s, int region, int sms, cudaStream_t st) {
-    // persistent grid: a multiple of the SM count, 128-thread CTAs
-    const int blocks = sms * 8;
+    // persistent grid: SM count x resident CTAs per SM, 128-thread CTAs
     switch (region) {
-        case spb::IREG_SERIES: k_ipass<spb::IREG_SERIES><<<blocks, 128, 0, st>>>(job, s); break;
-        case spb::IREG_ASYI: k_ipass<spb::IREG_ASYI><<<blocks, 128, 0, st>>>(job, s); break;
-        case spb::IREG_MLRI: k_ipass<spb::IREG_MLRI><<<blocks, 128, 0, st>>>(job, s); break;
-        case spb::IREG_WRSK: k_ipass<spb::IREG_WRSK><<<blocks, 128, 0, st>>>(job, s); break;
+        case spb::IREG_SERIES:
+            k_ipass<spb::IREG_SERIES><<<resident_grid(k_ipass<spb::IREG_SERIES>, 128, sms), 128, 0, st>>>(job, s);
+            break;
+        case spb::IREG_ASYI:
+            k_ipass<spb::IREG_ASYI><<<resident_grid(k_ipass<spb::IREG_ASYI>, 128, sms), 128, 0, st>>>(job, s);
+            break;
+        case spb::IREG_MLRI:
+            k_ipass<spb::IREG_MLRI><<<resident_grid(k_ipass<spb::IREG_MLRI>, 128, sms), 128, 0, st>>>(job, s);
+            break;
+        case spb::IREG_WRSK:
+            k_ipass<spb::IREG_WRSK><<<resident_grid(k_ipass<spb::IREG_WRSK>, 128, sms), 128, 0, st>>>(job, s);
+            break;
         default: break;
     }
 }

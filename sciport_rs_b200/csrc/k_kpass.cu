@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(128) k_kpass(DevJob job, Scratch s) {
 }
 
 void launch_kpass(const DevJob &job, const Scratch &s, int sms, cudaStream_t st) {
-    k_kpass<<<sms * 8, 128, 0, st>>>(job, s);
+    k_kpass<<<resident_grid(k_kpass, 128, sms), 128, 0, st>>>(job, s);
 }
 
 }  // namespace spbk

@@ -40,6 +40,23 @@ constexpr int TILE = 2048;  // points per classification tile
 constexpr int BIN_GENERAL = 7;
 constexpr int GLIST_LEN_SLOT = 16;
 
+// Persistent grids are sized to exactly the number of CTAs that are resident at once
+// (SM count x occupancy), so every CTA starts in the first wave and the grid-stride
+// loops finish together.
+template <class Kernel>
+inline int resident_grid(Kernel kernel, int threads, int sms) {
+    static int per_sm[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    if (per_sm[dev] == 0) {
+        int nb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, threads, 0) != cudaSuccess || nb < 1) nb = 1;
+        per_sm[dev] = nb;
+    }
+    return per_sm[dev] * sms;
+}
+
 // kernels.cu
 void launch_classify(const DevJob &job, const Scratch &s, cudaStream_t st);
 void launch_scan_scatter(const DevJob &job, const Scratch &s, cudaStream_t st);
