@@ -117,6 +117,21 @@ SPB_HD cplx csqrt_(cplx a) {
     return cplx(r, a.im < real(0.0) ? -s : s);
 }
 
+// square root of a when its modulus d = |a| is already known
+SPB_HD cplx csqrt_mod(cplx a, real d) {
+    if (a.im == real(0.0)) {
+        if (a.re >= real(0.0)) return cplx(sqrt(a.re), real(0.0));
+        return cplx(real(0.0), sqrt(-a.re));
+    }
+    if (a.re > real(0.0)) {
+        real r = sqrt(real(0.5) * (d + a.re));
+        return cplx(r, a.im / (r + r));
+    }
+    real s = sqrt(real(0.5) * (d - a.re));
+    real r = rabs(a.im) / (s + s);
+    return cplx(r, a.im < real(0.0) ? -s : s);
+}
+
 // sin and cos of the same argument in one call on the device
 SPB_HD void sincos_(real x, real &s, real &c) {
 #if defined(__CUDA_ARCH__)

@@ -21,6 +21,32 @@ namespace spb {
 #define SPB_RANGE_IK 1073741823.5
 #define SPB_RANGE_JYH 2251799813685248.0 /* 0.5/tol */
 
+// Phase factors that depend on the order only: one sincos per point serves every rotation of the
+// combine step (half-angle for the J / Hankel rotations, full angle by the double-angle formulas for
+// the I / continuation factors).
+struct OrderPhase {
+    real ch, sh;  // cos, sin of (pi/2) (fnu - (inu - ir)),  ir = inu mod 2
+    real cp, sp;  // cos, sin of pi (fnu - inu)
+    int inu;
+};
+
+SPB_HD OrderPhase order_phase(real fnu) {
+    OrderPhase ph;
+    ph.inu = (int)fnu;
+    int ir = ph.inu & 1;
+    real a = (fnu - real(ph.inu - ir)) * real(SPB_HPI);
+    sincos_(a, ph.sh, ph.ch);
+    real c2 = ph.ch * ph.ch - ph.sh * ph.sh;
+    real s2 = (ph.sh + ph.sh) * ph.ch;
+    if (ir) {
+        c2 = -c2;
+        s2 = -s2;
+    }
+    ph.cp = c2;
+    ph.sp = s2;
+    return ph;
+}
+
 // K(fnu, zn e^{i pi mr}) = e^{-i pi mr fnu} K(fnu, zn) - i pi mr I(fnu, zn)
 SPB_FN int acon(cplx z, real fnu, int kode, int mr, int n, cplx *y, real rl, real fnul, real tol,
                 real elim, real alim) {
@@ -41,13 +67,14 @@ SPB_FN int acon(cplx z, real fnu, int kode, int mr, int n, cplx *y, real rl, rea
     cplx csgn(0.0, sgn);
     if (kode != 1) {
         real yy = -zn.im;
-        csgn = csgn * cplx(cos(yy), sin(yy));
+        real sn, cs;
+        sincos_(yy, sn, cs);
+        csgn = csgn * cplx(cs, sn);
     }
-    // cspn = exp(i pi fnu) with the integer part folded out
-    int inu = (int)fnu;
-    real arg = (fnu - real(inu)) * sgn;
-    cplx cspn(cos(arg), sin(arg));
-    if (inu % 2 != 0) cspn = -cspn;
+    // cspn = exp(i sgn fnu) with the integer part folded out
+    const OrderPhase ph = order_phase(fnu);
+    cplx cspn(ph.cp, (fmr < real(0.0)) ? ph.sp : -ph.sp);
+    if (ph.inu % 2 != 0) cspn = -cspn;
     int iuf = 0;
     cplx c1 = s1;
     cplx c2 = y[0];
@@ -164,12 +191,10 @@ SPB_FN int besi(cplx z, real fnu, int kode, int n, cplx *cy, int &ierr) {
     cplx csgn(1.0, 0.0);
     if (z.re < real(0.0)) {
         zn = -z;
-        // csgn = exp(i pi fnu) with the integer part folded out
-        int inu = (int)fnu;
-        real arg = (fnu - real(inu)) * SPB_PI;
-        if (z.im < real(0.0)) arg = -arg;
-        csgn = cplx(cos(arg), sin(arg));
-        if (inu % 2 != 0) csgn = -csgn;
+        // csgn = exp(+-i pi fnu) with the integer part folded out
+        const OrderPhase ph = order_phase(fnu);
+        csgn = cplx(ph.cp, (z.im < real(0.0)) ? -ph.sp : ph.sp);
+        if (ph.inu % 2 != 0) csgn = -csgn;
     }
     nz = binu(zn, fnu, kode, n, cy, rl, fnul, tol, elim, alim);
     if (nz < 0) {
@@ -210,12 +235,9 @@ SPB_FN int besj(cplx z, real fnu, int kode, int n, cplx *cy, int &ierr) {
     if (az > aa || fn > aa) ierr = 3;
     // csgn = exp(i fnu pi/2) with the integer part folded out
     real cii = 1.0;
-    int inu = (int)fnu;
-    int inuh = inu / 2;
-    int ir = inu - 2 * inuh;
-    real arg = (fnu - real(inu - ir)) * hpi;
-    cplx csgn(cos(arg), sin(arg));
-    if (inuh % 2 == 1) csgn = -csgn;
+    const OrderPhase ph = order_phase(fnu);
+    cplx csgn(ph.ch, ph.sh);
+    if ((ph.inu / 2) % 2 == 1) csgn = -csgn;
     // zn = -i z is in the right half plane for Im z >= 0
     cplx zn(z.im, -z.re);
     if (z.im < real(0.0)) {
@@ -419,14 +441,10 @@ SPB_FN int besh(cplx z, real fnu, int kode, int m, int n, cplx *cy, int &ierr) {
         }
     }
     // H(m,fnu,z) = -fmm (i/hpi) zt^fnu K(fnu, -z zt), zt = exp(-fmm hpi i)
-    real sgn = (-fmm < real(0.0)) ? -hpi : hpi;
-    int inu = (int)fnu;
-    int inuh = inu / 2;
-    int ir = inu - 2 * inuh;
-    real arg = (fnu - real(inu - ir)) * sgn;
-    real rhpi = real(1.0) / sgn;
-    cplx csgn(-rhpi * sin(arg), rhpi * cos(arg));
-    if (inuh % 2 == 1) csgn = -csgn;
+    const real tpi = 0.63661977236758134308;  // 2/pi
+    const OrderPhase ph = order_phase(fnu);
+    cplx csgn(-tpi * ph.sh, (m == 1) ? -tpi * ph.ch : tpi * ph.ch);
+    if ((ph.inu / 2) % 2 == 1) csgn = -csgn;
     real zti = -fmm;
     real rtol = real(1.0) / tol;
     real ascle = ufl * rtol;
@@ -467,7 +485,8 @@ SPB_FN int besy(cplx z, real fnu, int kode, cplx *cy, int &ierr) {
         cy[0] = cplx(-d.im * hci, d.re * hci);
         return nz;
     }
-    real exr = cos(z.re), exi = sin(z.re);
+    real exr, exi;
+    sincos_(z.re, exi, exr);
     real ey = 0.0;
     real tay = rabs(z.im + z.im);
     if (tay < elim) ey = exp(-tay);

@@ -51,6 +51,11 @@ struct Prep {
 // Conservative bound on |Re(-zeta1 + zeta2 -+ w)| of the leading uniform term for
 // order gnu at w: if it stays below alim, uoik() returns 0 without touching y.
 SPB_HD bool uoik_is_noop(real az, real gnu, real alim) {
+    // cheap sufficient test first (covers small orders at moderate |z| without a division or logarithm):
+    // for 2^-20 <= t = az/gnu <= 2^20, ln(1 + 2/t + t) < 15.3
+    if (az >= gnu * real(9.5367431640625e-07) && az <= gnu * real(1048576.0) &&
+        gnu * real(19.5) + az + az < alim)
+        return true;
     real t = az / gnu;
     real b = gnu * (log(real(1.0) + real(2.0) / t + t) + real(SPB_PI) + real(1.0)) + az + az;
     return b < alim;
@@ -186,19 +191,20 @@ SPB_FN int kpass_region(cplx w, real fnu, int kode, cplx &val) {
 }
 
 // continuation K(w e^{i pi mr}) from (K(w), I(w)) for one member (acon with n = 1)
-SPB_FN cplx acon_combine(cplx w, real fnu, int kode, int mr, cplx kval, cplx ival, int &nz) {
+SPB_FN cplx acon_combine(cplx w, const OrderPhase &ph, int kode, int mr, cplx kval, cplx ival, int &nz) {
     const real tol = SPB_TOL, alim = SPB_ALIM, pi = SPB_PI;
     nz = 0;
     real sgn = (mr < 0) ? pi : -pi;
     cplx csgn(0.0, sgn);
     if (kode != 1) {
         real yy = -w.im;
-        csgn = csgn * cplx(cos(yy), sin(yy));
+        real sn, cs;
+        sincos_(yy, sn, cs);
+        csgn = csgn * cplx(cs, sn);
     }
-    int inu = (int)fnu;
-    real arg = (fnu - real(inu)) * sgn;
-    cplx cspn(cos(arg), sin(arg));
-    if (inu % 2 != 0) cspn = -cspn;
+    // cspn = exp(i sgn (fnu - inu)) (-1)^inu
+    cplx cspn(ph.cp, (mr < 0) ? ph.sp : -ph.sp);
+    if (ph.inu % 2 != 0) cspn = -cspn;
     cplx c1 = kval, c2 = ival;
     if (kode != 1) {
         int iuf = 0;
@@ -208,19 +214,13 @@ SPB_FN cplx acon_combine(cplx w, real fnu, int kode, int mr, cplx kval, cplx iva
     return cspn * c1 + csgn * c2;
 }
 
-// rotation applied by the Hankel driver after K (or its continuation)
-SPB_FN cplx hankel_rotate(int m, real fnu, cplx y) {
-    const real tol = SPB_TOL, hpi = SPB_HPI;
-    int mm = 3 - m - m;
-    real fmm = real(mm);
-    real sgn = (-fmm < real(0.0)) ? -hpi : hpi;
-    int inu = (int)fnu;
-    int inuh = inu / 2;
-    int ir = inu - 2 * inuh;
-    real arg = (fnu - real(inu - ir)) * sgn;
-    real rhpi = real(1.0) / sgn;
-    cplx csgn(-rhpi * sin(arg), rhpi * cos(arg));
-    if (inuh % 2 == 1) csgn = -csgn;
+// rotation applied by the Hankel driver after K (or its continuation):
+// H(m) = -+ (2i/pi) exp(-+ i fnu pi/2) K
+SPB_FN cplx hankel_rotate(int m, const OrderPhase &ph, cplx y) {
+    const real tol = SPB_TOL;
+    const real tpi = 0.63661977236758134308;  // 2/pi
+    cplx csgn(-tpi * ph.sh, (m == 1) ? -tpi * ph.ch : tpi * ph.ch);
+    if ((ph.inu / 2) % 2 == 1) csgn = -csgn;
     real rtol = real(1.0) / tol;
     real ascle = SPB_D1MACH1 * real(1.0e3) * rtol;
     return rot_guard(y, csgn, rtol, ascle, tol);
@@ -233,7 +233,8 @@ SPB_FN cplx y_from_hankels(cplx z, int kode, cplx h1, cplx h2, int nz1, int nz2,
         cplx d = h2 - h1;
         return cplx(-d.im * hci, d.re * hci);
     }
-    real exr = cos(z.re), exi = sin(z.re);
+    real exr, exi;
+    sincos_(z.re, exi, exr);
     real ey = 0.0;
     real tay = rabs(z.im + z.im);
     if (tay < elim) ey = exp(-tay);
@@ -267,31 +268,26 @@ SPB_FN cplx finish(int fam, const Prep &p, cplx z, real fnu, int kode, cplx ival
     if (p.combine == CMB_I_ROT) {
         nz = inz;
         if (nz != 0) return cplx(0.0, 0.0);
+        if (fam == FAM_I && !(z.re < real(0.0))) return ival;
+        const OrderPhase ph = order_phase(fnu);
         if (fam == FAM_I) {
-            if (!(z.re < real(0.0))) return ival;
-            int inu = (int)fnu;
-            real arg = (fnu - real(inu)) * real(SPB_PI);
-            if (z.im < real(0.0)) arg = -arg;
-            cplx csgn(cos(arg), sin(arg));
-            if (inu % 2 != 0) csgn = -csgn;
+            // csgn = exp(+-i pi fnu)
+            cplx csgn(ph.cp, (z.im < real(0.0)) ? -ph.sp : ph.sp);
+            if (ph.inu % 2 != 0) csgn = -csgn;
             return rot_guard(ival, csgn, rtol, ascle, tol);
         }
-        int inu = (int)fnu;
-        int inuh = inu / 2;
-        int ir = inu - 2 * inuh;
-        real arg = (fnu - real(inu - ir)) * real(SPB_HPI);
-        cplx csgn(cos(arg), sin(arg));
-        if (inuh % 2 == 1) csgn = -csgn;
+        // csgn = exp(+-i fnu pi/2)
+        cplx csgn(ph.ch, ph.sh);
+        if ((ph.inu / 2) % 2 == 1) csgn = -csgn;
         if (z.im < real(0.0)) csgn.im = -csgn.im;
         return rot_guard(ival, csgn, rtol, ascle, tol);
     }
-    if (fam == FAM_K) {
-        if (p.combine == CMB_K_ROT) {
-            nz = knz;
-            return kval;
-        }
-        return acon_combine(p.w, fnu, kode, p.mr, kval, ival, nz);
+    if (fam == FAM_K && p.combine == CMB_K_ROT) {
+        nz = knz;
+        return kval;
     }
+    const OrderPhase ph = order_phase(fnu);
+    if (fam == FAM_K) return acon_combine(p.w, ph, kode, p.mr, kval, ival, nz);
     if (fam == FAM_H1 || fam == FAM_H2) {
         int m = (fam == FAM_H1) ? 1 : 2;
         cplx y;
@@ -299,9 +295,9 @@ SPB_FN cplx finish(int fam, const Prep &p, cplx z, real fnu, int kode, cplx ival
             nz = knz;
             y = kval;
         } else {
-            y = acon_combine(p.w, fnu, kode, p.mr, kval, ival, nz);
+            y = acon_combine(p.w, ph, kode, p.mr, kval, ival, nz);
         }
-        return hankel_rotate(m, fnu, y);
+        return hankel_rotate(m, ph, y);
     }
     // FAM_Y
     cplx h1, h2;
@@ -309,19 +305,19 @@ SPB_FN cplx finish(int fam, const Prep &p, cplx z, real fnu, int kode, cplx ival
     if (p.combine == CMB_Y_CONJ) {
         // H1 from K(w), w = (0,-x); H2 from K(conj w) = conj K(w)
         nz1 = nz2 = knz;
-        h1 = hankel_rotate(1, fnu, kval);
-        h2 = hankel_rotate(2, fnu, conj(kval));
+        h1 = hankel_rotate(1, ph, kval);
+        h2 = hankel_rotate(2, ph, conj(kval));
     } else if (p.mr == -1) {
         // H1 continued (mr = -mm = -1), H2 direct
-        cplx yc = acon_combine(p.w, fnu, kode, -1, kval, ival, nz1);
-        h1 = hankel_rotate(1, fnu, yc);
+        cplx yc = acon_combine(p.w, ph, kode, -1, kval, ival, nz1);
+        h1 = hankel_rotate(1, ph, yc);
         nz2 = knz;
-        h2 = hankel_rotate(2, fnu, kval);
+        h2 = hankel_rotate(2, ph, kval);
     } else {
         nz1 = knz;
-        h1 = hankel_rotate(1, fnu, kval);
-        cplx yc = acon_combine(p.w, fnu, kode, 1, kval, ival, nz2);
-        h2 = hankel_rotate(2, fnu, yc);
+        h1 = hankel_rotate(1, ph, kval);
+        cplx yc = acon_combine(p.w, ph, kode, 1, kval, ival, nz2);
+        h2 = hankel_rotate(2, ph, yc);
     }
     return y_from_hankels(z, kode, h1, h2, nz1, nz2, nz);
 }

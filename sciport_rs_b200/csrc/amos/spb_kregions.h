@@ -154,7 +154,8 @@ SPB_FN int bknu(cplx z, real fnu, int kode, int n, cplx *y, real tol, real elim,
     int nz = 0;
     int iflag = 0;
     int koded = kode;
-    cplx rz = crecip(z) * real(2.0);
+    real rcaz = real(1.0) / caz;
+    cplx rz = cplx(z.re * rcaz, -z.im * rcaz) * (rcaz + rcaz);
     int inu = (int)(fnu + real(0.5));
     real dnu = fnu - real(inu);
     real dnu2 = 0.0;
@@ -265,7 +266,8 @@ SPB_FN int bknu(cplx z, real fnu, int kode, int n, cplx *y, real tol, real elim,
     if (miller) {
         // iflag=1: an underflow of exp(-z) is anticipated; proceed as kode=2 and test for
         // on-scale values during the forward recurrence
-        coef = cdiv(cplx(rthpi, 0.0), csqrt_(z));
+        // rthpi / sqrt(z) = rthpi conj(sqrt z) / |z|
+        coef = conj(csqrt_mod(z, caz)) * (rthpi * rcaz);
         kflag = 2;
         if (koded != 2) {
             if (z.re > alim) {
@@ -274,7 +276,9 @@ SPB_FN int bknu(cplx z, real fnu, int kode, int n, cplx *y, real tol, real elim,
                 kflag = 2;
             } else {
                 real str = exp(-z.re) * cssr[kflag - 1];
-                cplx st(str * cos(z.im), -str * sin(z.im));
+                real sn, cs;
+                sincos_(z.im, sn, cs);
+                cplx st(str * cs, -str * sn);
                 coef = coef * st;
             }
         }

@@ -36,15 +36,23 @@ __global__ void __launch_bounds__(256) k_classify(DevJob job, Scratch s) {
         unsigned char c;
         if (p.combine == spb::CMB_GENERAL) {
             c = (unsigned char)(7 | (3 << 3) | (1 << 5));
-            atomicAdd(&hist[BIN_GENERAL], 1u);
         } else {
             int bi = p.ireg >= 0 ? p.ireg : 7;
             int bk = p.kreg >= 0 ? p.kreg : 3;
             c = (unsigned char)(bi | (bk << 3));
-            if (bi != 7) atomicAdd(&hist[bi], 1u);
-            if (bk != 3) atomicAdd(&hist[4 + bk], 1u);
         }
         s.cls[i] = c;
+        // warp-aggregated histogram: one shared atomic per (warp, bin present) instead of one per thread
+        const unsigned int act = __activemask();
+        int bi, bk;
+        bool gen;
+        point_bins(c, bi, bk, gen);
+#pragma unroll
+        for (int b = 0; b < NBINS; ++b) {
+            bool in = (b < 4) ? (bi == b) : (b < 7) ? (bk == b - 4) : gen;
+            unsigned int m = __ballot_sync(act, in);
+            if (m != 0 && (threadIdx.x & 31) == (__ffs(act) - 1)) atomicAdd(&hist[b], (unsigned int)__popc(m));
+        }
     }
     __syncthreads();
     if (threadIdx.x < NBINS) s.blockcnt[(size_t)threadIdx.x * s.nblocks + blockIdx.x] = hist[threadIdx.x];
