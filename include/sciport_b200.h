@@ -100,7 +100,8 @@ typedef struct spb_exec {
     int n_devices;      /* 0 or 1: one device; >1: slice [i*n/G,(i+1)*n/G) per device (host pointers only) */
     const int *devices; /* device ordinals, NULL = 0..n_devices-1 (or the current device)                  */
     int device_ptrs;    /* 0: all buffers are host memory (pinned or pageable); 1: device memory on devices[0] */
-    void *stream;       /* cudaStream_t to enqueue on when device_ptrs = 1 (NULL = default stream)         */
+    void *stream;       /* cudaStream_t to enqueue on when device_ptrs = 1 (NULL = default stream); such calls
+                           only ENQUEUE work and return: synchronise the stream before reading results      */
     int flags;          /* spb_flags, OR-ed                                                                */
 } spb_exec;
 
@@ -141,7 +142,8 @@ int spb_synth(int cfg, uint64_t seed, int64_t offset, int64_t n, int64_t n_total
 /* sustained DFMA throughput of `device` in TFLOP/s (register-resident, 8 independent chains/thread) */
 int spb_fp64_peak(int device, double seconds, double *tflops, double *sm_mhz);
 /* device time (ms) spent in kernels of the last spb_* compute call on this thread, measured with
- * CUDA events on the launching stream, and how many kernels it launched */
+ * CUDA events on the launching stream (asking for kernel_ms waits for that call to finish; pass NULL
+ * to only read the launch count), and how many kernels it launched */
 int spb_last_timing(double *kernel_ms, int *launches);
 /* per-kernel records of the last spb_bessel call made with SPB_PROFILE on this thread: returns the number of
  * records written (<= max_records); points = elements the launch processed */

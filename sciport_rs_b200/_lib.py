@@ -88,10 +88,11 @@ def make_exec(device_ptrs=False, stream=0, flags=0, devices=None):
     return ex
 
 
-def last_timing():
+def last_timing(want_ms=True):
+    """(kernel_ms, launches) of the last compute call on this thread; want_ms=False does not synchronise."""
     ms = ctypes.c_double()
     n = ctypes.c_int()
-    lib.spb_last_timing(ctypes.byref(ms), ctypes.byref(n))
+    lib.spb_last_timing(ctypes.byref(ms) if want_ms else None, ctypes.byref(n))
     return ms.value, n.value
 
 

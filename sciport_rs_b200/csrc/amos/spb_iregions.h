@@ -278,8 +278,10 @@ SPB_FN int mlri(cplx z, real fnu, int kode, int n, cplx *y, real tol) {
         p2 = p1 - ck * pt;
         p1 = pt;
         ck = ck + rz;
-        real ap = cabs_(p2);
-        if (ap > tst * ak * ak) {
+        // |p2| > tst ak^2 compared on the squares (magnitudes stay below 1e25 here): no modulus per step
+        real ap2 = p2.re * p2.re + p2.im * p2.im;
+        real th = tst * ak * ak;
+        if (ap2 > th * th) {
             found = true;
             break;
         }
@@ -303,12 +305,13 @@ SPB_FN int mlri(cplx z, real fnu, int kode, int n, cplx *y, real tol) {
             p2 = p1 - ck * pt;
             p1 = pt;
             ck = ck + rz;
-            real ap = cabs_(p2);
-            if (ap < tst) continue;
+            real ap2 = p2.re * p2.re + p2.im * p2.im;
+            if (ap2 < tst * tst) continue;
             if (itime == 2) {
                 found = true;
                 break;
             }
+            real ap = sqrt(ap2);
             ack = cabs_(ck);
             real flam = ack + sqrt(ack * ack - real(1.0));
             real fkap = ap / cabs_(p1);

@@ -25,6 +25,8 @@ namespace {
 thread_local std::string g_err;
 thread_local double g_last_ms = 0.0;
 thread_local int g_last_launches = 0;
+// device-pointer calls are asynchronous: their events are resolved when the timing is asked for
+thread_local cudaEvent_t g_pending_ev0 = nullptr, g_pending_ev1 = nullptr;
 
 int fail(int code, const std::string &msg) {
     g_err = msg;
@@ -303,10 +305,10 @@ int run_device(DeviceCtx *c, const BesselArgs &a, cudaStream_t st, double *ms_ou
     }
     CK(cudaEventRecord(c->ev1, st));
     CK(cudaGetLastError());
-    CK(cudaEventSynchronize(c->ev1));
-    float ms = 0.f;
-    CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
-    if (ms_out) *ms_out = ms;
+    // no host synchronisation: the call returns as soon as the launches are queued on the caller's stream
+    g_pending_ev0 = c->ev0;
+    g_pending_ev1 = c->ev1;
+    if (ms_out) *ms_out = 0.0;
     if (launches_out) *launches_out = launches;
     return SPB_OK;
 }
@@ -429,6 +431,7 @@ int bessel_impl(int fn, int kode, const double *v, int64_t v_stride, const spb_c
     if (rc != SPB_OK) return rc;
     g_last_ms = 0.0;
     g_last_launches = 0;
+    g_pending_ev0 = g_pending_ev1 = nullptr;
     if (n == 0) return SPB_OK;
     BesselArgs a{fn, kode, v, v_stride, (const double2 *)z, x, (double2 *)out, ierr, nz, n, flags};
     if (dptr) return run_device(get_ctx(devs[0]), a, st, &g_last_ms, &g_last_launches);
@@ -693,6 +696,13 @@ int spb_last_profile(int max_records, int *kernel_ids, double *ms, int64_t *poin
 }
 
 int spb_last_timing(double *kernel_ms, int *launches) {
+    if (kernel_ms && g_pending_ev1) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(g_pending_ev1) == cudaSuccess &&
+            cudaEventElapsedTime(&ms, g_pending_ev0, g_pending_ev1) == cudaSuccess)
+            g_last_ms = ms;
+        g_pending_ev0 = g_pending_ev1 = nullptr;
+    }
     if (kernel_ms) *kernel_ms = g_last_ms;
     if (launches) *launches = g_last_launches;
     return SPB_OK;

@@ -1,57 +1,75 @@
-// k_pipeline.cu — region classification and warp-aggregated STABLE compaction.
+// k_pipeline.cu — region classification and STABLE compaction by algorithm region.
 //
-//   k_classify : one thread per point; computes spb::prepare() (family rotation,
-//                I region, K region, simple/general), writes a 1-byte class and a
-//                per-tile histogram of the 8 bins.
+//   k_classify : one thread per point (coalesced 16-byte loads); computes
+//                spb::prepare() (family rotation, I region, K region,
+//                simple/general), writes a 1-byte class and a per-tile histogram
+//                of the 8 bins.  Counts are kept as eight 16-bit fields packed in
+//                two 64-bit registers and reduced with warp shuffles, so the
+//                histogram costs 10 shuffles + 16 shared atomics per warp.
 //   k_scan     : exclusive scan of the [bin][tile] histogram (bin-major) so that
 //                every (bin, tile) pair knows where its points start.
-//   k_scatter  : re-reads the class bytes of a tile and writes each point's index
-//                to its bin segment; the rank inside the tile comes from warp
-//                ballots + a per-warp prefix in shared memory, so indices stay in
-//                ascending order inside a bin (stable => region kernels read and
-//                write z / out in ascending, mostly contiguous order).
+//   k_scatter  : each thread re-reads the class bytes of 8 CONSECUTIVE points with
+//                one 8-byte load, a block-wide exclusive scan of the packed counts
+//                gives every thread its start offset in each bin, and the point
+//                indices are written in ascending order (stable => region kernels
+//                read z and write results in ascending, mostly contiguous order).
 #include "spb_dev.cuh"
 
 namespace spbk {
 
-__device__ __forceinline__ void point_bins(unsigned char c, int &bi, int &bk, bool &gen) {
+__device__ __forceinline__ void point_bins(unsigned int c, int &bi, int &bk, bool &gen) {
     gen = (c >> 5) & 1;
-    bi = c & 7;          // 0..3, 7 = none
-    bk = (c >> 3) & 3;   // 0..2, 3 = none
+    bi = c & 7;         // 0..3, 7 = none
+    bk = (c >> 3) & 3;  // 0..2, 3 = none
+}
+
+// packed 16-bit counters: lo holds bins 0..3 (I regions), hi holds bins 4..7 (K regions, general)
+__device__ __forceinline__ void packed_add(unsigned int c, unsigned long long &lo, unsigned long long &hi) {
+    int bi, bk;
+    bool gen;
+    point_bins(c, bi, bk, gen);
+    if (bi != 7) lo += 1ull << (16 * bi);
+    if (bk != 3) hi += 1ull << (16 * bk);
+    if (gen) hi += 1ull << 48;
 }
 
 __global__ void __launch_bounds__(256) k_classify(DevJob job, Scratch s) {
     __shared__ unsigned int hist[NBINS];
     if (threadIdx.x < NBINS) hist[threadIdx.x] = 0;
     __syncthreads();
-    long long base = (long long)blockIdx.x * TILE;
-#pragma unroll 1
-    for (int k = threadIdx.x; k < TILE; k += blockDim.x) {
+    const long long base = (long long)blockIdx.x * TILE;
+    unsigned long long lo = 0, hi = 0;
+#pragma unroll 2
+    for (int k = threadIdx.x; k < TILE; k += 256) {
         long long i = base + k;
-        if (i >= job.n) break;
-        cplx z;
-        double v;
-        load_point(job, i, z, v);
-        spb::Prep p = spb::prepare(job.fam, z, v, job.kode);
-        unsigned char c;
-        if (p.combine == spb::CMB_GENERAL) {
-            c = (unsigned char)(7 | (3 << 3) | (1 << 5));
-        } else {
-            int bi = p.ireg >= 0 ? p.ireg : 7;
-            int bk = p.kreg >= 0 ? p.kreg : 3;
-            c = (unsigned char)(bi | (bk << 3));
+        if (i < job.n) {
+            cplx z;
+            double v;
+            load_point(job, i, z, v);
+            spb::Prep p = spb::prepare(job.fam, z, v, job.kode);
+            unsigned int c;
+            if (p.combine == spb::CMB_GENERAL) {
+                c = 7u | (3u << 3) | (1u << 5);
+            } else {
+                unsigned int bi = p.ireg >= 0 ? (unsigned int)p.ireg : 7u;
+                unsigned int bk = p.kreg >= 0 ? (unsigned int)p.kreg : 3u;
+                c = bi | (bk << 3);
+            }
+            s.cls[i] = (unsigned char)c;
+            packed_add(c, lo, hi);
         }
-        s.cls[i] = c;
-        // warp-aggregated histogram: one shared atomic per (warp, bin present) instead of one per thread
-        const unsigned int act = __activemask();
-        int bi, bk;
-        bool gen;
-        point_bins(c, bi, bk, gen);
+    }
 #pragma unroll
-        for (int b = 0; b < NBINS; ++b) {
-            bool in = (b < 4) ? (bi == b) : (b < 7) ? (bk == b - 4) : gen;
-            unsigned int m = __ballot_sync(act, in);
-            if (m != 0 && (threadIdx.x & 31) == (__ffs(act) - 1)) atomicAdd(&hist[b], (unsigned int)__popc(m));
+    for (int d = 16; d > 0; d >>= 1) {
+        lo += __shfl_xor_sync(0xffffffffu, lo, d);
+        hi += __shfl_xor_sync(0xffffffffu, hi, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            unsigned int a = (unsigned int)((lo >> (16 * b)) & 0xffffu), h = (unsigned int)((hi >> (16 * b)) & 0xffffu);
+            if (a) atomicAdd(&hist[b], a);
+            if (h) atomicAdd(&hist[4 + b], h);
         }
     }
     __syncthreads();
@@ -108,68 +126,72 @@ __global__ void __launch_bounds__(1024) k_scan(Scratch s) {
 }
 
 __global__ void __launch_bounds__(256) k_scatter(DevJob job, Scratch s) {
-    // ranks[b]: running count of bin b inside this tile
-    __shared__ unsigned int running[NBINS];
-    __shared__ unsigned int warp_cnt[8][NBINS];
-    if (threadIdx.x < NBINS) running[threadIdx.x] = 0;
-    __syncthreads();
+    __shared__ unsigned long long warp_lo[8], warp_hi[8];
+    __shared__ unsigned int tile_base[NBINS];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const long long base = (long long)blockIdx.x * TILE;
-    const unsigned int i_base = s.bins[0];              // = 0
-    const unsigned int k_base = s.bins[4];              // start of K bins in scan order
-    const unsigned int g_base = s.bins[BIN_GENERAL];    // start of the general bin in scan order
-#pragma unroll 1
-    for (int k0 = 0; k0 < TILE; k0 += 256) {
-        long long i = base + k0 + threadIdx.x;
-        bool valid = i < job.n;
-        int bi = 7, bk = 3;
-        bool gen = false;
-        if (valid) point_bins(s.cls[i], bi, bk, gen);
-        // per-warp rank for every bin via ballots
-        unsigned int my_rank_i = 0, my_rank_k = 0, my_rank_g = 0;
+    const long long base = (long long)blockIdx.x * TILE + (long long)threadIdx.x * 8;
+    if (threadIdx.x < NBINS) {
+        // where this tile's points of bin b start inside the bin's perm array
+        unsigned int seg = threadIdx.x < 4 ? s.bins[0] : threadIdx.x < 7 ? s.bins[4] : s.bins[BIN_GENERAL];
+        tile_base[threadIdx.x] = s.blockcnt[(size_t)threadIdx.x * s.nblocks + blockIdx.x] - seg;
+    }
+    // class bytes of 8 consecutive points in one load (tiles are 2048-aligned, so 8-byte aligned)
+    unsigned long long cls8 = 0;
+    int valid = 0;
+    if (base + 8 <= job.n) {
+        cls8 = *reinterpret_cast<const unsigned long long *>(s.cls + base);
+        valid = 8;
+    } else if (base < job.n) {
+        valid = (int)(job.n - base);
+        for (int k = 0; k < valid; ++k) cls8 |= (unsigned long long)s.cls[base + k] << (8 * k);
+    }
+    unsigned long long lo = 0, hi = 0;
 #pragma unroll
-        for (int b = 0; b < NBINS; ++b) {
-            bool in = valid && ((b < 4) ? (bi == b) : (b < 7) ? (bk == b - 4) : gen);
-            unsigned int m = __ballot_sync(0xffffffffu, in);
-            unsigned int r = __popc(m & ((1u << lane) - 1u));
-            if (in) {
-                if (b < 4) my_rank_i = r;
-                else if (b < 7) my_rank_k = r;
-                else my_rank_g = r;
-            }
-            if (lane == 0) warp_cnt[wid][b] = __popc(m);
+    for (int k = 0; k < 8; ++k)
+        if (k < valid) packed_add((unsigned int)((cls8 >> (8 * k)) & 0xffu), lo, hi);
+    // block-wide exclusive scan of the packed counters (fields never exceed 2048)
+    unsigned long long ilo = lo, ihi = hi;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        unsigned long long a = __shfl_up_sync(0xffffffffu, ilo, d);
+        unsigned long long b = __shfl_up_sync(0xffffffffu, ihi, d);
+        if (lane >= d) {
+            ilo += a;
+            ihi += b;
         }
-        __syncthreads();
-        // exclusive prefix over the 8 warps (tiny: done redundantly by every thread that needs it)
-        if (valid) {
-            if (bi != 7) {
-                unsigned int off = running[bi];
-                for (int w = 0; w < wid; ++w) off += warp_cnt[w][bi];
-                unsigned int dst = s.blockcnt[(size_t)bi * s.nblocks + blockIdx.x] - i_base + off + my_rank_i;
-                s.perm_i[dst] = (unsigned int)i;
-            }
-            if (bk != 3) {
-                int b = 4 + bk;
-                unsigned int off = running[b];
-                for (int w = 0; w < wid; ++w) off += warp_cnt[w][b];
-                unsigned int dst = s.blockcnt[(size_t)b * s.nblocks + blockIdx.x] - k_base + off + my_rank_k;
-                s.perm_k[dst] = (unsigned int)i;
-            }
-            if (gen) {
-                unsigned int off = running[BIN_GENERAL];
-                for (int w = 0; w < wid; ++w) off += warp_cnt[w][BIN_GENERAL];
-                unsigned int dst =
-                    s.blockcnt[(size_t)BIN_GENERAL * s.nblocks + blockIdx.x] - g_base + off + my_rank_g;
-                s.glist[dst] = (unsigned int)i;
-            }
+    }
+    if (lane == 31) {
+        warp_lo[wid] = ilo;
+        warp_hi[wid] = ihi;
+    }
+    __syncthreads();
+    unsigned long long olo = ilo - lo, ohi = ihi - hi;
+    for (int w = 0; w < wid; ++w) {
+        olo += warp_lo[w];
+        ohi += warp_hi[w];
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        if (k >= valid) break;
+        int bi, bk;
+        bool gen;
+        point_bins((unsigned int)((cls8 >> (8 * k)) & 0xffu), bi, bk, gen);
+        const unsigned int idx = (unsigned int)(base + k);
+        if (bi != 7) {
+            unsigned int off = (unsigned int)((olo >> (16 * bi)) & 0xffffu);
+            s.perm_i[tile_base[bi] + off] = idx;
+            olo += 1ull << (16 * bi);
         }
-        __syncthreads();
-        if (threadIdx.x < NBINS) {
-            unsigned int t = 0;
-            for (int w = 0; w < 8; ++w) t += warp_cnt[w][threadIdx.x];
-            running[threadIdx.x] += t;
+        if (bk != 3) {
+            unsigned int off = (unsigned int)((ohi >> (16 * bk)) & 0xffffu);
+            s.perm_k[tile_base[4 + bk] + off] = idx;
+            ohi += 1ull << (16 * bk);
         }
-        __syncthreads();
+        if (gen) {
+            unsigned int off = (unsigned int)((ohi >> 48) & 0xffffu);
+            s.glist[tile_base[BIN_GENERAL] + off] = idx;
+            ohi += 1ull << 48;
+        }
     }
 }
 
