@@ -222,6 +222,7 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
+    launches_timed = launches[0]
     if rank == 0 and len(sampler.lines) - n_before < 2:
         # very short timed region: keep the GPU busy a little longer so that at least two samples are under load
         t_busy = time.time()
@@ -252,7 +253,7 @@ def main():
         res = {fn: (torch.empty(N_POINTS, dtype=torch.complex128).pin_memory().numpy(),
                     torch.empty(N_POINTS, dtype=torch.int32).pin_memory().numpy(),
                     torch.empty(N_POINTS, dtype=torch.int32).pin_memory().numpy()) for fn in ("J", "Y")}
-        special.bessel("J", ORDER, zn[: 1 << 20])  # warm the staging buffers
+        special.bessel("J", ORDER, zn, out=res["J"][0], ierr=res["J"][1], nz=res["J"][2])  # warm the staging buffers
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -317,7 +318,7 @@ def main():
         "config": {"workload": WORKLOAD, "points_per_gpu": N_POINTS, "order": ORDER,
                    "l2": "inputs+outputs per step 1.1 GB >> 126 MB L2 (no flush needed)",
                    "timing": "CUDA events on the launching stream, max over ranks", "path": "binned"},
-        "clocks": clocks, "e2e": e2e, "gpu_launches": launches[0],
+        "clocks": clocks, "e2e": e2e, "gpu_launches": launches_timed,
         "kernel_ms_per_step": sum(r["ms"] for r in prof) if prof else None, "fp64_peak_tflops": fp64_peak,
         "roofline": roofline, "cpu_baseline": cpu_baseline,
     }

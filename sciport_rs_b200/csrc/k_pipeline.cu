@@ -80,45 +80,43 @@ __global__ void __launch_bounds__(256) k_classify(DevJob job, Scratch s) {
 // records where each bin starts inside its own perm array.
 __global__ void __launch_bounds__(1024) k_scan(Scratch s) {
     __shared__ unsigned int warp_tot[32];
-    __shared__ unsigned int carry;
     __shared__ unsigned int bin_start[NBINS + 1];
     const int total = NBINS * s.nblocks;
-    if (threadIdx.x == 0) carry = 0;
+    // every thread owns a contiguous run of counters: serial sum, one block scan, serial write-back
+    const int per = (total + 1023) / 1024;
+    const int lo = min((int)threadIdx.x * per, total), hi = min(lo + per, total);
+    unsigned int sum = 0;
+    for (int i = lo; i < hi; ++i) sum += s.blockcnt[i];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned int incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        unsigned int y = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += y;
+    }
+    if (lane == 31) warp_tot[wid] = incl;
     __syncthreads();
-    for (int base = 0; base < total; base += 1024) {
-        int idx = base + threadIdx.x;
-        unsigned int x = idx < total ? s.blockcnt[idx] : 0u;
-        unsigned int incl = x;
-        int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (wid == 0) {
+        unsigned int w = warp_tot[lane];
+        unsigned int wi = w;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            unsigned int y = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += y;
+            unsigned int y = __shfl_up_sync(0xffffffffu, wi, d);
+            if (lane >= d) wi += y;
         }
-        if (lane == 31) warp_tot[wid] = incl;
-        __syncthreads();
-        if (wid == 0) {
-            unsigned int w = warp_tot[lane];
-            unsigned int wi = w;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                unsigned int y = __shfl_up_sync(0xffffffffu, wi, d);
-                if (lane >= d) wi += y;
-            }
-            warp_tot[lane] = wi - w;  // exclusive prefix of warp totals
-        }
-        __syncthreads();
-        unsigned int excl = carry + warp_tot[wid] + incl - x;
-        if (idx < total) {
-            s.blockcnt[idx] = excl;
-            if (idx % s.nblocks == 0) bin_start[idx / s.nblocks] = excl;
-        }
-        __syncthreads();
-        if (threadIdx.x == 1023) carry = excl + x;
-        __syncthreads();
+        warp_tot[lane] = wi - w;  // exclusive prefix of warp totals
+        if (lane == 31) bin_start[NBINS] = wi;
     }
+    __syncthreads();
+    unsigned int running = warp_tot[wid] + incl - sum;
+    for (int i = lo; i < hi; ++i) {
+        unsigned int x = s.blockcnt[i];
+        s.blockcnt[i] = running;
+        if (i % s.nblocks == 0) bin_start[i / s.nblocks] = running;
+        running += x;
+    }
+    __syncthreads();
     if (threadIdx.x == 0) {
-        bin_start[NBINS] = carry;
         // absolute starts in the concatenated order: I bins 0..3 | K bins 4..6 | general 7
         for (int b = 0; b <= NBINS; ++b) s.bins[b] = bin_start[b];
         s.bins[GLIST_LEN_SLOT] = bin_start[NBINS] - bin_start[BIN_GENERAL];

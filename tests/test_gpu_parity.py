@@ -57,9 +57,13 @@ def test_vs_cpu_oracle_and_monolithic(special, fn, cfg):
         mono, ierr_m, nz_m = special.bessel(fn, vt, zt, scaled=(kode == 2), path="monolithic")
         g, m = to_np(got), to_np(mono)
         want, ierr_c, nz_c = helpers.cpu_bessel(fn, kode, v, z)
-        comp = helpers.cpu_bessel(so.COMPANION[fn], kode, v, z)[0]
-        scale = np.maximum(np.abs(want), np.where(np.isfinite(np.abs(comp)), np.abs(comp), 0) *
-                           {"J": 1, "Y": 1, "I": 1 / np.pi, "K": np.pi, "H1": 0, "H2": 0}[fn])
+        # absolute bound near zeros: scale by the terms that cancel (same rule as so.scale_near_zeros)
+        cname = {"J": "Y", "Y": "J", "I": "K", "K": "I", "H1": "J", "H2": "J"}[fn]
+        weight = {"J": 1, "Y": 1, "I": 1 / np.pi, "K": np.pi, "H1": 1, "H2": 1}[fn]
+        where = {"J": True, "Y": True, "I": np.abs(z.real) <= 1, "K": z.real < 0, "H1": z.imag < 0,
+                 "H2": z.imag > 0}[fn]
+        comp = np.abs(helpers.cpu_bessel(cname, kode, v, z)[0]) * weight
+        scale = np.maximum(np.abs(want), np.where(np.isfinite(comp) & where, comp, 0))
         err = so.mismatch(g, want, scale)
         okv = (ierr_c == 0) & (nz_c == 0)
         bad = okv & (err > so.tolerance(want, z, v))
