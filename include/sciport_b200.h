@@ -41,7 +41,9 @@ enum spb_fn {
     SPB_FN_I = 2,  /* I_v(z)   — replaces bessel_i, mod.rs:10 */
     SPB_FN_K = 3,  /* K_v(z)   — replaces bessel_k, kv.rs:19  */
     SPB_FN_H1 = 4, /* H^(1)_v(z)                              */
-    SPB_FN_H2 = 5  /* H^(2)_v(z)                              */
+    SPB_FN_H2 = 5, /* H^(2)_v(z)                              */
+    SPB_FN_JY = 6  /* J_v and Y_v together (spb_bessel_jy only): both need I_v at the same rotated point,
+                      so the pair costs one I pass + one K pass instead of two + one */
 };
 
 /* kode: 1 = unscaled (kv), 2 = exponentially scaled (kve; I,J,Y: e^{-|Re z|} resp. e^{-|Im z|};
@@ -111,6 +113,10 @@ typedef struct spb_exec {
  * ierr / nz may be NULL.  nz = number of members set to zero by underflow. */
 int spb_bessel(int fn, int kode, const double *v, int64_t v_stride, const spb_c128 *z, spb_c128 *out,
                int32_t *ierr, int32_t *nz, int64_t n, int n_orders, const spb_exec *ex);
+
+/* J_v(z_i) and Y_v(z_i) in one pass (n_orders = 1).  Results equal spb_bessel(SPB_FN_J) / spb_bessel(SPB_FN_Y). */
+int spb_bessel_jy(int kode, const double *v, int64_t v_stride, const spb_c128 *z, spb_c128 *out_j, spb_c128 *out_y,
+                  int32_t *ierr_j, int32_t *ierr_y, int32_t *nz_j, int32_t *nz_y, int64_t n, const spb_exec *ex);
 
 /* same with real arguments promoted to complex, the shape of special::i0 (mod.rs:8-13: `v.into()`) */
 int spb_bessel_real(int fn, int kode, const double *v, int64_t v_stride, const double *x, spb_c128 *out,

@@ -94,6 +94,27 @@ int spbo_bessel_pipeline(int fn, int kode, const double *v, int64_t v_stride, co
     return 0;
 }
 
+// J and Y together through the FAM_JY flow (out_j, out_y as re,im pairs)
+int spbo_bessel_jy_pipeline(int kode, const double *v, int64_t v_stride, const double *z, double *out_j, double *out_y,
+                            int32_t *codes /* [4][n]: ierr_j, ierr_y, nz_j, nz_y */, int64_t n, int threads) {
+    parallel_for(n, threads, [=](int64_t lo, int64_t hi) {
+        for (int64_t i = lo; i < hi; ++i) {
+            cplx jv, yv;
+            int je, jn, ye, yn, pth;
+            pipeline_eval_jy(cplx(z[2 * i], z[2 * i + 1]), v[i * v_stride], kode, jv, je, jn, yv, ye, yn, pth);
+            out_j[2 * i] = jv.re;
+            out_j[2 * i + 1] = jv.im;
+            out_y[2 * i] = yv.re;
+            out_y[2 * i + 1] = yv.im;
+            codes[i] = je;
+            codes[n + i] = ye;
+            codes[2 * n + i] = jn;
+            codes[3 * n + i] = yn;
+        }
+    });
+    return 0;
+}
+
 // which: 0 Ai, 1 Ai', 2 Bi, 3 Bi'
 int spbo_airy(int which, int kode, const double *z, double *out, int32_t *ierr, int32_t *nz, int64_t n,
               int threads) {

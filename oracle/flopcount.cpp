@@ -70,6 +70,35 @@ int spbo_count_ops(int fam, int kode, const double *v, int64_t v_stride, const d
         ops[0] += prep_ops;
         pts[0] += 1;
         int ierr, nz;
+        if (fam == FAM_JY) {
+            // pair family: I pass charged to its region kernel, K pass + both finishes to kpass
+            bool general = (p.combine == CMB_GENERAL);
+            cplx iv(0.0, 0.0), kv(0.0, 0.0), jv, yv;
+            int inz = 0, knz = 0, e2, n2;
+            if (!general) {
+                g_ops = prep_ops;
+                inz = ipass_region(p.ireg, p.w, fnu, kode, iv);
+                ops[2 + p.ireg] += g_ops;
+                pts[2 + p.ireg] += 1;
+                if (inz < 0) general = true;
+            }
+            if (!general) {
+                g_ops = prep_ops;
+                knz = kpass_region(p.w, fnu, kode, kv);
+                if (knz < 0 || (knz != 0 && p.combine == CMB_Y_SHARED)) general = true;
+                else finish_jy(p, zz, fnu, kode, iv, inz, kv, knz, jv, ierr, nz, yv, e2, n2);
+                ops[6] += g_ops;
+                pts[6] += 1;
+            }
+            if (general) {
+                g_ops = 0;
+                general_eval(FAM_J, zz, fnu, kode, ierr, nz);
+                general_eval(FAM_Y, zz, fnu, kode, ierr, nz);
+                ops[7] += g_ops;
+                pts[7] += 1;
+            }
+            continue;
+        }
         if (p.combine == CMB_GENERAL) {
             g_ops = 0;
             general_eval(fam, zz, fnu, kode, ierr, nz);

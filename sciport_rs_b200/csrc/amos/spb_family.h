@@ -23,7 +23,8 @@
 
 namespace spb {
 
-enum Family { FAM_J = 0, FAM_Y = 1, FAM_I = 2, FAM_K = 3, FAM_H1 = 4, FAM_H2 = 5 };
+// FAM_JY evaluates J and Y together: both need I_v at the same right-half-plane point, so the I pass is shared.
+enum Family { FAM_J = 0, FAM_Y = 1, FAM_I = 2, FAM_K = 3, FAM_H1 = 4, FAM_H2 = 5, FAM_JY = 6 };
 
 // how finish() combines the pass results
 enum Combine {
@@ -134,7 +135,7 @@ SPB_FN Prep prepare(int fam, cplx z, real fnu, int kode) {
         p.w = left ? -zn : zn;
         p.mr = -mm;
         p.combine = left ? CMB_ACON : CMB_K_ROT;
-    } else {  // FAM_Y
+    } else {  // FAM_Y, FAM_JY
         // H1 uses zn1 = -i z, H2 uses zn2 = +i z = -zn1
         cplx zn1(z.im, -z.re);
         if (z.im == real(0.0) && z.re > real(0.0)) {
@@ -151,6 +152,7 @@ SPB_FN Prep prepare(int fam, cplx z, real fnu, int kode) {
         }
     }
     p.kreg = kregion(p.w, fnu);
+    if (fam == FAM_JY) left = true;  // J needs I(w) even where Y alone would not (positive real axis)
     if (left) {
         bool simple;
         p.ireg = iregion_simple(p.w, fnu, az, simple);
@@ -256,6 +258,17 @@ SPB_FN cplx y_from_hankels(cplx z, int kode, cplx h1, cplx h2, int nz1, int nz2,
     return cplx(-st.im * hci, st.re * hci);
 }
 
+// J from I(w): the rotation of the J driver (shared by finish() and finish_jy()).
+SPB_HD cplx j_from_i(cplx z, const OrderPhase &ph, cplx ival) {
+    const real tol = SPB_TOL;
+    real rtol = real(1.0) / tol;
+    real ascle = SPB_D1MACH1 * rtol * real(1.0e3);
+    cplx csgn(ph.ch, ph.sh);
+    if ((ph.inu / 2) % 2 == 1) csgn = -csgn;
+    if (z.im < real(0.0)) csgn.im = -csgn.im;
+    return rot_guard(ival, csgn, rtol, ascle, tol);
+}
+
 // Combine pass results into the family value.  inz/knz are the nz codes of the
 // passes (>= 0).  Sets ierr/nz like the per-point drivers.
 SPB_FN cplx finish(int fam, const Prep &p, cplx z, real fnu, int kode, cplx ival, int inz, cplx kval, int knz,
@@ -277,10 +290,7 @@ SPB_FN cplx finish(int fam, const Prep &p, cplx z, real fnu, int kode, cplx ival
             return rot_guard(ival, csgn, rtol, ascle, tol);
         }
         // csgn = exp(+-i fnu pi/2)
-        cplx csgn(ph.ch, ph.sh);
-        if ((ph.inu / 2) % 2 == 1) csgn = -csgn;
-        if (z.im < real(0.0)) csgn.im = -csgn.im;
-        return rot_guard(ival, csgn, rtol, ascle, tol);
+        return j_from_i(z, ph, ival);
     }
     if (fam == FAM_K && p.combine == CMB_K_ROT) {
         nz = knz;
@@ -320,6 +330,34 @@ SPB_FN cplx finish(int fam, const Prep &p, cplx z, real fnu, int kode, cplx ival
         h2 = hankel_rotate(2, ph, yc);
     }
     return y_from_hankels(z, kode, h1, h2, nz1, nz2, nz);
+}
+
+// J and Y from one (I(w), K(w)) pair.  Same arithmetic as finish(FAM_J) and finish(FAM_Y).
+SPB_FN void finish_jy(const Prep &p, cplx z, real fnu, int kode, cplx ival, int inz, cplx kval, int knz, cplx &jv,
+                      int &jerr, int &jnz, cplx &yv, int &yerr, int &ynz) {
+    const OrderPhase ph = order_phase(fnu);
+    jerr = p.ierr;
+    yerr = p.ierr;
+    jnz = inz;
+    jv = (inz != 0) ? cplx(0.0, 0.0) : j_from_i(z, ph, ival);
+    cplx h1, h2;
+    int nz1 = 0, nz2 = 0;
+    if (p.combine == CMB_Y_CONJ) {
+        nz1 = nz2 = knz;
+        h1 = hankel_rotate(1, ph, kval);
+        h2 = hankel_rotate(2, ph, conj(kval));
+    } else if (p.mr == -1) {
+        cplx yc = acon_combine(p.w, ph, kode, -1, kval, ival, nz1);
+        h1 = hankel_rotate(1, ph, yc);
+        nz2 = knz;
+        h2 = hankel_rotate(2, ph, kval);
+    } else {
+        nz1 = knz;
+        h1 = hankel_rotate(1, ph, kval);
+        cplx yc = acon_combine(p.w, ph, kode, 1, kval, ival, nz2);
+        h2 = hankel_rotate(2, ph, yc);
+    }
+    yv = y_from_hankels(z, kode, h1, h2, nz1, nz2, ynz);
 }
 
 // The general per-point path (same routine on CPU checker and GPU).
@@ -409,6 +447,32 @@ SPB_FN cplx pipeline_eval(int fam, cplx z, real fnu, int kode, int &ierr, int &n
     }
     path = 0;
     return finish(fam, p, z, fnu, kode, ival, inz, kval, knz, ierr, nz);
+}
+
+// J and Y together, in the order the GPU runs the FAM_JY pipeline.
+SPB_FN void pipeline_eval_jy(cplx z, real fnu, int kode, cplx &jv, int &jerr, int &jnz, cplx &yv, int &yerr,
+                             int &ynz, int &path) {
+    Prep p = prepare(FAM_JY, z, fnu, kode);
+    path = 1;
+    cplx ival(0.0, 0.0), kval(0.0, 0.0);
+    int inz = 0, knz = 0;
+    bool general = (p.combine == CMB_GENERAL);
+    if (!general) {
+        path = 2;
+        inz = ipass_region(p.ireg, p.w, fnu, kode, ival);
+        if (inz < 0) general = true;
+    }
+    if (!general) {
+        knz = kpass_region(p.w, fnu, kode, kval);
+        if (knz < 0 || (knz != 0 && p.combine == CMB_Y_SHARED)) general = true;
+    }
+    if (general) {
+        jv = general_eval(FAM_J, z, fnu, kode, jerr, jnz);
+        yv = general_eval(FAM_Y, z, fnu, kode, yerr, ynz);
+        return;
+    }
+    path = 0;
+    finish_jy(p, z, fnu, kode, ival, inz, kval, knz, jv, jerr, jnz, yv, yerr, ynz);
 }
 
 }  // namespace spb

@@ -56,6 +56,9 @@ struct StageSet {  // device staging for host-pointer mode
     double2 *out = nullptr;
     int *ierr = nullptr;
     int *nz = nullptr;
+    double2 *out2 = nullptr;
+    int *ierr2 = nullptr;
+    int *nz2 = nullptr;
     long long cap = 0;
     long long cap_out = 0;
 };
@@ -138,6 +141,7 @@ int ensure_scratch(ScratchSet &ss, long long n) {
     ss.s.blockcnt = (unsigned int *)(base + o_bc);
     ss.s.bins = (unsigned int *)(base + o_bins);
     ss.s.nblocks = (int)((n + TILE - 1) / TILE);
+    cudaMemset(ss.s.bins, 0, 32 * 4);  // counters of the scan's last-CTA hand-off start at zero
     return SPB_OK;
 }
 
@@ -179,7 +183,7 @@ int enqueue_chunk(const DevJob &job, ScratchSet &ss, int sms, int flags, cudaStr
     p.mark(SPB_K_SCAN_SCATTER, st);
     launch_scan_scatter(job, ss.s, st);
     launches += 3;
-    const bool ktype = !(job.fam == SPB_FN_J || job.fam == SPB_FN_I);
+    const bool ktype = !(job.fam == SPB_FN_J || job.fam == SPB_FN_I);  // K, H1, H2, Y and the JY pair
     for (int r = 0; r < 4; ++r) {
         p.mark(SPB_K_IPASS_SERIES + r, st);
         launch_ipass(job, ss.s, r, sms, st);
@@ -257,6 +261,9 @@ struct BesselArgs {
     int *nz;
     long long n;
     int flags;
+    double2 *out2 = nullptr;  // pair families
+    int *ierr2 = nullptr;
+    int *nz2 = nullptr;
 };
 
 // data resident on the device: chunk over the batch on the caller's stream
@@ -283,6 +290,9 @@ int run_device(DeviceCtx *c, const BesselArgs &a, cudaStream_t st, double *ms_ou
         job.out = a.out + off;
         job.ierr = a.ierr ? a.ierr + off : nullptr;
         job.nz = a.nz ? a.nz + off : nullptr;
+        job.out2 = a.out2 ? a.out2 + off : nullptr;
+        job.ierr2 = a.ierr2 ? a.ierr2 + off : nullptr;
+        job.nz2 = a.nz2 ? a.nz2 + off : nullptr;
         job.n = m;
         launches += enqueue_chunk(job, c->scratch[0], c->sms, a.flags, st, &prof);
         if (prof.on) {
@@ -321,10 +331,15 @@ int ensure_stage(StageSet &s, long long n, bool real_in, bool per_elem_v, bool w
         cudaFree(s.out);
         cudaFree(s.ierr);
         cudaFree(s.nz);
+        cudaFree(s.out2);
+        cudaFree(s.ierr2);
+        cudaFree(s.nz2);
         s = StageSet();
         if (cudaMalloc(&s.z, n * 16) != cudaSuccess || cudaMalloc(&s.x, n * 8) != cudaSuccess ||
             cudaMalloc(&s.v, n * 8) != cudaSuccess || cudaMalloc(&s.out, n * 16) != cudaSuccess ||
-            cudaMalloc(&s.ierr, n * 4) != cudaSuccess || cudaMalloc(&s.nz, n * 4) != cudaSuccess) {
+            cudaMalloc(&s.ierr, n * 4) != cudaSuccess || cudaMalloc(&s.nz, n * 4) != cudaSuccess ||
+            cudaMalloc(&s.out2, n * 16) != cudaSuccess || cudaMalloc(&s.ierr2, n * 4) != cudaSuccess ||
+            cudaMalloc(&s.nz2, n * 4) != cudaSuccess) {
             cudaGetLastError();
             return fail(SPB_E_ALLOC, "cudaMalloc of staging buffers failed");
         }
@@ -369,6 +384,10 @@ int run_host_slice(DeviceCtx *c, const BesselArgs &a, double *ms_out, int *launc
     po.pin(a.out, a.n * 16);
     if (a.ierr) pe.pin(a.ierr, a.n * 4);
     if (a.nz) pn.pin(a.nz, a.n * 4);
+    Pin po2, pe2, pn2;
+    if (a.out2) po2.pin(a.out2, a.n * 16);
+    if (a.ierr2) pe2.pin(a.ierr2, a.n * 4);
+    if (a.nz2) pn2.pin(a.nz2, a.n * 4);
     int launches = 0;
     int k = 0;
     double v0 = a.v[0];
@@ -401,11 +420,17 @@ int run_host_slice(DeviceCtx *c, const BesselArgs &a, double *ms_out, int *launc
         job.out = s.out;
         job.ierr = a.ierr ? s.ierr : nullptr;
         job.nz = a.nz ? s.nz : nullptr;
+        job.out2 = a.out2 ? s.out2 : nullptr;
+        job.ierr2 = a.ierr2 ? s.ierr2 : nullptr;
+        job.nz2 = a.nz2 ? s.nz2 : nullptr;
         job.n = m;
         launches += enqueue_chunk(job, c->scratch[b], c->sms, a.flags, st);
         CK(cudaMemcpyAsync(a.out + off, s.out, m * 16, cudaMemcpyDeviceToHost, st));
         if (a.ierr) CK(cudaMemcpyAsync(a.ierr + off, s.ierr, m * 4, cudaMemcpyDeviceToHost, st));
         if (a.nz) CK(cudaMemcpyAsync(a.nz + off, s.nz, m * 4, cudaMemcpyDeviceToHost, st));
+        if (a.out2) CK(cudaMemcpyAsync(a.out2 + off, s.out2, m * 16, cudaMemcpyDeviceToHost, st));
+        if (a.ierr2) CK(cudaMemcpyAsync(a.ierr2 + off, s.ierr2, m * 4, cudaMemcpyDeviceToHost, st));
+        if (a.nz2) CK(cudaMemcpyAsync(a.nz2 + off, s.nz2, m * 4, cudaMemcpyDeviceToHost, st));
         // the staging set of this stream is reused two chunks later: stream order protects it
     }
     CK(cudaStreamSynchronize(c->streams[0]));
@@ -417,8 +442,10 @@ int run_host_slice(DeviceCtx *c, const BesselArgs &a, double *ms_out, int *launc
 }
 
 int bessel_impl(int fn, int kode, const double *v, int64_t v_stride, const spb_c128 *z, const double *x,
-                spb_c128 *out, int32_t *ierr, int32_t *nz, int64_t n, int n_orders, const spb_exec *ex) {
-    if (fn < SPB_FN_J || fn > SPB_FN_H2) return fail(SPB_E_ARG, "unknown function selector");
+                spb_c128 *out, int32_t *ierr, int32_t *nz, int64_t n, int n_orders, const spb_exec *ex,
+                spb_c128 *out2 = nullptr, int32_t *ierr2 = nullptr, int32_t *nz2 = nullptr) {
+    if (fn < SPB_FN_J || fn > SPB_FN_JY) return fail(SPB_E_ARG, "unknown function selector");
+    if ((fn == SPB_FN_JY) != (out2 != nullptr) && n > 0) return fail(SPB_E_ARG, "pair family needs two result buffers");
     if (kode != 1 && kode != 2) return fail(SPB_E_ARG, "kode must be 1 or 2");
     if (n < 0 || v_stride < 0) return fail(SPB_E_ARG, "negative n or v_stride");
     if (n_orders != 1) return fail(SPB_E_ARG, "n_orders != 1: use spb_bessel_seq");
@@ -434,6 +461,9 @@ int bessel_impl(int fn, int kode, const double *v, int64_t v_stride, const spb_c
     g_pending_ev0 = g_pending_ev1 = nullptr;
     if (n == 0) return SPB_OK;
     BesselArgs a{fn, kode, v, v_stride, (const double2 *)z, x, (double2 *)out, ierr, nz, n, flags};
+    a.out2 = (double2 *)out2;
+    a.ierr2 = ierr2;
+    a.nz2 = nz2;
     if (dptr) return run_device(get_ctx(devs[0]), a, st, &g_last_ms, &g_last_launches);
     const int G = (int)devs.size();
     if (G == 1) return run_host_slice(get_ctx(devs[0]), a, &g_last_ms, &g_last_launches);
@@ -451,6 +481,9 @@ int bessel_impl(int fn, int kode, const double *v, int64_t v_stride, const spb_c
             s.out = a.out + lo;
             s.ierr = a.ierr ? a.ierr + lo : nullptr;
             s.nz = a.nz ? a.nz + lo : nullptr;
+            s.out2 = a.out2 ? a.out2 + lo : nullptr;
+            s.ierr2 = a.ierr2 ? a.ierr2 + lo : nullptr;
+            s.nz2 = a.nz2 ? a.nz2 + lo : nullptr;
             s.n = hi - lo;
             if (s.n > 0) rcs[g] = run_host_slice(get_ctx(devs[g]), s, nullptr, &ls[g]);
             errs[g] = g_err;
@@ -518,6 +551,12 @@ extern "C" {
 int spb_bessel(int fn, int kode, const double *v, int64_t v_stride, const spb_c128 *z, spb_c128 *out, int32_t *ierr,
                int32_t *nz, int64_t n, int n_orders, const spb_exec *ex) {
     return bessel_impl(fn, kode, v, v_stride, z, nullptr, out, ierr, nz, n, n_orders, ex);
+}
+
+int spb_bessel_jy(int kode, const double *v, int64_t v_stride, const spb_c128 *z, spb_c128 *out_j, spb_c128 *out_y,
+                  int32_t *ierr_j, int32_t *ierr_y, int32_t *nz_j, int32_t *nz_y, int64_t n, const spb_exec *ex) {
+    if (n > 0 && !out_y) return fail(SPB_E_ARG, "null buffer");
+    return bessel_impl(SPB_FN_JY, kode, v, v_stride, z, nullptr, out_j, ierr_j, nz_j, n, 1, ex, out_y, ierr_y, nz_y);
 }
 
 int spb_bessel_real(int fn, int kode, const double *v, int64_t v_stride, const double *x, spb_c128 *out,

@@ -33,6 +33,14 @@ __global__ void __launch_bounds__(128) k_kpass(DevJob job, Scratch s) {
             continue;
         }
         int ierr, nz;
+        if (job.fam == spb::FAM_JY) {
+            cplx jv, yv;
+            int yerr, ynz;
+            spb::finish_jy(p, z, v, job.kode, ival, inz, kval, knz, jv, ierr, nz, yv, yerr, ynz);
+            store_point(job, i, jv, ierr, nz);
+            store_point2(job, i, yv, yerr, ynz);
+            continue;
+        }
         cplx val = spb::finish(job.fam, p, z, v, job.kode, ival, inz, kval, knz, ierr, nz);
         store_point(job, i, val, ierr, nz);
     }

@@ -76,50 +76,70 @@ __global__ void __launch_bounds__(256) k_classify(DevJob job, Scratch s) {
     if (threadIdx.x < NBINS) s.blockcnt[(size_t)threadIdx.x * s.nblocks + blockIdx.x] = hist[threadIdx.x];
 }
 
-// single-block exclusive scan over NBINS*nblocks counters (bin-major); also
-// records where each bin starts inside its own perm array.
+// Exclusive scan of the [bin][tile] histogram: one CTA per bin scans that bin's tile counters (8 consecutive
+// counters per thread, coalesced), so blockcnt[b][t] becomes the offset of tile t inside bin b.  The last CTA to
+// finish turns the bin totals into the bin start offsets (bins[0..8]) and the general-list length.
 __global__ void __launch_bounds__(1024) k_scan(Scratch s) {
     __shared__ unsigned int warp_tot[32];
-    __shared__ unsigned int bin_start[NBINS + 1];
-    const int total = NBINS * s.nblocks;
-    // every thread owns a contiguous run of counters: serial sum, one block scan, serial write-back
-    const int per = (total + 1023) / 1024;
-    const int lo = min((int)threadIdx.x * per, total), hi = min(lo + per, total);
-    unsigned int sum = 0;
-    for (int i = lo; i < hi; ++i) sum += s.blockcnt[i];
+    __shared__ unsigned int carry_s;
+    const int b = blockIdx.x;
+    unsigned int *cnt = s.blockcnt + (size_t)b * s.nblocks;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    unsigned int incl = sum;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        unsigned int y = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += y;
-    }
-    if (lane == 31) warp_tot[wid] = incl;
+    if (threadIdx.x == 0) carry_s = 0;
     __syncthreads();
-    if (wid == 0) {
-        unsigned int w = warp_tot[lane];
-        unsigned int wi = w;
+    for (int base = 0; base < s.nblocks; base += 8192) {
+        const int i0 = base + (int)threadIdx.x * 8;
+        unsigned int x[8];
+        unsigned int sum = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            x[k] = (i0 + k < s.nblocks) ? cnt[i0 + k] : 0u;
+            sum += x[k];
+        }
+        unsigned int incl = sum;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            unsigned int y = __shfl_up_sync(0xffffffffu, wi, d);
-            if (lane >= d) wi += y;
+            unsigned int y = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += y;
         }
-        warp_tot[lane] = wi - w;  // exclusive prefix of warp totals
-        if (lane == 31) bin_start[NBINS] = wi;
+        if (lane == 31) warp_tot[wid] = incl;
+        __syncthreads();
+        const unsigned int carry = carry_s;
+        if (wid == 0) {
+            unsigned int w = warp_tot[lane];
+            unsigned int wi = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                unsigned int y = __shfl_up_sync(0xffffffffu, wi, d);
+                if (lane >= d) wi += y;
+            }
+            warp_tot[lane] = wi - w;  // exclusive prefix of warp totals
+            if (lane == 31) carry_s = carry + wi;
+        }
+        __syncthreads();
+        unsigned int running = carry + warp_tot[wid] + incl - sum;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (i0 + k < s.nblocks) cnt[i0 + k] = running;
+            running += x[k];
+        }
+        __syncthreads();
     }
-    __syncthreads();
-    unsigned int running = warp_tot[wid] + incl - sum;
-    for (int i = lo; i < hi; ++i) {
-        unsigned int x = s.blockcnt[i];
-        s.blockcnt[i] = running;
-        if (i % s.nblocks == 0) bin_start[i / s.nblocks] = running;
-        running += x;
-    }
-    __syncthreads();
     if (threadIdx.x == 0) {
-        // absolute starts in the concatenated order: I bins 0..3 | K bins 4..6 | general 7
-        for (int b = 0; b <= NBINS; ++b) s.bins[b] = bin_start[b];
-        s.bins[GLIST_LEN_SLOT] = bin_start[NBINS] - bin_start[BIN_GENERAL];
+        s.bins[18 + b] = carry_s;  // total of this bin
+        __threadfence();
+        unsigned int done = atomicAdd(&s.bins[17], 1u);
+        if (done == NBINS - 1) {
+            // absolute starts in the concatenated order: I bins 0..3 | K bins 4..6 | general 7
+            unsigned int acc = 0;
+            for (int k = 0; k < NBINS; ++k) {
+                s.bins[k] = acc;
+                acc += ((volatile unsigned int *)s.bins)[18 + k];
+            }
+            s.bins[NBINS] = acc;
+            s.bins[GLIST_LEN_SLOT] = ((volatile unsigned int *)s.bins)[18 + BIN_GENERAL];
+            s.bins[17] = 0;  // re-arm for the next chunk
+        }
     }
 }
 
@@ -131,7 +151,8 @@ __global__ void __launch_bounds__(256) k_scatter(DevJob job, Scratch s) {
     if (threadIdx.x < NBINS) {
         // where this tile's points of bin b start inside the bin's perm array
         unsigned int seg = threadIdx.x < 4 ? s.bins[0] : threadIdx.x < 7 ? s.bins[4] : s.bins[BIN_GENERAL];
-        tile_base[threadIdx.x] = s.blockcnt[(size_t)threadIdx.x * s.nblocks + blockIdx.x] - seg;
+        tile_base[threadIdx.x] =
+            s.bins[threadIdx.x] - seg + s.blockcnt[(size_t)threadIdx.x * s.nblocks + blockIdx.x];
     }
     // class bytes of 8 consecutive points in one load (tiles are 2048-aligned, so 8-byte aligned)
     unsigned long long cls8 = 0;
@@ -198,7 +219,7 @@ void launch_classify(const DevJob &job, const Scratch &s, cudaStream_t st) {
 }
 
 void launch_scan_scatter(const DevJob &job, const Scratch &s, cudaStream_t st) {
-    k_scan<<<1, 1024, 0, st>>>(s);
+    k_scan<<<NBINS, 1024, 0, st>>>(s);
     k_scatter<<<s.nblocks, 256, 0, st>>>(job, s);
 }
 

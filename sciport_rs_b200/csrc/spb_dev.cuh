@@ -24,9 +24,24 @@ __device__ __forceinline__ void store_point(const DevJob &j, long long i, cplx v
     if (j.nz) j.nz[i] = nz;
 }
 
+__device__ __forceinline__ void store_point2(const DevJob &j, long long i, cplx val, int ierr, int nz) {
+    j.out2[i] = make_double2(val.re, val.im);
+    if (j.ierr2) j.ierr2[i] = ierr;
+    if (j.nz2) j.nz2[i] = nz;
+}
+
 // general per-point evaluation + optional oracle-compatible post-processing
 __device__ __forceinline__ void eval_general_store(const DevJob &j, long long i, cplx z, double v) {
     int ierr, nz;
+    if (j.fam == spb::FAM_JY) {
+        cplx a = spb::general_eval(spb::FAM_J, z, v, j.kode, ierr, nz);
+        if (j.sem) a = spb::apply_semantics(spb::FAM_J, z, v, j.kode, a, ierr, nz);
+        store_point(j, i, a, ierr, nz);
+        cplx b = spb::general_eval(spb::FAM_Y, z, v, j.kode, ierr, nz);
+        if (j.sem) b = spb::apply_semantics(spb::FAM_Y, z, v, j.kode, b, ierr, nz);
+        store_point2(j, i, b, ierr, nz);
+        return;
+    }
     cplx val = spb::general_eval(j.fam, z, v, j.kode, ierr, nz);
     if (j.sem) val = spb::apply_semantics(j.fam, z, v, j.kode, val, ierr, nz);
     store_point(j, i, val, ierr, nz);

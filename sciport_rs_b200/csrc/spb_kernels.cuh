@@ -18,6 +18,9 @@ struct DevJob {
     double2 *out;
     int *ierr;  // nullable
     int *nz;    // nullable
+    double2 *out2;  // second result of a pair family (FAM_JY: out = J, out2 = Y)
+    int *ierr2;     // nullable
+    int *nz2;       // nullable
     long long n;  // points in this chunk
 };
 

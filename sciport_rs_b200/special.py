@@ -131,6 +131,54 @@ def bessel(fn, v, z, scaled=False, semantics="amos", path="binned", real_input=F
     return out, ierr, nz
 
 
+def bessel_jy(v, z, scaled=False, semantics="amos", profile=False, outs=None, codes=None):
+    """J_v(z) and Y_v(z) in one pass (spb_bessel_jy): returns ((J, ierr_j, nz_j), (Y, ierr_y, nz_y)).
+    Both functions need I_v at the same rotated point, so the pair shares classification and the I pass."""
+    kode = 2 if scaled else 1
+    flags = (SEM_SCIPY if semantics == "scipy" else SEM_AMOS) | (PROFILE if profile else 0)
+    if _is_torch(z):
+        zc = z.contiguous().to(torch.complex128)
+        n = zc.numel()
+        if _is_torch(v):
+            vt = v.to(device=zc.device, dtype=torch.float64).contiguous()
+            stride = 0 if vt.numel() == 1 else 1
+        else:
+            vt = torch.full((1,), float(v), dtype=torch.float64, device=zc.device)
+            stride = 0
+        outs = [torch.empty(zc.shape, dtype=torch.complex128, device=zc.device) for _ in range(2)]
+        codes = [torch.empty(zc.shape, dtype=torch.int32, device=zc.device) for _ in range(4)]
+        with torch.cuda.device(zc.device):
+            ex = make_exec(device_ptrs=True, stream=_stream_for(zc), flags=flags, devices=[zc.device.index])
+            check(lib.spb_bessel_jy(kode, vt.data_ptr(), stride, zc.data_ptr(), outs[0].data_ptr(), outs[1].data_ptr(),
+                                    codes[0].data_ptr(), codes[1].data_ptr(), codes[2].data_ptr(), codes[3].data_ptr(),
+                                    n, ctypes.byref(ex)))
+        if profile and _PROFILE_LOG is not None:
+            for r in _lib.last_profile():
+                r["name"] = f"JY/{r['name']}"
+                _PROFILE_LOG.append(r)
+        return (outs[0], codes[0], codes[2]), (outs[1], codes[1], codes[3])
+    za = np.ascontiguousarray(z, dtype=np.complex128)
+    va = np.asarray(v, dtype=np.float64)
+    if va.size == 1:
+        va, stride = np.ascontiguousarray(va.reshape(1)), 0
+    else:
+        va, stride = np.ascontiguousarray(np.broadcast_to(va, za.shape)), 1
+    # caller-provided (e.g. pinned) buffers: outs = [J, Y], codes = [ierr_j, ierr_y, nz_j, nz_y]
+    outs = [np.empty(za.shape, np.complex128) for _ in range(2)] if outs is None else outs
+    codes = [np.empty(za.shape, np.int32) for _ in range(4)] if codes is None else codes
+    ex = make_exec(flags=flags)
+    check(lib.spb_bessel_jy(kode, va.ctypes.data, stride, za.ctypes.data, outs[0].ctypes.data, outs[1].ctypes.data,
+                            codes[0].ctypes.data, codes[1].ctypes.data, codes[2].ctypes.data, codes[3].ctypes.data,
+                            za.size, ctypes.byref(ex)))
+    return (outs[0], codes[0], codes[2]), (outs[1], codes[1], codes[3])
+
+
+def jvyv(v, z, scaled=False):
+    """(jv(v, z), yv(v, z)) computed together; raises on the first Err of either."""
+    (j, ej, _), (y, ey, _) = bessel_jy(v, z, scaled=scaled)
+    return _result(j, ej), _result(y, ey)
+
+
 def first_error(ierr):
     """(index, code) of the first non-zero ierr in index order, (-1, 0) if none."""
     idx = ctypes.c_int64()

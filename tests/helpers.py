@@ -25,6 +25,7 @@ def oracle_lib():
         lib.spbo_bessel_sem.argtypes = [I, I, I, P, L, P, P, P, P, L, I]
         lib.spbo_bessel_pipeline.argtypes = [I, I, P, L, P, P, P, P, P, L, I]
         lib.spbo_airy.argtypes = [I, I, P, P, P, P, L, I]
+        lib.spbo_bessel_jy_pipeline.argtypes = [I, P, L, P, P, P, P, L, I]
         lib.spbo_gamma.argtypes = [I, P, P, L]
         lib.spbo_cgamma.argtypes = [I, P, P, L]
         _oracle = lib
@@ -46,6 +47,17 @@ def cpu_bessel(fn, kode, v, z, sem=0, pipeline=False, threads=8):
     lib.spbo_bessel_sem(FN[fn], kode, sem, v.ctypes.data, 1, z.ctypes.data, out.ctypes.data, ierr.ctypes.data,
                         nz.ctypes.data, z.size, threads)
     return out, ierr, nz
+
+
+def cpu_bessel_jy(kode, v, z, threads=8):
+    lib = oracle_lib()
+    z = np.ascontiguousarray(z, dtype=np.complex128)
+    v = np.ascontiguousarray(np.broadcast_to(np.asarray(v, dtype=np.float64), z.shape))
+    oj, oy = np.empty_like(z), np.empty_like(z)
+    codes = np.empty((4, z.size), np.int32)
+    lib.spbo_bessel_jy_pipeline(kode, v.ctypes.data, 1, z.ctypes.data, oj.ctypes.data, oy.ctypes.data, codes.ctypes.data,
+                                z.size, threads)
+    return (oj, codes[0], codes[2]), (oy, codes[1], codes[3])
 
 
 def cpu_airy(which, kode, z, threads=8):

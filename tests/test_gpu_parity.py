@@ -226,3 +226,27 @@ def test_full_size_cfg2_properties(special):
         comp, _, _ = helpers.cpu_bessel("Y" if fn == "J" else "J", 1, 2.5, zs)
         err = so.mismatch(to_np(out[idx]), want, np.maximum(np.abs(want), np.abs(comp)))
         assert np.all(err <= 1e-13), err.max()
+
+
+@pytest.mark.parametrize("cfg", ["cfg2", "cfg3", "real", "wide"])
+def test_jy_pair_matches_separate_calls(special, cfg):
+    """spb_bessel_jy (shared I pass) vs spb_bessel(J) and spb_bessel(Y): same region math, so agreement to rounding
+    (FMA contraction differs per kernel) and identical error classes."""
+    rng = np.random.default_rng(abs(hash(("jy-gpu", cfg))) % 2**32)
+    v, z = gen(cfg, 200000, rng)
+    zt, vt = torch.from_numpy(z).cuda(), torch.from_numpy(v).cuda()
+    for scaled in (False, True):
+        (j, ej, nj), (y, ey, ny) = special.bessel_jy(vt, zt, scaled=scaled)
+        a, ia, na = special.bessel("J", vt, zt, scaled=scaled)
+        b, ib, nb = special.bessel("Y", vt, zt, scaled=scaled)
+        assert torch.equal(ej, ia) and torch.equal(nj, na) and torch.equal(ey, ib) and torch.equal(ny, nb)
+        ja, ya, aa, ba = to_np(j), to_np(y), to_np(a), to_np(b)
+        scale = np.maximum(np.abs(aa), np.abs(ba))
+        ok = (to_np(ia) == 0) & (to_np(ib) == 0) & np.isfinite(scale)
+        assert np.all(so.mismatch(ja, aa, scale)[ok] <= 2e-14)
+        assert np.all(so.mismatch(ya, ba, scale)[ok] <= so.tolerance(ba, z, v)[ok])
+    # host-pointer path of the pair
+    (jh, ejh, _), (yh, eyh, _) = special.bessel_jy(v[:50000], z[:50000])
+    (jd, _, _), (yd, _, _) = special.bessel_jy(vt[:50000], zt[:50000])
+    assert np.array_equal(jh.view(np.uint64), to_np(jd).view(np.uint64))
+    assert np.array_equal(yh.view(np.uint64), to_np(yd).view(np.uint64))

@@ -43,3 +43,16 @@ def test_golden_points_through_pipeline():
             b, ib, nb, _ = helpers.cpu_bessel(fn, kode, g["v"], g["z"], pipeline=True)
             same = (a.view(np.uint64) == b.view(np.uint64)).reshape(-1, 2).all(1) | (np.isnan(a.real) & np.isnan(b.real))
             assert same.all() and np.array_equal(ia, ib) and np.array_equal(na, nb)
+
+
+@pytest.mark.parametrize("cfg", ["cfg2", "cfg3", "cfg4", "real", "wide"])
+def test_jy_pair_matches_separate_drivers(cfg):
+    """The shared-I-pass J/Y pair must give exactly what the J and Y drivers give separately."""
+    rng = np.random.default_rng(abs(hash(("jy", cfg))) % 2**32)
+    v, z = gen(cfg, 20000, rng)
+    for kode in (1, 2):
+        (j, ej, nj), (y, ey, ny) = helpers.cpu_bessel_jy(kode, v, z)
+        a, ia, na = helpers.cpu_bessel("J", kode, v, z)
+        b, ib, nb = helpers.cpu_bessel("Y", kode, v, z)
+        assert np.array_equal(j.view(np.uint64), a.view(np.uint64)) and np.array_equal(ej, ia) and np.array_equal(nj, na)
+        assert np.array_equal(y.view(np.uint64), b.view(np.uint64)) and np.array_equal(ey, ib) and np.array_equal(ny, nb)

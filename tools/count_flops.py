@@ -20,7 +20,7 @@ from test_pipeline_cpu import gen  # noqa: E402
 
 KERNELS = ["classify", "scan_scatter", "ipass_series", "ipass_asyi", "ipass_mlri", "ipass_wrsk", "kpass", "general",
            "monolithic"]
-FN = {"J": 0, "Y": 1, "I": 2, "K": 3, "H1": 4, "H2": 5}
+FN = {"J": 0, "Y": 1, "I": 2, "K": 3, "H1": 4, "H2": 5, "JY": 6}
 
 
 def cfg2_sample(n):
@@ -39,7 +39,7 @@ def main():
     out = {"_rule": "add/sub/mul/div/sqrt = 1, exp/log/sin/cos/atan/sinh/cosh = 30, pow = 60; per point, "
                     "prepare + region + finish", "_sample": {}}
     rng = np.random.default_rng(1)
-    samples = {"cfg2": (cfg2_sample(1 << 18), ("J", "Y"), 1),
+    samples = {"cfg2": (cfg2_sample(1 << 18), ("J", "Y", "JY"), 1),
                "cfg3": (gen("cfg3", 1 << 17, rng), ("I", "K"), 2),
                "cfg4": (gen("cfg4", 1 << 17, rng), ("H1", "H2"), 1)}
     for cfg, ((v, z), fams, kode) in samples.items():
