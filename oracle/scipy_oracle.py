@@ -112,7 +112,7 @@ def tolerance(want, z=None, v=None, rtol=RTOL):
     Conditioning terms widen it where one rounding of an exponent / phase already exceeds rtol:
     * |f| beyond 1e+-49: the result is exp(x), |x| > 112; bound 4 eps |ln|f|| ("away from overflow");
     * |z| > 200 (outside the BASELINE configs' box): bound rtol |z| / 200;
-    * uniform-asymptotic region (see uniform_region): bound 8 eps max(|z|, v);
+    * uniform-asymptotic region (see uniform_region): bound 16 eps max(|z|, v);
     * forward / backward recurrences over the order: bound 16 eps v."""
     with np.errstate(all="ignore"):
         lf = np.abs(np.log(np.abs(want)))
@@ -122,7 +122,7 @@ def tolerance(want, z=None, v=None, rtol=RTOL):
         tol = tol * np.maximum(1.0, np.abs(z) / 200.0)
         if v is not None:
             vv = np.broadcast_to(np.asarray(v, dtype=np.float64), np.shape(z))
-            tol = np.maximum(tol, np.where(uniform_region(vv, z), 8 * EPS * np.maximum(np.abs(z), vv), 0.0))
+            tol = np.maximum(tol, np.where(uniform_region(vv, z), 16 * EPS * np.maximum(np.abs(z), vv), 0.0))
             tol = np.maximum(tol, 16 * EPS * vv)  # order recurrences accumulate ~v roundings (matters above v = 28)
     return tol
 
