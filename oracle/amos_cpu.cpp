@@ -115,6 +115,46 @@ int spbo_bessel_jy_pipeline(int kode, const double *v, int64_t v_stride, const d
     return 0;
 }
 
+// Order sequences: out[k*n + i] = F_{v_i + k}(z_i), k < n_orders (J, I, K, H1, H2; Y through its Hankel pair).
+int spbo_bessel_seq(int fn, int kode, const double *v, int64_t v_stride, const double *z, double *out, int32_t *ierr,
+                    int32_t *nz, int64_t n, int n_orders, int threads) {
+    parallel_for(n, threads, [=](int64_t lo, int64_t hi) {
+        std::vector<cplx> cy(n_orders), cw(n_orders);
+        for (int64_t i = lo; i < hi; ++i) {
+            cplx zz(z[2 * i], z[2 * i + 1]);
+            double fnu = v[i * v_stride];
+            int ie = 0, nzz = 0;
+            for (int k = 0; k < n_orders; ++k) cy[k] = cplx(0.0, 0.0);
+            switch (fn) {
+                case FN_J: nzz = besj(zz, fnu, kode, n_orders, cy.data(), ie); break;
+                case FN_I: nzz = besi(zz, fnu, kode, n_orders, cy.data(), ie); break;
+                case FN_K: nzz = besk(zz, fnu, kode, n_orders, cy.data(), ie); break;
+                case FN_H1: nzz = besh(zz, fnu, kode, 1, n_orders, cy.data(), ie); break;
+                case FN_H2: nzz = besh(zz, fnu, kode, 2, n_orders, cy.data(), ie); break;
+                case FN_Y:
+                    // member by member through the Hankel pair (no sequence recurrence of its own)
+                    for (int k = 0; k < n_orders; ++k) {
+                        cplx one[1];
+                        one[0] = cplx(0.0, 0.0);
+                        int iek = 0;
+                        nzz += besy(zz, fnu + (double)k, kode, one, iek);
+                        cy[k] = one[0];
+                        if (iek != 0 && (ie == 0 || ie == 3)) ie = iek;
+                    }
+                    break;
+                default: ie = 1;
+            }
+            for (int k = 0; k < n_orders; ++k) {
+                out[2 * (k * n + i)] = cy[k].re;
+                out[2 * (k * n + i) + 1] = cy[k].im;
+            }
+            if (ierr) ierr[i] = ie;
+            if (nz) nz[i] = nzz;
+        }
+    });
+    return 0;
+}
+
 // which: 0 Ai, 1 Ai', 2 Bi, 3 Bi'
 int spbo_airy(int which, int kode, const double *z, double *out, int32_t *ierr, int32_t *nz, int64_t n,
               int threads) {

@@ -13,12 +13,14 @@
 namespace spb {
 
 // forward: full I-function region driver (spb_binu.h), used by biry
-SPB_FN int binu(cplx z, real fnu, int kode, int n, cplx *cy, real rl, real fnul, real tol, real elim,
+template <class Y>
+SPB_FN int binu(cplx z, real fnu, int kode, int n, Y cy, real rl, real fnul, real tol, real elim,
                 real alim);
 
 // Analytic continuation K(fnu, zn e^{mp}) = K(fnu,zn) e^{-mp fnu} - mp I(fnu,zn), mp = i pi mr,
 // specialised to the Airy orders (fnu = 1/3, 2/3; n = 1).
-SPB_FN int acai(cplx z, real fnu, int kode, int mr, int n, cplx *y, real rl, real tol, real elim,
+template <class Y>
+SPB_FN int acai(cplx z, real fnu, int kode, int mr, int n, Y y, real rl, real tol, real elim,
                 real alim) {
     int nz = 0;
     cplx zn = -z;

@@ -14,7 +14,8 @@ namespace spb {
 
 // ikflg = 1: I sequence (leading members may be zeroed, nuf = how many);
 // ikflg = 2: K sequence; nuf = -1 signals overflow.
-SPB_FN int uoik(cplx z, real fnu, int kode, int ikflg, int n, cplx *y, real tol, real elim, real alim) {
+template <class Y>
+SPB_FN int uoik(cplx z, real fnu, int kode, int ikflg, int n, Y y, real tol, real elim, real alim) {
     const real aic = 1.265512123484645396;  // ln(2 sqrt(pi))
     int nuf = 0;
     int nn = n;
@@ -133,7 +134,8 @@ SPB_FN int uoik(cplx z, real fnu, int kode, int ikflg, int n, cplx *y, real tol,
 }
 
 // I by ratios from rati normalised through the Wronskian with K_fnu, K_fnu+1.
-SPB_FN int wrsk(cplx zr, real fnu, int kode, int n, cplx *y, real tol, real elim, real alim) {
+template <class Y>
+SPB_FN int wrsk(cplx zr, real fnu, int kode, int n, Y y, real tol, real elim, real alim) {
     cplx cw[2];
     int nw = bknu(zr, fnu, kode, 2, cw, tol, elim, alim);
     if (nw != 0) return (nw == -2) ? -2 : -1;
@@ -172,7 +174,8 @@ SPB_FN int wrsk(cplx zr, real fnu, int kode, int n, cplx *y, real tol, real elim
 }
 
 // Uniform expansion of I for |arg z| <= pi/3 (Debye type).
-SPB_FN int uni1(cplx z, real fnu, int kode, int n, cplx *y, int &nlast, real fnul, real tol, real elim,
+template <class Y>
+SPB_FN int uni1(cplx z, real fnu, int kode, int n, Y y, int &nlast, real fnul, real tol, real elim,
                 real alim) {
     int nz = 0;
     int nd = n;
@@ -303,7 +306,8 @@ SPB_FN int uni1(cplx z, real fnu, int kode, int n, cplx *y, int &nlast, real fnu
 
 // Uniform expansion of I in the rest of the right half plane, through the
 // Airy-type expansion of J(fnu, zn), zn = -+ i z.
-SPB_FN int uni2(cplx z, real fnu, int kode, int n, cplx *y, int &nlast, real fnul, real tol, real elim,
+template <class Y>
+SPB_FN int uni2(cplx z, real fnu, int kode, int n, Y y, int &nlast, real fnul, real tol, real elim,
                 real alim) {
     const real hpi = SPB_HPI;
     const real aic = 1.265512123484645396;
@@ -461,7 +465,8 @@ SPB_FN int uni2(cplx z, real fnu, int kode, int n, cplx *y, int &nlast, real fnu
 
 // I for |z| > fnul or fnu+n-1 > fnul: evaluate at an order raised by nui and
 // recur backward; nlast != 0 leaves the low orders for another method.
-SPB_FN int buni(cplx z, real fnu, int kode, int n, cplx *y, int nui, int &nlast, real fnul, real tol,
+template <class Y>
+SPB_FN int buni(cplx z, real fnu, int kode, int n, Y y, int nui, int &nlast, real fnul, real tol,
                 real elim, real alim) {
     int nz = 0;
     real ax = rabs(z.re) * real(1.7321);
@@ -584,7 +589,8 @@ SPB_HD int binu_region(cplx z, real fnu, int n, real rl, real fnul) {
     return IREG_MLRI;
 }
 
-SPB_FN int binu(cplx z, real fnu, int kode, int n, cplx *cy, real rl, real fnul, real tol, real elim,
+template <class Y>
+SPB_FN int binu(cplx z, real fnu, int kode, int n, Y cy, real rl, real fnul, real tol, real elim,
                 real alim) {
     int nz = 0;
     real az = cabs_(z);

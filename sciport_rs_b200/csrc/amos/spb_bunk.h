@@ -255,7 +255,8 @@ SPB_FN int unk2_single(cplx z, real fnu, int kode, int mr, cplx &y, real tol, re
     return nz;
 }
 
-SPB_FN int bunk(cplx z, real fnu, int kode, int mr, int n, cplx *y, real tol, real elim, real alim) {
+template <class Y>
+SPB_FN int bunk(cplx z, real fnu, int kode, int mr, int n, Y y, real tol, real elim, real alim) {
     real ax = rabs(z.re) * real(1.7321);
     real ay = rabs(z.im);
     int nz = 0;

@@ -175,3 +175,12 @@ SPB_HD int uchk(cplx y, real ascle, real tol) {
 }
 
 }  // namespace spb
+
+namespace spb {
+// Strided view of a result sequence stored [order][point] in global memory: y[k] is member k of one point.
+struct StridedSeq {
+    cplx *base;
+    long long stride;
+    SPB_HD cplx &operator[](int k) const { return base[(long long)k * stride]; }
+};
+}  // namespace spb

@@ -48,7 +48,8 @@ SPB_HD OrderPhase order_phase(real fnu) {
 }
 
 // K(fnu, zn e^{i pi mr}) = e^{-i pi mr fnu} K(fnu, zn) - i pi mr I(fnu, zn)
-SPB_FN int acon(cplx z, real fnu, int kode, int mr, int n, cplx *y, real rl, real fnul, real tol,
+template <class Y>
+SPB_FN int acon(cplx z, real fnu, int kode, int mr, int n, Y y, real rl, real fnul, real tol,
                 real elim, real alim) {
     const real pi = SPB_PI;
     int nz = 0;
@@ -170,7 +171,8 @@ SPB_HD cplx rot_guard(cplx y, cplx csgn, real rtol, real ascle, real tol) {
 }
 
 // ---------------------------------------------------------------- I
-SPB_FN int besi(cplx z, real fnu, int kode, int n, cplx *cy, int &ierr) {
+template <class Y>
+SPB_FN int besi(cplx z, real fnu, int kode, int n, Y cy, int &ierr) {
     const real tol = SPB_TOL, elim = SPB_ELIM, alim = SPB_ALIM, rl = SPB_RL, fnul = SPB_FNUL;
     ierr = 0;
     int nz = 0;
@@ -215,7 +217,8 @@ SPB_FN int besi(cplx z, real fnu, int kode, int n, cplx *cy, int &ierr) {
 }
 
 // ---------------------------------------------------------------- J
-SPB_FN int besj(cplx z, real fnu, int kode, int n, cplx *cy, int &ierr) {
+template <class Y>
+SPB_FN int besj(cplx z, real fnu, int kode, int n, Y cy, int &ierr) {
     const real tol = SPB_TOL, elim = SPB_ELIM, alim = SPB_ALIM, rl = SPB_RL, fnul = SPB_FNUL;
     const real hpi = SPB_HPI;
     ierr = 0;
@@ -262,7 +265,8 @@ SPB_FN int besj(cplx z, real fnu, int kode, int n, cplx *cy, int &ierr) {
 }
 
 // ---------------------------------------------------------------- K
-SPB_FN int besk(cplx z, real fnu, int kode, int n, cplx *cy, int &ierr) {
+template <class Y>
+SPB_FN int besk(cplx z, real fnu, int kode, int n, Y cy, int &ierr) {
     const real tol = SPB_TOL, elim = SPB_ELIM, alim = SPB_ALIM, rl = SPB_RL, fnul = SPB_FNUL;
     ierr = 0;
     int nz = 0;
@@ -351,7 +355,8 @@ SPB_FN int besk(cplx z, real fnu, int kode, int n, cplx *cy, int &ierr) {
 }
 
 // ---------------------------------------------------------------- H1 / H2
-SPB_FN int besh(cplx z, real fnu, int kode, int m, int n, cplx *cy, int &ierr) {
+template <class Y>
+SPB_FN int besh(cplx z, real fnu, int kode, int m, int n, Y cy, int &ierr) {
     const real tol = SPB_TOL, elim = SPB_ELIM, alim = SPB_ALIM, rl = SPB_RL, fnul = SPB_FNUL;
     const real hpi = SPB_HPI;
     ierr = 0;

@@ -17,7 +17,8 @@ namespace spb {
 // ---------------------------------------------------------------------------
 // Power series.  nz = -k means: k members underflowed and |z|^2/4 exceeds the
 // remaining order, so the caller must finish with another method.
-SPB_FN int seri(cplx z, real fnu, int kode, int n, cplx *y, real tol, real elim, real alim) {
+template <class Y>
+SPB_FN int seri(cplx z, real fnu, int kode, int n, Y y, real tol, real elim, real alim) {
     int nz = 0;
     real az = cabs_(z);
     if (az == real(0.0)) {
@@ -147,7 +148,8 @@ SPB_FN int seri(cplx z, real fnu, int kode, int n, cplx *y, real tol, real elim,
 // table, so the inner loop is one complex multiply and two real multiplies per
 // term (no division, no modulus).  The second exponential exp(-2z) is below
 // half an ulp of the leading sum once 2 Re z > 80 and is skipped there.
-SPB_FN int asyi(cplx z, real fnu, int kode, int n, cplx *y, real rl, real tol, real elim, real alim) {
+template <class Y>
+SPB_FN int asyi(cplx z, real fnu, int kode, int n, Y y, real rl, real tol, real elim, real alim) {
     static const double RJ[48] = {
         0.0, 1.0, 1.0 / 2, 1.0 / 3, 1.0 / 4, 1.0 / 5, 1.0 / 6, 1.0 / 7, 1.0 / 8, 1.0 / 9, 1.0 / 10, 1.0 / 11,
         1.0 / 12, 1.0 / 13, 1.0 / 14, 1.0 / 15, 1.0 / 16, 1.0 / 17, 1.0 / 18, 1.0 / 19, 1.0 / 20, 1.0 / 21,
@@ -252,7 +254,8 @@ SPB_FN int asyi(cplx z, real fnu, int kode, int n, cplx *y, real rl, real tol, r
 
 // ---------------------------------------------------------------------------
 // Miller algorithm normalised by a Neumann series.  nz = -2: no convergence.
-SPB_FN int mlri(cplx z, real fnu, int kode, int n, cplx *y, real tol) {
+template <class Y>
+SPB_FN int mlri(cplx z, real fnu, int kode, int n, Y y, real tol) {
     const real scle = SPB_D1MACH1 / tol;
     real az = cabs_(z);
     int iaz = (int)az;
@@ -384,7 +387,8 @@ SPB_FN int mlri(cplx z, real fnu, int kode, int n, cplx *y, real tol) {
 // ---------------------------------------------------------------------------
 // Ratios cy[k] = I_{fnu+k+1}(z)/I_{fnu+k}(z), k = 0..n-1, by backward
 // recurrence started from an index chosen by a forward magnitude walk.
-SPB_FN void rati(cplx z, real fnu, int n, cplx *cy, real tol) {
+template <class Y>
+SPB_FN void rati(cplx z, real fnu, int n, Y cy, real tol) {
     const real rt2 = 1.41421356237309515;
     real az = cabs_(z);
     int inu = (int)fnu;

@@ -21,7 +21,8 @@ SPB_HD void sinhcosh(cplx z, cplx &sh, cplx &ch) {
 // Set K members to zero on underflow, carry the recurrence on scaled values
 // until two consecutive members are on scale; returns nz, leaves the on-scale
 // members in y scaled by 1/tol.
-SPB_FN int kscl(cplx zr, real fnu, int n, cplx *y, cplx rz, real ascle, real tol, real elim) {
+template <class Y>
+SPB_FN int kscl(cplx zr, real fnu, int n, Y y, cplx rz, real ascle, real tol, real elim) {
     int nz = 0, ic = 0;
     int nn = n < 2 ? n : 2;
     cplx cy[2];
@@ -129,7 +130,8 @@ SPB_FN int s1s2(cplx zr, cplx &s1, cplx &s2, real ascle, real alim, int &iuf) {
 }
 
 // K_{fnu+k}(z), k=0..n-1, Re z >= 0.  Returns nz (>=0), -1 overflow/invalid, -2 no convergence.
-SPB_FN int bknu(cplx z, real fnu, int kode, int n, cplx *y, real tol, real elim, real alim) {
+template <class Y>
+SPB_FN int bknu(cplx z, real fnu, int kode, int n, Y y, real tol, real elim, real alim) {
     const int kmax = 30;
     const real r1 = 2.0;
     const real dpi = SPB_PI;

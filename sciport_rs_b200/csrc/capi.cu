@@ -59,8 +59,9 @@ struct StageSet {  // device staging for host-pointer mode
     double2 *out2 = nullptr;
     int *ierr2 = nullptr;
     int *nz2 = nullptr;
+    double2 *seq = nullptr;  // [n_orders][m] block of an order-sequence chunk
     long long cap = 0;
-    long long cap_out = 0;
+    long long cap_out = 0;   // capacity of seq in values
 };
 
 struct DeviceCtx {
@@ -264,7 +265,41 @@ struct BesselArgs {
     double2 *out2 = nullptr;  // pair families
     int *ierr2 = nullptr;
     int *nz2 = nullptr;
+    int n_orders = 1;         // > 1: order sequence, out is [n_orders][out_stride]
+    long long out_stride = 0; // points per order row of the caller's result array
 };
+
+// Order sequences (n_orders > 1) with the batch resident on the device: one launch per chunk, every member
+// written straight into its [order][point] slot of the caller's array.
+int run_device_seq(DeviceCtx *c, const BesselArgs &a, cudaStream_t st, int *launches_out) {
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->dev));
+    int launches = 0;
+    CK(cudaEventRecord(c->ev0, st));
+    for (long long off = 0; off < a.n; off += CHUNK_DEVICE) {
+        long long m = std::min(CHUNK_DEVICE, a.n - off);
+        DevJob job{};
+        job.fam = a.fn;
+        job.kode = a.kode;
+        job.sem = (a.flags & SPB_SEM_SCIPY) ? 1 : 0;
+        job.v = a.v + off * a.v_stride;
+        job.v_stride = a.v_stride;
+        job.z = a.z ? a.z + off : nullptr;
+        job.x = a.x ? a.x + off : nullptr;
+        job.out = a.out + off;
+        job.ierr = a.ierr ? a.ierr + off : nullptr;
+        job.nz = a.nz ? a.nz + off : nullptr;
+        job.n = m;
+        launch_sequence(job, a.n_orders, a.out_stride, c->sms, st);
+        ++launches;
+    }
+    CK(cudaEventRecord(c->ev1, st));
+    CK(cudaGetLastError());
+    g_pending_ev0 = c->ev0;
+    g_pending_ev1 = c->ev1;
+    if (launches_out) *launches_out = launches;
+    return SPB_OK;
+}
 
 // data resident on the device: chunk over the batch on the caller's stream
 int run_device(DeviceCtx *c, const BesselArgs &a, cudaStream_t st, double *ms_out, int *launches_out) {
@@ -334,6 +369,7 @@ int ensure_stage(StageSet &s, long long n, bool real_in, bool per_elem_v, bool w
         cudaFree(s.out2);
         cudaFree(s.ierr2);
         cudaFree(s.nz2);
+        cudaFree(s.seq);
         s = StageSet();
         if (cudaMalloc(&s.z, n * 16) != cudaSuccess || cudaMalloc(&s.x, n * 8) != cudaSuccess ||
             cudaMalloc(&s.v, n * 8) != cudaSuccess || cudaMalloc(&s.out, n * 16) != cudaSuccess ||
@@ -441,6 +477,77 @@ int run_host_slice(DeviceCtx *c, const BesselArgs &a, double *ms_out, int *launc
     return SPB_OK;
 }
 
+// Order sequences with host buffers: chunks sized so that one staged [n_orders][m] block is <= 256 MiB; the block
+// goes back with one strided copy (row k of the block -> row k of the caller's [n_orders][n] array).
+int run_host_slice_seq(DeviceCtx *c, const BesselArgs &a, int *launches_out) {
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->dev));
+    Pin pz, px, pv, pe, pn;
+    if (a.z) pz.pin(a.z, a.n * 16);
+    if (a.x) px.pin(a.x, a.n * 8);
+    if (a.v_stride != 0) pv.pin(a.v, ((a.n - 1) * a.v_stride + 1) * 8);
+    if (a.ierr) pe.pin(a.ierr, a.n * 4);
+    if (a.nz) pn.pin(a.nz, a.n * 4);
+    // the result rows of this slice are not contiguous in the caller's array: pin row by row
+    std::vector<Pin> prow(a.n_orders);
+    for (int k = 0; k < a.n_orders; ++k) prow[k].pin(a.out + (long long)k * a.out_stride, a.n * 16);
+    long long chunk = std::max<long long>(1024, ((1ll << 24) / a.n_orders) & ~1023ll);
+    chunk = std::min(chunk, CHUNK_HOST);
+    int launches = 0, k = 0;
+    double v0 = a.v[0];
+    for (long long off = 0; off < a.n; off += chunk, ++k) {
+        long long m = std::min(chunk, a.n - off);
+        int b = k & 1;
+        cudaStream_t st = c->streams[b];
+        StageSet &s = c->stage[b];
+        int rc = ensure_stage(s, std::min(chunk, a.n), a.x != nullptr, a.v_stride != 0, a.ierr, a.nz);
+        if (rc != SPB_OK) return rc;
+        long long need = std::min(chunk, a.n) * a.n_orders;
+        if (need > s.cap_out) {
+            cudaFree(s.seq);
+            s.seq = nullptr;
+            s.cap_out = 0;
+            if (cudaMalloc(&s.seq, need * 16) != cudaSuccess) {
+                cudaGetLastError();
+                return fail(SPB_E_ALLOC, "cudaMalloc of the order-sequence staging block failed");
+            }
+            s.cap_out = need;
+        }
+        if (a.z) CK(cudaMemcpyAsync(s.z, a.z + off, m * 16, cudaMemcpyHostToDevice, st));
+        if (a.x) CK(cudaMemcpyAsync(s.x, a.x + off, m * 8, cudaMemcpyHostToDevice, st));
+        if (a.v_stride == 1) {
+            CK(cudaMemcpyAsync(s.v, a.v + off, m * 8, cudaMemcpyHostToDevice, st));
+        } else if (a.v_stride == 0) {
+            CK(cudaMemcpyAsync(s.v, &v0, 8, cudaMemcpyHostToDevice, st));
+        } else {
+            CK(cudaMemcpy2DAsync(s.v, 8, a.v + off * a.v_stride, a.v_stride * 8, 8, m, cudaMemcpyHostToDevice, st));
+        }
+        DevJob job{};
+        job.fam = a.fn;
+        job.kode = a.kode;
+        job.sem = (a.flags & SPB_SEM_SCIPY) ? 1 : 0;
+        job.v = s.v;
+        job.v_stride = a.v_stride == 0 ? 0 : 1;
+        job.z = a.z ? s.z : nullptr;
+        job.x = a.x ? s.x : nullptr;
+        job.out = s.seq;
+        job.ierr = a.ierr ? s.ierr : nullptr;
+        job.nz = a.nz ? s.nz : nullptr;
+        job.n = m;
+        launch_sequence(job, a.n_orders, m, c->sms, st);
+        ++launches;
+        CK(cudaMemcpy2DAsync(a.out + off, a.out_stride * 16, s.seq, m * 16, m * 16, a.n_orders, cudaMemcpyDeviceToHost,
+                             st));
+        if (a.ierr) CK(cudaMemcpyAsync(a.ierr + off, s.ierr, m * 4, cudaMemcpyDeviceToHost, st));
+        if (a.nz) CK(cudaMemcpyAsync(a.nz + off, s.nz, m * 4, cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(c->streams[0]));
+    CK(cudaStreamSynchronize(c->streams[1]));
+    CK(cudaGetLastError());
+    if (launches_out) *launches_out = launches;
+    return SPB_OK;
+}
+
 int bessel_impl(int fn, int kode, const double *v, int64_t v_stride, const spb_c128 *z, const double *x,
                 spb_c128 *out, int32_t *ierr, int32_t *nz, int64_t n, int n_orders, const spb_exec *ex,
                 spb_c128 *out2 = nullptr, int32_t *ierr2 = nullptr, int32_t *nz2 = nullptr) {
@@ -448,7 +555,8 @@ int bessel_impl(int fn, int kode, const double *v, int64_t v_stride, const spb_c
     if ((fn == SPB_FN_JY) != (out2 != nullptr) && n > 0) return fail(SPB_E_ARG, "pair family needs two result buffers");
     if (kode != 1 && kode != 2) return fail(SPB_E_ARG, "kode must be 1 or 2");
     if (n < 0 || v_stride < 0) return fail(SPB_E_ARG, "negative n or v_stride");
-    if (n_orders != 1) return fail(SPB_E_ARG, "n_orders != 1: use spb_bessel_seq");
+    if (n_orders < 1 || n_orders > 4096) return fail(SPB_E_ARG, "n_orders must be 1..4096");
+    if (n_orders > 1 && (fn == SPB_FN_JY)) return fail(SPB_E_ARG, "the JY pair has no order-sequence form");
     if (n > 0 && (!v || (!z && !x) || !out)) return fail(SPB_E_ARG, "null buffer");
     std::vector<int> devs;
     bool dptr;
@@ -464,9 +572,16 @@ int bessel_impl(int fn, int kode, const double *v, int64_t v_stride, const spb_c
     a.out2 = (double2 *)out2;
     a.ierr2 = ierr2;
     a.nz2 = nz2;
-    if (dptr) return run_device(get_ctx(devs[0]), a, st, &g_last_ms, &g_last_launches);
+    a.n_orders = n_orders;
+    a.out_stride = n;
+    const bool seq = n_orders > 1;
+    if (dptr)
+        return seq ? run_device_seq(get_ctx(devs[0]), a, st, &g_last_launches)
+                   : run_device(get_ctx(devs[0]), a, st, &g_last_ms, &g_last_launches);
     const int G = (int)devs.size();
-    if (G == 1) return run_host_slice(get_ctx(devs[0]), a, &g_last_ms, &g_last_launches);
+    if (G == 1)
+        return seq ? run_host_slice_seq(get_ctx(devs[0]), a, &g_last_launches)
+                   : run_host_slice(get_ctx(devs[0]), a, &g_last_ms, &g_last_launches);
     // contiguous slice i of G per device, one host thread per device (no collective: shards never talk)
     std::vector<int> rcs(G, SPB_OK), ls(G, 0);
     std::vector<std::string> errs(G);
@@ -485,7 +600,9 @@ int bessel_impl(int fn, int kode, const double *v, int64_t v_stride, const spb_c
             s.ierr2 = a.ierr2 ? a.ierr2 + lo : nullptr;
             s.nz2 = a.nz2 ? a.nz2 + lo : nullptr;
             s.n = hi - lo;
-            if (s.n > 0) rcs[g] = run_host_slice(get_ctx(devs[g]), s, nullptr, &ls[g]);
+            if (s.n > 0)
+                rcs[g] = seq ? run_host_slice_seq(get_ctx(devs[g]), s, &ls[g])
+                             : run_host_slice(get_ctx(devs[g]), s, nullptr, &ls[g]);
             errs[g] = g_err;
         });
     }

@@ -67,6 +67,7 @@ void launch_ipass(const DevJob &job, const Scratch &s, int region, int sms, cuda
 void launch_kpass(const DevJob &job, const Scratch &s, int sms, cudaStream_t st);
 void launch_general(const DevJob &job, const Scratch &s, int sms, cudaStream_t st);
 void launch_monolithic(const DevJob &job, cudaStream_t st);
+void launch_sequence(const DevJob &job, int n_orders, long long out_stride, int sms, cudaStream_t st);
 void launch_airy(int which, int kode, int sem, const double2 *z, double2 *out, int *ierr, int *nz, long long n,
                  cudaStream_t st);
 void launch_synth(int cfg, unsigned long long seed, long long offset, long long n, long long n_total, double *v,

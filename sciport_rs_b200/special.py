@@ -66,8 +66,11 @@ def profile_step(fn):
 
 
 def bessel(fn, v, z, scaled=False, semantics="amos", path="binned", real_input=False, devices=None, profile=False,
-           out=None, ierr=None, nz=None):
+           out=None, ierr=None, nz=None, n_orders=1):
     """Evaluate one family over a batch.  Returns ``(values, ierr, nz)``.
+
+    ``n_orders > 1`` evaluates the order sequence v, v+1, ..., v+n_orders-1 per point; ``values`` then has
+    shape ``(n_orders, n)`` (order-major, BASELINE config 5), ``ierr`` / ``nz`` stay per point.
 
     fn: 'J','Y','I','K','H1','H2'; v: scalar or array broadcast against z; z: complex128 (or float64 with
     ``real_input=True``, promoted like ``v.into()`` in mod.rs:10).  Host (numpy) calls may pass preallocated
@@ -96,14 +99,17 @@ def bessel(fn, v, z, scaled=False, semantics="amos", path="binned", real_input=F
         else:
             vt = torch.full((1,), float(v), dtype=torch.float64, device=zc.device)
             stride = 0
-        out = torch.empty(zc.shape, dtype=torch.complex128, device=zc.device)
+        oshape = tuple(zc.shape) if n_orders == 1 else (n_orders, n)
+        if out is None:
+            out = torch.empty(oshape, dtype=torch.complex128, device=zc.device)
+        assert out.is_contiguous() and out.numel() == n * n_orders and out.dtype == torch.complex128
         ierr = torch.empty(zc.shape, dtype=torch.int32, device=zc.device)
         nz = torch.empty(zc.shape, dtype=torch.int32, device=zc.device)
         with torch.cuda.device(zc.device):
             ex = make_exec(device_ptrs=True, stream=_stream_for(zc), flags=flags, devices=[zc.device.index])
             f = lib.spb_bessel_real if real_input else lib.spb_bessel
             check(f(FN[fn], kode, vt.data_ptr(), stride, zc.data_ptr(), out.data_ptr(), ierr.data_ptr(),
-                    nz.data_ptr(), n, 1, ctypes.byref(ex)))
+                    nz.data_ptr(), n, n_orders, ctypes.byref(ex)))
         if profile and _PROFILE_LOG is not None:
             for r in _lib.last_profile():
                 r["name"] = f"{fn}/{r['name']}"
@@ -119,15 +125,16 @@ def bessel(fn, v, z, scaled=False, semantics="amos", path="binned", real_input=F
         va = np.ascontiguousarray(np.broadcast_to(va, za.shape))
         stride = 1
     # caller-provided (e.g. pinned) result buffers are filled in place, like the C ABI
-    out = np.empty(za.shape, dtype=np.complex128) if out is None else out
+    oshape = za.shape if n_orders == 1 else (n_orders, n)
+    out = np.empty(oshape, dtype=np.complex128) if out is None else out
     ierr = np.empty(za.shape, dtype=np.int32) if ierr is None else ierr
     nz = np.empty(za.shape, dtype=np.int32) if nz is None else nz
     assert out.dtype == np.complex128 and ierr.dtype == np.int32 and nz.dtype == np.int32
-    assert out.size == n and ierr.size == n and nz.size == n and out.flags.c_contiguous
+    assert out.size == n * n_orders and ierr.size == n and nz.size == n and out.flags.c_contiguous
     ex = make_exec(device_ptrs=False, flags=flags, devices=devices)
     f = lib.spb_bessel_real if real_input else lib.spb_bessel
     check(f(FN[fn], kode, va.ctypes.data, stride, za.ctypes.data, out.ctypes.data, ierr.ctypes.data, nz.ctypes.data,
-            n, 1, ctypes.byref(ex)))
+            n, n_orders, ctypes.byref(ex)))
     return out, ierr, nz
 
 
@@ -252,6 +259,13 @@ iv, ive = _family("I", False), _family("I", True)
 kv_array, kve_array = _family("K", False), _family("K", True)
 hankel1, hankel1e = _family("H1", False), _family("H1", True)
 hankel2, hankel2e = _family("H2", False), _family("H2", True)
+
+
+def jn_sequence(n_orders, z, v0=0.0, scaled=False):
+    """Order sweep J_{v0+k}(z_i), k = 0..n_orders-1, as an (n_orders, n) array (BASELINE config 5); raises on the
+    first Err in index order."""
+    vals, ierr, _ = bessel("J", v0, z, scaled=scaled, n_orders=n_orders)
+    return _result(vals, ierr)
 
 
 def airy_raw(which, z, scaled=False, semantics="amos"):

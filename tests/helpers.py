@@ -13,6 +13,12 @@ CATS = ["", "domain", "overflow", "underflow", "loss", "no_result", "singular", 
 _oracle = None
 
 
+def seed_of(*parts):
+    """Deterministic 32-bit seed from strings (Python's hash() is salted per process)."""
+    import zlib
+    return zlib.crc32("/".join(str(p) for p in parts).encode())
+
+
 def oracle_lib():
     """oracle/libspb_oracle.so, built on demand with g++ (CPU only)."""
     global _oracle
@@ -26,6 +32,7 @@ def oracle_lib():
         lib.spbo_bessel_pipeline.argtypes = [I, I, P, L, P, P, P, P, P, L, I]
         lib.spbo_airy.argtypes = [I, I, P, P, P, P, L, I]
         lib.spbo_bessel_jy_pipeline.argtypes = [I, P, L, P, P, P, P, L, I]
+        lib.spbo_bessel_seq.argtypes = [I, I, P, L, P, P, P, P, L, I, I]
         lib.spbo_gamma.argtypes = [I, P, P, L]
         lib.spbo_cgamma.argtypes = [I, P, P, L]
         _oracle = lib
@@ -46,6 +53,19 @@ def cpu_bessel(fn, kode, v, z, sem=0, pipeline=False, threads=8):
         return out, ierr, nz, path
     lib.spbo_bessel_sem(FN[fn], kode, sem, v.ctypes.data, 1, z.ctypes.data, out.ctypes.data, ierr.ctypes.data,
                         nz.ctypes.data, z.size, threads)
+    return out, ierr, nz
+
+
+def cpu_bessel_seq(fn, kode, v, z, n_orders, threads=8):
+    """Order sequence F_{v+k}(z), k < n_orders, on the CPU checker: ((n_orders, n) values, ierr[n], nz[n])."""
+    lib = oracle_lib()
+    z = np.ascontiguousarray(z, dtype=np.complex128).ravel()
+    v = np.ascontiguousarray(np.broadcast_to(np.asarray(v, dtype=np.float64), z.shape))
+    out = np.empty((n_orders, z.size), np.complex128)
+    ierr = np.empty(z.size, np.int32)
+    nz = np.empty(z.size, np.int32)
+    lib.spbo_bessel_seq(FN[fn], kode, v.ctypes.data, 1, z.ctypes.data, out.ctypes.data, ierr.ctypes.data,
+                        nz.ctypes.data, z.size, n_orders, threads)
     return out, ierr, nz
 
 

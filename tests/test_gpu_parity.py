@@ -49,7 +49,7 @@ def test_golden_device_pointers(special, fn, kode):
 @pytest.mark.parametrize("fn", list(FN))
 def test_vs_cpu_oracle_and_monolithic(special, fn, cfg):
     """Binned CUDA path vs CPU oracle (tolerance) and vs the monolithic CUDA path (bit-identical)."""
-    rng = np.random.default_rng(abs(hash((fn, cfg, "gpu"))) % 2**32)
+    rng = np.random.default_rng(helpers.seed_of(fn, cfg, "gpu"))
     v, z = gen(cfg, 200000, rng)
     zt, vt = torch.from_numpy(z).cuda(), torch.from_numpy(v).cuda()
     for kode in (1, 2):
@@ -232,7 +232,7 @@ def test_full_size_cfg2_properties(special):
 def test_jy_pair_matches_separate_calls(special, cfg):
     """spb_bessel_jy (shared I pass) vs spb_bessel(J) and spb_bessel(Y): same region math, so agreement to rounding
     (FMA contraction differs per kernel) and identical error classes."""
-    rng = np.random.default_rng(abs(hash(("jy-gpu", cfg))) % 2**32)
+    rng = np.random.default_rng(helpers.seed_of("jy-gpu", cfg))
     v, z = gen(cfg, 200000, rng)
     zt, vt = torch.from_numpy(z).cuda(), torch.from_numpy(v).cuda()
     for scaled in (False, True):
@@ -250,3 +250,64 @@ def test_jy_pair_matches_separate_calls(special, cfg):
     (jd, _, _), (yd, _, _) = special.bessel_jy(vt[:50000], zt[:50000])
     assert np.array_equal(jh.view(np.uint64), to_np(jd).view(np.uint64))
     assert np.array_equal(yh.view(np.uint64), to_np(yd).view(np.uint64))
+
+
+# ---------------------------------------------------------------- order sequences (BASELINE config 5)
+def test_j_sweep_0_255_golden_and_oracle(special):
+    """out[k][i] = J_k(z_i), k = 0..255: golden (scipy per order), CPU oracle on a cfg5 sample, host-pointer path."""
+    from test_sequence_cpu import check_seq
+    g = helpers.load_golden("seq_golden.npz")
+    z = g["z5"]
+    for kode in (1, 2):
+        got, ierr, nz = special.bessel("J", 0.0, torch.from_numpy(z).cuda(), scaled=(kode == 2), n_orders=256)
+        assert got.shape == (256, z.size)
+        check_seq(to_np(got), to_np(ierr), to_np(nz), g[f"J5_{kode}"], g[f"Y5_{kode}"], np.zeros(z.size),
+                  f"J sweep kode={kode}", z=z)
+    v, zs = special.synth(5, 20000, n_total=1 << 24)
+    dev, ierr, nz = special.bessel("J", 0.0, torch.from_numpy(zs).cuda(), n_orders=256)
+    dev = to_np(dev)
+    want, ierr_c, nz_c = helpers.cpu_bessel_seq("J", 1, 0.0, zs, 256)
+    assert np.array_equal(to_np(ierr), ierr_c) and np.array_equal(to_np(nz), nz_c)
+    # same algorithm on both sides, different FMA contraction: agreement to a few roundings of the recurrence
+    ycomp = helpers.cpu_bessel_seq("Y", 1, 0.0, zs, 256)[0]
+    check_seq(dev, ierr_c, nz_c, want, ycomp, np.zeros(zs.size), "J sweep vs CPU oracle", z=zs)
+    # zeros (underflowed leading members) sit in the same slots
+    assert np.array_equal(dev == 0, want == 0)
+    host, ierr_h, nz_h = special.bessel("J", 0.0, zs, n_orders=256)  # numpy in: staged, strided copy back
+    assert np.array_equal(host.view(np.uint64), dev.view(np.uint64))
+    assert np.array_equal(ierr_h, ierr_c) and np.array_equal(nz_h, nz_c)
+    swept = special.jn_sequence(256, zs[:100])
+    assert np.array_equal(swept.view(np.uint64), dev[:, :100].copy().view(np.uint64))
+
+
+@pytest.mark.parametrize("fn", ["J", "Y", "I", "K", "H1", "H2"])
+def test_short_sequences_golden(special, fn):
+    from test_sequence_cpu import check_seq
+    g = helpers.load_golden("seq_golden.npz")
+    z, v = g["zs"], g["vs"]
+    for kode in (1, 2):
+        got, ierr, nz = special.bessel(fn, torch.from_numpy(v).cuda(), torch.from_numpy(z).cuda(),
+                                       scaled=(kode == 2), n_orders=12)
+        comp = g[f"{so.COMPANION[fn]}s_{kode}"] if fn in ("J", "Y") else None
+        check_seq(to_np(got), to_np(ierr), to_np(nz), g[f"{fn}s_{kode}"], comp, v, f"{fn} kode={kode}", z=z)
+        _, ierr_c, nz_c = helpers.cpu_bessel_seq(fn, kode, v, z, 12)
+        assert np.array_equal(to_np(ierr), ierr_c) and np.array_equal(to_np(nz), nz_c)
+
+
+def test_sweep_recurrence_property_large(special):
+    """Size-independent property on 2^20 cfg5 points x 256 orders (4 GiB of results): the three-term
+    recurrence J_{k-1}(z) + J_{k+1}(z) = (2k/z) J_k(z) holds for every interior member."""
+    n = 1 << 20
+    v, z = special.synth(5, n, n_total=1 << 24, device="cuda:0")
+    out, ierr, nz = special.bessel("J", 0.0, z, n_orders=256)
+    assert special.first_error(ierr) == (-1, 0)
+    worst = 0.0
+    for k0 in range(1, 255, 32):  # slabs of orders to bound temporary memory
+        k1 = min(k0 + 32, 255)
+        k = torch.arange(k0, k1, device="cuda:0", dtype=torch.float64)[:, None]
+        mid = out[k0:k1]
+        res = out[k0 - 1:k1 - 1] + out[k0 + 1:k1 + 1] - (2.0 * k / z[None, :]) * mid
+        scale = out[k0 - 1:k1 - 1].abs() + out[k0 + 1:k1 + 1].abs() + ((2.0 * k / z[None, :]) * mid).abs()
+        ok = scale > 1e-290
+        worst = max(worst, float((res.abs() / scale.clamp_min(1e-300))[ok].max()))
+    assert worst <= 1e-14, worst

@@ -1,0 +1,75 @@
+"""CPU: pin the order-sequence form of the oracle restatement (out[k][i] = F_{v_i+k}(z_i), BASELINE config 5)
+against tests/golden/seq_golden.npz (scipy.special, one order at a time).
+
+Tolerance: a sequence is produced by ONE evaluation at the top (or bottom) of the range followed by the
+three-term recurrence over the order (backward from the top member for I / J, forward for K / H), so a member
+carries up to ~n_orders roundings relative to scipy's independent per-order evaluation: normalised error
+<= max(1e-13, 8 eps (v + n_orders)) + 4 eps |ln|f|| (both sides are that far
+from the mpmath truth at the small-|z| / high-order corner), against max(|J|, |Y|) for J and Y (absolute bound near
+zeros).  For the config-5 sweep (256 orders) that is 4.5e-13."""
+import numpy as np
+import pytest
+
+import helpers
+from oracle import scipy_oracle as so
+
+
+def seq_tolerance(want, v0, n_orders):
+    k = np.zeros((n_orders, 1)) + np.asarray(v0, dtype=float)[None, :] + n_orders
+    with np.errstate(all="ignore"):
+        lf = np.abs(np.log(np.abs(want)))
+    lf = np.where(np.isfinite(lf), lf, 0.0)
+    return np.maximum(1e-13, 8 * so.EPS * k) + 4 * so.EPS * lf
+
+
+def check_seq(got, ierr, nz, want, comp, v0, label, z=None):
+    """comp = companion values (Y for J, J for Y): the scale near zeros is max(|f|, |comp|), applied only where
+    zeros can occur (order <= |z|; beyond the turning point J and Y have no zeros and plain relative error holds)."""
+    n_orders = want.shape[0]
+    scale = np.abs(want)
+    if comp is not None:
+        c = np.where(np.isfinite(np.abs(comp)), np.abs(comp), 0.0)
+        if z is not None:
+            order = np.arange(n_orders, dtype=float)[:, None] + np.asarray(v0, dtype=float)[None, :]
+            c = np.where(order <= np.abs(z)[None, :], c, 0.0)
+        scale = np.maximum(scale, c)
+    err = so.mismatch(got, want, scale)
+    # members the algorithm zeroes by underflow (nz) are below 1e-305 in the oracle as well
+    live = np.isfinite(want.real) & np.isfinite(want.imag) & (np.abs(want) > 1e-300) & (ierr[None, :] == 0)
+    bad = live & (err > seq_tolerance(want, v0, n_orders))
+    assert not bad.any(), f"{label}: {bad.sum()} mismatches, worst {np.where(live, err, 0).max():.2e}"
+    dead = (np.abs(want) < 1e-305) & (ierr[None, :] == 0)
+    assert np.all(np.abs(got[dead]) < 1e-300), f"{label}: underflowed members must be (near) zero"
+    return np.where(live, err, 0).max()
+
+
+@pytest.mark.parametrize("kode", [1, 2])
+def test_j_sweep_0_255_vs_golden(kode):
+    g = helpers.load_golden("seq_golden.npz")
+    z = g["z5"]
+    got, ierr, nz = helpers.cpu_bessel_seq("J", kode, 0.0, z, 256)
+    assert np.all(ierr == 0)
+    check_seq(got, ierr, nz, g[f"J5_{kode}"], g[f"Y5_{kode}"], np.zeros(z.size), f"J sweep kode={kode}", z=z)
+    # nz counts the leading (highest-order) members that underflowed
+    assert np.array_equal(nz, (got == 0).sum(axis=0))
+
+
+@pytest.mark.parametrize("kode", [1, 2])
+@pytest.mark.parametrize("fn", ["J", "Y", "I", "K", "H1", "H2"])
+def test_short_sequences_vs_golden(fn, kode):
+    g = helpers.load_golden("seq_golden.npz")
+    z, v = g["zs"], g["vs"]
+    got, ierr, nz = helpers.cpu_bessel_seq(fn, kode, v, z, 12)
+    comp = g[f"{so.COMPANION[fn]}s_{kode}"] if fn in ("J", "Y") else None
+    check_seq(got, ierr, nz, g[f"{fn}s_{kode}"], comp, v, f"{fn} kode={kode}", z=z)
+
+
+def test_sequence_member_zero_equals_single_order():
+    """Member 0 of a length-1 'sequence' is the single-order driver bit for bit."""
+    g = helpers.load_golden("seq_golden.npz")
+    z, v = g["zs"], g["vs"]
+    for fn in ("J", "I", "K", "H1", "H2"):
+        a, ea, na = helpers.cpu_bessel_seq(fn, 1, v, z, 1)
+        b, eb, nb = helpers.cpu_bessel(fn, 1, v, z)
+        assert np.array_equal(a[0].view(np.float64), b.view(np.float64), equal_nan=True)
+        assert np.array_equal(ea, eb) and np.array_equal(na, nb)
