@@ -135,11 +135,12 @@ SPB_FN int uoik(cplx z, real fnu, int kode, int ikflg, int n, Y y, real tol, rea
 
 // I by ratios from rati normalised through the Wronskian with K_fnu, K_fnu+1.
 template <class Y>
-SPB_FN int wrsk(cplx zr, real fnu, int kode, int n, Y y, real tol, real elim, real alim) {
+SPB_FN int wrsk(cplx zr, real fnu, int kode, int n, Y y, real tol, real elim, real alim,
+                real az_known = real(-1.0)) {
     cplx cw[2];
-    int nw = bknu(zr, fnu, kode, 2, cw, tol, elim, alim);
+    int nw = bknu(zr, fnu, kode, 2, cw, tol, elim, alim, az_known);
     if (nw != 0) return (nw == -2) ? -2 : -1;
-    rati(zr, fnu, n, y, tol);
+    rati(zr, fnu, n, y, tol, az_known);
     // recur forward on I(fnu+1,z) = R(fnu,z) I(fnu,z)
     cplx cinu(1.0, 0.0);
     if (kode != 1) cinu = cplx(cos(zr.im), sin(zr.im));
@@ -575,8 +576,8 @@ enum IRegion {
 
 // First region binu() enters for a single member (n = 1); series hand-over
 // (nz < 0) and uniform "nlast" hand-backs are resolved inside binu itself.
-SPB_HD int binu_region(cplx z, real fnu, int n, real rl, real fnul) {
-    real az = cabs_(z);
+SPB_HD int binu_region(cplx z, real fnu, int n, real rl, real fnul, real az_known = real(-1.0)) {
+    real az = az_known >= real(0.0) ? az_known : cabs_(z);
     real dfnu = fnu + real(n - 1);
     if (az <= real(2.0) || !(az * az * real(0.25) > dfnu + real(1.0))) return IREG_SERIES;
     if (!(az < rl)) {

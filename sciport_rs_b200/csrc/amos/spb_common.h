@@ -174,6 +174,32 @@ SPB_HD int uchk(cplx y, real ascle, real tol) {
     return (ss < st) ? 1 : 0;
 }
 
+// Phase factors that depend on the order only: one sincos per point serves every rotation of the
+// combine step (half-angle for the J / Hankel rotations, full angle by the double-angle formulas for
+// the I / continuation factors).
+struct OrderPhase {
+    real ch, sh;  // cos, sin of (pi/2) (fnu - (inu - ir)),  ir = inu mod 2
+    real cp, sp;  // cos, sin of pi (fnu - inu)
+    int inu;
+};
+
+SPB_HD OrderPhase order_phase(real fnu) {
+    OrderPhase ph;
+    ph.inu = (int)fnu;
+    int ir = ph.inu & 1;
+    real a = (fnu - real(ph.inu - ir)) * real(SPB_HPI);
+    sincos_(a, ph.sh, ph.ch);
+    real c2 = ph.ch * ph.ch - ph.sh * ph.sh;
+    real s2 = (ph.sh + ph.sh) * ph.ch;
+    if (ir) {
+        c2 = -c2;
+        s2 = -s2;
+    }
+    ph.cp = c2;
+    ph.sp = s2;
+    return ph;
+}
+
 }  // namespace spb
 
 namespace spb {

@@ -47,6 +47,7 @@ struct Prep {
     int kreg;     // KRegion for the K pass, -1 if K is not needed
     int ierr;     // preliminary ierr (0 or 3)
     int mr;       // continuation direction (+-1)
+    real az;      // |z| = |w| (rotations and reflections keep the modulus bit for bit): shared by every pass
 };
 
 // Conservative bound on |Re(-zeta1 + zeta2 -+ w)| of the leading uniform term for
@@ -62,18 +63,18 @@ SPB_HD bool uoik_is_noop(real az, real gnu, real alim) {
     return b < alim;
 }
 
-SPB_HD int kregion(cplx w, real fnu) {
+SPB_HD int kregion(cplx w, real fnu, real az_known = real(-1.0)) {
     int inu = (int)(fnu + real(0.5));
     real dnu = fnu - real(inu);
     if (rabs(dnu) == real(0.5)) return KREG_HALF;
-    if (!(cabs_(w) > real(2.0))) return KREG_SERIES;
+    if (!((az_known >= real(0.0) ? az_known : cabs_(w)) > real(2.0))) return KREG_SERIES;
     return KREG_MILLER;
 }
 
 // Is the I evaluation at (w, fnu) simple, and in which region?
 SPB_HD int iregion_simple(cplx w, real fnu, real az, bool &simple) {
     const real rl = SPB_RL, fnul = SPB_FNUL, alim = SPB_ALIM;
-    int r = binu_region(w, fnu, 1, rl, fnul);
+    int r = binu_region(w, fnu, 1, rl, fnul, az);
     simple = true;
     if (r == IREG_MLRI || r == IREG_WRSK || r == IREG_BUNI) {
         // these are entered through uoik(ikflg=1) unless dfnu <= 1 took the direct Miller route
@@ -99,6 +100,7 @@ SPB_FN Prep prepare(int fam, cplx z, real fnu, int kode) {
     p.mr = 0;
     // anything unusual (invalid input, NaN, huge or tiny arguments) goes to the driver
     real az = cabs_(z);
+    p.az = az;
     if (!(fnu >= real(0.0)) || !(az == az) || !(az < real(32767.0)) || !(fnu < real(32767.0))) return p;
     if (fam == FAM_J || fam == FAM_I) {
         if (fam == FAM_J) {
@@ -151,7 +153,7 @@ SPB_FN Prep prepare(int fam, cplx z, real fnu, int kode) {
             left = true;
         }
     }
-    p.kreg = kregion(p.w, fnu);
+    p.kreg = kregion(p.w, fnu, az);
     if (fam == FAM_JY) left = true;  // J needs I(w) even where Y alone would not (positive real axis)
     if (left) {
         bool simple;
@@ -167,27 +169,28 @@ SPB_FN Prep prepare(int fam, cplx z, real fnu, int kode) {
 
 // One region of the I pass.  Returns the AMOS nz (>= 0) or < 0 when the region
 // wants to hand over (-> general path).
-SPB_FN int ipass_region(int region, cplx w, real fnu, int kode, cplx &val) {
+SPB_FN int ipass_region(int region, cplx w, real fnu, int kode, cplx &val, real az = real(-1.0),
+                        const OrderPhase *oph = nullptr) {
     const real tol = SPB_TOL, elim = SPB_ELIM, alim = SPB_ALIM, rl = SPB_RL;
     cplx y[1];
     y[0] = cplx(0.0, 0.0);
     int nw;
     switch (region) {
-        case IREG_SERIES: nw = seri(w, fnu, kode, 1, y, tol, elim, alim); break;
-        case IREG_ASYI: nw = asyi(w, fnu, kode, 1, y, rl, tol, elim, alim); break;
-        case IREG_MLRI: nw = mlri(w, fnu, kode, 1, y, tol); break;
-        case IREG_WRSK: nw = wrsk(w, fnu, kode, 1, y, tol, elim, alim); break;
+        case IREG_SERIES: nw = seri(w, fnu, kode, 1, y, tol, elim, alim, az); break;
+        case IREG_ASYI: nw = asyi(w, fnu, kode, 1, y, rl, tol, elim, alim, az, oph); break;
+        case IREG_MLRI: nw = mlri(w, fnu, kode, 1, y, tol, az); break;
+        case IREG_WRSK: nw = wrsk(w, fnu, kode, 1, y, tol, elim, alim, az); break;
         default: nw = -9; break;
     }
     val = y[0];
     return nw;
 }
 
-SPB_FN int kpass_region(cplx w, real fnu, int kode, cplx &val) {
+SPB_FN int kpass_region(cplx w, real fnu, int kode, cplx &val, real az = real(-1.0)) {
     const real tol = SPB_TOL, elim = SPB_ELIM, alim = SPB_ALIM;
     cplx y[1];
     y[0] = cplx(0.0, 0.0);
-    int nw = bknu(w, fnu, kode, 1, y, tol, elim, alim);
+    int nw = bknu(w, fnu, kode, 1, y, tol, elim, alim, az);
     val = y[0];
     return nw;
 }
@@ -272,7 +275,7 @@ SPB_HD cplx j_from_i(cplx z, const OrderPhase &ph, cplx ival) {
 // Combine pass results into the family value.  inz/knz are the nz codes of the
 // passes (>= 0).  Sets ierr/nz like the per-point drivers.
 SPB_FN cplx finish(int fam, const Prep &p, cplx z, real fnu, int kode, cplx ival, int inz, cplx kval, int knz,
-                   int &ierr, int &nz) {
+                   int &ierr, int &nz, const OrderPhase *oph = nullptr) {
     const real tol = SPB_TOL;
     ierr = p.ierr;
     nz = 0;
@@ -282,7 +285,7 @@ SPB_FN cplx finish(int fam, const Prep &p, cplx z, real fnu, int kode, cplx ival
         nz = inz;
         if (nz != 0) return cplx(0.0, 0.0);
         if (fam == FAM_I && !(z.re < real(0.0))) return ival;
-        const OrderPhase ph = order_phase(fnu);
+        const OrderPhase ph = oph ? *oph : order_phase(fnu);
         if (fam == FAM_I) {
             // csgn = exp(+-i pi fnu)
             cplx csgn(ph.cp, (z.im < real(0.0)) ? -ph.sp : ph.sp);
@@ -296,7 +299,7 @@ SPB_FN cplx finish(int fam, const Prep &p, cplx z, real fnu, int kode, cplx ival
         nz = knz;
         return kval;
     }
-    const OrderPhase ph = order_phase(fnu);
+    const OrderPhase ph = oph ? *oph : order_phase(fnu);
     if (fam == FAM_K) return acon_combine(p.w, ph, kode, p.mr, kval, ival, nz);
     if (fam == FAM_H1 || fam == FAM_H2) {
         int m = (fam == FAM_H1) ? 1 : 2;
@@ -334,8 +337,8 @@ SPB_FN cplx finish(int fam, const Prep &p, cplx z, real fnu, int kode, cplx ival
 
 // J and Y from one (I(w), K(w)) pair.  Same arithmetic as finish(FAM_J) and finish(FAM_Y).
 SPB_FN void finish_jy(const Prep &p, cplx z, real fnu, int kode, cplx ival, int inz, cplx kval, int knz, cplx &jv,
-                      int &jerr, int &jnz, cplx &yv, int &yerr, int &ynz) {
-    const OrderPhase ph = order_phase(fnu);
+                      int &jerr, int &jnz, cplx &yv, int &yerr, int &ynz, const OrderPhase *oph = nullptr) {
+    const OrderPhase ph = oph ? *oph : order_phase(fnu);
     jerr = p.ierr;
     yerr = p.ierr;
     jnz = inz;
@@ -436,11 +439,11 @@ SPB_FN cplx pipeline_eval(int fam, cplx z, real fnu, int kode, int &ierr, int &n
     int inz = 0, knz = 0;
     path = 2;
     if (p.ireg >= 0) {
-        inz = ipass_region(p.ireg, p.w, fnu, kode, ival);
+        inz = ipass_region(p.ireg, p.w, fnu, kode, ival, p.az);
         if (inz < 0) return general_eval(fam, z, fnu, kode, ierr, nz);
     }
     if (p.kreg >= 0) {
-        knz = kpass_region(p.w, fnu, kode, kval);
+        knz = kpass_region(p.w, fnu, kode, kval, p.az);
         if (knz < 0) return general_eval(fam, z, fnu, kode, ierr, nz);
         if (knz != 0 && (p.combine == CMB_ACON || p.combine == CMB_Y_SHARED))
             return general_eval(fam, z, fnu, kode, ierr, nz);
@@ -459,11 +462,11 @@ SPB_FN void pipeline_eval_jy(cplx z, real fnu, int kode, cplx &jv, int &jerr, in
     bool general = (p.combine == CMB_GENERAL);
     if (!general) {
         path = 2;
-        inz = ipass_region(p.ireg, p.w, fnu, kode, ival);
+        inz = ipass_region(p.ireg, p.w, fnu, kode, ival, p.az);
         if (inz < 0) general = true;
     }
     if (!general) {
-        knz = kpass_region(p.w, fnu, kode, kval);
+        knz = kpass_region(p.w, fnu, kode, kval, p.az);
         if (knz < 0 || (knz != 0 && p.combine == CMB_Y_SHARED)) general = true;
     }
     if (general) {

@@ -18,9 +18,10 @@ namespace spb {
 // Power series.  nz = -k means: k members underflowed and |z|^2/4 exceeds the
 // remaining order, so the caller must finish with another method.
 template <class Y>
-SPB_FN int seri(cplx z, real fnu, int kode, int n, Y y, real tol, real elim, real alim) {
+SPB_FN int seri(cplx z, real fnu, int kode, int n, Y y, real tol, real elim, real alim,
+                real az_known = real(-1.0)) {
     int nz = 0;
-    real az = cabs_(z);
+    real az = az_known >= real(0.0) ? az_known : cabs_(z);
     if (az == real(0.0)) {
         y[0] = cplx(fnu == real(0.0) ? 1.0 : 0.0, 0.0);
         for (int i = 1; i < n; ++i) y[i] = cplx(0.0, 0.0);
@@ -149,7 +150,8 @@ SPB_FN int seri(cplx z, real fnu, int kode, int n, Y y, real tol, real elim, rea
 // term (no division, no modulus).  The second exponential exp(-2z) is below
 // half an ulp of the leading sum once 2 Re z > 80 and is skipped there.
 template <class Y>
-SPB_FN int asyi(cplx z, real fnu, int kode, int n, Y y, real rl, real tol, real elim, real alim) {
+SPB_FN int asyi(cplx z, real fnu, int kode, int n, Y y, real rl, real tol, real elim, real alim,
+                real az_known = real(-1.0), const OrderPhase *oph = nullptr) {
     static const double RJ[48] = {
         0.0, 1.0, 1.0 / 2, 1.0 / 3, 1.0 / 4, 1.0 / 5, 1.0 / 6, 1.0 / 7, 1.0 / 8, 1.0 / 9, 1.0 / 10, 1.0 / 11,
         1.0 / 12, 1.0 / 13, 1.0 / 14, 1.0 / 15, 1.0 / 16, 1.0 / 17, 1.0 / 18, 1.0 / 19, 1.0 / 20, 1.0 / 21,
@@ -157,7 +159,7 @@ SPB_FN int asyi(cplx z, real fnu, int kode, int n, Y y, real rl, real tol, real 
         1.0 / 32, 1.0 / 33, 1.0 / 34, 1.0 / 35, 1.0 / 36, 1.0 / 37, 1.0 / 38, 1.0 / 39, 1.0 / 40, 1.0 / 41,
         1.0 / 42, 1.0 / 43, 1.0 / 44, 1.0 / 45, 1.0 / 46, 1.0 / 47};
     const real rtpi = 0.159154943091895336;  // 1/(2 pi)
-    real az = cabs_(z);
+    real az = az_known >= real(0.0) ? az_known : cabs_(z);
     const real arm = real(1.0e3) * SPB_D1MACH1;
     const real rtr1 = sqrt(arm);
     int il = n < 2 ? n : 2;
@@ -196,11 +198,16 @@ SPB_FN int asyi(cplx z, real fnu, int kode, int n, Y y, real rl, real tol, real 
     cplx e2(0.0, 0.0);
     if (z.im != real(0.0)) {
         // exp(i pi (1/2 + fnu + n - il)) with the integer part folded out
+        // sin, cos of pi (fnu - inu) come from the order phase (one sincos per distinct order, shared with the
+        // rotations of the combine step)
         int inu = (int)fnu;
-        real arg = (fnu - real(inu)) * SPB_PI;
+        OrderPhase local;
+        if (!oph) {
+            local = order_phase(fnu);
+            oph = &local;
+        }
         inu = inu + n - il;
-        real sn, cs;
-        sincos_(arg, sn, cs);
+        real sn = oph->sp, cs = oph->cp;
         real ak = -sn;
         real bk = cs;
         if (z.im < real(0.0)) bk = -bk;
@@ -255,9 +262,9 @@ SPB_FN int asyi(cplx z, real fnu, int kode, int n, Y y, real rl, real tol, real 
 // ---------------------------------------------------------------------------
 // Miller algorithm normalised by a Neumann series.  nz = -2: no convergence.
 template <class Y>
-SPB_FN int mlri(cplx z, real fnu, int kode, int n, Y y, real tol) {
+SPB_FN int mlri(cplx z, real fnu, int kode, int n, Y y, real tol, real az_known = real(-1.0)) {
     const real scle = SPB_D1MACH1 / tol;
-    real az = cabs_(z);
+    real az = az_known >= real(0.0) ? az_known : cabs_(z);
     int iaz = (int)az;
     int ifnu = (int)fnu;
     int inu = ifnu + n - 1;
@@ -388,9 +395,9 @@ SPB_FN int mlri(cplx z, real fnu, int kode, int n, Y y, real tol) {
 // Ratios cy[k] = I_{fnu+k+1}(z)/I_{fnu+k}(z), k = 0..n-1, by backward
 // recurrence started from an index chosen by a forward magnitude walk.
 template <class Y>
-SPB_FN void rati(cplx z, real fnu, int n, Y cy, real tol) {
+SPB_FN void rati(cplx z, real fnu, int n, Y cy, real tol, real az_known = real(-1.0)) {
     const real rt2 = 1.41421356237309515;
-    real az = cabs_(z);
+    real az = az_known >= real(0.0) ? az_known : cabs_(z);
     int inu = (int)fnu;
     int idnu = inu + n - 1;
     int magz = (int)az;

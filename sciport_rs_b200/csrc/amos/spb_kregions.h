@@ -131,7 +131,8 @@ SPB_FN int s1s2(cplx zr, cplx &s1, cplx &s2, real ascle, real alim, int &iuf) {
 
 // K_{fnu+k}(z), k=0..n-1, Re z >= 0.  Returns nz (>=0), -1 overflow/invalid, -2 no convergence.
 template <class Y>
-SPB_FN int bknu(cplx z, real fnu, int kode, int n, Y y, real tol, real elim, real alim) {
+SPB_FN int bknu(cplx z, real fnu, int kode, int n, Y y, real tol, real elim, real alim,
+                real az_known = real(-1.0)) {
     const int kmax = 30;
     const real r1 = 2.0;
     const real dpi = SPB_PI;
@@ -144,7 +145,7 @@ SPB_FN int bknu(cplx z, real fnu, int kode, int n, Y y, real tol, real elim, rea
     const real cc[8] = {5.77215664901532861e-01,  -4.20026350340952355e-02, -4.21977345555443367e-02,
                         7.21894324666309954e-03,  -2.15241674114950973e-04, -2.01348547807882387e-05,
                         1.13302723198169588e-06,  6.11609510448141582e-09};
-    real caz = cabs_(z);
+    real caz = az_known >= real(0.0) ? az_known : cabs_(z);
     real csclr = real(1.0) / tol;
     real crscr = tol;
     real cssr[3] = {csclr, 1.0, crscr};

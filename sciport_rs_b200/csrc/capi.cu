@@ -413,17 +413,6 @@ struct Pin {
 int run_host_slice(DeviceCtx *c, const BesselArgs &a, double *ms_out, int *launches_out) {
     std::lock_guard<std::mutex> lk(c->mu);
     CK(cudaSetDevice(c->dev));
-    Pin pz, px, pv, po, pe, pn;
-    if (a.z) pz.pin(a.z, a.n * 16);
-    if (a.x) px.pin(a.x, a.n * 8);
-    if (a.v_stride != 0) pv.pin(a.v, ((a.n - 1) * a.v_stride + 1) * 8);
-    po.pin(a.out, a.n * 16);
-    if (a.ierr) pe.pin(a.ierr, a.n * 4);
-    if (a.nz) pn.pin(a.nz, a.n * 4);
-    Pin po2, pe2, pn2;
-    if (a.out2) po2.pin(a.out2, a.n * 16);
-    if (a.ierr2) pe2.pin(a.ierr2, a.n * 4);
-    if (a.nz2) pn2.pin(a.nz2, a.n * 4);
     int launches = 0;
     int k = 0;
     double v0 = a.v[0];
@@ -482,15 +471,6 @@ int run_host_slice(DeviceCtx *c, const BesselArgs &a, double *ms_out, int *launc
 int run_host_slice_seq(DeviceCtx *c, const BesselArgs &a, int *launches_out) {
     std::lock_guard<std::mutex> lk(c->mu);
     CK(cudaSetDevice(c->dev));
-    Pin pz, px, pv, pe, pn;
-    if (a.z) pz.pin(a.z, a.n * 16);
-    if (a.x) px.pin(a.x, a.n * 8);
-    if (a.v_stride != 0) pv.pin(a.v, ((a.n - 1) * a.v_stride + 1) * 8);
-    if (a.ierr) pe.pin(a.ierr, a.n * 4);
-    if (a.nz) pn.pin(a.nz, a.n * 4);
-    // the result rows of this slice are not contiguous in the caller's array: pin row by row
-    std::vector<Pin> prow(a.n_orders);
-    for (int k = 0; k < a.n_orders; ++k) prow[k].pin(a.out + (long long)k * a.out_stride, a.n * 16);
     long long chunk = std::max<long long>(1024, ((1ll << 24) / a.n_orders) & ~1023ll);
     chunk = std::min(chunk, CHUNK_HOST);
     int launches = 0, k = 0;
@@ -578,6 +558,18 @@ int bessel_impl(int fn, int kode, const double *v, int64_t v_stride, const spb_c
     if (dptr)
         return seq ? run_device_seq(get_ctx(devs[0]), a, st, &g_last_launches)
                    : run_device(get_ctx(devs[0]), a, st, &g_last_ms, &g_last_launches);
+    // Pin the caller's buffers once for the whole call (a copy may not straddle separately registered ranges, and
+    // the slices of a multi-device call share pages at their boundaries), unless they already are pinned.
+    Pin pz, px, pv, po, pe, pn, po2, pe2, pn2;
+    if (a.z) pz.pin(a.z, n * 16);
+    if (a.x) px.pin(a.x, n * 8);
+    if (v_stride != 0) pv.pin(v, ((n - 1) * v_stride + 1) * 8);
+    po.pin(out, (size_t)n * n_orders * 16);
+    if (ierr) pe.pin(ierr, n * 4);
+    if (nz) pn.pin(nz, n * 4);
+    if (out2) po2.pin(out2, n * 16);
+    if (ierr2) pe2.pin(ierr2, n * 4);
+    if (nz2) pn2.pin(nz2, n * 4);
     const int G = (int)devs.size();
     if (G == 1)
         return seq ? run_host_slice_seq(get_ctx(devs[0]), a, &g_last_launches)

@@ -3,6 +3,11 @@
 // each a persistent grid that walks its bin segment of perm_i.  For the J and I
 // families the kernel also applies the final rotation and stores the result;
 // for K-type families it parks I(w) in itemp for the K pass.
+//
+// The walk is software-pipelined two deep: while point t is being evaluated the
+// 16-byte load of point t+stride is in flight and the permutation index of point
+// t+2*stride is being fetched, so the dependent pair of global loads
+// (perm_i -> z) never sits on the critical path of a warp.
 #include "spb_dev.cuh"
 
 namespace spbk {
@@ -12,15 +17,32 @@ __global__ void __launch_bounds__(128) k_ipass(DevJob job, Scratch s) {
     const unsigned int start = s.bins[REGION] - s.bins[0];
     const unsigned int count = s.bins[REGION + 1] - s.bins[REGION];
     const unsigned int stride = gridDim.x * blockDim.x;
+    const unsigned int *perm = s.perm_i + start;
+    unsigned int t = blockIdx.x * blockDim.x + threadIdx.x;
+    bool have1 = t < count, have2 = (t + stride) < count;
+    unsigned int i1 = have1 ? __ldg(perm + t) : 0u;
+    unsigned int i2 = have2 ? __ldg(perm + t + stride) : 0u;
+    cplx z1(0.0, 0.0);
+    double v1 = 0.0;
+    if (have1) load_point(job, i1, z1, v1);
+    PhaseCache pc;
 #pragma unroll 1
-    for (unsigned int t = blockIdx.x * blockDim.x + threadIdx.x; t < count; t += stride) {
-        const long long i = s.perm_i[start + t];
-        cplx z;
-        double v;
-        load_point(job, i, z, v);
+    while (have1) {
+        const long long i = i1;
+        const cplx z = z1;
+        const double v = v1;
+        // advance the pipeline before the arithmetic so that both loads overlap it
+        t += stride;
+        have1 = have2;
+        i1 = i2;
+        have2 = (t + stride) < count;
+        if (have2) i2 = __ldg(perm + t + stride);
+        if (have1) load_point(job, i1, z1, v1);
+
         spb::Prep p = spb::prepare(job.fam, z, v, job.kode);
+        const spb::OrderPhase *ph = pc.get(v);
         cplx ival;
-        int inz = spb::ipass_region(REGION, p.w, v, job.kode, ival);
+        int inz = spb::ipass_region(REGION, p.w, v, job.kode, ival, p.az, ph);
         if (inz < 0) {
             // the region wants to hand over: finish this point on the general path
             unsigned int g = atomicAdd(&s.bins[GLIST_LEN_SLOT], 1u);
@@ -30,7 +52,7 @@ __global__ void __launch_bounds__(128) k_ipass(DevJob job, Scratch s) {
         }
         if (p.combine == spb::CMB_I_ROT) {
             int ierr, nz;
-            cplx val = spb::finish(job.fam, p, z, v, job.kode, ival, inz, cplx(0.0, 0.0), 0, ierr, nz);
+            cplx val = spb::finish(job.fam, p, z, v, job.kode, ival, inz, cplx(0.0, 0.0), 0, ierr, nz, ph);
             store_point(job, i, val, ierr, nz);
         } else {
             s.itemp[i] = make_double2(ival.re, ival.im);

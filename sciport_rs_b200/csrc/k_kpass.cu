@@ -3,6 +3,10 @@
 // K region: Temme series / Miller / half-odd closed form), then the family's
 // combine step (rotation, analytic continuation with the parked I(w), Hankel
 // difference for Y) and the final store.
+//
+// Same two-deep software pipeline as the I pass: the point (z, v, parked I(w) and
+// its code) of iteration t+stride and the permutation index of t+2*stride are
+// loaded while iteration t computes.
 #include "spb_dev.cuh"
 
 namespace spbk {
@@ -10,38 +14,65 @@ namespace spbk {
 __global__ void __launch_bounds__(128) k_kpass(DevJob job, Scratch s) {
     const unsigned int count = s.bins[BIN_GENERAL] - s.bins[4];
     const unsigned int stride = gridDim.x * blockDim.x;
+    const unsigned int *perm = s.perm_k;
+    unsigned int t = blockIdx.x * blockDim.x + threadIdx.x;
+    bool have1 = t < count, have2 = (t + stride) < count;
+    unsigned int i1 = have1 ? __ldg(perm + t) : 0u;
+    unsigned int i2 = have2 ? __ldg(perm + t + stride) : 0u;
+    cplx z1(0.0, 0.0);
+    double v1 = 0.0;
+    double2 it1 = make_double2(0.0, 0.0);
+    int ic1 = 0;
+    if (have1) {
+        load_point(job, i1, z1, v1);
+        it1 = s.itemp[i1];
+        ic1 = s.icode[i1];
+    }
+    PhaseCache pc;
 #pragma unroll 1
-    for (unsigned int t = blockIdx.x * blockDim.x + threadIdx.x; t < count; t += stride) {
-        const long long i = s.perm_k[t];
-        cplx z;
-        double v;
-        load_point(job, i, z, v);
+    while (have1) {
+        const long long i = i1;
+        const cplx z = z1;
+        const double v = v1;
+        const double2 itv = it1;
+        const int icv = ic1;
+        t += stride;
+        have1 = have2;
+        i1 = i2;
+        have2 = (t + stride) < count;
+        if (have2) i2 = __ldg(perm + t + stride);
+        if (have1) {
+            load_point(job, i1, z1, v1);
+            it1 = s.itemp[i1];  // only meaningful where the point went through the I pass
+            ic1 = s.icode[i1];
+        }
+
         spb::Prep p = spb::prepare(job.fam, z, v, job.kode);
         cplx ival(0.0, 0.0);
         int inz = 0;
         if (p.ireg >= 0) {
-            inz = s.icode[i];
+            inz = icv;
             if (inz < 0) continue;  // already queued on the general path by the I pass
-            double2 t2 = s.itemp[i];
-            ival = cplx(t2.x, t2.y);
+            ival = cplx(itv.x, itv.y);
         }
         cplx kval;
-        int knz = spb::kpass_region(p.w, v, job.kode, kval);
+        int knz = spb::kpass_region(p.w, v, job.kode, kval, p.az);
         if (knz < 0 || (knz != 0 && (p.combine == spb::CMB_ACON || p.combine == spb::CMB_Y_SHARED))) {
             unsigned int g = atomicAdd(&s.bins[GLIST_LEN_SLOT], 1u);
             s.glist[g] = (unsigned int)i;
             continue;
         }
+        const spb::OrderPhase *ph = pc.get(v);
         int ierr, nz;
         if (job.fam == spb::FAM_JY) {
             cplx jv, yv;
             int yerr, ynz;
-            spb::finish_jy(p, z, v, job.kode, ival, inz, kval, knz, jv, ierr, nz, yv, yerr, ynz);
+            spb::finish_jy(p, z, v, job.kode, ival, inz, kval, knz, jv, ierr, nz, yv, yerr, ynz, ph);
             store_point(job, i, jv, ierr, nz);
             store_point2(job, i, yv, yerr, ynz);
             continue;
         }
-        cplx val = spb::finish(job.fam, p, z, v, job.kode, ival, inz, kval, knz, ierr, nz);
+        cplx val = spb::finish(job.fam, p, z, v, job.kode, ival, inz, kval, knz, ierr, nz, ph);
         store_point(job, i, val, ierr, nz);
     }
 }

@@ -30,6 +30,23 @@ __device__ __forceinline__ void store_point2(const DevJob &j, long long i, cplx 
     if (j.nz2) j.nz2[i] = nz;
 }
 
+// Per-thread cache of the order-dependent phase factors: one sincos per DISTINCT order a thread meets.  With a
+// broadcast scalar order (v_stride = 0) it is filled once per thread; with per-element orders it is refilled
+// per point (one compare extra).  The cached value is exactly spb::order_phase(v), so results do not depend on
+// whether the cache hit.
+struct PhaseCache {
+    double v;
+    spb::OrderPhase ph;
+    __device__ __forceinline__ PhaseCache() : v(__builtin_nan("")) {}
+    __device__ __forceinline__ const spb::OrderPhase *get(double fnu) {
+        if (!(fnu == v)) {
+            ph = spb::order_phase(fnu);
+            v = fnu;
+        }
+        return &ph;
+    }
+};
+
 // general per-point evaluation + optional oracle-compatible post-processing
 __device__ __forceinline__ void eval_general_store(const DevJob &j, long long i, cplx z, double v) {
     int ierr, nz;
