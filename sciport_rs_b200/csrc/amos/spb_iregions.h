@@ -297,7 +297,11 @@ SPB_FN int mlri(cplx z, real fnu, int kode, int n, Y y, real tol, real az_known 
         }
         ak += real(1.0);
     }
-    if (!found) return -2;
+    // No early return between the data-dependent loops: a `return` here would move the reconvergence point of
+    // the loop exits to the end of the routine, and lanes leaving the walk at different indices would run
+    // the (long) backward recurrence below in separate passes.  A failed walk is carried in `fail` instead.
+    bool fail = !found;
+    if (fail) i = 80;
     i += 1;
     int k = 0;
     if (inu >= iaz) {
@@ -329,7 +333,10 @@ SPB_FN int mlri(cplx z, real fnu, int kode, int n, Y y, real tol, real az_known 
             tst = tst * sqrt(rho / (rho * rho - real(1.0)));
             itime = 2;
         }
-        if (!found) return -2;
+        if (!found) {
+            fail = true;
+            k = 80;
+        }
     }
     // backward recurrence and sum of the normalising relation
     k += 1;
@@ -387,6 +394,10 @@ SPB_FN int mlri(cplx z, real fnu, int kode, int n, Y y, real tol, real az_known 
     real rap = real(1.0) / ap;
     cplx e = cexp_(q) * rap;
     cplx cnorm = e * (conj(p2) * rap);
+    if (fail) {
+        for (int j = 0; j < n; ++j) y[j] = cplx(0.0, 0.0);
+        return -2;
+    }
     for (int j = 0; j < n; ++j) y[j] = y[j] * cnorm;
     return 0;
 }

@@ -48,13 +48,15 @@ def by_line(rows, h, obj, kernel, top):
             where[int(m.group(1), 16)] = cur
     ai, si, ii = h.index("Address"), h.index("# Samples"), h.index("Instructions Executed")
     base = min(int(r[ai], 16) for r in rows[1:] if len(r) > ii)
-    agg = collections.defaultdict(lambda: [0, 0])
+    ti = h.index("Thread Instructions Executed")
+    agg = collections.defaultdict(lambda: [0, 0, 0])
     for r in rows[1:]:
-        if len(r) <= ii:
+        if len(r) <= max(ii, ti):
             continue
         loc = where.get(int(r[ai], 16) - base, ("(library/unknown)", 0))
         agg[loc][0] += int(r[si] or 0)
         agg[loc][1] += int(r[ii] or 0)
+        agg[loc][2] += int(r[ti] or 0)
     tot_s = sum(v[0] for v in agg.values()) or 1
     tot_i = sum(v[1] for v in agg.values()) or 1
     files = collections.defaultdict(lambda: [0, 0])
@@ -64,9 +66,9 @@ def by_line(rows, h, obj, kernel, top):
     print("per file (samples share, inst share):")
     for f, v in sorted(files.items(), key=lambda kv: -kv[1][0]):
         print(f"  {f:40s} {v[0] / tot_s:6.3f} {v[1] / tot_i:6.3f}")
-    print("hottest lines (samples share, inst share, file:line):")
-    for (f, l), v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
-        print(f"  {v[0] / tot_s:6.3f} {v[1] / tot_i:6.3f}  {f}:{l}")
+    print("hottest lines (samples share, inst share, avg active lanes, file:line):")
+    for (f, l), v in sorted(agg.items(), key=lambda kv: -kv[1][0] - kv[1][1] * tot_s / tot_i)[:top]:
+        print(f"  {v[0] / tot_s:6.3f} {v[1] / tot_i:6.3f} {v[2] / max(v[1], 1):5.1f}  {f}:{l}")
 
 
 def main():
