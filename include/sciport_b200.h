@@ -94,7 +94,9 @@ enum spb_kernel_id {
     SPB_K_IPASS_WRSK = 5,    /* I pass: Miller ratios, Wronskian normalisation       */
     SPB_K_KPASS = 6,         /* K pass + family combine                              */
     SPB_K_GENERAL = 7,       /* general per-point path                               */
-    SPB_K_MONOLITHIC = 8     /* whole batch through the general path                 */
+    SPB_K_MONOLITHIC = 8,    /* whole batch through the general path                 */
+    SPB_K_IPASS_UNI1 = 9,    /* I pass: uniform (Debye-type) expansion at raised order */
+    SPB_K_IPASS_UNI2 = 10    /* I pass: uniform (Airy-type) expansion at raised order  */
 };
 
 /* where the buffers live and which GPUs to use */

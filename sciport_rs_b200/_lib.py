@@ -14,7 +14,7 @@ FN = {"J": 0, "Y": 1, "I": 2, "K": 3, "H1": 4, "H2": 5}
 AIRY = {"Ai": 0, "Aip": 1, "Bi": 2, "Bip": 3}
 SEM_AMOS, SEM_SCIPY, PATH_MONOLITHIC, PROFILE = 0, 1, 16, 32
 KERNEL_NAMES = ["classify", "scan_scatter", "ipass_series", "ipass_asyi", "ipass_mlri", "ipass_wrsk", "kpass",
-                "general", "monolithic"]
+                "general", "monolithic", "ipass_uni1", "ipass_uni2"]
 E_ARG, E_NO_DEVICE, E_CUDA, E_ALLOC = -1, -2, -3, -4
 
 

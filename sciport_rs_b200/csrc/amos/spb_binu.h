@@ -468,12 +468,13 @@ SPB_FN int uni2(cplx z, real fnu, int kode, int n, Y y, int &nlast, real fnul, r
 // recur backward; nlast != 0 leaves the low orders for another method.
 template <class Y>
 SPB_FN int buni(cplx z, real fnu, int kode, int n, Y y, int nui, int &nlast, real fnul, real tol,
-                real elim, real alim) {
+                real elim, real alim, int iform_known = 0) {
     int nz = 0;
     real ax = rabs(z.re) * real(1.7321);
     real ay = rabs(z.im);
     int iform = 1;
     if (ay > ax) iform = 2;
+    if (iform_known != 0) iform = iform_known;  // region kernels compile one form only
     int nw;
     if (nui == 0) {
         if (iform == 2)
@@ -570,8 +571,9 @@ enum IRegion {
     IREG_ASYI = 1,    // large-|z| asymptotic
     IREG_MLRI = 2,    // Miller + Neumann normalisation (after uoik)
     IREG_WRSK = 3,    // Miller ratios + Wronskian (after uoik)
-    IREG_BUNI = 4,    // uniform asymptotics (after uoik)
-    IREG_COUNT = 5
+    IREG_UNI1 = 4,    // uniform asymptotics, Debye-type form (|Im z| <= sqrt(3) |Re z|), after uoik
+    IREG_UNI2 = 5,    // uniform asymptotics, Airy-type form, after uoik
+    IREG_COUNT = 6
 };
 
 // First region binu() enters for a single member (n = 1); series hand-over
@@ -585,7 +587,10 @@ SPB_HD int binu_region(cplx z, real fnu, int n, real rl, real fnul, real az_know
     } else if (dfnu <= real(1.0)) {
         return IREG_MLRI;
     }
-    if (dfnu > fnul || az > fnul) return IREG_BUNI;
+    if (dfnu > fnul || az > fnul) {
+        // same split as buni(): form 2 when |Im z| > 1.7321 |Re z|
+        return (rabs(z.im) > rabs(z.re) * real(1.7321)) ? IREG_UNI2 : IREG_UNI1;
+    }
     if (az > rl) return IREG_WRSK;
     return IREG_MLRI;
 }

@@ -51,15 +51,21 @@ struct Prep {
 };
 
 // Conservative bound on |Re(-zeta1 + zeta2 -+ w)| of the leading uniform term for
-// order gnu at w: if it stays below alim, uoik() returns 0 without touching y.
-SPB_HD bool uoik_is_noop(real az, real gnu, real alim) {
+// order gnu at w (x = |Re w|, az = |w|): if it stays below alim, uoik() returns 0 without touching y.
+//   zeta2 = sqrt(gnu^2 + w^2):  Re zeta2 <= sqrt(gnu^2 + x^2) <= gnu + x   (if Re zeta2 were larger, |Im zeta2|
+//           would exceed |Im w| and Re zeta2 Im zeta2 = x Im w could not hold);
+//   zeta1 = gnu ln((gnu + zeta2)/w):  gnu/az <= |(gnu + zeta2)/w| <= 1 + 2 gnu/az, so with t = az/gnu
+//           |Re zeta1| <= gnu ln(1 + 2/t + t);  pi gnu covers the branch bookkeeping of the Airy-type form;
+SPB_HD bool uoik_is_noop(real az, real gnu, real alim, real x, int kode) {
+    // scaled variants test Re(zeta2 - zeta1 - w): x <= Re zeta2 <= x + gnu, so the x terms cancel
+    if (kode != 1) x = real(0.0);
     // cheap sufficient test first (covers small orders at moderate |z| without a division or logarithm):
     // for 2^-20 <= t = az/gnu <= 2^20, ln(1 + 2/t + t) < 15.3
     if (az >= gnu * real(9.5367431640625e-07) && az <= gnu * real(1048576.0) &&
-        gnu * real(19.5) + az + az < alim)
+        gnu * real(19.5) + x < alim)
         return true;
     real t = az / gnu;
-    real b = gnu * (log(real(1.0) + real(2.0) / t + t) + real(SPB_PI) + real(1.0)) + az + az;
+    real b = gnu * (log(real(1.0) + real(2.0) / t + t) + real(SPB_PI) + real(1.0)) + x;
     return b < alim;
 }
 
@@ -72,20 +78,19 @@ SPB_HD int kregion(cplx w, real fnu, real az_known = real(-1.0)) {
 }
 
 // Is the I evaluation at (w, fnu) simple, and in which region?
-SPB_HD int iregion_simple(cplx w, real fnu, real az, bool &simple) {
+SPB_HD int iregion_simple(cplx w, real fnu, real az, bool &simple, int kode) {
     const real rl = SPB_RL, fnul = SPB_FNUL, alim = SPB_ALIM;
     int r = binu_region(w, fnu, 1, rl, fnul, az);
     simple = true;
-    if (r == IREG_MLRI || r == IREG_WRSK || r == IREG_BUNI) {
+    if (r == IREG_MLRI || r == IREG_WRSK || r == IREG_UNI1 || r == IREG_UNI2) {
         // these are entered through uoik(ikflg=1) unless dfnu <= 1 took the direct Miller route
         bool direct = (r == IREG_MLRI) && (az < rl) && (fnu <= real(1.0));
-        if (!direct && !uoik_is_noop(az, rmax(fnu, real(1.0)), alim)) simple = false;
+        if (!direct && !uoik_is_noop(az, rmax(fnu, real(1.0)), alim, rabs(w.re), kode)) simple = false;
     }
     if (r == IREG_WRSK) {
         // second pre-test on K_fnu, K_fnu+1
-        if (!uoik_is_noop(az, rmax(fnu + real(1.0), real(2.0)), alim)) simple = false;
+        if (!uoik_is_noop(az, rmax(fnu + real(1.0), real(2.0)), alim, rabs(w.re), kode)) simple = false;
     }
-    if (r == IREG_BUNI) simple = false;  // raised-order recurrences stay on the general path
     return r;
 }
 
@@ -111,17 +116,13 @@ SPB_FN Prep prepare(int fam, cplx z, real fnu, int kode) {
         }
         bool simple;
         if (az == real(0.0)) return p;
-        p.ireg = iregion_simple(p.w, fnu, az, simple);
+        p.ireg = iregion_simple(p.w, fnu, az, simple, kode);
         if (simple) p.combine = CMB_I_ROT;
         return p;
     }
     // K-type families
     if (az < real(1.0e-290) || fnu > fnul) return p;
-    if (fnu > real(2.0)) {
-        if (!uoik_is_noop(az, rmax(fnu, real(1.0)), alim)) return p;
-    } else if (fnu > real(1.0) && !(az > tol)) {
-        return p;
-    }
+    if (!(fnu > real(2.0)) && fnu > real(1.0) && !(az > tol)) return p;
     bool left;
     if (fam == FAM_K) {
         left = z.re < real(0.0);
@@ -153,11 +154,16 @@ SPB_FN Prep prepare(int fam, cplx z, real fnu, int kode) {
             left = true;
         }
     }
+    // over/underflow pre-test of the K drivers (made at the rotated point) must be a no-op
+    if (fnu > real(2.0) && !uoik_is_noop(az, rmax(fnu, real(1.0)), alim, rabs(p.w.re), kode)) {
+        p.combine = CMB_GENERAL;
+        return p;
+    }
     p.kreg = kregion(p.w, fnu, az);
     if (fam == FAM_JY) left = true;  // J needs I(w) even where Y alone would not (positive real axis)
     if (left) {
         bool simple;
-        p.ireg = iregion_simple(p.w, fnu, az, simple);
+        p.ireg = iregion_simple(p.w, fnu, az, simple, kode);
         if (!simple) {
             p.combine = CMB_GENERAL;
             p.ireg = -1;
@@ -180,6 +186,18 @@ SPB_FN int ipass_region(int region, cplx w, real fnu, int kode, cplx &val, real 
         case IREG_ASYI: nw = asyi(w, fnu, kode, 1, y, rl, tol, elim, alim, az, oph); break;
         case IREG_MLRI: nw = mlri(w, fnu, kode, 1, y, tol, az); break;
         case IREG_WRSK: nw = wrsk(w, fnu, kode, 1, y, tol, elim, alim, az); break;
+        case IREG_UNI1:
+        case IREG_UNI2: {
+            // order raised to fnul, uniform expansion there, backward recurrence (binu()'s route for
+            // |z| > fnul or fnu > fnul once the over/underflow pre-test is known to be a no-op)
+            const real fnul = SPB_FNUL;
+            int nui = (int)(fnul - fnu) + 1;
+            if (nui < 0) nui = 0;
+            int nlast = 0;
+            nw = buni(w, fnu, kode, 1, y, nui, nlast, fnul, tol, elim, alim, region == IREG_UNI1 ? 1 : 2);
+            if (nw != 0 || nlast != 0) nw = -1;  // the driver would continue with another method
+            break;
+        }
         default: nw = -9; break;
     }
     val = y[0];

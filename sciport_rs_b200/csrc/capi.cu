@@ -125,7 +125,7 @@ int ensure_scratch(ScratchSet &ss, long long n) {
         return o;
     };
     size_t o_cls = take(cap), o_pi = take(cap * 4), o_pk = take(cap * 4), o_gl = take(cap * 4),
-           o_it = take(cap * 16), o_ic = take(cap), o_bc = take((size_t)NBINS * nblocks_cap * 4), o_bins = take(32 * 4);
+           o_it = take(cap * 16), o_ic = take(cap), o_bc = take((size_t)NBINS * nblocks_cap * 4), o_bins = take(BINS_WORDS * 4);
     char *base = nullptr;
     if (cudaMalloc(&base, off) != cudaSuccess) {
         cudaGetLastError();
@@ -142,7 +142,7 @@ int ensure_scratch(ScratchSet &ss, long long n) {
     ss.s.blockcnt = (unsigned int *)(base + o_bc);
     ss.s.bins = (unsigned int *)(base + o_bins);
     ss.s.nblocks = (int)((n + TILE - 1) / TILE);
-    cudaMemset(ss.s.bins, 0, 32 * 4);  // counters of the scan's last-CTA hand-off start at zero
+    cudaMemset(ss.s.bins, 0, BINS_WORDS * 4);  // counters of the scan's last-CTA hand-off start at zero
     return SPB_OK;
 }
 
@@ -185,8 +185,10 @@ int enqueue_chunk(const DevJob &job, ScratchSet &ss, int sms, int flags, cudaStr
     launch_scan_scatter(job, ss.s, st);
     launches += 3;
     const bool ktype = !(job.fam == SPB_FN_J || job.fam == SPB_FN_I);  // K, H1, H2, Y and the JY pair
-    for (int r = 0; r < 4; ++r) {
-        p.mark(SPB_K_IPASS_SERIES + r, st);
+    static const int ipass_id[NB_I] = {SPB_K_IPASS_SERIES, SPB_K_IPASS_ASYI, SPB_K_IPASS_MLRI,
+                                       SPB_K_IPASS_WRSK,   SPB_K_IPASS_UNI1, SPB_K_IPASS_UNI2};
+    for (int r = 0; r < NB_I; ++r) {
+        p.mark(ipass_id[r], st);
         launch_ipass(job, ss.s, r, sms, st);
         ++launches;
     }
@@ -205,7 +207,7 @@ int enqueue_chunk(const DevJob &job, ScratchSet &ss, int sms, int flags, cudaStr
 // turn the recorded events into (kernel, ms, points) records; call after the stream is idle
 void collect_profile(Prof &p, const ScratchSet &ss, long long n) {
     if (!p.on) return;
-    unsigned int bins[17] = {0};
+    unsigned int bins[GLIST_LEN_SLOT + 1] = {0};
     cudaMemcpy(bins, ss.s.bins, sizeof(bins), cudaMemcpyDeviceToHost);
     for (size_t i = 0; i + 1 < p.ev.size(); ++i) {
         if (p.ids[i] < 0) continue;
@@ -213,11 +215,11 @@ void collect_profile(Prof &p, const ScratchSet &ss, long long n) {
         cudaEventElapsedTime(&ms, p.ev[i], p.ev[i + 1]);
         long long pts = n;
         int id = p.ids[i];
-        if (id >= SPB_K_IPASS_SERIES && id <= SPB_K_IPASS_WRSK) {
-            int r = id - SPB_K_IPASS_SERIES;
+        if ((id >= SPB_K_IPASS_SERIES && id <= SPB_K_IPASS_WRSK) || id == SPB_K_IPASS_UNI1 || id == SPB_K_IPASS_UNI2) {
+            int r = id == SPB_K_IPASS_UNI1 ? 4 : id == SPB_K_IPASS_UNI2 ? 5 : id - SPB_K_IPASS_SERIES;
             pts = (long long)bins[r + 1] - bins[r];
         } else if (id == SPB_K_KPASS) {
-            pts = (long long)bins[BIN_GENERAL] - bins[4];
+            pts = (long long)bins[BIN_GENERAL] - bins[BIN_K0];
         } else if (id == SPB_K_GENERAL) {
             pts = bins[GLIST_LEN_SLOT];
         }

@@ -1,5 +1,6 @@
 // k_ipass.cu — I pass of the binned pipeline: one kernel per I region
-// (power series / large-|z| asymptotic / Miller + Neumann / Miller + Wronskian),
+// (power series / large-|z| asymptotic / Miller + Neumann / Miller + Wronskian /
+// uniform expansion of Debye type / uniform expansion of Airy type),
 // each a persistent grid that walks its bin segment of perm_i.  For the J and I
 // families the kernel also applies the final rotation and stores the result;
 // for K-type families it parks I(w) in itemp for the K pass.
@@ -75,6 +76,12 @@ void launch_ipass(const DevJob &job, const Scratch &s, int region, int sms, cuda
             break;
         case spb::IREG_WRSK:
             k_ipass<spb::IREG_WRSK><<<resident_grid(k_ipass<spb::IREG_WRSK>, 128, sms), 128, 0, st>>>(job, s);
+            break;
+        case spb::IREG_UNI1:
+            k_ipass<spb::IREG_UNI1><<<resident_grid(k_ipass<spb::IREG_UNI1>, 128, sms), 128, 0, st>>>(job, s);
+            break;
+        case spb::IREG_UNI2:
+            k_ipass<spb::IREG_UNI2><<<resident_grid(k_ipass<spb::IREG_UNI2>, 128, sms), 128, 0, st>>>(job, s);
             break;
         default: break;
     }

@@ -12,7 +12,7 @@
 namespace spbk {
 
 __global__ void __launch_bounds__(128) k_kpass(DevJob job, Scratch s) {
-    const unsigned int count = s.bins[BIN_GENERAL] - s.bins[4];
+    const unsigned int count = s.bins[BIN_GENERAL] - s.bins[BIN_K0];
     const unsigned int stride = gridDim.x * blockDim.x;
     const unsigned int *perm = s.perm_k;
     unsigned int t = blockIdx.x * blockDim.x + threadIdx.x;

@@ -3,9 +3,9 @@
 //   k_classify : one thread per point (coalesced 16-byte loads); computes
 //                spb::prepare() (family rotation, I region, K region,
 //                simple/general), writes a 1-byte class and a per-tile histogram
-//                of the 8 bins.  Counts are kept as eight 16-bit fields packed in
-//                two 64-bit registers and reduced with warp shuffles, so the
-//                histogram costs 10 shuffles + 16 shared atomics per warp.
+//                of the NBINS bins.  Counts are kept as 16-bit fields packed four
+//                to a 64-bit register and reduced with warp shuffles, so the
+//                histogram costs 5 shuffles per word + <= NBINS shared atomics per warp.
 //   k_scan     : exclusive scan of the [bin][tile] histogram (bin-major) so that
 //                every (bin, tile) pair knows where its points start.
 //   k_scatter  : each thread re-reads the class bytes of 8 CONSECUTIVE points with
@@ -19,18 +19,38 @@ namespace spbk {
 
 __device__ __forceinline__ void point_bins(unsigned int c, int &bi, int &bk, bool &gen) {
     gen = (c >> 5) & 1;
-    bi = c & 7;         // 0..3, 7 = none
-    bk = (c >> 3) & 3;  // 0..2, 3 = none
+    bi = c & 7;         // 0..NB_I-1, 7 = none
+    bk = (c >> 3) & 3;  // 0..NB_K-1, 3 = none
 }
 
-// packed 16-bit counters: lo holds bins 0..3 (I regions), hi holds bins 4..7 (K regions, general)
-__device__ __forceinline__ void packed_add(unsigned int c, unsigned long long &lo, unsigned long long &hi) {
+// packed 16-bit counters, one field per bin: field f lives in word f/4 at bit 16*(f%4)
+struct Packed {
+    unsigned long long w[NWORDS];
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int k = 0; k < NWORDS; ++k) w[k] = 0;
+    }
+    __device__ __forceinline__ void bump(int f) {
+#pragma unroll
+        for (int k = 0; k < NWORDS; ++k)
+            if ((f >> 2) == k) w[k] += 1ull << (16 * (f & 3));
+    }
+    __device__ __forceinline__ unsigned int field(int f) const {
+        unsigned long long x = 0;
+#pragma unroll
+        for (int k = 0; k < NWORDS; ++k)
+            if ((f >> 2) == k) x = w[k];
+        return (unsigned int)((x >> (16 * (f & 3))) & 0xffffu);
+    }
+};
+
+__device__ __forceinline__ void packed_add(unsigned int c, Packed &p) {
     int bi, bk;
     bool gen;
     point_bins(c, bi, bk, gen);
-    if (bi != 7) lo += 1ull << (16 * bi);
-    if (bk != 3) hi += 1ull << (16 * bk);
-    if (gen) hi += 1ull << 48;
+    if (bi != 7) p.bump(bi);
+    if (bk != 3) p.bump(BIN_K0 + bk);
+    if (gen) p.bump(BIN_GENERAL);
 }
 
 __global__ void __launch_bounds__(256) k_classify(DevJob job, Scratch s) {
@@ -38,7 +58,8 @@ __global__ void __launch_bounds__(256) k_classify(DevJob job, Scratch s) {
     if (threadIdx.x < NBINS) hist[threadIdx.x] = 0;
     __syncthreads();
     const long long base = (long long)blockIdx.x * TILE;
-    unsigned long long lo = 0, hi = 0;
+    Packed cnt;
+    cnt.clear();
 #pragma unroll 2
     for (int k = threadIdx.x; k < TILE; k += 256) {
         long long i = base + k;
@@ -56,20 +77,19 @@ __global__ void __launch_bounds__(256) k_classify(DevJob job, Scratch s) {
                 c = bi | (bk << 3);
             }
             s.cls[i] = (unsigned char)c;
-            packed_add(c, lo, hi);
+            packed_add(c, cnt);
         }
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
-        lo += __shfl_xor_sync(0xffffffffu, lo, d);
-        hi += __shfl_xor_sync(0xffffffffu, hi, d);
+#pragma unroll
+        for (int k = 0; k < NWORDS; ++k) cnt.w[k] += __shfl_xor_sync(0xffffffffu, cnt.w[k], d);
     }
     if ((threadIdx.x & 31) == 0) {
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            unsigned int a = (unsigned int)((lo >> (16 * b)) & 0xffffu), h = (unsigned int)((hi >> (16 * b)) & 0xffffu);
+        for (int b = 0; b < NBINS; ++b) {
+            unsigned int a = cnt.field(b);
             if (a) atomicAdd(&hist[b], a);
-            if (h) atomicAdd(&hist[4 + b], h);
         }
     }
     __syncthreads();
@@ -126,33 +146,33 @@ __global__ void __launch_bounds__(1024) k_scan(Scratch s) {
         __syncthreads();
     }
     if (threadIdx.x == 0) {
-        s.bins[18 + b] = carry_s;  // total of this bin
+        s.bins[SLOT_TOTALS + b] = carry_s;  // total of this bin
         __threadfence();
-        unsigned int done = atomicAdd(&s.bins[17], 1u);
+        unsigned int done = atomicAdd(&s.bins[SLOT_DONE], 1u);
         if (done == NBINS - 1) {
-            // absolute starts in the concatenated order: I bins 0..3 | K bins 4..6 | general 7
+            // absolute starts in the concatenated order: I bins | K bins | general
             unsigned int acc = 0;
             for (int k = 0; k < NBINS; ++k) {
                 s.bins[k] = acc;
-                acc += ((volatile unsigned int *)s.bins)[18 + k];
+                acc += ((volatile unsigned int *)s.bins)[SLOT_TOTALS + k];
             }
             s.bins[NBINS] = acc;
-            s.bins[GLIST_LEN_SLOT] = ((volatile unsigned int *)s.bins)[18 + BIN_GENERAL];
-            s.bins[17] = 0;  // re-arm for the next chunk
+            s.bins[GLIST_LEN_SLOT] = ((volatile unsigned int *)s.bins)[SLOT_TOTALS + BIN_GENERAL];
+            s.bins[SLOT_DONE] = 0;  // re-arm for the next chunk
         }
     }
 }
 
 __global__ void __launch_bounds__(256) k_scatter(DevJob job, Scratch s) {
-    __shared__ unsigned long long warp_lo[8], warp_hi[8];
+    __shared__ unsigned long long warp_tot[8][NWORDS];
     __shared__ unsigned int tile_base[NBINS];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const long long base = (long long)blockIdx.x * TILE + (long long)threadIdx.x * 8;
     if (threadIdx.x < NBINS) {
-        // where this tile's points of bin b start inside the bin's perm array
-        unsigned int seg = threadIdx.x < 4 ? s.bins[0] : threadIdx.x < 7 ? s.bins[4] : s.bins[BIN_GENERAL];
-        tile_base[threadIdx.x] =
-            s.bins[threadIdx.x] - seg + s.blockcnt[(size_t)threadIdx.x * s.nblocks + blockIdx.x];
+        // where this tile's points of bin b start inside the bin's index array (perm_i / perm_k / glist)
+        const int b = threadIdx.x;
+        unsigned int seg = b < BIN_K0 ? s.bins[0] : b < BIN_GENERAL ? s.bins[BIN_K0] : s.bins[BIN_GENERAL];
+        tile_base[b] = s.bins[b] - seg + s.blockcnt[(size_t)b * s.nblocks + blockIdx.x];
     }
     // class bytes of 8 consecutive points in one load (tiles are 2048-aligned, so 8-byte aligned)
     unsigned long long cls8 = 0;
@@ -164,30 +184,32 @@ __global__ void __launch_bounds__(256) k_scatter(DevJob job, Scratch s) {
         valid = (int)(job.n - base);
         for (int k = 0; k < valid; ++k) cls8 |= (unsigned long long)s.cls[base + k] << (8 * k);
     }
-    unsigned long long lo = 0, hi = 0;
+    Packed mine;
+    mine.clear();
 #pragma unroll
     for (int k = 0; k < 8; ++k)
-        if (k < valid) packed_add((unsigned int)((cls8 >> (8 * k)) & 0xffu), lo, hi);
+        if (k < valid) packed_add((unsigned int)((cls8 >> (8 * k)) & 0xffu), mine);
     // block-wide exclusive scan of the packed counters (fields never exceed 2048)
-    unsigned long long ilo = lo, ihi = hi;
+    Packed incl = mine;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-        unsigned long long a = __shfl_up_sync(0xffffffffu, ilo, d);
-        unsigned long long b = __shfl_up_sync(0xffffffffu, ihi, d);
-        if (lane >= d) {
-            ilo += a;
-            ihi += b;
+#pragma unroll
+        for (int k = 0; k < NWORDS; ++k) {
+            unsigned long long a = __shfl_up_sync(0xffffffffu, incl.w[k], d);
+            if (lane >= d) incl.w[k] += a;
         }
     }
     if (lane == 31) {
-        warp_lo[wid] = ilo;
-        warp_hi[wid] = ihi;
+#pragma unroll
+        for (int k = 0; k < NWORDS; ++k) warp_tot[wid][k] = incl.w[k];
     }
     __syncthreads();
-    unsigned long long olo = ilo - lo, ohi = ihi - hi;
+    Packed off;
+#pragma unroll
+    for (int k = 0; k < NWORDS; ++k) off.w[k] = incl.w[k] - mine.w[k];
     for (int w = 0; w < wid; ++w) {
-        olo += warp_lo[w];
-        ohi += warp_hi[w];
+#pragma unroll
+        for (int k = 0; k < NWORDS; ++k) off.w[k] += warp_tot[w][k];
     }
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -197,19 +219,16 @@ __global__ void __launch_bounds__(256) k_scatter(DevJob job, Scratch s) {
         point_bins((unsigned int)((cls8 >> (8 * k)) & 0xffu), bi, bk, gen);
         const unsigned int idx = (unsigned int)(base + k);
         if (bi != 7) {
-            unsigned int off = (unsigned int)((olo >> (16 * bi)) & 0xffffu);
-            s.perm_i[tile_base[bi] + off] = idx;
-            olo += 1ull << (16 * bi);
+            s.perm_i[tile_base[bi] + off.field(bi)] = idx;
+            off.bump(bi);
         }
         if (bk != 3) {
-            unsigned int off = (unsigned int)((ohi >> (16 * bk)) & 0xffffu);
-            s.perm_k[tile_base[4 + bk] + off] = idx;
-            ohi += 1ull << (16 * bk);
+            s.perm_k[tile_base[BIN_K0 + bk] + off.field(BIN_K0 + bk)] = idx;
+            off.bump(BIN_K0 + bk);
         }
         if (gen) {
-            unsigned int off = (unsigned int)((ohi >> 48) & 0xffffu);
-            s.glist[tile_base[BIN_GENERAL] + off] = idx;
-            ohi += 1ull << 48;
+            s.glist[tile_base[BIN_GENERAL] + off.field(BIN_GENERAL)] = idx;
+            off.bump(BIN_GENERAL);
         }
     }
 }

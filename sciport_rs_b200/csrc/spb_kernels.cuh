@@ -33,15 +33,24 @@ struct Scratch {
     double2 *itemp;         // [n] I(w) for families that also need K
     signed char *icode;     // [n] nz of the I pass (<0: handed to the general path)
     unsigned int *blockcnt; // [NBINS][nblocks] per-tile histogram, then exclusive offsets
-    unsigned int *bins;     // [NBINS+1] start offsets of bins inside their perm arrays; [16] = glist length
+    unsigned int *bins;     // [NBINS+1] start offsets of bins (concatenated order); [SLOT_GLEN] = glist length
     int nblocks;            // tiles in this chunk
 };
 
-// bins: 0..3 I regions (series, asyi, mlri, wrsk), 4..6 K regions (series, miller, half), 7 general
-constexpr int NBINS = 8;
-constexpr int TILE = 2048;  // points per classification tile
-constexpr int BIN_GENERAL = 7;
-constexpr int GLIST_LEN_SLOT = 16;
+// bins: 0..5 I regions (series, asyi, mlri, wrsk, uniform form 1, uniform form 2), 6..8 K regions (series,
+// miller, half), 9 general.  The I bins index perm_i, the K bins perm_k, the general bin glist.
+constexpr int NB_I = 6;
+constexpr int NB_K = 3;
+constexpr int BIN_K0 = NB_I;
+constexpr int BIN_GENERAL = NB_I + NB_K;
+constexpr int NBINS = BIN_GENERAL + 1;
+constexpr int NWORDS = (NBINS + 3) / 4;  // packed 16-bit counters, four per 64-bit word
+constexpr int TILE = 2048;               // points per classification tile
+// slots of Scratch::bins beyond the NBINS+1 start offsets
+constexpr int GLIST_LEN_SLOT = 24;  // current length of the general list (grows when a pass hands a point over)
+constexpr int SLOT_DONE = 25;       // CTAs of k_scan that have finished
+constexpr int SLOT_TOTALS = 32;     // [NBINS] bin totals
+constexpr int BINS_WORDS = 64;
 
 // Persistent grids are sized to exactly the number of CTAs that are resident at once
 // (SM count x occupancy), so every CTA starts in the first wave and the grid-stride

@@ -17,11 +17,20 @@ def gen(cfg, n, rng):
         return np.full(n, 2.5), 10 ** (-3 + 7 * rng.random(n)) * np.exp(1j * np.pi * (2 * rng.random(n) - 1))
     if cfg == "real":
         return rng.integers(0, 2, n).astype(float), (100 * rng.random(n)).astype(np.complex128)
+    if cfg == "far":
+        # large moduli in every direction, half of them hugging the axes (small |Re w| or small |Im w| at large |w|):
+        # the corner where the over/underflow pre-test bound of prepare() is tightest
+        r = 10 ** rng.uniform(1.5, 4.5, n)
+        th = np.pi * (2 * rng.random(n) - 1)
+        snap = rng.integers(0, 4, n)
+        near = np.round(th / (np.pi / 2)) * (np.pi / 2) + 10 ** rng.uniform(-6, -0.5, n) * rng.choice([-1, 1], n)
+        th = np.where(snap < 2, near, th)
+        return 10 ** rng.uniform(-1, 1.9, n), r * np.exp(1j * th)
     v = 10 ** rng.uniform(-2, 2.3, n)
     return v, 10 ** rng.uniform(-3, 3, n) * np.exp(1j * np.pi * (2 * rng.random(n) - 1))
 
 
-@pytest.mark.parametrize("cfg", ["cfg2", "cfg3", "cfg4", "real", "wide"])
+@pytest.mark.parametrize("cfg", ["cfg2", "cfg3", "cfg4", "real", "wide", "far"])
 @pytest.mark.parametrize("fn", list(FN))
 def test_pipeline_matches_drivers(fn, cfg):
     rng = np.random.default_rng(helpers.seed_of(fn, cfg))
@@ -33,6 +42,8 @@ def test_pipeline_matches_drivers(fn, cfg):
         assert np.array_equal(ia, ib) and np.array_equal(na, nb)
     if cfg == "cfg2":
         assert (path == 0).all(), "every cfg2 point must take the binned path"
+    if cfg == "cfg3":
+        assert (path == 0).mean() > 0.99, "cfg3 (orders <= 50, |z| <= 200) must stay on the binned path"
 
 
 def test_golden_points_through_pipeline():
