@@ -576,6 +576,17 @@ enum IRegion {
     IREG_COUNT = 6
 };
 
+// Where the published algorithm raises the order to fnul and uses the Airy-type uniform expansion although
+// the order itself is below fnul (|z| > fnul, 2|z| < order^2, |arg z| > pi/3), the Miller/Wronskian route is
+// used instead as long as its recurrence length (about |z|) stays moderate: the choice of fnul as its upper
+// limit bounds the sequential cost of the recurrence, not its accuracy, and the Airy-type expansion costs
+// about six times more arithmetic per point at these moduli.  One rule for the region map, the drivers and
+// the CPU checker.
+#define SPB_WRSK_AZ_MAX 257.76407594148639 /* 3 fnul */
+SPB_HD bool wrsk_instead_of_uni2(real az, real dfnu, real fnul) {
+    return !(dfnu > fnul) && !(az > real(SPB_WRSK_AZ_MAX));
+}
+
 // First region binu() enters for a single member (n = 1); series hand-over
 // (nz < 0) and uniform "nlast" hand-backs are resolved inside binu itself.
 SPB_HD int binu_region(cplx z, real fnu, int n, real rl, real fnul, real az_known = real(-1.0)) {
@@ -589,7 +600,9 @@ SPB_HD int binu_region(cplx z, real fnu, int n, real rl, real fnul, real az_know
     }
     if (dfnu > fnul || az > fnul) {
         // same split as buni(): form 2 when |Im z| > 1.7321 |Re z|
-        return (rabs(z.im) > rabs(z.re) * real(1.7321)) ? IREG_UNI2 : IREG_UNI1;
+        if (!(rabs(z.im) > rabs(z.re) * real(1.7321))) return IREG_UNI1;
+        if (wrsk_instead_of_uni2(az, dfnu, fnul)) return IREG_WRSK;
+        return IREG_UNI2;
     }
     if (az > rl) return IREG_WRSK;
     return IREG_MLRI;
@@ -633,7 +646,8 @@ SPB_FN int binu(cplx z, real fnu, int kode, int n, Y cy, real rl, real fnul, rea
             nn -= nw;
             if (nn == 0) return nz;
             dfnu = fnu + real(nn - 1);
-            if (dfnu > fnul || az > fnul) {
+            const bool form2 = rabs(z.im) > rabs(z.re) * real(1.7321);
+            if ((dfnu > fnul || az > fnul) && !(form2 && wrsk_instead_of_uni2(az, dfnu, fnul))) {
                 // raise the order to fnul, compute there and recur backward
                 int nui = (int)(fnul - dfnu) + 1;
                 if (nui < 0) nui = 0;

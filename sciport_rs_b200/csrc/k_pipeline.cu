@@ -3,7 +3,7 @@
 //   k_classify : one thread per point (coalesced 16-byte loads); computes
 //                spb::prepare() (family rotation, I region, K region,
 //                simple/general), writes a 1-byte class and a per-tile histogram
-//                of the NBINS bins.  Counts are kept as 16-bit fields packed four
+//                of the NBINS bins.  Counts are kept as 12-bit fields packed five
 //                to a 64-bit register and reduced with warp shuffles, so the
 //                histogram costs 5 shuffles per word + <= NBINS shared atomics per warp.
 //   k_scan     : exclusive scan of the [bin][tile] histogram (bin-major) so that
@@ -23,7 +23,8 @@ __device__ __forceinline__ void point_bins(unsigned int c, int &bi, int &bk, boo
     bk = (c >> 3) & 3;  // 0..NB_K-1, 3 = none
 }
 
-// packed 16-bit counters, one field per bin: field f lives in word f/4 at bit 16*(f%4)
+// packed counters, one 12-bit field per bin (a tile has 2048 points; a count of exactly 2048 still fits):
+// field f lives in word f / 5 at bit 12 * (f % 5)
 struct Packed {
     unsigned long long w[NWORDS];
     __device__ __forceinline__ void clear() {
@@ -31,16 +32,18 @@ struct Packed {
         for (int k = 0; k < NWORDS; ++k) w[k] = 0;
     }
     __device__ __forceinline__ void bump(int f) {
+        const int word = f / FIELDS_PER_WORD, sh = FIELD_BITS * (f % FIELDS_PER_WORD);
 #pragma unroll
         for (int k = 0; k < NWORDS; ++k)
-            if ((f >> 2) == k) w[k] += 1ull << (16 * (f & 3));
+            if (word == k) w[k] += 1ull << sh;
     }
     __device__ __forceinline__ unsigned int field(int f) const {
+        const int word = f / FIELDS_PER_WORD, sh = FIELD_BITS * (f % FIELDS_PER_WORD);
         unsigned long long x = 0;
 #pragma unroll
         for (int k = 0; k < NWORDS; ++k)
-            if ((f >> 2) == k) x = w[k];
-        return (unsigned int)((x >> (16 * (f & 3))) & 0xffffu);
+            if (word == k) x = w[k];
+        return (unsigned int)((x >> sh) & ((1u << FIELD_BITS) - 1u));
     }
 };
 

@@ -44,7 +44,10 @@ constexpr int NB_K = 3;
 constexpr int BIN_K0 = NB_I;
 constexpr int BIN_GENERAL = NB_I + NB_K;
 constexpr int NBINS = BIN_GENERAL + 1;
-constexpr int NWORDS = (NBINS + 3) / 4;  // packed 16-bit counters, four per 64-bit word
+// packed per-tile counters: a tile holds 2048 points, so 12 bits per field and five fields per 64-bit word
+constexpr int FIELD_BITS = 12;
+constexpr int FIELDS_PER_WORD = 5;
+constexpr int NWORDS = (NBINS + FIELDS_PER_WORD - 1) / FIELDS_PER_WORD;
 constexpr int TILE = 2048;               // points per classification tile
 // slots of Scratch::bins beyond the NBINS+1 start offsets
 constexpr int GLIST_LEN_SLOT = 24;  // current length of the general list (grows when a pass hands a point over)
