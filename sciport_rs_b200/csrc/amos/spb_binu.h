@@ -139,7 +139,9 @@ SPB_FN int wrsk(cplx zr, real fnu, int kode, int n, Y y, real tol, real elim, re
                 real az_known = real(-1.0)) {
     cplx cw[2];
     int nw = bknu(zr, fnu, kode, 2, cw, tol, elim, alim, az_known);
-    if (nw != 0) return (nw == -2) ? -2 : -1;
+    // a failed K evaluation is reported at the end (no return between the data-dependent loops of bknu and
+    // rati, so that their exits reconverge here)
+    const bool kfail = nw != 0;
     rati(zr, fnu, n, y, tol, az_known);
     // recur forward on I(fnu+1,z) = R(fnu,z) I(fnu,z)
     cplx cinu(1.0, 0.0);
@@ -170,6 +172,10 @@ SPB_FN int wrsk(cplx zr, real fnu, int kode, int n, Y y, real tol, real elim, re
         cinu = st * cinu;
         st = y[i];
         y[i] = cinu * csclr;
+    }
+    if (kfail) {
+        for (int i = 0; i < n; ++i) y[i] = cplx(0.0, 0.0);
+        return (nw == -2) ? -2 : -1;
     }
     return 0;
 }

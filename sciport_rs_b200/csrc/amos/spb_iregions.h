@@ -434,22 +434,26 @@ SPB_FN void rati(cplx z, real fnu, int n, Y cy, real tol, real az_known = real(-
     p1 = p1 * rap1;
     p2 = p2 * rap1;
     ap2 = ap2 * rap1;
+    // the walk compares squared moduli (values stay below 1e20 here): one square root only when a test fires
+    real ap2s = ap2 * ap2, ap1s, tests = test * test;
     for (;;) {
         k += 1;
-        ap1 = ap2;
+        ap1s = ap2s;
         cplx pt = p2;
         p2 = p1 - t1 * pt;
         p1 = pt;
         t1 = t1 + rz;
-        ap2 = cabs_(p2);
-        if (ap1 <= test) continue;
+        ap2s = p2.re * p2.re + p2.im * p2.im;
+        if (ap1s <= tests) continue;
         if (itime == 2) break;
         real ak = cabs_(t1) * real(0.5);
         real flam = ak + sqrt(ak * ak - real(1.0));
-        real rho = rmin(ap2 / ap1, flam);
+        real rho = rmin(sqrt(ap2s / ap1s), flam);
         test = test1 * sqrt(rho / (rho * rho - real(1.0)));
+        tests = test * test;
         itime = 2;
     }
+    ap2 = sqrt(ap2s);
     int kk = k + 1 - id;
     real ak = real(kk);
     real t1r = ak;

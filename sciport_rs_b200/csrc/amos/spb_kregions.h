@@ -130,9 +130,12 @@ SPB_FN int s1s2(cplx zr, cplx &s1, cplx &s2, real ascle, real alim, int &iuf) {
 }
 
 // K_{fnu+k}(z), k=0..n-1, Re z >= 0.  Returns nz (>=0), -1 overflow/invalid, -2 no convergence.
+// The body reports a failed start-index search of the Miller algorithm through `noconv` instead of
+// returning on the spot: a `return` between the data-dependent loops would move the reconvergence point of
+// their exits to the end of the routine and leave a warp split for the rest of it.
 template <class Y>
-SPB_FN int bknu(cplx z, real fnu, int kode, int n, Y y, real tol, real elim, real alim,
-                real az_known = real(-1.0)) {
+SPB_FN int bknu_body(cplx z, real fnu, int kode, int n, Y y, real tol, real elim, real alim, real az_known,
+                     bool &noconv) {
     const int kmax = 30;
     const real r1 = 2.0;
     const real dpi = SPB_PI;
@@ -338,7 +341,7 @@ SPB_FN int bknu(cplx z, real fnu, int kode, int n, Y y, real tol, real elim, rea
                             break;
                         }
                     }
-                    if (!ok) return -2;
+                    if (!ok) noconv = true;
                     fk += spi * t1 * sqrt(t2 / caz);
                     fhs = rabs(real(0.25) - dnu2);
                     have_fk = true;
@@ -543,6 +546,18 @@ SPB_FN int bknu(cplx z, real fnu, int kode, int n, Y y, real tol, real elim, rea
             s2 = s2 * sc;
             p1r = csrr[kflag - 1];
         }
+    }
+    return nz;
+}
+
+template <class Y>
+SPB_FN int bknu(cplx z, real fnu, int kode, int n, Y y, real tol, real elim, real alim,
+                real az_known = real(-1.0)) {
+    bool noconv = false;
+    int nz = bknu_body(z, fnu, kode, n, y, tol, elim, alim, az_known, noconv);
+    if (noconv) {
+        for (int k = 0; k < n; ++k) y[k] = cplx(0.0, 0.0);
+        return -2;
     }
     return nz;
 }

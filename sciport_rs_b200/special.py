@@ -152,8 +152,11 @@ def bessel_jy(v, z, scaled=False, semantics="amos", profile=False, outs=None, co
         else:
             vt = torch.full((1,), float(v), dtype=torch.float64, device=zc.device)
             stride = 0
-        outs = [torch.empty(zc.shape, dtype=torch.complex128, device=zc.device) for _ in range(2)]
-        codes = [torch.empty(zc.shape, dtype=torch.int32, device=zc.device) for _ in range(4)]
+        # caller-provided device buffers are filled in place (the C ABI never allocates results)
+        if outs is None:
+            outs = [torch.empty(zc.shape, dtype=torch.complex128, device=zc.device) for _ in range(2)]
+        if codes is None:
+            codes = [torch.empty(zc.shape, dtype=torch.int32, device=zc.device) for _ in range(4)]
         with torch.cuda.device(zc.device):
             ex = make_exec(device_ptrs=True, stream=_stream_for(zc), flags=flags, devices=[zc.device.index])
             check(lib.spb_bessel_jy(kode, vt.data_ptr(), stride, zc.data_ptr(), outs[0].data_ptr(), outs[1].data_ptr(),
