@@ -692,10 +692,17 @@ int spb_airy(int which, int kode, const spb_c128 *z, spb_c128 *out, int32_t *ier
     std::lock_guard<std::mutex> lk(c->mu);
     CK(cudaSetDevice(c->dev));
     int sem = (flags & SPB_SEM_SCIPY) ? 1 : 0;
-    g_last_launches = 1;
+    g_last_launches = 0;
     if (dptr) {
         CK(cudaEventRecord(c->ev0, st));
-        launch_airy(which, kode, sem, (const double2 *)z, (double2 *)out, ierr, nz, n, st);
+        for (long long off = 0; off < n; off += CHUNK_DEVICE) {
+            long long m = std::min<long long>(CHUNK_DEVICE, n - off);
+            rc = ensure_scratch(c->scratch[0], m);
+            if (rc != SPB_OK) return rc;
+            g_last_launches += launch_airy(which, kode, sem, (const double2 *)z + off, (double2 *)out + off,
+                                           ierr ? ierr + off : nullptr, nz ? nz + off : nullptr, m, &c->scratch[0].s,
+                                           c->sms, st);
+        }
         CK(cudaEventRecord(c->ev1, st));
         CK(cudaGetLastError());
         CK(cudaEventSynchronize(c->ev1));
@@ -713,8 +720,10 @@ int spb_airy(int which, int kode, const spb_c128 *z, spb_c128 *out, int32_t *ier
         if (rc != SPB_OK) return rc;
         StageSet &s = c->stage[b];
         CK(cudaMemcpyAsync(s.z, z + off, m * 16, cudaMemcpyHostToDevice, s0));
-        launch_airy(which, kode, sem, s.z, s.out, ierr ? s.ierr : nullptr, nz ? s.nz : nullptr, m, s0);
-        ++launches;
+        rc = ensure_scratch(c->scratch[b], m);
+        if (rc != SPB_OK) return rc;
+        launches += launch_airy(which, kode, sem, s.z, s.out, ierr ? s.ierr : nullptr, nz ? s.nz : nullptr, m,
+                                &c->scratch[b].s, c->sms, s0);
         CK(cudaMemcpyAsync(out + off, s.out, m * 16, cudaMemcpyDeviceToHost, s0));
         if (ierr) CK(cudaMemcpyAsync(ierr + off, s.ierr, m * 4, cudaMemcpyDeviceToHost, s0));
         if (nz) CK(cudaMemcpyAsync(nz + off, s.nz, m * 4, cudaMemcpyDeviceToHost, s0));

@@ -1,35 +1,133 @@
-// k_airy.cu — Airy Ai, Ai', Bi, Bi' over a batch (one thread per point).
+// k_airy.cu — Airy Ai, Ai', Bi, Bi' over a batch.
+//
+// Same shape as the Bessel pipeline: a classification pass writes a region key per point (Maclaurin series,
+// K_{1/3} by Temme series / Miller algorithm, analytic continuation through I by power series / Miller /
+// large-|zeta| expansion), the shared scan + stable compaction sorts the point indices by key, and one
+// persistent kernel walks the sorted list so that the 32 lanes of a warp run the same region of the
+// algorithm.  The key only groups work: every point still goes through the complete routine, so a point whose
+// key is off by one region (the key uses |zeta| = (2/3)|z|^(3/2) and arg z without forming zeta) is merely
+// evaluated in a mixed warp.
 #include "spb_dev.cuh"
 #include "amos/spb_airy.h"
 
 namespace spbk {
 
-__global__ void __launch_bounds__(128) k_airy(int which, int kode, int sem, const double2 *z, double2 *out, int *ierr,
+// bins 0..5 of the I-bin field: 0 Maclaurin; 1 K series; 2 K Miller; 3 I series; 4 I Miller; 5 I asymptotic
+__device__ __forceinline__ unsigned int airy_key(bool bi, cplx z) {
+    const double az = spb::cabs_(z);
+    if (!(az > 1.0)) return 0u;
+    const double azeta = (2.0 / 3.0) * az * sqrt(az);
+    // Ai: K_{1/3}(zeta) directly when |arg z| <= pi/3 (Re zeta >= 0, Re z > 0); otherwise, and always for Bi,
+    // through I_{+-1/3}(zeta)
+    if (!bi && z.re >= 0.5 * az) return azeta > 2.0 ? 2u : 1u;
+    if (azeta <= 2.0 || azeta * azeta * 0.25 <= 4.0 / 3.0) return 3u;
+    return azeta < SPB_RL ? 4u : 5u;
+}
+
+__global__ void __launch_bounds__(256) k_classify_airy(int which, const double2 *z, long long n, Scratch s) {
+    __shared__ unsigned int hist[NBINS];
+    if (threadIdx.x < NBINS) hist[threadIdx.x] = 0;
+    __syncthreads();
+    const long long base = (long long)blockIdx.x * TILE;
+    unsigned int cnt[NB_I];
+#pragma unroll
+    for (int b = 0; b < NB_I; ++b) cnt[b] = 0;
+    for (int k = threadIdx.x; k < TILE; k += 256) {
+        long long i = base + k;
+        if (i < n) {
+            double2 t = __ldg(z + i);
+            unsigned int key = airy_key(which >= 2, cplx(t.x, t.y));
+            s.cls[i] = (unsigned char)(key | (3u << 3));  // no K bin, not general
+#pragma unroll
+            for (int b = 0; b < NB_I; ++b) cnt[b] += (key == (unsigned int)b);
+        }
+    }
+#pragma unroll
+    for (int b = 0; b < NB_I; ++b) {
+        unsigned int c = cnt[b];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+        if ((threadIdx.x & 31) == 0 && c) atomicAdd(&hist[b], c);
+    }
+    __syncthreads();
+    if (threadIdx.x < NBINS) s.blockcnt[(size_t)threadIdx.x * s.nblocks + blockIdx.x] = hist[threadIdx.x];
+}
+
+template <bool BI>
+__device__ __forceinline__ void airy_point(int id, int kode, int sem, cplx zz, long long i, double2 *out, int *ierr,
+                                           int *nz) {
+    int ie = 0, nzz = 0;
+    cplx val = BI ? spb::biry(zz, id, kode, ie) : spb::airy(zz, id, kode, nzz, ie);
+    if (sem) val = spb::airy_semantics(zz, val, ie);
+    out[i] = make_double2(val.re, val.im);
+    if (ierr) ierr[i] = ie;
+    if (nz) nz[i] = nzz;
+}
+
+// persistent walk over the key-sorted index list (two-deep software pipeline as in the Bessel passes)
+template <bool BI>
+__global__ void __launch_bounds__(128) k_airy_sorted(int id, int kode, int sem, const double2 *z, double2 *out,
+                                                     int *ierr, int *nz, long long n, Scratch s) {
+    const unsigned int count = (unsigned int)n;
+    const unsigned int stride = gridDim.x * blockDim.x;
+    const unsigned int *perm = s.perm_i;
+    unsigned int t = blockIdx.x * blockDim.x + threadIdx.x;
+    bool have1 = t < count, have2 = (t + stride) < count;
+    unsigned int i1 = have1 ? __ldg(perm + t) : 0u;
+    unsigned int i2 = have2 ? __ldg(perm + t + stride) : 0u;
+    double2 z1 = make_double2(0.0, 0.0);
+    if (have1) z1 = __ldg(z + i1);
+#pragma unroll 1
+    while (have1) {
+        const long long i = i1;
+        const cplx zz(z1.x, z1.y);
+        t += stride;
+        have1 = have2;
+        i1 = i2;
+        have2 = (t + stride) < count;
+        if (have2) i2 = __ldg(perm + t + stride);
+        if (have1) z1 = __ldg(z + i1);
+        airy_point<BI>(id, kode, sem, zz, i, out, ierr, nz);
+    }
+}
+
+// small batches: one thread per point in index order (no sort)
+template <bool BI>
+__global__ void __launch_bounds__(128) k_airy(int id, int kode, int sem, const double2 *z, double2 *out, int *ierr,
                                               int *nz, long long n) {
     const long long stride = (long long)gridDim.x * blockDim.x;
 #pragma unroll 1
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         double2 t = __ldg(z + i);
-        cplx zz(t.x, t.y);
-        int ie = 0, nzz = 0;
-        cplx val;
-        if (which < 2)
-            val = spb::airy(zz, which, kode, nzz, ie);
-        else
-            val = spb::biry(zz, which - 2, kode, ie);
-        if (sem) val = spb::airy_semantics(zz, val, ie);
-        out[i] = make_double2(val.re, val.im);
-        if (ierr) ierr[i] = ie;
-        if (nz) nz[i] = nzz;
+        airy_point<BI>(id, kode, sem, cplx(t.x, t.y), i, out, ierr, nz);
     }
 }
 
-void launch_airy(int which, int kode, int sem, const double2 *z, double2 *out, int *ierr, int *nz, long long n,
-                 cudaStream_t st) {
-    long long blocks = (n + 127) / 128;
-    if (blocks > 148 * 32) blocks = 148 * 32;
-    if (blocks < 1) blocks = 1;
-    k_airy<<<(int)blocks, 128, 0, st>>>(which, kode, sem, z, out, ierr, nz, n);
+int launch_airy(int which, int kode, int sem, const double2 *z, double2 *out, int *ierr, int *nz, long long n,
+                const Scratch *s, int sms, cudaStream_t st) {
+    const bool bi = which >= 2;
+    const int id = which & 1;
+    if (!s || n < 8192) {
+        long long blocks = (n + 127) / 128;
+        if (blocks > 148 * 32) blocks = 148 * 32;
+        if (blocks < 1) blocks = 1;
+        if (bi)
+            k_airy<true><<<(int)blocks, 128, 0, st>>>(id, kode, sem, z, out, ierr, nz, n);
+        else
+            k_airy<false><<<(int)blocks, 128, 0, st>>>(id, kode, sem, z, out, ierr, nz, n);
+        return 1;
+    }
+    k_classify_airy<<<s->nblocks, 256, 0, st>>>(which, z, n, *s);
+    DevJob job{};
+    job.n = n;
+    launch_scan_scatter(job, *s, st);
+    if (bi)
+        k_airy_sorted<true><<<resident_grid(k_airy_sorted<true>, 128, sms), 128, 0, st>>>(id, kode, sem, z, out, ierr, nz,
+                                                                                         n, *s);
+    else
+        k_airy_sorted<false><<<resident_grid(k_airy_sorted<false>, 128, sms), 128, 0, st>>>(id, kode, sem, z, out, ierr,
+                                                                                           nz, n, *s);
+    return 4;
 }
 
 }  // namespace spbk

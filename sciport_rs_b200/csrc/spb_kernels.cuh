@@ -80,8 +80,9 @@ void launch_kpass(const DevJob &job, const Scratch &s, int sms, cudaStream_t st)
 void launch_general(const DevJob &job, const Scratch &s, int sms, cudaStream_t st);
 void launch_monolithic(const DevJob &job, cudaStream_t st);
 void launch_sequence(const DevJob &job, int n_orders, long long out_stride, int sms, cudaStream_t st);
-void launch_airy(int which, int kode, int sem, const double2 *z, double2 *out, int *ierr, int *nz, long long n,
-                 cudaStream_t st);
+// returns the number of kernels launched; with scratch (sized for n) the points are sorted by region first
+int launch_airy(int which, int kode, int sem, const double2 *z, double2 *out, int *ierr, int *nz, long long n,
+                const Scratch *s, int sms, cudaStream_t st);
 void launch_synth(int cfg, unsigned long long seed, long long offset, long long n, long long n_total, double *v,
                   double2 *z, cudaStream_t st);
 void launch_first_error(const int *ierr, long long n, unsigned long long *packed, cudaStream_t st);
