@@ -117,7 +117,10 @@ int spbo_bessel_jy_pipeline(int kode, const double *v, int64_t v_stride, const d
 
 // Order sequences: out[k*n + i] = F_{v_i + k}(z_i), k < n_orders (J, I, K, H1, H2; Y through its Hankel pair).
 int spbo_bessel_seq(int fn, int kode, const double *v, int64_t v_stride, const double *z, double *out, int32_t *ierr,
-                    int32_t *nz, int64_t n, int n_orders, int threads) {
+                    int32_t *nz, int64_t n, int n_orders, int threads_and_mode) {
+    // bit 16 of the last argument switches the sweep off (classic sequence drivers only: cross-check)
+    const int threads = threads_and_mode & 0xffff;
+    const bool sweep = (threads_and_mode & 0x10000) == 0;
     parallel_for(n, threads, [=](int64_t lo, int64_t hi) {
         std::vector<cplx> cy(n_orders), cw(n_orders);
         for (int64_t i = lo; i < hi; ++i) {
@@ -126,8 +129,20 @@ int spbo_bessel_seq(int fn, int kode, const double *v, int64_t v_stride, const d
             int ie = 0, nzz = 0;
             for (int k = 0; k < n_orders; ++k) cy[k] = cplx(0.0, 0.0);
             switch (fn) {
-                case FN_J: nzz = besj(zz, fnu, kode, n_orders, cy.data(), ie); break;
-                case FN_I: nzz = besi(zz, fnu, kode, n_orders, cy.data(), ie); break;
+                // J and I sweeps: the write-once two-pass recurrence (spb_sweep.h) where it applies, the classic
+                // sequence driver where it declines — the same rule the CUDA sequence kernels follow
+                case FN_J: {
+                    bool declined = true;
+                    if (sweep) nzz = besj_sweep(zz, fnu, kode, n_orders, cy.data(), ie, declined);
+                    if (declined) nzz = besj(zz, fnu, kode, n_orders, cy.data(), ie);
+                    break;
+                }
+                case FN_I: {
+                    bool declined = true;
+                    if (sweep) nzz = besi_sweep(zz, fnu, kode, n_orders, cy.data(), ie, declined);
+                    if (declined) nzz = besi(zz, fnu, kode, n_orders, cy.data(), ie);
+                    break;
+                }
                 case FN_K: nzz = besk(zz, fnu, kode, n_orders, cy.data(), ie); break;
                 case FN_H1: nzz = besh(zz, fnu, kode, 1, n_orders, cy.data(), ie); break;
                 case FN_H2: nzz = besh(zz, fnu, kode, 2, n_orders, cy.data(), ie); break;

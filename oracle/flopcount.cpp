@@ -45,6 +45,7 @@ inline counted atan2(counted a, counted b) { g_ops += 30; return counted(std::at
 inline counted pow(counted a, counted b) { g_ops += 60; return counted(std::pow(a.v, b.v)); }
 inline bool signbit(counted a) { return std::signbit(a.v); }
 
+inline counted fma_(counted a, counted b, counted c) { return a * b + c; }
 #define SPB_REAL counted
 #include "../sciport_rs_b200/csrc/amos/spb_family.h"
 

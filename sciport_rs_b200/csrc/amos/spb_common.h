@@ -73,6 +73,16 @@ SPB_HD real rabs(real x) { return fabs(x); }
 SPB_HD real rmax(real a, real b) { return a > b ? a : b; }
 SPB_HD real rmin(real a, real b) { return a < b ? a : b; }
 
+// explicit fused multiply-add (never left to the compiler's contraction rules where two code paths must agree
+// bit for bit); an op-counting scalar type supplies its own overload
+SPB_HD double fma_(double a, double b, double c) {
+#if defined(__CUDA_ARCH__)
+    return fma(a, b, c);
+#else
+    return __builtin_fma(a, b, c);
+#endif
+}
+
 // |z| without premature over/underflow (the ZABS of the algorithm).
 SPB_HD real cabs_(cplx z) {
     real u = rabs(z.re), v = rabs(z.im);

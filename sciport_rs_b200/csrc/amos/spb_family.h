@@ -20,6 +20,7 @@
 #include "spb_common.h"
 #include "spb_binu.h"
 #include "spb_drivers.h"
+#include "spb_sweep.h"
 
 namespace spb {
 

@@ -1,0 +1,237 @@
+// spb_sweep.h — order sweeps  I_{fnu+k}(w)  /  J_{fnu+k}(z),  k = 0..n-1,  written ONCE per member.
+//
+// BASELINE config 5 (J_n(z), n = 0..255 per point, output [order][point]) is bound by its 16-byte stores, so
+// the sequence form of the classic driver — which keeps the members in an array and re-reads the two it has
+// just written at every step of its recurrences — is the wrong shape for a GPU.  This routine produces the
+// same quantities from the same ingredients the published algorithm uses for its Miller / Wronskian route
+// (ratios by backward recurrence started from an index found by a forward magnitude walk; normalisation
+// through  I_v K_{v+1} + I_{v+1} K_v = 1/w  with K from bknu), arranged as two passes over the recurrence:
+//
+//   pass A  runs the backward recurrence from the start index down to order fnu in registers, rescaling by
+//           2^-200 whenever the iterate grows past 2^200 and counting the rescalings; its last two iterates
+//           give the ratio I_{fnu+1}/I_{fnu}, hence (Wronskian) I_fnu itself and the normalising factor;
+//   pass B  repeats the identical recurrence (same seeds, same rescalings, so the same rounding) and stores
+//           member k as  factor * iterate * 2^(-200 j)  the moment it appears, j = rescalings still to come.
+//
+// Members whose modulus is below exp(-elim) are flushed to zero and counted in nz, as the sequence drivers do
+// for the leading (highest-order) members.  The routine DECLINES (returns < 0 before storing anything) for
+// arguments near the exponent limits or outside its cost envelope; the caller then uses the classic sequence
+// driver, so every input is still served.
+#pragma once
+#include "spb_common.h"
+#include "spb_kregions.h"
+#include "spb_drivers.h"
+
+namespace spb {
+
+#define SPB_SWEEP_AZ_MAX 1024.0
+#define SPB_SWEEP_MIN_ORDERS 16
+#define SPB_SWEEP_BIG 1.6069380442589903e+60    /* 2^200 */
+#define SPB_SWEEP_SMALL 6.2230152778611417e-61  /* 2^-200 */
+
+// One step of the backward recurrence, a * c + b, with the fused multiply-adds written out in a fixed order:
+// pass A and pass B must round identically (their rescaling counts are compared), whatever the compiler would
+// otherwise contract, and the same holds between the CPU checker and the device.
+SPB_HD cplx sweep_step(cplx a, cplx c, cplx b) {
+    return cplx(fma_(a.re, c.re, fma_(-a.im, c.im, b.re)), fma_(a.re, c.im, fma_(a.im, c.re, b.im)));
+}
+
+// unit^m for unit in {1, i, -1, -i} (exact)
+SPB_HD cplx unit_pow(cplx unit, int m) {
+    cplx r(1.0, 0.0);
+    m &= 3;
+    for (int i = 0; i < m; ++i) r = r * unit;
+    return r;
+}
+
+// y[k] = rot_k * I_{fnu+k}(w), rot_k = csgn0 * step^k (step a unit: 1, +-i or -1), Re w >= 0, az = |w|.
+// rotate = false skips the rotation (rot_k = 1).  Returns nz >= 0, or -1 when it declines.
+template <class Y>
+SPB_FN int isweep(cplx w, real fnu, int kode, int n, Y y, real az, bool rotate, cplx csgn0, cplx step) {
+    const real tol = SPB_TOL, elim = SPB_ELIM, alim = SPB_ALIM;
+    // short sequences stay with the classic drivers (cheap there, and a direct evaluation of so few members is
+    // slightly more accurate than the ratio / Wronskian route)
+    if (n < SPB_SWEEP_MIN_ORDERS || !(az > real(0.0)) || !(az <= real(SPB_SWEEP_AZ_MAX))) return -1;
+    if (kode == 1 && !(w.re < alim)) return -1;
+    // K_fnu(w), K_fnu+1(w) scaled by e^w (never underflow that way; failure or a set-to-zero member declines)
+    cplx ck[2];
+    ck[0] = cplx(0.0, 0.0);
+    ck[1] = cplx(0.0, 0.0);
+    const int nw = bknu(w, fnu, 2, 2, ck, tol, elim, alim, az);
+    // ---- start index: forward magnitude walk of the ratio algorithm (squared moduli)
+    const int inu = (int)fnu;
+    const int idnu = inu + n - 1;
+    const int magz = (int)az;
+    const real amagz = real(magz + 1);
+    const real fdnu = real(idnu);
+    const real fnup = rmax(amagz, fdnu);
+    int id = idnu - magz - 1;
+    if (id > 0) id = 0;
+    const cplx rz = crecip(w) * real(2.0);
+    int k = 1;
+    {
+        cplx t1 = rz * fnup;
+        cplx p2 = -t1;
+        cplx p1(1.0, 0.0);
+        t1 = t1 + rz;
+        real ap2s = p2.re * p2.re + p2.im * p2.im;
+        real ap1s;
+        const real test1s = real(2.0) * sqrt(ap2s) / tol;  // (sqrt(2 |p2| / tol))^2
+        real tests = test1s;
+        int itime = 1;
+        for (;;) {
+            k += 1;
+            ap1s = ap2s;
+            cplx pt = p2;
+            p2 = p1 - t1 * pt;
+            p1 = pt;
+            t1 = t1 + rz;
+            ap2s = p2.re * p2.re + p2.im * p2.im;
+            if (ap1s <= tests && k < 100000) continue;
+            if (itime == 2) break;
+            real ak = cabs_(t1) * real(0.5);
+            real flam = ak + sqrt(ak * ak - real(1.0));
+            real rho = rmin(sqrt(ap2s / ap1s), flam);
+            tests = test1s * (rho / (rho * rho - real(1.0)));
+            itime = 2;
+        }
+    }
+    const int kk = k + 1 - id;
+    const int steps = kk + n - 1;
+    const real dfnu = fnu + real(n - 1);
+    // ---- pass A: recurrence in registers, count the rescalings
+    int etot = 0;
+    cplx p1(1.0, 0.0), p2(0.0, 0.0);
+    {
+        real t1r = real(kk);
+        for (int i = 1; i <= steps; ++i) {
+            cplx pt = p1;
+            p1 = sweep_step(pt, rz * (dfnu + t1r), p2);
+            p2 = pt;
+            t1r -= real(1.0);
+            if (rmax(rabs(p1.re), rabs(p1.im)) > real(SPB_SWEEP_BIG)) {
+                p1 = p1 * real(SPB_SWEEP_SMALL);
+                p2 = p2 * real(SPB_SWEEP_SMALL);
+                etot += 1;
+            }
+        }
+    }
+    if (p1.re == real(0.0) && p1.im == real(0.0)) p1 = cplx(tol, tol);
+    // ---- I_fnu from the Wronskian:  I_fnu = e^{i Im w} / (w (r K_fnu + K_fnu+1)),  r = I_fnu+1 / I_fnu
+    cplx q;
+    {
+        const cplx r = cdiv(p2, p1);
+        const cplx ct = w * (r * ck[0] + ck[1]);
+        const real act = cabs_(ct);
+        const real ract = real(1.0) / act;
+        real sn, cs;
+        sincos_(w.im, sn, cs);
+        cplx cinu(cs, sn);
+        if (kode == 1) cinu = cinu * exp(w.re);
+        const cplx ifnu = (cinu * ract) * (conj(ct) * ract);
+        // normalising factor q = I_fnu / (bottom iterate)
+        const real bm = real(1.0) / cabs_(p1);
+        q = (ifnu * conj(p1 * bm)) * bm;
+        // a failed K evaluation or non-finite factor: decline before anything is stored
+        if (nw != 0 || !(q.re == q.re) || !(q.im == q.im) || !(rabs(q.re) <= real(SPB_D1MACH2)) ||
+            !(rabs(q.im) <= real(SPB_D1MACH2)))
+            return -1;
+    }
+    // ---- pass B: same recurrence, store each member once (top order first)
+    const real flush = 3.9222272510438042e-305;  // exp(-elim)
+    const real rtol = real(1.0) / tol;
+    const real ascle = SPB_D1MACH1 * rtol * real(1.0e3);
+    cplx rot(1.0, 0.0), unstep(1.0, 0.0);
+    if (rotate) {
+        rot = csgn0 * unit_pow(step, n - 1);
+        unstep = conj(step);
+    }
+    int nz = 0;
+    bool leading = true;
+    {
+        int e = 0;
+        int member = n;  // next member to store is member - 1
+        real t1r = real(kk);
+        cplx a(1.0, 0.0), b(0.0, 0.0);
+        for (int i = 1; i <= steps; ++i) {
+            cplx pt = a;
+            a = sweep_step(pt, rz * (dfnu + t1r), b);
+            b = pt;
+            t1r -= real(1.0);
+            if (rmax(rabs(a.re), rabs(a.im)) > real(SPB_SWEEP_BIG)) {
+                a = a * real(SPB_SWEEP_SMALL);
+                b = b * real(SPB_SWEEP_SMALL);
+                e += 1;
+            }
+            if (i < kk) continue;
+            member -= 1;
+            const int j = etot - e;  // rescalings still to come: true size is 2^(-200 j) of the iterate
+            cplx val(0.0, 0.0);
+            if (j <= 5) {
+                cplx s = a;
+                for (int t = 0; t < j; ++t) s = s * real(SPB_SWEEP_SMALL);
+                val = s * q;
+                if (!(rmax(rabs(val.re), rabs(val.im)) >= flush)) val = cplx(0.0, 0.0);
+            }
+            const bool zero = (val.re == real(0.0) && val.im == real(0.0));
+            if (zero && leading) nz += 1;
+            if (!zero) leading = false;
+            if (rotate) {
+                if (!zero) val = rot_guard(val, rot, rtol, ascle, tol);
+                rot = rot * unstep;
+            }
+            y[member] = val;
+        }
+    }
+    return nz;
+}
+
+// J_{fnu+k}(z), k < n, through the sweep.  declined = true: nothing was stored, use besj().
+template <class Y>
+SPB_FN int besj_sweep(cplx z, real fnu, int kode, int n, Y cy, int &ierr, bool &declined) {
+    ierr = 0;
+    declined = true;
+    if (!(fnu >= real(0.0)) || !(fnu < real(32000.0)) || n < 2 || n > 100000) return 0;
+    if (!(z.re == z.re) || !(z.im == z.im)) return 0;
+    const real az = cabs_(z);
+    const OrderPhase ph = order_phase(fnu);
+    cplx csgn(ph.ch, ph.sh);
+    if ((ph.inu / 2) % 2 == 1) csgn = -csgn;
+    cplx zn(z.im, -z.re);
+    real cii = 1.0;
+    if (z.im < real(0.0)) {
+        zn = -zn;
+        csgn.im = -csgn.im;
+        cii = -cii;
+    }
+    const int nz = isweep(zn, fnu, kode, n, cy, az, true, csgn, cplx(0.0, cii));
+    if (nz < 0) return 0;
+    declined = false;
+    return nz;
+}
+
+// I_{fnu+k}(z), k < n, through the sweep.  declined = true: nothing was stored, use besi().
+template <class Y>
+SPB_FN int besi_sweep(cplx z, real fnu, int kode, int n, Y cy, int &ierr, bool &declined) {
+    ierr = 0;
+    declined = true;
+    if (!(fnu >= real(0.0)) || !(fnu < real(32000.0)) || n < 2 || n > 100000) return 0;
+    if (!(z.re == z.re) || !(z.im == z.im)) return 0;
+    const real az = cabs_(z);
+    cplx zn = z;
+    cplx csgn(1.0, 0.0);
+    bool rotate = false;
+    if (z.re < real(0.0)) {
+        zn = -z;
+        const OrderPhase ph = order_phase(fnu);
+        csgn = cplx(ph.cp, (z.im < real(0.0)) ? -ph.sp : ph.sp);
+        if (ph.inu % 2 != 0) csgn = -csgn;
+        rotate = true;
+    }
+    const int nz = isweep(zn, fnu, kode, n, cy, az, rotate, csgn, cplx(-1.0, 0.0));
+    if (nz < 0) return 0;
+    declined = false;
+    return nz;
+}
+
+}  // namespace spb

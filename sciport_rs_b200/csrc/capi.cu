@@ -292,8 +292,9 @@ int run_device_seq(DeviceCtx *c, const BesselArgs &a, cudaStream_t st, int *laun
         job.ierr = a.ierr ? a.ierr + off : nullptr;
         job.nz = a.nz ? a.nz + off : nullptr;
         job.n = m;
-        launch_sequence(job, a.n_orders, a.out_stride, c->sms, st);
-        ++launches;
+        int rc = ensure_scratch(c->scratch[0], m);
+        if (rc != SPB_OK) return rc;
+        launches += launch_sequence(job, a.n_orders, a.out_stride, c->scratch[0].s, c->sms, st);
     }
     CK(cudaEventRecord(c->ev1, st));
     CK(cudaGetLastError());
@@ -516,8 +517,9 @@ int run_host_slice_seq(DeviceCtx *c, const BesselArgs &a, int *launches_out) {
         job.ierr = a.ierr ? s.ierr : nullptr;
         job.nz = a.nz ? s.nz : nullptr;
         job.n = m;
-        launch_sequence(job, a.n_orders, m, c->sms, st);
-        ++launches;
+        rc = ensure_scratch(c->scratch[b], m);
+        if (rc != SPB_OK) return rc;
+        launches += launch_sequence(job, a.n_orders, m, c->scratch[b].s, c->sms, st);
         CK(cudaMemcpy2DAsync(a.out + off, a.out_stride * 16, s.seq, m * 16, m * 16, a.n_orders, cudaMemcpyDeviceToHost,
                              st));
         if (a.ierr) CK(cudaMemcpyAsync(a.ierr + off, s.ierr, m * 4, cudaMemcpyDeviceToHost, st));

@@ -1,17 +1,60 @@
 // k_sequence.cu — order sequences: out[k*stride + i] = F_{v_i + k}(z_i), k = 0..n_orders-1 (BASELINE config 5:
-// J_n(z), n = 0..255 per point).  One thread per point runs the sequence form of the driver (series /
-// asymptotic / Miller / uniform expansions for the top members, then the backward recurrence in the order),
-// writing every member straight into its [order][point] slot through a strided view, so that at each order
-// the 32 lanes of a warp store 32 consecutive double2 values (coalesced) and no per-thread array exists.
-// The recurrences re-read the two members just written (L1/L2 hits).
+// J_n(z), n = 0..255 per point; 16 bytes stored per eval, so the path is bound by its stores).
+//
+//   k_sweep     J and I families: the write-once two-pass recurrence of amos/spb_sweep.h.  One thread per
+//               point; every member is produced in registers and stored exactly once, as one 16-byte store
+//               into its [order][point] slot, so at each order the lanes of a warp write consecutive double2
+//               values.  Points the sweep declines (arguments near the exponent limits, very large |z|, short
+//               sequences) are appended to a list.
+//   k_sequence  the classic sequence form of the drivers through a strided view of the result array (members
+//               are re-read by the recurrences): K, H1, H2, Y sequences, and the points k_sweep declined.
 #include "spb_dev.cuh"
 
 namespace spbk {
 
-__global__ void __launch_bounds__(128) k_sequence(DevJob job, int n_orders, long long out_stride) {
+// store-only view of one point's column of the [order][point] result: y[k] = value is one 128-bit store
+struct SeqStore {
+    double2 *base;
+    long long stride;
+    struct Slot {
+        double2 *p;
+        __device__ __forceinline__ void operator=(const cplx &v) const { *p = make_double2(v.re, v.im); }
+    };
+    __device__ __forceinline__ Slot operator[](int k) const { return Slot{base + (long long)k * stride}; }
+};
+
+__global__ void __launch_bounds__(128) k_sweep(DevJob job, int n_orders, long long out_stride, unsigned int *list,
+                                               unsigned int *list_len) {
     const long long stride = (long long)gridDim.x * blockDim.x;
 #pragma unroll 1
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < job.n; i += stride) {
+        cplx z;
+        double v;
+        load_point(job, i, z, v);
+        SeqStore y{job.out + i, out_stride};
+        int ierr = 0, nz = 0;
+        bool declined = true;
+        if (job.fam == spb::FAM_J)
+            nz = spb::besj_sweep(z, v, job.kode, n_orders, y, ierr, declined);
+        else
+            nz = spb::besi_sweep(z, v, job.kode, n_orders, y, ierr, declined);
+        if (declined) {
+            list[atomicAdd(list_len, 1u)] = (unsigned int)i;
+            continue;
+        }
+        if (job.ierr) job.ierr[i] = ierr;
+        if (job.nz) job.nz[i] = nz;
+    }
+}
+
+// classic sequence drivers; list == nullptr: every point of the chunk, else the listed points
+__global__ void __launch_bounds__(128) k_sequence(DevJob job, int n_orders, long long out_stride,
+                                                  const unsigned int *list, const unsigned int *list_len) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long count = list ? (long long)*list_len : job.n;
+#pragma unroll 1
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < count; t += stride) {
+        const long long i = list ? (long long)list[t] : t;
         cplx z;
         double v;
         load_point(job, i, z, v);
@@ -50,8 +93,17 @@ __global__ void __launch_bounds__(128) k_sequence(DevJob job, int n_orders, long
     }
 }
 
-void launch_sequence(const DevJob &job, int n_orders, long long out_stride, int sms, cudaStream_t st) {
-    k_sequence<<<resident_grid(k_sequence, 128, sms), 128, 0, st>>>(job, n_orders, out_stride);
+int launch_sequence(const DevJob &job, int n_orders, long long out_stride, const Scratch &s, int sms,
+                    cudaStream_t st) {
+    if (job.fam == spb::FAM_J || job.fam == spb::FAM_I) {
+        unsigned int *len = s.bins + GLIST_LEN_SLOT;
+        cudaMemsetAsync(len, 0, sizeof(unsigned int), st);
+        k_sweep<<<resident_grid(k_sweep, 128, sms), 128, 0, st>>>(job, n_orders, out_stride, s.glist, len);
+        k_sequence<<<resident_grid(k_sequence, 128, sms), 128, 0, st>>>(job, n_orders, out_stride, s.glist, len);
+        return 2;
+    }
+    k_sequence<<<resident_grid(k_sequence, 128, sms), 128, 0, st>>>(job, n_orders, out_stride, nullptr, nullptr);
+    return 1;
 }
 
 }  // namespace spbk

@@ -79,7 +79,8 @@ void launch_ipass(const DevJob &job, const Scratch &s, int region, int sms, cuda
 void launch_kpass(const DevJob &job, const Scratch &s, int sms, cudaStream_t st);
 void launch_general(const DevJob &job, const Scratch &s, int sms, cudaStream_t st);
 void launch_monolithic(const DevJob &job, cudaStream_t st);
-void launch_sequence(const DevJob &job, int n_orders, long long out_stride, int sms, cudaStream_t st);
+int launch_sequence(const DevJob &job, int n_orders, long long out_stride, const Scratch &s, int sms,
+                    cudaStream_t st);
 // returns the number of kernels launched; with scratch (sized for n) the points are sorted by region first
 int launch_airy(int which, int kode, int sem, const double2 *z, double2 *out, int *ierr, int *nz, long long n,
                 const Scratch *s, int sms, cudaStream_t st);

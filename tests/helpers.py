@@ -56,8 +56,9 @@ def cpu_bessel(fn, kode, v, z, sem=0, pipeline=False, threads=8):
     return out, ierr, nz
 
 
-def cpu_bessel_seq(fn, kode, v, z, n_orders, threads=8):
-    """Order sequence F_{v+k}(z), k < n_orders, on the CPU checker: ((n_orders, n) values, ierr[n], nz[n])."""
+def cpu_bessel_seq(fn, kode, v, z, n_orders, threads=8, classic=False):
+    """Order sequence F_{v+k}(z), k < n_orders, on the CPU checker: ((n_orders, n) values, ierr[n], nz[n]).
+    classic=True forces the classic sequence drivers (no write-once sweep) for J and I."""
     lib = oracle_lib()
     z = np.ascontiguousarray(z, dtype=np.complex128).ravel()
     v = np.ascontiguousarray(np.broadcast_to(np.asarray(v, dtype=np.float64), z.shape))
@@ -65,7 +66,7 @@ def cpu_bessel_seq(fn, kode, v, z, n_orders, threads=8):
     ierr = np.empty(z.size, np.int32)
     nz = np.empty(z.size, np.int32)
     lib.spbo_bessel_seq(FN[fn], kode, v.ctypes.data, 1, z.ctypes.data, out.ctypes.data, ierr.ctypes.data,
-                        nz.ctypes.data, z.size, n_orders, threads)
+                        nz.ctypes.data, z.size, n_orders, threads | (0x10000 if classic else 0))
     return out, ierr, nz
 
 

@@ -34,12 +34,18 @@ def check_seq(got, ierr, nz, want, comp, v0, label, z=None):
             c = np.where(order <= np.abs(z)[None, :], c, 0.0)
         scale = np.maximum(scale, c)
     err = so.mismatch(got, want, scale)
-    # members the algorithm zeroes by underflow (nz) are below 1e-305 in the oracle as well
-    live = np.isfinite(want.real) & np.isfinite(want.imag) & (np.abs(want) > 1e-300) & (ierr[None, :] == 0)
+    # Underflow band: below exp(-alim) = 1.8e-289 the reference flushes a member to zero or keeps it depending on
+    # rounding noise in its negligible component (the `uchk` test of the algorithm: J_177(-3) = 4e-292 is
+    # flushed, J_176(-3) = 5e-290 is kept); the write-once sweep flushes on the modulus at exp(-elim) = 3.9e-305.
+    # Both count as underflow: inside the band either a zero or the value itself is accepted.
+    BAND = 2e-288
+    live = np.isfinite(want.real) & np.isfinite(want.imag) & (np.abs(want) >= BAND) & (ierr[None, :] == 0)
     bad = live & (err > seq_tolerance(want, v0, n_orders))
     assert not bad.any(), f"{label}: {bad.sum()} mismatches, worst {np.where(live, err, 0).max():.2e}"
-    dead = (np.abs(want) < 1e-305) & (ierr[None, :] == 0)
-    assert np.all(np.abs(got[dead]) < 1e-300), f"{label}: underflowed members must be (near) zero"
+    band = np.isfinite(want.real) & (np.abs(want) < BAND) & (ierr[None, :] == 0)
+    assert np.all(np.abs(got[band]) < 10 * BAND), f"{label}: members in the underflow band must stay there"
+    inband = band & (np.abs(want) > 1e-300) & (got != 0)
+    assert np.all(err[inband] <= 1e-9), f"{label}: kept members of the underflow band must still be accurate"
     return np.where(live, err, 0).max()
 
 
@@ -52,6 +58,9 @@ def test_j_sweep_0_255_vs_golden(kode):
     check_seq(got, ierr, nz, g[f"J5_{kode}"], g[f"Y5_{kode}"], np.zeros(z.size), f"J sweep kode={kode}", z=z)
     # nz counts the leading (highest-order) members that underflowed
     assert np.array_equal(nz, (got == 0).sum(axis=0))
+    # the classic sequence driver (array form, re-reading its members) agrees with the write-once sweep
+    classic, ierr_c, nz_c = helpers.cpu_bessel_seq("J", kode, 0.0, z, 256, classic=True)
+    check_seq(got, ierr, nz, classic, g[f"Y5_{kode}"], np.zeros(z.size), f"sweep vs classic kode={kode}", z=z)
 
 
 @pytest.mark.parametrize("kode", [1, 2])
