@@ -83,6 +83,27 @@ SPB_HD double fma_(double a, double b, double c) {
 #endif
 }
 
+// 2^e for -1022 <= e <= 1023 (exact, built from the exponent field)
+SPB_HD double pow2_(int e) {
+#if defined(__CUDA_ARCH__)
+    return __longlong_as_double((long long)(1023 + e) << 52);
+#else
+    union {
+        unsigned long long u;
+        double d;
+    } x;
+    x.u = (unsigned long long)(1023 + e) << 52;
+    return x.d;
+#endif
+}
+
+// largest value of x among the currently converged lanes of the warp (device); the value itself on the host
+#if defined(__CUDA_ARCH__)
+#define SPB_WARP_MAX(x) __reduce_max_sync(__activemask(), (x))
+#else
+#define SPB_WARP_MAX(x) (x)
+#endif
+
 // |z| without premature over/underflow (the ZABS of the algorithm).
 SPB_HD real cabs_(cplx z) {
     real u = rabs(z.re), v = rabs(z.im);

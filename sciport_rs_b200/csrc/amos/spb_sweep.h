@@ -25,6 +25,7 @@
 namespace spb {
 
 #define SPB_SWEEP_AZ_MAX 1024.0
+#define SPB_SWEEP_AZ_MIN 9.765625e-4 /* 2^-10: bounds the growth per recurrence step (see the rescaling test) */
 #define SPB_SWEEP_MIN_ORDERS 16
 #define SPB_SWEEP_BIG 1.6069380442589903e+60    /* 2^200 */
 #define SPB_SWEEP_SMALL 6.2230152778611417e-61  /* 2^-200 */
@@ -51,7 +52,8 @@ SPB_FN int isweep(cplx w, real fnu, int kode, int n, Y y, real az, bool rotate, 
     const real tol = SPB_TOL, elim = SPB_ELIM, alim = SPB_ALIM;
     // short sequences stay with the classic drivers (cheap there, and a direct evaluation of so few members is
     // slightly more accurate than the ratio / Wronskian route)
-    if (n < SPB_SWEEP_MIN_ORDERS || !(az > real(0.0)) || !(az <= real(SPB_SWEEP_AZ_MAX))) return -1;
+    if (n < SPB_SWEEP_MIN_ORDERS || !(az >= real(SPB_SWEEP_AZ_MIN)) || !(az <= real(SPB_SWEEP_AZ_MAX))) return -1;
+    if (!(fnu + real(n) < real(4096.0))) return -1;
     if (kode == 1 && !(w.re < alim)) return -1;
     // K_fnu(w), K_fnu+1(w) scaled by e^w (never underflow that way; failure or a set-to-zero member declines)
     cplx ck[2];
@@ -109,7 +111,9 @@ SPB_FN int isweep(cplx w, real fnu, int kode, int n, Y y, real az, bool rotate, 
             p1 = sweep_step(pt, rz * (dfnu + t1r), p2);
             p2 = pt;
             t1r -= real(1.0);
-            if (rmax(rabs(p1.re), rabs(p1.im)) > real(SPB_SWEEP_BIG)) {
+            // one step grows the iterate by at most 2 (order + steps) / |w| < 2^24, so testing every fourth step
+            // keeps it below 2^300
+            if ((i & 3) == 0 && rmax(rabs(p1.re), rabs(p1.im)) > real(SPB_SWEEP_BIG)) {
                 p1 = p1 * real(SPB_SWEEP_SMALL);
                 p2 = p2 * real(SPB_SWEEP_SMALL);
                 etot += 1;
@@ -149,16 +153,23 @@ SPB_FN int isweep(cplx w, real fnu, int kode, int n, Y y, real az, bool rotate, 
     int nz = 0;
     bool leading = true;
     {
+        // On the device the lanes of a warp start this pass staggered by (largest kk of the warp - own kk)
+        // idle iterations, so that all lanes produce member k in the same iteration and the warp's 32 stores
+        // of one order go out as one coalesced 512-byte request.  Timing only: the arithmetic of a lane does
+        // not depend on its neighbours.
+        const int delay = SPB_WARP_MAX(kk) - kk;
         int e = 0;
         int member = n;  // next member to store is member - 1
         real t1r = real(kk);
         cplx a(1.0, 0.0), b(0.0, 0.0);
-        for (int i = 1; i <= steps; ++i) {
+        for (int it = 1 - delay; it <= steps; ++it) {
+            if (it < 1) continue;
+            const int i = it;
             cplx pt = a;
             a = sweep_step(pt, rz * (dfnu + t1r), b);
             b = pt;
             t1r -= real(1.0);
-            if (rmax(rabs(a.re), rabs(a.im)) > real(SPB_SWEEP_BIG)) {
+            if ((i & 3) == 0 && rmax(rabs(a.re), rabs(a.im)) > real(SPB_SWEEP_BIG)) {
                 a = a * real(SPB_SWEEP_SMALL);
                 b = b * real(SPB_SWEEP_SMALL);
                 e += 1;
@@ -166,13 +177,13 @@ SPB_FN int isweep(cplx w, real fnu, int kode, int n, Y y, real az, bool rotate, 
             if (i < kk) continue;
             member -= 1;
             const int j = etot - e;  // rescalings still to come: true size is 2^(-200 j) of the iterate
-            cplx val(0.0, 0.0);
-            if (j <= 5) {
-                cplx s = a;
-                for (int t = 0; t < j; ++t) s = s * real(SPB_SWEEP_SMALL);
-                val = s * q;
-                if (!(rmax(rabs(val.re), rabs(val.im)) >= flush)) val = cplx(0.0, 0.0);
-            }
+            // scale in two exact stages around the multiplication by q (|iterate| < 2^300, |q| may be as large
+            // as e^alim for unscaled values): neither stage can overflow, and a stage that underflows belongs
+            // to a member far below the flush threshold anyway
+            const int j1 = j < 5 ? j : 5;
+            cplx val = (a * pow2_(-200 * j1)) * q;
+            if (j > 5) val = (j <= 10) ? val * pow2_(-200 * (j - 5)) : cplx(0.0, 0.0);
+            if (!(rmax(rabs(val.re), rabs(val.im)) >= flush)) val = cplx(0.0, 0.0);
             const bool zero = (val.re == real(0.0) && val.im == real(0.0));
             if (zero && leading) nz += 1;
             if (!zero) leading = false;
