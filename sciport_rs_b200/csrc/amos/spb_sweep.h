@@ -37,18 +37,22 @@ SPB_HD cplx sweep_step(cplx a, cplx c, cplx b) {
     return cplx(fma_(a.re, c.re, fma_(-a.im, c.im, b.re)), fma_(a.re, c.im, fma_(a.im, c.re, b.im)));
 }
 
-// unit^m for unit in {1, i, -1, -i} (exact)
-SPB_HD cplx unit_pow(cplx unit, int m) {
-    cplx r(1.0, 0.0);
-    m &= 3;
-    for (int i = 0; i < m; ++i) r = r * unit;
-    return r;
+// i^m * v (exact: a swap and sign changes, no floating-point operation)
+SPB_HD cplx rot_i(cplx v, int m) {
+    real x = (m & 1) ? -v.im : v.re;
+    real y = (m & 1) ? v.re : v.im;
+    if (m & 2) {
+        x = -x;
+        y = -y;
+    }
+    return cplx(x, y);
 }
 
-// y[k] = rot_k * I_{fnu+k}(w), rot_k = csgn0 * step^k (step a unit: 1, +-i or -1), Re w >= 0, az = |w|.
-// rotate = false skips the rotation (rot_k = 1).  Returns nz >= 0, or -1 when it declines.
+// y[k] = csgn0 * i^(dm k) * I_{fnu+k}(w),  Re w >= 0,  az = |w|.  The order-independent factor csgn0 is folded into
+// the normalising factor once; the per-order unit i^(dm k) is applied exactly (dm = +-1 for J, 2 for I continued
+// to the left half plane, 0 for none).  Returns nz >= 0, or -1 when it declines.
 template <class Y>
-SPB_FN int isweep(cplx w, real fnu, int kode, int n, Y y, real az, bool rotate, cplx csgn0, cplx step) {
+SPB_FN int isweep(cplx w, real fnu, int kode, int n, Y y, real az, cplx csgn0, int dm) {
     const real tol = SPB_TOL, elim = SPB_ELIM, alim = SPB_ALIM;
     // short sequences stay with the classic drivers (cheap there, and a direct evaluation of so few members is
     // slightly more accurate than the ratio / Wronskian route)
@@ -135,7 +139,7 @@ SPB_FN int isweep(cplx w, real fnu, int kode, int n, Y y, real az, bool rotate, 
         const cplx ifnu = (cinu * ract) * (conj(ct) * ract);
         // normalising factor q = I_fnu / (bottom iterate)
         const real bm = real(1.0) / cabs_(p1);
-        q = (ifnu * conj(p1 * bm)) * bm;
+        q = ((ifnu * conj(p1 * bm)) * bm) * csgn0;
         // a failed K evaluation or non-finite factor: decline before anything is stored
         if (nw != 0 || !(q.re == q.re) || !(q.im == q.im) || !(rabs(q.re) <= real(SPB_D1MACH2)) ||
             !(rabs(q.im) <= real(SPB_D1MACH2)))
@@ -143,13 +147,7 @@ SPB_FN int isweep(cplx w, real fnu, int kode, int n, Y y, real az, bool rotate, 
     }
     // ---- pass B: same recurrence, store each member once (top order first)
     const real flush = 3.9222272510438042e-305;  // exp(-elim)
-    const real rtol = real(1.0) / tol;
-    const real ascle = SPB_D1MACH1 * rtol * real(1.0e3);
-    cplx rot(1.0, 0.0), unstep(1.0, 0.0);
-    if (rotate) {
-        rot = csgn0 * unit_pow(step, n - 1);
-        unstep = conj(step);
-    }
+    int m = (dm * (n - 1)) & 3;                  // unit of the top member
     int nz = 0;
     bool leading = true;
     {
@@ -180,18 +178,20 @@ SPB_FN int isweep(cplx w, real fnu, int kode, int n, Y y, real az, bool rotate, 
             // scale in two exact stages around the multiplication by q (|iterate| < 2^300, |q| may be as large
             // as e^alim for unscaled values): neither stage can overflow, and a stage that underflows belongs
             // to a member far below the flush threshold anyway
-            const int j1 = j < 5 ? j : 5;
-            cplx val = (a * pow2_(-200 * j1)) * q;
-            if (j > 5) val = (j <= 10) ? val * pow2_(-200 * (j - 5)) : cplx(0.0, 0.0);
-            if (!(rmax(rabs(val.re), rabs(val.im)) >= flush)) val = cplx(0.0, 0.0);
-            const bool zero = (val.re == real(0.0) && val.im == real(0.0));
-            if (zero && leading) nz += 1;
-            if (!zero) leading = false;
-            if (rotate) {
-                if (!zero) val = rot_guard(val, rot, rtol, ascle, tol);
-                rot = rot * unstep;
+            cplx val;
+            if (j == 0) {
+                val = a * q;
+            } else {
+                const int j1 = j < 5 ? j : 5;
+                val = (a * pow2_(-200 * j1)) * q;
+                if (j > 5) val = (j <= 10) ? val * pow2_(-200 * (j - 5)) : cplx(0.0, 0.0);
             }
-            y[member] = val;
+            const bool zero = !(rmax(rabs(val.re), rabs(val.im)) >= flush);
+            if (zero) val = cplx(0.0, 0.0);
+            nz += (zero && leading) ? 1 : 0;
+            leading = leading && zero;
+            y[member] = rot_i(val, m);
+            m = (m - dm) & 3;
         }
     }
     return nz;
@@ -215,7 +215,7 @@ SPB_FN int besj_sweep(cplx z, real fnu, int kode, int n, Y cy, int &ierr, bool &
         csgn.im = -csgn.im;
         cii = -cii;
     }
-    const int nz = isweep(zn, fnu, kode, n, cy, az, true, csgn, cplx(0.0, cii));
+    const int nz = isweep(zn, fnu, kode, n, cy, az, csgn, cii > real(0.0) ? 1 : -1);
     if (nz < 0) return 0;
     declined = false;
     return nz;
@@ -231,15 +231,15 @@ SPB_FN int besi_sweep(cplx z, real fnu, int kode, int n, Y cy, int &ierr, bool &
     const real az = cabs_(z);
     cplx zn = z;
     cplx csgn(1.0, 0.0);
-    bool rotate = false;
+    int dm = 0;
     if (z.re < real(0.0)) {
         zn = -z;
         const OrderPhase ph = order_phase(fnu);
         csgn = cplx(ph.cp, (z.im < real(0.0)) ? -ph.sp : ph.sp);
         if (ph.inu % 2 != 0) csgn = -csgn;
-        rotate = true;
+        dm = 2;
     }
-    const int nz = isweep(zn, fnu, kode, n, cy, az, rotate, csgn, cplx(-1.0, 0.0));
+    const int nz = isweep(zn, fnu, kode, n, cy, az, csgn, dm);
     if (nz < 0) return 0;
     declined = false;
     return nz;
