@@ -141,6 +141,13 @@ int spb_sinc(const double *x, double *out, int64_t n, const spb_exec *ex);
  * *idx = -1, *code = 0 when every element is OK.  ierr lives where ex says. */
 int spb_first_error(const int32_t *ierr, int64_t n, int64_t *idx, int32_t *code, const spb_exec *ex);
 
+/* Same answer for the LAST spb_bessel* / spb_airy call of this thread without any per-element array: every kernel
+ * keeps the smallest (index, ierr) of its failing elements in one device word, so callers that only need the
+ * reference's `Result<Array, i32>` may pass ierr = nz = NULL and save 8 bytes per element of device-to-host
+ * traffic.  which = 0: primary output, 1: second output of spb_bessel_jy.  Waits for a device-pointer call to
+ * finish.  *idx = -1, *code = 0 when no element failed. */
+int spb_last_first_error(int which, int64_t *idx, int32_t *code);
+
 /* ---- synthetic inputs: index-addressable splitmix64 stream -----------------
  * Fills v[offset..offset+n) / z[...] for BASELINE config `cfg` (2,3,4,5) directly where ex says. */
 int spb_synth(int cfg, uint64_t seed, int64_t offset, int64_t n, int64_t n_total, double *v, spb_c128 *z,

@@ -73,7 +73,14 @@ struct DeviceCtx {
     cudaStream_t streams[2] = {nullptr, nullptr};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     unsigned long long *d_packed = nullptr;
+    unsigned long long *d_first = nullptr;         // [2] first failing element (packed) of the call in flight
+    unsigned long long h_first[2] = {~0ull, ~0ull};  // host copy, valid once the call has completed
 };
+
+// which devices the last compute call of this thread used, for spb_last_first_error()
+thread_local std::vector<int> g_first_devs;
+thread_local cudaStream_t g_first_stream = nullptr;
+thread_local bool g_first_pending = false;  // device-pointer call: result still to be fetched from d_first
 
 std::mutex g_ctx_mu;
 std::vector<DeviceCtx *> g_ctx;
@@ -101,6 +108,7 @@ DeviceCtx *get_ctx(int dev) {
         cudaEventCreate(&c->ev0);
         cudaEventCreate(&c->ev1);
         cudaMalloc(&c->d_packed, sizeof(unsigned long long));
+        cudaMalloc(&c->d_first, 2 * sizeof(unsigned long long));
         g_ctx[dev] = c;
     }
     return g_ctx[dev];
@@ -267,6 +275,7 @@ struct BesselArgs {
     double2 *out2 = nullptr;  // pair families
     int *ierr2 = nullptr;
     int *nz2 = nullptr;
+    long long index_base = 0; // global index of element 0 of this slice (first-error bookkeeping)
     int n_orders = 1;         // > 1: order sequence, out is [n_orders][out_stride]
     long long out_stride = 0; // points per order row of the caller's result array
 };
@@ -277,10 +286,13 @@ int run_device_seq(DeviceCtx *c, const BesselArgs &a, cudaStream_t st, int *laun
     std::lock_guard<std::mutex> lk(c->mu);
     CK(cudaSetDevice(c->dev));
     int launches = 0;
+    CK(cudaMemsetAsync(c->d_first, 0xff, 16, st));
     CK(cudaEventRecord(c->ev0, st));
     for (long long off = 0; off < a.n; off += CHUNK_DEVICE) {
         long long m = std::min(CHUNK_DEVICE, a.n - off);
         DevJob job{};
+        job.first_err = c->d_first;
+        job.index_base = a.index_base + off;
         job.fam = a.fn;
         job.kode = a.kode;
         job.sem = (a.flags & SPB_SEM_SCIPY) ? 1 : 0;
@@ -312,6 +324,7 @@ int run_device(DeviceCtx *c, const BesselArgs &a, cudaStream_t st, double *ms_ou
     Prof prof;
     prof.on = (a.flags & SPB_PROFILE) != 0;
     if (prof.on) g_prof.clear();
+    CK(cudaMemsetAsync(c->d_first, 0xff, 16, st));
     CK(cudaEventRecord(c->ev0, st));
     for (long long off = 0; off < a.n; off += CHUNK_DEVICE) {
         long long m = std::min(CHUNK_DEVICE, a.n - off);
@@ -332,6 +345,9 @@ int run_device(DeviceCtx *c, const BesselArgs &a, cudaStream_t st, double *ms_ou
         job.ierr2 = a.ierr2 ? a.ierr2 + off : nullptr;
         job.nz2 = a.nz2 ? a.nz2 + off : nullptr;
         job.n = m;
+        job.first_err = c->d_first;
+        job.first_err2 = c->d_first + 1;
+        job.index_base = a.index_base + off;
         launches += enqueue_chunk(job, c->scratch[0], c->sms, a.flags, st, &prof);
         if (prof.on) {
             // profiling serialises the chunks so that the bin counters can be read back per chunk
@@ -419,6 +435,10 @@ int run_host_slice(DeviceCtx *c, const BesselArgs &a, double *ms_out, int *launc
     int launches = 0;
     int k = 0;
     double v0 = a.v[0];
+    {
+        const unsigned long long ones[2] = {~0ull, ~0ull};
+        CK(cudaMemcpy(c->d_first, ones, 16, cudaMemcpyHostToDevice));  // nothing of this thread is in flight here
+    }
     for (long long off = 0; off < a.n; off += CHUNK_HOST, ++k) {
         long long m = std::min(CHUNK_HOST, a.n - off);
         int b = k & 1;
@@ -452,6 +472,9 @@ int run_host_slice(DeviceCtx *c, const BesselArgs &a, double *ms_out, int *launc
         job.ierr2 = a.ierr2 ? s.ierr2 : nullptr;
         job.nz2 = a.nz2 ? s.nz2 : nullptr;
         job.n = m;
+        job.first_err = c->d_first;
+        job.first_err2 = c->d_first + 1;
+        job.index_base = a.index_base + off;
         launches += enqueue_chunk(job, c->scratch[b], c->sms, a.flags, st);
         CK(cudaMemcpyAsync(a.out + off, s.out, m * 16, cudaMemcpyDeviceToHost, st));
         if (a.ierr) CK(cudaMemcpyAsync(a.ierr + off, s.ierr, m * 4, cudaMemcpyDeviceToHost, st));
@@ -464,6 +487,7 @@ int run_host_slice(DeviceCtx *c, const BesselArgs &a, double *ms_out, int *launc
     CK(cudaStreamSynchronize(c->streams[0]));
     CK(cudaStreamSynchronize(c->streams[1]));
     CK(cudaGetLastError());
+    CK(cudaMemcpy(c->h_first, c->d_first, 16, cudaMemcpyDeviceToHost));
     if (ms_out) *ms_out = 0.0;
     if (launches_out) *launches_out = launches;
     return SPB_OK;
@@ -478,6 +502,10 @@ int run_host_slice_seq(DeviceCtx *c, const BesselArgs &a, int *launches_out) {
     chunk = std::min(chunk, CHUNK_HOST);
     int launches = 0, k = 0;
     double v0 = a.v[0];
+    {
+        const unsigned long long ones[2] = {~0ull, ~0ull};
+        CK(cudaMemcpy(c->d_first, ones, 16, cudaMemcpyHostToDevice));
+    }
     for (long long off = 0; off < a.n; off += chunk, ++k) {
         long long m = std::min(chunk, a.n - off);
         int b = k & 1;
@@ -517,6 +545,8 @@ int run_host_slice_seq(DeviceCtx *c, const BesselArgs &a, int *launches_out) {
         job.ierr = a.ierr ? s.ierr : nullptr;
         job.nz = a.nz ? s.nz : nullptr;
         job.n = m;
+        job.first_err = c->d_first;
+        job.index_base = a.index_base + off;
         rc = ensure_scratch(c->scratch[b], m);
         if (rc != SPB_OK) return rc;
         launches += launch_sequence(job, a.n_orders, m, c->scratch[b].s, c->sms, st);
@@ -528,6 +558,7 @@ int run_host_slice_seq(DeviceCtx *c, const BesselArgs &a, int *launches_out) {
     CK(cudaStreamSynchronize(c->streams[0]));
     CK(cudaStreamSynchronize(c->streams[1]));
     CK(cudaGetLastError());
+    CK(cudaMemcpy(c->h_first, c->d_first, 16, cudaMemcpyDeviceToHost));
     if (launches_out) *launches_out = launches;
     return SPB_OK;
 }
@@ -559,6 +590,9 @@ int bessel_impl(int fn, int kode, const double *v, int64_t v_stride, const spb_c
     a.n_orders = n_orders;
     a.out_stride = n;
     const bool seq = n_orders > 1;
+    g_first_devs = devs;
+    g_first_stream = st;
+    g_first_pending = dptr;
     if (dptr)
         return seq ? run_device_seq(get_ctx(devs[0]), a, st, &g_last_launches)
                    : run_device(get_ctx(devs[0]), a, st, &g_last_ms, &g_last_launches);
@@ -586,6 +620,7 @@ int bessel_impl(int fn, int kode, const double *v, int64_t v_stride, const spb_c
         th.emplace_back([&, g] {
             long long lo = n * g / G, hi = n * (g + 1) / G;
             BesselArgs s = a;
+            s.index_base = lo;
             s.v = a.v + lo * a.v_stride;
             s.z = a.z ? a.z + lo : nullptr;
             s.x = a.x ? a.x + lo : nullptr;
@@ -695,7 +730,11 @@ int spb_airy(int which, int kode, const spb_c128 *z, spb_c128 *out, int32_t *ier
     CK(cudaSetDevice(c->dev));
     int sem = (flags & SPB_SEM_SCIPY) ? 1 : 0;
     g_last_launches = 0;
+    g_first_devs = devs;
+    g_first_stream = st;
+    g_first_pending = dptr;
     if (dptr) {
+        CK(cudaMemsetAsync(c->d_first, 0xff, 16, st));
         CK(cudaEventRecord(c->ev0, st));
         for (long long off = 0; off < n; off += CHUNK_DEVICE) {
             long long m = std::min<long long>(CHUNK_DEVICE, n - off);
@@ -703,7 +742,7 @@ int spb_airy(int which, int kode, const spb_c128 *z, spb_c128 *out, int32_t *ier
             if (rc != SPB_OK) return rc;
             g_last_launches += launch_airy(which, kode, sem, (const double2 *)z + off, (double2 *)out + off,
                                            ierr ? ierr + off : nullptr, nz ? nz + off : nullptr, m, &c->scratch[0].s,
-                                           c->sms, st);
+                                           c->sms, st, c->d_first, off);
         }
         CK(cudaEventRecord(c->ev1, st));
         CK(cudaGetLastError());
@@ -714,6 +753,10 @@ int spb_airy(int which, int kode, const spb_c128 *z, spb_c128 *out, int32_t *ier
         return SPB_OK;
     }
     int launches = 0, k = 0;
+    {
+        const unsigned long long ones[2] = {~0ull, ~0ull};
+        CK(cudaMemcpy(c->d_first, ones, 16, cudaMemcpyHostToDevice));
+    }
     for (long long off = 0; off < n; off += CHUNK_HOST, ++k) {
         long long m = std::min<long long>(CHUNK_HOST, n - off);
         int b = k & 1;
@@ -725,13 +768,14 @@ int spb_airy(int which, int kode, const spb_c128 *z, spb_c128 *out, int32_t *ier
         rc = ensure_scratch(c->scratch[b], m);
         if (rc != SPB_OK) return rc;
         launches += launch_airy(which, kode, sem, s.z, s.out, ierr ? s.ierr : nullptr, nz ? s.nz : nullptr, m,
-                                &c->scratch[b].s, c->sms, s0);
+                                &c->scratch[b].s, c->sms, s0, c->d_first, off);
         CK(cudaMemcpyAsync(out + off, s.out, m * 16, cudaMemcpyDeviceToHost, s0));
         if (ierr) CK(cudaMemcpyAsync(ierr + off, s.ierr, m * 4, cudaMemcpyDeviceToHost, s0));
         if (nz) CK(cudaMemcpyAsync(nz + off, s.nz, m * 4, cudaMemcpyDeviceToHost, s0));
     }
     CK(cudaStreamSynchronize(c->streams[0]));
     CK(cudaStreamSynchronize(c->streams[1]));
+    CK(cudaMemcpy(c->h_first, c->d_first, 16, cudaMemcpyDeviceToHost));
     g_last_launches = launches;
     return SPB_OK;
 }
@@ -866,6 +910,30 @@ int spb_last_timing(double *kernel_ms, int *launches) {
     }
     if (kernel_ms) *kernel_ms = g_last_ms;
     if (launches) *launches = g_last_launches;
+    return SPB_OK;
+}
+
+int spb_last_first_error(int which, int64_t *idx, int32_t *code) {
+    if (!idx || !code || which < 0 || which > 1) return fail(SPB_E_ARG, "bad argument");
+    *idx = -1;
+    *code = 0;
+    unsigned long long best = ~0ull;
+    for (int d : g_first_devs) {
+        DeviceCtx *c = get_ctx(d);
+        if (g_first_pending) {
+            // device-pointer call: fetch the word behind the work queued on the caller's stream
+            std::lock_guard<std::mutex> lk(c->mu);
+            CK(cudaSetDevice(c->dev));
+            CK(cudaMemcpyAsync(c->h_first, c->d_first, 16, cudaMemcpyDeviceToHost, g_first_stream));
+            CK(cudaStreamSynchronize(g_first_stream));
+        }
+        best = std::min(best, c->h_first[which]);
+    }
+    g_first_pending = false;
+    if (best != ~0ull) {
+        *idx = (int64_t)(best >> 8);
+        *code = (int32_t)(best & 0xff);
+    }
     return SPB_OK;
 }
 

@@ -55,19 +55,21 @@ __global__ void __launch_bounds__(256) k_classify_airy(int which, const double2 
 
 template <bool BI>
 __device__ __forceinline__ void airy_point(int id, int kode, int sem, cplx zz, long long i, double2 *out, int *ierr,
-                                           int *nz) {
+                                           int *nz, unsigned long long *first_err, long long index_base) {
     int ie = 0, nzz = 0;
     cplx val = BI ? spb::biry(zz, id, kode, ie) : spb::airy(zz, id, kode, nzz, ie);
     if (sem) val = spb::airy_semantics(zz, val, ie);
     out[i] = make_double2(val.re, val.im);
     if (ierr) ierr[i] = ie;
     if (nz) nz[i] = nzz;
+    note_error(first_err, index_base + i, ie);
 }
 
 // persistent walk over the key-sorted index list (two-deep software pipeline as in the Bessel passes)
 template <bool BI>
 __global__ void __launch_bounds__(128) k_airy_sorted(int id, int kode, int sem, const double2 *z, double2 *out,
-                                                     int *ierr, int *nz, long long n, Scratch s) {
+                                                     int *ierr, int *nz, long long n, Scratch s,
+                                                     unsigned long long *first_err, long long index_base) {
     const unsigned int count = (unsigned int)n;
     const unsigned int stride = gridDim.x * blockDim.x;
     const unsigned int *perm = s.perm_i;
@@ -87,24 +89,25 @@ __global__ void __launch_bounds__(128) k_airy_sorted(int id, int kode, int sem, 
         have2 = (t + stride) < count;
         if (have2) i2 = __ldg(perm + t + stride);
         if (have1) z1 = __ldg(z + i1);
-        airy_point<BI>(id, kode, sem, zz, i, out, ierr, nz);
+        airy_point<BI>(id, kode, sem, zz, i, out, ierr, nz, first_err, index_base);
     }
 }
 
 // small batches: one thread per point in index order (no sort)
 template <bool BI>
 __global__ void __launch_bounds__(128) k_airy(int id, int kode, int sem, const double2 *z, double2 *out, int *ierr,
-                                              int *nz, long long n) {
+                                              int *nz, long long n, unsigned long long *first_err,
+                                              long long index_base) {
     const long long stride = (long long)gridDim.x * blockDim.x;
 #pragma unroll 1
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         double2 t = __ldg(z + i);
-        airy_point<BI>(id, kode, sem, cplx(t.x, t.y), i, out, ierr, nz);
+        airy_point<BI>(id, kode, sem, cplx(t.x, t.y), i, out, ierr, nz, first_err, index_base);
     }
 }
 
 int launch_airy(int which, int kode, int sem, const double2 *z, double2 *out, int *ierr, int *nz, long long n,
-                const Scratch *s, int sms, cudaStream_t st) {
+                const Scratch *s, int sms, cudaStream_t st, unsigned long long *first_err, long long index_base) {
     const bool bi = which >= 2;
     const int id = which & 1;
     if (!s || n < 8192) {
@@ -112,9 +115,9 @@ int launch_airy(int which, int kode, int sem, const double2 *z, double2 *out, in
         if (blocks > 148 * 32) blocks = 148 * 32;
         if (blocks < 1) blocks = 1;
         if (bi)
-            k_airy<true><<<(int)blocks, 128, 0, st>>>(id, kode, sem, z, out, ierr, nz, n);
+            k_airy<true><<<(int)blocks, 128, 0, st>>>(id, kode, sem, z, out, ierr, nz, n, first_err, index_base);
         else
-            k_airy<false><<<(int)blocks, 128, 0, st>>>(id, kode, sem, z, out, ierr, nz, n);
+            k_airy<false><<<(int)blocks, 128, 0, st>>>(id, kode, sem, z, out, ierr, nz, n, first_err, index_base);
         return 1;
     }
     k_classify_airy<<<s->nblocks, 256, 0, st>>>(which, z, n, *s);
@@ -123,10 +126,10 @@ int launch_airy(int which, int kode, int sem, const double2 *z, double2 *out, in
     launch_scan_scatter(job, *s, st);
     if (bi)
         k_airy_sorted<true><<<resident_grid(k_airy_sorted<true>, 128, sms), 128, 0, st>>>(id, kode, sem, z, out, ierr, nz,
-                                                                                         n, *s);
+                                                                                         n, *s, first_err, index_base);
     else
         k_airy_sorted<false><<<resident_grid(k_airy_sorted<false>, 128, sms), 128, 0, st>>>(id, kode, sem, z, out, ierr,
-                                                                                           nz, n, *s);
+                                                                                           nz, n, *s, first_err, index_base);
     return 4;
 }
 

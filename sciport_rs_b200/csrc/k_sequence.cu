@@ -44,6 +44,7 @@ __global__ void __launch_bounds__(128) k_sweep(DevJob job, int n_orders, long lo
         }
         if (job.ierr) job.ierr[i] = ierr;
         if (job.nz) job.nz[i] = nz;
+        note_error(job.first_err, job.index_base + i, ierr);
     }
 }
 
@@ -90,6 +91,7 @@ __global__ void __launch_bounds__(128) k_sequence(DevJob job, int n_orders, long
         }
         if (job.ierr) job.ierr[i] = ierr;
         if (job.nz) job.nz[i] = nz;
+        note_error(job.first_err, job.index_base + i, ierr);
     }
 }
 

@@ -18,16 +18,23 @@ __device__ __forceinline__ void load_point(const DevJob &j, long long i, cplx &z
     v = __ldg(j.v + i * j.v_stride);
 }
 
+// record a failing element in the call-wide "first error" word (rare path: one atomic per failing element)
+__device__ __forceinline__ void note_error(unsigned long long *slot, long long index, int ierr) {
+    if (ierr != 0 && slot) atomicMin(slot, ((unsigned long long)index << 8) | (unsigned long long)(ierr & 0xff));
+}
+
 __device__ __forceinline__ void store_point(const DevJob &j, long long i, cplx val, int ierr, int nz) {
     j.out[i] = make_double2(val.re, val.im);  // one 128-bit store per point
     if (j.ierr) j.ierr[i] = ierr;
     if (j.nz) j.nz[i] = nz;
+    note_error(j.first_err, j.index_base + i, ierr);
 }
 
 __device__ __forceinline__ void store_point2(const DevJob &j, long long i, cplx val, int ierr, int nz) {
     j.out2[i] = make_double2(val.re, val.im);
     if (j.ierr2) j.ierr2[i] = ierr;
     if (j.nz2) j.nz2[i] = nz;
+    note_error(j.first_err2, j.index_base + i, ierr);
 }
 
 // Per-thread cache of the order-dependent phase factors: one sincos per DISTINCT order a thread meets.  With a

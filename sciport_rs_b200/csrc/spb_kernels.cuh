@@ -22,6 +22,11 @@ struct DevJob {
     int *ierr2;     // nullable
     int *nz2;       // nullable
     long long n;  // points in this chunk
+    // first failing element of the whole call, packed (global index << 8 | ierr), kept with atomicMin so that a
+    // caller who only wants `collect::<Result<_, i32>>` semantics never has to read per-element codes back
+    unsigned long long *first_err;   // nullable; primary output
+    unsigned long long *first_err2;  // nullable; second output of a pair family
+    long long index_base;            // global index of element 0 of this chunk
 };
 
 // Scratch of one chunk (device memory, owned by the per-device cache in capi.cu).
@@ -83,7 +88,7 @@ int launch_sequence(const DevJob &job, int n_orders, long long out_stride, const
                     cudaStream_t st);
 // returns the number of kernels launched; with scratch (sized for n) the points are sorted by region first
 int launch_airy(int which, int kode, int sem, const double2 *z, double2 *out, int *ierr, int *nz, long long n,
-                const Scratch *s, int sms, cudaStream_t st);
+                const Scratch *s, int sms, cudaStream_t st, unsigned long long *first_err, long long index_base);
 void launch_synth(int cfg, unsigned long long seed, long long offset, long long n, long long n_total, double *v,
                   double2 *z, cudaStream_t st);
 void launch_first_error(const int *ierr, long long n, unsigned long long *packed, cudaStream_t st);

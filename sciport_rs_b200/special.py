@@ -66,8 +66,12 @@ def profile_step(fn):
 
 
 def bessel(fn, v, z, scaled=False, semantics="amos", path="binned", real_input=False, devices=None, profile=False,
-           out=None, ierr=None, nz=None, n_orders=1):
+           out=None, ierr=None, nz=None, n_orders=1, want_codes=True):
     """Evaluate one family over a batch.  Returns ``(values, ierr, nz)``.
+
+    ``want_codes=False`` passes NULL for the per-element ``ierr`` / ``nz`` arrays (they come back as ``None``):
+    the first failing element is still available through :func:`last_first_error`, which is all the
+    reference's ``Result<Array, i32>`` needs, and 8 bytes per element of device-to-host traffic are saved.
 
     ``n_orders > 1`` evaluates the order sequence v, v+1, ..., v+n_orders-1 per point; ``values`` then has
     shape ``(n_orders, n)`` (order-major, BASELINE config 5), ``ierr`` / ``nz`` stay per point.
@@ -103,13 +107,14 @@ def bessel(fn, v, z, scaled=False, semantics="amos", path="binned", real_input=F
         if out is None:
             out = torch.empty(oshape, dtype=torch.complex128, device=zc.device)
         assert out.is_contiguous() and out.numel() == n * n_orders and out.dtype == torch.complex128
-        ierr = torch.empty(zc.shape, dtype=torch.int32, device=zc.device)
-        nz = torch.empty(zc.shape, dtype=torch.int32, device=zc.device)
+        ierr = torch.empty(zc.shape, dtype=torch.int32, device=zc.device) if want_codes else None
+        nz = torch.empty(zc.shape, dtype=torch.int32, device=zc.device) if want_codes else None
         with torch.cuda.device(zc.device):
             ex = make_exec(device_ptrs=True, stream=_stream_for(zc), flags=flags, devices=[zc.device.index])
             f = lib.spb_bessel_real if real_input else lib.spb_bessel
-            check(f(FN[fn], kode, vt.data_ptr(), stride, zc.data_ptr(), out.data_ptr(), ierr.data_ptr(),
-                    nz.data_ptr(), n, n_orders, ctypes.byref(ex)))
+            check(f(FN[fn], kode, vt.data_ptr(), stride, zc.data_ptr(), out.data_ptr(),
+                    ierr.data_ptr() if want_codes else None, nz.data_ptr() if want_codes else None, n, n_orders,
+                    ctypes.byref(ex)))
         if profile and _PROFILE_LOG is not None:
             for r in _lib.last_profile():
                 r["name"] = f"{fn}/{r['name']}"
@@ -127,18 +132,22 @@ def bessel(fn, v, z, scaled=False, semantics="amos", path="binned", real_input=F
     # caller-provided (e.g. pinned) result buffers are filled in place, like the C ABI
     oshape = za.shape if n_orders == 1 else (n_orders, n)
     out = np.empty(oshape, dtype=np.complex128) if out is None else out
-    ierr = np.empty(za.shape, dtype=np.int32) if ierr is None else ierr
-    nz = np.empty(za.shape, dtype=np.int32) if nz is None else nz
-    assert out.dtype == np.complex128 and ierr.dtype == np.int32 and nz.dtype == np.int32
-    assert out.size == n * n_orders and ierr.size == n and nz.size == n and out.flags.c_contiguous
+    assert out.dtype == np.complex128 and out.size == n * n_orders and out.flags.c_contiguous
+    if want_codes:
+        ierr = np.empty(za.shape, dtype=np.int32) if ierr is None else ierr
+        nz = np.empty(za.shape, dtype=np.int32) if nz is None else nz
+        assert ierr.dtype == np.int32 and nz.dtype == np.int32 and ierr.size == n and nz.size == n
+    else:
+        ierr = nz = None
     ex = make_exec(device_ptrs=False, flags=flags, devices=devices)
     f = lib.spb_bessel_real if real_input else lib.spb_bessel
-    check(f(FN[fn], kode, va.ctypes.data, stride, za.ctypes.data, out.ctypes.data, ierr.ctypes.data, nz.ctypes.data,
-            n, n_orders, ctypes.byref(ex)))
+    check(f(FN[fn], kode, va.ctypes.data, stride, za.ctypes.data, out.ctypes.data,
+            ierr.ctypes.data if want_codes else None, nz.ctypes.data if want_codes else None, n, n_orders,
+            ctypes.byref(ex)))
     return out, ierr, nz
 
 
-def bessel_jy(v, z, scaled=False, semantics="amos", profile=False, outs=None, codes=None):
+def bessel_jy(v, z, scaled=False, semantics="amos", profile=False, outs=None, codes=None, want_codes=True):
     """J_v(z) and Y_v(z) in one pass (spb_bessel_jy): returns ((J, ierr_j, nz_j), (Y, ierr_y, nz_y)).
     Both functions need I_v at the same rotated point, so the pair shares classification and the I pass."""
     kode = 2 if scaled else 1
@@ -155,13 +164,15 @@ def bessel_jy(v, z, scaled=False, semantics="amos", profile=False, outs=None, co
         # caller-provided device buffers are filled in place (the C ABI never allocates results)
         if outs is None:
             outs = [torch.empty(zc.shape, dtype=torch.complex128, device=zc.device) for _ in range(2)]
-        if codes is None:
+        if not want_codes:
+            codes = [None] * 4
+        elif codes is None:
             codes = [torch.empty(zc.shape, dtype=torch.int32, device=zc.device) for _ in range(4)]
+        cp = [c.data_ptr() if c is not None else None for c in codes]
         with torch.cuda.device(zc.device):
             ex = make_exec(device_ptrs=True, stream=_stream_for(zc), flags=flags, devices=[zc.device.index])
             check(lib.spb_bessel_jy(kode, vt.data_ptr(), stride, zc.data_ptr(), outs[0].data_ptr(), outs[1].data_ptr(),
-                                    codes[0].data_ptr(), codes[1].data_ptr(), codes[2].data_ptr(), codes[3].data_ptr(),
-                                    n, ctypes.byref(ex)))
+                                    cp[0], cp[1], cp[2], cp[3], n, ctypes.byref(ex)))
         if profile and _PROFILE_LOG is not None:
             for r in _lib.last_profile():
                 r["name"] = f"JY/{r['name']}"
@@ -175,18 +186,35 @@ def bessel_jy(v, z, scaled=False, semantics="amos", profile=False, outs=None, co
         va, stride = np.ascontiguousarray(np.broadcast_to(va, za.shape)), 1
     # caller-provided (e.g. pinned) buffers: outs = [J, Y], codes = [ierr_j, ierr_y, nz_j, nz_y]
     outs = [np.empty(za.shape, np.complex128) for _ in range(2)] if outs is None else outs
-    codes = [np.empty(za.shape, np.int32) for _ in range(4)] if codes is None else codes
+    if not want_codes:
+        codes = [None] * 4
+    elif codes is None:
+        codes = [np.empty(za.shape, np.int32) for _ in range(4)]
+    cp = [c.ctypes.data if c is not None else None for c in codes]
     ex = make_exec(flags=flags)
     check(lib.spb_bessel_jy(kode, va.ctypes.data, stride, za.ctypes.data, outs[0].ctypes.data, outs[1].ctypes.data,
-                            codes[0].ctypes.data, codes[1].ctypes.data, codes[2].ctypes.data, codes[3].ctypes.data,
-                            za.size, ctypes.byref(ex)))
+                            cp[0], cp[1], cp[2], cp[3], za.size, ctypes.byref(ex)))
     return (outs[0], codes[0], codes[2]), (outs[1], codes[1], codes[3])
 
 
-def jvyv(v, z, scaled=False):
-    """(jv(v, z), yv(v, z)) computed together; raises on the first Err of either."""
-    (j, ej, _), (y, ey, _) = bessel_jy(v, z, scaled=scaled)
-    return _result(j, ej), _result(y, ey)
+def jvyv(v, z, scaled=False, outs=None):
+    """(jv(v, z), yv(v, z)) computed together; raises on the first Err of either.  No per-element codes are
+    produced: the library tracks the first failing element of each output on the device."""
+    (j, _, _), (y, _, _) = bessel_jy(v, z, scaled=scaled, outs=outs, want_codes=False)
+    for which in (0, 1):
+        idx, code = last_first_error(which)
+        if idx >= 0:
+            raise SpecialError(code, idx)
+    return j, y
+
+
+def last_first_error(which=0):
+    """(index, code) of the first failing element of the last bessel / bessel_jy / airy call of this thread
+    (-1, 0 if none); which = 1 selects the second output of bessel_jy."""
+    idx = ctypes.c_int64()
+    code = ctypes.c_int32()
+    check(lib.spb_last_first_error(which, ctypes.byref(idx), ctypes.byref(code)))
+    return idx.value, code.value
 
 
 def first_error(ierr):
@@ -216,8 +244,11 @@ def _result(vals, ierr, accept_half=True):
 # ---------------------------------------------------------------- reference surface
 def i0(x):
     """special::i0 (mod.rs:8-13): I_0 of a real array through the complex routine; complex result."""
-    vals, ierr, _ = bessel("I", 0.0, x, real_input=True)
-    return _result(vals, ierr)
+    vals, _, _ = bessel("I", 0.0, x, real_input=True, want_codes=False)
+    idx, code = last_first_error(0)
+    if idx >= 0:
+        raise SpecialError(code, idx)
+    return vals
 
 
 def kv(v, z):
@@ -250,8 +281,11 @@ def sinc(x):
 # ---------------------------------------------------------------- widened batched surface
 def _family(fn, scaled):
     def f(v, z, **kw):
-        vals, ierr, _ = bessel(fn, v, z, scaled=scaled, **kw)
-        return _result(vals, ierr)
+        vals, _, _ = bessel(fn, v, z, scaled=scaled, want_codes=False, **kw)
+        idx, code = last_first_error(0)
+        if idx >= 0:
+            raise SpecialError(code, idx)
+        return vals
 
     return f
 
@@ -267,8 +301,11 @@ hankel2, hankel2e = _family("H2", False), _family("H2", True)
 def jn_sequence(n_orders, z, v0=0.0, scaled=False):
     """Order sweep J_{v0+k}(z_i), k = 0..n_orders-1, as an (n_orders, n) array (BASELINE config 5); raises on the
     first Err in index order."""
-    vals, ierr, _ = bessel("J", v0, z, scaled=scaled, n_orders=n_orders)
-    return _result(vals, ierr)
+    vals, _, _ = bessel("J", v0, z, scaled=scaled, n_orders=n_orders, want_codes=False)
+    idx, code = last_first_error(0)
+    if idx >= 0:
+        raise SpecialError(code, idx)
+    return vals
 
 
 def airy_raw(which, z, scaled=False, semantics="amos"):

@@ -311,3 +311,40 @@ def test_sweep_recurrence_property_large(special):
         ok = scale > 1e-290
         worst = max(worst, float((res.abs() / scale.clamp_min(1e-300))[ok].max()))
     assert worst <= 1e-14, worst
+
+
+def test_first_error_tracked_on_device(special):
+    """`collect::<Result<_, i32>>` (mod.rs:11-12) without per-element code arrays: the kernels keep the smallest
+    failing (index, ierr) of the call in one device word (spb_last_first_error)."""
+    n = (1 << 22) + 12345  # more than one host chunk
+    z = np.full(n, 1.0 + 0.5j)
+    z[n - 7] = 900.0        # I overflows (ierr 2)
+    z[4200000] = 800.0      # ... and here, earlier, in the second staged chunk
+    out, ierr, nz = special.bessel("I", 2.5, z, want_codes=False)
+    assert ierr is None and nz is None
+    assert special.last_first_error() == (4200000, 2)
+    zt = torch.from_numpy(z).cuda()
+    special.bessel("I", 2.5, zt, want_codes=False)
+    assert special.last_first_error() == (4200000, 2)
+    full, ierr_full, _ = special.bessel("I", 2.5, zt)  # with codes: same answer from the array
+    assert special.first_error(ierr_full) == (4200000, 2)
+    assert special.last_first_error() == (4200000, 2)
+    z[4200000] = 1.0
+    z[n - 7] = 1.0
+    special.bessel("I", 2.5, z, want_codes=False)
+    assert special.last_first_error() == (-1, 0)
+    # pair family: separate words for J and Y (Y is singular at the origin, J is not)
+    zz = np.array([1 + 1j, 0j, 2 + 0j, 0j])
+    special.bessel_jy(2.5, zz, want_codes=False)
+    assert special.last_first_error(0) == (-1, 0)
+    assert special.last_first_error(1)[0] == 1
+    with pytest.raises(special.SpecialError) as e:
+        special.jvyv(2.5, zz)
+    assert e.value.index == 1
+    # Airy: no result beyond |z| ~ 1.05e6
+    za = np.array([1.0, 2.0, 2e6, 3.0], dtype=complex)
+    special.airy_raw("Ai", za)
+    assert special.last_first_error() == (2, 4)
+    # order sweeps: ierr is per point
+    special.bessel("K", 0.5, np.array([1.0, 0.0, 2.0], dtype=complex), n_orders=20, want_codes=False)
+    assert special.last_first_error() == (1, 1)
