@@ -468,7 +468,7 @@ SPB_FN int besy(cplx z, real fnu, int kode, cplx *cy, int &ierr) {
     sincos_(z.re, exi, exr);
     real ey = 0.0;
     real tay = rabs(z.im + z.im);
-    if (tay < elim) ey = exp(-tay);
+    if (tay < elim) ey = exp_(-tay);
     cplx c1, c2;
     if (z.im < real(0.0)) {
         c1 = cplx(exr, exi);

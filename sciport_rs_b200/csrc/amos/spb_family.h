@@ -261,7 +261,7 @@ SPB_FN cplx y_from_hankels(cplx z, int kode, cplx h1, cplx h2, int nz1, int nz2,
     sincos_(z.re, exi, exr);
     real ey = 0.0;
     real tay = rabs(z.im + z.im);
-    if (tay < elim) ey = exp(-tay);
+    if (tay < elim) ey = exp_(-tay);
     cplx c1, c2;
     if (z.im < real(0.0)) {
         c1 = cplx(exr, exi);

@@ -62,7 +62,7 @@ SPB_FN int seri(cplx z, real fnu, int kode, int n, Y y, real tol, real elim, rea
                 crscr = tol;
                 ascle = arm * ss;
             }
-            real aa = exp(ak1.re);
+            real aa = exp_(ak1.re);
             if (iflag == 1) aa *= ss;
             cplx coef(aa * cos(ak1.im), aa * sin(ak1.im));
             real atol = tol * acz / fnup;
@@ -347,7 +347,7 @@ SPB_FN int mlri(cplx z, real fnu, int kode, int n, Y y, real tol, real az_known 
     real fnf = fnu - real(ifnu);
     real tfnf = fnf + fnf;
     real bk = gamln(fkk + tfnf + real(1.0)) - gamln(fkk + real(1.0)) - gamln(tfnf + real(1.0));
-    bk = exp(bk);
+    bk = exp_(bk);
     cplx sum(0.0, 0.0);
     int km = kk - inu;
     for (int j = 1; j <= km; ++j) {

@@ -151,12 +151,13 @@ SPB_FN int bknu_body(cplx z, real fnu, int kode, int n, Y y, real tol, real elim
     real caz = az_known >= real(0.0) ? az_known : cabs_(z);
     real csclr = real(1.0) / tol;
     real crscr = tol;
-    real cssr[3] = {csclr, 1.0, crscr};
-    real csrr[3] = {crscr, 1.0, csclr};
-    real bry[3];
-    bry[0] = real(1.0e3) * SPB_D1MACH1 / tol;
-    bry[1] = real(1.0) / bry[0];
-    bry[2] = SPB_D1MACH2;
+    // three-level scaling constants, selected (not indexed: a dynamically indexed array would live in local
+    // memory on the device) by the level k = 1, 2, 3
+    const real bry0 = real(1.0e3) * SPB_D1MACH1 / tol;
+    const real bry1 = real(1.0) / bry0;
+    auto CSSR = [&](int k) -> real { return k == 1 ? csclr : (k == 2 ? real(1.0) : crscr); };
+    auto CSRR = [&](int k) -> real { return k == 1 ? crscr : (k == 2 ? real(1.0) : csclr); };
+    auto BRY = [&](int k) -> real { return k == 1 ? bry0 : (k == 2 ? bry1 : real(SPB_D1MACH2)); };
     int nz = 0;
     int iflag = 0;
     int koded = kode;
@@ -166,7 +167,7 @@ SPB_FN int bknu_body(cplx z, real fnu, int kode, int n, Y y, real tol, real elim
     real dnu = fnu - real(inu);
     real dnu2 = 0.0;
     cplx s1, s2, ck, coef, zd, p1, p2;
-    cplx cy[2];
+    cplx cy0(0.0, 0.0), cy1(0.0, 0.0);  // two-slot buffer of the iflag = 1 path
     int kflag = 2;
     real fhs = 0.0, fk = 0.0, ak = 0.0;
     bool half = (rabs(dnu) == real(0.5));
@@ -189,7 +190,7 @@ SPB_FN int bknu_body(cplx z, real fnu, int kode, int n, Y y, real tol, real elim
         }
         real a2 = real(1.0) + dnu;
         // t1 = 1/Gamma(1-dnu), t2 = 1/Gamma(1+dnu) via Gamma(1-d)Gamma(1+d) = pi d / sin(pi d)
-        real t2 = exp(-gamln(a2));
+        real t2 = exp_(-gamln(a2));
         real t1 = real(1.0) / (t2 * fc);
         real g1;
         if (rabs(dnu) > real(0.1)) {
@@ -257,7 +258,7 @@ SPB_FN int bknu_body(cplx z, real fnu, int kode, int n, Y y, real tol, real elim
         a1 = fnu + real(1.0);
         real aks = a1 * rabs(smu.re);
         if (aks > alim) kflag = 3;
-        real str = cssr[kflag - 1];
+        real str = CSSR(kflag);
         p2 = s2 * str;
         s2 = p2 * rz;
         s1 = s1 * str;
@@ -281,7 +282,7 @@ SPB_FN int bknu_body(cplx z, real fnu, int kode, int n, Y y, real tol, real elim
                 iflag = 1;
                 kflag = 2;
             } else {
-                real str = exp(-z.re) * cssr[kflag - 1];
+                real str = exp_(-z.re) * CSSR(kflag);
                 real sn, cs;
                 sincos_(z.im, sn, cs);
                 cplx st(str * cs, -str * sn);
@@ -414,7 +415,7 @@ SPB_FN int bknu_body(cplx z, real fnu, int kode, int n, Y y, real tol, real elim
                 real helim = real(0.5) * elim;
                 real elm = exp(-elim);
                 real celmr = elm;
-                real ascle = bry[0];
+                real ascle = bry0;
                 int ic = -1;
                 int j = 2;
                 bool two = false;
@@ -435,7 +436,7 @@ SPB_FN int bknu_body(cplx z, real fnu, int kode, int n, Y y, real tol, real elim
                         if (uchk(pp, ascle, tol) != 0) bad = true;
                         if (!bad) {
                             j = 3 - j;
-                            cy[j - 1] = pp;
+                            if (j == 1) cy0 = pp; else cy1 = pp;
                             if (ic == i - 1) {
                                 two = true;
                                 break;
@@ -456,9 +457,9 @@ SPB_FN int bknu_body(cplx z, real fnu, int kode, int n, Y y, real tol, real elim
                 } else {
                     kflag = 1;
                     inub = i + 1;
-                    s2 = cy[j - 1];
+                    s2 = (j == 1) ? cy0 : cy1;
                     j = 3 - j;
-                    s1 = cy[j - 1];
+                    s1 = (j == 1) ? cy0 : cy1;
                     if (inub > inu) {
                         if (n == 1) s1 = s2;
                         fin = 240;
@@ -467,8 +468,8 @@ SPB_FN int bknu_body(cplx z, real fnu, int kode, int n, Y y, real tol, real elim
                 }
             }
             if (regular) {
-                real p1r = csrr[kflag - 1];
-                real ascle = bry[kflag - 1];
+                real p1r = CSRR(kflag);
+                real ascle = BRY(kflag);
                 for (int i = inub; i <= inu; ++i) {
                     cplx st = s2;
                     s2 = ck * st + s1;
@@ -479,13 +480,13 @@ SPB_FN int bknu_body(cplx z, real fnu, int kode, int n, Y y, real tol, real elim
                     real p2m = rmax(rabs(pp.re), rabs(pp.im));
                     if (p2m <= ascle) continue;
                     kflag += 1;
-                    ascle = bry[kflag - 1];
+                    ascle = BRY(kflag);
                     s1 = s1 * p1r;
                     s2 = pp;
-                    real sc = cssr[kflag - 1];
+                    real sc = CSSR(kflag);
                     s1 = s1 * sc;
                     s2 = s2 * sc;
-                    p1r = csrr[kflag - 1];
+                    p1r = CSRR(kflag);
                 }
                 if (n == 1) s1 = s2;
                 fin = 240;
@@ -501,21 +502,21 @@ SPB_FN int bknu_body(cplx z, real fnu, int kode, int n, Y y, real tol, real elim
     if (fin == 270) {
         y[0] = s1;
         if (n != 1) y[1] = s2;
-        nz = kscl(zd, fnu, n, y, rz, bry[0], tol, elim);
+        nz = kscl(zd, fnu, n, y, rz, bry0, tol, elim);
         inu = n - nz;
         if (inu <= 0) return nz;
         kk = nz + 1;
         s1 = y[kk - 1];
-        y[kk - 1] = s1 * csrr[0];
+        y[kk - 1] = s1 * CSRR(1);
         if (inu == 1) return nz;
         kk = nz + 2;
         s2 = y[kk - 1];
-        y[kk - 1] = s2 * csrr[0];
+        y[kk - 1] = s2 * CSRR(1);
         if (inu == 2) return nz;
         ck = rz * (fnu + real(kk - 1));
         kflag = 1;
     } else {
-        real str = csrr[kflag - 1];
+        real str = CSRR(kflag);
         y[0] = s1 * str;
         if (n == 1) return nz;
         y[1] = s2 * str;
@@ -525,8 +526,8 @@ SPB_FN int bknu_body(cplx z, real fnu, int kode, int n, Y y, real tol, real elim
     kk += 1;
     if (kk > n) return nz;
     {
-        real p1r = csrr[kflag - 1];
-        real ascle = bry[kflag - 1];
+        real p1r = CSRR(kflag);
+        real ascle = BRY(kflag);
         for (int i = kk; i <= n; ++i) {
             cplx pp = s2;
             s2 = ck * pp + s1;
@@ -538,13 +539,13 @@ SPB_FN int bknu_body(cplx z, real fnu, int kode, int n, Y y, real tol, real elim
             real p2m = rmax(rabs(pp.re), rabs(pp.im));
             if (p2m <= ascle) continue;
             kflag += 1;
-            ascle = bry[kflag - 1];
+            ascle = BRY(kflag);
             s1 = s1 * p1r;
             s2 = pp;
-            real sc = cssr[kflag - 1];
+            real sc = CSSR(kflag);
             s1 = s1 * sc;
             s2 = s2 * sc;
-            p1r = csrr[kflag - 1];
+            p1r = CSRR(kflag);
         }
     }
     return nz;

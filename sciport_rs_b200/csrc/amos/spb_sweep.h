@@ -135,7 +135,7 @@ SPB_FN int isweep(cplx w, real fnu, int kode, int n, Y y, real az, cplx csgn0, i
         real sn, cs;
         sincos_(w.im, sn, cs);
         cplx cinu(cs, sn);
-        if (kode == 1) cinu = cinu * exp(w.re);
+        if (kode == 1) cinu = cinu * exp_(w.re);
         const cplx ifnu = (cinu * ract) * (conj(ct) * ract);
         // normalising factor q = I_fnu / (bottom iterate)
         const real bm = real(1.0) / cabs_(p1);

@@ -13,8 +13,15 @@
 
 namespace spbk {
 
+// minimum resident CTAs per SM the register allocation must allow (occupancy hides the FP64 dependency
+// latency of the region routines; measured on B200)
+#ifndef SPB_IPASS_MINB_ASYI
+#define SPB_IPASS_MINB_ASYI 7
+#endif
+#define SPB_IPASS_MINB(R) ((R) == 1 ? SPB_IPASS_MINB_ASYI : 1)
+
 template <int REGION>
-__global__ void __launch_bounds__(128) k_ipass(DevJob job, Scratch s) {
+__global__ void __launch_bounds__(128, SPB_IPASS_MINB(REGION)) k_ipass(DevJob job, Scratch s) {
     const unsigned int start = s.bins[REGION] - s.bins[0];
     const unsigned int count = s.bins[REGION + 1] - s.bins[REGION];
     const unsigned int stride = gridDim.x * blockDim.x;

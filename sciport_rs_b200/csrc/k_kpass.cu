@@ -11,7 +11,11 @@
 
 namespace spbk {
 
-__global__ void __launch_bounds__(128) k_kpass(DevJob job, Scratch s) {
+#ifndef SPB_KPASS_MINB
+#define SPB_KPASS_MINB 4
+#endif
+
+__global__ void __launch_bounds__(128, SPB_KPASS_MINB) k_kpass(DevJob job, Scratch s) {
     const unsigned int count = s.bins[BIN_GENERAL] - s.bins[BIN_K0];
     const unsigned int stride = gridDim.x * blockDim.x;
     const unsigned int *perm = s.perm_k;
