@@ -36,6 +36,38 @@ WORKLOAD = "cfg2: jv+yv, v=2.5, 4096x4096 complex grid |z|<=200 (2 evals per poi
 BYTES_PER_EVAL = 32.0
 
 
+def slice_bounds(n, world):
+    """Contiguous slice [i n / G, (i + 1) n / G) of an n-point batch per rank / device: the partition the C ABI uses
+    for n_devices = G (capi.cu) and the one a multi-rank job uses to shard one batch.  No element is shared, so
+    no collective runs on the data path."""
+    return [(n * r // world, n * (r + 1) // world) for r in range(world)]
+
+
+def max_over_ranks(value, device=None):
+    """Timing rule of the bench contract: the slowest rank defines the step.  all_reduce(MAX) over the default
+    process group (NCCL on GPUs, gloo in the CPU tests); identity without a process group."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def traffic_for(kernel_name):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/)."""
+    sass = {"kpass": "k_kpass(DevJob, Scratch)", "ipass_asyi": "void k_ipass<1>(DevJob, Scratch)",
+            "ipass_mlri": "void k_ipass<2>(DevJob, Scratch)", "classify": "k_classify(DevJob, Scratch)"}
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            t = json.load(f)["kernels"]
+        rec = t[sass[kernel_name.split("/")[-1]]]
+        return rec["dram_read_bytes"] + rec["dram_write_bytes"]
+    except Exception:
+        return None
+
+
 def load_flops_per_eval():
     path = os.path.join(ROOT, "profiles", "flops_per_eval.json")
     try:
@@ -130,7 +162,7 @@ def reference_arm(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    n_sample = N_POINTS  # the whole grid: about 1 s per step on 16 cores
+    n_sample = min(max(args.ref_sample, 4096), N_POINTS)  # default: the whole grid, about 1 s per step on 16 cores
     for _ in range(args.warmup):
         run_cpu_port(1 << 18, threads)
     t0 = time.perf_counter()
@@ -138,7 +170,7 @@ def reference_arm(args):
         run_cpu_port(n_sample, threads)
     dt = time.perf_counter() - t0
     value = 2 * n_sample * args.steps / dt
-    sample = f"all {n_sample} points of the 4096x4096 grid per step, jv+yv"
+    sample = f"{n_sample} evenly strided points of the 4096x4096 grid per step (all of it by default), jv+yv"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -160,6 +192,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=4)
+    ap.add_argument("--ref-sample", type=int, default=N_POINTS, help="points per step of the reference arm")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)
@@ -185,6 +218,9 @@ def main():
 
     # inputs resident in HBM: this rank's own 4096 x 4096 grid
     v, z = special.synth(2, N_POINTS, n_total=N_POINTS, device=dev)
+    if world > 1:
+        # every rank works on its own grid (weak scaling): the same disc |z| <= 200 turned by a rank-dependent angle
+        z = z * complex(np.cos(0.1 * rank), np.sin(0.1 * rank))
     vt = torch.full((1,), ORDER, dtype=torch.float64, device=dev)
 
     kernel_ms = [0.0]
@@ -240,10 +276,8 @@ def main():
         sampler.lines = sampler.lines[n_before:]
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = max_over_ranks(ms, dev)
         dist.barrier()
-        ms = float(t.item())
     evals_per_step = 2 * N_POINTS * world
     value = evals_per_step * args.steps / (ms * 1e-3)
 
@@ -269,10 +303,7 @@ def main():
             oj, oy = special.jvyv(ORDER, zn, outs=outs)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
+        dt = max_over_ranks(dt, dev)
         h2d = zn.nbytes + 8
         d2h = oj.nbytes + oy.nbytes + 16
         e2e = {"value": evals_per_step * args.e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d,
@@ -301,7 +332,10 @@ def main():
         achieved = (fpe * pts / (top["ms"] * 1e-3) / 1e12) if (fpe and pts) else None
         roofline = {
             "bound": "fp64", "kernel": top["name"], "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-            "frac": (achieved / fp64_peak) if achieved else None, "traffic": None,
+            "frac": (achieved / fp64_peak) if achieved else None, "traffic": traffic_for(top["name"]),
+            "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one launch, from the committed "
+                            "ncu --set full capture (profiles/r1_traffic.json)",
+            "algorithmic_bytes": BYTES_PER_EVAL * pts * (1.5 if top["name"].endswith("kpass") else 1.0),
             "peak_source": "spb_fp64_peak DFMA microbenchmark on this GPU (MEASURED_PEAKS.json has no FP64 figure)",
             "flops_per_point": fpe, "points_per_launch": pts, "launch_ms": top["ms"],
             "share_of_step": top["ms"] / max(sum(r["ms"] for r in prof), 1e-9),

@@ -51,14 +51,16 @@ inline counted fma_(counted a, counted b, counted c) { return a * b + c; }
 
 using namespace spb;
 
+static inline int islot(int ireg) { return ireg < 4 ? 2 + ireg : 5 + ireg; }  // regions 4, 5 -> ids 9, 10
+
 extern "C" {
 
-// ops[9]: classify(prepare), 4 ipass regions (region + its share of finish), kpass (+finish), general, and
-// pts[9] the number of points charged to each, following the kernel ids of include/sciport_b200.h
-// (0 classify, 2..5 ipass, 6 kpass, 7 general).
+// ops[11]: classify(prepare), 6 ipass regions (region + its share of finish), kpass (+finish), general, and
+// pts[11] the number of points charged to each, following the kernel ids of include/sciport_b200.h
+// (0 classify, 2..5 ipass series/asyi/mlri/wrsk, 6 kpass, 7 general, 9 / 10 ipass uniform forms 1 / 2).
 int spbo_count_ops(int fam, int kode, const double *v, int64_t v_stride, const double *z, int64_t n, double *ops,
                    int64_t *pts) {
-    for (int k = 0; k < 9; ++k) {
+    for (int k = 0; k < 11; ++k) {
         ops[k] = 0;
         pts[k] = 0;
     }
@@ -79,8 +81,8 @@ int spbo_count_ops(int fam, int kode, const double *v, int64_t v_stride, const d
             if (!general) {
                 g_ops = prep_ops;
                 inz = ipass_region(p.ireg, p.w, fnu, kode, iv);
-                ops[2 + p.ireg] += g_ops;
-                pts[2 + p.ireg] += 1;
+                ops[islot(p.ireg)] += g_ops;
+                pts[islot(p.ireg)] += 1;
                 if (inz < 0) general = true;
             }
             if (!general) {
@@ -115,8 +117,8 @@ int spbo_count_ops(int fam, int kode, const double *v, int64_t v_stride, const d
             inz = ipass_region(p.ireg, p.w, fnu, kode, ival);
             if (inz < 0) handed = true;
             if (!handed && p.combine == CMB_I_ROT) finish(fam, p, zz, fnu, kode, ival, inz, kval, 0, ierr, nz);
-            ops[2 + p.ireg] += g_ops;
-            pts[2 + p.ireg] += 1;
+            ops[islot(p.ireg)] += g_ops;
+            pts[islot(p.ireg)] += 1;
         }
         if (!handed && p.kreg >= 0) {
             g_ops = prep_ops;

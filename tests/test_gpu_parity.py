@@ -348,3 +348,23 @@ def test_first_error_tracked_on_device(special):
     # order sweeps: ierr is per point
     special.bessel("K", 0.5, np.array([1.0, 0.0, 2.0], dtype=complex), n_orders=20, want_codes=False)
     assert special.last_first_error() == (1, 1)
+
+
+def test_multi_device_slices_match_single_device(special):
+    """spb_exec.n_devices = G: contiguous slices, one host thread + two streams per device, no collective.
+    Results (and the first-error index, which is global) must not depend on G."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    rng = np.random.default_rng(21)
+    v, z = gen("cfg3", 3_000_017, rng)
+    z[2_900_000] = 0.0  # K is singular at the origin: ierr 1 in the second slice
+    one, e1, n1 = special.bessel("K", v, z, scaled=True)
+    idx1 = special.last_first_error()
+    g = torch.cuda.device_count()
+    many, eg, ng = special.bessel("K", v, z, scaled=True, devices=list(range(g)))
+    assert special.last_first_error() == idx1 == (2_900_000, 1)
+    assert np.array_equal(one.view(np.uint64), many.view(np.uint64))
+    assert np.array_equal(e1, eg) and np.array_equal(n1, ng)
+    sw1, _, _ = special.bessel("J", 0.0, z[:200_001], n_orders=32, want_codes=False)
+    swg, _, _ = special.bessel("J", 0.0, z[:200_001], n_orders=32, want_codes=False, devices=list(range(g)))
+    assert np.array_equal(sw1.view(np.uint64), swg.view(np.uint64))

@@ -19,7 +19,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 from test_pipeline_cpu import gen  # noqa: E402
 
 KERNELS = ["classify", "scan_scatter", "ipass_series", "ipass_asyi", "ipass_mlri", "ipass_wrsk", "kpass", "general",
-           "monolithic"]
+           "monolithic", "ipass_uni1", "ipass_uni2"]
 FN = {"J": 0, "Y": 1, "I": 2, "K": 3, "H1": 4, "H2": 5, "JY": 6}
 
 
@@ -46,11 +46,11 @@ def main():
         v = np.ascontiguousarray(v, dtype=np.float64)
         z = np.ascontiguousarray(z, dtype=np.complex128)
         for fn in fams:
-            ops = np.zeros(9)
-            pts = np.zeros(9, np.int64)
+            ops = np.zeros(11)
+            pts = np.zeros(11, np.int64)
             lib.spbo_count_ops(FN[fn], kode, v.ctypes.data, 1, z.ctypes.data, z.size, ops.ctypes.data, pts.ctypes.data)
-            total = ops[2:8].sum() + ops[0]
-            for k in range(9):
+            total = ops[2:8].sum() + ops[9:11].sum() + ops[0]
+            for k in range(11):
                 if pts[k]:
                     key = f"{fn}/{KERNELS[k]}" if cfg == "cfg2" else f"{cfg}:{fn}/{KERNELS[k]}"
                     out[key] = {"flops_per_point": ops[k] / pts[k], "points": int(pts[k])}
