@@ -137,6 +137,14 @@ int spb_clgamma(const spb_c128 *z, spb_c128 *out, int64_t n, const spb_exec *ex)
 /* ---- sinc, special::sinc (trig.rs:4-13): sin(pi x)/(pi x), 1 at x = 0 ---------------------- */
 int spb_sinc(const double *x, double *out, int64_t n, const spb_exec *ex);
 
+/* ---- windows built on the path (the batched in-tree consumers) -------------------------------------
+ * spb_kaiser: signal::windows::kaiser(m, beta, sym) (fir_filter_design/windows.rs:540-558): argument generation,
+ * I_0 through the complex routine, division by I_0(beta) and modulus fused in one pass; out has m doubles.
+ * spb_lanczos: signal::windows::lanczos(m, sym) (windows.rs:509-538) on the fused sinc.
+ * sym = 0 gives the periodic (fftbins) form: first m points of the symmetric window of length m + 1. */
+int spb_kaiser(int64_t m, double beta, int sym, double *out, const spb_exec *ex);
+int spb_lanczos(int64_t m, int sym, double *out, const spb_exec *ex);
+
 /* ---- first error in index order = `.collect::<Result<_, i32>>()` (mod.rs:11-12) ------------
  * *idx = -1, *code = 0 when every element is OK.  ierr lives where ex says. */
 int spb_first_error(const int32_t *ierr, int64_t n, int64_t *idx, int32_t *code, const spb_exec *ex);

@@ -170,6 +170,46 @@ int spbo_bessel_seq(int fn, int kode, const double *v, int64_t v_stride, const d
     return 0;
 }
 
+// signal::windows::kaiser (/root/reference/src/signal/fir_filter_design/windows.rs:540-558), restated with the
+// checker's I_0: l = beta sqrt(1 - ((n - alpha)/alpha)^2); w = |I0(l) / I0(beta)|; periodic form = first m points of
+// the symmetric window of length m + 1; lengths <= 1 give ones.
+int spbo_kaiser(int64_t m, double beta, int sym, double *out) {
+    if (m <= 1) {
+        for (int64_t i = 0; i < m; ++i) out[i] = 1.0;
+        return 0;
+    }
+    const int64_t m_ext = sym ? m : m + 1;
+    const double alpha = 0.5 * ((double)m_ext - 1.0);
+    int ie, nz;
+    const cplx r = general_eval(FN_I, cplx(beta, 0.0), 0.0, 1, ie, nz);
+    for (int64_t n = 0; n < m; ++n) {
+        const double t = ((double)n - alpha) / alpha;
+        const double l = beta * std::sqrt(1.0 - t * t);
+        const cplx q = cdiv(general_eval(FN_I, cplx(l, 0.0), 0.0, 1, ie, nz), r);
+        out[n] = cabs_(q);
+    }
+    return 0;
+}
+
+// signal::windows::lanczos (windows.rs:509-538)
+int spbo_lanczos(int64_t m, int sym, double *out) {
+    if (m <= 1) {
+        for (int64_t i = 0; i < m; ++i) out[i] = 1.0;
+        return 0;
+    }
+    const int64_t m_ext = sym ? m : m + 1;
+    const int64_t half = (m_ext % 2 == 0) ? m_ext / 2 : (m_ext + 1) / 2;
+    for (int64_t n = 0; n < m; ++n) {
+        if (m_ext % 2 == 1 && n == (m_ext - 1) / 2) {
+            out[n] = 1.0;
+            continue;
+        }
+        const int64_t j = n >= half ? n : (m_ext - 1 - n);
+        out[n] = sinc_real(2.0 * (double)j / ((double)m_ext - 1.0) - 1.0);
+    }
+    return 0;
+}
+
 // which: 0 Ai, 1 Ai', 2 Bi, 3 Bi'
 int spbo_airy(int which, int kode, const double *z, double *out, int32_t *ierr, int32_t *nz, int64_t n,
               int threads) {

@@ -75,6 +75,7 @@ struct DeviceCtx {
     unsigned long long *d_packed = nullptr;
     unsigned long long *d_first = nullptr;         // [2] first failing element (packed) of the call in flight
     unsigned long long h_first[2] = {~0ull, ~0ull};  // host copy, valid once the call has completed
+    double2 *d_scalar = nullptr;                   // one complex scalar (I0(beta) of the Kaiser window)
 };
 
 // which devices the last compute call of this thread used, for spb_last_first_error()
@@ -109,6 +110,7 @@ DeviceCtx *get_ctx(int dev) {
         cudaEventCreate(&c->ev1);
         cudaMalloc(&c->d_packed, sizeof(unsigned long long));
         cudaMalloc(&c->d_first, 2 * sizeof(unsigned long long));
+        cudaMalloc(&c->d_scalar, sizeof(double2));
         g_ctx[dev] = c;
     }
     return g_ctx[dev];
@@ -805,6 +807,58 @@ int spb_sinc(const double *x, double *out, int64_t n, const spb_exec *ex) {
         launch_sinc((const double *)i, (double *)o, m, st);
     });
 }
+
+// windows: nothing is read, m doubles are written (device pointer: on the caller's stream; host pointer: staged)
+static int window_impl(int kind, int64_t m, double beta, int sym, double *out, const spb_exec *ex) {
+    std::vector<int> devs;
+    bool dptr;
+    cudaStream_t st;
+    int flags;
+    int rc = check_exec(ex, devs, dptr, st, flags);
+    if (rc != SPB_OK) return rc;
+    if (m < 0) return fail(SPB_E_ARG, "negative window length");
+    if (m == 0) return SPB_OK;
+    if (!out) return fail(SPB_E_ARG, "null buffer");
+    if (kind == 0 && !(beta == beta)) return fail(SPB_E_ARG, "beta is NaN");
+    DeviceCtx *c = get_ctx(devs[0]);
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->dev));
+    cudaStream_t s0 = dptr ? st : c->streams[0];
+    double *dout = out;
+    if (!dptr && cudaMalloc(&dout, m * 8) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(SPB_E_ALLOC, "cudaMalloc failed");
+    }
+    g_last_launches = 1;
+    if (m <= 1) {
+        // len_guards (windows.rs:624-626, 650-656): windows of length <= 1 are all ones
+        const double one = 1.0;
+        CK(cudaMemcpyAsync(dout, &one, 8, cudaMemcpyHostToDevice, s0));
+    } else {
+        // periodic windows (sym = false) are the first m points of the symmetric window of length m + 1
+        // (extend / truncate, windows.rs:628-647)
+        const long long m_ext = sym ? m : m + 1;
+        if (kind == 0) {
+            launch_kaiser(m_ext, m, beta, c->d_scalar, dout, c->sms, s0);
+            g_last_launches = 2;
+        } else {
+            launch_lanczos(m_ext, m, dout, s0);
+        }
+    }
+    CK(cudaGetLastError());
+    if (!dptr) {
+        cudaError_t e = cudaMemcpyAsync(out, dout, m * 8, cudaMemcpyDeviceToHost, s0);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s0);
+        cudaFree(dout);
+        if (e != cudaSuccess) return fail(SPB_E_CUDA, cudaGetErrorString(e));
+    }
+    return SPB_OK;
+}
+
+int spb_kaiser(int64_t m, double beta, int sym, double *out, const spb_exec *ex) {
+    return window_impl(0, m, beta, sym, out, ex);
+}
+int spb_lanczos(int64_t m, int sym, double *out, const spb_exec *ex) { return window_impl(1, m, 0.0, sym, out, ex); }
 
 int spb_first_error(const int32_t *ierr, int64_t n, int64_t *idx, int32_t *code, const spb_exec *ex) {
     if (!idx || !code) return fail(SPB_E_ARG, "null output");

@@ -33,6 +33,8 @@ def oracle_lib():
         lib.spbo_airy.argtypes = [I, I, P, P, P, P, L, I]
         lib.spbo_bessel_jy_pipeline.argtypes = [I, P, L, P, P, P, P, L, I]
         lib.spbo_bessel_seq.argtypes = [I, I, P, L, P, P, P, P, L, I, I]
+        lib.spbo_kaiser.argtypes = [L, ctypes.c_double, I, P]
+        lib.spbo_lanczos.argtypes = [L, I, P]
         lib.spbo_gamma.argtypes = [I, P, P, L]
         lib.spbo_cgamma.argtypes = [I, P, P, L]
         _oracle = lib
@@ -102,6 +104,18 @@ def cpu_gamma(which, x):
     x = np.ascontiguousarray(x, dtype=np.float64)
     out = np.empty_like(x)
     lib.spbo_gamma(which, x.ctypes.data, out.ctypes.data, x.size)
+    return out
+
+
+def cpu_kaiser(m, beta, sym=True):
+    out = np.empty(m, np.float64)
+    oracle_lib().spbo_kaiser(m, float(beta), 1 if sym else 0, out.ctypes.data)
+    return out
+
+
+def cpu_lanczos(m, sym=True):
+    out = np.empty(m, np.float64)
+    oracle_lib().spbo_lanczos(m, 1 if sym else 0, out.ctypes.data)
     return out
 
 
