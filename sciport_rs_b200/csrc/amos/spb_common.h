@@ -107,6 +107,11 @@ SPB_HD double pow2_(int e) {
 // |z| without premature over/underflow (the ZABS of the algorithm).
 SPB_HD real cabs_(cplx z) {
     real u = rabs(z.re), v = rabs(z.im);
+    // both squares on scale: the plain form (one square root, no division) is as accurate as the scaled one
+    {
+        real m = rmax(u, v);
+        if (m > real(1.0e-140) && m < real(1.0e140)) return sqrt(u * u + v * v);
+    }
     real s = u + v;
     // s*1.0 in the original forces a store; here we only need the zero test.
     if (s == real(0.0)) return real(0.0);

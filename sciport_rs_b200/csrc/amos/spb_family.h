@@ -95,19 +95,10 @@ SPB_HD int iregion_simple(cplx w, real fnu, real az, bool &simple, int kode) {
     return r;
 }
 
-SPB_FN Prep prepare(int fam, cplx z, real fnu, int kode) {
-    const real fnul = SPB_FNUL, alim = SPB_ALIM, tol = SPB_TOL;
-    Prep p;
-    p.w = z;
-    p.combine = CMB_GENERAL;
-    p.ireg = -1;
-    p.kreg = -1;
-    p.ierr = 0;
-    p.mr = 0;
-    // anything unusual (invalid input, NaN, huge or tiny arguments) goes to the driver
-    real az = cabs_(z);
-    p.az = az;
-    if (!(fnu >= real(0.0)) || !(az == az) || !(az < real(32767.0)) || !(fnu < real(32767.0))) return p;
+// Geometry of a family at z: the right-half-plane evaluation point w, the continuation direction and the way the
+// pass results combine, assuming the point turns out simple.  Returns whether I_v(w) is needed.  Shared by the
+// classifier (prepare) and by the region passes (prepare_pass), which skip the region tests.
+SPB_HD bool prepare_geometry(int fam, cplx z, Prep &p) {
     if (fam == FAM_J || fam == FAM_I) {
         if (fam == FAM_J) {
             p.w = cplx(z.im, -z.re);
@@ -115,15 +106,9 @@ SPB_FN Prep prepare(int fam, cplx z, real fnu, int kode) {
         } else if (z.re < real(0.0)) {
             p.w = -z;
         }
-        bool simple;
-        if (az == real(0.0)) return p;
-        p.ireg = iregion_simple(p.w, fnu, az, simple, kode);
-        if (simple) p.combine = CMB_I_ROT;
-        return p;
+        p.combine = CMB_I_ROT;
+        return true;
     }
-    // K-type families
-    if (az < real(1.0e-290) || fnu > fnul) return p;
-    if (!(fnu > real(2.0)) && fnu > real(1.0) && !(az > tol)) return p;
     bool left;
     if (fam == FAM_K) {
         left = z.re < real(0.0);
@@ -155,13 +140,42 @@ SPB_FN Prep prepare(int fam, cplx z, real fnu, int kode) {
             left = true;
         }
     }
+    if (fam == FAM_JY) left = true;  // J needs I(w) even where Y alone would not (positive real axis)
+    return left;
+}
+
+SPB_FN Prep prepare(int fam, cplx z, real fnu, int kode) {
+    const real fnul = SPB_FNUL, alim = SPB_ALIM, tol = SPB_TOL;
+    Prep p;
+    p.w = z;
+    p.combine = CMB_GENERAL;
+    p.ireg = -1;
+    p.kreg = -1;
+    p.ierr = 0;
+    p.mr = 0;
+    // anything unusual (invalid input, NaN, huge or tiny arguments) goes to the driver
+    real az = cabs_(z);
+    p.az = az;
+    if (!(fnu >= real(0.0)) || !(az == az) || !(az < real(32767.0)) || !(fnu < real(32767.0))) return p;
+    if (fam == FAM_J || fam == FAM_I) {
+        if (az == real(0.0)) return p;
+        prepare_geometry(fam, z, p);
+        p.combine = CMB_GENERAL;
+        bool simple;
+        p.ireg = iregion_simple(p.w, fnu, az, simple, kode);
+        if (simple) p.combine = CMB_I_ROT;
+        return p;
+    }
+    // K-type families
+    if (az < real(1.0e-290) || fnu > fnul) return p;
+    if (!(fnu > real(2.0)) && fnu > real(1.0) && !(az > tol)) return p;
+    const bool left = prepare_geometry(fam, z, p);
     // over/underflow pre-test of the K drivers (made at the rotated point) must be a no-op
     if (fnu > real(2.0) && !uoik_is_noop(az, rmax(fnu, real(1.0)), alim, rabs(p.w.re), kode)) {
         p.combine = CMB_GENERAL;
         return p;
     }
     p.kreg = kregion(p.w, fnu, az);
-    if (fam == FAM_JY) left = true;  // J needs I(w) even where Y alone would not (positive real axis)
     if (left) {
         bool simple;
         p.ireg = iregion_simple(p.w, fnu, az, simple, kode);
@@ -171,6 +185,21 @@ SPB_FN Prep prepare(int fam, cplx z, real fnu, int kode) {
             p.kreg = -1;
         }
     }
+    return p;
+}
+
+// prepare() for a point the classifier has already binned: the region tests are known to have passed, so only
+// the geometry and the modulus are recomputed.  has_i = the class byte carries an I bin.
+SPB_FN Prep prepare_pass(int fam, cplx z, bool has_i) {
+    Prep p;
+    p.w = z;
+    p.combine = CMB_GENERAL;
+    p.ireg = has_i ? 0 : -1;  // passes only ask whether I(w) exists
+    p.kreg = -1;
+    p.ierr = 0;
+    p.mr = 0;
+    p.az = cabs_(z);
+    prepare_geometry(fam, z, p);
     return p;
 }
 
@@ -454,6 +483,13 @@ SPB_FN cplx pipeline_eval(int fam, cplx z, real fnu, int kode, int &ierr, int &n
     Prep p = prepare(fam, z, fnu, kode);
     path = 1;
     if (p.combine == CMB_GENERAL) return general_eval(fam, z, fnu, kode, ierr, nz);
+    {
+        // the region passes see only the class (bins) and recompute the geometry: same thing here
+        const int ireg = p.ireg, kreg = p.kreg;
+        p = prepare_pass(fam, z, ireg >= 0);
+        p.ireg = ireg;
+        p.kreg = kreg;
+    }
     cplx ival(0.0, 0.0), kval(0.0, 0.0);
     int inz = 0, knz = 0;
     path = 2;
@@ -479,6 +515,12 @@ SPB_FN void pipeline_eval_jy(cplx z, real fnu, int kode, cplx &jv, int &jerr, in
     cplx ival(0.0, 0.0), kval(0.0, 0.0);
     int inz = 0, knz = 0;
     bool general = (p.combine == CMB_GENERAL);
+    if (!general) {
+        const int ireg = p.ireg, kreg = p.kreg;
+        p = prepare_pass(FAM_JY, z, ireg >= 0);
+        p.ireg = ireg;
+        p.kreg = kreg;
+    }
     if (!general) {
         path = 2;
         inz = ipass_region(p.ireg, p.w, fnu, kode, ival, p.az);

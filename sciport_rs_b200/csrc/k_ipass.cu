@@ -47,7 +47,8 @@ __global__ void __launch_bounds__(128, SPB_IPASS_MINB(REGION)) k_ipass(DevJob jo
         if (have2) i2 = __ldg(perm + t + stride);
         if (have1) load_point(job, i1, z1, v1);
 
-        spb::Prep p = spb::prepare(job.fam, z, v, job.kode);
+        // the classifier has already established region and simplicity of this point: geometry only
+        spb::Prep p = spb::prepare_pass(job.fam, z, true);
         const spb::OrderPhase *ph = pc.get(v);
         cplx ival;
         int inz = spb::ipass_region(REGION, p.w, v, job.kode, ival, p.az, ph);

@@ -27,10 +27,12 @@ __global__ void __launch_bounds__(128, SPB_KPASS_MINB) k_kpass(DevJob job, Scrat
     double v1 = 0.0;
     double2 it1 = make_double2(0.0, 0.0);
     int ic1 = 0;
+    unsigned int cl1 = 0;
     if (have1) {
         load_point(job, i1, z1, v1);
         it1 = s.itemp[i1];
         ic1 = s.icode[i1];
+        cl1 = s.cls[i1];
     }
     PhaseCache pc;
 #pragma unroll 1
@@ -40,6 +42,7 @@ __global__ void __launch_bounds__(128, SPB_KPASS_MINB) k_kpass(DevJob job, Scrat
         const double v = v1;
         const double2 itv = it1;
         const int icv = ic1;
+        const bool has_i = (cl1 & 7u) != 7u;  // the class byte carries an I bin: I(w) was parked by the I pass
         t += stride;
         have1 = have2;
         i1 = i2;
@@ -49,9 +52,11 @@ __global__ void __launch_bounds__(128, SPB_KPASS_MINB) k_kpass(DevJob job, Scrat
             load_point(job, i1, z1, v1);
             it1 = s.itemp[i1];  // only meaningful where the point went through the I pass
             ic1 = s.icode[i1];
+            cl1 = s.cls[i1];
         }
 
-        spb::Prep p = spb::prepare(job.fam, z, v, job.kode);
+        // the classifier has already established regions and simplicity of this point: geometry only
+        spb::Prep p = spb::prepare_pass(job.fam, z, has_i);
         cplx ival(0.0, 0.0);
         int inz = 0;
         if (p.ireg >= 0) {
