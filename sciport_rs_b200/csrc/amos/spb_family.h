@@ -236,11 +236,8 @@ SPB_FN int ipass_region(int region, cplx w, real fnu, int kode, cplx &val, real 
 
 SPB_FN int kpass_region(cplx w, real fnu, int kode, cplx &val, real az = real(-1.0)) {
     const real tol = SPB_TOL, elim = SPB_ELIM, alim = SPB_ALIM;
-    cplx y[1];
-    y[0] = cplx(0.0, 0.0);
-    int nw = bknu(w, fnu, kode, 1, y, tol, elim, alim, az);
-    val = y[0];
-    return nw;
+    // binned points stay on the middle scaling level (their pre-test is a no-op): the lean form of the routine
+    return bknu_simple(w, fnu, kode, val, tol, elim, alim, az);
 }
 
 // continuation K(w e^{i pi mr}) from (K(w), I(w)) for one member (acon with n = 1)

@@ -133,9 +133,14 @@ SPB_FN int s1s2(cplx zr, cplx &s1, cplx &s2, real ascle, real alim, int &iuf) {
 // The body reports a failed start-index search of the Miller algorithm through `noconv` instead of
 // returning on the spot: a `return` between the data-dependent loops would move the reconvergence point of
 // their exits to the end of the routine and leave a warp split for the rest of it.
-template <class Y>
+//
+// SIMPLE = true is the form the binned K pass uses for points whose over/underflow pre-test is known to be a
+// no-op: the value stays on the middle scaling level throughout, so the three-level machinery is compiled out
+// and a point that would leave the middle level after all is reported through `handover` (the caller sends it
+// to the general path).  On the middle level every scaling factor is exactly 1, so both forms round identically.
+template <bool SIMPLE, class Y>
 SPB_FN int bknu_body(cplx z, real fnu, int kode, int n, Y y, real tol, real elim, real alim, real az_known,
-                     bool &noconv) {
+                     bool &noconv, bool &handover) {
     const int kmax = 30;
     const real r1 = 2.0;
     const real dpi = SPB_PI;
@@ -257,7 +262,12 @@ SPB_FN int bknu_body(cplx z, real fnu, int kode, int n, Y y, real tol, real elim
         kflag = 2;
         a1 = fnu + real(1.0);
         real aks = a1 * rabs(smu.re);
-        if (aks > alim) kflag = 3;
+        if (aks > alim) {
+            if (SIMPLE)
+                handover = true;
+            else
+                kflag = 3;
+        }
         real str = CSSR(kflag);
         p2 = s2 * str;
         s2 = p2 * rz;
@@ -277,7 +287,8 @@ SPB_FN int bknu_body(cplx z, real fnu, int kode, int n, Y y, real tol, real elim
         coef = conj(csqrt_mod(z, caz)) * (rthpi * rcaz);
         kflag = 2;
         if (koded != 2) {
-            if (z.re > alim) {
+            if (z.re > alim && SIMPLE) handover = true;
+            if (z.re > alim && !SIMPLE) {
                 koded = 2;
                 iflag = 1;
                 kflag = 2;
@@ -410,7 +421,7 @@ SPB_FN int bknu_body(cplx z, real fnu, int kode, int n, Y y, real tol, real elim
         zd = z;
         if (inu > 0) {
             bool regular = true;
-            if (iflag == 1) {
+            if (!SIMPLE && iflag == 1) {
                 // iflag=1: forward recurrence on scaled values until two members are on scale
                 real helim = real(0.5) * elim;
                 real elm = exp(-elim);
@@ -475,6 +486,10 @@ SPB_FN int bknu_body(cplx z, real fnu, int kode, int n, Y y, real tol, real elim
                     s2 = ck * st + s1;
                     s1 = st;
                     ck = ck + rz;
+                    if (SIMPLE) {
+                        if (rmax(rabs(s2.re), rabs(s2.im)) > ascle) handover = true;
+                        continue;
+                    }
                     if (kflag >= 3) continue;
                     cplx pp = s2 * p1r;
                     real p2m = rmax(rabs(pp.re), rabs(pp.im));
@@ -499,7 +514,7 @@ SPB_FN int bknu_body(cplx z, real fnu, int kode, int n, Y y, real tol, real elim
 
     // ---------------------------------------------------------------- store / finish the sequence
     int kk;
-    if (fin == 270) {
+    if (!SIMPLE && fin == 270) {
         y[0] = s1;
         if (n != 1) y[1] = s2;
         nz = kscl(zd, fnu, n, y, rz, bry0, tol, elim);
@@ -554,13 +569,26 @@ SPB_FN int bknu_body(cplx z, real fnu, int kode, int n, Y y, real tol, real elim
 template <class Y>
 SPB_FN int bknu(cplx z, real fnu, int kode, int n, Y y, real tol, real elim, real alim,
                 real az_known = real(-1.0)) {
-    bool noconv = false;
-    int nz = bknu_body(z, fnu, kode, n, y, tol, elim, alim, az_known, noconv);
+    bool noconv = false, handover = false;
+    int nz = bknu_body<false>(z, fnu, kode, n, y, tol, elim, alim, az_known, noconv, handover);
     if (noconv) {
         for (int k = 0; k < n; ++k) y[k] = cplx(0.0, 0.0);
         return -2;
     }
     return nz;
+}
+
+// K_fnu(z), one member, for a point of the binned K pass (see bknu_body).  Returns 0, or < 0: hand the point to
+// the general path (-2 no convergence, -9 the value left the middle scaling level).
+SPB_FN int bknu_simple(cplx z, real fnu, int kode, cplx &val, real tol, real elim, real alim, real az_known) {
+    bool noconv = false, handover = false;
+    cplx y[1];
+    y[0] = cplx(0.0, 0.0);
+    int nz = bknu_body<true>(z, fnu, kode, 1, y, tol, elim, alim, az_known, noconv, handover);
+    val = y[0];
+    if (noconv) return -2;
+    if (handover || nz != 0) return -9;
+    return 0;
 }
 
 }  // namespace spb
