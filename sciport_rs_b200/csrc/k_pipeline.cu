@@ -47,13 +47,32 @@ struct Packed {
     }
 };
 
+// The three keys of a class byte land in fixed places of the two words (NB_I = 6, five fields per word):
+// I bins 0..4 -> word 0, field bi; I bin 5 -> word 1, field 0; K bins -> word 1, fields 1..3; general -> word 1,
+// field 4.  Written out so that the only variable-dependent work is one multiply and one shift per key.
+static_assert(NB_I == 6 && NB_K == 3 && FIELDS_PER_WORD == 5 && NWORDS == 2, "packed layout below assumes 6 + 3 + 1 bins");
+
 __device__ __forceinline__ void packed_add(unsigned int c, Packed &p) {
     int bi, bk;
     bool gen;
     point_bins(c, bi, bk, gen);
-    if (bi != 7) p.bump(bi);
-    if (bk != 3) p.bump(BIN_K0 + bk);
-    if (gen) p.bump(BIN_GENERAL);
+    if (bi < 5)
+        p.w[0] += 1ull << (FIELD_BITS * bi);
+    else if (bi == 5)
+        p.w[1] += 1ull;
+    if (bk != 3) p.w[1] += 1ull << (FIELD_BITS * (bk + 1));
+    if (gen) p.w[1] += 1ull << (FIELD_BITS * 4);
+}
+
+__device__ __forceinline__ unsigned int field_i(const Packed &p, int bi) {
+    unsigned long long x = bi < 5 ? (p.w[0] >> (FIELD_BITS * bi)) : p.w[1];
+    return (unsigned int)x & ((1u << FIELD_BITS) - 1u);
+}
+__device__ __forceinline__ unsigned int field_k(const Packed &p, int bk) {
+    return (unsigned int)(p.w[1] >> (FIELD_BITS * (bk + 1))) & ((1u << FIELD_BITS) - 1u);
+}
+__device__ __forceinline__ unsigned int field_g(const Packed &p) {
+    return (unsigned int)(p.w[1] >> (FIELD_BITS * 4)) & ((1u << FIELD_BITS) - 1u);
 }
 
 __global__ void __launch_bounds__(256) k_classify(DevJob job, Scratch s) {
@@ -168,7 +187,8 @@ __global__ void __launch_bounds__(1024) k_scan(Scratch s) {
 
 __global__ void __launch_bounds__(256) k_scatter(DevJob job, Scratch s) {
     __shared__ unsigned long long warp_tot[8][NWORDS];
-    __shared__ unsigned int tile_base[NBINS];
+    __shared__ unsigned int tile_base[NBINS], lstart[NBINS], seg_total[3];
+    __shared__ unsigned int stage[3][TILE];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const long long base = (long long)blockIdx.x * TILE + (long long)threadIdx.x * 8;
     if (threadIdx.x < NBINS) {
@@ -207,13 +227,38 @@ __global__ void __launch_bounds__(256) k_scatter(DevJob job, Scratch s) {
         for (int k = 0; k < NWORDS; ++k) warp_tot[wid][k] = incl.w[k];
     }
     __syncthreads();
-    Packed off;
+    Packed off, total;
 #pragma unroll
-    for (int k = 0; k < NWORDS; ++k) off.w[k] = incl.w[k] - mine.w[k];
-    for (int w = 0; w < wid; ++w) {
-#pragma unroll
-        for (int k = 0; k < NWORDS; ++k) off.w[k] += warp_tot[w][k];
+    for (int k = 0; k < NWORDS; ++k) {
+        off.w[k] = incl.w[k] - mine.w[k];
+        total.w[k] = 0;
     }
+    for (int w = 0; w < 8; ++w) {
+#pragma unroll
+        for (int k = 0; k < NWORDS; ++k) {
+            if (w < wid) off.w[k] += warp_tot[w][k];
+            total.w[k] += warp_tot[w][k];
+        }
+    }
+    // The indices are first laid out in shared memory in their final (bin-major, stable) order and then
+    // written out by consecutive threads: a thread's 8 consecutive points would otherwise produce stride-8
+    // 4-byte stores (eight L2 write requests per warp instruction instead of one).
+    if (threadIdx.x < NBINS) {
+        const int b = threadIdx.x;
+        const int first = b < BIN_K0 ? 0 : b < BIN_GENERAL ? BIN_K0 : BIN_GENERAL;
+        unsigned int st = 0;
+        for (int k = first; k < b; ++k) st += total.field(k);
+        lstart[b] = st;
+    }
+    if (threadIdx.x == 0) {
+        unsigned int ti = 0, tk = 0;
+        for (int k = 0; k < BIN_K0; ++k) ti += total.field(k);
+        for (int k = BIN_K0; k < BIN_GENERAL; ++k) tk += total.field(k);
+        seg_total[0] = ti;
+        seg_total[1] = tk;
+        seg_total[2] = total.field(BIN_GENERAL);
+    }
+    __syncthreads();
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         if (k >= valid) break;
@@ -221,19 +266,29 @@ __global__ void __launch_bounds__(256) k_scatter(DevJob job, Scratch s) {
         bool gen;
         point_bins((unsigned int)((cls8 >> (8 * k)) & 0xffu), bi, bk, gen);
         const unsigned int idx = (unsigned int)(base + k);
-        if (bi != 7) {
-            s.perm_i[tile_base[bi] + off.field(bi)] = idx;
-            off.bump(bi);
-        }
-        if (bk != 3) {
-            s.perm_k[tile_base[BIN_K0 + bk] + off.field(BIN_K0 + bk)] = idx;
-            off.bump(BIN_K0 + bk);
-        }
-        if (gen) {
-            s.glist[tile_base[BIN_GENERAL] + off.field(BIN_GENERAL)] = idx;
-            off.bump(BIN_GENERAL);
-        }
+        if (bi != 7) stage[0][lstart[bi] + field_i(off, bi)] = idx;
+        if (bk != 3) stage[1][lstart[BIN_K0 + bk] + field_k(off, bk)] = idx;
+        if (gen) stage[2][field_g(off)] = idx;
+        packed_add((unsigned int)((cls8 >> (8 * k)) & 0xffu), off);
     }
+    __syncthreads();
+    // coalesced write-out, one segment at a time; position j of a segment belongs to the last bin whose local
+    // start is <= j
+    for (unsigned int j = threadIdx.x; j < seg_total[0]; j += 256) {
+        int b = 0;
+#pragma unroll
+        for (int k = 1; k < NB_I; ++k)
+            if (j >= lstart[k]) b = k;
+        s.perm_i[tile_base[b] + (j - lstart[b])] = stage[0][j];
+    }
+    for (unsigned int j = threadIdx.x; j < seg_total[1]; j += 256) {
+        int b = BIN_K0;
+#pragma unroll
+        for (int k = BIN_K0 + 1; k < BIN_GENERAL; ++k)
+            if (j >= lstart[k]) b = k;
+        s.perm_k[tile_base[b] + (j - lstart[b])] = stage[1][j];
+    }
+    for (unsigned int j = threadIdx.x; j < seg_total[2]; j += 256) s.glist[tile_base[BIN_GENERAL] + j] = stage[2][j];
 }
 
 void launch_classify(const DevJob &job, const Scratch &s, cudaStream_t st) {
