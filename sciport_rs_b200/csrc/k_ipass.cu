@@ -20,6 +20,32 @@ namespace spbk {
 #endif
 #define SPB_IPASS_MINB(R) ((R) == 1 ? SPB_IPASS_MINB_ASYI : 1)
 
+// one point of the I pass: I_v(w) by the region routine; J / I families finish here, the others park I(w)
+template <int REGION>
+__device__ __forceinline__ void ipass_point(const DevJob &job, const Scratch &s, long long i, cplx z, double v,
+                                            PhaseCache &pc) {
+    // the classifier has already established region and simplicity of this point: geometry only
+    spb::Prep p = spb::prepare_pass(job.fam, z, true);
+    const spb::OrderPhase *ph = pc.get(v);
+    cplx ival;
+    int inz = spb::ipass_region(REGION, p.w, v, job.kode, ival, p.az, ph);
+    if (inz < 0) {
+        // the region wants to hand over: finish this point on the general path
+        unsigned int g = atomicAdd(&s.bins[GLIST_LEN_SLOT], 1u);
+        s.glist[g] = (unsigned int)i;
+        s.icode[i] = (signed char)-1;
+        return;
+    }
+    if (p.combine == spb::CMB_I_ROT) {
+        int ierr, nz;
+        cplx val = spb::finish(job.fam, p, z, v, job.kode, ival, inz, cplx(0.0, 0.0), 0, ierr, nz, ph);
+        store_point(job, i, val, ierr, nz);
+    } else {
+        s.itemp[i] = make_double2(ival.re, ival.im);
+        s.icode[i] = (signed char)inz;
+    }
+}
+
 template <int REGION>
 __global__ void __launch_bounds__(128, SPB_IPASS_MINB(REGION)) k_ipass(DevJob job, Scratch s) {
     const unsigned int start = s.bins[REGION] - s.bins[0];
@@ -46,27 +72,51 @@ __global__ void __launch_bounds__(128, SPB_IPASS_MINB(REGION)) k_ipass(DevJob jo
         have2 = (t + stride) < count;
         if (have2) i2 = __ldg(perm + t + stride);
         if (have1) load_point(job, i1, z1, v1);
+        ipass_point<REGION>(job, s, i, z, v, pc);
+    }
+}
 
-        // the classifier has already established region and simplicity of this point: geometry only
-        spb::Prep p = spb::prepare_pass(job.fam, z, true);
-        const spb::OrderPhase *ph = pc.get(v);
-        cplx ival;
-        int inz = spb::ipass_region(REGION, p.w, v, job.kode, ival, p.az, ph);
-        if (inz < 0) {
-            // the region wants to hand over: finish this point on the general path
-            unsigned int g = atomicAdd(&s.bins[GLIST_LEN_SLOT], 1u);
-            s.glist[g] = (unsigned int)i;
-            s.icode[i] = (signed char)-1;
-            continue;
+// Per-element orders, Miller / Wronskian region: batches grouped by predicted work (spb_dev.cuh)
+template <int REGION>
+__global__ void __launch_bounds__(128) k_ipass_sorted(DevJob job, Scratch s) {
+    __shared__ SortSmem sm;
+    __shared__ unsigned int s_idx[SORT_B];
+    __shared__ double2 s_z[SORT_B];
+    __shared__ double s_v[SORT_B];
+    const unsigned int start = s.bins[REGION] - s.bins[0];
+    const unsigned int count = s.bins[REGION + 1] - s.bins[REGION];
+    const unsigned int *perm = s.perm_i + start;
+    PhaseCache pc;
+#pragma unroll 1
+    for (unsigned int t0 = blockIdx.x * SORT_B; t0 < count; t0 += gridDim.x * SORT_B) {
+        const unsigned int m = min((unsigned int)SORT_B, count - t0);
+        unsigned int bucket[SORT_R];
+#pragma unroll
+        for (int r = 0; r < SORT_R; ++r) {
+            const unsigned int slot = threadIdx.x + 128 * r;
+            bucket[r] = 0xffu;
+            if (slot < m) {
+                const unsigned int i = __ldg(perm + t0 + slot);
+                cplx z;
+                double v;
+                load_point(job, i, z, v);
+                s_idx[slot] = i;
+                s_z[slot] = make_double2(z.re, z.im);
+                s_v[slot] = v;
+                bucket[r] = bucket_of(wrsk_work(spb::cabs_(z), v), 0.1);
+            }
         }
-        if (p.combine == spb::CMB_I_ROT) {
-            int ierr, nz;
-            cplx val = spb::finish(job.fam, p, z, v, job.kode, ival, inz, cplx(0.0, 0.0), 0, ierr, nz, ph);
-            store_point(job, i, val, ierr, nz);
-        } else {
-            s.itemp[i] = make_double2(ival.re, ival.im);
-            s.icode[i] = (signed char)inz;
+        batch_sort(sm, bucket);
+#pragma unroll 1
+        for (int r = 0; r < SORT_R; ++r) {
+            const unsigned int pos = threadIdx.x + 128 * r;
+            if (pos < m) {
+                const unsigned int slot = sm.order[pos];
+                const double2 zz = s_z[slot];
+                ipass_point<REGION>(job, s, s_idx[slot], cplx(zz.x, zz.y), s_v[slot], pc);
+            }
         }
+        __syncthreads();
     }
 }
 
@@ -83,7 +133,11 @@ void launch_ipass(const DevJob &job, const Scratch &s, int region, int sms, cuda
             k_ipass<spb::IREG_MLRI><<<resident_grid(k_ipass<spb::IREG_MLRI>, 128, sms), 128, 0, st>>>(job, s);
             break;
         case spb::IREG_WRSK:
-            k_ipass<spb::IREG_WRSK><<<resident_grid(k_ipass<spb::IREG_WRSK>, 128, sms), 128, 0, st>>>(job, s);
+            if (job.v_stride != 0)
+                k_ipass_sorted<spb::IREG_WRSK>
+                    <<<resident_grid(k_ipass_sorted<spb::IREG_WRSK>, 128, sms), 128, 0, st>>>(job, s);
+            else
+                k_ipass<spb::IREG_WRSK><<<resident_grid(k_ipass<spb::IREG_WRSK>, 128, sms), 128, 0, st>>>(job, s);
             break;
         case spb::IREG_UNI1:
             k_ipass<spb::IREG_UNI1><<<resident_grid(k_ipass<spb::IREG_UNI1>, 128, sms), 128, 0, st>>>(job, s);

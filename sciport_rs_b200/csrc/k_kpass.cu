@@ -15,6 +15,39 @@ namespace spbk {
 #define SPB_KPASS_MINB 4
 #endif
 
+// one point of the K pass: K_v(w), combine with the parked I(w), store
+__device__ __forceinline__ void kpass_point(const DevJob &job, const Scratch &s, long long i, cplx z, double v,
+                                            double2 itv, int icv, bool has_i, PhaseCache &pc) {
+    // the classifier has already established regions and simplicity of this point: geometry only
+    spb::Prep p = spb::prepare_pass(job.fam, z, has_i);
+    cplx ival(0.0, 0.0);
+    int inz = 0;
+    if (p.ireg >= 0) {
+        inz = icv;
+        if (inz < 0) return;  // already queued on the general path by the I pass
+        ival = cplx(itv.x, itv.y);
+    }
+    cplx kval;
+    int knz = spb::kpass_region(p.w, v, job.kode, kval, p.az);
+    if (knz < 0 || (knz != 0 && (p.combine == spb::CMB_ACON || p.combine == spb::CMB_Y_SHARED))) {
+        unsigned int g = atomicAdd(&s.bins[GLIST_LEN_SLOT], 1u);
+        s.glist[g] = (unsigned int)i;
+        return;
+    }
+    const spb::OrderPhase *ph = pc.get(v);
+    int ierr, nz;
+    if (job.fam == spb::FAM_JY) {
+        cplx jv, yv;
+        int yerr, ynz;
+        spb::finish_jy(p, z, v, job.kode, ival, inz, kval, knz, jv, ierr, nz, yv, yerr, ynz, ph);
+        store_point(job, i, jv, ierr, nz);
+        store_point2(job, i, yv, yerr, ynz);
+        return;
+    }
+    cplx val = spb::finish(job.fam, p, z, v, job.kode, ival, inz, kval, knz, ierr, nz, ph);
+    store_point(job, i, val, ierr, nz);
+}
+
 __global__ void __launch_bounds__(128, SPB_KPASS_MINB) k_kpass(DevJob job, Scratch s) {
     const unsigned int count = s.bins[BIN_GENERAL] - s.bins[BIN_K0];
     const unsigned int stride = gridDim.x * blockDim.x;
@@ -54,40 +87,64 @@ __global__ void __launch_bounds__(128, SPB_KPASS_MINB) k_kpass(DevJob job, Scrat
             ic1 = s.icode[i1];
             cl1 = s.cls[i1];
         }
+        kpass_point(job, s, i, z, v, itv, icv, has_i, pc);
+    }
+}
 
-        // the classifier has already established regions and simplicity of this point: geometry only
-        spb::Prep p = spb::prepare_pass(job.fam, z, has_i);
-        cplx ival(0.0, 0.0);
-        int inz = 0;
-        if (p.ireg >= 0) {
-            inz = icv;
-            if (inz < 0) continue;  // already queued on the general path by the I pass
-            ival = cplx(itv.x, itv.y);
+// Per-element orders: batches of SORT_B points staged in shared memory and grouped by predicted work
+// (spb_dev.cuh) instead of the register pipeline above.
+__global__ void __launch_bounds__(128, SPB_KPASS_MINB) k_kpass_sorted(DevJob job, Scratch s) {
+    __shared__ SortSmem sm;
+    __shared__ unsigned int s_idx[SORT_B];
+    __shared__ double2 s_z[SORT_B], s_it[SORT_B];
+    __shared__ double s_v[SORT_B];
+    __shared__ signed char s_ic[SORT_B];
+    __shared__ unsigned char s_cl[SORT_B];
+    const unsigned int count = s.bins[BIN_GENERAL] - s.bins[BIN_K0];
+    const unsigned int *perm = s.perm_k;
+    PhaseCache pc;
+#pragma unroll 1
+    for (unsigned int t0 = blockIdx.x * SORT_B; t0 < count; t0 += gridDim.x * SORT_B) {
+        const unsigned int m = min((unsigned int)SORT_B, count - t0);
+        unsigned int bucket[SORT_R];
+#pragma unroll
+        for (int r = 0; r < SORT_R; ++r) {
+            const unsigned int slot = threadIdx.x + 128 * r;
+            bucket[r] = 0xffu;
+            if (slot < m) {
+                const unsigned int i = __ldg(perm + t0 + slot);
+                cplx z;
+                double v;
+                load_point(job, i, z, v);
+                s_idx[slot] = i;
+                s_z[slot] = make_double2(z.re, z.im);
+                s_v[slot] = v;
+                s_it[slot] = s.itemp[i];
+                s_ic[slot] = s.icode[i];
+                s_cl[slot] = s.cls[i];
+                bucket[r] = bucket_of(kpass_work(spb::cabs_(z), v), 0.25);
+            }
         }
-        cplx kval;
-        int knz = spb::kpass_region(p.w, v, job.kode, kval, p.az);
-        if (knz < 0 || (knz != 0 && (p.combine == spb::CMB_ACON || p.combine == spb::CMB_Y_SHARED))) {
-            unsigned int g = atomicAdd(&s.bins[GLIST_LEN_SLOT], 1u);
-            s.glist[g] = (unsigned int)i;
-            continue;
+        batch_sort(sm, bucket);
+#pragma unroll 1
+        for (int r = 0; r < SORT_R; ++r) {
+            const unsigned int pos = threadIdx.x + 128 * r;
+            if (pos < m) {
+                const unsigned int slot = sm.order[pos];
+                const double2 zz = s_z[slot];
+                kpass_point(job, s, s_idx[slot], cplx(zz.x, zz.y), s_v[slot], s_it[slot], s_ic[slot],
+                            (s_cl[slot] & 7u) != 7u, pc);
+            }
         }
-        const spb::OrderPhase *ph = pc.get(v);
-        int ierr, nz;
-        if (job.fam == spb::FAM_JY) {
-            cplx jv, yv;
-            int yerr, ynz;
-            spb::finish_jy(p, z, v, job.kode, ival, inz, kval, knz, jv, ierr, nz, yv, yerr, ynz, ph);
-            store_point(job, i, jv, ierr, nz);
-            store_point2(job, i, yv, yerr, ynz);
-            continue;
-        }
-        cplx val = spb::finish(job.fam, p, z, v, job.kode, ival, inz, kval, knz, ierr, nz, ph);
-        store_point(job, i, val, ierr, nz);
+        __syncthreads();  // the next batch overwrites the staging arrays
     }
 }
 
 void launch_kpass(const DevJob &job, const Scratch &s, int sms, cudaStream_t st) {
-    k_kpass<<<resident_grid(k_kpass, 128, sms), 128, 0, st>>>(job, s);
+    if (job.v_stride != 0)
+        k_kpass_sorted<<<resident_grid(k_kpass_sorted, 128, sms), 128, 0, st>>>(job, s);
+    else
+        k_kpass<<<resident_grid(k_kpass, 128, sms), 128, 0, st>>>(job, s);
 }
 
 }  // namespace spbk

@@ -54,6 +54,67 @@ struct PhaseCache {
     }
 };
 
+// ---- block-level grouping by predicted work ----------------------------------------------------------------
+// With per-element orders the trip counts of the region routines (forward recurrence over the order, Miller
+// start index, ratio walk) differ from lane to lane even inside one region bin (measured: 14 of 32 lanes active
+// in the K pass of config 3).  The passes then work in batches of SORT_B points per CTA: the batch is staged
+// in shared memory, a counting sort by a cheap work estimate (32 buckets) orders it, and thread t takes the
+// sorted positions t, t + 128, ... so that the lanes of a warp run points of similar length in every round.
+constexpr int SORT_R = 4;              // points per thread per batch
+constexpr int SORT_B = 128 * SORT_R;   // points per batch
+constexpr int SORT_BUCKETS = 32;
+
+struct SortSmem {
+    unsigned int cnt[SORT_BUCKETS];
+    unsigned short order[SORT_B];
+};
+
+// bucket[r] is the bucket of slot threadIdx.x + 128 r, or 0xff for an empty slot.  On return sm.order[0..m) holds
+// the slots grouped by ascending bucket (m = number of non-empty slots).
+__device__ __forceinline__ void batch_sort(SortSmem &sm, const unsigned int (&bucket)[SORT_R]) {
+    if (threadIdx.x < SORT_BUCKETS) sm.cnt[threadIdx.x] = 0;
+    __syncthreads();
+    unsigned int rank[SORT_R];
+#pragma unroll
+    for (int r = 0; r < SORT_R; ++r)
+        if (bucket[r] != 0xffu) rank[r] = atomicAdd(&sm.cnt[bucket[r]], 1u);
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const unsigned int c = sm.cnt[threadIdx.x];
+        unsigned int incl = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            unsigned int y = __shfl_up_sync(0xffffffffu, incl, d);
+            if ((int)threadIdx.x >= d) incl += y;
+        }
+        sm.cnt[threadIdx.x] = incl - c;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < SORT_R; ++r)
+        if (bucket[r] != 0xffu) sm.order[sm.cnt[bucket[r]] + rank[r]] = (unsigned short)(threadIdx.x + 128 * r);
+    __syncthreads();
+}
+
+// Work estimates (arbitrary units, only their order matters) -> bucket 0..31
+__device__ __forceinline__ unsigned int bucket_of(double est, double scale) {
+    double b = est * scale;
+    return b >= 31.0 ? 31u : (unsigned int)b;
+}
+
+// K_v(w): Miller start index ~ 9 + 175/|w| for 2 < |w| < 28.7 (about 12 beyond), each step two divisions;
+// then int(v + 1/2) forward-recurrence steps
+__device__ __forceinline__ double kpass_work(double az, double v) {
+    double k = az <= 2.0 ? 20.0 : (az < 28.7 ? 9.0 + 175.0 / az : 12.0);
+    return 3.0 * k + v;
+}
+
+// I_v(w) by ratios + Wronskian: walk of ~40 steps plus max(0, |w| - v) backward steps, plus K_v, K_v+1
+__device__ __forceinline__ double wrsk_work(double az, double v) {
+    double d = az - v;
+    return 40.0 + (d > 0.0 ? d : 0.0) + 0.25 * kpass_work(az, v);
+}
+
 // general per-point evaluation + optional oracle-compatible post-processing
 __device__ __forceinline__ void eval_general_store(const DevJob &j, long long i, cplx z, double v) {
     int ierr, nz;
