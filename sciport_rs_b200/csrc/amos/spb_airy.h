@@ -28,18 +28,21 @@ SPB_FN int acai(cplx z, real fnu, int kode, int mr, int n, Y y, real rl, real to
     int nn = n;
     real dfnu = fnu + real(n - 1);
     int nw;
+    // failures are carried to the end of the routine (no return between the data-dependent loops of the I and K
+    // routines: their exits must reconverge before the next routine starts)
+    int fail = 0;
     if (az <= real(2.0) || !(az * az * real(0.25) > dfnu + real(1.0))) {
-        nw = seri(zn, fnu, kode, nn, y, tol, elim, alim);
+        nw = seri(zn, fnu, kode, nn, y, tol, elim, alim, az);
     } else if (!(az < rl)) {
-        nw = asyi(zn, fnu, kode, nn, y, rl, tol, elim, alim);
-        if (nw < 0) return (nw == -2) ? -2 : -1;
+        nw = asyi(zn, fnu, kode, nn, y, rl, tol, elim, alim, az);
+        if (nw < 0) fail = (nw == -2) ? -2 : -1;
     } else {
-        nw = mlri(zn, fnu, kode, nn, y, tol);
-        if (nw < 0) return (nw == -2) ? -2 : -1;
+        nw = mlri(zn, fnu, kode, nn, y, tol, az);
+        if (nw < 0) fail = (nw == -2) ? -2 : -1;
     }
     cplx cy[2];
-    nw = bknu(zn, fnu, kode, 1, cy, tol, elim, alim);
-    if (nw != 0) return (nw == -2) ? -2 : -1;
+    nw = bknu(zn, fnu, kode, 1, cy, tol, elim, alim, az);
+    if (nw != 0 && fail == 0) fail = (nw == -2) ? -2 : -1;
     real fmr = real(mr);
     real sgn = (fmr < real(0.0)) ? real(SPB_PI) : real(-SPB_PI);
     cplx csgn(0.0, sgn);
@@ -60,6 +63,10 @@ SPB_FN int acai(cplx z, real fnu, int kode, int mr, int n, Y y, real rl, real to
         nz += nw;
     }
     y[0] = cspn * c1 + csgn * c2;
+    if (fail != 0) {
+        y[0] = cplx(0.0, 0.0);
+        return fail;
+    }
     return nz;
 }
 
@@ -296,10 +303,8 @@ SPB_FN cplx biry(cplx z, int id, int kode, int &ierr) {
     // fmr*fnu is the phase of the analytic continuation of I(fnu, zta)
     cplx cy[2];
     int nz = binu(zta, fnu, kode, 1, cy, rl, fnul, tol, elim, alim);
-    if (nz < 0) {
-        ierr = (nz == -1) ? 2 : 5;
-        return cplx(0.0, 0.0);
-    }
+    // a failure of the first I evaluation is reported after the second one (reconvergence, see acai)
+    const int nz_first = nz;
     aa = fmr * fnu;
     cplx s1 = (cy[0] * cplx(cos(aa), sin(aa))) * sfac;
     fnu = (real(2.0) - fid) / real(3.0);
@@ -310,6 +315,10 @@ SPB_FN cplx biry(cplx z, int id, int kode, int &ierr) {
     cplx s2 = cdiv(cy[0], zta) * (fnu + fnu) + cy[1];
     aa = fmr * (fnu - real(1.0));
     s1 = (s1 + s2 * cplx(cos(aa), sin(aa))) * coef;
+    if (nz_first < 0) {
+        ierr = (nz_first == -1) ? 2 : 5;
+        return cplx(0.0, 0.0);
+    }
     if (id != 1) {
         bi = csq * s1;
         return bi * (real(1.0) / sfac);
