@@ -279,13 +279,66 @@ def sinc(x):
 
 
 # ---------------------------------------------------------------- widened batched surface
+def _checked(fn, v, z, scaled, **kw):
+    vals, _, _ = bessel(fn, v, z, scaled=scaled, want_codes=False, **kw)
+    idx, code = last_first_error(0)
+    if idx >= 0:
+        raise SpecialError(code, idx)
+    return vals
+
+
+def _reflect(fn, v, z, scaled, **kw):
+    """Negative orders (host arrays) by the reflection formulae, composed from the kernels' results at |v|:
+         J_-v = cos(pi v) J_v - sin(pi v) Y_v        Y_-v = sin(pi v) J_v + cos(pi v) Y_v
+         I_-v = I_v + (2/pi) sin(pi v) K_v           K_-v = K_v
+         H1_-v = e^{i pi v} H1_v                     H2_-v = e^{-i pi v} H2_v
+    with the integer-order cases reduced to sign changes (J_-n = (-1)^n J_n, I_-n = I_n).  The scaled variants carry
+    the scale factor of the target function (for I: K is rescaled from e^z to e^{-|Re z|})."""
+    za = np.asarray(z, dtype=np.complex128)
+    va = np.broadcast_to(np.asarray(v, dtype=np.float64), za.shape)
+    neg = va < 0
+    av = np.abs(va)
+    out = np.empty(za.shape, np.complex128)
+    if (~neg).any():
+        out[~neg] = _checked(fn, av[~neg], za[~neg], scaled, **kw)
+    if not neg.any():
+        return out
+    zn, vn = za[neg], av[neg]
+    s, c = np.sin(np.pi * vn), np.cos(np.pi * vn)
+    whole = vn == np.floor(vn)
+    s = np.where(whole, 0.0, s)
+    c = np.where(whole, np.where(vn % 2 == 0, 1.0, -1.0), c)
+    if fn == "K":
+        out[neg] = _checked("K", vn, zn, scaled, **kw)
+    elif fn in ("H1", "H2"):
+        ph = c + 1j * s if fn == "H1" else c - 1j * s
+        out[neg] = ph * _checked(fn, vn, zn, scaled, **kw)
+    elif fn in ("J", "Y"):
+        (j, _, _), (y, _, _) = bessel_jy(vn, zn, scaled=scaled, want_codes=False)
+        for which in (0, 1):
+            idx, code = last_first_error(which)
+            # a failing Y only matters where it enters the formula (non-integer order, or Y itself is wanted)
+            if idx >= 0 and (which == 0 or fn == "Y" or not whole[idx]):
+                raise SpecialError(code, int(np.flatnonzero(neg)[idx]))
+        y = np.where(whole & (fn == "J"), 0.0, y)
+        out[neg] = c * j - s * y if fn == "J" else s * j + c * y
+    else:  # I
+        i = _checked("I", vn, zn, scaled, **kw)
+        k = np.zeros_like(i)
+        frac = ~whole
+        if frac.any():
+            k[frac] = _checked("K", vn[frac], zn[frac], scaled, **kw)
+            if scaled:  # e^{z} K -> e^{-|Re z|} K
+                k[frac] *= np.exp(-zn[frac] - np.abs(zn[frac].real))
+        out[neg] = i + (2.0 / np.pi) * s * k
+    return out
+
+
 def _family(fn, scaled):
     def f(v, z, **kw):
-        vals, _, _ = bessel(fn, v, z, scaled=scaled, want_codes=False, **kw)
-        idx, code = last_first_error(0)
-        if idx >= 0:
-            raise SpecialError(code, idx)
-        return vals
+        if not _is_torch(z) and not _is_torch(v) and np.any(np.asarray(v) < 0):
+            return _reflect(fn, v, z, scaled, **kw)
+        return _checked(fn, v, z, scaled, **kw)
 
     return f
 

@@ -368,3 +368,29 @@ def test_multi_device_slices_match_single_device(special):
     sw1, _, _ = special.bessel("J", 0.0, z[:200_001], n_orders=32, want_codes=False)
     swg, _, _ = special.bessel("J", 0.0, z[:200_001], n_orders=32, want_codes=False, devices=list(range(g)))
     assert np.array_equal(sw1.view(np.uint64), swg.view(np.uint64))
+
+
+def test_negative_orders_by_reflection(special):
+    """Orders < 0 (host arrays): reflection formulae composed from the kernels' results, checked against scipy."""
+    import scipy.special as sc
+    rng = np.random.default_rng(9)
+    n = 4000
+    v = np.where(rng.random(n) < 0.3, -rng.integers(0, 12, n).astype(float), -12 * rng.random(n))
+    v[::7] = np.abs(v[::7])  # mixed signs in one call
+    z = 30 * rng.random(n) * np.exp(1j * np.pi * (2 * rng.random(n) - 1)) + 0.05
+    pairs = {"jv": (special.jv, sc.jv, sc.yv), "yv": (special.yv, sc.yv, sc.jv), "iv": (special.iv, sc.iv, sc.kv),
+             "kv": (special.kv_array, sc.kv, None), "h1": (special.hankel1, sc.hankel1, None),
+             "h2": (special.hankel2, sc.hankel2, None), "ive": (special.ive, sc.ive, sc.kve),
+             "jve": (special.jve, sc.jve, sc.yve)}
+    for name, (ours, ref, comp) in pairs.items():
+        got = ours(v, z)
+        want = ref(v, z)
+        scale = np.abs(want)
+        if comp is not None:
+            with np.errstate(all="ignore"):
+                cw = np.abs(comp(np.abs(v), z)) * (np.exp(-z.real - np.abs(z.real)) if name == "ive" else 1.0)
+            scale = np.maximum(scale, np.where(np.isfinite(cw), cw, 0))
+            scale = np.maximum(scale, np.abs(ref(np.abs(v), z)))
+        ok = np.isfinite(want.real) & (scale > 1e-280) & (scale < 1e280)
+        err = np.abs(got - want)[ok] / scale[ok]
+        assert err.max() <= 2e-13, (name, err.max())
