@@ -87,7 +87,7 @@ def bessel(fn, v, z, scaled=False, semantics="amos", path="binned", real_input=F
     if _is_torch(z):
         if not z.is_cuda:
             raise ValueError("torch inputs must be CUDA tensors (use numpy arrays for host buffers)")
-        zc = z.contiguous()
+        zc = z.resolve_conj().contiguous()  # a lazy conjugate view shares storage with the unconjugated tensor
         want = torch.float64 if real_input else torch.complex128
         if zc.dtype != want:
             zc = zc.to(want)
@@ -153,7 +153,7 @@ def bessel_jy(v, z, scaled=False, semantics="amos", profile=False, outs=None, co
     kode = 2 if scaled else 1
     flags = (SEM_SCIPY if semantics == "scipy" else SEM_AMOS) | (PROFILE if profile else 0)
     if _is_torch(z):
-        zc = z.contiguous().to(torch.complex128)
+        zc = z.resolve_conj().contiguous().to(torch.complex128)
         n = zc.numel()
         if _is_torch(v):
             vt = v.to(device=zc.device, dtype=torch.float64).contiguous()
@@ -365,7 +365,7 @@ def airy_raw(which, z, scaled=False, semantics="amos"):
     kode = 2 if scaled else 1
     flags = SEM_SCIPY if semantics == "scipy" else SEM_AMOS
     if _is_torch(z):
-        zc = z.contiguous().to(torch.complex128)
+        zc = z.resolve_conj().contiguous().to(torch.complex128)
         out = torch.empty_like(zc)
         ierr = torch.empty(zc.shape, dtype=torch.int32, device=zc.device)
         nz = torch.empty(zc.shape, dtype=torch.int32, device=zc.device)
@@ -414,7 +414,7 @@ def _real_map(fn, x):
 
 def _cplx_map(fn, z):
     if _is_torch(z):
-        zc = z.contiguous().to(torch.complex128)
+        zc = z.resolve_conj().contiguous().to(torch.complex128)
         out = torch.empty_like(zc)
         with torch.cuda.device(zc.device):
             ex = make_exec(device_ptrs=True, stream=_stream_for(zc), devices=[zc.device.index])

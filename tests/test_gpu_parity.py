@@ -394,3 +394,64 @@ def test_negative_orders_by_reflection(special):
         ok = np.isfinite(want.real) & (scale > 1e-280) & (scale < 1e280)
         err = np.abs(got - want)[ok] / scale[ok]
         assert err.max() <= 2e-13, (name, err.max())
+
+
+def test_full_size_cfg3_properties(special):
+    """BASELINE config 3 at its full size (2^28 = 268 435 456 points, per-element order in [0, 50], |z| <= 200, scaled
+    I and K; 17 chunks of 2^24): size-independent properties.
+    (a) no element fails; (b) f(conj z) = conj f(z) on a slab; (c) a strided sample agrees with the CPU oracle;
+    (d) the Wronskian I_v K_{v+1} + I_{v+1} K_v = 1/z on a slab (ties the I and K kernels together)."""
+    n = 1 << 28
+    v, z = special.synth(3, n, n_total=n, device="cuda:0")
+    idx = torch.arange(0, n, 262147, device="cuda:0")
+    zs, vs = to_np(z[idx]), to_np(v[idx])
+    for fn in ("I", "K"):
+        out, _, _ = special.bessel(fn, v, z, scaled=True, want_codes=False)
+        assert special.last_first_error() == (-1, 0)
+        want, _, _ = helpers.cpu_bessel(fn, 2, vs, zs)
+        comp = np.abs(helpers.cpu_bessel("K" if fn == "I" else "I", 2, vs, zs)[0])
+        comp = comp * (np.exp(-2 * np.abs(zs.real)) / np.pi if fn == "I" else np.pi * np.exp(2 * np.abs(zs.real)))
+        where = (np.abs(zs.real) <= 1) if fn == "I" else (zs.real < 0)
+        scale = np.maximum(np.abs(want), np.where(np.isfinite(comp) & where, comp, 0))
+        err = so.mismatch(to_np(out[idx]), want, scale)
+        assert np.all(err <= so.tolerance(want, zs, vs)), err.max()
+        slab = slice(5 << 24, (5 << 24) + (1 << 22))
+        mirrored, _, _ = special.bessel(fn, v[slab], z[slab].conj(), scaled=True, want_codes=False)
+        rel = (mirrored.conj() - out[slab]).abs() / out[slab].abs()
+        assert float(rel.max()) <= 1e-13, float(rel.max())
+        del out, mirrored
+    slab = slice(9 << 24, (9 << 24) + (1 << 22))
+    zz, vv = z[slab], v[slab]
+    zz = torch.where(zz.real < 0, -zz, zz)  # right half plane: plain Wronskian
+    i0_, _, _ = special.bessel("I", vv, zz, scaled=True, want_codes=False)
+    i1_, _, _ = special.bessel("I", vv + 1, zz, scaled=True, want_codes=False)
+    k0_, _, _ = special.bessel("K", vv, zz, scaled=True, want_codes=False)
+    k1_, _, _ = special.bessel("K", vv + 1, zz, scaled=True, want_codes=False)
+    # scaled: I e^{-Re z}, K e^{z}  ->  product carries e^{i Im z}
+    w = (i0_ * k1_ + i1_ * k0_) * zz * torch.exp(-1j * zz.imag)
+    terms = (i0_ * k1_).abs() + (i1_ * k0_).abs()
+    resid = (w - 1).abs() / (terms * zz.abs()).clamp_min(1.0)
+    assert float(resid.max()) <= 2e-13, float(resid.max())
+
+
+def test_full_size_cfg5_per_gpu_share(special):
+    """BASELINE config 5, the share of one of 8 GPUs: 2^21 points x 256 orders = 8 GiB of results.  Every interior
+    member satisfies the three-term recurrence and the top/bottom rows agree with single-order calls."""
+    n = 1 << 21
+    v, z = special.synth(5, n, n_total=1 << 24, offset=3 << 21, device="cuda:0")
+    out, _, _ = special.bessel("J", 0.0, z, n_orders=256, want_codes=False)
+    assert special.last_first_error() == (-1, 0)
+    single0, _, _ = special.bessel("J", 0.0, z, want_codes=False)
+    y0, _, _ = special.bessel("Y", 0.0, z, want_codes=False)
+    scale0 = torch.maximum(single0.abs(), y0.abs())
+    assert float(((out[0] - single0).abs() / scale0).max()) <= 4.5e-13
+    worst = 0.0
+    for k0 in range(1, 255, 16):
+        k1 = min(k0 + 16, 255)
+        k = torch.arange(k0, k1, device="cuda:0", dtype=torch.float64)[:, None]
+        mid = (2.0 * k / z[None, :]) * out[k0:k1]
+        res = out[k0 - 1:k1 - 1] + out[k0 + 1:k1 + 1] - mid
+        scale = out[k0 - 1:k1 - 1].abs() + out[k0 + 1:k1 + 1].abs() + mid.abs()
+        ok = scale > 1e-280
+        worst = max(worst, float((res.abs() / scale.clamp_min(1e-300))[ok].max()))
+    assert worst <= 1e-14, worst

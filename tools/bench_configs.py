@@ -65,6 +65,13 @@ def main():
         for name, f in (("gamma", special.gamma), ("gammaln", special.gammaln), ("sinc", special.sinc)):
             ms = timed(torch, lambda: f(x), args.reps)
             emit(1, name, n, ms, extra={"gbs": 16.0 * n / (ms * 1e-3) / 1e9})
+        # the same memory-bound maps at a size that is not launch-bound (2^27 points, 2 GiB of traffic)
+        nbig = 1 << 27
+        xb = x.repeat(nbig // n)
+        for name, f in (("gamma 2^27", special.gamma), ("gammaln 2^27", special.gammaln), ("sinc 2^27", special.sinc)):
+            ms = timed(torch, lambda: f(xb), args.reps)
+            emit(1, name, nbig, ms, extra={"gbs": 16.0 * nbig / (ms * 1e-3) / 1e9})
+        del xb
         for fn in ("J", "Y"):
             for order in (0.0, 1.0):
                 bessel_case(1, f"{fn}{int(order)} (real promoted)", fn, order, x, False, real_input=True)
