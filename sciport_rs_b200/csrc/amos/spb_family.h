@@ -190,16 +190,16 @@ SPB_FN Prep prepare(int fam, cplx z, real fnu, int kode) {
 
 // prepare() for a point the classifier has already binned: the region tests are known to have passed, so only
 // the geometry and the modulus are recomputed.  has_i = the class byte carries an I bin.
-SPB_FN Prep prepare_pass(int fam, cplx z, bool has_i) {
+SPB_FN Prep prepare_pass(int fam, cplx z) {
     Prep p;
     p.w = z;
     p.combine = CMB_GENERAL;
-    p.ireg = has_i ? 0 : -1;  // passes only ask whether I(w) exists
     p.kreg = -1;
     p.ierr = 0;
     p.mr = 0;
     p.az = cabs_(z);
-    prepare_geometry(fam, z, p);
+    // a binned point carries an I bin exactly when its geometry needs I(w) (prepare() sets ireg under `left`)
+    p.ireg = prepare_geometry(fam, z, p) ? 0 : -1;  // the passes only ask whether I(w) exists
     return p;
 }
 
@@ -483,7 +483,8 @@ SPB_FN cplx pipeline_eval(int fam, cplx z, real fnu, int kode, int &ierr, int &n
     {
         // the region passes see only the class (bins) and recompute the geometry: same thing here
         const int ireg = p.ireg, kreg = p.kreg;
-        p = prepare_pass(fam, z, ireg >= 0);
+        p = prepare_pass(fam, z);
+        if ((p.ireg >= 0) != (ireg >= 0)) p.combine = CMB_GENERAL;  // cannot happen; would show up as a path-1 mismatch
         p.ireg = ireg;
         p.kreg = kreg;
     }
@@ -514,7 +515,7 @@ SPB_FN void pipeline_eval_jy(cplx z, real fnu, int kode, cplx &jv, int &jerr, in
     bool general = (p.combine == CMB_GENERAL);
     if (!general) {
         const int ireg = p.ireg, kreg = p.kreg;
-        p = prepare_pass(FAM_JY, z, ireg >= 0);
+        p = prepare_pass(FAM_JY, z);
         p.ireg = ireg;
         p.kreg = kreg;
     }

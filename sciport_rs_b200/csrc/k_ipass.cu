@@ -16,17 +16,16 @@ namespace spbk {
 // minimum resident CTAs per SM the register allocation must allow (occupancy hides the FP64 dependency
 // latency of the region routines; measured on B200)
 #ifndef SPB_IPASS_MINB_ASYI
-#define SPB_IPASS_MINB_ASYI 7
+#define SPB_IPASS_MINB_ASYI 8
 #endif
 #define SPB_IPASS_MINB(R) ((R) == 1 ? SPB_IPASS_MINB_ASYI : 1)
 
 // one point of the I pass: I_v(w) by the region routine; J / I families finish here, the others park I(w)
 template <int REGION>
 __device__ __forceinline__ void ipass_point(const DevJob &job, const Scratch &s, long long i, cplx z, double v,
-                                            PhaseCache &pc) {
+                                            const spb::OrderPhase *ph) {
     // the classifier has already established region and simplicity of this point: geometry only
-    spb::Prep p = spb::prepare_pass(job.fam, z, true);
-    const spb::OrderPhase *ph = pc.get(v);
+    spb::Prep p = spb::prepare_pass(job.fam, z);
     cplx ival;
     int inz = spb::ipass_region(REGION, p.w, v, job.kode, ival, p.az, ph);
     if (inz < 0) {
@@ -46,8 +45,15 @@ __device__ __forceinline__ void ipass_point(const DevJob &job, const Scratch &s,
     }
 }
 
-template <int REGION>
+// SCALAR = the order is one broadcast value (v_stride = 0): its phase factors are computed once per CTA into shared
+// memory; otherwise they are computed per point
+template <int REGION, bool SCALAR>
 __global__ void __launch_bounds__(128, SPB_IPASS_MINB(REGION)) k_ipass(DevJob job, Scratch s) {
+    __shared__ spb::OrderPhase s_ph;
+    if (SCALAR) {
+        if (threadIdx.x == 0) s_ph = spb::order_phase(__ldg(job.v));
+        __syncthreads();
+    }
     const unsigned int start = s.bins[REGION] - s.bins[0];
     const unsigned int count = s.bins[REGION + 1] - s.bins[REGION];
     const unsigned int stride = gridDim.x * blockDim.x;
@@ -59,7 +65,6 @@ __global__ void __launch_bounds__(128, SPB_IPASS_MINB(REGION)) k_ipass(DevJob jo
     cplx z1(0.0, 0.0);
     double v1 = 0.0;
     if (have1) load_point(job, i1, z1, v1);
-    PhaseCache pc;
 #pragma unroll 1
     while (have1) {
         const long long i = i1;
@@ -72,7 +77,12 @@ __global__ void __launch_bounds__(128, SPB_IPASS_MINB(REGION)) k_ipass(DevJob jo
         have2 = (t + stride) < count;
         if (have2) i2 = __ldg(perm + t + stride);
         if (have1) load_point(job, i1, z1, v1);
-        ipass_point<REGION>(job, s, i, z, v, pc);
+        if (SCALAR) {
+            ipass_point<REGION>(job, s, i, z, v, &s_ph);
+        } else {
+            const spb::OrderPhase ph = spb::order_phase(v);
+            ipass_point<REGION>(job, s, i, z, v, &ph);
+        }
     }
 }
 
@@ -86,7 +96,6 @@ __global__ void __launch_bounds__(128) k_ipass_sorted(DevJob job, Scratch s) {
     const unsigned int start = s.bins[REGION] - s.bins[0];
     const unsigned int count = s.bins[REGION + 1] - s.bins[REGION];
     const unsigned int *perm = s.perm_i + start;
-    PhaseCache pc;
 #pragma unroll 1
     for (unsigned int t0 = blockIdx.x * SORT_B; t0 < count; t0 += gridDim.x * SORT_B) {
         const unsigned int m = min((unsigned int)SORT_B, count - t0);
@@ -113,38 +122,38 @@ __global__ void __launch_bounds__(128) k_ipass_sorted(DevJob job, Scratch s) {
             if (pos < m) {
                 const unsigned int slot = sm.order[pos];
                 const double2 zz = s_z[slot];
-                ipass_point<REGION>(job, s, s_idx[slot], cplx(zz.x, zz.y), s_v[slot], pc);
+                const double vv = s_v[slot];
+                const spb::OrderPhase ph = spb::order_phase(vv);
+                ipass_point<REGION>(job, s, s_idx[slot], cplx(zz.x, zz.y), vv, &ph);
             }
         }
         __syncthreads();
     }
 }
 
+template <int REGION>
+static void launch_ipass_region(const DevJob &job, const Scratch &s, int sms, cudaStream_t st) {
+    if (job.v_stride == 0)
+        k_ipass<REGION, true><<<resident_grid(k_ipass<REGION, true>, 128, sms), 128, 0, st>>>(job, s);
+    else
+        k_ipass<REGION, false><<<resident_grid(k_ipass<REGION, false>, 128, sms), 128, 0, st>>>(job, s);
+}
+
 void launch_ipass(const DevJob &job, const Scratch &s, int region, int sms, cudaStream_t st) {
     // persistent grid: SM count x resident CTAs per SM, 128-thread CTAs
     switch (region) {
-        case spb::IREG_SERIES:
-            k_ipass<spb::IREG_SERIES><<<resident_grid(k_ipass<spb::IREG_SERIES>, 128, sms), 128, 0, st>>>(job, s);
-            break;
-        case spb::IREG_ASYI:
-            k_ipass<spb::IREG_ASYI><<<resident_grid(k_ipass<spb::IREG_ASYI>, 128, sms), 128, 0, st>>>(job, s);
-            break;
-        case spb::IREG_MLRI:
-            k_ipass<spb::IREG_MLRI><<<resident_grid(k_ipass<spb::IREG_MLRI>, 128, sms), 128, 0, st>>>(job, s);
-            break;
+        case spb::IREG_SERIES: launch_ipass_region<spb::IREG_SERIES>(job, s, sms, st); break;
+        case spb::IREG_ASYI: launch_ipass_region<spb::IREG_ASYI>(job, s, sms, st); break;
+        case spb::IREG_MLRI: launch_ipass_region<spb::IREG_MLRI>(job, s, sms, st); break;
         case spb::IREG_WRSK:
             if (job.v_stride != 0)
                 k_ipass_sorted<spb::IREG_WRSK>
                     <<<resident_grid(k_ipass_sorted<spb::IREG_WRSK>, 128, sms), 128, 0, st>>>(job, s);
             else
-                k_ipass<spb::IREG_WRSK><<<resident_grid(k_ipass<spb::IREG_WRSK>, 128, sms), 128, 0, st>>>(job, s);
+                launch_ipass_region<spb::IREG_WRSK>(job, s, sms, st);
             break;
-        case spb::IREG_UNI1:
-            k_ipass<spb::IREG_UNI1><<<resident_grid(k_ipass<spb::IREG_UNI1>, 128, sms), 128, 0, st>>>(job, s);
-            break;
-        case spb::IREG_UNI2:
-            k_ipass<spb::IREG_UNI2><<<resident_grid(k_ipass<spb::IREG_UNI2>, 128, sms), 128, 0, st>>>(job, s);
-            break;
+        case spb::IREG_UNI1: launch_ipass_region<spb::IREG_UNI1>(job, s, sms, st); break;
+        case spb::IREG_UNI2: launch_ipass_region<spb::IREG_UNI2>(job, s, sms, st); break;
         default: break;
     }
 }

@@ -17,9 +17,9 @@ namespace spbk {
 
 // one point of the K pass: K_v(w), combine with the parked I(w), store
 __device__ __forceinline__ void kpass_point(const DevJob &job, const Scratch &s, long long i, cplx z, double v,
-                                            double2 itv, int icv, bool has_i, PhaseCache &pc) {
+                                            double2 itv, int icv, const spb::OrderPhase *ph) {
     // the classifier has already established regions and simplicity of this point: geometry only
-    spb::Prep p = spb::prepare_pass(job.fam, z, has_i);
+    spb::Prep p = spb::prepare_pass(job.fam, z);
     cplx ival(0.0, 0.0);
     int inz = 0;
     if (p.ireg >= 0) {
@@ -34,7 +34,6 @@ __device__ __forceinline__ void kpass_point(const DevJob &job, const Scratch &s,
         s.glist[g] = (unsigned int)i;
         return;
     }
-    const spb::OrderPhase *ph = pc.get(v);
     int ierr, nz;
     if (job.fam == spb::FAM_JY) {
         cplx jv, yv;
@@ -48,7 +47,12 @@ __device__ __forceinline__ void kpass_point(const DevJob &job, const Scratch &s,
     store_point(job, i, val, ierr, nz);
 }
 
+// broadcast scalar order (v_stride = 0): the order-dependent phase factors are computed once per CTA and live in
+// shared memory, not in registers of the persistent loop
 __global__ void __launch_bounds__(128, SPB_KPASS_MINB) k_kpass(DevJob job, Scratch s) {
+    __shared__ spb::OrderPhase s_ph;
+    if (threadIdx.x == 0) s_ph = spb::order_phase(__ldg(job.v));
+    __syncthreads();
     const unsigned int count = s.bins[BIN_GENERAL] - s.bins[BIN_K0];
     const unsigned int stride = gridDim.x * blockDim.x;
     const unsigned int *perm = s.perm_k;
@@ -60,14 +64,11 @@ __global__ void __launch_bounds__(128, SPB_KPASS_MINB) k_kpass(DevJob job, Scrat
     double v1 = 0.0;
     double2 it1 = make_double2(0.0, 0.0);
     int ic1 = 0;
-    unsigned int cl1 = 0;
     if (have1) {
         load_point(job, i1, z1, v1);
         it1 = s.itemp[i1];
         ic1 = s.icode[i1];
-        cl1 = s.cls[i1];
     }
-    PhaseCache pc;
 #pragma unroll 1
     while (have1) {
         const long long i = i1;
@@ -75,7 +76,6 @@ __global__ void __launch_bounds__(128, SPB_KPASS_MINB) k_kpass(DevJob job, Scrat
         const double v = v1;
         const double2 itv = it1;
         const int icv = ic1;
-        const bool has_i = (cl1 & 7u) != 7u;  // the class byte carries an I bin: I(w) was parked by the I pass
         t += stride;
         have1 = have2;
         i1 = i2;
@@ -85,9 +85,8 @@ __global__ void __launch_bounds__(128, SPB_KPASS_MINB) k_kpass(DevJob job, Scrat
             load_point(job, i1, z1, v1);
             it1 = s.itemp[i1];  // only meaningful where the point went through the I pass
             ic1 = s.icode[i1];
-            cl1 = s.cls[i1];
         }
-        kpass_point(job, s, i, z, v, itv, icv, has_i, pc);
+        kpass_point(job, s, i, z, v, itv, icv, &s_ph);
     }
 }
 
@@ -99,10 +98,8 @@ __global__ void __launch_bounds__(128, SPB_KPASS_MINB) k_kpass_sorted(DevJob job
     __shared__ double2 s_z[SORT_B], s_it[SORT_B];
     __shared__ double s_v[SORT_B];
     __shared__ signed char s_ic[SORT_B];
-    __shared__ unsigned char s_cl[SORT_B];
     const unsigned int count = s.bins[BIN_GENERAL] - s.bins[BIN_K0];
     const unsigned int *perm = s.perm_k;
-    PhaseCache pc;
 #pragma unroll 1
     for (unsigned int t0 = blockIdx.x * SORT_B; t0 < count; t0 += gridDim.x * SORT_B) {
         const unsigned int m = min((unsigned int)SORT_B, count - t0);
@@ -121,7 +118,6 @@ __global__ void __launch_bounds__(128, SPB_KPASS_MINB) k_kpass_sorted(DevJob job
                 s_v[slot] = v;
                 s_it[slot] = s.itemp[i];
                 s_ic[slot] = s.icode[i];
-                s_cl[slot] = s.cls[i];
                 bucket[r] = bucket_of(kpass_work(spb::cabs_(z), v), 0.25);
             }
         }
@@ -132,8 +128,9 @@ __global__ void __launch_bounds__(128, SPB_KPASS_MINB) k_kpass_sorted(DevJob job
             if (pos < m) {
                 const unsigned int slot = sm.order[pos];
                 const double2 zz = s_z[slot];
-                kpass_point(job, s, s_idx[slot], cplx(zz.x, zz.y), s_v[slot], s_it[slot], s_ic[slot],
-                            (s_cl[slot] & 7u) != 7u, pc);
+                const double vv = s_v[slot];
+                const spb::OrderPhase ph = spb::order_phase(vv);  // per-element orders: one phase per point
+                kpass_point(job, s, s_idx[slot], cplx(zz.x, zz.y), vv, s_it[slot], s_ic[slot], &ph);
             }
         }
         __syncthreads();  // the next batch overwrites the staging arrays
@@ -141,7 +138,7 @@ __global__ void __launch_bounds__(128, SPB_KPASS_MINB) k_kpass_sorted(DevJob job
 }
 
 void launch_kpass(const DevJob &job, const Scratch &s, int sms, cudaStream_t st) {
-    if (job.v_stride != 0)
+    if (job.v_stride != 0 || job.n < 2)
         k_kpass_sorted<<<resident_grid(k_kpass_sorted, 128, sms), 128, 0, st>>>(job, s);
     else
         k_kpass<<<resident_grid(k_kpass, 128, sms), 128, 0, st>>>(job, s);
