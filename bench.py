@@ -68,6 +68,32 @@ def traffic_for(kernel_name):
         return None
 
 
+def bind_to_gpu_numa_node(torch, index):
+    """Best effort: run this rank on the CPUs of the NUMA node its GPU hangs off, so that the pinned host buffers
+    allocated afterwards (first touch) and the staging copies stay on the PCIe root the GPU is attached to.
+    Returns a short description for the JSON line, or None when the topology cannot be read."""
+    try:
+        pr = torch.cuda.get_device_properties(index)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return f"rank bound to NUMA node {node} ({len(cpus)} cpus) of GPU {bdf}"
+    except Exception:
+        return None
+
+
 def load_flops_per_eval():
     path = os.path.join(ROOT, "profiles", "flops_per_eval.json")
     try:
@@ -211,6 +237,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: sciport_rs_b200 has no CPU path")
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    numa_note = bind_to_gpu_numa_node(torch, local_rank) if world > 1 else None
     warmup = max(args.warmup, 3)
 
     # FP64 peak of this GPU (DFMA microbenchmark, part of the library), before the timed region
@@ -308,6 +335,7 @@ def main():
         d2h = oj.nbytes + oy.nbytes + 16
         e2e = {"value": evals_per_step * args.e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "steps": args.e2e_steps,
+               "numa": numa_note,
                "note": "special.jvyv on pinned host buffers through spb_bessel_jy: H2D of z, kernels, D2H of J and Y "
                        "and of the 16-byte first-error words inside the timed region"}
 

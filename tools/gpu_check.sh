@@ -7,6 +7,7 @@ mkdir -p gpurun_out
 python -m pytest tests -m gpu -q -x "$@" > gpurun_out/pytest_${tag}.log 2>&1
 echo "pytest rc=$?" | tee -a gpurun_out/pytest_${tag}.log
 tail -5 gpurun_out/pytest_${tag}.log
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke_${tag}.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/smoke_${tag}.log
 python bench.py --steps 20 --warmup 3 > gpurun_out/bench_${tag}.json 2> gpurun_out/bench_${tag}.err
 echo "bench rc=$?"; tail -c 600 gpurun_out/bench_${tag}.json
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref_${tag}.json 2>> gpurun_out/bench_${tag}.err
