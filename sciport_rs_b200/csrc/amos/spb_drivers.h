@@ -135,13 +135,13 @@ SPB_FN int acon(cplx z, real fnu, int kode, int mr, int n, Y y, real rl, real fn
 
 // Multiply y by csgn with the underflow guard used after every rotation.
 SPB_HD cplx rot_guard(cplx y, cplx csgn, real rtol, real ascle, real tol) {
-    real aa = y.re, bb = y.im, atol = 1.0;
-    if (!(rmax(rabs(aa), rabs(bb)) > ascle)) {
-        aa *= rtol;
-        bb *= rtol;
-        atol = tol;
-    }
-    return cplx((aa * csgn.re - bb * csgn.im) * atol, (aa * csgn.im + bb * csgn.re) * atol);
+    real aa = y.re, bb = y.im;
+    // on scale (practically always): the plain product; the factors 1.0 of the guarded form are exact, so both
+    // forms round identically
+    if (rmax(rabs(aa), rabs(bb)) > ascle) return cplx(aa * csgn.re - bb * csgn.im, aa * csgn.im + bb * csgn.re);
+    aa *= rtol;
+    bb *= rtol;
+    return cplx((aa * csgn.re - bb * csgn.im) * tol, (aa * csgn.im + bb * csgn.re) * tol);
 }
 
 // ---------------------------------------------------------------- I

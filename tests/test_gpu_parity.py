@@ -45,7 +45,7 @@ def test_golden_device_pointers(special, fn, kode):
     assert ok.all(), f"{(~ok).sum()} ierr/nz mismatches, first v={v[~ok][0]} z={z[~ok][0]}"
 
 
-@pytest.mark.parametrize("cfg", ["cfg2", "cfg3", "cfg4", "real", "wide"])
+@pytest.mark.parametrize("cfg", ["cfg2", "cfg3", "cfg4", "real", "wide", "far"])
 @pytest.mark.parametrize("fn", list(FN))
 def test_vs_cpu_oracle_and_monolithic(special, fn, cfg):
     """Binned CUDA path vs CPU oracle (tolerance) and vs the monolithic CUDA path (bit-identical)."""
