@@ -372,6 +372,31 @@ def main():
             "kernels": prof,
         }
 
+    # accuracy of this very run against the CPU oracle on a strided parity sample (BASELINE metric: "max rel err"):
+    # normalised error |got - want| / max(|J|, |Y|) (absolute bound near zeros), ierr / nz must agree exactly
+    accuracy = None
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import helpers  # noqa: E402  (test infrastructure; the checker leg)
+        from oracle import scipy_oracle as so  # noqa: E402
+        n_acc = 1 << 16
+        idx = torch.arange(0, N_POINTS, N_POINTS // n_acc, device=dev)[:n_acc]
+        zs = z[idx].cpu().numpy()
+        (oj, ej, nj), (oy, ey, ny) = special.bessel_jy(vt, z)
+        gj, gy = oj[idx].cpu().numpy(), oy[idx].cpu().numpy()
+        wj, ejc, njc = helpers.cpu_bessel("J", 1, ORDER, zs)
+        wy, eyc, nyc = helpers.cpu_bessel("Y", 1, ORDER, zs)
+        scale = np.maximum(np.abs(wj), np.abs(wy))
+        err = np.concatenate([so.mismatch(gj, wj, scale), so.mismatch(gy, wy, scale)])
+        codes_ok = (np.array_equal(ej[idx].cpu().numpy(), ejc) and np.array_equal(ey[idx].cpu().numpy(), eyc) and
+                    np.array_equal(nj[idx].cpu().numpy(), njc) and np.array_equal(ny[idx].cpu().numpy(), nyc))
+        accuracy = {"max_norm_err": float(err.max()), "p999_norm_err": float(np.quantile(err, 0.999)),
+                    "tolerance": so.RTOL, "within_tolerance": bool(err.max() <= so.RTOL), "ierr_nz_identical": codes_ok,
+                    "sample": f"{n_acc} evenly strided grid points, J and Y, vs the CPU oracle (oracle/)"}
+        del oj, oy
+    except Exception as e:  # the checker is optional for the timing line
+        accuracy = {"error": repr(e)}
+
     cpu_baseline = None
     if not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
@@ -391,7 +416,7 @@ def main():
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches_timed,
         "kernel_ms_per_step": sum(r["ms"] for r in prof) if prof else None,
         "host_enqueue_ms_per_step": host_enqueue_ms, "fp64_peak_tflops": fp64_peak,
-        "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "roofline": roofline, "accuracy": accuracy, "cpu_baseline": cpu_baseline,
     }
     print(json.dumps(line))
     if world > 1:
