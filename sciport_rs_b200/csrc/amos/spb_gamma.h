@@ -39,6 +39,50 @@ SPB_HD real sinpi_(real x) {
 #endif
 }
 
+#if defined(__CUDA_ARCH__)
+// ln y = hi + lo with an absolute error of a few 1e-18 (y > 0, finite, normal): the Stirling exponent
+// (y - 1/2) ln y - y is as large as 709, so a plain double logarithm (error 1.1e-16 |ln y|) would cost 1e-13 in
+// Gamma.  m = y 2^-e in [0.707, 1.414], s = (m - 1)/(m + 1) carried with its rounding residual,
+// ln m = 2 s + 2 s^3/3 + ... (eleven terms), e ln 2 added in two parts.
+__device__ __forceinline__ void log_dd(double y, double &hi, double &lo) {
+    int hx = __double2hiint(y);
+    const int lx = __double2loint(y);
+    int e = (hx >> 20) - 1023;
+    hx = (hx & 0x000fffff) | 0x3ff00000;
+    double m = __hiloint2double(hx, lx);
+    if (m > 1.4142135623730951) {
+        m *= 0.5;
+        e += 1;
+    }
+    const double f = m - 1.0;            // exact
+    const double dh = m + 1.0;           // may round: keep the residual
+    const double dl = m - (dh - 1.0);
+    const double r = 1.0 / dh;
+    const double sh = f * r;
+    const double sl = (fma(-sh, dh, f) - sh * dl) * r;
+    const double s2 = sh * sh;
+    double p = 0.08695652173913043;      // 2/23
+    p = fma(p, s2, 0.09523809523809523);
+    p = fma(p, s2, 0.10526315789473684);
+    p = fma(p, s2, 0.11764705882352941);
+    p = fma(p, s2, 0.13333333333333333);
+    p = fma(p, s2, 0.15384615384615385);
+    p = fma(p, s2, 0.18181818181818182);
+    p = fma(p, s2, 0.2222222222222222);
+    p = fma(p, s2, 0.2857142857142857);
+    p = fma(p, s2, 0.4);
+    p = fma(p, s2, 0.6666666666666666);
+    const double mh = sh + sh;
+    const double ml = fma(sh * s2, p, sl + sl);
+    const double fe = (double)e;
+    const double eh = fe * 0.6931471803691238;  // exact: 21 trailing zero bits
+    const double t = eh + mh;                    // |eh| >= |mh| unless e == 0 (then t == mh exactly)
+    const double err = mh - (t - eh);
+    hi = t;
+    lo = err + fma(fe, 1.9082149292705877e-10, ml);
+}
+#endif
+
 SPB_FN real gamma_pos(real x) {
     // x > 0
     const real sq2pi = 2.50662827463100050242;
@@ -49,6 +93,23 @@ SPB_FN real gamma_pos(real x) {
         prod *= y;
         y += real(1.0);
     }
+#if defined(__CUDA_ARCH__)
+    {
+        // Gamma(y) = exp((y - 1/2) ln y - y + ln sqrt(2 pi) + tail(y)), the exponent in double-double
+        double lh, ll;
+        log_dd(y, lh, ll);
+        const double a = y - 0.5;  // exact
+        const double p = a * lh;
+        const double pe = fma(a, lh, -p) + a * ll;
+        const double t1 = p - y;  // |p| > y for y >= 12
+        const double te = -y - (t1 - p);
+        const double rest = ((te + pe) + stirling_tail(y)) + 0.9189385332046728;
+        const double th = t1 + rest;
+        const double tl = rest - (th - t1);
+        const double r = exp_(0.5 * th);
+        return (r * fma(r, tl, r)) / prod;
+    }
+#endif
     real w = pow(y, real(0.5) * y - real(0.25));
     real g = sq2pi * exp(stirling_tail(y));
     g = (w * exp(-y)) * w * g;
