@@ -46,6 +46,12 @@ inline counted pow(counted a, counted b) { g_ops += 60; return counted(std::pow(
 inline bool signbit(counted a) { return std::signbit(a.v); }
 
 inline counted fma_(counted a, counted b, counted c) { return a * b + c; }
+inline int expo_(counted a) {
+    union { double d; unsigned long long u; } t;
+    t.d = a.v;
+    return (int)((t.u >> 52) & 0x7ffull);
+}
+inline counted neg_(counted a) { return counted(-a.v); }
 #define SPB_REAL counted
 #include "../sciport_rs_b200/csrc/amos/spb_family.h"
 

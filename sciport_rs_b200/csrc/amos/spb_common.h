@@ -97,6 +97,28 @@ SPB_HD double pow2_(int e) {
 #endif
 }
 
+// Exponent field (biased, 0..2047) and sign flip of a double through its high word: integer-pipe operations where
+// a comparison of moduli or a negation would otherwise occupy the FP64 pipe of a store-bound loop.
+SPB_HD int expo_(double x) {
+#if defined(__CUDA_ARCH__)
+    return (__double2hiint(x) >> 20) & 0x7ff;
+#else
+    union {
+        double d;
+        unsigned long long u;
+    } t;
+    t.d = x;
+    return (int)((t.u >> 52) & 0x7ffull);
+#endif
+}
+SPB_HD double neg_(double x) {
+#if defined(__CUDA_ARCH__)
+    return __hiloint2double(__double2hiint(x) ^ (int)0x80000000, __double2loint(x));
+#else
+    return -x;
+#endif
+}
+
 // largest value of x among the currently converged lanes of the warp (device); the value itself on the host
 #if defined(__CUDA_ARCH__)
 #define SPB_WARP_MAX(x) __reduce_max_sync(__activemask(), (x))

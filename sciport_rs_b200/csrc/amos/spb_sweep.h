@@ -13,8 +13,8 @@
 //   pass B  repeats the identical recurrence (same seeds, same rescalings, so the same rounding) and stores
 //           member k as  factor * iterate * 2^(-200 j)  the moment it appears, j = rescalings still to come.
 //
-// Members whose modulus is below exp(-elim) are flushed to zero and counted in nz, as the sequence drivers do
-// for the leading (highest-order) members.  The routine DECLINES (returns < 0 before storing anything) for
+// Leading (highest-order) members with both components below 2^-1011 = 4.6e-305 (about exp(-elim)) are flushed to
+// zero and counted in nz, as the sequence drivers do for the leading members.  The routine DECLINES (returns < 0 before storing anything) for
 // arguments near the exponent limits or outside its cost envelope; the caller then uses the classic sequence
 // driver, so every input is still served.
 #pragma once
@@ -39,14 +39,22 @@ SPB_HD cplx sweep_step(cplx a, cplx c, cplx b) {
 
 // i^m * v (exact: a swap and sign changes, no floating-point operation)
 SPB_HD cplx rot_i(cplx v, int m) {
-    real x = (m & 1) ? -v.im : v.re;
+    real x = (m & 1) ? neg_(v.im) : v.re;
     real y = (m & 1) ? v.re : v.im;
     if (m & 2) {
-        x = -x;
-        y = -y;
+        x = neg_(x);
+        y = neg_(y);
     }
     return cplx(x, y);
 }
+
+// |x| >= 2^200 for either component (also true for Inf / NaN), by the exponent fields
+SPB_HD bool sweep_big(cplx a) {
+    const int e = expo_(a.re) > expo_(a.im) ? expo_(a.re) : expo_(a.im);
+    return e >= 1023 + 200;
+}
+// both components below 2^-1011 = 4.6e-305 (the flush threshold, about exp(-elim))
+SPB_HD bool sweep_tiny(cplx a) { return expo_(a.re) < 12 && expo_(a.im) < 12; }
 
 // y[k] = csgn0 * i^(dm k) * I_{fnu+k}(w),  Re w >= 0,  az = |w|.  The order-independent factor csgn0 is folded into
 // the normalising factor once; the per-order unit i^(dm k) is applied exactly (dm = +-1 for J, 2 for I continued
@@ -104,23 +112,32 @@ SPB_FN int isweep(cplx w, real fnu, int kode, int n, Y y, real az, cplx csgn0, i
     }
     const int kk = k + 1 - id;
     const int steps = kk + n - 1;
-    const real dfnu = fnu + real(n - 1);
+    // Both passes count the recurrence by `it` = steps still to come after this one (it = steps-1 .. 0): step `it`
+    // produces the iterate of order fnu + it from the two above it, member it is stored when it < n, and the
+    // rescaling test is made whenever it is a multiple of 4 (one step grows the iterate by at most
+    // 2 (order + steps) / |w| < 2^24, so it stays below 2^300).  On the device the lanes of a warp enter the loops
+    // staggered by (largest steps of the warp - own steps) idle iterations: `it` is then warp-uniform, so the test
+    // schedule does not diverge and, in pass B, the 32 stores of one order go out in the same instruction as one
+    // coalesced 512-byte request.  Timing only: the arithmetic of a lane does not depend on its neighbours.
+    // The rescaling itself is branch-free (a multiplication by 1 or by 2^-200).
+    const int it0 = SPB_WARP_MAX(steps) - 1;
     // ---- pass A: recurrence in registers, count the rescalings
     int etot = 0;
     cplx p1(1.0, 0.0), p2(0.0, 0.0);
     {
-        real t1r = real(kk);
-        for (int i = 1; i <= steps; ++i) {
+        real rap = fnu + real(steps);
+        for (int it = it0; it >= 0; --it) {
+            if (it >= steps) continue;
             cplx pt = p1;
-            p1 = sweep_step(pt, rz * (dfnu + t1r), p2);
+            p1 = sweep_step(pt, rz * rap, p2);
             p2 = pt;
-            t1r -= real(1.0);
-            // one step grows the iterate by at most 2 (order + steps) / |w| < 2^24, so testing every fourth step
-            // keeps it below 2^300
-            if ((i & 3) == 0 && rmax(rabs(p1.re), rabs(p1.im)) > real(SPB_SWEEP_BIG)) {
-                p1 = p1 * real(SPB_SWEEP_SMALL);
-                p2 = p2 * real(SPB_SWEEP_SMALL);
-                etot += 1;
+            rap -= real(1.0);
+            if ((it & 3) == 0) {
+                const bool big = sweep_big(p1);
+                const real sc = big ? real(SPB_SWEEP_SMALL) : real(1.0);
+                p1 = p1 * sc;
+                p2 = p2 * sc;
+                etot += big ? 1 : 0;
             }
         }
     }
@@ -146,34 +163,28 @@ SPB_FN int isweep(cplx w, real fnu, int kode, int n, Y y, real az, cplx csgn0, i
             return -1;
     }
     // ---- pass B: same recurrence, store each member once (top order first)
-    const real flush = 3.9222272510438042e-305;  // exp(-elim)
     int m = (dm * (n - 1)) & 3;                  // unit of the top member
     int nz = 0;
     bool leading = true;
     {
-        // On the device the lanes of a warp start this pass staggered by (largest kk of the warp - own kk)
-        // idle iterations, so that all lanes produce member k in the same iteration and the warp's 32 stores
-        // of one order go out as one coalesced 512-byte request.  Timing only: the arithmetic of a lane does
-        // not depend on its neighbours.
-        const int delay = SPB_WARP_MAX(kk) - kk;
         int e = 0;
-        int member = n;  // next member to store is member - 1
-        real t1r = real(kk);
+        real rap = fnu + real(steps);
         cplx a(1.0, 0.0), b(0.0, 0.0);
-        for (int it = 1 - delay; it <= steps; ++it) {
-            if (it < 1) continue;
-            const int i = it;
+        for (int it = it0; it >= 0; --it) {
+            if (it >= steps) continue;
             cplx pt = a;
-            a = sweep_step(pt, rz * (dfnu + t1r), b);
+            a = sweep_step(pt, rz * rap, b);
             b = pt;
-            t1r -= real(1.0);
-            if ((i & 3) == 0 && rmax(rabs(a.re), rabs(a.im)) > real(SPB_SWEEP_BIG)) {
-                a = a * real(SPB_SWEEP_SMALL);
-                b = b * real(SPB_SWEEP_SMALL);
-                e += 1;
+            rap -= real(1.0);
+            if ((it & 3) == 0) {
+                const bool big = sweep_big(a);
+                const real sc = big ? real(SPB_SWEEP_SMALL) : real(1.0);
+                a = a * sc;
+                b = b * sc;
+                e += big ? 1 : 0;
             }
-            if (i < kk) continue;
-            member -= 1;
+            if (it >= n) continue;
+            const int member = it;
             const int j = etot - e;  // rescalings still to come: true size is 2^(-200 j) of the iterate
             // scale in two exact stages around the multiplication by q (|iterate| < 2^300, |q| may be as large
             // as e^alim for unscaled values): neither stage can overflow, and a stage that underflows belongs
@@ -186,10 +197,16 @@ SPB_FN int isweep(cplx w, real fnu, int kode, int n, Y y, real az, cplx csgn0, i
                 val = (a * pow2_(-200 * j1)) * q;
                 if (j > 5) val = (j <= 10) ? val * pow2_(-200 * (j - 5)) : cplx(0.0, 0.0);
             }
-            const bool zero = !(rmax(rabs(val.re), rabs(val.im)) >= flush);
-            if (zero) val = cplx(0.0, 0.0);
-            nz += (zero && leading) ? 1 : 0;
-            leading = leading && zero;
+            // underflow concerns the leading (highest-order) members only: once one member is on scale the
+            // lower orders are too (they grow towards the order |w| and oscillate at O(|w|^-1/2) below it)
+            if (leading) {
+                if (sweep_tiny(val)) {
+                    val = cplx(0.0, 0.0);
+                    nz += 1;
+                } else {
+                    leading = false;
+                }
+            }
             y[member] = rot_i(val, m);
             m = (m - dm) & 3;
         }
