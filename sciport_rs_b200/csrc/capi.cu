@@ -76,7 +76,22 @@ struct DeviceCtx {
     unsigned long long *d_first = nullptr;         // [2] first failing element (packed) of the call in flight
     unsigned long long h_first[2] = {~0ull, ~0ull};  // host copy, valid once the call has completed
     double2 *d_scalar = nullptr;                   // one complex scalar (I0(beta) of the Kaiser window)
+    // The scratch of a device is shared by all calls on it.  Device-pointer calls return while their kernels are
+    // still queued, so a following call on ANOTHER stream first waits (on the device) for the event that ends the
+    // previous one; calls on the same stream are ordered by the stream itself.
+    cudaEvent_t busy = nullptr;
+    cudaStream_t busy_stream = nullptr;
+    bool busy_valid = false;
 };
+
+static void order_after_previous(DeviceCtx *c, cudaStream_t st) {
+    if (c->busy_valid && c->busy_stream != st) cudaStreamWaitEvent(st, c->busy, 0);
+}
+static void mark_busy(DeviceCtx *c, cudaStream_t st) {
+    cudaEventRecord(c->busy, st);
+    c->busy_stream = st;
+    c->busy_valid = true;
+}
 
 // which devices the last compute call of this thread used, for spb_last_first_error()
 thread_local std::vector<int> g_first_devs;
@@ -108,6 +123,7 @@ DeviceCtx *get_ctx(int dev) {
         cudaStreamCreateWithFlags(&c->streams[1], cudaStreamNonBlocking);
         cudaEventCreate(&c->ev0);
         cudaEventCreate(&c->ev1);
+        cudaEventCreateWithFlags(&c->busy, cudaEventDisableTiming);
         cudaMalloc(&c->d_packed, sizeof(unsigned long long));
         cudaMalloc(&c->d_first, 2 * sizeof(unsigned long long));
         cudaMalloc(&c->d_scalar, sizeof(double2));
@@ -288,6 +304,7 @@ int run_device_seq(DeviceCtx *c, const BesselArgs &a, cudaStream_t st, int *laun
     std::lock_guard<std::mutex> lk(c->mu);
     CK(cudaSetDevice(c->dev));
     int launches = 0;
+    order_after_previous(c, st);
     CK(cudaMemsetAsync(c->d_first, 0xff, 16, st));
     CK(cudaEventRecord(c->ev0, st));
     for (long long off = 0; off < a.n; off += CHUNK_DEVICE) {
@@ -311,6 +328,7 @@ int run_device_seq(DeviceCtx *c, const BesselArgs &a, cudaStream_t st, int *laun
         launches += launch_sequence(job, a.n_orders, a.out_stride, c->scratch[0].s, c->sms, st);
     }
     CK(cudaEventRecord(c->ev1, st));
+    mark_busy(c, st);
     CK(cudaGetLastError());
     g_pending_ev0 = c->ev0;
     g_pending_ev1 = c->ev1;
@@ -326,6 +344,7 @@ int run_device(DeviceCtx *c, const BesselArgs &a, cudaStream_t st, double *ms_ou
     Prof prof;
     prof.on = (a.flags & SPB_PROFILE) != 0;
     if (prof.on) g_prof.clear();
+    order_after_previous(c, st);
     CK(cudaMemsetAsync(c->d_first, 0xff, 16, st));
     CK(cudaEventRecord(c->ev0, st));
     for (long long off = 0; off < a.n; off += CHUNK_DEVICE) {
@@ -370,6 +389,7 @@ int run_device(DeviceCtx *c, const BesselArgs &a, cudaStream_t st, double *ms_ou
         }
     }
     CK(cudaEventRecord(c->ev1, st));
+    mark_busy(c, st);
     CK(cudaGetLastError());
     // no host synchronisation: the call returns as soon as the launches are queued on the caller's stream
     g_pending_ev0 = c->ev0;
@@ -439,7 +459,8 @@ int run_host_slice(DeviceCtx *c, const BesselArgs &a, double *ms_out, int *launc
     double v0 = a.v[0];
     {
         const unsigned long long ones[2] = {~0ull, ~0ull};
-        CK(cudaMemcpy(c->d_first, ones, 16, cudaMemcpyHostToDevice));  // nothing of this thread is in flight here
+        if (c->busy_valid) cudaEventSynchronize(c->busy);  // a queued device-pointer call still owns the scratch
+        CK(cudaMemcpy(c->d_first, ones, 16, cudaMemcpyHostToDevice));  // host-buffer calls are synchronous
     }
     for (long long off = 0; off < a.n; off += CHUNK_HOST, ++k) {
         long long m = std::min(CHUNK_HOST, a.n - off);
@@ -506,6 +527,7 @@ int run_host_slice_seq(DeviceCtx *c, const BesselArgs &a, int *launches_out) {
     double v0 = a.v[0];
     {
         const unsigned long long ones[2] = {~0ull, ~0ull};
+        if (c->busy_valid) cudaEventSynchronize(c->busy);  // a queued device-pointer call still owns the scratch
         CK(cudaMemcpy(c->d_first, ones, 16, cudaMemcpyHostToDevice));
     }
     for (long long off = 0; off < a.n; off += chunk, ++k) {
@@ -665,9 +687,11 @@ int run_map(const spb_exec *ex, long long n, size_t in_bytes_per, size_t out_byt
     CK(cudaSetDevice(c->dev));
     g_last_launches = 1;
     if (dptr) {
+        order_after_previous(c, st);
         CK(cudaEventRecord(c->ev0, st));
         launch(in, out, n, st);
         CK(cudaEventRecord(c->ev1, st));
+        mark_busy(c, st);
         CK(cudaGetLastError());
         CK(cudaEventSynchronize(c->ev1));
         float ms = 0.f;
@@ -736,6 +760,7 @@ int spb_airy(int which, int kode, const spb_c128 *z, spb_c128 *out, int32_t *ier
     g_first_stream = st;
     g_first_pending = dptr;
     if (dptr) {
+        order_after_previous(c, st);
         CK(cudaMemsetAsync(c->d_first, 0xff, 16, st));
         CK(cudaEventRecord(c->ev0, st));
         for (long long off = 0; off < n; off += CHUNK_DEVICE) {
@@ -747,6 +772,7 @@ int spb_airy(int which, int kode, const spb_c128 *z, spb_c128 *out, int32_t *ier
                                            c->sms, st, c->d_first, off);
         }
         CK(cudaEventRecord(c->ev1, st));
+        mark_busy(c, st);
         CK(cudaGetLastError());
         CK(cudaEventSynchronize(c->ev1));
         float ms = 0.f;
@@ -757,6 +783,7 @@ int spb_airy(int which, int kode, const spb_c128 *z, spb_c128 *out, int32_t *ier
     int launches = 0, k = 0;
     {
         const unsigned long long ones[2] = {~0ull, ~0ull};
+        if (c->busy_valid) cudaEventSynchronize(c->busy);  // a queued device-pointer call still owns the scratch
         CK(cudaMemcpy(c->d_first, ones, 16, cudaMemcpyHostToDevice));
     }
     for (long long off = 0; off < n; off += CHUNK_HOST, ++k) {

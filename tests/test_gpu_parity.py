@@ -466,3 +466,28 @@ def test_full_size_cfg5_per_gpu_share(special):
         ok = scale > 1e-280
         worst = max(worst, float((res.abs() / scale.clamp_min(1e-300))[ok].max()))
     assert worst <= 1e-14, worst
+
+
+def test_calls_on_different_streams_share_scratch_safely(special):
+    """Device-pointer calls only enqueue; the per-device scratch is shared, so a call on another stream must be
+    ordered behind the previous one by the library itself."""
+    rng = np.random.default_rng(33)
+    v, z = gen("cfg3", 1 << 20, rng)
+    zt, vt = torch.from_numpy(z).cuda(), torch.from_numpy(v).cuda()
+    ref_k, _, _ = special.bessel("K", vt, zt, scaled=True)
+    ref_j, _, _ = special.bessel("J", 2.5, zt)
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    outs = []
+    for rep in range(4):
+        with torch.cuda.stream(s1):
+            a, _, _ = special.bessel("K", vt, zt, scaled=True)
+        with torch.cuda.stream(s2):
+            b, _, _ = special.bessel("J", 2.5, zt)
+        outs.append((a, b))
+    torch.cuda.synchronize()
+    for a, b in outs:
+        assert torch.equal(a.view(torch.float64), ref_k.view(torch.float64))
+        assert torch.equal(b.view(torch.float64), ref_j.view(torch.float64))
+    host, _, _ = special.bessel("K", v, z, scaled=True)  # a host-buffer call right behind queued device work
+    assert np.array_equal(host.view(np.uint64), to_np(ref_k).view(np.uint64))
