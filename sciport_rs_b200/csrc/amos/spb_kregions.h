@@ -377,8 +377,13 @@ SPB_FN int bknu_body(cplx z, real fnu, int kode, int n, Y y, real tol, real elim
             cplx cs = p2;
             for (int i = 1; i <= k; ++i) {
                 real a1 = fks - fk;
-                real a = (fks + fk) / (a1 + fhs);
-                real rak = real(2.0) / (fk + real(1.0));
+                // a = (fks + fk) / (a1 + fhs) and rak = 2 / (fk + 1) from ONE reciprocal (a division costs as
+                // much as a dozen multiplications on the device; the Miller iteration is self-normalising, so
+                // the two extra roundings do not matter)
+                real d1 = a1 + fhs, d2 = fk + real(1.0);
+                real rr = real(1.0) / (d1 * d2);
+                real a = (fks + fk) * (d2 * rr);
+                real rak = real(2.0) * (d1 * rr);
                 cplx cb = cplx(fk + z.re, z.im) * rak;
                 cplx pt = p2;
                 p2 = (pt * cb - p1) * a;
