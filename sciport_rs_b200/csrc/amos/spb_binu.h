@@ -190,16 +190,18 @@ SPB_FN int uni1(cplx z, real fnu, int kode, int n, Y y, int &nlast, real fnul, r
     // values with exponents between alim and elim are carried scaled by tol^{+-1}
     real cscl = real(1.0) / tol;
     real crsc = tol;
-    real cssr[3] = {cscl, 1.0, crsc};
-    real csrr[3] = {crsc, 1.0, cscl};
-    real bry[3];
-    bry[0] = real(1.0e3) * SPB_D1MACH1 / tol;
+    // scaling levels by selection, not by indexing (a dynamically indexed array lives in local memory on the device)
+    const real bry0 = real(1.0e3) * SPB_D1MACH1 / tol;
+    auto CSSR = [&](int k) -> real { return k == 1 ? cscl : (k == 2 ? real(1.0) : crsc); };
+    auto CSRR = [&](int k) -> real { return k == 1 ? crsc : (k == 2 ? real(1.0) : cscl); };
+    auto BRY = [&](int k) -> real { return k == 1 ? bry0 : (k == 2 ? real(1.0) / bry0 : real(SPB_D1MACH2)); };
     cplx phi, zeta1, zeta2, sum, s1, s2;
-    cplx cwrk[16], cy[2];
+    cplx cwrk[16];
+    cplx cy0(0.0, 0.0), cy1(0.0, 0.0);
     // over/underflow check on the first member
     real fn = rmax(fnu, real(1.0));
     int init = 0;
-    unik(z, fn, 1, 1, tol, init, phi, zeta1, zeta2, sum, cwrk);
+    unik(z, fn, 1, 1, tol, init, phi, zeta1, zeta2, sum, cwrk, false);
     if (kode == 1) {
         s1 = zeta2 - zeta1;
     } else {
@@ -221,7 +223,7 @@ SPB_FN int uni1(cplx z, real fnu, int kode, int n, Y y, int &nlast, real fnul, r
         for (int i = 1; i <= nn; ++i) {
             fn = fnu + real(nd - i);
             init = 0;
-            unik(z, fn, 1, 0, tol, init, phi, zeta1, zeta2, sum, cwrk);
+            unik(z, fn, 1, 0, tol, init, phi, zeta1, zeta2, sum, cwrk, false);
             if (kode == 1) {
                 s1 = zeta2 - zeta1;
             } else {
@@ -249,10 +251,10 @@ SPB_FN int uni1(cplx z, real fnu, int kode, int n, Y y, int &nlast, real fnul, r
             if (!bad) {
                 // scale s1 if |s1| < ascle
                 s2 = phi * sum;
-                real e = exp(s1.re) * cssr[iflag - 1];
+                real e = exp(s1.re) * CSSR(iflag);
                 cplx st(e * cos(s1.im), e * sin(s1.im));
                 s2 = s2 * st;
-                if (iflag == 1 && uchk(s2, bry[0], tol) != 0) bad = true;
+                if (iflag == 1 && uchk(s2, bry0, tol) != 0) bad = true;
             }
             if (bad) {
                 // set underflow and update parameters
@@ -274,19 +276,17 @@ SPB_FN int uni1(cplx z, real fnu, int kode, int n, Y y, int &nlast, real fnul, r
                 nlast = nd;
                 return nz;
             }
-            cy[i - 1] = s2;
-            y[nd - i] = s2 * csrr[iflag - 1];
+            if (i == 1) cy0 = s2; else cy1 = s2;
+            y[nd - i] = s2 * CSRR(iflag);
         }
         if (!redo) break;
     }
     if (nd <= 2) return nz;
     cplx rz = crecip(z) * real(2.0);
-    bry[1] = real(1.0) / bry[0];
-    bry[2] = SPB_D1MACH2;
-    s1 = cy[0];
-    s2 = cy[1];
-    real c1r = csrr[iflag - 1];
-    real ascle = bry[iflag - 1];
+    s1 = cy0;
+    s2 = cy1;
+    real c1r = CSRR(iflag);
+    real ascle = BRY(iflag);
     int k = nd - 2;
     fn = real(k);
     for (int i = 3; i <= nd; ++i) {
@@ -301,12 +301,12 @@ SPB_FN int uni1(cplx z, real fnu, int kode, int n, Y y, int &nlast, real fnul, r
         real c2m = rmax(rabs(c2.re), rabs(c2.im));
         if (c2m <= ascle) continue;
         iflag += 1;
-        ascle = bry[iflag - 1];
+        ascle = BRY(iflag);
         s1 = s1 * c1r;
         s2 = c2;
-        s1 = s1 * cssr[iflag - 1];
-        s2 = s2 * cssr[iflag - 1];
-        c1r = csrr[iflag - 1];
+        s1 = s1 * CSSR(iflag);
+        s2 = s2 * CSSR(iflag);
+        c1r = CSRR(iflag);
     }
     return nz;
 }
@@ -325,10 +325,11 @@ SPB_FN int uni2(cplx z, real fnu, int kode, int n, Y y, int &nlast, real fnul, r
     nlast = 0;
     real cscl = real(1.0) / tol;
     real crsc = tol;
-    real cssr[3] = {cscl, 1.0, crsc};
-    real csrr[3] = {crsc, 1.0, cscl};
-    real bry[3];
-    bry[0] = real(1.0e3) * SPB_D1MACH1 / tol;
+    // scaling levels by selection, not by indexing (a dynamically indexed array lives in local memory on the device)
+    const real bry0 = real(1.0e3) * SPB_D1MACH1 / tol;
+    auto CSSR = [&](int k) -> real { return k == 1 ? cscl : (k == 2 ? real(1.0) : crsc); };
+    auto CSRR = [&](int k) -> real { return k == 1 ? crsc : (k == 2 ? real(1.0) : cscl); };
+    auto BRY = [&](int k) -> real { return k == 1 ? bry0 : (k == 2 ? real(1.0) / bry0 : real(SPB_D1MACH2)); };
     // zn is in the right half plane after rotation by +-i
     cplx zn(z.im, -z.re);
     cplx zb = z;
@@ -347,7 +348,7 @@ SPB_FN int uni2(cplx z, real fnu, int kode, int n, Y y, int &nlast, real fnul, r
         c2.im = -c2.im;
     }
     cplx phi, arg, zeta1, zeta2, asum, bsum, s1, s2;
-    cplx cy[2];
+    cplx cy0(0.0, 0.0), cy1(0.0, 0.0);
     // over/underflow check on the first member
     real fn = rmax(fnu, real(1.0));
     unhj(zn, fn, 1, tol, phi, arg, zeta1, zeta2, asum, bsum);
@@ -402,10 +403,10 @@ SPB_FN int uni2(cplx z, real fnu, int kode, int n, Y y, int &nlast, real fnul, r
                 cplx dai = airy(arg, 1, 2, ndai, idum);
                 cplx st = dai * bsum + ai * asum;
                 s2 = phi * st;
-                real e = exp(s1.re) * cssr[iflag - 1];
+                real e = exp(s1.re) * CSSR(iflag);
                 cplx ex(e * cos(s1.im), e * sin(s1.im));
                 s2 = s2 * ex;
-                if (iflag == 1 && uchk(s2, bry[0], tol) != 0) bad = true;
+                if (iflag == 1 && uchk(s2, bry0, tol) != 0) bad = true;
             }
             if (bad) {
                 if (rs1 > real(0.0)) return -1;
@@ -432,20 +433,18 @@ SPB_FN int uni2(cplx z, real fnu, int kode, int n, Y y, int &nlast, real fnul, r
             }
             if (!(z.im > real(0.0))) s2.im = -s2.im;
             s2 = s2 * c2;
-            cy[i - 1] = s2;
-            y[nd - i] = s2 * csrr[iflag - 1];
+            if (i == 1) cy0 = s2; else cy1 = s2;
+            y[nd - i] = s2 * CSRR(iflag);
             c2 = c2 * cplx(0.0, cidi);
         }
         if (!redo) break;
     }
     if (nd <= 2) return nz;
     cplx rz = crecip(z) * real(2.0);
-    bry[1] = real(1.0) / bry[0];
-    bry[2] = SPB_D1MACH2;
-    s1 = cy[0];
-    s2 = cy[1];
-    real c1r = csrr[iflag - 1];
-    real ascle = bry[iflag - 1];
+    s1 = cy0;
+    s2 = cy1;
+    real c1r = CSRR(iflag);
+    real ascle = BRY(iflag);
     int k = nd - 2;
     fn = real(k);
     for (int i = 3; i <= nd; ++i) {
@@ -460,12 +459,12 @@ SPB_FN int uni2(cplx z, real fnu, int kode, int n, Y y, int &nlast, real fnul, r
         real c2m = rmax(rabs(c.re), rabs(c.im));
         if (c2m <= ascle) continue;
         iflag += 1;
-        ascle = bry[iflag - 1];
+        ascle = BRY(iflag);
         s1 = s1 * c1r;
         s2 = c;
-        s1 = s1 * cssr[iflag - 1];
-        s2 = s2 * cssr[iflag - 1];
-        c1r = csrr[iflag - 1];
+        s1 = s1 * CSSR(iflag);
+        s2 = s2 * CSSR(iflag);
+        c1r = CSRR(iflag);
     }
     return nz;
 }
