@@ -247,8 +247,12 @@ def test_jy_pair_matches_separate_calls(special, cfg):
         ja, ya, aa, ba = to_np(j), to_np(y), to_np(a), to_np(b)
         scale = np.maximum(np.abs(aa), np.abs(ba))
         ok = (to_np(ia) == 0) & (to_np(ib) == 0) & np.isfinite(scale)
-        assert np.all(so.mismatch(ja, aa, scale)[ok] <= 2e-14)
-        assert np.all(so.mismatch(ya, ba, scale)[ok] <= so.tolerance(ba, z, v)[ok])
+        # a point may be binned in one family and general in the other (the pair is classified like Y); outside the
+        # BASELINE boxes that difference of route shows the algorithm's own conditioning, eps max(|z|, v)
+        cond = 16.0 if cfg == "wide" else 0.0
+        tolj = np.maximum(2e-14, so.tolerance(aa, z, v, conditioning=cond)) if cond else np.full(z.shape, 2e-14)
+        assert np.all(so.mismatch(ja, aa, scale)[ok] <= tolj[ok])
+        assert np.all(so.mismatch(ya, ba, scale)[ok] <= so.tolerance(ba, z, v, conditioning=cond)[ok])
     # host-pointer path of the pair
     (jh, ejh, _), (yh, eyh, _) = special.bessel_jy(v[:50000], z[:50000])
     (jd, _, _), (yd, _, _) = special.bessel_jy(vt[:50000], zt[:50000])
