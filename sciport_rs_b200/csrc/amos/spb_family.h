@@ -49,6 +49,7 @@ struct Prep {
     int ierr;     // preliminary ierr (0 or 3)
     int mr;       // continuation direction (+-1)
     real az;      // |z| = |w| (rotations and reflections keep the modulus bit for bit): shared by every pass
+    int final_ierr, final_nz;  // CMB_FINAL: the result is 0 with these codes
 };
 
 // Conservative bound on |Re(-zeta1 + zeta2 -+ w)| of the leading uniform term for
@@ -153,6 +154,8 @@ SPB_FN Prep prepare(int fam, cplx z, real fnu, int kode) {
     p.kreg = -1;
     p.ierr = 0;
     p.mr = 0;
+    p.final_ierr = 0;
+    p.final_nz = 0;
     // anything unusual (invalid input, NaN, huge or tiny arguments) goes to the driver
     real az = cabs_(z);
     p.az = az;
@@ -172,6 +175,22 @@ SPB_FN Prep prepare(int fam, cplx z, real fnu, int kode) {
     const bool left = prepare_geometry(fam, z, p);
     // over/underflow pre-test of the K drivers (made at the rotated point) must be a no-op
     if (fnu > real(2.0) && !uoik_is_noop(az, rmax(fnu, real(1.0)), alim, rabs(p.w.re), kode)) {
+        // ... or provably an underflow of K_v(w): Re(zeta2 - zeta1) >= |Re w| - gnu (ln(1 + 2/t + t) + pi) > elim makes
+        // the pre-test zero the whole (single-member) sequence.  The K and Hankel drivers then return 0 with nz = 1
+        // in the right half plane and report an overflow (ierr = 2) in the left one, where the vanished K would
+        // have been continued with the growing I.  (Unscaled functions only: the scaled pre-test has no |Re w|.)
+        if (kode == 1 && (fam == FAM_K || fam == FAM_H1 || fam == FAM_H2)) {
+            const real gnu = rmax(fnu, real(1.0));
+            const real t = az / gnu;
+            const real b = gnu * (log(real(1.0) + real(2.0) / t + t) + real(SPB_PI));
+            if (rabs(p.w.re) - b > real(SPB_ELIM)) {
+                const bool was_left = (p.combine == CMB_ACON);
+                p.combine = CMB_FINAL;
+                p.final_ierr = was_left ? 2 : 0;
+                p.final_nz = was_left ? 0 : 1;
+                return p;
+            }
+        }
         p.combine = CMB_GENERAL;
         return p;
     }
@@ -480,6 +499,13 @@ SPB_FN cplx pipeline_eval(int fam, cplx z, real fnu, int kode, int &ierr, int &n
     Prep p = prepare(fam, z, fnu, kode);
     path = 1;
     if (p.combine == CMB_GENERAL) return general_eval(fam, z, fnu, kode, ierr, nz);
+    if (p.combine == CMB_FINAL) {
+        // decided by the classifier (a provable underflow of K)
+        path = 0;
+        ierr = p.final_ierr;
+        nz = p.final_nz;
+        return cplx(0.0, 0.0);
+    }
     {
         // the region passes see only the class (bins) and recompute the geometry: same thing here
         const int ireg = p.ireg, kreg = p.kreg;

@@ -224,9 +224,8 @@ int enqueue_chunk(const DevJob &job, ScratchSet &ss, int sms, int flags, cudaStr
         ++launches;
     }
     p.mark(SPB_K_GENERAL, st);
-    launch_general(job, ss.s, sms, st);
+    launches += launch_general(job, ss.s, sms, st);
     p.mark(-1, st);
-    ++launches;
     return launches;
 }
 

@@ -91,7 +91,8 @@ __global__ void __launch_bounds__(256) k_classify(DevJob job, Scratch s) {
             load_point(job, i, z, v);
             spb::Prep p = spb::prepare(job.fam, z, v, job.kode);
             unsigned int c;
-            if (p.combine == spb::CMB_GENERAL) {
+            if (p.combine == spb::CMB_GENERAL || p.combine == spb::CMB_FINAL) {
+                // (CMB_FINAL: decided by prepare(); the general kernel stores it without running the drivers)
                 c = 7u | (3u << 3) | (1u << 5);
             } else {
                 unsigned int bi = p.ireg >= 0 ? (unsigned int)p.ireg : 7u;
@@ -181,6 +182,7 @@ __global__ void __launch_bounds__(1024) k_scan(Scratch s) {
             s.bins[NBINS] = acc;
             s.bins[GLIST_LEN_SLOT] = ((volatile unsigned int *)s.bins)[SLOT_TOTALS + BIN_GENERAL];
             s.bins[SLOT_DONE] = 0;  // re-arm for the next chunk
+            s.bins[SLOT_G2] = 0;
         }
     }
 }

@@ -57,6 +57,7 @@ constexpr int TILE = 2048;               // points per classification tile
 // slots of Scratch::bins beyond the NBINS+1 start offsets
 constexpr int GLIST_LEN_SLOT = 24;  // current length of the general list (grows when a pass hands a point over)
 constexpr int SLOT_DONE = 25;       // CTAs of k_scan that have finished
+constexpr int SLOT_G2 = 26;         // length of the second-stage general list (points left after the shortcuts)
 constexpr int SLOT_TOTALS = 32;     // [NBINS] bin totals
 constexpr int BINS_WORDS = 64;
 
@@ -82,7 +83,7 @@ void launch_classify(const DevJob &job, const Scratch &s, cudaStream_t st);
 void launch_scan_scatter(const DevJob &job, const Scratch &s, cudaStream_t st);
 void launch_ipass(const DevJob &job, const Scratch &s, int region, int sms, cudaStream_t st);
 void launch_kpass(const DevJob &job, const Scratch &s, int sms, cudaStream_t st);
-void launch_general(const DevJob &job, const Scratch &s, int sms, cudaStream_t st);
+int launch_general(const DevJob &job, const Scratch &s, int sms, cudaStream_t st);
 void launch_monolithic(const DevJob &job, cudaStream_t st);
 int launch_sequence(const DevJob &job, int n_orders, long long out_stride, const Scratch &s, int sms,
                     cudaStream_t st);
