@@ -65,31 +65,55 @@ __device__ __forceinline__ void airy_point(int id, int kode, int sem, cplx zz, l
     note_error(first_err, index_base + i, ie);
 }
 
-// persistent walk over the key-sorted index list (two-deep software pipeline as in the Bessel passes)
+// rough length of the evaluation at |zeta| inside one region key (arbitrary units; only the order matters)
+__device__ __forceinline__ double airy_work(cplx z) {
+    const double az = spb::cabs_(z);
+    if (!(az > 1.0)) return 10.0 + 20.0 * az;  // Maclaurin terms grow with |z|
+    const double azeta = (2.0 / 3.0) * az * sqrt(az);
+    // Miller start indices fall like 1/|zeta| (K) or grow like |zeta| (I below rl); asymptotic series shorten
+    double k = azeta <= 2.0 ? 25.0 : (azeta < 28.7 ? 9.0 + 175.0 / azeta : 12.0);
+    double i = azeta < SPB_RL ? 30.0 + 2.0 * azeta : 12.0 + 600.0 / azeta;
+    return 2.0 * k + i;
+}
+
+// persistent walk over the key-sorted index list: batches of SORT_B points staged in shared memory and grouped by
+// predicted work (spb_dev.cuh), so that the lanes of a warp run evaluations of similar length inside a region
 template <bool BI>
 __global__ void __launch_bounds__(128) k_airy_sorted(int id, int kode, int sem, const double2 *z, double2 *out,
                                                      int *ierr, int *nz, long long n, Scratch s,
                                                      unsigned long long *first_err, long long index_base) {
+    __shared__ SortSmem sm;
+    __shared__ unsigned int s_idx[SORT_B];
+    __shared__ double2 s_z[SORT_B];
     const unsigned int count = (unsigned int)n;
-    const unsigned int stride = gridDim.x * blockDim.x;
     const unsigned int *perm = s.perm_i;
-    unsigned int t = blockIdx.x * blockDim.x + threadIdx.x;
-    bool have1 = t < count, have2 = (t + stride) < count;
-    unsigned int i1 = have1 ? __ldg(perm + t) : 0u;
-    unsigned int i2 = have2 ? __ldg(perm + t + stride) : 0u;
-    double2 z1 = make_double2(0.0, 0.0);
-    if (have1) z1 = __ldg(z + i1);
 #pragma unroll 1
-    while (have1) {
-        const long long i = i1;
-        const cplx zz(z1.x, z1.y);
-        t += stride;
-        have1 = have2;
-        i1 = i2;
-        have2 = (t + stride) < count;
-        if (have2) i2 = __ldg(perm + t + stride);
-        if (have1) z1 = __ldg(z + i1);
-        airy_point<BI>(id, kode, sem, zz, i, out, ierr, nz, first_err, index_base);
+    for (unsigned int t0 = blockIdx.x * SORT_B; t0 < count; t0 += gridDim.x * SORT_B) {
+        const unsigned int m = min((unsigned int)SORT_B, count - t0);
+        unsigned int bucket[SORT_R];
+#pragma unroll
+        for (int r = 0; r < SORT_R; ++r) {
+            const unsigned int slot = threadIdx.x + 128 * r;
+            bucket[r] = 0xffu;
+            if (slot < m) {
+                const unsigned int i = __ldg(perm + t0 + slot);
+                const double2 zz = __ldg(z + i);
+                s_idx[slot] = i;
+                s_z[slot] = zz;
+                bucket[r] = bucket_of(airy_work(cplx(zz.x, zz.y)), 0.2);
+            }
+        }
+        batch_sort(sm, bucket);
+#pragma unroll 1
+        for (int r = 0; r < SORT_R; ++r) {
+            const unsigned int pos = threadIdx.x + 128 * r;
+            if (pos < m) {
+                const unsigned int slot = sm.order[pos];
+                const double2 zz = s_z[slot];
+                airy_point<BI>(id, kode, sem, cplx(zz.x, zz.y), s_idx[slot], out, ierr, nz, first_err, index_base);
+            }
+        }
+        __syncthreads();
     }
 }
 
