@@ -179,15 +179,17 @@ SPB_FN Prep prepare(int fam, cplx z, real fnu, int kode) {
         // the pre-test zero the whole (single-member) sequence.  The K and Hankel drivers then return 0 with nz = 1
         // in the right half plane and report an overflow (ierr = 2) in the left one, where the vanished K would
         // have been continued with the growing I.  (Unscaled functions only: the scaled pre-test has no |Re w|.)
-        if (kode == 1 && (fam == FAM_K || fam == FAM_H1 || fam == FAM_H2)) {
+        // Y = (H1 - H2)/2i evaluates both Hankel functions at the same |Re w|: one of them vanishes, the other one
+        // is the overflow, so Y reports ierr = 2.
+        if (kode == 1 && (fam == FAM_K || fam == FAM_H1 || fam == FAM_H2 || fam == FAM_Y)) {
             const real gnu = rmax(fnu, real(1.0));
             const real t = az / gnu;
             const real b = gnu * (log(real(1.0) + real(2.0) / t + t) + real(SPB_PI));
             if (rabs(p.w.re) - b > real(SPB_ELIM)) {
-                const bool was_left = (p.combine == CMB_ACON);
+                const bool overflow = (p.combine == CMB_ACON) || fam == FAM_Y;
                 p.combine = CMB_FINAL;
-                p.final_ierr = was_left ? 2 : 0;
-                p.final_nz = was_left ? 0 : 1;
+                p.final_ierr = overflow ? 2 : 0;
+                p.final_nz = overflow ? 0 : 1;
                 return p;
             }
         }

@@ -21,7 +21,7 @@ __global__ void __launch_bounds__(128) k_general(DevJob job, const unsigned int 
     }
 }
 
-// First stage for the unscaled K / H1 / H2 families: most of their non-simple points sit at huge |Re w|, where
+// First stage for the unscaled K / H1 / H2 / Y families: most of their non-simple points sit at huge |Re w|, where
 // prepare() has already PROVED that K underflows (CMB_FINAL: value 0 with known codes).  Those are stored here;
 // the few that really need the drivers are appended to a second list, so that the expensive kernel runs them in
 // full warps instead of one or two lanes per warp.
@@ -61,7 +61,8 @@ __global__ void __launch_bounds__(128) k_monolithic(DevJob job) {
 }
 
 int launch_general(const DevJob &job, const Scratch &s, int sms, cudaStream_t st) {
-    const bool shortcuts = job.kode == 1 && (job.fam == spb::FAM_K || job.fam == spb::FAM_H1 || job.fam == spb::FAM_H2);
+    const bool shortcuts = job.kode == 1 && (job.fam == spb::FAM_K || job.fam == spb::FAM_H1 ||
+                                             job.fam == spb::FAM_H2 || job.fam == spb::FAM_Y);
     if (shortcuts) {
         k_general_shortcuts<<<sms * 4, 256, 0, st>>>(job, s);
         k_general<<<resident_grid(k_general, 128, sms), 128, 0, st>>>(job, s.perm_k, s.bins + SLOT_G2);
