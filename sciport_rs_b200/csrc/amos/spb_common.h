@@ -23,6 +23,23 @@
 #define SPB_FN inline
 #endif
 
+// Data-dependent loops of the region routines stay rolled on the device: unrolled by the compiler they make the
+// pass kernels a quarter of a megabyte each, and warps sitting in different loops then miss the instruction cache
+// (28 % of the stall samples of the K pass with per-element orders were "no instruction").
+#if defined(__CUDACC__)
+#define SPB_NO_UNROLL _Pragma("unroll 1")
+#else
+#define SPB_NO_UNROLL
+#endif
+
+// Rarely taken fallbacks (scaled modulus, library transcendentals outside the fast range) are kept out of line on
+// the device: force-inlined at every call site they made up more than half of the code of the pass kernels.
+#if defined(__CUDACC__)
+#define SPB_COLD static __host__ __device__ __noinline__
+#else
+#define SPB_COLD static inline
+#endif
+
 // The scalar type can be swapped for an op-counting type on the host
 // (oracle/flopcount.cpp) to tally algorithmic flops per evaluation.
 #ifndef SPB_REAL
@@ -126,16 +143,10 @@ SPB_HD double neg_(double x) {
 #define SPB_WARP_MAX(x) (x)
 #endif
 
-// |z| without premature over/underflow (the ZABS of the algorithm).
-SPB_HD real cabs_(cplx z) {
-    real u = rabs(z.re), v = rabs(z.im);
-    // both squares on scale: the plain form (one square root, no division) is as accurate as the scaled one
-    {
-        real m = rmax(u, v);
-        if (m > real(1.0e-140) && m < real(1.0e140)) return sqrt(u * u + v * v);
-    }
+// |z| without premature over/underflow (the ZABS of the algorithm): scaled form for components whose squares
+// would leave the range
+SPB_COLD real cabs_scaled(real u, real v) {
     real s = u + v;
-    // s*1.0 in the original forces a store; here we only need the zero test.
     if (s == real(0.0)) return real(0.0);
     if (u > v) {
         real q = v / u;
@@ -143,6 +154,13 @@ SPB_HD real cabs_(cplx z) {
     }
     real q = u / v;
     return v * sqrt(real(1.0) + q * q);
+}
+SPB_HD real cabs_(cplx z) {
+    real u = rabs(z.re), v = rabs(z.im);
+    // both squares on scale: the plain form (one square root, no division) is as accurate as the scaled one
+    real m = rmax(u, v);
+    if (m > real(1.0e-140) && m < real(1.0e140)) return sqrt(u * u + v * v);
+    return cabs_scaled(u, v);
 }
 
 // a / b via the modulus of b (keeps intermediate values on scale).
@@ -213,11 +231,16 @@ static __constant__ double EXPC[12] = {1.6059043836821613e-10, 2.08767569878681e
 }  // namespace fm
 #endif
 
+#if defined(__CUDACC__)
+static __device__ __noinline__ void sincos_library(double x, double *s, double *c) { sincos(x, s, c); }
+static __device__ __noinline__ double exp_library(double x) { return exp(x); }
+#endif
+
 // sin and cos of the same argument in one call
 SPB_HD void sincos_(real x, real &s, real &c) {
 #if defined(__CUDA_ARCH__)
     if (!(fabs(x) < 1048576.0)) {
-        sincos(x, &s, &c);
+        sincos_library(x, &s, &c);
         return;
     }
     const int n = __double2int_rn(x * 0.6366197723675814);
@@ -250,7 +273,7 @@ SPB_HD void sincos_(real x, real &s, real &c) {
 // e^x
 SPB_HD real exp_(real x) {
 #if defined(__CUDA_ARCH__)
-    if (!(fabs(x) < 700.0)) return exp(x);
+    if (!(fabs(x) < 700.0)) return exp_library(x);
     const int k = __double2int_rn(x * 1.4426950408889634);
     const double fk = (double)k;
     double r = fma(fk, -0.6931471805599453, x);

@@ -226,6 +226,7 @@ SPB_FN int bknu_body(cplx z, real fnu, int kode, int n, Y y, real tol, real elim
             if (!(caz < tol)) {
                 cplx cz = (z * z) * real(0.25);
                 real t1s = real(0.25) * caz * caz;
+                SPB_NO_UNROLL
                 do {
                     f = (f * akk + p + q) * (real(1.0) / bk);
                     p = p * (real(1.0) / (akk - dnu));
@@ -246,6 +247,7 @@ SPB_FN int bknu_body(cplx z, real fnu, int kode, int n, Y y, real tol, real elim
         if (!(caz < tol)) {
             cplx cz = (z * z) * real(0.25);
             real t1s = real(0.25) * caz * caz;
+            SPB_NO_UNROLL
             do {
                 f = (f * akk + p + q) * (real(1.0) / bk);
                 p = p * (real(1.0) / (akk - dnu));
@@ -337,6 +339,7 @@ SPB_FN int bknu_body(cplx z, real fnu, int kode, int n, Y y, real tol, real elim
                     real ckr = caz + caz + real(2.0);
                     real p1r = 0.0, p2r = 1.0;
                     bool ok = false;
+                    SPB_NO_UNROLL
                     for (int i = 1; i <= kmax; ++i) {
                         real a = fhs / fks;
                         real cbr = ckr / (fk + real(1.0));
@@ -375,6 +378,7 @@ SPB_FN int bknu_body(cplx z, real fnu, int kode, int n, Y y, real tol, real elim
             p1 = cplx(0.0, 0.0);
             p2 = cplx(tol, 0.0);
             cplx cs = p2;
+            SPB_NO_UNROLL
             for (int i = 1; i <= k; ++i) {
                 real a1 = fks - fk;
                 // a = (fks + fk) / (a1 + fhs) and rak = 2 / (fk + 1) from ONE reciprocal (a division costs as
@@ -486,6 +490,7 @@ SPB_FN int bknu_body(cplx z, real fnu, int kode, int n, Y y, real tol, real elim
             if (regular) {
                 real p1r = CSRR(kflag);
                 real ascle = BRY(kflag);
+                SPB_NO_UNROLL
                 for (int i = inub; i <= inu; ++i) {
                     cplx st = s2;
                     s2 = ck * st + s1;
