@@ -49,7 +49,10 @@ __device__ __forceinline__ void kpass_point(const DevJob &job, const Scratch &s,
 
 // broadcast scalar order (v_stride = 0): the order-dependent phase factors are computed once per CTA and live in
 // shared memory, not in registers of the persistent loop
+template <int FAM, int KODE>
 __global__ void __launch_bounds__(128, SPB_KPASS_MINB) k_kpass(DevJob job, Scratch s) {
+    job.fam = FAM;  // compile-time family and scaling flag (dispatch_fam_kode)
+    job.kode = KODE;
     __shared__ spb::OrderPhase s_ph;
     if (threadIdx.x == 0) s_ph = spb::order_phase(__ldg(job.v));
     __syncthreads();
@@ -92,7 +95,10 @@ __global__ void __launch_bounds__(128, SPB_KPASS_MINB) k_kpass(DevJob job, Scrat
 
 // Per-element orders: batches of SORT_B points staged in shared memory and grouped by predicted work
 // (spb_dev.cuh) instead of the register pipeline above.
+template <int FAM, int KODE>
 __global__ void __launch_bounds__(128, SPB_KPASS_MINB) k_kpass_sorted(DevJob job, Scratch s) {
+    job.fam = FAM;
+    job.kode = KODE;
     __shared__ SortSmem sm;
     __shared__ unsigned int s_idx[SORT_B];
     __shared__ double2 s_z[SORT_B], s_it[SORT_B];
@@ -137,11 +143,27 @@ __global__ void __launch_bounds__(128, SPB_KPASS_MINB) k_kpass_sorted(DevJob job
     }
 }
 
+template <int FAM, int KODE>
+struct KpassLaunch {
+    static void run(const DevJob &job, const Scratch &s, int sms, cudaStream_t st) {
+        if (job.v_stride != 0 || job.n < 2)
+            k_kpass_sorted<FAM, KODE><<<resident_grid(k_kpass_sorted<FAM, KODE>, 128, sms), 128, 0, st>>>(job, s);
+        else
+            k_kpass<FAM, KODE><<<resident_grid(k_kpass<FAM, KODE>, 128, sms), 128, 0, st>>>(job, s);
+    }
+};
+// J and I never reach the K pass: their instantiations stay empty
+template <int KODE>
+struct KpassLaunch<spb::FAM_J, KODE> {
+    static void run(const DevJob &, const Scratch &, int, cudaStream_t) {}
+};
+template <int KODE>
+struct KpassLaunch<spb::FAM_I, KODE> {
+    static void run(const DevJob &, const Scratch &, int, cudaStream_t) {}
+};
+
 void launch_kpass(const DevJob &job, const Scratch &s, int sms, cudaStream_t st) {
-    if (job.v_stride != 0 || job.n < 2)
-        k_kpass_sorted<<<resident_grid(k_kpass_sorted, 128, sms), 128, 0, st>>>(job, s);
-    else
-        k_kpass<<<resident_grid(k_kpass, 128, sms), 128, 0, st>>>(job, s);
+    dispatch_fam_kode<KpassLaunch>(job.fam, job.kode, job, s, sms, st);
 }
 
 }  // namespace spbk

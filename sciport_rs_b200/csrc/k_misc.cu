@@ -4,8 +4,28 @@
 #include "spb_dev.cuh"
 #include "amos/spb_gamma.h"
 #include <chrono>
+#include <map>
+#include <mutex>
+#include <utility>
 
 namespace spbk {
+
+// Resident CTAs per SM of one kernel on the current device (cudaOccupancyMaxActiveBlocksPerMultiprocessor),
+// cached per (kernel, device, CTA size): persistent grids are sized from it on every launch.
+int resident_ctas_per_sm(const void *kernel, int threads) {
+    static std::mutex mu;
+    static std::map<std::pair<const void *, long long>, int> cache;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const std::pair<const void *, long long> key(kernel, ((long long)dev << 16) | threads);
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, threads, 0) != cudaSuccess || nb < 1) nb = 1;
+    cache[key] = nb;
+    return nb;
+}
 
 // ---------------------------------------------------------------- synthetic inputs
 __device__ __forceinline__ unsigned long long mix64(unsigned long long x) {

@@ -75,7 +75,11 @@ __device__ __forceinline__ unsigned int field_g(const Packed &p) {
     return (unsigned int)(p.w[1] >> (FIELD_BITS * 4)) & ((1u << FIELD_BITS) - 1u);
 }
 
+// FAM / KODE: the job's family and scaling flag as compile-time constants (dispatch_fam_kode)
+template <int FAM, int KODE>
 __global__ void __launch_bounds__(256) k_classify(DevJob job, Scratch s) {
+    job.fam = FAM;
+    job.kode = KODE;
     __shared__ unsigned int hist[NBINS];
     if (threadIdx.x < NBINS) hist[threadIdx.x] = 0;
     __syncthreads();
@@ -293,8 +297,15 @@ __global__ void __launch_bounds__(256) k_scatter(DevJob job, Scratch s) {
     for (unsigned int j = threadIdx.x; j < seg_total[2]; j += 256) s.glist[tile_base[BIN_GENERAL] + j] = stage[2][j];
 }
 
+template <int FAM, int KODE>
+struct ClassifyLaunch {
+    static void run(const DevJob &job, const Scratch &s, cudaStream_t st) {
+        k_classify<FAM, KODE><<<s.nblocks, 256, 0, st>>>(job, s);
+    }
+};
+
 void launch_classify(const DevJob &job, const Scratch &s, cudaStream_t st) {
-    k_classify<<<s.nblocks, 256, 0, st>>>(job, s);
+    dispatch_fam_kode<ClassifyLaunch>(job.fam, job.kode, job, s, st);
 }
 
 void launch_scan_scatter(const DevJob &job, const Scratch &s, cudaStream_t st) {
