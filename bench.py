@@ -363,7 +363,7 @@ def main():
             "frac": (achieved / fp64_peak) if achieved else None, "traffic": traffic_for(top["name"]),
             "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one launch, from the committed "
                             "ncu --set full capture (profiles/r1_traffic.json)",
-            "algorithmic_bytes": BYTES_PER_EVAL * pts * (1.5 if top["name"].endswith("kpass") else 1.0),
+            "algorithmic_bytes": BYTES_PER_EVAL * pts * (1.5 if top["name"].endswith(("kpass", "ipass_asyi")) else 1.0),
             "peak_source": "spb_fp64_peak DFMA microbenchmark on this GPU (MEASURED_PEAKS.json has no FP64 figure)",
             "flops_per_point": fpe, "points_per_launch": pts, "launch_ms": top["ms"],
             "share_of_step": top["ms"] / max(sum(r["ms"] for r in prof), 1e-9),

@@ -79,11 +79,15 @@ int spbo_bessel_sem(int fn, int kode, int sem, const double *v, int64_t v_stride
 // Same batch through the restructured flow the GPU kernels use (prepare / I pass /
 // K pass / finish); path[i] = 0 binned, 1 general from prepare, 2 general after a pass.
 int spbo_bessel_pipeline(int fn, int kode, const double *v, int64_t v_stride, const double *z, double *out,
-                         int32_t *ierr, int32_t *nz, int32_t *path, int64_t n, int threads) {
+                         int32_t *ierr, int32_t *nz, int32_t *path, int64_t n, int threads_and_mode) {
+    // bit 16 of the last argument: route points that need I and K in the large-|w| region of I through the
+    // fused routine (the flow of the fused region kernel)
+    const int threads = threads_and_mode & 0xffff;
+    const bool fuse = (threads_and_mode & 0x10000) != 0;
     parallel_for(n, threads, [=](int64_t lo, int64_t hi) {
         for (int64_t i = lo; i < hi; ++i) {
             int ie, nzz, pth;
-            cplx o = pipeline_eval(fn, cplx(z[2 * i], z[2 * i + 1]), v[i * v_stride], kode, ie, nzz, pth);
+            cplx o = pipeline_eval(fn, cplx(z[2 * i], z[2 * i + 1]), v[i * v_stride], kode, ie, nzz, pth, fuse);
             out[2 * i] = o.re;
             out[2 * i + 1] = o.im;
             if (ierr) ierr[i] = ie;
@@ -96,12 +100,16 @@ int spbo_bessel_pipeline(int fn, int kode, const double *v, int64_t v_stride, co
 
 // J and Y together through the FAM_JY flow (out_j, out_y as re,im pairs)
 int spbo_bessel_jy_pipeline(int kode, const double *v, int64_t v_stride, const double *z, double *out_j, double *out_y,
-                            int32_t *codes /* [4][n]: ierr_j, ierr_y, nz_j, nz_y */, int64_t n, int threads) {
+                            int32_t *codes /* [4][n]: ierr_j, ierr_y, nz_j, nz_y */, int64_t n,
+                            int threads_and_mode) {
+    const int threads = threads_and_mode & 0xffff;
+    const bool fuse = (threads_and_mode & 0x10000) != 0;  // as in spbo_bessel_pipeline
     parallel_for(n, threads, [=](int64_t lo, int64_t hi) {
         for (int64_t i = lo; i < hi; ++i) {
             cplx jv, yv;
             int je, jn, ye, yn, pth;
-            pipeline_eval_jy(cplx(z[2 * i], z[2 * i + 1]), v[i * v_stride], kode, jv, je, jn, yv, ye, yn, pth);
+            pipeline_eval_jy(cplx(z[2 * i], z[2 * i + 1]), v[i * v_stride], kode, jv, je, jn, yv, ye, yn, pth,
+                             fuse);
             out_j[2 * i] = jv.re;
             out_j[2 * i + 1] = jv.im;
             out_y[2 * i] = yv.re;

@@ -64,8 +64,10 @@ extern "C" {
 // ops[11]: classify(prepare), 6 ipass regions (region + its share of finish), kpass (+finish), general, and
 // pts[11] the number of points charged to each, following the kernel ids of include/sciport_b200.h
 // (0 classify, 2..5 ipass series/asyi/mlri/wrsk, 6 kpass, 7 general, 9 / 10 ipass uniform forms 1 / 2).
-int spbo_count_ops(int fam, int kode, const double *v, int64_t v_stride, const double *z, int64_t n, double *ops,
-                   int64_t *pts) {
+// fuse = 1: points that need I and K with I in the large-|w| region are charged, as one unit (fused routine +
+// finish), to the large-|w| region kernel, like the library does for a broadcast scalar order.
+int spbo_count_ops2(int fam, int kode, int fuse, const double *v, int64_t v_stride, const double *z, int64_t n,
+                    double *ops, int64_t *pts) {
     for (int k = 0; k < 11; ++k) {
         ops[k] = 0;
         pts[k] = 0;
@@ -74,7 +76,7 @@ int spbo_count_ops(int fam, int kode, const double *v, int64_t v_stride, const d
         cplx zz(counted(z[2 * i]), counted(z[2 * i + 1]));
         counted fnu(v[i * v_stride]);
         g_ops = 0;
-        Prep p = prepare(fam, zz, fnu, kode);
+        Prep p = prepare(fam, zz, fnu, kode, fuse != 0);
         uint64_t prep_ops = g_ops;
         ops[0] += prep_ops;
         pts[0] += 1;
@@ -84,14 +86,23 @@ int spbo_count_ops(int fam, int kode, const double *v, int64_t v_stride, const d
             bool general = (p.combine == CMB_GENERAL);
             cplx iv(0.0, 0.0), kv(0.0, 0.0), jv, yv;
             int inz = 0, knz = 0, e2, n2;
-            if (!general) {
+            if (!general && p.kreg == KREG_FUSED) {
+                g_ops = prep_ops;
+                if (fused_ik_region(p.w, fnu, kode, iv, inz, kv, knz, p.az) < 0 ||
+                    (knz != 0 && p.combine == CMB_Y_SHARED))
+                    general = true;
+                else
+                    finish_jy(p, zz, fnu, kode, iv, inz, kv, knz, jv, ierr, nz, yv, e2, n2);
+                ops[islot(IREG_ASYI)] += g_ops;
+                pts[islot(IREG_ASYI)] += 1;
+            } else if (!general) {
                 g_ops = prep_ops;
                 inz = ipass_region(p.ireg, p.w, fnu, kode, iv);
                 ops[islot(p.ireg)] += g_ops;
                 pts[islot(p.ireg)] += 1;
                 if (inz < 0) general = true;
             }
-            if (!general) {
+            if (!general && p.kreg != KREG_FUSED) {
                 g_ops = prep_ops;
                 knz = kpass_region(p.w, fnu, kode, kv);
                 if (knz < 0 || (knz != 0 && p.combine == CMB_Y_SHARED)) general = true;
@@ -118,7 +129,16 @@ int spbo_count_ops(int fam, int kode, const double *v, int64_t v_stride, const d
         cplx ival(0.0, 0.0), kval(0.0, 0.0);
         int inz = 0, knz = 0;
         bool handed = false;
-        if (p.ireg >= 0) {
+        if (p.kreg == KREG_FUSED) {
+            g_ops = prep_ops;
+            if (fused_ik_region(p.w, fnu, kode, ival, inz, kval, knz, p.az) < 0 ||
+                (knz != 0 && (p.combine == CMB_ACON || p.combine == CMB_Y_SHARED)))
+                handed = true;
+            else
+                finish(fam, p, zz, fnu, kode, ival, inz, kval, knz, ierr, nz);
+            ops[islot(IREG_ASYI)] += g_ops;
+            pts[islot(IREG_ASYI)] += 1;
+        } else if (p.ireg >= 0) {
             g_ops = prep_ops;  // the region kernel recomputes prepare()
             inz = ipass_region(p.ireg, p.w, fnu, kode, ival);
             if (inz < 0) handed = true;
@@ -144,6 +164,11 @@ int spbo_count_ops(int fam, int kode, const double *v, int64_t v_stride, const d
         }
     }
     return 0;
+}
+
+int spbo_count_ops(int fam, int kode, const double *v, int64_t v_stride, const double *z, int64_t n, double *ops,
+                   int64_t *pts) {
+    return spbo_count_ops2(fam, kode, 0, v, v_stride, z, n, ops, pts);
 }
 
 }  // extern "C"

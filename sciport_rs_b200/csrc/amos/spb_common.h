@@ -347,6 +347,31 @@ SPB_HD OrderPhase order_phase(real fnu) {
     return ph;
 }
 
+// Quantities of a right-half-plane point w that BOTH the large-|w| routine of I and the K routine use: where a
+// family needs I_v(w) and K_v(w) at the same point (analytic continuation, Y, the J/Y pair) the fused region
+// kernel computes them once and hands them to both routines; each routine computes the very same expressions
+// itself when called alone, so the fused and the separate paths round identically.
+struct WShared {
+    real raz;     // 1/|w|
+    cplx rcz;     // 1/w
+    cplx rsq;     // 1/sqrt(w) = conj(sqrt w)/|w|
+    real sn, cs;  // sin, cos of Im w
+    real em;      // exp(-Re w) when have_em
+    bool have_em;
+};
+SPB_HD cplx w_recip(cplx w, real raz) { return cplx(w.re * raz, -w.im * raz) * raz; }
+SPB_HD cplx w_rsqrt(cplx w, real az, real raz) { return conj(csqrt_mod(w, az)) * raz; }
+SPB_HD WShared w_shared(cplx w, real az, bool need_em) {
+    WShared s;
+    s.raz = real(1.0) / az;
+    s.rcz = w_recip(w, s.raz);
+    s.rsq = w_rsqrt(w, az, s.raz);
+    sincos_(w.im, s.sn, s.cs);
+    s.have_em = need_em;
+    s.em = need_em ? exp_(-w.re) : real(0.0);
+    return s;
+}
+
 }  // namespace spb
 
 namespace spb {

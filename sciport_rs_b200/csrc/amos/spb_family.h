@@ -40,6 +40,8 @@ enum Combine {
 
 // K-pass regions
 enum KRegion { KREG_SERIES = 0, KREG_MILLER = 1, KREG_HALF = 2, KREG_COUNT = 3 };
+// kreg of a point whose K_v(w) is evaluated together with I_v(w) by the fused large-|w| routine (no K bin)
+enum { KREG_FUSED = -2 };
 
 struct Prep {
     cplx w;       // right-half-plane evaluation point
@@ -145,7 +147,9 @@ SPB_HD bool prepare_geometry(int fam, cplx z, Prep &p) {
     return left;
 }
 
-SPB_FN Prep prepare(int fam, cplx z, real fnu, int kode) {
+// fuse: points that need I_v(w) AND K_v(w) with I in the large-|w| region get kreg = KREG_FUSED (one routine
+// evaluates both, sharing 1/w, 1/sqrt(w), the sincos of Im w and exp(-Re w)) instead of a K bin.
+SPB_FN Prep prepare(int fam, cplx z, real fnu, int kode, bool fuse = false) {
     const real fnul = SPB_FNUL, alim = SPB_ALIM, tol = SPB_TOL;
     Prep p;
     p.w = z;
@@ -204,6 +208,8 @@ SPB_FN Prep prepare(int fam, cplx z, real fnu, int kode) {
             p.combine = CMB_GENERAL;
             p.ireg = -1;
             p.kreg = -1;
+        } else if (fuse && p.ireg == IREG_ASYI) {
+            p.kreg = KREG_FUSED;
         }
     }
     return p;
@@ -227,14 +233,14 @@ SPB_FN Prep prepare_pass(int fam, cplx z) {
 // One region of the I pass.  Returns the AMOS nz (>= 0) or < 0 when the region
 // wants to hand over (-> general path).
 SPB_FN int ipass_region(int region, cplx w, real fnu, int kode, cplx &val, real az = real(-1.0),
-                        const OrderPhase *oph = nullptr) {
+                        const OrderPhase *oph = nullptr, const WShared *ws = nullptr) {
     const real tol = SPB_TOL, elim = SPB_ELIM, alim = SPB_ALIM, rl = SPB_RL;
     cplx y[1];
     y[0] = cplx(0.0, 0.0);
     int nw;
     switch (region) {
         case IREG_SERIES: nw = seri(w, fnu, kode, 1, y, tol, elim, alim, az); break;
-        case IREG_ASYI: nw = asyi(w, fnu, kode, 1, y, rl, tol, elim, alim, az, oph); break;
+        case IREG_ASYI: nw = asyi(w, fnu, kode, 1, y, rl, tol, elim, alim, az, oph, ws); break;
         case IREG_MLRI: nw = mlri(w, fnu, kode, 1, y, tol, az); break;
         case IREG_WRSK: nw = wrsk(w, fnu, kode, 1, y, tol, elim, alim, az); break;
         case IREG_UNI1:
@@ -255,10 +261,22 @@ SPB_FN int ipass_region(int region, cplx w, real fnu, int kode, cplx &val, real 
     return nw;
 }
 
-SPB_FN int kpass_region(cplx w, real fnu, int kode, cplx &val, real az = real(-1.0)) {
+SPB_FN int kpass_region(cplx w, real fnu, int kode, cplx &val, real az = real(-1.0), const WShared *ws = nullptr) {
     const real tol = SPB_TOL, elim = SPB_ELIM, alim = SPB_ALIM;
     // binned points stay on the middle scaling level (their pre-test is a no-op): the lean form of the routine
-    return bknu_simple(w, fnu, kode, val, tol, elim, alim, az);
+    return bknu_simple(w, fnu, kode, val, tol, elim, alim, az, ws);
+}
+
+// I_v(w) and K_v(w) of a KREG_FUSED point (large-|w| region of I): the quantities both routines need are
+// computed once.  Returns < 0 when either routine hands the point over to the general path.
+SPB_FN int fused_ik_region(cplx w, real fnu, int kode, cplx &ival, int &inz, cplx &kval, int &knz, real az,
+                           const OrderPhase *oph = nullptr) {
+    // exp(-Re w): factor of the unscaled K; the second exponential of I squares it
+    const WShared ws = w_shared(w, az, kode == 1);
+    inz = ipass_region(IREG_ASYI, w, fnu, kode, ival, az, oph, &ws);
+    if (inz < 0) return inz;
+    knz = kpass_region(w, fnu, kode, kval, az, &ws);
+    return knz < 0 ? knz : 0;
 }
 
 // continuation K(w e^{i pi mr}) from (K(w), I(w)) for one member (acon with n = 1)
@@ -497,8 +515,8 @@ SPB_FN cplx apply_semantics(int fam, cplx z, real fnu, int kode, cplx val, int i
 // Whole pipeline for one point, in the order the GPU runs it (prepare -> I pass
 // -> K pass -> finish, general path on any hand-over).  `path` reports which
 // route was taken: 0 binned, 1 general from prepare, 2 general after a pass.
-SPB_FN cplx pipeline_eval(int fam, cplx z, real fnu, int kode, int &ierr, int &nz, int &path) {
-    Prep p = prepare(fam, z, fnu, kode);
+SPB_FN cplx pipeline_eval(int fam, cplx z, real fnu, int kode, int &ierr, int &nz, int &path, bool fuse = false) {
+    Prep p = prepare(fam, z, fnu, kode, fuse);
     path = 1;
     if (p.combine == CMB_GENERAL) return general_eval(fam, z, fnu, kode, ierr, nz);
     if (p.combine == CMB_FINAL) {
@@ -519,7 +537,12 @@ SPB_FN cplx pipeline_eval(int fam, cplx z, real fnu, int kode, int &ierr, int &n
     cplx ival(0.0, 0.0), kval(0.0, 0.0);
     int inz = 0, knz = 0;
     path = 2;
-    if (p.ireg >= 0) {
+    if (p.kreg == KREG_FUSED) {
+        if (fused_ik_region(p.w, fnu, kode, ival, inz, kval, knz, p.az) < 0)
+            return general_eval(fam, z, fnu, kode, ierr, nz);
+        if (knz != 0 && (p.combine == CMB_ACON || p.combine == CMB_Y_SHARED))
+            return general_eval(fam, z, fnu, kode, ierr, nz);
+    } else if (p.ireg >= 0) {
         inz = ipass_region(p.ireg, p.w, fnu, kode, ival, p.az);
         if (inz < 0) return general_eval(fam, z, fnu, kode, ierr, nz);
     }
@@ -535,8 +558,8 @@ SPB_FN cplx pipeline_eval(int fam, cplx z, real fnu, int kode, int &ierr, int &n
 
 // J and Y together, in the order the GPU runs the FAM_JY pipeline.
 SPB_FN void pipeline_eval_jy(cplx z, real fnu, int kode, cplx &jv, int &jerr, int &jnz, cplx &yv, int &yerr,
-                             int &ynz, int &path) {
-    Prep p = prepare(FAM_JY, z, fnu, kode);
+                             int &ynz, int &path, bool fuse = false) {
+    Prep p = prepare(FAM_JY, z, fnu, kode, fuse);
     path = 1;
     cplx ival(0.0, 0.0), kval(0.0, 0.0);
     int inz = 0, knz = 0;
@@ -547,14 +570,20 @@ SPB_FN void pipeline_eval_jy(cplx z, real fnu, int kode, cplx &jv, int &jerr, in
         p.ireg = ireg;
         p.kreg = kreg;
     }
-    if (!general) {
+    if (!general && p.kreg == KREG_FUSED) {
         path = 2;
-        inz = ipass_region(p.ireg, p.w, fnu, kode, ival, p.az);
-        if (inz < 0) general = true;
-    }
-    if (!general) {
-        knz = kpass_region(p.w, fnu, kode, kval, p.az);
-        if (knz < 0 || (knz != 0 && p.combine == CMB_Y_SHARED)) general = true;
+        if (fused_ik_region(p.w, fnu, kode, ival, inz, kval, knz, p.az) < 0) general = true;
+        if (knz != 0 && p.combine == CMB_Y_SHARED) general = true;
+    } else {
+        if (!general) {
+            path = 2;
+            inz = ipass_region(p.ireg, p.w, fnu, kode, ival, p.az);
+            if (inz < 0) general = true;
+        }
+        if (!general) {
+            knz = kpass_region(p.w, fnu, kode, kval, p.az);
+            if (knz < 0 || (knz != 0 && p.combine == CMB_Y_SHARED)) general = true;
+        }
     }
     if (general) {
         jv = general_eval(FAM_J, z, fnu, kode, jerr, jnz);

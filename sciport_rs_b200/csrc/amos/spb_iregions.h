@@ -151,38 +151,40 @@ SPB_FN int seri(cplx z, real fnu, int kode, int n, Y y, real tol, real elim, rea
 // half an ulp of the leading sum once 2 Re z > 80 and is skipped there.
 template <class Y>
 SPB_FN int asyi(cplx z, real fnu, int kode, int n, Y y, real rl, real tol, real elim, real alim,
-                real az_known = real(-1.0), const OrderPhase *oph = nullptr) {
+                real az_known = real(-1.0), const OrderPhase *oph = nullptr, const WShared *ws = nullptr) {
     static const double RJ[48] = {
         0.0, 1.0, 1.0 / 2, 1.0 / 3, 1.0 / 4, 1.0 / 5, 1.0 / 6, 1.0 / 7, 1.0 / 8, 1.0 / 9, 1.0 / 10, 1.0 / 11,
         1.0 / 12, 1.0 / 13, 1.0 / 14, 1.0 / 15, 1.0 / 16, 1.0 / 17, 1.0 / 18, 1.0 / 19, 1.0 / 20, 1.0 / 21,
         1.0 / 22, 1.0 / 23, 1.0 / 24, 1.0 / 25, 1.0 / 26, 1.0 / 27, 1.0 / 28, 1.0 / 29, 1.0 / 30, 1.0 / 31,
         1.0 / 32, 1.0 / 33, 1.0 / 34, 1.0 / 35, 1.0 / 36, 1.0 / 37, 1.0 / 38, 1.0 / 39, 1.0 / 40, 1.0 / 41,
         1.0 / 42, 1.0 / 43, 1.0 / 44, 1.0 / 45, 1.0 / 46, 1.0 / 47};
-    const real rtpi = 0.159154943091895336;  // 1/(2 pi)
+    const real rt2pi = 0.398942280401432678;  // 1/sqrt(2 pi)
     real az = az_known >= real(0.0) ? az_known : cabs_(z);
     const real arm = real(1.0e3) * SPB_D1MACH1;
     const real rtr1 = sqrt(arm);
     int il = n < 2 ? n : 2;
     real dfnu = fnu + real(n - il);
-    // 1/z through the modulus (on scale for any |z| >= rl)
-    real raz = real(1.0) / az;
-    cplx rcz = cplx(z.re * raz, -z.im * raz) * raz;
-    // leading factor sqrt(1/(2 pi z)) * exp(z); Re(1/z) >= 0, modulus known
-    cplx ak1;
-    {
-        cplx a = rcz * rtpi;
-        real d = rtpi * raz;
-        real r = sqrt(real(0.5) * (d + a.re));
-        ak1 = cplx(r, a.im / (r + r));
-    }
+    // 1/z through the modulus (on scale for any |z| >= rl); ws: the quantities shared with the K routine
+    real raz = ws ? ws->raz : real(1.0) / az;
+    cplx rcz = ws ? ws->rcz : w_recip(z, raz);
+    // leading factor sqrt(1/(2 pi z)) * exp(z)
+    cplx ak1 = (ws ? ws->rsq : w_rsqrt(z, az, raz)) * rt2pi;
     cplx cz = z;
     if (kode == 2) cz.re = 0.0;
     if (rabs(cz.re) > elim) return -1;
+    real sny, csy;  // sin, cos of Im z: phase of exp(z) and, doubled, of the second exponential
+    if (ws) {
+        sny = ws->sn;
+        csy = ws->cs;
+    } else {
+        sincos_(z.im, sny, csy);
+    }
     real dnu2 = dfnu + dfnu;
     int koded = 1;
     if (!(rabs(cz.re) > alim && n > 2)) {
         koded = 0;
-        ak1 = ak1 * cexp_(cz);
+        real zm = exp_(cz.re);
+        ak1 = ak1 * cplx(zm * csy, zm * sny);
     }
     real fdn = 0.0;
     if (dnu2 > rtr1) fdn = dnu2 * dnu2;
@@ -213,7 +215,12 @@ SPB_FN int asyi(cplx z, real fnu, int kode, int n, Y y, real rl, real tol, real 
         if (z.im < real(0.0)) bk = -bk;
         p1 = cplx(ak, bk);
         if (inu % 2 != 0) p1 = -p1;
-        if (second) e2 = cexp_(z * real(-2.0));
+        if (second) {
+            // exp(-2z) = exp(-Re z)^2 (cos 2y - i sin 2y): the K routine needs the same exp(-Re z)
+            real em = (ws && ws->have_em) ? ws->em : exp_(-z.re);
+            real e2m = em * em;
+            e2 = cplx(e2m * ((csy - sny) * (csy + sny)), -e2m * ((sny + sny) * csy));
+        }
     }
     for (int k = 1; k <= il; ++k) {
         real sqk = fdn - real(1.0);

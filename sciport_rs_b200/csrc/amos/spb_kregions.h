@@ -140,7 +140,7 @@ SPB_FN int s1s2(cplx zr, cplx &s1, cplx &s2, real ascle, real alim, int &iuf) {
 // to the general path).  On the middle level every scaling factor is exactly 1, so both forms round identically.
 template <bool SIMPLE, class Y>
 SPB_FN int bknu_body(cplx z, real fnu, int kode, int n, Y y, real tol, real elim, real alim, real az_known,
-                     bool &noconv, bool &handover) {
+                     bool &noconv, bool &handover, const WShared *ws = nullptr) {
     const int kmax = 30;
     const real r1 = 2.0;
     const real dpi = SPB_PI;
@@ -166,8 +166,10 @@ SPB_FN int bknu_body(cplx z, real fnu, int kode, int n, Y y, real tol, real elim
     int nz = 0;
     int iflag = 0;
     int koded = kode;
-    real rcaz = real(1.0) / caz;
-    cplx rz = cplx(z.re * rcaz, -z.im * rcaz) * (rcaz + rcaz);
+    // ws: 1/|z|, 1/z, 1/sqrt(z), sincos(Im z), exp(-Re z) already computed for the I routine at the same point
+    // (fused I+K region kernel, |z| >= rl there): 2 (1/z) is the same number either way
+    real rcaz = ws ? ws->raz : real(1.0) / caz;
+    cplx rz = ws ? ws->rcz * real(2.0) : cplx(z.re * rcaz, -z.im * rcaz) * (rcaz + rcaz);
     int inu = (int)(fnu + real(0.5));
     real dnu = fnu - real(inu);
     real dnu2 = 0.0;
@@ -286,7 +288,7 @@ SPB_FN int bknu_body(cplx z, real fnu, int kode, int n, Y y, real tol, real elim
         // iflag=1: an underflow of exp(-z) is anticipated; proceed as kode=2 and test for
         // on-scale values during the forward recurrence
         // rthpi / sqrt(z) = rthpi conj(sqrt z) / |z|
-        coef = conj(csqrt_mod(z, caz)) * (rthpi * rcaz);
+        coef = (ws ? ws->rsq : w_rsqrt(z, caz, rcaz)) * rthpi;
         kflag = 2;
         if (koded != 2) {
             if (z.re > alim && SIMPLE) handover = true;
@@ -295,9 +297,14 @@ SPB_FN int bknu_body(cplx z, real fnu, int kode, int n, Y y, real tol, real elim
                 iflag = 1;
                 kflag = 2;
             } else {
-                real str = exp_(-z.re) * CSSR(kflag);
+                real str = ((ws && ws->have_em) ? ws->em : exp_(-z.re)) * CSSR(kflag);
                 real sn, cs;
-                sincos_(z.im, sn, cs);
+                if (ws) {
+                    sn = ws->sn;
+                    cs = ws->cs;
+                } else {
+                    sincos_(z.im, sn, cs);
+                }
                 cplx st(str * cs, -str * sn);
                 coef = coef * st;
             }
@@ -590,11 +597,12 @@ SPB_FN int bknu(cplx z, real fnu, int kode, int n, Y y, real tol, real elim, rea
 
 // K_fnu(z), one member, for a point of the binned K pass (see bknu_body).  Returns 0, or < 0: hand the point to
 // the general path (-2 no convergence, -9 the value left the middle scaling level).
-SPB_FN int bknu_simple(cplx z, real fnu, int kode, cplx &val, real tol, real elim, real alim, real az_known) {
+SPB_FN int bknu_simple(cplx z, real fnu, int kode, cplx &val, real tol, real elim, real alim, real az_known,
+                       const WShared *ws = nullptr) {
     bool noconv = false, handover = false;
     cplx y[1];
     y[0] = cplx(0.0, 0.0);
-    int nz = bknu_body<true>(z, fnu, kode, 1, y, tol, elim, alim, az_known, noconv, handover);
+    int nz = bknu_body<true>(z, fnu, kode, 1, y, tol, elim, alim, az_known, noconv, handover, ws);
     val = y[0];
     if (noconv) return -2;
     if (handover || nz != 0) return -9;

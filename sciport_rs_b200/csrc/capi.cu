@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -195,9 +196,26 @@ struct Prof {
 };
 
 // enqueue the whole pipeline for one chunk; returns number of kernel launches
-int enqueue_chunk(const DevJob &job, ScratchSet &ss, int sms, int flags, cudaStream_t st, Prof *pf = nullptr) {
+// SPB_FUSE (environment, read once): 0 never fuse, 1 (default) fuse for a broadcast scalar order, 2 always
+static int fuse_mode() {
+    static const int mode = [] {
+        const char *e = getenv("SPB_FUSE");
+        return e ? atoi(e) : 1;
+    }();
+    return mode;
+}
+
+int enqueue_chunk(const DevJob &job_in, ScratchSet &ss, int sms, int flags, cudaStream_t st, Prof *pf = nullptr) {
     Prof dummy;
     Prof &p = pf ? *pf : dummy;
+    DevJob job = job_in;
+    {
+        // families that need K: points with I in the large-|w| region take the fused I + K kernel.  With
+        // per-element orders the K pass groups its points by predicted work instead, which the fused walk cannot.
+        const bool ktype = !(job.fam == SPB_FN_J || job.fam == SPB_FN_I);
+        const int mode = fuse_mode();
+        job.fuse = (ktype && !(flags & SPB_PATH_MONOLITHIC) && (mode >= 2 || (mode == 1 && job.v_stride == 0))) ? 1 : 0;
+    }
     if (flags & SPB_PATH_MONOLITHIC) {
         p.mark(SPB_K_MONOLITHIC, st);
         launch_monolithic(job, st);

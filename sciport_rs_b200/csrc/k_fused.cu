@@ -1,0 +1,38 @@
+// k_fused.cu — fused I + K form of the large-|w| region kernel.
+//
+// Families that need I_v(w) AND K_v(w) at the same right-half-plane point (the J/Y pair and Y everywhere, K and
+// the Hankel functions where they are continued into the left half plane) spend most of a large-|z| batch in
+// the asymptotic region of I.  There both routines start from the same quantities — 1/w, 1/sqrt(w), the sincos
+// of Im w, exp(-Re w) — so one kernel evaluates I, K, the family combine and the store for such a point
+// (spb::fused_ik_region): no parked I(w), no second walk over the point, and the shared quantities once.
+// The classifier gives these points no K bin (spb::KREG_FUSED), so the K pass never sees them.
+#include "k_ipass.cuh"
+
+namespace spbk {
+
+template <int FAM, int KODE>
+struct FusedLaunch {
+    static void run(const DevJob &job, const Scratch &s, int sms, cudaStream_t st) {
+        if (job.v_stride == 0)
+            k_ipass<spb::IREG_ASYI, true, FAM, KODE>
+                <<<resident_grid(k_ipass<spb::IREG_ASYI, true, FAM, KODE>, 128, sms), 128, 0, st>>>(job, s);
+        else
+            k_ipass<spb::IREG_ASYI, false, FAM, KODE>
+                <<<resident_grid(k_ipass<spb::IREG_ASYI, false, FAM, KODE>, 128, sms), 128, 0, st>>>(job, s);
+    }
+};
+// J and I never need K
+template <int KODE>
+struct FusedLaunch<spb::FAM_J, KODE> {
+    static void run(const DevJob &, const Scratch &, int, cudaStream_t) {}
+};
+template <int KODE>
+struct FusedLaunch<spb::FAM_I, KODE> {
+    static void run(const DevJob &, const Scratch &, int, cudaStream_t) {}
+};
+
+void launch_fused(const DevJob &job, const Scratch &s, int sms, cudaStream_t st) {
+    dispatch_fam_kode<FusedLaunch>(job.fam, job.kode, job, s, sms, st);
+}
+
+}  // namespace spbk

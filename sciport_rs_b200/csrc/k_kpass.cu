@@ -34,17 +34,7 @@ __device__ __forceinline__ void kpass_point(const DevJob &job, const Scratch &s,
         s.glist[g] = (unsigned int)i;
         return;
     }
-    int ierr, nz;
-    if (job.fam == spb::FAM_JY) {
-        cplx jv, yv;
-        int yerr, ynz;
-        spb::finish_jy(p, z, v, job.kode, ival, inz, kval, knz, jv, ierr, nz, yv, yerr, ynz, ph);
-        store_point(job, i, jv, ierr, nz);
-        store_point2(job, i, yv, yerr, ynz);
-        return;
-    }
-    cplx val = spb::finish(job.fam, p, z, v, job.kode, ival, inz, kval, knz, ierr, nz, ph);
-    store_point(job, i, val, ierr, nz);
+    finish_store(job, p, i, z, v, ival, inz, kval, knz, ph);
 }
 
 // broadcast scalar order (v_stride = 0): the order-dependent phase factors are computed once per CTA and live in

@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(256) k_classify(DevJob job, Scratch s) {
             cplx z;
             double v;
             load_point(job, i, z, v);
-            spb::Prep p = spb::prepare(job.fam, z, v, job.kode);
+            spb::Prep p = spb::prepare(job.fam, z, v, job.kode, job.fuse != 0);
             unsigned int c;
             if (p.combine == spb::CMB_GENERAL || p.combine == spb::CMB_FINAL) {
                 // (CMB_FINAL: decided by prepare(); the general kernel stores it without running the drivers)

@@ -37,6 +37,22 @@ __device__ __forceinline__ void store_point2(const DevJob &j, long long i, cplx 
     note_error(j.first_err2, j.index_base + i, ierr);
 }
 
+// family combine (rotation, continuation with I(w), Hankel difference; for the JY pair both results) and store
+__device__ __forceinline__ void finish_store(const DevJob &job, const spb::Prep &p, long long i, cplx z, double v,
+                                             cplx ival, int inz, cplx kval, int knz, const spb::OrderPhase *ph) {
+    int ierr, nz;
+    if (job.fam == spb::FAM_JY) {
+        cplx jv, yv;
+        int yerr, ynz;
+        spb::finish_jy(p, z, v, job.kode, ival, inz, kval, knz, jv, ierr, nz, yv, yerr, ynz, ph);
+        store_point(job, i, jv, ierr, nz);
+        store_point2(job, i, yv, yerr, ynz);
+        return;
+    }
+    cplx val = spb::finish(job.fam, p, z, v, job.kode, ival, inz, kval, knz, ierr, nz, ph);
+    store_point(job, i, val, ierr, nz);
+}
+
 // Per-thread cache of the order-dependent phase factors: one sincos per DISTINCT order a thread meets.  With a
 // broadcast scalar order (v_stride = 0) it is filled once per thread; with per-element orders it is refilled
 // per point (one compare extra).  The cached value is exactly spb::order_phase(v), so results do not depend on

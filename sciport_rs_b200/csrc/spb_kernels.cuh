@@ -11,6 +11,7 @@ struct DevJob {
     int fam;   // spb::Family
     int kode;  // 1 | 2
     int sem;   // 0 raw AMOS, 1 scipy-compatible post-processing
+    int fuse;  // 1: points needing I and K with I in the large-|w| region are evaluated by the fused region kernel
     const double *v;
     long long v_stride;  // 0 = broadcast
     const double2 *z;    // complex input, or
@@ -101,6 +102,7 @@ inline void dispatch_fam_kode(int fam, int kode, A &&...a) {
 void launch_classify(const DevJob &job, const Scratch &s, cudaStream_t st);
 void launch_scan_scatter(const DevJob &job, const Scratch &s, cudaStream_t st);
 void launch_ipass(const DevJob &job, const Scratch &s, int region, int sms, cudaStream_t st);
+void launch_fused(const DevJob &job, const Scratch &s, int sms, cudaStream_t st);  // job.fuse: I + K, large-|w| region
 void launch_kpass(const DevJob &job, const Scratch &s, int sms, cudaStream_t st);
 int launch_general(const DevJob &job, const Scratch &s, int sms, cudaStream_t st);
 void launch_monolithic(const DevJob &job, cudaStream_t st);

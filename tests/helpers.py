@@ -41,7 +41,7 @@ def oracle_lib():
     return _oracle
 
 
-def cpu_bessel(fn, kode, v, z, sem=0, pipeline=False, threads=8):
+def cpu_bessel(fn, kode, v, z, sem=0, pipeline=False, threads=8, fuse=False):
     lib = oracle_lib()
     z = np.ascontiguousarray(z, dtype=np.complex128)
     v = np.ascontiguousarray(np.broadcast_to(np.asarray(v, dtype=np.float64), z.shape))
@@ -51,7 +51,7 @@ def cpu_bessel(fn, kode, v, z, sem=0, pipeline=False, threads=8):
     if pipeline:
         path = np.empty(z.shape, np.int32)
         lib.spbo_bessel_pipeline(FN[fn], kode, v.ctypes.data, 1, z.ctypes.data, out.ctypes.data, ierr.ctypes.data,
-                                 nz.ctypes.data, path.ctypes.data, z.size, threads)
+                                 nz.ctypes.data, path.ctypes.data, z.size, threads | (0x10000 if fuse else 0))
         return out, ierr, nz, path
     lib.spbo_bessel_sem(FN[fn], kode, sem, v.ctypes.data, 1, z.ctypes.data, out.ctypes.data, ierr.ctypes.data,
                         nz.ctypes.data, z.size, threads)
@@ -72,14 +72,14 @@ def cpu_bessel_seq(fn, kode, v, z, n_orders, threads=8, classic=False):
     return out, ierr, nz
 
 
-def cpu_bessel_jy(kode, v, z, threads=8):
+def cpu_bessel_jy(kode, v, z, threads=8, fuse=False):
     lib = oracle_lib()
     z = np.ascontiguousarray(z, dtype=np.complex128)
     v = np.ascontiguousarray(np.broadcast_to(np.asarray(v, dtype=np.float64), z.shape))
     oj, oy = np.empty_like(z), np.empty_like(z)
     codes = np.empty((4, z.size), np.int32)
     lib.spbo_bessel_jy_pipeline(kode, v.ctypes.data, 1, z.ctypes.data, oj.ctypes.data, oy.ctypes.data, codes.ctypes.data,
-                                z.size, threads)
+                                z.size, threads | (0x10000 if fuse else 0))
     return (oj, codes[0], codes[2]), (oy, codes[1], codes[3])
 
 

@@ -30,14 +30,17 @@ def gen(cfg, n, rng):
     return v, 10 ** rng.uniform(-3, 3, n) * np.exp(1j * np.pi * (2 * rng.random(n) - 1))
 
 
+@pytest.mark.parametrize("fuse", [False, True], ids=["separate", "fused"])
 @pytest.mark.parametrize("cfg", ["cfg2", "cfg3", "cfg4", "real", "wide", "far"])
 @pytest.mark.parametrize("fn", list(FN))
-def test_pipeline_matches_drivers(fn, cfg):
+def test_pipeline_matches_drivers(fn, cfg, fuse):
+    """fuse: points needing I and K in the large-|w| region of I go through the fused routine (shared 1/w,
+    1/sqrt(w), sincos(Im w), exp(-Re w)) like in the fused region kernel."""
     rng = np.random.default_rng(helpers.seed_of(fn, cfg))
     v, z = gen(cfg, 20000, rng)
     for kode in (1, 2):
         a, ia, na = helpers.cpu_bessel(fn, kode, v, z)
-        b, ib, nb, path = helpers.cpu_bessel(fn, kode, v, z, pipeline=True)
+        b, ib, nb, path = helpers.cpu_bessel(fn, kode, v, z, pipeline=True, fuse=fuse)
         assert np.array_equal(a.view(np.uint64), b.view(np.uint64))
         assert np.array_equal(ia, ib) and np.array_equal(na, nb)
     if cfg == "cfg2":
@@ -56,13 +59,14 @@ def test_golden_points_through_pipeline():
             assert same.all() and np.array_equal(ia, ib) and np.array_equal(na, nb)
 
 
+@pytest.mark.parametrize("fuse", [False, True], ids=["separate", "fused"])
 @pytest.mark.parametrize("cfg", ["cfg2", "cfg3", "cfg4", "real", "wide"])
-def test_jy_pair_matches_separate_drivers(cfg):
+def test_jy_pair_matches_separate_drivers(cfg, fuse):
     """The shared-I-pass J/Y pair must give exactly what the J and Y drivers give separately."""
     rng = np.random.default_rng(helpers.seed_of("jy", cfg))
     v, z = gen(cfg, 20000, rng)
     for kode in (1, 2):
-        (j, ej, nj), (y, ey, ny) = helpers.cpu_bessel_jy(kode, v, z)
+        (j, ej, nj), (y, ey, ny) = helpers.cpu_bessel_jy(kode, v, z, fuse=fuse)
         a, ia, na = helpers.cpu_bessel("J", kode, v, z)
         b, ib, nb = helpers.cpu_bessel("Y", kode, v, z)
         assert np.array_equal(j.view(np.uint64), a.view(np.uint64)) and np.array_equal(ej, ia) and np.array_equal(nj, na)

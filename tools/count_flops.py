@@ -35,20 +35,22 @@ def main():
     subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "libspb_flopcount.so"], check=True)
     lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "libspb_flopcount.so"))
     P = ctypes.c_void_p
-    lib.spbo_count_ops.argtypes = [ctypes.c_int, ctypes.c_int, P, ctypes.c_int64, P, ctypes.c_int64, P, P]
+    lib.spbo_count_ops2.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, P, ctypes.c_int64, P, ctypes.c_int64, P, P]
     out = {"_rule": "add/sub/mul/div/sqrt = 1, exp/log/sin/cos/atan/sinh/cosh = 30, pow = 60; per point, "
                     "prepare + region + finish", "_sample": {}}
     rng = np.random.default_rng(1)
-    samples = {"cfg2": (cfg2_sample(1 << 18), ("J", "Y", "JY"), 1),
-               "cfg3": (gen("cfg3", 1 << 17, rng), ("I", "K"), 2),
-               "cfg4": (gen("cfg4", 1 << 17, rng), ("H1", "H2"), 1)}
-    for cfg, ((v, z), fams, kode) in samples.items():
+    # last field: fused I + K in the large-|w| region (the library's choice for a broadcast scalar order)
+    samples = {"cfg2": (cfg2_sample(1 << 18), ("J", "Y", "JY"), 1, 1),
+               "cfg3": (gen("cfg3", 1 << 17, rng), ("I", "K"), 2, 0),
+               "cfg4": (gen("cfg4", 1 << 17, rng), ("H1", "H2"), 1, 1)}
+    for cfg, ((v, z), fams, kode, fuse) in samples.items():
         v = np.ascontiguousarray(v, dtype=np.float64)
         z = np.ascontiguousarray(z, dtype=np.complex128)
         for fn in fams:
             ops = np.zeros(11)
             pts = np.zeros(11, np.int64)
-            lib.spbo_count_ops(FN[fn], kode, v.ctypes.data, 1, z.ctypes.data, z.size, ops.ctypes.data, pts.ctypes.data)
+            lib.spbo_count_ops2(FN[fn], kode, fuse, v.ctypes.data, 1, z.ctypes.data, z.size, ops.ctypes.data,
+                                pts.ctypes.data)
             total = ops[2:8].sum() + ops[9:11].sum() + ops[0]
             for k in range(11):
                 if pts[k]:
@@ -56,7 +58,7 @@ def main():
                     out[key] = {"flops_per_point": ops[k] / pts[k], "points": int(pts[k])}
             key = f"{fn}/per_eval" if cfg == "cfg2" else f"{cfg}:{fn}/per_eval"
             out[key] = {"flops_per_point": total / z.size, "points": int(z.size)}
-            out["_sample"][f"{cfg}:{fn}"] = f"{z.size} points, kode={kode}"
+            out["_sample"][f"{cfg}:{fn}"] = f"{z.size} points, kode={kode}, fused I+K in the large-|w| region: {bool(fuse)}"
     os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
     with open(os.path.join(ROOT, "profiles", "flops_per_eval.json"), "w") as f:
         json.dump(out, f, indent=1)
