@@ -213,6 +213,27 @@ __global__ void __launch_bounds__(256) k_scatter(DevJob job, Scratch s) {
         valid = (int)(job.n - base);
         for (int k = 0; k < valid; ++k) cls8 |= (unsigned long long)s.cls[base + k] << (8 * k);
     }
+    // Homogeneous tile (every point in the same class: the rule on gridded inputs, where 2048 consecutive points
+    // are neighbours): the sorted order is the index order, so the indices are written straight out.
+    {
+        const long long tile0 = (long long)blockIdx.x * TILE;
+        const unsigned int c0 = s.cls[tile0];
+        const unsigned long long rep = 0x0101010101010101ull * c0;
+        const bool same = valid == 8 ? (cls8 == rep) : (((cls8 ^ rep) & ((1ull << (8 * valid)) - 1ull)) == 0ull);
+        if (__syncthreads_and(same)) {  // (also orders the tile_base[] writes before their use)
+            int bi, bk;
+            bool gen;
+            point_bins(c0, bi, bk, gen);
+            const unsigned int m = (unsigned int)min((long long)TILE, job.n - tile0);
+            for (unsigned int j = threadIdx.x; j < m; j += 256) {
+                const unsigned int idx = (unsigned int)(tile0 + j);
+                if (bi != 7) s.perm_i[tile_base[bi] + j] = idx;
+                if (bk != 3) s.perm_k[tile_base[BIN_K0 + bk] + j] = idx;
+                if (gen) s.glist[tile_base[BIN_GENERAL] + j] = idx;
+            }
+            return;
+        }
+    }
     Packed mine;
     mine.clear();
 #pragma unroll

@@ -495,3 +495,59 @@ def test_calls_on_different_streams_share_scratch_safely(special):
         assert torch.equal(b.view(torch.float64), ref_j.view(torch.float64))
     host, _, _ = special.bessel("K", v, z, scaled=True)  # a host-buffer call right behind queued device work
     assert np.array_equal(host.view(np.uint64), to_np(ref_k).view(np.uint64))
+
+
+@pytest.mark.parametrize("order", [0.0, 0.3, 2.5, 7.25, 30.0])
+@pytest.mark.parametrize("fn", ["Y", "K", "H1", "H2"])
+def test_fused_large_w_kernel_scalar_order(special, fn, order):
+    """A broadcast scalar order sends every point that needs I_v(w) and K_v(w) with I in the large-|w| region
+    through the fused I + K kernel (k_fused.cu); per-element orders take the separate I and K passes.  Both must
+    match the CPU oracle, agree with each other to rounding and report identical codes."""
+    for cfg in ("cfg2", "cfg4", "far"):
+        rng = np.random.default_rng(helpers.seed_of("fused", fn, cfg, str(order)))
+        _, z = gen(cfg, 100000, rng)
+        v = np.full(z.shape, order)
+        zt = torch.from_numpy(z).cuda()
+        for kode in (1, 2):
+            got, ierr, nz = special.bessel(fn, order, zt, scaled=(kode == 2))  # scalar order: fused kernel
+            sep, ierr_s, nz_s = special.bessel(fn, torch.from_numpy(v).cuda(), zt, scaled=(kode == 2))
+            assert torch.equal(ierr, ierr_s) and torch.equal(nz, nz_s)
+            g, s = to_np(got), to_np(sep)
+            want, ierr_c, nz_c = helpers.cpu_bessel(fn, kode, v, z)
+            cname = {"Y": "J", "K": "I", "H1": "J", "H2": "J"}[fn]
+            weight = {"Y": 1, "K": np.pi, "H1": 1, "H2": 1}[fn]
+            where = {"Y": True, "K": z.real < 0, "H1": z.imag < 0, "H2": z.imag > 0}[fn]
+            comp = np.abs(helpers.cpu_bessel(cname, kode, v, z)[0]) * weight
+            scale = np.maximum(np.abs(want), np.where(np.isfinite(comp) & where, comp, 0))
+            okv = (ierr_c == 0) & (nz_c == 0)
+            # the north star's 1e-13 on the BASELINE orders; higher scalar orders and the adversarial distribution
+            # carry the algorithm's own conditioning term (see so.tolerance: two correct implementations differ by
+            # a few eps max(|z|, v); measured here 1.6e-13 at v = 30, z = -71.3+0.39i, both 1e-13 from mpmath)
+            tol = so.tolerance(want, z, v, conditioning=16.0 if (cfg == "far" or order > 2.5) else 0.0)
+            bad = okv & (so.mismatch(g, want, scale) > tol)
+            assert not bad.any(), f"{cfg} kode={kode}: {bad.sum()} mismatches, first z={z[bad][0]}"
+            assert not (okv & (so.mismatch(g, s, scale) > tol)).any()
+            diff = (to_np(ierr) != ierr_c) | (to_np(nz) != nz_c)
+            assert diff.sum() <= 2
+
+
+def test_compaction_of_homogeneous_and_ragged_tiles(special):
+    """Tiles whose 2048 points share one class are compacted by the straight index write-out of k_scatter, mixed
+    tiles by the staged scan: a batch made of long constant runs, one mixed stretch and a ragged tail must come
+    back in the original order either way."""
+    rng = np.random.default_rng(5)
+    runs = [np.full(5000, 150.0 + 20.0j), np.full(4096, 0.5 - 0.25j), np.full(3000, -40.0 + 3.0j)]
+    _, mixed = gen("cfg4", 6000, rng)
+    z = np.concatenate(runs[:2] + [mixed] + runs[2:] + [np.full(777, 9.0 + 9.0j)])
+    zt = torch.from_numpy(z).cuda()
+    for fn in ("J", "Y", "K"):
+        got, ierr, nz = special.bessel(fn, 2.5, zt)
+        want, ierr_c, nz_c = helpers.cpu_bessel(fn, 1, 2.5, z)
+        comp = np.abs(helpers.cpu_bessel({"J": "Y", "Y": "J", "K": "I"}[fn], 1, 2.5, z)[0]) * (np.pi if fn == "K" else 1)
+        scale = np.maximum(np.abs(want), np.where(np.isfinite(comp), comp, 0))
+        okv = (ierr_c == 0) & (nz_c == 0)
+        assert np.array_equal(to_np(ierr), ierr_c) and np.array_equal(to_np(nz), nz_c)
+        assert np.all(so.mismatch(to_np(got), want, scale)[okv] <= so.tolerance(want, z, np.full(z.shape, 2.5))[okv])
+    (j, _, _), (y, _, _) = special.bessel_jy(2.5, zt)
+    a, _, _ = special.bessel("J", 2.5, zt)
+    assert np.all(np.abs(to_np(j) - to_np(a)) <= 1e-13 * np.maximum(np.abs(to_np(a)), np.abs(to_np(y))))
