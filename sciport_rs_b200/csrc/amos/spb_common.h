@@ -361,11 +361,41 @@ struct WShared {
 };
 SPB_HD cplx w_recip(cplx w, real raz) { return cplx(w.re * raz, -w.im * raz) * raz; }
 SPB_HD cplx w_rsqrt(cplx w, real az, real raz) { return conj(csqrt_mod(w, az)) * raz; }
+#if defined(__CUDA_ARCH__)
+// Branch-free reciprocal and reciprocal square root for arguments known to be on scale (the fused region has
+// 21.78 <= |w| < 32767): hardware seed (about 20 bits) and one third-order correction, error below 1 ulp.  The
+// library forms carry a slow-path branch each, which also keeps the compiler from scheduling the independent
+// exp / sincos arithmetic across them.
+__device__ __forceinline__ double rcp_onscale(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-x, y, 1.0);
+    return fma(y, fma(e, e, e), y);  // y (1 + e + e^2)
+}
+__device__ __forceinline__ double rsqrt_onscale(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-x * y, y, 1.0);              // 1 - x y^2
+    return fma(y, e * fma(0.375, e, 0.5), y);          // y (1 + e/2 + 3 e^2/8)
+}
+#endif
 SPB_HD WShared w_shared(cplx w, real az, bool need_em) {
     WShared s;
+#if defined(__CUDA_ARCH__)
+    s.raz = rcp_onscale(az);
+    s.rcz = w_recip(w, s.raz);
+    // 1/sqrt(w) = conj(sqrt w)/|w| with sqrt w = (r, Im w/(2r)), r = sqrt((|w| + Re w)/2), Re w >= 0: through
+    // 1/r, so no division and no second square root
+    const double t = 0.5 * (az + w.re);
+    const double ri = rsqrt_onscale(t);
+    double r = t * ri;
+    r = fma(fma(-r, r, t), 0.5 * ri, r);
+    s.rsq = cplx(r * s.raz, -(w.im * (0.5 * ri)) * s.raz);
+#else
     s.raz = real(1.0) / az;
     s.rcz = w_recip(w, s.raz);
     s.rsq = w_rsqrt(w, az, s.raz);
+#endif
     sincos_(w.im, s.sn, s.cs);
     s.have_em = need_em;
     s.em = need_em ? exp_(-w.re) : real(0.0);

@@ -12,7 +12,7 @@ namespace spbk {
 #endif
 #define SPB_IPASS_MINB(R) ((R) == 1 ? SPB_IPASS_MINB_ASYI : 1)
 #ifndef SPB_FUSED_MINB
-#define SPB_FUSED_MINB 4
+#define SPB_FUSED_MINB 5
 #endif
 
 // one point of the I pass: I_v(w) by the region routine; J / I families finish here, the others park I(w)
