@@ -236,10 +236,11 @@ static __device__ __noinline__ void sincos_library(double x, double *s, double *
 static __device__ __noinline__ double exp_library(double x) { return exp(x); }
 #endif
 
-// sin and cos of the same argument in one call
+// sin and cos of the same argument in one call.  BOUNDED: the caller guarantees |x| < 2^20 (no fallback branch)
+template <bool BOUNDED = false>
 SPB_HD void sincos_(real x, real &s, real &c) {
 #if defined(__CUDA_ARCH__)
-    if (!(fabs(x) < 1048576.0)) {
+    if (!BOUNDED && !(fabs(x) < 1048576.0)) {
         sincos_library(x, &s, &c);
         return;
     }
@@ -273,7 +274,10 @@ SPB_HD void sincos_(real x, real &s, real &c) {
 // e^x
 SPB_HD real exp_(real x) {
 #if defined(__CUDA_ARCH__)
-    if (!(fabs(x) < 700.0)) return exp_library(x);
+    // branch-free over the whole range: beyond the limits the argument is pinned where the result is already 0 or
+    // inf, and the power of two is applied in two exact halves (so the scale never leaves the exponent range)
+    x = x < -746.0 ? -746.0 : x;  // (comparisons, not fmin / fmax: a NaN passes through and comes out as NaN)
+    x = x > 710.0 ? 710.0 : x;
     const int k = __double2int_rn(x * 1.4426950408889634);
     const double fk = (double)k;
     double r = fma(fk, -0.6931471805599453, x);
@@ -282,8 +286,10 @@ SPB_HD real exp_(real x) {
 #pragma unroll
     for (int j = 1; j < 12; ++j) p = fma(p, r, fm::EXPC[j]);
     p = fma(p * r, r, r);  // r + r^2 (1/2 + ...)
-    const double scale = __longlong_as_double((long long)(1023 + k) << 52);
-    return fma(p, scale, scale);
+    const int k1 = k >> 1, k2 = k - k1;
+    const double s1 = __longlong_as_double((long long)(1023 + k1) << 52);
+    const double s2 = __longlong_as_double((long long)(1023 + k2) << 52);
+    return fma(p, s1, s1) * s2;
 #else
     return exp(x);
 #endif
@@ -335,7 +341,7 @@ SPB_HD OrderPhase order_phase(real fnu) {
     ph.inu = (int)fnu;
     int ir = ph.inu & 1;
     real a = (fnu - real(ph.inu - ir)) * real(SPB_HPI);
-    sincos_(a, ph.sh, ph.ch);
+    sincos_<true>(a, ph.sh, ph.ch);  // 0 <= a < pi
     real c2 = ph.ch * ph.ch - ph.sh * ph.sh;
     real s2 = (ph.sh + ph.sh) * ph.ch;
     if (ir) {
@@ -352,6 +358,7 @@ SPB_HD OrderPhase order_phase(real fnu) {
 // kernel computes them once and hands them to both routines; each routine computes the very same expressions
 // itself when called alone, so the fused and the separate paths round identically.
 struct WShared {
+    real az;      // |w|
     real raz;     // 1/|w|
     cplx rcz;     // 1/w
     cplx rsq;     // 1/sqrt(w) = conj(sqrt w)/|w|
@@ -379,10 +386,21 @@ __device__ __forceinline__ double rsqrt_onscale(double x) {
     return fma(y, e * fma(0.375, e, 0.5), y);          // y (1 + e/2 + 3 e^2/8)
 }
 #endif
+// az < 0: the modulus is not known yet (fused region kernel: |w| and 1/|w| come out of one reciprocal square root)
 SPB_HD WShared w_shared(cplx w, real az, bool need_em) {
     WShared s;
 #if defined(__CUDA_ARCH__)
-    s.raz = rcp_onscale(az);
+    if (az < real(0.0)) {
+        const double m2 = fma(w.re, w.re, w.im * w.im);
+        const double mi = rsqrt_onscale(m2);
+        double m = m2 * mi;
+        m = fma(fma(-m, m, m2), 0.5 * mi, m);
+        az = m;
+        s.raz = fma(mi, fma(-m, mi, 1.0), mi);  // 1/|w| from the seed 1/sqrt(|w|^2), one correction
+    } else {
+        s.raz = rcp_onscale(az);
+    }
+    s.az = az;
     s.rcz = w_recip(w, s.raz);
     // 1/sqrt(w) = conj(sqrt w)/|w| with sqrt w = (r, Im w/(2r)), r = sqrt((|w| + Re w)/2), Re w >= 0: through
     // 1/r, so no division and no second square root
@@ -391,12 +409,15 @@ SPB_HD WShared w_shared(cplx w, real az, bool need_em) {
     double r = t * ri;
     r = fma(fma(-r, r, t), 0.5 * ri, r);
     s.rsq = cplx(r * s.raz, -(w.im * (0.5 * ri)) * s.raz);
+    sincos_<true>(w.im, s.sn, s.cs);  // |Im w| <= |w| < 32767 for every binned point
 #else
+    if (az < real(0.0)) az = cabs_(w);
+    s.az = az;
     s.raz = real(1.0) / az;
     s.rcz = w_recip(w, s.raz);
     s.rsq = w_rsqrt(w, az, s.raz);
-#endif
     sincos_(w.im, s.sn, s.cs);
+#endif
     s.have_em = need_em;
     s.em = need_em ? exp_(-w.re) : real(0.0);
     return s;

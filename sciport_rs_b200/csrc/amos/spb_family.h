@@ -217,14 +217,14 @@ SPB_FN Prep prepare(int fam, cplx z, real fnu, int kode, bool fuse = false) {
 
 // prepare() for a point the classifier has already binned: the region tests are known to have passed, so only
 // the geometry and the modulus are recomputed.  has_i = the class byte carries an I bin.
-SPB_FN Prep prepare_pass(int fam, cplx z) {
+SPB_FN Prep prepare_pass(int fam, cplx z, bool with_modulus = true) {
     Prep p;
     p.w = z;
     p.combine = CMB_GENERAL;
     p.kreg = -1;
     p.ierr = 0;
     p.mr = 0;
-    p.az = cabs_(z);
+    p.az = with_modulus ? cabs_(z) : real(-1.0);  // (the fused routine computes |w| with its reciprocal)
     // a binned point carries an I bin exactly when its geometry needs I(w) (prepare() sets ireg under `left`)
     p.ireg = prepare_geometry(fam, z, p) ? 0 : -1;  // the passes only ask whether I(w) exists
     return p;
@@ -272,10 +272,11 @@ SPB_FN int kpass_region(cplx w, real fnu, int kode, cplx &val, real az = real(-1
 SPB_FN int fused_ik_region(cplx w, real fnu, int kode, cplx &ival, int &inz, cplx &kval, int &knz, real az,
                            const OrderPhase *oph = nullptr) {
     // exp(-Re w): factor of the unscaled K; the second exponential of I squares it
+    // (az < 0: |w| not computed yet, see w_shared)
     const WShared ws = w_shared(w, az, kode == 1);
-    inz = ipass_region(IREG_ASYI, w, fnu, kode, ival, az, oph, &ws);
+    inz = ipass_region(IREG_ASYI, w, fnu, kode, ival, ws.az, oph, &ws);
     if (inz < 0) return inz;
-    knz = kpass_region(w, fnu, kode, kval, az, &ws);
+    knz = kpass_region(w, fnu, kode, kval, ws.az, &ws);
     return knz < 0 ? knz : 0;
 }
 

@@ -21,7 +21,7 @@ template <int REGION, bool FUSED = false>
 __device__ __forceinline__ void ipass_point(const DevJob &job, const Scratch &s, long long i, cplx z, double v,
                                             const spb::OrderPhase *ph) {
     // the classifier has already established region and simplicity of this point: geometry only
-    spb::Prep p = spb::prepare_pass(job.fam, z);
+    spb::Prep p = spb::prepare_pass(job.fam, z, !FUSED);
     if (FUSED) {
         cplx ival, kval;
         int inz = 0, knz = 0;
