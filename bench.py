@@ -57,12 +57,14 @@ def max_over_ranks(value, device=None):
 
 def traffic_for(kernel_name):
     """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/)."""
-    sass = {"kpass": "k_kpass(DevJob, Scratch)", "ipass_asyi": "void k_ipass<1>(DevJob, Scratch)",
-            "ipass_mlri": "void k_ipass<2>(DevJob, Scratch)", "classify": "k_classify(DevJob, Scratch)"}
+    # kernel names as ncu prints them (template arguments: region, scalar order, family, kode)
+    prefix = {"kpass": "void k_kpass<", "ipass_asyi": "void k_ipass<1,", "ipass_mlri": "void k_ipass<2,",
+              "classify": "void k_classify<"}
     try:
         with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
             t = json.load(f)["kernels"]
-        rec = t[sass[kernel_name.split("/")[-1]]]
+        want = prefix[kernel_name.split("/")[-1]]
+        rec = next(v for k, v in t.items() if k.startswith(want))
         return rec["dram_read_bytes"] + rec["dram_write_bytes"]
     except Exception:
         return None

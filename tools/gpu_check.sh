@@ -15,7 +15,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1 > gpurun_out/ncu_launch_${tag}.log 2>&1
 echo "ncu launch list rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:'k_kpass|k_ipass|k_classify|k_scatter|k_scan' \
-    --launch-skip 33 --launch-count 11 -o gpurun_out/full_${tag} -f \
+    --launch-skip 30 --launch-count 10 -o gpurun_out/full_${tag} -f \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --e2e-steps 1 > gpurun_out/ncu_full_${tag}.log 2>&1
 echo "ncu full rc=$?"
 ls -la gpurun_out | tail -12

@@ -67,12 +67,18 @@ def main():
                               "time_us": float(r[1])}
     json.dump({"_source": f"ncu --set full capture {os.path.basename(rep)} (per launch, cfg2 bench step)",
                "kernels": traffic}, open(os.path.join(prof, f"{pre}_traffic.json"), "w"), indent=1)
-    for kern, obj, mangled in (("k_kpass", "k_kpass.o", "k_kpass"), ("k_ipass", "k_ipass.o", "k_ipassILi1E")):
-        block = "0" if kern == "k_kpass" else "1"
+    # source-level views of the dominant kernels of the cfg2 step: the fused I+K kernel of the large-|w| region
+    # (second k_ipass launch of a step) and the classifier; hot lines (ncu_hot) and cost by inline call path (ncu_tree)
+    build = os.path.join(ROOT, "sciport_rs_b200", "csrc", "build")
+    for kern, obj, mangled, launch, label in (("k_ipass", "k_fused.o", "k_ipassILi1ELb1ELi6ELi1", 1, "fused_asyi_k"),
+                                              ("k_classify", "k_pipeline.o", "k_classifyILi6ELi1", 0, "classify")):
         out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_hot.py"), rep, kern, "30",
-                              os.path.join(ROOT, "sciport_rs_b200", "csrc", "build", obj), block, mangled],
+                              os.path.join(build, obj), str(launch), mangled], capture_output=True, text=True).stdout
+        open(os.path.join(prof, f"{pre}_hot_{label}.txt"), "w").write(out)
+        out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_tree.py"), rep, kern,
+                              os.path.join(build, obj), mangled, "5", str(2 * launch), "0.015"],
                              capture_output=True, text=True).stdout
-        open(os.path.join(prof, f"{pre}_hot_{mangled}.txt"), "w").write(out)
+        open(os.path.join(prof, f"{pre}_tree_{label}.txt"), "w").write(out)
     print("profiles written")
 
 
