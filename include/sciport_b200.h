@@ -137,6 +137,10 @@ int spb_clgamma(const spb_c128 *z, spb_c128 *out, int64_t n, const spb_exec *ex)
 /* ---- sinc, special::sinc (trig.rs:4-13): sin(pi x)/(pi x), 1 at x = 0 ---------------------- */
 int spb_sinc(const double *x, double *out, int64_t n, const spb_exec *ex);
 
+/* ---- the device transcendentals of the region kernels, exported for accuracy tests only (no reference
+ * counterpart): which = 0 exp(x), 1 exp(-x) (second member of the exp pair), 2 sin(x), 3 cos(x) ------------ */
+int spb_devmath(int which, const double *x, double *out, int64_t n, const spb_exec *ex);
+
 /* ---- windows built on the path (the batched in-tree consumers) -------------------------------------
  * spb_kaiser: signal::windows::kaiser(m, beta, sym) (fir_filter_design/windows.rs:540-558): argument generation,
  * I_0 through the complex routine, division by I_0(beta) and modulus fused in one pass; out has m doubles.

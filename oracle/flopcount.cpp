@@ -52,6 +52,14 @@ inline int expo_(counted a) {
     return (int)((t.u >> 52) & 0x7ffull);
 }
 inline counted neg_(counted a) { return counted(-a.v); }
+// e^x and e^-x from one argument reduction (spb::exp_pair): charged as ONE exponential plus the two combining
+// additions, which is what the kernels spend on it
+#define SPB_EXP_PAIR_HOOK 1
+inline void exp_pair_hook(counted x, counted &ep, counted &em) {
+    g_ops += 32;
+    ep = counted(std::exp(x.v));
+    em = counted(std::exp(-x.v));
+}
 #define SPB_REAL counted
 #include "../sciport_rs_b200/csrc/amos/spb_family.h"
 

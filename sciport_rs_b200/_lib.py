@@ -48,6 +48,7 @@ def _load():
     lib.spb_airy.argtypes = [I, I, P, P, P, P, L, EX]
     for name in ("spb_gamma", "spb_lgamma", "spb_cgamma", "spb_clgamma", "spb_sinc"):
         getattr(lib, name).argtypes = [P, P, L, EX]
+    lib.spb_devmath.argtypes = [I, P, P, L, EX]
     lib.spb_kaiser.argtypes = [L, ctypes.c_double, I, P, EX]
     lib.spb_lanczos.argtypes = [L, I, P, EX]
     lib.spb_first_error.argtypes = [P, L, ctypes.POINTER(L), ctypes.POINTER(ctypes.c_int32), EX]
@@ -64,7 +65,7 @@ def _load():
 
 EXPORTS = [
     "spb_bessel", "spb_bessel_jy", "spb_bessel_real", "spb_airy", "spb_gamma", "spb_lgamma", "spb_cgamma", "spb_clgamma",
-    "spb_sinc", "spb_kaiser", "spb_lanczos", "spb_first_error", "spb_last_first_error", "spb_synth", "spb_fp64_peak", "spb_last_timing", "spb_last_profile", "spb_device_count",
+    "spb_sinc", "spb_devmath", "spb_kaiser", "spb_lanczos", "spb_first_error", "spb_last_first_error", "spb_synth", "spb_fp64_peak", "spb_last_timing", "spb_last_profile", "spb_device_count",
     "spb_version", "spb_last_error",
 ]
 

@@ -212,8 +212,8 @@ SPB_HD cplx csqrt_mod(cplx a, real d) {
 // exp and sincos account for 15-30 % of the instructions of the hot region kernels.  The library versions
 // materialise every polynomial coefficient with two moves before the DFMA that uses it and carry slow-path
 // calls for huge arguments; the versions below keep the coefficients in constant memory (a DFMA reads them as
-// constant-bank operands), reduce with fused multiply-adds (three-part pi/2, two-part ln 2) and fall back to the
-// library outside the range the region kernels produce (|x| >= 2^20 for sincos, |x| >= 700 for exp).  The
+// constant-bank operands), reduce with fused multiply-adds (three-part pi/2, two-part ln 2); sincos falls back
+// to the library for |x| >= 2^20 (unless the caller guarantees the range), exp is branch-free (see exp_pair).  The
 // coefficient tables are generated by tools/gen_tables.py (Chebyshev fits of (sin r / r - 1) / r^2 and
 // (cos r - 1 + r^2/2) / r^4 on |r| <= pi/4, Taylor coefficients of exp); measured error <= 1.6 ulp.
 #if defined(__CUDACC__)
@@ -224,16 +224,16 @@ static __constant__ double SINC[7] = {-7.58549250782124013e-13, 1.60585109795353
 static __constant__ double COSC[7] = {4.74520215570235880e-14,  -1.14704494124097104e-11, 2.08767557179572958e-09,
                                       -2.75573192211901978e-07, 2.48015873015843708e-05,  -1.38888888888888873e-03,
                                       4.16666666666666644e-02};
-static __constant__ double EXPC[12] = {1.6059043836821613e-10, 2.08767569878681e-09,   2.505210838544172e-08,
-                                       2.755731922398589e-07,  2.7557319223985893e-06, 2.48015873015873e-05,
-                                       0.0001984126984126984,  0.001388888888888889,   0.008333333333333333,
-                                       0.041666666666666664,   0.16666666666666666,    0.5};
+// Taylor coefficients of cosh r - 1 (1/12! .. 1/2!) and of sinh r / r - 1 (1/13! .. 1/3!), highest power first
+static __constant__ double EXPE[6] = {2.08767569878681e-09, 2.755731922398589e-07, 2.48015873015873e-05,
+                                      0.001388888888888889, 0.041666666666666664,  0.5};
+static __constant__ double EXPO[6] = {1.6059043836821613e-10, 2.505210838544172e-08, 2.7557319223985893e-06,
+                                      0.0001984126984126984,  0.008333333333333333,  0.16666666666666666};
 }  // namespace fm
 #endif
 
 #if defined(__CUDACC__)
 static __device__ __noinline__ void sincos_library(double x, double *s, double *c) { sincos(x, s, c); }
-static __device__ __noinline__ double exp_library(double x) { return exp(x); }
 #endif
 
 // sin and cos of the same argument in one call.  BOUNDED: the caller guarantees |x| < 2^20 (no fallback branch)
@@ -271,25 +271,55 @@ SPB_HD void sincos_(real x, real &s, real &c) {
 #endif
 }
 
-// e^x
-SPB_HD real exp_(real x) {
+// e^x and e^-x from one argument reduction.  exp r = 1 + (cosh r - 1) + sinh r on |r| <= ln2/2: the even and
+// the odd part are two independent Horner chains in r^2 (half the dependent depth of one chain in r), and
+// e^-r is their difference, so the pair costs little more than one exponential.  Branch-free over the whole
+// range: beyond the limits the argument is pinned where the result is already 0 or inf, and the power of two is
+// applied in two exact halves (the scale never leaves the exponent range).  exp_(x) is the first member of the
+// pair bit for bit (the unused half is dead code).
 #if defined(__CUDA_ARCH__)
-    // branch-free over the whole range: beyond the limits the argument is pinned where the result is already 0 or
-    // inf, and the power of two is applied in two exact halves (so the scale never leaves the exponent range)
+__device__ __forceinline__ void exp_pair_dev(double x, double &ep, double &em) {
     x = x < -746.0 ? -746.0 : x;  // (comparisons, not fmin / fmax: a NaN passes through and comes out as NaN)
-    x = x > 710.0 ? 710.0 : x;
+    x = x > 746.0 ? 746.0 : x;
     const int k = __double2int_rn(x * 1.4426950408889634);
     const double fk = (double)k;
     double r = fma(fk, -0.6931471805599453, x);
     r = fma(fk, -2.3190468138462996e-17, r);
-    double p = fm::EXPC[0];
+    const double u = r * r;
+    double pe = fm::EXPE[0], po = fm::EXPO[0];
 #pragma unroll
-    for (int j = 1; j < 12; ++j) p = fma(p, r, fm::EXPC[j]);
-    p = fma(p * r, r, r);  // r + r^2 (1/2 + ...)
+    for (int j = 1; j < 6; ++j) {
+        pe = fma(pe, u, fm::EXPE[j]);
+        po = fma(po, u, fm::EXPO[j]);
+    }
+    const double c = pe * u;                // cosh r - 1
+    const double sh = fma(r * u, po, r);    // sinh r
     const int k1 = k >> 1, k2 = k - k1;
     const double s1 = __longlong_as_double((long long)(1023 + k1) << 52);
     const double s2 = __longlong_as_double((long long)(1023 + k2) << 52);
-    return fma(p, s1, s1) * s2;
+    const double t1 = __longlong_as_double((long long)(1023 - k1) << 52);
+    const double t2 = __longlong_as_double((long long)(1023 - k2) << 52);
+    ep = fma(c + sh, s1, s1) * s2;
+    em = fma(c - sh, t1, t1) * t2;
+}
+#endif
+SPB_HD void exp_pair(real x, real &ep, real &em) {
+#if defined(__CUDA_ARCH__)
+    exp_pair_dev(x, ep, em);
+#elif defined(SPB_EXP_PAIR_HOOK)
+    ::exp_pair_hook(x, ep, em);  // op-counting build (oracle/flopcount.cpp)
+#else
+    ep = exp(x);
+    em = exp(-x);
+#endif
+}
+
+// e^x
+SPB_HD real exp_(real x) {
+#if defined(__CUDA_ARCH__)
+    double ep, em;
+    exp_pair_dev(x, ep, em);
+    return ep;
 #else
     return exp(x);
 #endif
@@ -363,7 +393,7 @@ struct WShared {
     cplx rcz;     // 1/w
     cplx rsq;     // 1/sqrt(w) = conj(sqrt w)/|w|
     real sn, cs;  // sin, cos of Im w
-    real em;      // exp(-Re w) when have_em
+    real ep, em;  // exp(Re w), exp(-Re w) when have_em
     bool have_em;
 };
 SPB_HD cplx w_recip(cplx w, real raz) { return cplx(w.re * raz, -w.im * raz) * raz; }
@@ -419,7 +449,9 @@ SPB_HD WShared w_shared(cplx w, real az, bool need_em) {
     sincos_(w.im, s.sn, s.cs);
 #endif
     s.have_em = need_em;
-    s.em = need_em ? exp_(-w.re) : real(0.0);
+    s.ep = real(0.0);
+    s.em = real(0.0);
+    if (need_em) exp_pair(w.re, s.ep, s.em);
     return s;
 }
 

@@ -183,7 +183,8 @@ SPB_FN int asyi(cplx z, real fnu, int kode, int n, Y y, real rl, real tol, real 
     int koded = 1;
     if (!(rabs(cz.re) > alim && n > 2)) {
         koded = 0;
-        real zm = exp_(cz.re);
+        // (unscaled: exp(Re z), which the shared block has formed together with the exp(-Re z) of the K routine)
+        real zm = (ws && ws->have_em && kode != 2) ? ws->ep : exp_(cz.re);
         ak1 = ak1 * cplx(zm * csy, zm * sny);
     }
     real fdn = 0.0;

@@ -851,6 +851,12 @@ int spb_sinc(const double *x, double *out, int64_t n, const spb_exec *ex) {
         launch_sinc((const double *)i, (double *)o, m, st);
     });
 }
+int spb_devmath(int which, const double *x, double *out, int64_t n, const spb_exec *ex) {
+    if (which < 0 || which > 3) return fail(SPB_E_ARG, "which must be 0 (exp), 1 (exp(-x)), 2 (sin) or 3 (cos)");
+    return run_map(ex, n, 8, 8, x, out, [which](const void *i, void *o, long long m, cudaStream_t st) {
+        launch_devmath(which, (const double *)i, (double *)o, m, st);
+    });
+}
 
 // windows: nothing is read, m doubles are written (device pointer: on the caller's stream; host pointer: staged)
 static int window_impl(int kind, int64_t m, double beta, int sym, double *out, const spb_exec *ex) {

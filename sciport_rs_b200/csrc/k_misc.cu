@@ -120,11 +120,22 @@ void launch_first_error(const int *ierr, long long n, unsigned long long *packed
 
 // ---------------------------------------------------------------- gamma / lgamma / sinc (HBM-bound)
 // two points per thread through one 16-byte load / store
+// WHICH 0..2: the companions; 3..6: the device transcendentals of the region kernels (exp, exp(-x) as the second
+// member of the pair, sin, cos), exported through spb_devmath so that their accuracy is testable on its own
 template <int WHICH>
 __device__ __forceinline__ double gfun(double x) {
     if (WHICH == 0) return spb::gamma_real(x);
     if (WHICH == 1) return spb::lgamma_real(x);
-    return spb::sinc_real(x);
+    if (WHICH == 2) return spb::sinc_real(x);
+    if (WHICH == 3) return spb::exp_(x);
+    if (WHICH == 4) {
+        double ep, em;
+        spb::exp_pair(x, ep, em);
+        return em;
+    }
+    double sn, cs;
+    spb::sincos_(x, sn, cs);
+    return WHICH == 5 ? sn : cs;
 }
 
 template <int WHICH>
@@ -169,6 +180,14 @@ void launch_gamma(int which, const double *x, double *out, long long n, cudaStre
         launch_real_map<1>(x, out, n, st);
 }
 void launch_sinc(const double *x, double *out, long long n, cudaStream_t st) { launch_real_map<2>(x, out, n, st); }
+void launch_devmath(int which, const double *x, double *out, long long n, cudaStream_t st) {
+    switch (which) {
+        case 0: launch_real_map<3>(x, out, n, st); break;
+        case 1: launch_real_map<4>(x, out, n, st); break;
+        case 2: launch_real_map<5>(x, out, n, st); break;
+        default: launch_real_map<6>(x, out, n, st); break;
+    }
+}
 
 // ---------------------------------------------------------------- FP64 peak microbenchmark
 // 8 independent DFMA chains per thread, register resident; 2 flops per DFMA.

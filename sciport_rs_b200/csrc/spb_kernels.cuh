@@ -117,6 +117,7 @@ void launch_first_error(const int *ierr, long long n, unsigned long long *packed
 void launch_gamma(int which, const double *x, double *out, long long n, cudaStream_t st);
 void launch_cgamma(int which, const double2 *z, double2 *out, long long n, cudaStream_t st);
 void launch_sinc(const double *x, double *out, long long n, cudaStream_t st);
+void launch_devmath(int which, const double *x, double *out, long long n, cudaStream_t st);
 void launch_kaiser(long long m_ext, long long n_out, double beta, double2 *den, double *out, int sms, cudaStream_t st);
 void launch_lanczos(long long m_ext, long long n_out, double *out, cudaStream_t st);
 double run_fp64_peak(int device, double seconds, double *sm_mhz);

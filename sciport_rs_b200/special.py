@@ -278,6 +278,13 @@ def sinc(x):
     return _real_map(lib.spb_sinc, x)
 
 
+def devmath(which, x):
+    """The device transcendentals the region kernels use ('exp', 'expm' = exp(-x), 'sin', 'cos'), for accuracy
+    tests of the library itself."""
+    code = {"exp": 0, "expm": 1, "sin": 2, "cos": 3}[which]
+    return _real_map(lambda a, b, n, ex: lib.spb_devmath(code, a, b, n, ex), x)
+
+
 # ---------------------------------------------------------------- widened batched surface
 def _checked(fn, v, z, scaled, **kw):
     vals, _, _ = bessel(fn, v, z, scaled=scaled, want_codes=False, **kw)

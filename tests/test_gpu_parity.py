@@ -551,3 +551,36 @@ def test_compaction_of_homogeneous_and_ragged_tiles(special):
     (j, _, _), (y, _, _) = special.bessel_jy(2.5, zt)
     a, _, _ = special.bessel("J", 2.5, zt)
     assert np.all(np.abs(to_np(j) - to_np(a)) <= 1e-13 * np.maximum(np.abs(to_np(a)), np.abs(to_np(y))))
+
+
+def test_device_transcendentals(special):
+    """exp / exp(-x) (the two members of the device exp pair), sin and cos as the region kernels evaluate them,
+    against extended-precision references: <= 2 ulp over the ranges the kernels produce, exact limits outside."""
+    rng = np.random.default_rng(77)
+    x = np.concatenate([rng.uniform(-708, 708, 200000), rng.uniform(-2, 2, 100000), 10 ** rng.uniform(-300, -1, 1000),
+                        np.array([0.0, -0.0, 709.7, -745.0, 800.0, -800.0, 1e308, -1e308, np.inf, -np.inf, np.nan])])
+    xl = x.astype(np.longdouble)
+    xt = torch.from_numpy(x).cuda()
+    for which, ref in (("exp", np.exp(xl)), ("expm", np.exp(-xl))):
+        got = to_np(special.devmath(which, xt))
+        want = ref.astype(np.float64)
+        fin = np.isfinite(want) & (want > 1e-300)
+        ulp = np.abs((got[fin].astype(np.longdouble) - ref[fin]) / np.spacing(want[fin]).astype(np.longdouble))
+        assert ulp.max() <= 2.0, (which, float(ulp.max()))
+        assert np.array_equal(np.isnan(got), np.isnan(x))
+        sign = 1.0 if which == "exp" else -1.0
+        assert np.all(got[sign * x >= 710] == np.inf) and np.all(got[sign * x <= -746] == 0.0)
+        # subnormal results: a few units of the last (subnormal) place
+        sub = np.isfinite(want) & (want <= 1e-300) & (np.abs(x) < 746)
+        assert np.all(np.abs(got[sub] - want[sub]) <= 4 * np.spacing(np.maximum(want[sub], 5e-324)))
+    y = np.concatenate([rng.uniform(-40000, 40000, 200000), rng.uniform(-3, 3, 100000), rng.uniform(-1e15, 1e15, 2000)])
+    yl = y.astype(np.longdouble)
+    yt = torch.from_numpy(y).cuda()
+    small = np.abs(y) < 1048576
+    for which, ref in (("sin", np.sin(yl)), ("cos", np.cos(yl))):
+        got = to_np(special.devmath(which, yt))
+        # absolute error in units of the last place of 1 (the phase factors multiply values of modulus ~ 1); the
+        # longdouble reference reduces huge arguments with a 64-bit pi, so only the kernels' range is compared tightly
+        err = np.abs(got.astype(np.longdouble) - ref)
+        assert float(err[small].max()) <= 2 * 2.220446049250313e-16, (which, float(err[small].max()))
+        assert np.all(np.abs(got) <= 1.0)

@@ -212,20 +212,22 @@ def write(name, tables):
 def gen_fastmath():
     """Coefficients of the device exp / sincos in amos/spb_common.h (namespace fm): near-minimax (Chebyshev
     interpolation) fits of P(u) = (sin(sqrt u)/sqrt u - 1)/u and Q(u) = (cos(sqrt u) - 1 + u/2)/u^2 on
-    0 <= u <= 1.02 (pi/4)^2, highest power first, and the Taylor coefficients 1/13! .. 1/2! of exp.
+    0 <= u <= 1.02 (pi/4)^2, highest power first, and the Taylor coefficients of exp split into its even part
+    cosh r - 1 (EXPE: 1/12! .. 1/2!) and its odd part sinh r / r - 1 (EXPO: 1/13! .. 1/3!).
     `python tools/gen_tables.py --fastmath` prints them for comparison with the header."""
     q = (mp.pi / 4) ** 2 * mp.mpf("1.02")
     P = lambda u: (mp.sin(mp.sqrt(u)) / mp.sqrt(u) - 1) / u
     Q = lambda u: (mp.cos(mp.sqrt(u)) - 1 + u / 2) / (u * u)
     sinc = mp.chebyfit(P, [mp.mpf("1e-30"), q], 7)
     cosc = mp.chebyfit(Q, [mp.mpf("1e-30"), q], 7)
-    expc = [1 / mp.factorial(k) for k in range(13, 1, -1)]
-    return sinc, cosc, expc
+    expe = [1 / mp.factorial(k) for k in range(12, 1, -2)]
+    expo = [1 / mp.factorial(k) for k in range(13, 2, -2)]
+    return sinc, cosc, expe, expo
 
 
 def main():
     if "--fastmath" in sys.argv:
-        for name, t in zip(("SINC", "COSC", "EXPC"), gen_fastmath()):
+        for name, t in zip(("SINC", "COSC", "EXPE", "EXPO"), gen_fastmath()):
             print(name, ", ".join("%.17e" % float(c) for c in t))
         return
     gln = gen_gln()
