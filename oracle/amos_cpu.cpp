@@ -98,6 +98,22 @@ int spbo_bessel_pipeline(int fn, int kode, const double *v, int64_t v_stride, co
     return 0;
 }
 
+// Class bytes of the classifier: fast[i] = what the fast accept alone decides (-1 where it declines),
+// full[i] = what prepare() decides.  The fast accept is only allowed to agree or to decline.
+int spbo_classify(int fn, int kode, int fuse, const double *v, int64_t v_stride, const double *z, int8_t *fast,
+                  int8_t *full, int64_t n) {
+    for (int64_t i = 0; i < n; ++i) {
+        const cplx zz(z[2 * i], z[2 * i + 1]);
+        const double fnu = v[i * v_stride];
+        int ireg, kreg;
+        fast[i] = -1;
+        if (fast_classify(fn, zz, fnu, kode, fuse != 0, ireg, kreg))
+            fast[i] = (int8_t)class_byte(fn, zz, fnu, kode, fuse != 0, true);
+        full[i] = (int8_t)class_byte(fn, zz, fnu, kode, fuse != 0, false);
+    }
+    return 0;
+}
+
 // J and Y together through the FAM_JY flow (out_j, out_y as re,im pairs)
 int spbo_bessel_jy_pipeline(int kode, const double *v, int64_t v_stride, const double *z, double *out_j, double *out_y,
                             int32_t *codes /* [4][n]: ierr_j, ierr_y, nz_j, nz_y */, int64_t n,

@@ -215,6 +215,106 @@ SPB_FN Prep prepare(int fam, cplx z, real fnu, int kode, bool fuse = false) {
     return p;
 }
 
+// Fast accept of the classifier for the bulk of a large-|z| batch: decides from |z|^2 (no square root) and a
+// handful of comparisons whether prepare() is certain to return a simple point whose I region (if I_v(w) is
+// needed) is the large-|w| asymptotic one, and which K region it has.  Every comparison of prepare() that
+// involves the modulus is replaced by a sufficient condition on m2 = x^2 + y^2 with a relative margin of 1e-9
+// (rounding of m2 and of its square root is below 1e-15), so an accepted point is classified exactly as
+// prepare() would; everything near a region boundary, every unusual argument and every other region is
+// declined and goes through prepare().  tests/test_pipeline_cpu.py checks the equivalence on every distribution.
+// The order-dependent half of the test (computed once per thread when the order is a broadcast scalar): the
+// window of m2 inside which every modulus comparison of prepare() is decided, and the K region.
+struct FastOrder {
+    bool ok;          // 0 <= fnu <= fnul
+    bool pretest;     // fnu > 2: the over/underflow pre-test applies
+    real m2_lo, m2_hi;
+    real c19;         // 19.5 fnu, the order term of the cheap sufficient form of uoik_is_noop()
+    int kreg;         // KREG_HALF or KREG_MILLER (|z| > 2 inside the window)
+};
+SPB_HD FastOrder fast_order(real fnu) {
+    const real fnul = SPB_FNUL;
+    const real up = real(1.0) + real(1.0e-9), dn = real(1.0) - real(1.0e-9);
+    FastOrder o;
+    o.ok = (fnu >= real(0.0)) && (fnu <= fnul);
+    o.pretest = fnu > real(2.0);
+    // rl <= |z| < 32767
+    real lo = real(SPB_RL * SPB_RL) * up, hi = real(32767.0 * 32767.0) * dn;
+    // large-|w| region of I: not the power series (|z|^2/4 > fnu + 1), and fnu <= 1 or 2|z| >= fnu^2
+    lo = rmax(lo, (fnu + real(1.0)) * real(4.0) * up);
+    const real f2 = fnu * fnu;
+    if (!(fnu <= real(1.0))) lo = rmax(lo, f2 * f2 * real(0.25) * up);
+    if (o.pretest) {
+        // fnu 2^-20 <= |z| <= fnu 2^20
+        const real a = fnu * real(9.5367431640625e-07), b = fnu * real(1048576.0);
+        lo = rmax(lo, a * a * up);
+        hi = rmin(hi, b * b * dn);
+    }
+    o.m2_lo = lo;
+    o.m2_hi = hi;
+    o.c19 = fnu * real(19.5);
+    const int inu = (int)(fnu + real(0.5));
+    o.kreg = (rabs(fnu - real(inu)) == real(0.5)) ? KREG_HALF : KREG_MILLER;
+    return o;
+}
+SPB_HD bool fast_classify(int fam, cplx z, const FastOrder &o, int kode, bool fuse, int &ireg, int &kreg) {
+    const real alim = SPB_ALIM;
+    const real m2 = z.re * z.re + z.im * z.im;
+    if (!o.ok || !(m2 >= o.m2_lo) || !(m2 <= o.m2_hi)) return false;  // (a NaN fails the comparisons)
+    if (fam == FAM_J || fam == FAM_I) {
+        ireg = IREG_ASYI;
+        kreg = -1;
+        return true;
+    }
+    // K-type families: which half plane the evaluation point lies in, |Re w| for the pre-test
+    bool left;
+    real x;
+    if (fam == FAM_K) {
+        left = z.re < real(0.0);
+        x = rabs(z.re);
+    } else if (fam == FAM_H1 || fam == FAM_H2) {
+        const real fmm = (fam == FAM_H1) ? real(1.0) : real(-1.0);
+        const real znr = fmm * z.im, zni = -fmm * z.re;
+        left = (znr < real(0.0)) || (znr == real(0.0) && zni < real(0.0) && fam == FAM_H2);
+        x = rabs(z.im);
+    } else {
+        left = (fam == FAM_JY) || !(z.im == real(0.0) && z.re > real(0.0));
+        x = rabs(z.im);
+    }
+    if (o.pretest) {
+        if (kode != 1) x = real(0.0);
+        if (!(o.c19 + x < alim)) return false;
+    }
+    kreg = o.kreg;
+    ireg = -1;
+    if (left) {
+        ireg = IREG_ASYI;
+        if (fuse) kreg = KREG_FUSED;
+    }
+    return true;
+}
+SPB_HD bool fast_classify(int fam, cplx z, real fnu, int kode, bool fuse, int &ireg, int &kreg) {
+    const FastOrder o = fast_order(fnu);
+    return fast_classify(fam, z, o, kode, fuse, ireg, kreg);
+}
+
+// class byte of a point: bits 0-2 I bin (7 none), 3-4 K bin (3 none, also for KREG_FUSED), 5 general
+SPB_HD unsigned int class_of(int ireg, int kreg) {
+    const unsigned int bi = ireg >= 0 ? (unsigned int)ireg : 7u;
+    const unsigned int bk = kreg >= 0 ? (unsigned int)kreg : 3u;
+    return bi | (bk << 3);
+}
+SPB_HD unsigned int class_byte(int fam, cplx z, real fnu, int kode, bool fuse, bool allow_fast = true) {
+    int ireg, kreg;
+    if (!(allow_fast && fast_classify(fam, z, fnu, kode, fuse, ireg, kreg))) {
+        const Prep p = prepare(fam, z, fnu, kode, fuse);
+        // (CMB_FINAL: decided by prepare(); the general kernel stores it without running the drivers)
+        if (p.combine == CMB_GENERAL || p.combine == CMB_FINAL) return 7u | (3u << 3) | (1u << 5);
+        ireg = p.ireg;
+        kreg = p.kreg;
+    }
+    return class_of(ireg, kreg);
+}
+
 // prepare() for a point the classifier has already binned: the region tests are known to have passed, so only
 // the geometry and the modulus are recomputed.  has_i = the class byte carries an I bin.
 SPB_FN Prep prepare_pass(int fam, cplx z, bool with_modulus = true) {

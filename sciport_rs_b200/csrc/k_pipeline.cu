@@ -86,22 +86,50 @@ __global__ void __launch_bounds__(256) k_classify(DevJob job, Scratch s) {
     const long long base = (long long)blockIdx.x * TILE;
     Packed cnt;
     cnt.clear();
+    constexpr int PER_THREAD = TILE / 256;
+    // Phase 1: the fast accept (|z|^2 and a few comparisons) for the thread's 8 points at once: all loads are
+    // issued before the first test, so the phase runs at memory speed on batches that live in the large-|z|
+    // region.  A warp keeps a fast result only if all its lanes accepted that point.
+    unsigned int cls4[PER_THREAD / 4];  // class bytes, 0xff = not decided yet
+    {
+        double2 zk[PER_THREAD];
+        double vk[PER_THREAD];
+#pragma unroll
+        for (int k = 0; k < PER_THREAD; ++k) {
+            const long long i = base + threadIdx.x + 256 * k;
+            zk[k] = make_double2(0.0, 0.0);
+            vk[k] = 0.0;
+            if (i < job.n) {
+                cplx z;
+                load_point(job, i, z, vk[k]);
+                zk[k] = make_double2(z.re, z.im);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < PER_THREAD / 4; ++q) cls4[q] = 0;
+        const bool scalar_order = job.v_stride == 0;
+        spb::FastOrder fo = spb::fast_order(vk[0]);  // a broadcast order: its half of the test once per thread
+#pragma unroll
+        for (int k = 0; k < PER_THREAD; ++k) {
+            int ireg, kreg;
+            if (!scalar_order) fo = spb::fast_order(vk[k]);
+            const bool ok = spb::fast_classify(job.fam, cplx(zk[k].x, zk[k].y), fo, job.kode, job.fuse != 0, ireg, kreg);
+            unsigned int c = 0xffu;
+            if (__all_sync(0xffffffffu, ok)) c = spb::class_of(ireg, kreg);
+            cls4[k / 4] |= c << (8 * (k % 4));
+        }
+    }
+    // Phase 2: prepare() for the points the fast accept left open (warp-uniform per point), then store and count
 #pragma unroll 2
-    for (int k = threadIdx.x; k < TILE; k += 256) {
-        long long i = base + k;
+    for (int k = 0; k < PER_THREAD; ++k) {
+        const long long i = base + threadIdx.x + 256 * k;
+        unsigned int c = (cls4[k / 4] >> (8 * (k % 4))) & 0xffu;
         if (i < job.n) {
-            cplx z;
-            double v;
-            load_point(job, i, z, v);
-            spb::Prep p = spb::prepare(job.fam, z, v, job.kode, job.fuse != 0);
-            unsigned int c;
-            if (p.combine == spb::CMB_GENERAL || p.combine == spb::CMB_FINAL) {
-                // (CMB_FINAL: decided by prepare(); the general kernel stores it without running the drivers)
-                c = 7u | (3u << 3) | (1u << 5);
-            } else {
-                unsigned int bi = p.ireg >= 0 ? (unsigned int)p.ireg : 7u;
-                unsigned int bk = p.kreg >= 0 ? (unsigned int)p.kreg : 3u;
-                c = bi | (bk << 3);
+            if (c == 0xffu) {
+                cplx z;
+                double v;
+                load_point(job, i, z, v);
+                c = spb::class_byte(job.fam, z, v, job.kode, job.fuse != 0, false);
             }
             s.cls[i] = (unsigned char)c;
             packed_add(c, cnt);

@@ -72,6 +72,19 @@ def cpu_bessel_seq(fn, kode, v, z, n_orders, threads=8, classic=False):
     return out, ierr, nz
 
 
+def cpu_classify(fn, kode, v, z, fuse):
+    """(fast, full) class bytes of the classifier: fast = -1 where the fast accept declines."""
+    lib = oracle_lib()
+    z = np.ascontiguousarray(z, dtype=np.complex128)
+    v = np.ascontiguousarray(np.broadcast_to(np.asarray(v, dtype=np.float64), z.shape))
+    fast = np.empty(z.shape, np.int8)
+    full = np.empty(z.shape, np.int8)
+    lib.spbo_classify({**FN, "JY": 6}[fn], kode, int(fuse), ctypes.c_void_p(v.ctypes.data), ctypes.c_int64(1),
+                      ctypes.c_void_p(z.ctypes.data), ctypes.c_void_p(fast.ctypes.data),
+                      ctypes.c_void_p(full.ctypes.data), ctypes.c_int64(z.size))
+    return fast, full
+
+
 def cpu_bessel_jy(kode, v, z, threads=8, fuse=False):
     lib = oracle_lib()
     z = np.ascontiguousarray(z, dtype=np.complex128)

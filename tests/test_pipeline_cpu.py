@@ -71,3 +71,32 @@ def test_jy_pair_matches_separate_drivers(cfg, fuse):
         b, ib, nb = helpers.cpu_bessel("Y", kode, v, z)
         assert np.array_equal(j.view(np.uint64), a.view(np.uint64)) and np.array_equal(ej, ia) and np.array_equal(nj, na)
         assert np.array_equal(y.view(np.uint64), b.view(np.uint64)) and np.array_equal(ey, ib) and np.array_equal(ny, nb)
+
+
+@pytest.mark.parametrize("fuse", [False, True], ids=["separate", "fused"])
+@pytest.mark.parametrize("fn", list(FN) + ["JY"])
+def test_fast_accept_of_the_classifier_agrees_with_prepare(fn, fuse):
+    """spb::fast_classify (|z|^2 and a few comparisons, no square root) may only accept a point that prepare()
+    classifies identically; it must take the bulk of the large-|z| configs and decline near every boundary."""
+    rates = {}
+    for cfg in ("cfg2", "cfg3", "cfg4", "real", "wide", "far", "edges"):
+        rng = np.random.default_rng(helpers.seed_of("fast", fn, cfg))
+        if cfg == "edges":
+            # moduli hugging the thresholds the fast accept replaces: rl, 32767, 2 sqrt(fnu + 1), fnu^2 / 2
+            n = 40000
+            v = rng.choice([0.0, 0.5, 1.0, 2.5, 7.25, 30.0, 85.0, 85.92135864716213, 86.0], n)
+            r0 = rng.choice(4, n)
+            base = np.where(r0 == 0, 21.784271729432426, np.where(r0 == 1, 32767.0,
+                            np.where(r0 == 2, 2 * np.sqrt(v + 1), v * v / 2)))
+            r = np.maximum(base, 1e-3) * (1 + rng.choice([-1, 1], n) * 10 ** rng.uniform(-16, -6, n))
+            th = rng.choice([0.0, np.pi / 2, np.pi, -np.pi / 2, 1.0, -2.0, 3.0], n) + rng.choice([0, 1e-12, -1e-9], n)
+            z = r * np.exp(1j * th)
+            z = np.where(rng.random(n) < 0.2, z.real + 0j, z)  # exactly on the real axis as well
+        else:
+            v, z = gen(cfg, 50000, rng)
+        for kode in (1, 2):
+            fast, full = helpers.cpu_classify(fn, kode, v, z, fuse)
+            acc = fast >= 0
+            assert np.array_equal(fast[acc], full[acc]), f"{cfg} kode={kode}: fast accept disagrees with prepare()"
+            rates[cfg] = acc.mean()
+    assert rates["cfg2"] > 0.95, rates
