@@ -417,6 +417,15 @@ __device__ __forceinline__ double rsqrt_onscale(double x) {
 }
 #endif
 // az < 0: the modulus is not known yet (fused region kernel: |w| and 1/|w| come out of one reciprocal square root)
+// 1/x for an argument known to be far from the ends of the exponent range (loop counters, moduli inside a region):
+// the branch-free form on the device, a plain division on the host
+SPB_HD real rcp_fast(real x) {
+#if defined(__CUDA_ARCH__)
+    return rcp_onscale(x);
+#else
+    return real(1.0) / x;
+#endif
+}
 SPB_HD WShared w_shared(cplx w, real az, bool need_em) {
     WShared s;
 #if defined(__CUDA_ARCH__)

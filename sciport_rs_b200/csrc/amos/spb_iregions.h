@@ -362,7 +362,7 @@ SPB_FN int mlri(cplx z, real fnu, int kode, int n, Y y, real tol, real az_known 
         cplx pt = p2;
         p2 = p1 + (rz * pt) * (fkk + fnf);
         p1 = pt;
-        real a = real(1.0) - tfnf / (fkk + tfnf);
+        real a = real(1.0) - tfnf * rcp_fast(fkk + tfnf);  // 1 <= fkk + tfnf < 1e5
         real ac = bk * a;
         sum = sum + p1 * (ac + bk);
         bk = ac;
@@ -373,7 +373,7 @@ SPB_FN int mlri(cplx z, real fnu, int kode, int n, Y y, real tol, real az_known 
         cplx pt = p2;
         p2 = p1 + (rz * pt) * (fkk + fnf);
         p1 = pt;
-        real a = real(1.0) - tfnf / (fkk + tfnf);
+        real a = real(1.0) - tfnf * rcp_fast(fkk + tfnf);  // 1 <= fkk + tfnf < 1e5
         real ac = bk * a;
         sum = sum + p1 * (ac + bk);
         bk = ac;
@@ -384,7 +384,7 @@ SPB_FN int mlri(cplx z, real fnu, int kode, int n, Y y, real tol, real az_known 
         cplx pt = p2;
         p2 = p1 + (rz * pt) * (fkk + fnf);
         p1 = pt;
-        real a = real(1.0) - tfnf / (fkk + tfnf);
+        real a = real(1.0) - tfnf * rcp_fast(fkk + tfnf);  // 1 <= fkk + tfnf < 1e5
         real ac = bk * a;
         sum = sum + p1 * (ac + bk);
         bk = ac;

@@ -348,8 +348,8 @@ SPB_FN int bknu_body(cplx z, real fnu, int kode, int n, Y y, real tol, real elim
                     bool ok = false;
                     SPB_NO_UNROLL
                     for (int i = 1; i <= kmax; ++i) {
-                        real a = fhs / fks;
-                        real cbr = ckr / (fk + real(1.0));
+                        real a = fhs * rcp_fast(fks);  // 2 <= fks, fk + 1 < 1e4
+                        real cbr = ckr * rcp_fast(fk + real(1.0));
                         real ptr = p2r;
                         p2r = cbr * p2r - p1r * a;
                         p1r = ptr;
@@ -392,7 +392,7 @@ SPB_FN int bknu_body(cplx z, real fnu, int kode, int n, Y y, real tol, real elim
                 // much as a dozen multiplications on the device; the Miller iteration is self-normalising, so
                 // the two extra roundings do not matter)
                 real d1 = a1 + fhs, d2 = fk + real(1.0);
-                real rr = real(1.0) / (d1 * d2);
+                real rr = rcp_fast(d1 * d2);  // 1 <= d1 d2 < 1e9
                 real a = (fks + fk) * (d2 * rr);
                 real rak = real(2.0) * (d1 * rr);
                 cplx cb = cplx(fk + z.re, z.im) * rak;
