@@ -77,7 +77,7 @@ SPB_FN int seri(cplx z, real fnu, int kode, int n, Y y, real tol, real elim, rea
                     real s = fnup;
                     real a2 = 2.0;
                     do {
-                        real rs = real(1.0) / s;
+                        real rs = rcp_fast(s);  // s = k (fnu + k), k >= 1
                         t = (t * cz) * rs;
                         s1 = s1 + t;
                         s += akk;
@@ -194,7 +194,7 @@ SPB_FN int asyi(cplx z, real fnu, int kode, int n, Y y, real rl, real tol, real 
     real aez = real(8.0) * az;
     real raez = real(0.125) * raz;
     cplx rez = rcz * real(0.125);  // 1/(8z)
-    real s = tol / aez;
+    real s = tol * raez;
     int jl = (int)(rl + rl) + 2;
     cplx p1(0.0, 0.0);
     const bool second = (z.im != real(0.0)) && (z.re + z.re < real(80.0));

@@ -230,10 +230,10 @@ SPB_FN int bknu_body(cplx z, real fnu, int kode, int n, Y y, real tol, real elim
                 real t1s = real(0.25) * caz * caz;
                 SPB_NO_UNROLL
                 do {
-                    f = (f * akk + p + q) * (real(1.0) / bk);
-                    p = p * (real(1.0) / (akk - dnu));
-                    q = q * (real(1.0) / (akk + dnu));
-                    real rak = real(1.0) / akk;
+                    f = (f * akk + p + q) * rcp_fast(bk);
+                    p = p * rcp_fast(akk - dnu);
+                    q = q * rcp_fast(akk + dnu);
+                    real rak = rcp_fast(akk);
                     ckk = (ckk * cz) * rak;
                     s1 = s1 + ckk * f;
                     a1 = a1 * t1s * rak;
@@ -251,10 +251,10 @@ SPB_FN int bknu_body(cplx z, real fnu, int kode, int n, Y y, real tol, real elim
             real t1s = real(0.25) * caz * caz;
             SPB_NO_UNROLL
             do {
-                f = (f * akk + p + q) * (real(1.0) / bk);
-                p = p * (real(1.0) / (akk - dnu));
-                q = q * (real(1.0) / (akk + dnu));
-                real rak = real(1.0) / akk;
+                f = (f * akk + p + q) * rcp_fast(bk);
+                p = p * rcp_fast(akk - dnu);
+                q = q * rcp_fast(akk + dnu);
+                real rak = rcp_fast(akk);
                 ckk = (ckk * cz) * rak;
                 s1 = s1 + ckk * f;
                 s2 = s2 + ckk * (p - f * akk);
