@@ -48,11 +48,11 @@ SPB_FN int acai(cplx z, real fnu, int kode, int mr, int n, Y y, real rl, real to
     cplx csgn(0.0, sgn);
     if (kode != 1) {
         real yy = -zn.im;
-        csgn = csgn * cplx(cos(yy), sin(yy));
+        csgn = csgn * cis_(yy);
     }
     int inu = (int)fnu;
     real arg = (fnu - real(inu)) * sgn;
-    cplx cspn(cos(arg), sin(arg));
+    cplx cspn = cis_(arg);
     if (inu % 2 != 0) cspn = -cspn;
     cplx c1 = cy[0];
     cplx c2 = y[0];
@@ -90,11 +90,13 @@ SPB_FN void airy_series(cplx z, real az, real fid, real tol, cplx &s1, cplx &s2)
     ak = real(24.0) + real(9.0) * fid;
     bk = real(30.0) - real(9.0) * fid;
     for (int k = 1; k <= 25; ++k) {
-        trm1 = (trm1 * z3) * (real(1.0) / d1);
+        // (d1, d2: products of small loop counters; ad is one of them)
+        const real r1 = rcp_fast(d1), r2 = rcp_fast(d2);
+        trm1 = (trm1 * z3) * r1;
         s1 = s1 + trm1;
-        trm2 = (trm2 * z3) * (real(1.0) / d2);
+        trm2 = (trm2 * z3) * r2;
         s2 = s2 + trm2;
-        atrm = atrm * az3 / ad;
+        atrm = atrm * az3 * rmax(r1, r2);
         d1 += ak;
         d2 += bk;
         ad = rmin(d1, d2);
@@ -148,10 +150,8 @@ SPB_FN cplx airy(cplx z, int id, int kode, int &nz, int &ierr) {
     real fnu = (real(1.0) + fid) / real(3.0);
     real alaz = log(az);
     // range test: |z| > (min(0.5/tol, 2^30-ish))^(2/3) is total loss, its square root half loss
-    real aa = real(0.5) / tol;
-    real bb = real(2147483647.0) * real(0.5);
-    aa = rmin(aa, bb);
-    aa = pow(aa, tth);
+    // min(0.5/tol, (2^31 - 1)/2)^(2/3), a constant of the arithmetic (binary64: the second argument of the min)
+    real aa = real(1048575.9996744783);
     if (az > aa) {
         ierr = 4;
         nz = 0;
@@ -255,14 +255,12 @@ SPB_FN cplx biry(cplx z, int id, int kode, int &ierr) {
         }
         if (kode == 1) return bi;
         cplx zta = (z * csqrt_(z)) * tth;
-        real eaa = exp(-rabs(zta.re));
+        real eaa = exp_(-rabs(zta.re));
         return bi * eaa;
     }
     real fnu = (real(1.0) + fid) / real(3.0);
-    real aa = real(0.5) / tol;
-    real bb = real(2147483647.0) * real(0.5);
-    aa = rmin(aa, bb);
-    aa = pow(aa, tth);
+    // min(0.5/tol, (2^31 - 1)/2)^(2/3), a constant of the arithmetic (binary64: the second argument of the min)
+    real aa = real(1048575.9996744783);
     if (az > aa) {
         ierr = 4;
         return cplx(0.0, 0.0);
@@ -284,7 +282,7 @@ SPB_FN cplx biry(cplx z, int id, int kode, int &ierr) {
     aa = zta.re;
     if (kode != 2) {
         // overflow test
-        bb = rabs(aa);
+        real bb = rabs(aa);
         if (!(bb < alim)) {
             bb = bb + real(0.25) * log(az);
             sfac = tol;
@@ -306,7 +304,7 @@ SPB_FN cplx biry(cplx z, int id, int kode, int &ierr) {
     // a failure of the first I evaluation is reported after the second one (reconvergence, see acai)
     const int nz_first = nz;
     aa = fmr * fnu;
-    cplx s1 = (cy[0] * cplx(cos(aa), sin(aa))) * sfac;
+    cplx s1 = (cy[0] * cis_(aa)) * sfac;
     fnu = (real(2.0) - fid) / real(3.0);
     nz = binu(zta, fnu, kode, 2, cy, rl, fnul, tol, elim, alim);
     cy[0] = cy[0] * sfac;
@@ -314,7 +312,7 @@ SPB_FN cplx biry(cplx z, int id, int kode, int &ierr) {
     // one backward recurrence step gives order -1/3 or -2/3
     cplx s2 = cdiv(cy[0], zta) * (fnu + fnu) + cy[1];
     aa = fmr * (fnu - real(1.0));
-    s1 = (s1 + s2 * cplx(cos(aa), sin(aa))) * coef;
+    s1 = (s1 + s2 * cis_(aa)) * coef;
     if (nz_first < 0) {
         ierr = (nz_first == -1) ? 2 : 5;
         return cplx(0.0, 0.0);

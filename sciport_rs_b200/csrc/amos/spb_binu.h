@@ -75,9 +75,9 @@ SPB_FN int uoik(cplx z, real fnu, int kode, int ikflg, int n, Y y, real tol, rea
                     cz = cz - clog_(arg) * real(0.25);
                     cz.re -= aic;
                 }
-                real axx = exp(rcz) / tol;
+                real axx = exp_(rcz) / tol;
                 real ayy = cz.im;
-                cplx czz(axx * cos(ayy), axx * sin(ayy));
+                cplx czz = cis_(ayy) * axx;
                 if (uchk(czz, ascle, tol) != 0) zero_all = true;
             }
         }
@@ -119,9 +119,9 @@ SPB_FN int uoik(cplx z, real fnu, int kode, int ikflg, int n, Y y, real tol, rea
                     cz = cz - clog_(arg) * real(0.25);
                     cz.re -= aic;
                 }
-                real axx = exp(rcz) / tol;
+                real axx = exp_(rcz) / tol;
                 real ayy = cz.im;
-                cplx czz(axx * cos(ayy), axx * sin(ayy));
+                cplx czz = cis_(ayy) * axx;
                 if (uchk(czz, ascle, tol) != 0) under = true;
                 if (!under) return nuf;
             }
@@ -145,7 +145,7 @@ SPB_FN int wrsk(cplx zr, real fnu, int kode, int n, Y y, real tol, real elim, re
     rati(zr, fnu, n, y, tol, az_known);
     // recur forward on I(fnu+1,z) = R(fnu,z) I(fnu,z)
     cplx cinu(1.0, 0.0);
-    if (kode != 1) cinu = cplx(cos(zr.im), sin(zr.im));
+    if (kode != 1) cinu = cis_(zr.im);
     // K values can sit near either exponent extreme: scale the normalisation
     real acw = cabs_(cw[1]);
     real ascle = real(1.0e3) * SPB_D1MACH1 / tol;
@@ -251,8 +251,8 @@ SPB_FN int uni1(cplx z, real fnu, int kode, int n, Y y, int &nlast, real fnul, r
             if (!bad) {
                 // scale s1 if |s1| < ascle
                 s2 = phi * sum;
-                real e = exp(s1.re) * CSSR(iflag);
-                cplx st(e * cos(s1.im), e * sin(s1.im));
+                real e = exp_(s1.re) * CSSR(iflag);
+                cplx st = cis_(s1.im) * e;
                 s2 = s2 * st;
                 if (iflag == 1 && uchk(s2, bry0, tol) != 0) bad = true;
             }
@@ -336,7 +336,7 @@ SPB_FN int uni2(cplx z, real fnu, int kode, int n, Y y, int &nlast, real fnul, r
     real cidi = -1.0;
     int inu = (int)fnu;
     real ang = hpi * (fnu - real(inu));
-    cplx c2(cos(ang), sin(ang));
+    cplx c2 = cis_(ang);
     real car = c2.re, sar = c2.im;
     int in = inu + n - 1;
     in = in % 4;
@@ -403,8 +403,8 @@ SPB_FN int uni2(cplx z, real fnu, int kode, int n, Y y, int &nlast, real fnul, r
                 cplx dai = airy(arg, 1, 2, ndai, idum);
                 cplx st = dai * bsum + ai * asum;
                 s2 = phi * st;
-                real e = exp(s1.re) * CSSR(iflag);
-                cplx ex(e * cos(s1.im), e * sin(s1.im));
+                real e = exp_(s1.re) * CSSR(iflag);
+                cplx ex = cis_(s1.im) * e;
                 s2 = s2 * ex;
                 if (iflag == 1 && uchk(s2, bry0, tol) != 0) bad = true;
             }

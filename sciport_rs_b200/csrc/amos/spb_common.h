@@ -325,6 +325,13 @@ SPB_HD real exp_(real x) {
 #endif
 }
 
+// (cos x, sin x)
+SPB_HD cplx cis_(real x) {
+    real s, c;
+    sincos_(x, s, c);
+    return cplx(c, s);
+}
+
 SPB_HD cplx cexp_(cplx a) {
     real zm = exp_(a.re);
     real s, c;

@@ -64,7 +64,7 @@ SPB_FN int seri(cplx z, real fnu, int kode, int n, Y y, real tol, real elim, rea
             }
             real aa = exp_(ak1.re);
             if (iflag == 1) aa *= ss;
-            cplx coef(aa * cos(ak1.im), aa * sin(ak1.im));
+            cplx coef = cis_(ak1.im) * aa;
             real atol = tol * acz / fnup;
             int il = nn < 2 ? nn : 2;
             for (int i = 1; i <= il; ++i) {
