@@ -28,8 +28,10 @@
 // (28 % of the stall samples of the K pass with per-element orders were "no instruction").
 #if defined(__CUDACC__)
 #define SPB_NO_UNROLL _Pragma("unroll 1")
+#define SPB_UNROLL _Pragma("unroll")
 #else
 #define SPB_NO_UNROLL
+#define SPB_UNROLL
 #endif
 
 // Rarely taken fallbacks (scaled modulus, library transcendentals outside the fast range) are kept out of line on

@@ -10,7 +10,8 @@ namespace spbk {
 #ifndef SPB_IPASS_MINB_ASYI
 #define SPB_IPASS_MINB_ASYI 8
 #endif
-#define SPB_IPASS_MINB(R) ((R) == 1 ? SPB_IPASS_MINB_ASYI : 1)
+// (Debye-type uniform kernel: 3 CTAs need <= 168 registers, which is what the routine takes when left alone)
+#define SPB_IPASS_MINB(R) ((R) == 1 ? SPB_IPASS_MINB_ASYI : (R) == 4 ? 3 : 1)
 #ifndef SPB_FUSED_MINB
 #define SPB_FUSED_MINB 5
 #endif
