@@ -134,11 +134,15 @@ SPB_FN int uoik(cplx z, real fnu, int kode, int ikflg, int n, Y y, real tol, rea
 }
 
 // I by ratios from rati normalised through the Wronskian with K_fnu, K_fnu+1.
-template <class Y>
+// SIMPLE: the point is a binned one (both over/underflow pre-tests are no-ops), so K_fnu, K_fnu+1 stay on the
+// middle scaling level and the lean form of the K routine applies (it reports a point that leaves the level
+// after all, and the caller hands it to the general path); both forms round identically.
+template <bool SIMPLE = false, class Y>
 SPB_FN int wrsk(cplx zr, real fnu, int kode, int n, Y y, real tol, real elim, real alim,
                 real az_known = real(-1.0)) {
     cplx cw[2];
-    int nw = bknu(zr, fnu, kode, 2, cw, tol, elim, alim, az_known);
+    int nw = SIMPLE ? bknu_simple2(zr, fnu, kode, cw, tol, elim, alim, az_known)
+                    : bknu(zr, fnu, kode, 2, cw, tol, elim, alim, az_known);
     // a failed K evaluation is reported at the end (no return between the data-dependent loops of bknu and
     // rati, so that their exits reconverge here)
     const bool kfail = nw != 0;

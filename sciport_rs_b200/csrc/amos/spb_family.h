@@ -342,7 +342,7 @@ SPB_FN int ipass_region(int region, cplx w, real fnu, int kode, cplx &val, real 
         case IREG_SERIES: nw = seri(w, fnu, kode, 1, y, tol, elim, alim, az); break;
         case IREG_ASYI: nw = asyi(w, fnu, kode, 1, y, rl, tol, elim, alim, az, oph, ws); break;
         case IREG_MLRI: nw = mlri(w, fnu, kode, 1, y, tol, az); break;
-        case IREG_WRSK: nw = wrsk(w, fnu, kode, 1, y, tol, elim, alim, az); break;
+        case IREG_WRSK: nw = wrsk<true>(w, fnu, kode, 1, y, tol, elim, alim, az); break;
         case IREG_UNI1:
         case IREG_UNI2: {
             // order raised to fnul, uniform expansion there, backward recurrence (binu()'s route for

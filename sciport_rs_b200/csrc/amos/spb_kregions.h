@@ -609,4 +609,16 @@ SPB_FN int bknu_simple(cplx z, real fnu, int kode, cplx &val, real tol, real eli
     return 0;
 }
 
+// K_fnu(z) and K_fnu+1(z) for a binned point of the Miller + Wronskian region of I (both pre-tests known to be
+// no-ops): the lean form of the routine, hand-over codes as in bknu_simple.
+SPB_FN int bknu_simple2(cplx z, real fnu, int kode, cplx *cw, real tol, real elim, real alim, real az_known) {
+    bool noconv = false, handover = false;
+    cw[0] = cplx(0.0, 0.0);
+    cw[1] = cplx(0.0, 0.0);
+    int nz = bknu_body<true>(z, fnu, kode, 2, cw, tol, elim, alim, az_known, noconv, handover);
+    if (noconv) return -2;
+    if (handover || nz != 0) return -9;
+    return 0;
+}
+
 }  // namespace spb
