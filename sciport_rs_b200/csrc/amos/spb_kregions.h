@@ -109,13 +109,34 @@ SPB_FN int s1s2(cplx zr, cplx &s1, cplx &s2, real ascle, real alim, int &iuf) {
     real as1 = cabs_(s1);
     real as2 = cabs_(s2);
     if ((s1.re != real(0.0) || s1.im != real(0.0)) && as1 != real(0.0)) {
-        real aln = -zr.re - zr.re + log(as1);
+        // s1 exp(-2 zr), dropped when ln|s1| - 2 Re zr < -alim.  The binary exponent of |s1| brackets ln|s1| within
+        // ln 2, which decides the test without a logarithm except in a band of that width; the product form
+        // replaces exp(log s1 - 2 zr) (one exp and one sincos instead of log, atan2, exp, sincos) wherever
+        // exp(-2 Re zr) itself is on scale.
+        const real x2 = zr.re + zr.re;
+        const real thr = x2 - alim;
+        const real ln2 = 0.69314718055994531;
+        const int e = expo_((double)as1) - 1022;  // 2^(e-1) <= |s1| < 2^e (e = -1022 also for subnormals)
+        bool drop;
+        if (real(e) * ln2 + real(1.0e-9) < thr) {
+            drop = true;
+        } else if (real(e - 1) * ln2 - real(1.0e-9) >= thr) {
+            drop = false;
+        } else {
+            drop = (-x2 + log(as1) < -alim);
+        }
         cplx s1d = s1;
         s1 = cplx(0.0, 0.0);
         as1 = 0.0;
-        if (!(aln < -alim)) {
-            cplx c1 = clog_(s1d) - zr - zr;
-            s1 = cexp_(c1);
+        if (!drop) {
+            if (x2 < real(700.0)) {
+                const real em2 = exp_(-x2);
+                const cplx ph = cis_(-(zr.im + zr.im));
+                s1 = s1d * cplx(em2 * ph.re, em2 * ph.im);
+            } else {
+                cplx c1 = clog_(s1d) - zr - zr;
+                s1 = cexp_(c1);
+            }
             as1 = cabs_(s1);
             iuf += 1;
         }
