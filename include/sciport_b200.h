@@ -138,7 +138,7 @@ int spb_clgamma(const spb_c128 *z, spb_c128 *out, int64_t n, const spb_exec *ex)
 int spb_sinc(const double *x, double *out, int64_t n, const spb_exec *ex);
 
 /* ---- the device transcendentals of the region kernels, exported for accuracy tests only (no reference
- * counterpart): which = 0 exp(x), 1 exp(-x) (second member of the exp pair), 2 sin(x), 3 cos(x) ------------ */
+ * counterpart): which = 0 exp(x), 1 exp(-x) (second member of the exp pair), 2 sin(x), 3 cos(x), 4 log(x) -- */
 int spb_devmath(int which, const double *x, double *out, int64_t n, const spb_exec *ex);
 
 /* ---- windows built on the path (the batched in-tree consumers) -------------------------------------

@@ -244,7 +244,7 @@ SPB_FN int uni1(cplx z, real fnu, int kode, int n, Y y, int &nlast, real fnul, r
                 if (!(rabs(rs1) < alim)) {
                     // refine the test and scale
                     real aphi = cabs_(phi);
-                    rs1 = rs1 + log(aphi);
+                    rs1 = rs1 + log_(aphi);
                     if (rabs(rs1) > elim) bad = true;
                     if (!bad) {
                         if (i == 1) iflag = 1;
@@ -392,7 +392,7 @@ SPB_FN int uni2(cplx z, real fnu, int kode, int n, Y y, int &nlast, real fnul, r
                 if (!(rabs(rs1) < alim)) {
                     real aphi = cabs_(phi);
                     real aarg = cabs_(arg);
-                    rs1 = rs1 + log(aphi) - real(0.25) * log(aarg) - aic;
+                    rs1 = rs1 + log_(aphi) - real(0.25) * log_(aarg) - aic;
                     if (rabs(rs1) > elim) bad = true;
                     if (!bad) {
                         if (i == 1) iflag = 1;

@@ -231,12 +231,75 @@ static __constant__ double EXPE[6] = {2.08767569878681e-09, 2.755731922398589e-0
                                       0.001388888888888889, 0.041666666666666664,  0.5};
 static __constant__ double EXPO[6] = {1.6059043836821613e-10, 2.505210838544172e-08, 2.7557319223985893e-06,
                                       0.0001984126984126984,  0.008333333333333333,  0.16666666666666666};
+static __constant__ double LOGC[7] = {1.46437581696042513e-01, 1.53294900617389485e-01, 1.81829569361832921e-01,
+                                      2.22222101946705108e-01, 2.85714286317930388e-01, 3.99999999998865485e-01,
+                                      6.66666666666666963e-01};
 }  // namespace fm
 #endif
 
 #if defined(__CUDACC__)
 static __device__ __noinline__ void sincos_library(double x, double *s, double *c) { sincos(x, s, c); }
 #endif
+
+#if defined(__CUDA_ARCH__)
+// Branch-free reciprocal and reciprocal square root for arguments known to be on scale (the fused region has
+// 21.78 <= |w| < 32767): hardware seed (about 20 bits) and one third-order correction, error below 1 ulp.  The
+// library forms carry a slow-path branch each, which also keeps the compiler from scheduling the independent
+// exp / sincos arithmetic across them.
+__device__ __forceinline__ double rcp_onscale(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-x, y, 1.0);
+    return fma(y, fma(e, e, e), y);  // y (1 + e + e^2)
+}
+__device__ __forceinline__ double rsqrt_onscale(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-x * y, y, 1.0);              // 1 - x y^2
+    return fma(y, e * fma(0.375, e, 0.5), y);          // y (1 + e/2 + 3 e^2/8)
+}
+#endif
+// 1/x for an argument known to be far from the ends of the exponent range (loop counters, moduli inside a region):
+// the branch-free form on the device, a plain division on the host
+SPB_HD real rcp_fast(real x) {
+#if defined(__CUDA_ARCH__)
+    return rcp_onscale(x);
+#else
+    return real(1.0) / x;
+#endif
+}
+
+// Natural logarithm for the region kernels: x = 2^e m with sqrt(1/2) < m <= sqrt(2), f = m - 1, s = f / (2 + f),
+// ln(1 + f) = 2 atanh(s) = f - f^2/2 + s (f^2/2 + s^2 P(s^2)) with P a degree-6 fit of (2 atanh(s)/s - 2)/s^2 on
+// s^2 <= 0.03 (tools/gen_tables.py --fastmath; fit error 4e-16, below 1 ulp overall), e ln 2 added in two parts.
+// Zero, negative, subnormal, infinite and NaN arguments go to the library.
+#if defined(__CUDACC__)
+static __device__ __noinline__ double log_library(double x) { return log(x); }
+#endif
+SPB_HD real log_(real x) {
+#if defined(__CUDA_ARCH__)
+    const int hi = __double2hiint(x);
+    if ((unsigned int)(hi - 0x00100000) >= 0x7fe00000u) return log_library(x);
+    int e = (hi >> 20) - 1023;
+    double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));  // [1, 2)
+    const bool upper = m > 1.4142135623730951;
+    m = upper ? m * 0.5 : m;
+    e = upper ? e + 1 : e;
+    const double f = m - 1.0;
+    const double s = f * rcp_onscale(2.0 + f);
+    const double u = s * s;
+    double p = fm::LOGC[0];
+#pragma unroll
+    for (int k = 1; k < 7; ++k) p = fma(p, u, fm::LOGC[k]);
+    // f - f^2/2 + s (f^2/2 + R), R = s^2 P(s^2): the rounded quotient s multiplies only second-order terms
+    const double hfsq = 0.5 * f * f;
+    const double l1 = f - (hfsq - s * fma(u, p, hfsq));
+    const double fe = (double)e;
+    return fma(fe, 0.6931471805592082, fma(fe, 7.371002565167799e-13, l1));  // ln 2 = 40-bit head + tail
+#else
+    return log(x);
+#endif
+}
 
 // sin and cos of the same argument in one call.  BOUNDED: the caller guarantees |x| < 2^20 (no fallback branch)
 template <bool BOUNDED = false>
@@ -348,7 +411,7 @@ SPB_HD cplx clog_(cplx a, int &ierr) {
         ierr = 1;
         return cplx(real(0.0), real(0.0));
     }
-    return cplx(log(cabs_(a)), atan2(a.im, a.re));
+    return cplx(log_(cabs_(a)), atan2(a.im, a.re));
 }
 SPB_HD cplx clog_(cplx a) {
     int ie;
@@ -407,34 +470,7 @@ struct WShared {
 };
 SPB_HD cplx w_recip(cplx w, real raz) { return cplx(w.re * raz, -w.im * raz) * raz; }
 SPB_HD cplx w_rsqrt(cplx w, real az, real raz) { return conj(csqrt_mod(w, az)) * raz; }
-#if defined(__CUDA_ARCH__)
-// Branch-free reciprocal and reciprocal square root for arguments known to be on scale (the fused region has
-// 21.78 <= |w| < 32767): hardware seed (about 20 bits) and one third-order correction, error below 1 ulp.  The
-// library forms carry a slow-path branch each, which also keeps the compiler from scheduling the independent
-// exp / sincos arithmetic across them.
-__device__ __forceinline__ double rcp_onscale(double x) {
-    double y;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    const double e = fma(-x, y, 1.0);
-    return fma(y, fma(e, e, e), y);  // y (1 + e + e^2)
-}
-__device__ __forceinline__ double rsqrt_onscale(double x) {
-    double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    const double e = fma(-x * y, y, 1.0);              // 1 - x y^2
-    return fma(y, e * fma(0.375, e, 0.5), y);          // y (1 + e/2 + 3 e^2/8)
-}
-#endif
 // az < 0: the modulus is not known yet (fused region kernel: |w| and 1/|w| come out of one reciprocal square root)
-// 1/x for an argument known to be far from the ends of the exponent range (loop counters, moduli inside a region):
-// the branch-free form on the device, a plain division on the host
-SPB_HD real rcp_fast(real x) {
-#if defined(__CUDA_ARCH__)
-    return rcp_onscale(x);
-#else
-    return real(1.0) / x;
-#endif
-}
 SPB_HD WShared w_shared(cplx w, real az, bool need_em) {
     WShared s;
 #if defined(__CUDA_ARCH__)

@@ -46,6 +46,8 @@ SPB_FN real gamln(real z, int &ierr) {
             s = s + trm;
         }
     }
+    // (library logarithm here on purpose: the Stirling form multiplies it by z ~ 10 and cancels to O(0.1) for the
+    // arguments 1 + dnu of the Temme series, which amplifies half an ulp of difference to the CPU restatement)
     if (zinc == real(0.0)) {
         real tlg = log(z);
         return z * (tlg - real(1.0)) + real(0.5) * (con - tlg) + s;

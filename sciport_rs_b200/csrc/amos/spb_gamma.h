@@ -143,7 +143,7 @@ SPB_FN real lgamma_pos(real x) {
     const real hl2pi = 0.91893853320467274178;   // ln(2 pi)/2
     if (x >= real(12.0)) {
         if (x > real(1.0e305)) return real(1.0) / real(0.0);
-        real lx = log(x);
+        real lx = log_(x);
         return (x - real(0.5)) * lx - x + hl2pi + (x < real(1.0e17) ? stirling_tail(x) : real(0.0));
     }
     // (0, 12): lgamma(1+t), |t| <= 1/2, plus the log of the recurrence product
@@ -153,7 +153,7 @@ SPB_FN real lgamma_pos(real x) {
         t = x - m;
         real prod = real(1.0) + t;
         for (real j = 2.0; j < m; j += real(1.0)) prod *= (t + j);
-        extra = log(prod);  // lgamma(m+t) = lgamma(1+t) + ln((1+t)(2+t)...(m-1+t))
+        extra = log_(prod);  // lgamma(m+t) = lgamma(1+t) + ln((1+t)(2+t)...(m-1+t))
     } else if (x > real(1.5)) {
         t = x - real(2.0);
         extra = log1p(t);  // lgamma(2+t) = lgamma(1+t) + ln(1+t)
@@ -162,7 +162,7 @@ SPB_FN real lgamma_pos(real x) {
         extra = 0.0;
     } else {
         t = x;
-        extra = -log(x);  // lgamma(t) = lgamma(1+t) - ln t
+        extra = -log_(x);  // lgamma(t) = lgamma(1+t) - ln t
     }
     real s = real(LG1[31]);
 #pragma unroll

@@ -396,7 +396,7 @@ SPB_FN int bknu_body(cplx z, real fnu, int kode, int n, Y y, real tol, real elim
                 real akk = fpi * ak / (tol * sqrt(a2));
                 real aa = real(3.0) * t1 / (real(1.0) + caz);
                 real bb = real(14.7) * t1 / (real(28.0) + caz);
-                akk = (log(akk) + caz * cos(aa) / (real(1.0) + real(0.008) * caz)) / cos(bb);
+                akk = (log_(akk) + caz * cos(aa) / (real(1.0) + real(0.008) * caz)) / cos(bb);
                 fk = real(0.12125) * akk * akk / caz + real(1.5);
             }
             // backward recurrence loop of the Miller algorithm

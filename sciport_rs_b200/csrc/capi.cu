@@ -852,7 +852,7 @@ int spb_sinc(const double *x, double *out, int64_t n, const spb_exec *ex) {
     });
 }
 int spb_devmath(int which, const double *x, double *out, int64_t n, const spb_exec *ex) {
-    if (which < 0 || which > 3) return fail(SPB_E_ARG, "which must be 0 (exp), 1 (exp(-x)), 2 (sin) or 3 (cos)");
+    if (which < 0 || which > 4) return fail(SPB_E_ARG, "which must be 0 (exp), 1 (exp(-x)), 2 (sin), 3 (cos) or 4 (log)");
     return run_map(ex, n, 8, 8, x, out, [which](const void *i, void *o, long long m, cudaStream_t st) {
         launch_devmath(which, (const double *)i, (double *)o, m, st);
     });

@@ -120,8 +120,8 @@ void launch_first_error(const int *ierr, long long n, unsigned long long *packed
 
 // ---------------------------------------------------------------- gamma / lgamma / sinc (HBM-bound)
 // two points per thread through one 16-byte load / store
-// WHICH 0..2: the companions; 3..6: the device transcendentals of the region kernels (exp, exp(-x) as the second
-// member of the pair, sin, cos), exported through spb_devmath so that their accuracy is testable on its own
+// WHICH 0..2: the companions; 3..7: the device transcendentals of the region kernels (exp, exp(-x) as the second
+// member of the pair, sin, cos, log), exported through spb_devmath so that their accuracy is testable on its own
 template <int WHICH>
 __device__ __forceinline__ double gfun(double x) {
     if (WHICH == 0) return spb::gamma_real(x);
@@ -133,6 +133,7 @@ __device__ __forceinline__ double gfun(double x) {
         spb::exp_pair(x, ep, em);
         return em;
     }
+    if (WHICH == 7) return spb::log_(x);
     double sn, cs;
     spb::sincos_(x, sn, cs);
     return WHICH == 5 ? sn : cs;
@@ -185,7 +186,8 @@ void launch_devmath(int which, const double *x, double *out, long long n, cudaSt
         case 0: launch_real_map<3>(x, out, n, st); break;
         case 1: launch_real_map<4>(x, out, n, st); break;
         case 2: launch_real_map<5>(x, out, n, st); break;
-        default: launch_real_map<6>(x, out, n, st); break;
+        case 3: launch_real_map<6>(x, out, n, st); break;
+        default: launch_real_map<7>(x, out, n, st); break;
     }
 }
 

@@ -279,9 +279,9 @@ def sinc(x):
 
 
 def devmath(which, x):
-    """The device transcendentals the region kernels use ('exp', 'expm' = exp(-x), 'sin', 'cos'), for accuracy
+    """The device transcendentals the region kernels use ('exp', 'expm' = exp(-x), 'sin', 'cos', 'log'), for accuracy
     tests of the library itself."""
-    code = {"exp": 0, "expm": 1, "sin": 2, "cos": 3}[which]
+    code = {"exp": 0, "expm": 1, "sin": 2, "cos": 3, "log": 4}[which]
     return _real_map(lambda a, b, n, ex: lib.spb_devmath(code, a, b, n, ex), x)
 
 

@@ -584,3 +584,18 @@ def test_device_transcendentals(special):
         err = np.abs(got.astype(np.longdouble) - ref)
         assert float(err[small].max()) <= 2 * 2.220446049250313e-16, (which, float(err[small].max()))
         assert np.all(np.abs(got) <= 1.0)
+    # log: <= 1.5 ulp on positive normal arguments (tight around 1, where the result is small), library semantics
+    # for zero, negative, subnormal, infinite and NaN arguments
+    w = np.concatenate([10 ** rng.uniform(-307, 308, 200000), 1 + rng.uniform(-0.5, 0.5, 100000),
+                        1 + 10 ** rng.uniform(-16, -1, 20000) * rng.choice([-1, 1], 20000),
+                        np.array([1.0, 2.0, 0.5, np.sqrt(2.0), 1.7976931348623157e308, 2.2250738585072014e-308])])
+    got = to_np(special.devmath("log", torch.from_numpy(w).cuda()))
+    ref = np.log(w.astype(np.longdouble))
+    want = ref.astype(np.float64)
+    ulp = np.abs((got.astype(np.longdouble) - ref) / np.spacing(np.abs(want) + 5e-324).astype(np.longdouble))
+    assert got[0 + 320000] == 0.0 and float(ulp.max()) <= 1.5, float(ulp.max())
+    odd = np.array([0.0, -0.0, -1.0, 5e-324, 1e-310, np.inf, np.nan])
+    got = to_np(special.devmath("log", torch.from_numpy(odd).cuda()))
+    with np.errstate(all="ignore"):
+        want = np.log(odd)
+    assert np.array_equal(np.isnan(got), np.isnan(want)) and np.array_equal(got[~np.isnan(want)], want[~np.isnan(want)])

@@ -222,12 +222,15 @@ def gen_fastmath():
     cosc = mp.chebyfit(Q, [mp.mpf("1e-30"), q], 7)
     expe = [1 / mp.factorial(k) for k in range(12, 1, -2)]
     expo = [1 / mp.factorial(k) for k in range(13, 2, -2)]
-    return sinc, cosc, expe, expo
+    # log: (2 atanh(s)/s - 2)/s^2 as a polynomial in u = s^2 on u <= 1.02 ((sqrt 2 - 1)/(sqrt 2 + 1))^2
+    L = lambda u: (2 * mp.atanh(mp.sqrt(u)) / mp.sqrt(u) - 2) / u
+    logc = mp.chebyfit(L, [mp.mpf("1e-30"), mp.mpf("0.02944") * mp.mpf("1.02")], 7)
+    return sinc, cosc, expe, expo, logc
 
 
 def main():
     if "--fastmath" in sys.argv:
-        for name, t in zip(("SINC", "COSC", "EXPE", "EXPO"), gen_fastmath()):
+        for name, t in zip(("SINC", "COSC", "EXPE", "EXPO", "LOGC"), gen_fastmath()):
             print(name, ", ".join("%.17e" % float(c) for c in t))
         return
     gln = gen_gln()
