@@ -276,16 +276,9 @@ SPB_HD real rcp_fast(real x) {
 #if defined(__CUDACC__)
 static __device__ __noinline__ double log_library(double x) { return log(x); }
 #endif
-SPB_HD real log_(real x) {
 #if defined(__CUDA_ARCH__)
-    const int hi = __double2hiint(x);
-    if ((unsigned int)(hi - 0x00100000) >= 0x7fe00000u) return log_library(x);
-    int e = (hi >> 20) - 1023;
-    double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));  // [1, 2)
-    const bool upper = m > 1.4142135623730951;
-    m = upper ? m * 0.5 : m;
-    e = upper ? e + 1 : e;
-    const double f = m - 1.0;
+// ln(2^e (1 + f)), sqrt(1/2) - 1 < f <= sqrt(2) - 1
+__device__ __forceinline__ double log_core(double f, int e) {
     const double s = f * rcp_onscale(2.0 + f);
     const double u = s * s;
     double p = fm::LOGC[0];
@@ -296,8 +289,29 @@ SPB_HD real log_(real x) {
     const double l1 = f - (hfsq - s * fma(u, p, hfsq));
     const double fe = (double)e;
     return fma(fe, 0.6931471805592082, fma(fe, 7.371002565167799e-13, l1));  // ln 2 = 40-bit head + tail
+}
+#endif
+SPB_HD real log_(real x) {
+#if defined(__CUDA_ARCH__)
+    const int hi = __double2hiint(x);
+    if ((unsigned int)(hi - 0x00100000) >= 0x7fe00000u) return log_library(x);
+    int e = (hi >> 20) - 1023;
+    double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));  // [1, 2)
+    const bool upper = m > 1.4142135623730951;
+    m = upper ? m * 0.5 : m;
+    e = upper ? e + 1 : e;
+    return log_core(m - 1.0, e);
 #else
     return log(x);
+#endif
+}
+// ln(1 + t) for |t| <= 1/2 with the relative accuracy of log1p near t = 0 (t itself is the series argument there)
+SPB_HD real log1p_half_(real t) {
+#if defined(__CUDA_ARCH__)
+    if (t >= -0.29 && t <= 0.41) return log_core(t, 0);
+    return log_(1.0 + t);
+#else
+    return log1p(t);
 #endif
 }
 

@@ -17,7 +17,7 @@ namespace spb {
 SPB_HD real stirling_tail(real x) {
 #include "spb_tables_gln.inc"
     (void)GLN;
-    real r = real(1.0) / x;
+    real r = rcp_fast(x);  // x >= 12
     real r2 = r * r;
     real s = real(CF[8]);
 #pragma unroll
@@ -57,7 +57,7 @@ __device__ __forceinline__ void log_dd(double y, double &hi, double &lo) {
     const double f = m - 1.0;            // exact
     const double dh = m + 1.0;           // may round: keep the residual
     const double dl = m - (dh - 1.0);
-    const double r = 1.0 / dh;
+    const double r = rcp_onscale(dh);  // 1.7 <= dh <= 2.42; the residual below absorbs its rounding
     const double sh = f * r;
     const double sl = (fma(-sh, dh, f) - sh * dl) * r;
     const double s2 = sh * sh;
@@ -107,7 +107,7 @@ SPB_FN real gamma_pos(real x) {
         const double th = t1 + rest;
         const double tl = rest - (th - t1);
         const double r = exp_(0.5 * th);
-        return (r * fma(r, tl, r)) / prod;
+        return (r * fma(r, tl, r)) * rcp_onscale(prod);  // 1 <= prod < 12^12
     }
 #endif
     real w = pow(y, real(0.5) * y - real(0.25));
@@ -141,22 +141,26 @@ SPB_FN real lgamma_pos(real x) {
 #include "spb_tables_gamma.inc"
     const real euler1 = 0.42278433509846713939;  // 1 - Euler's constant
     const real hl2pi = 0.91893853320467274178;   // ln(2 pi)/2
-    if (x >= real(12.0)) {
-        if (x > real(1.0e305)) return real(1.0) / real(0.0);
-        real lx = log_(x);
-        return (x - real(0.5)) * lx - x + hl2pi + (x < real(1.0e17) ? stirling_tail(x) : real(0.0));
-    }
-    // (0, 12): lgamma(1+t), |t| <= 1/2, plus the log of the recurrence product
-    real t, extra;
     if (x > real(2.5)) {
-        real m = floor(x + real(0.5));  // x = m + t
-        t = x - m;
-        real prod = real(1.0) + t;
-        for (real j = 2.0; j < m; j += real(1.0)) prod *= (t + j);
-        extra = log_(prod);  // lgamma(m+t) = lgamma(1+t) + ln((1+t)(2+t)...(m-1+t))
-    } else if (x > real(1.5)) {
+        // Stirling series at y = x + n >= 12, minus the log of the recurrence product x (x+1) ... (x+n-1) < 12^10:
+        // lgamma >= 0.28 on this branch, so the absolute error of the two logarithms (a few 1e-15) stays far
+        // below the tolerance; the zeros at 1 and 2 belong to the Maclaurin branch below
+        if (x > real(1.0e305)) return real(1.0) / real(0.0);
+        real prod = 1.0;
+        real y = x;
+        while (y < real(12.0)) {
+            prod *= y;
+            y += real(1.0);
+        }
+        real ly = log_(y);
+        real r = (y - real(0.5)) * ly - y + hl2pi + (y < real(1.0e17) ? stirling_tail(y) : real(0.0));
+        return x < real(12.0) ? r - log_(prod) : r;
+    }
+    // (0, 2.5]: lgamma(1+t), |t| <= 1/2, plus the log term of the recurrence
+    real t, extra;
+    if (x > real(1.5)) {
         t = x - real(2.0);
-        extra = log1p(t);  // lgamma(2+t) = lgamma(1+t) + ln(1+t)
+        extra = log1p_half_(t);  // lgamma(2+t) = lgamma(1+t) + ln(1+t)
     } else if (x > real(0.5)) {
         t = x - real(1.0);
         extra = 0.0;
@@ -167,7 +171,7 @@ SPB_FN real lgamma_pos(real x) {
     real s = real(LG1[31]);
 #pragma unroll
     for (int k = 30; k >= 0; --k) s = s * t + real(LG1[k]);
-    return extra + (t * euler1 - log1p(t)) + s * t * t;
+    return extra + (t * euler1 - log1p_half_(t)) + s * t * t;
 }
 
 SPB_FN real lgamma_real(real x) {
