@@ -215,6 +215,7 @@ int enqueue_chunk(const DevJob &job_in, ScratchSet &ss, int sms, int flags, cuda
         const bool ktype = !(job.fam == SPB_FN_J || job.fam == SPB_FN_I);
         const int mode = fuse_mode();
         job.fuse = (ktype && !(flags & SPB_PATH_MONOLITHIC) && (mode >= 2 || (mode == 1 && job.v_stride == 0))) ? 1 : 0;
+        job.pdl = (pdl_enabled() && job.v_stride == 0) ? 1 : 0;
     }
     if (flags & SPB_PATH_MONOLITHIC) {
         p.mark(SPB_K_MONOLITHIC, st);

@@ -14,11 +14,11 @@ template <int FAM, int KODE>
 struct FusedLaunch {
     static void run(const DevJob &job, const Scratch &s, int sms, cudaStream_t st) {
         if (job.v_stride == 0)
-            k_ipass<spb::IREG_ASYI, true, FAM, KODE>
-                <<<resident_grid(k_ipass<spb::IREG_ASYI, true, FAM, KODE>, 128, sms), 128, 0, st>>>(job, s);
+            launch_pdl(job.pdl != 0, k_ipass<spb::IREG_ASYI, true, FAM, KODE>,
+                       resident_grid(k_ipass<spb::IREG_ASYI, true, FAM, KODE>, 128, sms), 128, st, job, s);
         else
-            k_ipass<spb::IREG_ASYI, false, FAM, KODE>
-                <<<resident_grid(k_ipass<spb::IREG_ASYI, false, FAM, KODE>, 128, sms), 128, 0, st>>>(job, s);
+            launch_pdl(job.pdl != 0, k_ipass<spb::IREG_ASYI, false, FAM, KODE>,
+                       resident_grid(k_ipass<spb::IREG_ASYI, false, FAM, KODE>, 128, sms), 128, st, job, s);
     }
 };
 // J and I never need K

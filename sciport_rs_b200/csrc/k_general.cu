@@ -9,6 +9,7 @@ namespace spbk {
 
 // list / len: the general list of the classifier, or the second-stage list k_general_shortcuts left behind
 __global__ void __launch_bounds__(128) k_general(DevJob job, const unsigned int *list, const unsigned int *len) {
+    pdl_enter();
     const unsigned int count = *len;
     const unsigned int stride = gridDim.x * blockDim.x;
 #pragma unroll 1
@@ -26,6 +27,7 @@ __global__ void __launch_bounds__(128) k_general(DevJob job, const unsigned int 
 // the few that really need the drivers are appended to a second list, so that the expensive kernel runs them in
 // full warps instead of one or two lanes per warp.
 __global__ void __launch_bounds__(256) k_general_shortcuts(DevJob job, Scratch s) {
+    pdl_enter();
     const unsigned int count = s.bins[GLIST_LEN_SLOT];
     const unsigned int stride = gridDim.x * blockDim.x;
     for (unsigned int t = blockIdx.x * blockDim.x + threadIdx.x; t < count; t += stride) {
@@ -64,11 +66,13 @@ int launch_general(const DevJob &job, const Scratch &s, int sms, cudaStream_t st
     const bool shortcuts = job.kode == 1 && (job.fam == spb::FAM_K || job.fam == spb::FAM_H1 ||
                                              job.fam == spb::FAM_H2 || job.fam == spb::FAM_Y);
     if (shortcuts) {
-        k_general_shortcuts<<<sms * 4, 256, 0, st>>>(job, s);
-        k_general<<<resident_grid(k_general, 128, sms), 128, 0, st>>>(job, s.perm_k, s.bins + SLOT_G2);
+        launch_pdl(job.pdl != 0, k_general_shortcuts, sms * 4, 256, st, job, s);
+        launch_pdl(job.pdl != 0, k_general, resident_grid(k_general, 128, sms), 128, st, job, (const unsigned int *)s.perm_k,
+                   (const unsigned int *)(s.bins + SLOT_G2));
         return 2;
     }
-    k_general<<<resident_grid(k_general, 128, sms), 128, 0, st>>>(job, s.glist, s.bins + GLIST_LEN_SLOT);
+    launch_pdl(job.pdl != 0, k_general, resident_grid(k_general, 128, sms), 128, st, job, (const unsigned int *)s.glist,
+               (const unsigned int *)(s.bins + GLIST_LEN_SLOT));
     return 1;
 }
 

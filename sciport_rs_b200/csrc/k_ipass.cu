@@ -16,9 +16,9 @@ namespace spbk {
 template <int REGION>
 static void launch_ipass_region(const DevJob &job, const Scratch &s, int sms, cudaStream_t st) {
     if (job.v_stride == 0)
-        k_ipass<REGION, true><<<resident_grid(k_ipass<REGION, true>, 128, sms), 128, 0, st>>>(job, s);
+        launch_pdl(job.pdl != 0, k_ipass<REGION, true>, resident_grid(k_ipass<REGION, true>, 128, sms), 128, st, job, s);
     else
-        k_ipass<REGION, false><<<resident_grid(k_ipass<REGION, false>, 128, sms), 128, 0, st>>>(job, s);
+        launch_pdl(job.pdl != 0, k_ipass<REGION, false>, resident_grid(k_ipass<REGION, false>, 128, sms), 128, st, job, s);
 }
 
 void launch_ipass(const DevJob &job, const Scratch &s, int region, int sms, cudaStream_t st) {
@@ -34,8 +34,8 @@ void launch_ipass(const DevJob &job, const Scratch &s, int region, int sms, cuda
         case spb::IREG_MLRI: launch_ipass_region<spb::IREG_MLRI>(job, s, sms, st); break;
         case spb::IREG_WRSK:
             if (job.v_stride != 0)
-                k_ipass_sorted<spb::IREG_WRSK>
-                    <<<resident_grid(k_ipass_sorted<spb::IREG_WRSK>, 128, sms), 128, 0, st>>>(job, s);
+                launch_pdl(job.pdl != 0, k_ipass_sorted<spb::IREG_WRSK>, resident_grid(k_ipass_sorted<spb::IREG_WRSK>, 128, sms), 128, st,
+                           job, s);
             else
                 launch_ipass_region<spb::IREG_WRSK>(job, s, sms, st);
             break;

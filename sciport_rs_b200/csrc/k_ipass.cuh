@@ -59,6 +59,7 @@ __device__ __forceinline__ void ipass_point(const DevJob &job, const Scratch &s,
 // FAM >= 0: the fused form of the kernel with the family and the scaling flag as compile-time constants
 template <int REGION, bool SCALAR, int FAM = -1, int KODE = 0>
 __global__ void __launch_bounds__(128, FAM >= 0 ? SPB_FUSED_MINB : SPB_IPASS_MINB(REGION)) k_ipass(DevJob job, Scratch s) {
+    pdl_enter();
     if (FAM >= 0) {
         job.fam = FAM;
         job.kode = KODE;
@@ -103,6 +104,7 @@ __global__ void __launch_bounds__(128, FAM >= 0 ? SPB_FUSED_MINB : SPB_IPASS_MIN
 // Per-element orders, Miller / Wronskian region: batches grouped by predicted work (spb_dev.cuh)
 template <int REGION>
 __global__ void __launch_bounds__(128) k_ipass_sorted(DevJob job, Scratch s) {
+    pdl_enter();
     __shared__ SortSmem sm;
     __shared__ unsigned int s_idx[SORT_B];
     __shared__ double2 s_z[SORT_B];

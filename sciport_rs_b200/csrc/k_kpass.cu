@@ -41,6 +41,7 @@ __device__ __forceinline__ void kpass_point(const DevJob &job, const Scratch &s,
 // shared memory, not in registers of the persistent loop
 template <int FAM, int KODE>
 __global__ void __launch_bounds__(128, SPB_KPASS_MINB) k_kpass(DevJob job, Scratch s) {
+    pdl_enter();
     job.fam = FAM;  // compile-time family and scaling flag (dispatch_fam_kode)
     job.kode = KODE;
     __shared__ spb::OrderPhase s_ph;
@@ -87,6 +88,7 @@ __global__ void __launch_bounds__(128, SPB_KPASS_MINB) k_kpass(DevJob job, Scrat
 // (spb_dev.cuh) instead of the register pipeline above.
 template <int FAM, int KODE>
 __global__ void __launch_bounds__(128, SPB_KPASS_MINB) k_kpass_sorted(DevJob job, Scratch s) {
+    pdl_enter();
     job.fam = FAM;
     job.kode = KODE;
     __shared__ SortSmem sm;
@@ -137,9 +139,9 @@ template <int FAM, int KODE>
 struct KpassLaunch {
     static void run(const DevJob &job, const Scratch &s, int sms, cudaStream_t st) {
         if (job.v_stride != 0 || job.n < 2)
-            k_kpass_sorted<FAM, KODE><<<resident_grid(k_kpass_sorted<FAM, KODE>, 128, sms), 128, 0, st>>>(job, s);
+            launch_pdl(job.pdl != 0, k_kpass_sorted<FAM, KODE>, resident_grid(k_kpass_sorted<FAM, KODE>, 128, sms), 128, st, job, s);
         else
-            k_kpass<FAM, KODE><<<resident_grid(k_kpass<FAM, KODE>, 128, sms), 128, 0, st>>>(job, s);
+            launch_pdl(job.pdl != 0, k_kpass<FAM, KODE>, resident_grid(k_kpass<FAM, KODE>, 128, sms), 128, st, job, s);
     }
 };
 // J and I never reach the K pass: their instantiations stay empty

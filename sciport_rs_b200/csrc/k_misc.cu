@@ -4,11 +4,20 @@
 #include "spb_dev.cuh"
 #include "amos/spb_gamma.h"
 #include <chrono>
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <utility>
 
 namespace spbk {
+
+bool pdl_enabled() {
+    static const bool on = [] {
+        const char *e = getenv("SPB_PDL");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
 
 // Resident CTAs per SM of one kernel on the current device (cudaOccupancyMaxActiveBlocksPerMultiprocessor),
 // cached per (kernel, device, CTA size): persistent grids are sized from it on every launch.

@@ -78,6 +78,7 @@ __device__ __forceinline__ unsigned int field_g(const Packed &p) {
 // FAM / KODE: the job's family and scaling flag as compile-time constants (dispatch_fam_kode)
 template <int FAM, int KODE>
 __global__ void __launch_bounds__(256) k_classify(DevJob job, Scratch s) {
+    pdl_enter();
     job.fam = FAM;
     job.kode = KODE;
     __shared__ unsigned int hist[NBINS];
@@ -155,6 +156,7 @@ __global__ void __launch_bounds__(256) k_classify(DevJob job, Scratch s) {
 // counters per thread, coalesced), so blockcnt[b][t] becomes the offset of tile t inside bin b.  The last CTA to
 // finish turns the bin totals into the bin start offsets (bins[0..8]) and the general-list length.
 __global__ void __launch_bounds__(1024) k_scan(Scratch s) {
+    pdl_enter();
     __shared__ unsigned int warp_tot[32];
     __shared__ unsigned int carry_s;
     const int b = blockIdx.x;
@@ -220,6 +222,7 @@ __global__ void __launch_bounds__(1024) k_scan(Scratch s) {
 }
 
 __global__ void __launch_bounds__(256) k_scatter(DevJob job, Scratch s) {
+    pdl_enter();
     __shared__ unsigned long long warp_tot[8][NWORDS];
     __shared__ unsigned int tile_base[NBINS], lstart[NBINS], seg_total[3];
     __shared__ unsigned int stage[3][TILE];
@@ -349,7 +352,7 @@ __global__ void __launch_bounds__(256) k_scatter(DevJob job, Scratch s) {
 template <int FAM, int KODE>
 struct ClassifyLaunch {
     static void run(const DevJob &job, const Scratch &s, cudaStream_t st) {
-        k_classify<FAM, KODE><<<s.nblocks, 256, 0, st>>>(job, s);
+        launch_pdl(job.pdl != 0, k_classify<FAM, KODE>, s.nblocks, 256, st, job, s);
     }
 };
 
@@ -358,8 +361,8 @@ void launch_classify(const DevJob &job, const Scratch &s, cudaStream_t st) {
 }
 
 void launch_scan_scatter(const DevJob &job, const Scratch &s, cudaStream_t st) {
-    k_scan<<<NBINS, 1024, 0, st>>>(s);
-    k_scatter<<<s.nblocks, 256, 0, st>>>(job, s);
+    launch_pdl(job.pdl != 0, k_scan, NBINS, 1024, st, s);
+    launch_pdl(job.pdl != 0, k_scatter, s.nblocks, 256, st, job, s);
 }
 
 }  // namespace spbk

@@ -12,6 +12,7 @@ struct DevJob {
     int kode;  // 1 | 2
     int sem;   // 0 raw AMOS, 1 scipy-compatible post-processing
     int fuse;  // 1: points needing I and K with I in the large-|w| region are evaluated by the fused region kernel
+    int pdl;   // 1: the kernels of this chunk are launched as programmatic dependents of each other (launch_pdl)
     const double *v;
     long long v_stride;  // 0 = broadcast
     const double2 *z;    // complex input, or
@@ -65,6 +66,36 @@ constexpr int BINS_WORDS = 64;
 // Persistent grids are sized to exactly the number of CTAs that are resident at once
 // (SM count x occupancy), so every CTA starts in the first wave and the grid-stride
 // loops finish together.
+// Programmatic dependent launch for the kernels of one pipeline: every pipeline kernel begins with
+// pdl_enter() (griddepcontrol.launch_dependents, then griddepcontrol.wait), so the NEXT kernel's CTAs may be
+// scheduled as soon as all CTAs of this one have started, and they block in their own wait until this kernel has
+// completed and its writes are visible.  Results are those of plain stream order; what overlaps is the launch
+// latency and the ramp-up of each kernel with the tail of its predecessor (a dozen launches per chunk, several of
+// them over empty bins).  Used for jobs with a broadcast scalar order (DevJob::pdl): with per-element orders the
+// kernels run for milliseconds and the early dependents measured 2-3 % slower.  SPB_PDL=0 in the environment
+// falls back to plain launches everywhere.
+bool pdl_enabled();
+template <class... KArgs, class... Args>
+inline void launch_pdl(bool on, void (*kernel)(KArgs...), int grid, int block, cudaStream_t st, Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned int)grid, 1, 1);
+    cfg.blockDim = dim3((unsigned int)block, 1, 1);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = on ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#if defined(__CUDACC__)
+__device__ __forceinline__ void pdl_enter() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+#endif
+
 // The occupancy of every kernel is looked up once per (kernel, device) and cached (k_misc.cu).
 int resident_ctas_per_sm(const void *kernel, int threads);
 template <class Kernel>
