@@ -106,6 +106,68 @@ SPB_FN void airy_series(cplx z, real az, real fid, real tol, cplx &s1, cplx &s2)
     }
 }
 
+// Ai / Ai' for |z| <= 1 (Maclaurin series): the branch of airy() the lean small-|z| kernel runs on its own
+SPB_FN cplx airy_small(cplx z, real az, int id, int kode) {
+    const real tth = 6.66666666666666667e-01;
+    const real c1 = 3.55028053887817240e-01;
+    const real c2 = 2.58819403792806799e-01;
+    const real tol = SPB_TOL;
+    const real fid = real(id);
+    cplx ai;
+    if (az < tol) {
+        real aa = real(1.0e3) * SPB_D1MACH1;
+        cplx s1(0.0, 0.0);
+        if (id != 1) {
+            if (az > aa) s1 = z * c2;
+            return cplx(c1 - s1.re, -s1.im);
+        }
+        ai = cplx(-c2, 0.0);
+        aa = sqrt(aa);
+        if (az > aa) s1 = (z * z) * real(0.5);
+        return ai + s1 * c1;
+    }
+    cplx s1, s2;
+    airy_series(z, az, fid, tol, s1, s2);
+    if (id != 1) {
+        ai = s1 * c1 - (z * s2) * c2;
+    } else {
+        ai = -s2 * c2;
+        if (az > tol) {
+            real cc = c1 / (real(1.0) + fid);
+            ai = ai + ((z * z) * s1) * cc;
+        }
+    }
+    if (kode == 1) return ai;
+    cplx zta = (z * csqrt_(z)) * tth;
+    return ai * cexp_(zta);
+}
+
+// Bi / Bi' for |z| <= 1 (Maclaurin series)
+SPB_FN cplx biry_small(cplx z, real az, int id, int kode) {
+    const real tth = 6.66666666666666667e-01;
+    const real c1 = 6.14926627446000736e-01;
+    const real c2 = 4.48288357353826359e-01;
+    const real tol = SPB_TOL;
+    const real fid = real(id);
+    cplx bi;
+    if (az < tol) return cplx(c1 * (real(1.0) - fid) + fid * c2, 0.0);
+    cplx s1, s2;
+    airy_series(z, az, fid, tol, s1, s2);
+    if (id != 1) {
+        bi = s1 * c1 + (z * s2) * c2;
+    } else {
+        bi = s2 * c2;
+        if (az > tol) {
+            real cc = c1 / (real(1.0) + fid);
+            bi = bi + ((z * z) * s1) * cc;
+        }
+    }
+    if (kode == 1) return bi;
+    cplx zta = (z * csqrt_(z)) * tth;
+    real eaa = exp_(-rabs(zta.re));
+    return bi * eaa;
+}
+
 // Ai (id=0) or Ai' (id=1).  Returns value; nz/ierr follow the AMOS convention.
 SPB_FN cplx airy(cplx z, int id, int kode, int &nz, int &ierr) {
     const real tth = 6.66666666666666667e-01;
@@ -118,34 +180,7 @@ SPB_FN cplx airy(cplx z, int id, int kode, int &nz, int &ierr) {
     real az = cabs_(z);
     real fid = real(id);
     cplx ai;
-    if (!(az > real(1.0))) {
-        if (az < tol) {
-            real aa = real(1.0e3) * SPB_D1MACH1;
-            cplx s1(0.0, 0.0);
-            if (id != 1) {
-                if (az > aa) s1 = z * c2;
-                return cplx(c1 - s1.re, -s1.im);
-            }
-            ai = cplx(-c2, 0.0);
-            aa = sqrt(aa);
-            if (az > aa) s1 = (z * z) * real(0.5);
-            return ai + s1 * c1;
-        }
-        cplx s1, s2;
-        airy_series(z, az, fid, tol, s1, s2);
-        if (id != 1) {
-            ai = s1 * c1 - (z * s2) * c2;
-        } else {
-            ai = -s2 * c2;
-            if (az > tol) {
-                real cc = c1 / (real(1.0) + fid);
-                ai = ai + ((z * z) * s1) * cc;
-            }
-        }
-        if (kode == 1) return ai;
-        cplx zta = (z * csqrt_(z)) * tth;
-        return ai * cexp_(zta);
-    }
+    if (!(az > real(1.0))) return airy_small(z, az, id, kode);
     // |z| > 1
     real fnu = (real(1.0) + fid) / real(3.0);
     real alaz = log(az);
@@ -240,24 +275,7 @@ SPB_FN cplx biry(cplx z, int id, int kode, int &ierr) {
     real az = cabs_(z);
     real fid = real(id);
     cplx bi;
-    if (!(az > real(1.0))) {
-        if (az < tol) return cplx(c1 * (real(1.0) - fid) + fid * c2, 0.0);
-        cplx s1, s2;
-        airy_series(z, az, fid, tol, s1, s2);
-        if (id != 1) {
-            bi = s1 * c1 + (z * s2) * c2;
-        } else {
-            bi = s2 * c2;
-            if (az > tol) {
-                real cc = c1 / (real(1.0) + fid);
-                bi = bi + ((z * z) * s1) * cc;
-            }
-        }
-        if (kode == 1) return bi;
-        cplx zta = (z * csqrt_(z)) * tth;
-        real eaa = exp_(-rabs(zta.re));
-        return bi * eaa;
-    }
+    if (!(az > real(1.0))) return biry_small(z, az, id, kode);
     real fnu = (real(1.0) + fid) / real(3.0);
     // min(0.5/tol, (2^31 - 1)/2)^(2/3), a constant of the arithmetic (binary64: the second argument of the min)
     real aa = real(1048575.9996744783);
