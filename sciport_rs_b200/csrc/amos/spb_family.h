@@ -367,17 +367,35 @@ SPB_FN int kpass_region(cplx w, real fnu, int kode, cplx &val, real az = real(-1
     return bknu_simple(w, fnu, kode, val, tol, elim, alim, az, ws);
 }
 
-// I_v(w) and K_v(w) of a KREG_FUSED point (large-|w| region of I): the quantities both routines need are
-// computed once.  Returns < 0 when either routine hands the point over to the general path.
+// I_v(w) and K_v(w) of a KREG_FUSED point (large-|w| region of I, |w| >= rl and 2|w| >= fnu^2 or fnu <= 1).  Both
+// functions have the same Hankel coefficients a_k(fnu) there,
+//     I_v(w) ~ e^w  / sqrt(2 pi w) sum (-1)^k a_k / w^k  (+ the second exponential),
+//     K_v(w) ~ e^-w sqrt(pi / 2w)  sum        a_k / w^k,
+// so the K series is the all-positive sum the I routine forms anyway for its second exponential: K costs one
+// complex product on top of I instead of the Miller algorithm the published region map runs here (third
+// departure from it, after the two of DESIGN.md section 2; |arg w| <= pi/2, so the remainder of the K series is
+// bounded by twice the first neglected term, DLMF 10.40(iii), and the convergence test of the I series bounds that
+// term by tol).  Shared quantities (1/w, 1/sqrt(w), sincos(Im w), exp(+-Re w)) are computed once.  Returns < 0
+// when the point has to go to the general path.
 SPB_FN int fused_ik_region(cplx w, real fnu, int kode, cplx &ival, int &inz, cplx &kval, int &knz, real az,
                            const OrderPhase *oph = nullptr) {
-    // exp(-Re w): factor of the unscaled K; the second exponential of I squares it
+    const real tol = SPB_TOL, elim = SPB_ELIM, alim = SPB_ALIM, rl = SPB_RL;
+    const real rthpi = 1.25331413731550025;  // sqrt(pi/2)
     // (az < 0: |w| not computed yet, see w_shared)
     const WShared ws = w_shared(w, az, kode == 1);
-    inz = ipass_region(IREG_ASYI, w, fnu, kode, ival, ws.az, oph, &ws);
+    cplx y[1], ksum(1.0, 0.0);
+    y[0] = cplx(0.0, 0.0);
+    inz = asyi(w, fnu, kode, 1, y, rl, tol, elim, alim, ws.az, oph, &ws, &ksum);
+    ival = y[0];
+    knz = 0;
     if (inz < 0) return inz;
-    knz = kpass_region(w, fnu, kode, kval, ws.az, &ws);
-    return knz < 0 ? knz : 0;
+    cplx coef = ws.rsq * rthpi;
+    if (kode == 1) {
+        if (w.re > alim) return -9;  // exp(-Re w) leaves the middle scaling level: like the lean K routine
+        coef = coef * cplx(ws.em * ws.cs, -ws.em * ws.sn);
+    }
+    kval = coef * ksum;
+    return 0;
 }
 
 // continuation K(w e^{i pi mr}) from (K(w), I(w)) for one member (acon with n = 1)

@@ -151,7 +151,8 @@ SPB_FN int seri(cplx z, real fnu, int kode, int n, Y y, real tol, real elim, rea
 // half an ulp of the leading sum once 2 Re z > 80 and is skipped there.
 template <class Y>
 SPB_FN int asyi(cplx z, real fnu, int kode, int n, Y y, real rl, real tol, real elim, real alim,
-                real az_known = real(-1.0), const OrderPhase *oph = nullptr, const WShared *ws = nullptr) {
+                real az_known = real(-1.0), const OrderPhase *oph = nullptr, const WShared *ws = nullptr,
+                cplx *ksum = nullptr) {
     static const double RJ[48] = {
         0.0, 1.0, 1.0 / 2, 1.0 / 3, 1.0 / 4, 1.0 / 5, 1.0 / 6, 1.0 / 7, 1.0 / 8, 1.0 / 9, 1.0 / 10, 1.0 / 11,
         1.0 / 12, 1.0 / 13, 1.0 / 14, 1.0 / 15, 1.0 / 16, 1.0 / 17, 1.0 / 18, 1.0 / 19, 1.0 / 20, 1.0 / 21,
@@ -245,6 +246,8 @@ SPB_FN int asyi(cplx z, real fnu, int kode, int n, Y y, real rl, real tol, real 
             }
         }
         if (!conv) return -2;
+        // the same terms with all signs positive are the large-|z| series of K (member of order fnu + n - 1 last)
+        if (ksum) *ksum = cs2;
         cplx s2 = cs1;
         if (second) s2 = s2 + (e2 * p1) * cs2;
         fdn = fdn + real(8.0) * dfnu + real(4.0);
