@@ -147,8 +147,9 @@ SPB_HD bool prepare_geometry(int fam, cplx z, Prep &p) {
     return left;
 }
 
-// fuse: points that need I_v(w) AND K_v(w) with I in the large-|w| region get kreg = KREG_FUSED (one routine
-// evaluates both, sharing 1/w, 1/sqrt(w), the sincos of Im w and exp(-Re w)) instead of a K bin.
+// fuse: K-type points whose w lies in the large-|w| region of I get kreg = KREG_FUSED instead of a K bin: one
+// routine evaluates I_v(w) and K_v(w) from the same series, sharing 1/w, 1/sqrt(w), the sincos of Im w and
+// exp(+-Re w) (also where the family needs K only: the series is several times cheaper than the Miller algorithm).
 SPB_FN Prep prepare(int fam, cplx z, real fnu, int kode, bool fuse = false) {
     const real fnul = SPB_FNUL, alim = SPB_ALIM, tol = SPB_TOL;
     Prep p;
@@ -211,6 +212,11 @@ SPB_FN Prep prepare(int fam, cplx z, real fnu, int kode, bool fuse = false) {
         } else if (fuse && p.ireg == IREG_ASYI) {
             p.kreg = KREG_FUSED;
         }
+    } else if (fuse && binu_region(p.w, fnu, 1, SPB_RL, SPB_FNUL, az) == IREG_ASYI) {
+        // I_v(w) is not needed here, but the point lies in the region where the fused routine takes K from the
+        // large-|w| series (a fraction of the cost of the Miller algorithm): same bin, the combine step ignores I
+        p.ireg = IREG_ASYI;
+        p.kreg = KREG_FUSED;
     }
     return p;
 }
@@ -285,10 +291,11 @@ SPB_HD bool fast_classify(int fam, cplx z, const FastOrder &o, int kode, bool fu
         if (!(o.c19 + x < alim)) return false;
     }
     kreg = o.kreg;
-    ireg = -1;
-    if (left) {
+    ireg = left ? IREG_ASYI : -1;
+    if (fuse) {
+        // the window is the large-|w| region of I: K comes from the same series whether or not I is needed
         ireg = IREG_ASYI;
-        if (fuse) kreg = KREG_FUSED;
+        kreg = KREG_FUSED;
     }
     return true;
 }
@@ -649,7 +656,8 @@ SPB_FN cplx pipeline_eval(int fam, cplx z, real fnu, int kode, int &ierr, int &n
         // the region passes see only the class (bins) and recompute the geometry: same thing here
         const int ireg = p.ireg, kreg = p.kreg;
         p = prepare_pass(fam, z);
-        if ((p.ireg >= 0) != (ireg >= 0)) p.combine = CMB_GENERAL;  // cannot happen; would show up as a path-1 mismatch
+        // (cannot happen except for fused points that do not need I; would show up as a path-1 mismatch)
+        if ((p.ireg >= 0) != (ireg >= 0) && kreg != KREG_FUSED) p.combine = CMB_GENERAL;
         p.ireg = ireg;
         p.kreg = kreg;
     }

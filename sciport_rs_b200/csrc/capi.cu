@@ -196,11 +196,11 @@ struct Prof {
 };
 
 // enqueue the whole pipeline for one chunk; returns number of kernel launches
-// SPB_FUSE (environment, read once): 0 never fuse, 1 (default) fuse for a broadcast scalar order, 2 always
+// SPB_FUSE (environment, read once): 0 never fuse, 1 fuse for a broadcast scalar order only, 2 (default) always
 static int fuse_mode() {
     static const int mode = [] {
         const char *e = getenv("SPB_FUSE");
-        return e ? atoi(e) : 1;
+        return e ? atoi(e) : 2;
     }();
     return mode;
 }
@@ -210,8 +210,8 @@ int enqueue_chunk(const DevJob &job_in, ScratchSet &ss, int sms, int flags, cuda
     Prof &p = pf ? *pf : dummy;
     DevJob job = job_in;
     {
-        // families that need K: points with I in the large-|w| region take the fused I + K kernel.  With
-        // per-element orders the K pass groups its points by predicted work instead, which the fused walk cannot.
+        // families that need K: points in the large-|w| region of I take the fused I + K kernel (K from the series
+        // the I routine sums anyway)
         const bool ktype = !(job.fam == SPB_FN_J || job.fam == SPB_FN_I);
         const int mode = fuse_mode();
         job.fuse = (ktype && !(flags & SPB_PATH_MONOLITHIC) && (mode >= 2 || (mode == 1 && job.v_stride == 0))) ? 1 : 0;

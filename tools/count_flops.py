@@ -39,9 +39,9 @@ def main():
     out = {"_rule": "add/sub/mul/div/sqrt = 1, exp/log/sin/cos/atan/sinh/cosh = 30, pow = 60; per point, "
                     "prepare + region + finish", "_sample": {}}
     rng = np.random.default_rng(1)
-    # last field: fused I + K in the large-|w| region (the library's choice for a broadcast scalar order)
+    # last field: fused I + K in the large-|w| region (the library's default)
     samples = {"cfg2": (cfg2_sample(1 << 18), ("J", "Y", "JY"), 1, 1),
-               "cfg3": (gen("cfg3", 1 << 17, rng), ("I", "K"), 2, 0),
+               "cfg3": (gen("cfg3", 1 << 17, rng), ("I", "K"), 2, 1),
                "cfg4": (gen("cfg4", 1 << 17, rng), ("H1", "H2"), 1, 1)}
     for cfg, ((v, z), fams, kode, fuse) in samples.items():
         v = np.ascontiguousarray(v, dtype=np.float64)
