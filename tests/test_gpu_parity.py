@@ -500,16 +500,17 @@ def test_calls_on_different_streams_share_scratch_safely(special):
 @pytest.mark.parametrize("order", [0.0, 0.3, 2.5, 7.25, 30.0])
 @pytest.mark.parametrize("fn", ["Y", "K", "H1", "H2"])
 def test_fused_large_w_kernel_scalar_order(special, fn, order):
-    """A broadcast scalar order sends every point that needs I_v(w) and K_v(w) with I in the large-|w| region
-    through the fused I + K kernel (k_fused.cu); per-element orders take the separate I and K passes.  Both must
-    match the CPU oracle, agree with each other to rounding and report identical codes."""
+    """Every K-type point in the large-|w| region of I goes through the fused I + K kernel (k_fused.cu: K from the
+    series the I routine sums), in its scalar-order and its per-element-order instantiation.  Both must match
+    the CPU oracle (whose drivers run the Miller algorithm / closed form for K there), agree with each other to
+    rounding and report identical codes."""
     for cfg in ("cfg2", "cfg4", "far"):
         rng = np.random.default_rng(helpers.seed_of("fused", fn, cfg, str(order)))
         _, z = gen(cfg, 100000, rng)
         v = np.full(z.shape, order)
         zt = torch.from_numpy(z).cuda()
         for kode in (1, 2):
-            got, ierr, nz = special.bessel(fn, order, zt, scaled=(kode == 2))  # scalar order: fused kernel
+            got, ierr, nz = special.bessel(fn, order, zt, scaled=(kode == 2))  # scalar-order instantiation
             sep, ierr_s, nz_s = special.bessel(fn, torch.from_numpy(v).cuda(), zt, scaled=(kode == 2))
             assert torch.equal(ierr, ierr_s) and torch.equal(nz, nz_s)
             g, s = to_np(got), to_np(sep)
