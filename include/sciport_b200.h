@@ -77,7 +77,15 @@ enum spb_flags {
     SPB_SEM_AMOS = 0,   /* value exactly as the algorithm leaves it (0 on failure) + ierr/nz  */
     SPB_SEM_SCIPY = 1,  /* value post-processed like scipy.special, the reference's test oracle
                            (tests/special.rs:10-16): NaN on ierr 1/2/4/5, +-inf on overflow
-                           where the sign is known, negative orders by reflection           */
+                           where the sign is known                                          */
+    SPB_RAW_NEG_ORDERS = 2, /* orders v < 0 are reported as ierr = 1 like the raw TOMS-644 drivers.
+                           DEFAULT (flag clear): negative orders are evaluated by the reflection
+                           formulae on the device -- K_-v = K_v (the reference calls kv(-3.5, 1000),
+                           kv.rs:53-54, and expects a value, not an Err), J_-v = cos(pi v) J_v -
+                           sin(pi v) Y_v, Y_-v = sin(pi v) J_v + cos(pi v) Y_v, I_-v = I_v +
+                           (2/pi) sin(pi v) K_v, H1_-v = e^{i pi v} H1_v, H2_-v = e^{-i pi v} H2_v,
+                           integer orders by sign changes; order sequences (n_orders > 1) keep
+                           the raw behaviour                                                 */
     SPB_PATH_BINNED = 0,     /* classify -> stable compaction by region -> per-region kernels */
     SPB_PATH_MONOLITHIC = 16, /* one thread runs the whole driver per point (debug / checker) */
     SPB_PROFILE = 32          /* device pointers only: CUDA events between the kernel launches;
@@ -101,7 +109,9 @@ enum spb_kernel_id {
 
 /* where the buffers live and which GPUs to use */
 typedef struct spb_exec {
-    int n_devices;      /* 0 or 1: one device; >1: slice [i*n/G,(i+1)*n/G) per device (host pointers only) */
+    int n_devices;      /* 0 or 1: one device; >1: slice [i*n/G,(i+1)*n/G) per device (host pointers only), one
+                           host thread (bound to the CPUs local to its GPU) and two streams per device; every
+                           batched entry point below honours it (Bessel, Airy, gamma family, sinc)          */
     const int *devices; /* device ordinals, NULL = 0..n_devices-1 (or the current device)                  */
     int device_ptrs;    /* 0: all buffers are host memory (pinned or pageable); 1: device memory on devices[0] */
     void *stream;       /* cudaStream_t to enqueue on when device_ptrs = 1 (NULL = default stream); such calls
@@ -175,6 +185,10 @@ int spb_last_timing(double *kernel_ms, int *launches);
 /* per-kernel records of the last spb_bessel call made with SPB_PROFILE on this thread: returns the number of
  * records written (<= max_records); points = elements the launch processed */
 int spb_last_profile(int max_records, int *kernel_ids, double *ms, int64_t *points);
+
+/* where device `device` hangs in the host: writes "bdf=<pci address> numa=<node or -1> cpus=<local_cpulist>" (what
+ * the per-device worker threads of a multi-device call bind to) into buf; returns the length written or < 0 */
+int spb_device_topology(int device, char *buf, int buflen);
 
 int spb_device_count(void);
 int spb_version(void);

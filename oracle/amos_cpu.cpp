@@ -28,6 +28,16 @@ inline void eval_one(int fn, int kode, double v, cplx z, cplx &out, int &ierr, i
     out = general_eval(fn, z, v, kode, ierr, nz);
 }
 
+// negative orders like the C ABI's default (include/sciport_b200.h, SPB_RAW_NEG_ORDERS clear): reflection formulae
+inline void eval_one_reflect(int fn, int kode, int sem, double v, cplx z, cplx &out, int &ierr, int &nz) {
+    if (v < 0.0) {
+        out = reflect_eval(fn, z, v, kode, ierr, nz, sem != 0);
+        return;
+    }
+    out = general_eval(fn, z, v, kode, ierr, nz);
+    if (sem) out = apply_semantics(fn, z, v, kode, out, ierr, nz);
+}
+
 template <class F>
 void parallel_for(int64_t n, int threads, F f) {
     if (threads <= 1 || n < 4096) {
@@ -65,8 +75,13 @@ int spbo_bessel_sem(int fn, int kode, int sem, const double *v, int64_t v_stride
             cplx o;
             int ie, nzz;
             cplx zz(z[2 * i], z[2 * i + 1]);
-            eval_one(fn, kode, v[i * v_stride], zz, o, ie, nzz);
-            if (sem) o = apply_semantics(fn, zz, v[i * v_stride], kode, o, ie, nzz);
+            // sem bit 0: scipy value conventions; bit 1: raw behaviour for negative orders (ierr = 1)
+            if (sem & 2) {
+                eval_one(fn, kode, v[i * v_stride], zz, o, ie, nzz);
+                if (sem & 1) o = apply_semantics(fn, zz, v[i * v_stride], kode, o, ie, nzz);
+            } else {
+                eval_one_reflect(fn, kode, sem & 1, v[i * v_stride], zz, o, ie, nzz);
+            }
             out[2 * i] = o.re;
             out[2 * i + 1] = o.im;
             if (ierr) ierr[i] = ie;

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libsciport_b200.so")
 
 FN = {"J": 0, "Y": 1, "I": 2, "K": 3, "H1": 4, "H2": 5}
 AIRY = {"Ai": 0, "Aip": 1, "Bi": 2, "Bip": 3}
-SEM_AMOS, SEM_SCIPY, PATH_MONOLITHIC, PROFILE = 0, 1, 16, 32
+SEM_AMOS, SEM_SCIPY, RAW_NEG_ORDERS, PATH_MONOLITHIC, PROFILE = 0, 1, 2, 16, 32
 KERNEL_NAMES = ["classify", "scan_scatter", "ipass_series", "ipass_asyi", "ipass_mlri", "ipass_wrsk", "kpass",
                 "general", "monolithic", "ipass_uni1", "ipass_uni2"]
 E_ARG, E_NO_DEVICE, E_CUDA, E_ALLOC = -1, -2, -3, -4
@@ -57,6 +57,7 @@ def _load():
     lib.spb_fp64_peak.argtypes = [I, ctypes.c_double, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
     lib.spb_last_timing.argtypes = [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(I)]
     lib.spb_last_profile.argtypes = [I, P, P, P]
+    lib.spb_device_topology.argtypes = [I, ctypes.c_char_p, I]
     lib.spb_last_error.restype = ctypes.c_char_p
     for name in EXPORTS:
         getattr(lib, name)  # every declared symbol must be exported
@@ -65,7 +66,7 @@ def _load():
 
 EXPORTS = [
     "spb_bessel", "spb_bessel_jy", "spb_bessel_real", "spb_airy", "spb_gamma", "spb_lgamma", "spb_cgamma", "spb_clgamma",
-    "spb_sinc", "spb_devmath", "spb_kaiser", "spb_lanczos", "spb_first_error", "spb_last_first_error", "spb_synth", "spb_fp64_peak", "spb_last_timing", "spb_last_profile", "spb_device_count",
+    "spb_sinc", "spb_devmath", "spb_kaiser", "spb_lanczos", "spb_first_error", "spb_last_first_error", "spb_synth", "spb_fp64_peak", "spb_last_timing", "spb_last_profile", "spb_device_topology", "spb_device_count",
     "spb_version", "spb_last_error",
 ]
 

@@ -638,6 +638,120 @@ SPB_FN cplx apply_semantics(int fam, cplx z, real fnu, int kode, cplx val, int i
     return out;
 }
 
+// ---- negative orders by reflection (the C ABI's default, SPB_RAW_NEG_ORDERS switches it off) --------------------
+// The reference calls kv(-3.5, 1000) (/root/reference/src/special/kv.rs:53-54) and unwraps the result, so a negative
+// order must produce a value where the raw TOMS-644 drivers report ierr = 1.  Formulae (DLMF 10.4, 10.27), av = -fnu:
+//     J_-av = cos(pi av) J_av - sin(pi av) Y_av        Y_-av = sin(pi av) J_av + cos(pi av) Y_av
+//     I_-av = I_av + (2/pi) sin(pi av) K_av            K_-av = K_av
+//     H1_-av = e^{i pi av} H1_av                       H2_-av = e^{-i pi av} H2_av
+// with the integer orders reduced to sign changes (sin(pi n) = 0 exactly).  The scaled variants carry the scale
+// factor of the target function (J, Y: e^{-|Im z|} for both terms; I: K_av is rescaled from e^{z} to e^{-|Re z|}).
+
+// sin(pi a), cos(pi a) for a >= 0, exact at the multiples of 1/2
+SPB_FN void sincospi_(real a, real &s, real &c) {
+    real q = floor(a + a + real(0.5));   // nearest half-integer index
+    real r = a - real(0.5) * q;         // |r| <= 1/4
+    real sr, cr;
+    sincos_(real(SPB_PI) * r, sr, cr);
+    if (r == real(0.0)) {
+        sr = 0.0;
+        cr = 1.0;
+    }
+    real qm = q - real(4.0) * floor(q * real(0.25));  // q mod 4
+    int k = (int)qm;
+    switch (k) {
+        case 0: s = sr; c = cr; break;
+        case 1: s = cr; c = -sr; break;
+        case 2: s = -sr; c = -cr; break;
+        default: s = -cr; c = sr; break;
+    }
+}
+
+// merge of the error codes of the two terms of a reflection formula: the first hard failure wins, else a 3 survives
+SPB_HD int merge_ierr(int a, int b) {
+    if (a != 0 && a != 3) return a;
+    if (b != 0 && b != 3) return b;
+    return (a == 3 || b == 3) ? 3 : 0;
+}
+
+SPB_FN void reflect_eval_jy(cplx z, real fnu, int kode, cplx &jv, int &jerr, int &jnz, cplx &yv, int &yerr, int &ynz,
+                            bool sem) {
+    const real av = -fnu;
+    real s, c;
+    sincospi_(av, s, c);
+    int ej, ey, nj, ny;
+    cplx j = general_eval(FAM_J, z, av, kode, ej, nj);
+    cplx y = general_eval(FAM_Y, z, av, kode, ey, ny);
+    const bool whole = (s == real(0.0));
+    // integer order: J_-n = (-1)^n J_n needs no Y (which may fail where J does not, e.g. at z = 0)
+    jerr = whole ? ej : merge_ierr(ej, ey);
+    yerr = whole ? ey : merge_ierr(ey, ej);
+    jnz = whole ? nj : 0;
+    ynz = whole ? ny : 0;
+    jv = whole ? j * c : j * c - y * s;
+    yv = whole ? y * c : j * s + y * c;
+    if (sem) {
+        if (whole) {
+            jv = apply_semantics(FAM_J, z, av, kode, j, ej, nj) * c;
+            yv = apply_semantics(FAM_Y, z, av, kode, y, ey, ny) * c;
+        } else {
+            const real inf = real(1.0) / real(0.0);
+            const real nan = inf - inf;
+            if (jerr != 0 && jerr != 3) jv = cplx(nan, nan);
+            if (yerr != 0 && yerr != 3) yv = cplx(nan, nan);
+        }
+    }
+}
+
+SPB_FN cplx reflect_eval(int fam, cplx z, real fnu, int kode, int &ierr, int &nz, bool sem) {
+    const real av = -fnu;
+    if (!(av == av) || !(z.re == z.re) || !(z.im == z.im)) return general_eval(fam, z, fnu, kode, ierr, nz);
+    if (fam == FAM_K) {
+        cplx k = general_eval(FAM_K, z, av, kode, ierr, nz);
+        return sem ? apply_semantics(FAM_K, z, av, kode, k, ierr, nz) : k;
+    }
+    if (fam == FAM_J || fam == FAM_Y) {
+        cplx jv, yv;
+        int ej, ey, nj, ny;
+        reflect_eval_jy(z, fnu, kode, jv, ej, nj, yv, ey, ny, sem);
+        ierr = fam == FAM_J ? ej : ey;
+        nz = fam == FAM_J ? nj : ny;
+        return fam == FAM_J ? jv : yv;
+    }
+    real s, c;
+    sincospi_(av, s, c);
+    const real inf = real(1.0) / real(0.0);
+    const real nan = inf - inf;
+    if (fam == FAM_H1 || fam == FAM_H2) {
+        cplx h = general_eval(fam, z, av, kode, ierr, nz);
+        if (sem) h = apply_semantics(fam, z, av, kode, h, ierr, nz);
+        return h * cplx(c, fam == FAM_H1 ? s : -s);
+    }
+    // FAM_I
+    int ei, ni;
+    cplx iv = general_eval(FAM_I, z, av, kode, ei, ni);
+    if (s == real(0.0)) {  // I_-n = I_n
+        ierr = ei;
+        nz = ni;
+        return sem ? apply_semantics(FAM_I, z, av, kode, iv, ei, ni) : iv;
+    }
+    int ek, nk;
+    cplx kv = general_eval(FAM_K, z, av, kode, ek, nk);
+    if (kode == 2) {
+        // e^{z} K -> e^{-|Re z|} K: factor e^{-z - |Re z|} (modulus <= 1)
+        real sn, cs;
+        sincos_(-z.im, sn, cs);
+        real m = z.re > real(0.0) ? exp_(real(-2.0) * z.re) : real(1.0);
+        if (z.re > real(0.0) && real(2.0) * z.re > real(SPB_ELIM)) m = 0.0;
+        kv = kv * cplx(m * cs, m * sn);
+    }
+    ierr = merge_ierr(ei, ek);
+    nz = 0;
+    cplx out = iv + kv * (real(0.63661977236758134308) * s);
+    if (sem && ierr != 0 && ierr != 3) out = cplx(nan, nan);
+    return out;
+}
+
 // Whole pipeline for one point, in the order the GPU runs it (prepare -> I pass
 // -> K pass -> finish, general path on any hand-over).  `path` reports which
 // route was taken: 0 binned, 1 general from prepare, 2 general after a pass.

@@ -10,7 +10,10 @@
 
 
 #include <cuda_runtime.h>
+#include <pthread.h>
+#include <sched.h>
 #include <algorithm>
+#include <cctype>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -41,8 +44,18 @@ int fail(int code, const std::string &msg) {
             return fail(SPB_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                 \
     } while (0)
 
-constexpr long long CHUNK_DEVICE = 1ll << 24;  // points per pipeline pass when data is resident
-constexpr long long CHUNK_HOST = 1ll << 22;    // points per staged chunk for host buffers
+// points per pipeline pass when data is resident (2^24) and per staged chunk for host buffers (2^22); the
+// environment knobs SPB_CHUNK_LOG2 / SPB_HOST_CHUNK_LOG2 (read once) exist for the tests: small chunks exercise the
+// multi-chunk paths on small batches, 2^25 and more makes k_scan take several rounds per bin
+long long env_log2(const char *name, int dflt, int lo, int hi) {
+    const char *e = getenv(name);
+    int l = e ? atoi(e) : dflt;
+    if (l < lo) l = lo;
+    if (l > hi) l = hi;
+    return 1ll << l;
+}
+const long long CHUNK_DEVICE = env_log2("SPB_CHUNK_LOG2", 24, 12, 27);
+const long long CHUNK_HOST = env_log2("SPB_HOST_CHUNK_LOG2", 22, 12, 26);
 
 struct ScratchSet {
     Scratch s{};
@@ -133,9 +146,111 @@ DeviceCtx *get_ctx(int dev) {
     return g_ctx[dev];
 }
 
+
+// ---- host topology of a device (sysfs): PCI address, NUMA node, CPUs local to its PCIe root ---------------------
+struct DevTopo {
+    std::string bdf, cpulist;
+    int numa = -1;
+    std::vector<int> cpus;
+};
+
+static std::string read_line(const std::string &path) {
+    std::string out;
+    if (FILE *f = fopen(path.c_str(), "r")) {
+        char buf[4096];
+        if (fgets(buf, sizeof buf, f)) out = buf;
+        fclose(f);
+    }
+    while (!out.empty() && (out.back() == '\n' || out.back() == ' ')) out.pop_back();
+    return out;
+}
+
+static std::vector<int> parse_cpulist(const std::string &spec) {
+    std::vector<int> cpus;
+    size_t i = 0;
+    while (i < spec.size()) {
+        size_t j = spec.find(',', i);
+        if (j == std::string::npos) j = spec.size();
+        const std::string part = spec.substr(i, j - i);
+        const size_t dash = part.find('-');
+        const int lo = atoi(part.c_str());
+        const int hi = dash == std::string::npos ? lo : atoi(part.c_str() + dash + 1);
+        for (int c = lo; c <= hi && c - lo < 4096; ++c) cpus.push_back(c);
+        i = j + 1;
+    }
+    return cpus;
+}
+
+static DevTopo device_topology(int dev) {
+    DevTopo t;
+    char id[32] = {0};
+    if (cudaDeviceGetPCIBusId(id, sizeof id, dev) != cudaSuccess) {
+        cudaGetLastError();
+        return t;
+    }
+    t.bdf = id;
+    for (auto &ch : t.bdf) ch = (char)tolower(ch);
+    const std::string base = "/sys/bus/pci/devices/" + t.bdf + "/";
+    const std::string node = read_line(base + "numa_node");
+    if (!node.empty()) t.numa = atoi(node.c_str());
+    // local_cpulist names the CPUs behind the device's PCIe root even where numa_node reads -1 (virtualised hosts)
+    t.cpulist = read_line(base + "local_cpulist");
+    if (t.cpulist.empty() && t.numa >= 0)
+        t.cpulist = read_line("/sys/devices/system/node/node" + std::to_string(t.numa) + "/cpulist");
+    t.cpus = parse_cpulist(t.cpulist);
+    return t;
+}
+
+// Run the calling thread on the CPUs local to `dev` (best effort; a no-op when the topology cannot be read or the
+// list covers every CPU anyway).  Used by the per-device worker threads of a multi-device call, so that the staging
+// copies of each slice are driven from the socket its GPU hangs off.
+static void bind_thread_near_device(int dev) {
+    const DevTopo t = device_topology(dev);
+    if (t.cpus.empty()) return;
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    int k = 0;
+    for (int c : t.cpus)
+        if (c >= 0 && c < CPU_SETSIZE) {
+            CPU_SET(c, &set);
+            ++k;
+        }
+    if (k > 0) pthread_setaffinity_np(pthread_self(), sizeof set, &set);
+}
+
+// Contiguous slice [g n / G, (g + 1) n / G) of an n-element batch per device: f(g, lo, hi, &launches) runs on one
+// host thread per device (the calling thread itself when there is one device).  No collective: shards never talk.
+template <class F>
+int slice_over_devices(const std::vector<int> &devs, long long n, int *launches_total, F f) {
+    const int G = (int)devs.size();
+    if (G == 1) {
+        int l = 0;
+        int rc = f(0, 0ll, n, &l);
+        if (launches_total) *launches_total += l;
+        return rc;
+    }
+    std::vector<int> rcs(G, SPB_OK), ls(G, 0);
+    std::vector<std::string> errs(G);
+    std::vector<std::thread> th;
+    for (int g = 0; g < G; ++g) {
+        th.emplace_back([&, g] {
+            bind_thread_near_device(devs[g]);
+            const long long lo = n * g / G, hi = n * (g + 1) / G;
+            if (hi > lo) rcs[g] = f(g, lo, hi, &ls[g]);
+            errs[g] = g_err;
+        });
+    }
+    for (auto &t : th) t.join();
+    for (int g = 0; g < G; ++g) {
+        if (launches_total) *launches_total += ls[g];
+        if (rcs[g] != SPB_OK) return fail(rcs[g], errs[g]);
+    }
+    return SPB_OK;
+}
+
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-int ensure_scratch(ScratchSet &ss, long long n) {
+int ensure_scratch(ScratchSet &ss, long long n, cudaStream_t st) {
     if (n <= ss.cap) {
         ss.s.nblocks = (int)((n + TILE - 1) / TILE);
         return SPB_OK;
@@ -169,7 +284,9 @@ int ensure_scratch(ScratchSet &ss, long long n) {
     ss.s.blockcnt = (unsigned int *)(base + o_bc);
     ss.s.bins = (unsigned int *)(base + o_bins);
     ss.s.nblocks = (int)((n + TILE - 1) / TILE);
-    cudaMemset(ss.s.bins, 0, BINS_WORDS * 4);  // counters of the scan's last-CTA hand-off start at zero
+    // counters of the scan's last-CTA hand-off start at zero: on the stream the pipeline kernels will run on (the
+    // pipeline streams are non-blocking, so a memset on the legacy stream would not be ordered before them)
+    cudaMemsetAsync(ss.s.bins, 0, BINS_WORDS * 4, st);
     return SPB_OK;
 }
 
@@ -333,6 +450,7 @@ int run_device_seq(DeviceCtx *c, const BesselArgs &a, cudaStream_t st, int *laun
         job.fam = a.fn;
         job.kode = a.kode;
         job.sem = (a.flags & SPB_SEM_SCIPY) ? 1 : 0;
+        job.reflect = 0;  // order sequences keep the raw behaviour for negative start orders
         job.v = a.v + off * a.v_stride;
         job.v_stride = a.v_stride;
         job.z = a.z ? a.z + off : nullptr;
@@ -341,7 +459,7 @@ int run_device_seq(DeviceCtx *c, const BesselArgs &a, cudaStream_t st, int *laun
         job.ierr = a.ierr ? a.ierr + off : nullptr;
         job.nz = a.nz ? a.nz + off : nullptr;
         job.n = m;
-        int rc = ensure_scratch(c->scratch[0], m);
+        int rc = ensure_scratch(c->scratch[0], m, st);
         if (rc != SPB_OK) return rc;
         launches += launch_sequence(job, a.n_orders, a.out_stride, c->scratch[0].s, c->sms, st);
     }
@@ -367,12 +485,13 @@ int run_device(DeviceCtx *c, const BesselArgs &a, cudaStream_t st, double *ms_ou
     CK(cudaEventRecord(c->ev0, st));
     for (long long off = 0; off < a.n; off += CHUNK_DEVICE) {
         long long m = std::min(CHUNK_DEVICE, a.n - off);
-        int rc = ensure_scratch(c->scratch[0], m);
+        int rc = ensure_scratch(c->scratch[0], m, st);
         if (rc != SPB_OK) return rc;
         DevJob job{};
         job.fam = a.fn;
         job.kode = a.kode;
         job.sem = (a.flags & SPB_SEM_SCIPY) ? 1 : 0;
+        job.reflect = (a.flags & SPB_RAW_NEG_ORDERS) ? 0 : 1;
         job.v = a.v + off * a.v_stride;
         job.v_stride = a.v_stride;
         job.z = a.z ? a.z + off : nullptr;
@@ -486,7 +605,7 @@ int run_host_slice(DeviceCtx *c, const BesselArgs &a, double *ms_out, int *launc
         cudaStream_t st = c->streams[b];
         int rc = ensure_stage(c->stage[b], std::min(CHUNK_HOST, a.n), a.x != nullptr, a.v_stride != 0, a.ierr, a.nz);
         if (rc != SPB_OK) return rc;
-        rc = ensure_scratch(c->scratch[b], m);
+        rc = ensure_scratch(c->scratch[b], m, st);
         if (rc != SPB_OK) return rc;
         StageSet &s = c->stage[b];
         if (a.z) CK(cudaMemcpyAsync(s.z, a.z + off, m * 16, cudaMemcpyHostToDevice, st));
@@ -502,6 +621,7 @@ int run_host_slice(DeviceCtx *c, const BesselArgs &a, double *ms_out, int *launc
         job.fam = a.fn;
         job.kode = a.kode;
         job.sem = (a.flags & SPB_SEM_SCIPY) ? 1 : 0;
+        job.reflect = (a.flags & SPB_RAW_NEG_ORDERS) ? 0 : 1;
         job.v = s.v;
         job.v_stride = a.v_stride == 0 ? 0 : 1;
         job.z = a.z ? s.z : nullptr;
@@ -579,6 +699,7 @@ int run_host_slice_seq(DeviceCtx *c, const BesselArgs &a, int *launches_out) {
         job.fam = a.fn;
         job.kode = a.kode;
         job.sem = (a.flags & SPB_SEM_SCIPY) ? 1 : 0;
+        job.reflect = 0;  // order sequences keep the raw behaviour for negative start orders
         job.v = s.v;
         job.v_stride = a.v_stride == 0 ? 0 : 1;
         job.z = a.z ? s.z : nullptr;
@@ -589,7 +710,7 @@ int run_host_slice_seq(DeviceCtx *c, const BesselArgs &a, int *launches_out) {
         job.n = m;
         job.first_err = c->d_first;
         job.index_base = a.index_base + off;
-        rc = ensure_scratch(c->scratch[b], m);
+        rc = ensure_scratch(c->scratch[b], m, st);
         if (rc != SPB_OK) return rc;
         launches += launch_sequence(job, a.n_orders, m, c->scratch[b].s, c->sms, st);
         CK(cudaMemcpy2DAsync(a.out + off, a.out_stride * 16, s.seq, m * 16, m * 16, a.n_orders, cudaMemcpyDeviceToHost,
@@ -650,44 +771,56 @@ int bessel_impl(int fn, int kode, const double *v, int64_t v_stride, const spb_c
     if (out2) po2.pin(out2, n * 16);
     if (ierr2) pe2.pin(ierr2, n * 4);
     if (nz2) pn2.pin(nz2, n * 4);
-    const int G = (int)devs.size();
-    if (G == 1)
-        return seq ? run_host_slice_seq(get_ctx(devs[0]), a, &g_last_launches)
-                   : run_host_slice(get_ctx(devs[0]), a, &g_last_ms, &g_last_launches);
-    // contiguous slice i of G per device, one host thread per device (no collective: shards never talk)
-    std::vector<int> rcs(G, SPB_OK), ls(G, 0);
-    std::vector<std::string> errs(G);
-    std::vector<std::thread> th;
-    for (int g = 0; g < G; ++g) {
-        th.emplace_back([&, g] {
-            long long lo = n * g / G, hi = n * (g + 1) / G;
-            BesselArgs s = a;
-            s.index_base = lo;
-            s.v = a.v + lo * a.v_stride;
-            s.z = a.z ? a.z + lo : nullptr;
-            s.x = a.x ? a.x + lo : nullptr;
-            s.out = a.out + lo;
-            s.ierr = a.ierr ? a.ierr + lo : nullptr;
-            s.nz = a.nz ? a.nz + lo : nullptr;
-            s.out2 = a.out2 ? a.out2 + lo : nullptr;
-            s.ierr2 = a.ierr2 ? a.ierr2 + lo : nullptr;
-            s.nz2 = a.nz2 ? a.nz2 + lo : nullptr;
-            s.n = hi - lo;
-            if (s.n > 0)
-                rcs[g] = seq ? run_host_slice_seq(get_ctx(devs[g]), s, &ls[g])
-                             : run_host_slice(get_ctx(devs[g]), s, nullptr, &ls[g]);
-            errs[g] = g_err;
-        });
+    // contiguous slice g of G per device, one host thread per device (no collective: shards never talk)
+    return slice_over_devices(devs, n, &g_last_launches, [&](int g, long long lo, long long hi, int *launches) {
+        BesselArgs sl = a;
+        sl.index_base = lo;
+        sl.v = a.v + lo * a.v_stride;
+        sl.z = a.z ? a.z + lo : nullptr;
+        sl.x = a.x ? a.x + lo : nullptr;
+        sl.out = a.out + lo;
+        sl.ierr = a.ierr ? a.ierr + lo : nullptr;
+        sl.nz = a.nz ? a.nz + lo : nullptr;
+        sl.out2 = a.out2 ? a.out2 + lo : nullptr;
+        sl.ierr2 = a.ierr2 ? a.ierr2 + lo : nullptr;
+        sl.nz2 = a.nz2 ? a.nz2 + lo : nullptr;
+        sl.n = hi - lo;
+        return seq ? run_host_slice_seq(get_ctx(devs[g]), sl, launches)
+                   : run_host_slice(get_ctx(devs[g]), sl, nullptr, launches);
+    });
+}
+
+// generic "map over a batch" helper for the elementwise kernels (gamma, ln|gamma|, complex gamma, sinc, ...):
+// device pointers -> one launch on the caller's stream; host pointers -> contiguous slice per device, each slice
+// staged in chunks over two streams (H2D, kernel, D2H of consecutive chunks overlap), buffers from the cached
+// staging set (no allocation in steady state)
+template <class F>
+int map_host_slice(DeviceCtx *c, const char *in, char *out, long long n, size_t in_bytes_per, size_t out_bytes_per,
+                   F launch, int *launches_out) {
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->dev));
+    if (c->busy_valid) cudaEventSynchronize(c->busy);
+    int k = 0, launches = 0;
+    for (long long off = 0; off < n; off += CHUNK_HOST, ++k) {
+        const long long m = std::min(CHUNK_HOST, n - off);
+        const int b = k & 1;
+        cudaStream_t st = c->streams[b];
+        int rc = ensure_stage(c->stage[b], std::min(CHUNK_HOST, n), false, false, false, false);
+        if (rc != SPB_OK) return rc;
+        StageSet &sg = c->stage[b];  // z: 16 B per element of input, out: 16 B per element of output
+        CK(cudaMemcpyAsync(sg.z, in + (size_t)off * in_bytes_per, (size_t)m * in_bytes_per, cudaMemcpyHostToDevice, st));
+        launch((const void *)sg.z, (void *)sg.out, m, st);
+        ++launches;
+        CK(cudaMemcpyAsync(out + (size_t)off * out_bytes_per, sg.out, (size_t)m * out_bytes_per, cudaMemcpyDeviceToHost,
+                           st));
     }
-    for (auto &t : th) t.join();
-    for (int g = 0; g < G; ++g) {
-        g_last_launches += ls[g];
-        if (rcs[g] != SPB_OK) return fail(rcs[g], errs[g]);
-    }
+    CK(cudaStreamSynchronize(c->streams[0]));
+    CK(cudaStreamSynchronize(c->streams[1]));
+    CK(cudaGetLastError());
+    if (launches_out) *launches_out = launches;
     return SPB_OK;
 }
 
-// generic "map over a batch" helper for the simple kernels (device or host pointers, one device)
 template <class F>
 int run_map(const spb_exec *ex, long long n, size_t in_bytes_per, size_t out_bytes_per, const void *in, void *out,
             F launch) {
@@ -698,41 +831,70 @@ int run_map(const spb_exec *ex, long long n, size_t in_bytes_per, size_t out_byt
     int rc = check_exec(ex, devs, dptr, st, flags);
     if (rc != SPB_OK) return rc;
     if (n < 0) return fail(SPB_E_ARG, "negative n");
+    g_last_ms = 0.0;
+    g_last_launches = 0;
+    g_pending_ev0 = g_pending_ev1 = nullptr;
     if (n == 0) return SPB_OK;
     if (!in || !out) return fail(SPB_E_ARG, "null buffer");
-    DeviceCtx *c = get_ctx(devs[0]);
-    std::lock_guard<std::mutex> lk(c->mu);
-    CK(cudaSetDevice(c->dev));
-    g_last_launches = 1;
+    if (in_bytes_per > 16 || out_bytes_per > 16) return fail(SPB_E_ARG, "element wider than the staging buffers");
     if (dptr) {
+        DeviceCtx *c = get_ctx(devs[0]);
+        std::lock_guard<std::mutex> lk(c->mu);
+        CK(cudaSetDevice(c->dev));
         order_after_previous(c, st);
         CK(cudaEventRecord(c->ev0, st));
         launch(in, out, n, st);
         CK(cudaEventRecord(c->ev1, st));
         mark_busy(c, st);
         CK(cudaGetLastError());
-        CK(cudaEventSynchronize(c->ev1));
-        float ms = 0.f;
-        CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
-        g_last_ms = ms;
+        // only enqueued, like every device-pointer call: spb_last_timing() resolves the events on demand
+        g_pending_ev0 = c->ev0;
+        g_pending_ev1 = c->ev1;
+        g_last_launches = 1;
         return SPB_OK;
     }
-    void *din = nullptr, *dout = nullptr;
-    if (cudaMalloc(&din, n * in_bytes_per) != cudaSuccess || cudaMalloc(&dout, n * out_bytes_per) != cudaSuccess) {
-        cudaGetLastError();
-        cudaFree(din);
-        return fail(SPB_E_ALLOC, "cudaMalloc failed");
+    Pin pi, po;
+    pi.pin(in, (size_t)n * in_bytes_per);
+    po.pin(out, (size_t)n * out_bytes_per);
+    return slice_over_devices(devs, n, &g_last_launches, [&](int g, long long lo, long long hi, int *launches) {
+        return map_host_slice(get_ctx(devs[g]), (const char *)in + (size_t)lo * in_bytes_per,
+                              (char *)out + (size_t)lo * out_bytes_per, hi - lo, in_bytes_per, out_bytes_per, launch,
+                              launches);
+    });
+}
+
+// Airy with host buffers, one device: staged chunks over two streams like run_host_slice
+int airy_host_slice(DeviceCtx *c, int which, int kode, int sem, const spb_c128 *z, spb_c128 *out, int32_t *ierr,
+                    int32_t *nz, long long n, long long index_base, int *launches_out) {
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->dev));
+    int launches = 0, k = 0;
+    {
+        const unsigned long long ones[2] = {~0ull, ~0ull};
+        if (c->busy_valid) cudaEventSynchronize(c->busy);  // a queued device-pointer call still owns the scratch
+        CK(cudaMemcpy(c->d_first, ones, 16, cudaMemcpyHostToDevice));
     }
-    cudaStream_t s0 = c->streams[0];
-    cudaError_t e = cudaMemcpyAsync(din, in, n * in_bytes_per, cudaMemcpyHostToDevice, s0);
-    if (e == cudaSuccess) {
-        launch(din, dout, n, s0);
-        e = cudaMemcpyAsync(out, dout, n * out_bytes_per, cudaMemcpyDeviceToHost, s0);
+    for (long long off = 0; off < n; off += CHUNK_HOST, ++k) {
+        const long long m = std::min<long long>(CHUNK_HOST, n - off);
+        const int b = k & 1;
+        cudaStream_t s0 = c->streams[b];
+        int rc = ensure_stage(c->stage[b], std::min<long long>(CHUNK_HOST, n), false, false, true, true);
+        if (rc != SPB_OK) return rc;
+        StageSet &sg = c->stage[b];
+        CK(cudaMemcpyAsync(sg.z, z + off, m * 16, cudaMemcpyHostToDevice, s0));
+        rc = ensure_scratch(c->scratch[b], m, s0);
+        if (rc != SPB_OK) return rc;
+        launches += launch_airy(which, kode, sem, sg.z, sg.out, ierr ? sg.ierr : nullptr, nz ? sg.nz : nullptr, m,
+                                &c->scratch[b].s, c->sms, s0, c->d_first, index_base + off);
+        CK(cudaMemcpyAsync(out + off, sg.out, m * 16, cudaMemcpyDeviceToHost, s0));
+        if (ierr) CK(cudaMemcpyAsync(ierr + off, sg.ierr, m * 4, cudaMemcpyDeviceToHost, s0));
+        if (nz) CK(cudaMemcpyAsync(nz + off, sg.nz, m * 4, cudaMemcpyDeviceToHost, s0));
     }
-    if (e == cudaSuccess) e = cudaStreamSynchronize(s0);
-    cudaFree(din);
-    cudaFree(dout);
-    if (e != cudaSuccess) return fail(SPB_E_CUDA, cudaGetErrorString(e));
+    CK(cudaStreamSynchronize(c->streams[0]));
+    CK(cudaStreamSynchronize(c->streams[1]));
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(c->h_first, c->d_first, 16, cudaMemcpyDeviceToHost));
+    if (launches_out) *launches_out = launches;
     return SPB_OK;
 }
 
@@ -769,21 +931,23 @@ int spb_airy(int which, int kode, const spb_c128 *z, spb_c128 *out, int32_t *ier
     if (n < 0) return fail(SPB_E_ARG, "negative n");
     if (n == 0) return SPB_OK;
     if (!z || !out) return fail(SPB_E_ARG, "null buffer");
-    DeviceCtx *c = get_ctx(devs[0]);
-    std::lock_guard<std::mutex> lk(c->mu);
-    CK(cudaSetDevice(c->dev));
-    int sem = (flags & SPB_SEM_SCIPY) ? 1 : 0;
+    const int sem = (flags & SPB_SEM_SCIPY) ? 1 : 0;
+    g_last_ms = 0.0;
     g_last_launches = 0;
+    g_pending_ev0 = g_pending_ev1 = nullptr;
     g_first_devs = devs;
     g_first_stream = st;
     g_first_pending = dptr;
     if (dptr) {
+        DeviceCtx *c = get_ctx(devs[0]);
+        std::lock_guard<std::mutex> lk(c->mu);
+        CK(cudaSetDevice(c->dev));
         order_after_previous(c, st);
         CK(cudaMemsetAsync(c->d_first, 0xff, 16, st));
         CK(cudaEventRecord(c->ev0, st));
         for (long long off = 0; off < n; off += CHUNK_DEVICE) {
             long long m = std::min<long long>(CHUNK_DEVICE, n - off);
-            rc = ensure_scratch(c->scratch[0], m);
+            rc = ensure_scratch(c->scratch[0], m, st);
             if (rc != SPB_OK) return rc;
             g_last_launches += launch_airy(which, kode, sem, (const double2 *)z + off, (double2 *)out + off,
                                            ierr ? ierr + off : nullptr, nz ? nz + off : nullptr, m, &c->scratch[0].s,
@@ -792,39 +956,20 @@ int spb_airy(int which, int kode, const spb_c128 *z, spb_c128 *out, int32_t *ier
         CK(cudaEventRecord(c->ev1, st));
         mark_busy(c, st);
         CK(cudaGetLastError());
-        CK(cudaEventSynchronize(c->ev1));
-        float ms = 0.f;
-        CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
-        g_last_ms = ms;
+        // only enqueued, like the Bessel entry points: synchronise the stream before reading the results
+        g_pending_ev0 = c->ev0;
+        g_pending_ev1 = c->ev1;
         return SPB_OK;
     }
-    int launches = 0, k = 0;
-    {
-        const unsigned long long ones[2] = {~0ull, ~0ull};
-        if (c->busy_valid) cudaEventSynchronize(c->busy);  // a queued device-pointer call still owns the scratch
-        CK(cudaMemcpy(c->d_first, ones, 16, cudaMemcpyHostToDevice));
-    }
-    for (long long off = 0; off < n; off += CHUNK_HOST, ++k) {
-        long long m = std::min<long long>(CHUNK_HOST, n - off);
-        int b = k & 1;
-        cudaStream_t s0 = c->streams[b];
-        rc = ensure_stage(c->stage[b], std::min<long long>(CHUNK_HOST, n), false, false, true, true);
-        if (rc != SPB_OK) return rc;
-        StageSet &s = c->stage[b];
-        CK(cudaMemcpyAsync(s.z, z + off, m * 16, cudaMemcpyHostToDevice, s0));
-        rc = ensure_scratch(c->scratch[b], m);
-        if (rc != SPB_OK) return rc;
-        launches += launch_airy(which, kode, sem, s.z, s.out, ierr ? s.ierr : nullptr, nz ? s.nz : nullptr, m,
-                                &c->scratch[b].s, c->sms, s0, c->d_first, off);
-        CK(cudaMemcpyAsync(out + off, s.out, m * 16, cudaMemcpyDeviceToHost, s0));
-        if (ierr) CK(cudaMemcpyAsync(ierr + off, s.ierr, m * 4, cudaMemcpyDeviceToHost, s0));
-        if (nz) CK(cudaMemcpyAsync(nz + off, s.nz, m * 4, cudaMemcpyDeviceToHost, s0));
-    }
-    CK(cudaStreamSynchronize(c->streams[0]));
-    CK(cudaStreamSynchronize(c->streams[1]));
-    CK(cudaMemcpy(c->h_first, c->d_first, 16, cudaMemcpyDeviceToHost));
-    g_last_launches = launches;
-    return SPB_OK;
+    Pin pz, po, pe, pn;
+    pz.pin(z, (size_t)n * 16);
+    po.pin(out, (size_t)n * 16);
+    if (ierr) pe.pin(ierr, (size_t)n * 4);
+    if (nz) pn.pin(nz, (size_t)n * 4);
+    return slice_over_devices(devs, n, &g_last_launches, [&](int g, long long lo, long long hi, int *launches) {
+        return airy_host_slice(get_ctx(devs[g]), which, kode, sem, z + lo, out + lo, ierr ? ierr + lo : nullptr,
+                               nz ? nz + lo : nullptr, hi - lo, lo, launches);
+    });
 }
 
 int spb_gamma(const double *x, double *out, int64_t n, const spb_exec *ex) {
@@ -1040,6 +1185,14 @@ int spb_last_first_error(int which, int64_t *idx, int32_t *code) {
         *code = (int32_t)(best & 0xff);
     }
     return SPB_OK;
+}
+
+int spb_device_topology(int device, char *buf, int buflen) {
+    const int ndev = device_count();
+    if (ndev <= 0) return fail(SPB_E_NO_DEVICE, "no CUDA device visible");
+    if (device < 0 || device >= ndev || !buf || buflen <= 0) return fail(SPB_E_ARG, "bad device or buffer");
+    const DevTopo t = device_topology(device);
+    return snprintf(buf, (size_t)buflen, "bdf=%s numa=%d cpus=%s", t.bdf.c_str(), t.numa, t.cpulist.c_str());
 }
 
 int spb_device_count(void) { return device_count(); }

@@ -158,12 +158,15 @@ __global__ void __launch_bounds__(256) k_classify(DevJob job, Scratch s) {
 __global__ void __launch_bounds__(1024) k_scan(Scratch s) {
     pdl_enter();
     __shared__ unsigned int warp_tot[32];
-    __shared__ unsigned int carry_s;
+    __shared__ unsigned int round_total;
     const int b = blockIdx.x;
     unsigned int *cnt = s.blockcnt + (size_t)b * s.nblocks;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (threadIdx.x == 0) carry_s = 0;
-    __syncthreads();
+    // The running total of the rounds already scanned lives in a REGISTER that every thread updates identically
+    // from round_total after the second barrier of a round; the trailing barrier keeps round_total (and warp_tot)
+    // of this round intact until every thread has read them.  (No thread ever reads a shared word that another
+    // thread may be overwriting between the same pair of barriers.)
+    unsigned int carry = 0;
     for (int base = 0; base < s.nblocks; base += 8192) {
         const int i0 = base + (int)threadIdx.x * 8;
         unsigned int x[8];
@@ -181,7 +184,6 @@ __global__ void __launch_bounds__(1024) k_scan(Scratch s) {
         }
         if (lane == 31) warp_tot[wid] = incl;
         __syncthreads();
-        const unsigned int carry = carry_s;
         if (wid == 0) {
             unsigned int w = warp_tot[lane];
             unsigned int wi = w;
@@ -191,7 +193,7 @@ __global__ void __launch_bounds__(1024) k_scan(Scratch s) {
                 if (lane >= d) wi += y;
             }
             warp_tot[lane] = wi - w;  // exclusive prefix of warp totals
-            if (lane == 31) carry_s = carry + wi;
+            if (lane == 31) round_total = wi;
         }
         __syncthreads();
         unsigned int running = carry + warp_tot[wid] + incl - sum;
@@ -200,10 +202,11 @@ __global__ void __launch_bounds__(1024) k_scan(Scratch s) {
             if (i0 + k < s.nblocks) cnt[i0 + k] = running;
             running += x[k];
         }
+        carry += round_total;
         __syncthreads();
     }
     if (threadIdx.x == 0) {
-        s.bins[SLOT_TOTALS + b] = carry_s;  // total of this bin
+        s.bins[SLOT_TOTALS + b] = carry;  // total of this bin
         __threadfence();
         unsigned int done = atomicAdd(&s.bins[SLOT_DONE], 1u);
         if (done == NBINS - 1) {

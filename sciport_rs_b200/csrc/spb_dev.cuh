@@ -16,6 +16,8 @@ __device__ __forceinline__ void load_point(const DevJob &j, long long i, cplx &z
         z = cplx(__ldg(j.x + i), 0.0);
     }
     v = __ldg(j.v + i * j.v_stride);
+    // K_{-v} = K_v: fold the order where it is loaded, so negative orders of K take the binned path like any other
+    if (j.reflect && j.fam == spb::FAM_K) v = fabs(v);
 }
 
 // record a failing element in the call-wide "first error" word (rare path: one atomic per failing element)
@@ -134,6 +136,20 @@ __device__ __forceinline__ double wrsk_work(double az, double v) {
 // general per-point evaluation + optional oracle-compatible post-processing
 __device__ __forceinline__ void eval_general_store(const DevJob &j, long long i, cplx z, double v) {
     int ierr, nz;
+    if (j.reflect && v < 0.0) {
+        // negative order: reflection formulae composed from the drivers' results at |v| (spb_family.h)
+        if (j.fam == spb::FAM_JY) {
+            cplx a, b;
+            int ierr2, nz2;
+            spb::reflect_eval_jy(z, v, j.kode, a, ierr, nz, b, ierr2, nz2, j.sem != 0);
+            store_point(j, i, a, ierr, nz);
+            store_point2(j, i, b, ierr2, nz2);
+            return;
+        }
+        cplx val = spb::reflect_eval(j.fam, z, v, j.kode, ierr, nz, j.sem != 0);
+        store_point(j, i, val, ierr, nz);
+        return;
+    }
     if (j.fam == spb::FAM_JY) {
         cplx a = spb::general_eval(spb::FAM_J, z, v, j.kode, ierr, nz);
         if (j.sem) a = spb::apply_semantics(spb::FAM_J, z, v, j.kode, a, ierr, nz);

@@ -13,6 +13,7 @@ struct DevJob {
     int sem;   // 0 raw AMOS, 1 scipy-compatible post-processing
     int fuse;  // 1: points needing I and K with I in the large-|w| region are evaluated by the fused region kernel
     int pdl;   // 1: the kernels of this chunk are launched as programmatic dependents of each other (launch_pdl)
+    int reflect;  // 1: orders v < 0 by the reflection formulae (K folds v -> |v| at load; the others on the general path)
     const double *v;
     long long v_stride;  // 0 = broadcast
     const double2 *z;    // complex input, or

@@ -21,7 +21,7 @@ import ctypes
 import numpy as np
 
 from . import _lib
-from ._lib import lib, check, make_exec, FN, AIRY, SEM_AMOS, SEM_SCIPY, PATH_MONOLITHIC, PROFILE
+from ._lib import lib, check, make_exec, FN, AIRY, SEM_AMOS, SEM_SCIPY, RAW_NEG_ORDERS, PATH_MONOLITHIC, PROFILE
 
 try:  # torch is plumbing only (device memory / streams)
     import torch
@@ -66,7 +66,7 @@ def profile_step(fn):
 
 
 def bessel(fn, v, z, scaled=False, semantics="amos", path="binned", real_input=False, devices=None, profile=False,
-           out=None, ierr=None, nz=None, n_orders=1, want_codes=True):
+           out=None, ierr=None, nz=None, n_orders=1, want_codes=True, raw_neg_orders=False):
     """Evaluate one family over a batch.  Returns ``(values, ierr, nz)``.
 
     ``want_codes=False`` passes NULL for the per-element ``ierr`` / ``nz`` arrays (they come back as ``None``):
@@ -84,9 +84,15 @@ def bessel(fn, v, z, scaled=False, semantics="amos", path="binned", real_input=F
     flags = (SEM_SCIPY if semantics == "scipy" else SEM_AMOS) | (PATH_MONOLITHIC if path == "monolithic" else 0)
     if profile:
         flags |= PROFILE
+    if raw_neg_orders:
+        flags |= RAW_NEG_ORDERS
     if _is_torch(z):
         if not z.is_cuda:
             raise ValueError("torch inputs must be CUDA tensors (use numpy arrays for host buffers)")
+        if ierr is not None or nz is not None:
+            raise ValueError("preallocated ierr / nz buffers are only taken for host (numpy) inputs")
+        if devices is not None:
+            raise ValueError("device tensors live on one device: `devices` is for host (numpy) inputs")
         zc = z.resolve_conj().contiguous()  # a lazy conjugate view shares storage with the unconjugated tensor
         want = torch.float64 if real_input else torch.complex128
         if zc.dtype != want:
@@ -147,7 +153,8 @@ def bessel(fn, v, z, scaled=False, semantics="amos", path="binned", real_input=F
     return out, ierr, nz
 
 
-def bessel_jy(v, z, scaled=False, semantics="amos", profile=False, outs=None, codes=None, want_codes=True):
+def bessel_jy(v, z, scaled=False, semantics="amos", profile=False, outs=None, codes=None, want_codes=True,
+              devices=None):
     """J_v(z) and Y_v(z) in one pass (spb_bessel_jy): returns ((J, ierr_j, nz_j), (Y, ierr_y, nz_y)).
     Both functions need I_v at the same rotated point, so the pair shares classification and the I pass."""
     kode = 2 if scaled else 1
@@ -157,6 +164,8 @@ def bessel_jy(v, z, scaled=False, semantics="amos", profile=False, outs=None, co
         n = zc.numel()
         if _is_torch(v):
             vt = v.to(device=zc.device, dtype=torch.float64).contiguous()
+            if vt.numel() != 1 and vt.numel() != n:
+                raise ValueError("v and z must have the same number of elements")
             stride = 0 if vt.numel() == 1 else 1
         else:
             vt = torch.full((1,), float(v), dtype=torch.float64, device=zc.device)
@@ -191,16 +200,16 @@ def bessel_jy(v, z, scaled=False, semantics="amos", profile=False, outs=None, co
     elif codes is None:
         codes = [np.empty(za.shape, np.int32) for _ in range(4)]
     cp = [c.ctypes.data if c is not None else None for c in codes]
-    ex = make_exec(flags=flags)
+    ex = make_exec(flags=flags, devices=devices)
     check(lib.spb_bessel_jy(kode, va.ctypes.data, stride, za.ctypes.data, outs[0].ctypes.data, outs[1].ctypes.data,
                             cp[0], cp[1], cp[2], cp[3], za.size, ctypes.byref(ex)))
     return (outs[0], codes[0], codes[2]), (outs[1], codes[1], codes[3])
 
 
-def jvyv(v, z, scaled=False, outs=None):
+def jvyv(v, z, scaled=False, outs=None, devices=None):
     """(jv(v, z), yv(v, z)) computed together; raises on the first Err of either.  No per-element codes are
     produced: the library tracks the first failing element of each output on the device."""
-    (j, _, _), (y, _, _) = bessel_jy(v, z, scaled=scaled, outs=outs, want_codes=False)
+    (j, _, _), (y, _, _) = bessel_jy(v, z, scaled=scaled, outs=outs, want_codes=False, devices=devices)
     for which in (0, 1):
         idx, code = last_first_error(which)
         if idx >= 0:
@@ -259,8 +268,8 @@ def kv(v, z):
         z = 0j
     if v != v:
         v = 0.0
-    if v < 0:
-        v = -v  # K_{-v} = K_v (the reference exercises kv(-3.5, 1000), kv.rs:53-54)
+    # (negative orders: the C ABI folds K_{-v} = K_v on the device; the reference exercises kv(-3.5, 1000),
+    # kv.rs:53-54)
     vals, ierr, _ = bessel("K", v, np.array([z], dtype=np.complex128))
     if ierr[0] != 0:
         print(f"{v} {z}")  # kv.rs:20-22
@@ -273,9 +282,9 @@ def kve(v, z):
     return kv(v, z) * np.exp(complex(z))
 
 
-def sinc(x):
+def sinc(x, devices=None, out=None):
     """special::sinc (trig.rs:4-13)."""
-    return _real_map(lib.spb_sinc, x)
+    return _real_map(lib.spb_sinc, x, devices, out)
 
 
 def devmath(which, x):
@@ -294,57 +303,10 @@ def _checked(fn, v, z, scaled, **kw):
     return vals
 
 
-def _reflect(fn, v, z, scaled, **kw):
-    """Negative orders (host arrays) by the reflection formulae, composed from the kernels' results at |v|:
-         J_-v = cos(pi v) J_v - sin(pi v) Y_v        Y_-v = sin(pi v) J_v + cos(pi v) Y_v
-         I_-v = I_v + (2/pi) sin(pi v) K_v           K_-v = K_v
-         H1_-v = e^{i pi v} H1_v                     H2_-v = e^{-i pi v} H2_v
-    with the integer-order cases reduced to sign changes (J_-n = (-1)^n J_n, I_-n = I_n).  The scaled variants carry
-    the scale factor of the target function (for I: K is rescaled from e^z to e^{-|Re z|})."""
-    za = np.asarray(z, dtype=np.complex128)
-    va = np.broadcast_to(np.asarray(v, dtype=np.float64), za.shape)
-    neg = va < 0
-    av = np.abs(va)
-    out = np.empty(za.shape, np.complex128)
-    if (~neg).any():
-        out[~neg] = _checked(fn, av[~neg], za[~neg], scaled, **kw)
-    if not neg.any():
-        return out
-    zn, vn = za[neg], av[neg]
-    s, c = np.sin(np.pi * vn), np.cos(np.pi * vn)
-    whole = vn == np.floor(vn)
-    s = np.where(whole, 0.0, s)
-    c = np.where(whole, np.where(vn % 2 == 0, 1.0, -1.0), c)
-    if fn == "K":
-        out[neg] = _checked("K", vn, zn, scaled, **kw)
-    elif fn in ("H1", "H2"):
-        ph = c + 1j * s if fn == "H1" else c - 1j * s
-        out[neg] = ph * _checked(fn, vn, zn, scaled, **kw)
-    elif fn in ("J", "Y"):
-        (j, _, _), (y, _, _) = bessel_jy(vn, zn, scaled=scaled, want_codes=False)
-        for which in (0, 1):
-            idx, code = last_first_error(which)
-            # a failing Y only matters where it enters the formula (non-integer order, or Y itself is wanted)
-            if idx >= 0 and (which == 0 or fn == "Y" or not whole[idx]):
-                raise SpecialError(code, int(np.flatnonzero(neg)[idx]))
-        y = np.where(whole & (fn == "J"), 0.0, y)
-        out[neg] = c * j - s * y if fn == "J" else s * j + c * y
-    else:  # I
-        i = _checked("I", vn, zn, scaled, **kw)
-        k = np.zeros_like(i)
-        frac = ~whole
-        if frac.any():
-            k[frac] = _checked("K", vn[frac], zn[frac], scaled, **kw)
-            if scaled:  # e^{z} K -> e^{-|Re z|} K
-                k[frac] *= np.exp(-zn[frac] - np.abs(zn[frac].real))
-        out[neg] = i + (2.0 / np.pi) * s * k
-    return out
-
-
 def _family(fn, scaled):
+    """Batched `xv` / `xve` entry point: orders of either sign (negative orders are evaluated by the reflection
+    formulae inside the library, on the device, for host and device inputs alike); raises on the first Err."""
     def f(v, z, **kw):
-        if not _is_torch(z) and not _is_torch(v) and np.any(np.asarray(v) < 0):
-            return _reflect(fn, v, z, scaled, **kw)
         return _checked(fn, v, z, scaled, **kw)
 
     return f
@@ -368,26 +330,27 @@ def jn_sequence(n_orders, z, v0=0.0, scaled=False):
     return vals
 
 
-def airy_raw(which, z, scaled=False, semantics="amos"):
+def airy_raw(which, z, scaled=False, semantics="amos", devices=None, out=None, want_codes=True):
     kode = 2 if scaled else 1
     flags = SEM_SCIPY if semantics == "scipy" else SEM_AMOS
     if _is_torch(z):
         zc = z.resolve_conj().contiguous().to(torch.complex128)
-        out = torch.empty_like(zc)
-        ierr = torch.empty(zc.shape, dtype=torch.int32, device=zc.device)
-        nz = torch.empty(zc.shape, dtype=torch.int32, device=zc.device)
+        out = torch.empty_like(zc) if out is None else out
+        ierr = torch.empty(zc.shape, dtype=torch.int32, device=zc.device) if want_codes else None
+        nz = torch.empty(zc.shape, dtype=torch.int32, device=zc.device) if want_codes else None
         with torch.cuda.device(zc.device):
             ex = make_exec(device_ptrs=True, stream=_stream_for(zc), flags=flags, devices=[zc.device.index])
-            check(lib.spb_airy(AIRY[which], kode, zc.data_ptr(), out.data_ptr(), ierr.data_ptr(), nz.data_ptr(),
+            check(lib.spb_airy(AIRY[which], kode, zc.data_ptr(), out.data_ptr(),
+                               ierr.data_ptr() if want_codes else None, nz.data_ptr() if want_codes else None,
                                zc.numel(), ctypes.byref(ex)))
         return out, ierr, nz
     za = np.ascontiguousarray(z, dtype=np.complex128)
-    out = np.empty_like(za)
-    ierr = np.empty(za.shape, np.int32)
-    nz = np.empty(za.shape, np.int32)
-    ex = make_exec(flags=flags)
-    check(lib.spb_airy(AIRY[which], kode, za.ctypes.data, out.ctypes.data, ierr.ctypes.data, nz.ctypes.data, za.size,
-                       ctypes.byref(ex)))
+    out = np.empty_like(za) if out is None else out
+    ierr = np.empty(za.shape, np.int32) if want_codes else None
+    nz = np.empty(za.shape, np.int32) if want_codes else None
+    ex = make_exec(flags=flags, devices=devices)
+    check(lib.spb_airy(AIRY[which], kode, za.ctypes.data, out.ctypes.data, ierr.ctypes.data if want_codes else None,
+                       nz.ctypes.data if want_codes else None, za.size, ctypes.byref(ex)))
     return out, ierr, nz
 
 
@@ -404,32 +367,32 @@ def airye(z):
     return airy(z, scaled=True)
 
 
-def _real_map(fn, x):
+def _real_map(fn, x, devices=None, out=None):
     if _is_torch(x):
         xc = x.contiguous().to(torch.float64)
-        out = torch.empty_like(xc)
+        out = torch.empty_like(xc) if out is None else out
         with torch.cuda.device(xc.device):
             ex = make_exec(device_ptrs=True, stream=_stream_for(xc), devices=[xc.device.index])
             check(fn(xc.data_ptr(), out.data_ptr(), xc.numel(), ctypes.byref(ex)))
         return out
     xa = np.ascontiguousarray(x, dtype=np.float64)
-    out = np.empty_like(xa)
-    ex = make_exec()
+    out = np.empty_like(xa) if out is None else out
+    ex = make_exec(devices=devices)
     check(fn(xa.ctypes.data, out.ctypes.data, xa.size, ctypes.byref(ex)))
     return out
 
 
-def _cplx_map(fn, z):
+def _cplx_map(fn, z, devices=None, out=None):
     if _is_torch(z):
         zc = z.resolve_conj().contiguous().to(torch.complex128)
-        out = torch.empty_like(zc)
+        out = torch.empty_like(zc) if out is None else out
         with torch.cuda.device(zc.device):
             ex = make_exec(device_ptrs=True, stream=_stream_for(zc), devices=[zc.device.index])
             check(fn(zc.data_ptr(), out.data_ptr(), zc.numel(), ctypes.byref(ex)))
         return out
     za = np.ascontiguousarray(z, dtype=np.complex128)
-    out = np.empty_like(za)
-    ex = make_exec()
+    out = np.empty_like(za) if out is None else out
+    ex = make_exec(devices=devices)
     check(fn(za.ctypes.data, out.ctypes.data, za.size, ctypes.byref(ex)))
     return out
 
@@ -440,18 +403,22 @@ def _is_complex(a):
     return np.iscomplexobj(a)
 
 
-def gamma(x):
-    return _cplx_map(lib.spb_cgamma, x) if _is_complex(x) else _real_map(lib.spb_gamma, x)
+def gamma(x, devices=None, out=None):
+    if _is_complex(x):
+        return _cplx_map(lib.spb_cgamma, x, devices, out)
+    return _real_map(lib.spb_gamma, x, devices, out)
 
 
-def gammaln(x):
+def gammaln(x, devices=None, out=None):
     """ln|Gamma(x)| for real x."""
-    return _real_map(lib.spb_lgamma, x)
+    return _real_map(lib.spb_lgamma, x, devices, out)
 
 
-def loggamma(z):
+def loggamma(z, devices=None, out=None):
     """Principal branch of log Gamma(z) for complex z; ln|Gamma(x)| for real x."""
-    return _cplx_map(lib.spb_clgamma, z) if _is_complex(z) else _real_map(lib.spb_lgamma, z)
+    if _is_complex(z):
+        return _cplx_map(lib.spb_clgamma, z, devices, out)
+    return _real_map(lib.spb_lgamma, z, devices, out)
 
 
 def synth(cfg, n, n_total=None, offset=0, seed=None, device=None):
@@ -473,6 +440,15 @@ def synth(cfg, n, n_total=None, offset=0, seed=None, device=None):
     ex = make_exec()
     check(lib.spb_synth(cfg, seed, offset, n, n_total, v.ctypes.data, z.ctypes.data, ctypes.byref(ex)))
     return v, z
+
+
+def device_topology(device=0):
+    """'bdf=<pci address> numa=<node> cpus=<local_cpulist>' of a device (what multi-device worker threads bind to)."""
+    buf = ctypes.create_string_buffer(512)
+    n = lib.spb_device_topology(device, buf, 512)
+    if n < 0:
+        check(n)
+    return buf.value.decode()
 
 
 def fp64_peak(device=0, seconds=2.0):
