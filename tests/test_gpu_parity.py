@@ -48,7 +48,8 @@ def test_golden_device_pointers(special, fn, kode):
 @pytest.mark.parametrize("cfg", ["cfg2", "cfg3", "cfg4", "real", "wide", "far"])
 @pytest.mark.parametrize("fn", list(FN))
 def test_vs_cpu_oracle_and_monolithic(special, fn, cfg):
-    """Binned CUDA path vs CPU oracle (tolerance) and vs the monolithic CUDA path (bit-identical)."""
+    """Binned CUDA path vs LIVE scipy.special (the reference's declared oracle; primary check), vs the CPU port
+    (second check: values and error classes) and vs the monolithic CUDA path."""
     rng = np.random.default_rng(helpers.seed_of(fn, cfg, "gpu"))
     v, z = gen(cfg, 200000, rng)
     zt, vt = torch.from_numpy(z).cuda(), torch.from_numpy(v).cuda()
@@ -70,6 +71,16 @@ def test_vs_cpu_oracle_and_monolithic(special, fn, cfg):
         cond = 16.0 if cfg in ("wide", "far") else 0.0
         bad = okv & (err > so.tolerance(want, z, v, conditioning=cond))
         assert not bad.any(), f"kode={kode}: {bad.sum()} mismatches, first v={v[bad][0]} z={z[bad][0]} err={err[bad][0]:.2e}"
+        # primary check: live scipy (independent of the product's headers), same scale and tolerance policy;
+        # skipped where scipy has no value (nan / inf), is known to be defective (kode 2, order > fnul) or has
+        # lost half its digits by its own account (|z| or v > 32767: sf_error "loss")
+        ws = so.evaluate(fn, kode, v, z)
+        oks = okv & np.isfinite(ws.real) & np.isfinite(ws.imag) & ~scipy_kode2_defect(fn, kode, v)
+        oks &= (np.abs(z) < 32767.0) & (v < 32767.0)
+        errs = so.mismatch(g, ws, np.maximum(scale, np.abs(ws)))
+        bads = oks & (errs > so.tolerance(ws, z, v, conditioning=cond))
+        assert not bads.any(), (f"kode={kode}: {bads.sum()} mismatches vs scipy, first v={v[bads][0]} z={z[bads][0]} "
+                                f"err={errs[bads][0]:.2e}")
         # the two CUDA paths run the same region math, but nvcc contracts FMAs per kernel, so they agree to
         # rounding (same tolerance), not bit for bit; their error classes must be identical
         errm = so.mismatch(g, m, scale)
@@ -376,10 +387,66 @@ def test_multi_device_slices_match_single_device(special):
     sw1, _, _ = special.bessel("J", 0.0, z[:200_001], n_orders=32, want_codes=False)
     swg, _, _ = special.bessel("J", 0.0, z[:200_001], n_orders=32, want_codes=False, devices=list(range(g)))
     assert np.array_equal(sw1.view(np.uint64), swg.view(np.uint64))
+    # the J/Y pair, Airy and the elementwise companions take the same split
+    devs = list(range(g))
+    (j1, _, _), (y1, _, _) = special.bessel_jy(2.5, z)
+    (jg, _, _), (yg, _, _) = special.bessel_jy(2.5, z, devices=devs)
+    assert np.array_equal(j1.view(np.uint64), jg.view(np.uint64)) and np.array_equal(y1.view(np.uint64), yg.view(np.uint64))
+    zz = z.copy()
+    zz[2_900_001] = complex("nan")
+    for which in ("Ai", "Bi"):
+        a1, ea1, na1 = special.airy_raw(which, zz)
+        i1 = special.last_first_error()
+        ag, eag, nag = special.airy_raw(which, zz, devices=devs)
+        assert special.last_first_error() == i1 and i1[0] == 2_900_001
+        same = (a1.view(np.uint64) == ag.view(np.uint64)).reshape(-1, 2).all(1) | (np.isnan(a1.real) & np.isnan(ag.real))
+        assert same.all() and np.array_equal(ea1, eag) and np.array_equal(na1, nag)
+    x = np.abs(z.real) + 0.25
+    for f in (special.gamma, special.gammaln, special.sinc):
+        assert np.array_equal(f(x).view(np.uint64), f(x, devices=devs).view(np.uint64))
+    for f in (special.gamma, special.loggamma):
+        a, b = f(z * 0.3), f(z * 0.3, devices=devs)
+        same = (a.view(np.uint64) == b.view(np.uint64)).reshape(-1, 2).all(1) | (np.isnan(a.real) & np.isnan(b.real))
+        assert same.all()
+    assert "bdf=" in special.device_topology(g - 1)
+
+
+def test_negative_orders_inside_the_c_abi(special):
+    """The reference calls kv(-3.5, 1000) and unwraps (kv.rs:53-54): spb_bessel itself must evaluate negative orders
+    (reflection on the device), for host and device pointers alike; SPB_RAW_NEG_ORDERS restores ierr = 1."""
+    import ctypes
+    from sciport_rs_b200 import _lib
+    v = np.array([-3.5], dtype=np.float64)
+    z = np.array([1000.0 + 0j])
+    out = np.empty(1, np.complex128)
+    ierr = np.full(1, -7, np.int32)
+    nz = np.full(1, -7, np.int32)
+    ex = _lib.make_exec()
+    _lib.check(_lib.lib.spb_bessel(_lib.FN["K"], 1, v.ctypes.data, 0, z.ctypes.data, out.ctypes.data, ierr.ctypes.data,
+                                   nz.ctypes.data, 1, 1, ctypes.byref(ex)))
+    assert out[0] == 0 and ierr[0] == 0 and nz[0] == 1  # K_3.5(1000) = 0 by underflow, not an Err
+    ex = _lib.make_exec(flags=_lib.RAW_NEG_ORDERS)
+    _lib.check(_lib.lib.spb_bessel(_lib.FN["K"], 1, v.ctypes.data, 0, z.ctypes.data, out.ctypes.data, ierr.ctypes.data,
+                                   nz.ctypes.data, 1, 1, ctypes.byref(ex)))
+    assert ierr[0] == 1
+    # device inputs take the same route (large batch: binned K path with the order folded at load)
+    rng = np.random.default_rng(3)
+    n = 100000
+    vv = -12 * rng.random(n)
+    zz = 30 * rng.random(n) * np.exp(1j * np.pi * (2 * rng.random(n) - 1)) + 0.05
+    for fn in ("K", "J", "I", "H1"):
+        a, ea, _ = special.bessel(fn, vv, zz)
+        b, eb, _ = special.bessel(fn, torch.from_numpy(vv).cuda(), torch.from_numpy(zz).cuda())
+        assert np.array_equal(ea, to_np(eb)) and (ea == 0).all()
+        assert np.all(np.abs(a - to_np(b)) <= 1e-13 * np.maximum(np.abs(a), 1e-300))
+    (j, ej, _), (y, ey, _) = special.bessel_jy(vv, zz)
+    a, _, _ = special.bessel("J", vv, zz)
+    b, _, _ = special.bessel("Y", vv, zz)
+    assert np.array_equal(j.view(np.uint64), a.view(np.uint64)) and np.array_equal(y.view(np.uint64), b.view(np.uint64))
 
 
 def test_negative_orders_by_reflection(special):
-    """Orders < 0 (host arrays): reflection formulae composed from the kernels' results, checked against scipy."""
+    """Orders < 0: reflection formulae evaluated inside the library, checked against scipy."""
     import scipy.special as sc
     rng = np.random.default_rng(9)
     n = 4000
@@ -600,3 +667,49 @@ def test_device_transcendentals(special):
     with np.errstate(all="ignore"):
         want = np.log(odd)
     assert np.array_equal(np.isnan(got), np.isnan(want)) and np.array_equal(got[~np.isnan(want)], want[~np.isnan(want)])
+
+
+def test_host_generator_matches_device_stream(special):
+    """bench.py's numpy restatement of the SURVEY 8d generator (used by the CPU legs) addresses the same stream as
+    spb_synth on the device."""
+    import bench
+    n_total = 1 << 28
+    off = 123_456_789
+    v, z = special.synth(3, 4096, n_total=n_total, offset=off, device="cuda:0")
+    vh, zh = bench.cfg3_points(np.arange(off, off + 4096, dtype=np.int64))
+    assert np.array_equal(to_np(v), vh)
+    assert np.all(np.abs(to_np(z) - zh) <= 4 * so.EPS * np.abs(zh))
+
+
+def test_scan_with_several_rounds_per_bin():
+    """k_scan scans 8192 tile counters per round: a chunk of 2^25 points (16384 tiles, SPB_CHUNK_LOG2 = 25) makes
+    every bin take two rounds, with the carry handed from round to round; an adversarial input puts points of every
+    region into both halves.  Runs in a fresh process (the chunk size is read once) and must reproduce the default
+    chunking bit for bit."""
+    import subprocess, sys, os
+    code = r"""
+import numpy as np, torch, sys
+sys.path.insert(0, %r)
+from sciport_rs_b200 import special
+n = (1 << 25) + 12345
+v, z = special.synth(3, n, n_total=1 << 28, device="cuda:0")
+# second half: another distribution (log-uniform moduli), so the bin populations of the two rounds differ
+_, z4 = special.synth(4, n // 2, n_total=1 << 30, device="cuda:0")
+z[n // 2: n // 2 + z4.numel()] = z4
+out = {}
+for fn in ("I", "K"):
+    o, e, k = special.bessel(fn, v, z, scaled=True)
+    out[fn] = (o.cpu().numpy().view(np.uint64), e.cpu().numpy(), k.cpu().numpy())
+np.savez(sys.argv[1], **{f"{fn}_{i}": a for fn, t in out.items() for i, a in enumerate(t)})
+""" % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        res = {}
+        for tag, log2 in (("a", "24"), ("b", "25")):
+            env = dict(os.environ, SPB_CHUNK_LOG2=log2)
+            r = subprocess.run([sys.executable, "-c", code, os.path.join(d, tag + ".npz")], env=env, capture_output=True,
+                               text=True, timeout=900)
+            assert r.returncode == 0, r.stderr[-2000:]
+            res[tag] = np.load(os.path.join(d, tag + ".npz"))
+        for k in res["a"].files:
+            assert np.array_equal(res["a"][k], res["b"][k]), k
