@@ -104,7 +104,8 @@ enum spb_kernel_id {
     SPB_K_GENERAL = 7,       /* general per-point path                               */
     SPB_K_MONOLITHIC = 8,    /* whole batch through the general path                 */
     SPB_K_IPASS_UNI1 = 9,    /* I pass: uniform (Debye-type) expansion at raised order */
-    SPB_K_IPASS_UNI2 = 10    /* I pass: uniform (Airy-type) expansion at raised order  */
+    SPB_K_IPASS_UNI2 = 10,   /* I pass: uniform (Airy-type) expansion at raised order  */
+    SPB_K_IPASS_DEBYE = 11   /* I and/or K: Debye-type expansion at the order itself   */
 };
 
 /* where the buffers live and which GPUs to use */

@@ -97,8 +97,9 @@ int spbo_bessel_pipeline(int fn, int kode, const double *v, int64_t v_stride, co
                          int32_t *ierr, int32_t *nz, int32_t *path, int64_t n, int threads_and_mode) {
     // bit 16 of the last argument: route points that need I and K in the large-|w| region of I through the
     // fused routine (the flow of the fused region kernel)
+    // bit 17: the Debye-direct region (spb_debye.h) is enabled as well
     const int threads = threads_and_mode & 0xffff;
-    const bool fuse = (threads_and_mode & 0x10000) != 0;
+    const int fuse = ((threads_and_mode & 0x10000) ? FUSE_ASYI : 0) | ((threads_and_mode & 0x20000) ? FUSE_DEBYE : 0);
     parallel_for(n, threads, [=](int64_t lo, int64_t hi) {
         for (int64_t i = lo; i < hi; ++i) {
             int ie, nzz, pth;
@@ -122,9 +123,9 @@ int spbo_classify(int fn, int kode, int fuse, const double *v, int64_t v_stride,
         const double fnu = v[i * v_stride];
         int ireg, kreg;
         fast[i] = -1;
-        if (fast_classify(fn, zz, fnu, kode, fuse != 0, ireg, kreg))
-            fast[i] = (int8_t)class_byte(fn, zz, fnu, kode, fuse != 0, true);
-        full[i] = (int8_t)class_byte(fn, zz, fnu, kode, fuse != 0, false);
+        if (fast_classify(fn, zz, fnu, kode, fuse, ireg, kreg))
+            fast[i] = (int8_t)class_byte(fn, zz, fnu, kode, fuse, true);
+        full[i] = (int8_t)class_byte(fn, zz, fnu, kode, fuse, false);
     }
     return 0;
 }
@@ -134,7 +135,7 @@ int spbo_bessel_jy_pipeline(int kode, const double *v, int64_t v_stride, const d
                             int32_t *codes /* [4][n]: ierr_j, ierr_y, nz_j, nz_y */, int64_t n,
                             int threads_and_mode) {
     const int threads = threads_and_mode & 0xffff;
-    const bool fuse = (threads_and_mode & 0x10000) != 0;  // as in spbo_bessel_pipeline
+    const int fuse = ((threads_and_mode & 0x10000) ? FUSE_ASYI : 0) | ((threads_and_mode & 0x20000) ? FUSE_DEBYE : 0);
     parallel_for(n, threads, [=](int64_t lo, int64_t hi) {
         for (int64_t i = lo; i < hi; ++i) {
             cplx jv, yv;

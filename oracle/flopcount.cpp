@@ -65,18 +65,20 @@ inline void exp_pair_hook(counted x, counted &ep, counted &em) {
 
 using namespace spb;
 
-static inline int islot(int ireg) { return ireg < 4 ? 2 + ireg : 5 + ireg; }  // regions 4, 5 -> ids 9, 10
+static inline int islot(int ireg) { return ireg < 4 ? 2 + ireg : 5 + ireg; }  // regions 4, 5, 6 -> ids 9, 10, 11
+static const int NSLOT = 12;
 
 extern "C" {
 
-// ops[11]: classify(prepare), 6 ipass regions (region + its share of finish), kpass (+finish), general, and
+// ops[12]: classify(prepare), 7 ipass regions (region + its share of finish), kpass (+finish), general, and
 // pts[11] the number of points charged to each, following the kernel ids of include/sciport_b200.h
-// (0 classify, 2..5 ipass series/asyi/mlri/wrsk, 6 kpass, 7 general, 9 / 10 ipass uniform forms 1 / 2).
+// (0 classify, 2..5 ipass series/asyi/mlri/wrsk, 6 kpass, 7 general, 9 / 10 ipass uniform forms 1 / 2, 11 the
+// Debye-direct region).  fuse is the bitmask of spb_family.h (FUSE_ASYI | FUSE_DEBYE).
 // fuse = 1: points that need I and K with I in the large-|w| region are charged, as one unit (fused routine +
 // finish), to the large-|w| region kernel, like the library does for a broadcast scalar order.
 int spbo_count_ops2(int fam, int kode, int fuse, const double *v, int64_t v_stride, const double *z, int64_t n,
                     double *ops, int64_t *pts) {
-    for (int k = 0; k < 11; ++k) {
+    for (int k = 0; k < NSLOT; ++k) {
         ops[k] = 0;
         pts[k] = 0;
     }
@@ -84,7 +86,7 @@ int spbo_count_ops2(int fam, int kode, int fuse, const double *v, int64_t v_stri
         cplx zz(counted(z[2 * i]), counted(z[2 * i + 1]));
         counted fnu(v[i * v_stride]);
         g_ops = 0;
-        Prep p = prepare(fam, zz, fnu, kode, fuse != 0);
+        Prep p = prepare(fam, zz, fnu, kode, fuse);
         uint64_t prep_ops = g_ops;
         ops[0] += prep_ops;
         pts[0] += 1;
@@ -94,7 +96,15 @@ int spbo_count_ops2(int fam, int kode, int fuse, const double *v, int64_t v_stri
             bool general = (p.combine == CMB_GENERAL);
             cplx iv(0.0, 0.0), kv(0.0, 0.0), jv, yv;
             int inz = 0, knz = 0, e2, n2;
-            if (!general && p.kreg == KREG_FUSED) {
+            if (!general && p.ireg == IREG_DEBYE) {
+                g_ops = prep_ops;
+                if (debye_region(FAM_JY, p.w, fnu, kode, true, iv, inz, kv, knz, p.az) < 0)
+                    general = true;
+                else
+                    finish_jy(p, zz, fnu, kode, iv, inz, kv, knz, jv, ierr, nz, yv, e2, n2);
+                ops[islot(IREG_DEBYE)] += g_ops;
+                pts[islot(IREG_DEBYE)] += 1;
+            } else if (!general && p.kreg == KREG_FUSED) {
                 g_ops = prep_ops;
                 if (fused_ik_region(p.w, fnu, kode, iv, inz, kv, knz, p.az) < 0 ||
                     (knz != 0 && p.combine == CMB_Y_SHARED))
@@ -137,7 +147,17 @@ int spbo_count_ops2(int fam, int kode, int fuse, const double *v, int64_t v_stri
         cplx ival(0.0, 0.0), kval(0.0, 0.0);
         int inz = 0, knz = 0;
         bool handed = false;
-        if (p.kreg == KREG_FUSED) {
+        if (p.ireg == IREG_DEBYE) {
+            g_ops = prep_ops;
+            Prep q = p;
+            const bool need_i = (fam == FAM_J || fam == FAM_I) || prepare_geometry(fam, zz, q);
+            if (debye_region(fam, p.w, fnu, kode, need_i, ival, inz, kval, knz, p.az) < 0)
+                handed = true;
+            else
+                finish(fam, p, zz, fnu, kode, ival, inz, kval, knz, ierr, nz);
+            ops[islot(IREG_DEBYE)] += g_ops;
+            pts[islot(IREG_DEBYE)] += 1;
+        } else if (p.kreg == KREG_FUSED) {
             g_ops = prep_ops;
             if (fused_ik_region(p.w, fnu, kode, ival, inz, kval, knz, p.az) < 0 ||
                 (knz != 0 && (p.combine == CMB_ACON || p.combine == CMB_Y_SHARED)))
@@ -172,6 +192,20 @@ int spbo_count_ops2(int fam, int kode, int fuse, const double *v, int64_t v_stri
         }
     }
     return 0;
+}
+
+// Airy: mean operation count per point of Ai / Ai' / Bi / Bi' (which = 0..3) through the complete routine
+double spbo_count_ops_airy(int which, int kode, const double *z, int64_t n) {
+    g_ops = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        cplx zz(counted(z[2 * i]), counted(z[2 * i + 1]));
+        int ierr = 0, nz = 0;
+        if (which >= 2)
+            biry(zz, which & 1, kode, ierr);
+        else
+            airy(zz, which & 1, kode, nz, ierr);
+    }
+    return n > 0 ? (double)g_ops / (double)n : 0.0;
 }
 
 int spbo_count_ops(int fam, int kode, const double *v, int64_t v_stride, const double *z, int64_t n, double *ops,

@@ -9,6 +9,7 @@
 #include "spb_kregions.h"
 #include "spb_uniform.h"
 #include "spb_airy.h"
+#include "spb_debye.h"
 
 namespace spb {
 
@@ -582,7 +583,9 @@ enum IRegion {
     IREG_WRSK = 3,    // Miller ratios + Wronskian (after uoik)
     IREG_UNI1 = 4,    // uniform asymptotics, Debye-type form (|Im z| <= sqrt(3) |Re z|), after uoik
     IREG_UNI2 = 5,    // uniform asymptotics, Airy-type form, after uoik
-    IREG_COUNT = 6
+    IREG_DEBYE = 6,   // uniform (Debye-type) expansion at the order itself + second exponential (spb_debye.h): binned
+                      // pipeline only; carved out of the four regions above where its parameters are large enough
+    IREG_COUNT = 7
 };
 
 // Where the published algorithm raises the order to fnul and uses the Airy-type uniform expansion although

@@ -38,6 +38,11 @@ enum Combine {
     CMB_Y_CONJ = 6    // Y on the positive real axis: K(w) and its conjugate
 };
 
+// `fuse` argument of prepare() / the classifier: which of the single-evaluation region routines of the binned
+// pipeline are enabled (the classic per-point drivers know neither)
+enum { FUSE_ASYI = 1,   // I and K of a K-type point in the large-|w| region of I from one Hankel series (fused_ik_region)
+       FUSE_DEBYE = 2 };  // Debye-direct region (spb_debye.h) for I, K or both
+
 // K-pass regions
 enum KRegion { KREG_SERIES = 0, KREG_MILLER = 1, KREG_HALF = 2, KREG_COUNT = 3 };
 // kreg of a point whose K_v(w) is evaluated together with I_v(w) by the fused large-|w| routine (no K bin)
@@ -81,8 +86,10 @@ SPB_HD int kregion(cplx w, real fnu, real az_known = real(-1.0)) {
     return KREG_MILLER;
 }
 
-// Is the I evaluation at (w, fnu) simple, and in which region?
-SPB_HD int iregion_simple(cplx w, real fnu, real az, bool &simple, int kode) {
+// Is the I evaluation at (w, fnu) simple, and in which region?  debye: carve the Debye-direct region out of the
+// Miller / Wronskian / raised-order regions (only where the point is simple: both over/underflow pre-tests no-ops,
+// which also keeps the exponent of the expansion on the middle scaling level).
+SPB_HD int iregion_simple(cplx w, real fnu, real az, bool &simple, int kode, bool debye = false) {
     const real rl = SPB_RL, fnul = SPB_FNUL, alim = SPB_ALIM;
     int r = binu_region(w, fnu, 1, rl, fnul, az);
     simple = true;
@@ -95,6 +102,7 @@ SPB_HD int iregion_simple(cplx w, real fnu, real az, bool &simple, int kode) {
         // second pre-test on K_fnu, K_fnu+1
         if (!uoik_is_noop(az, rmax(fnu + real(1.0), real(2.0)), alim, rabs(w.re), kode)) simple = false;
     }
+    if (debye && simple && r >= IREG_MLRI && r <= IREG_UNI2 && debye_ok(w, fnu)) r = IREG_DEBYE;
     return r;
 }
 
@@ -150,7 +158,7 @@ SPB_HD bool prepare_geometry(int fam, cplx z, Prep &p) {
 // fuse: K-type points whose w lies in the large-|w| region of I get kreg = KREG_FUSED instead of a K bin: one
 // routine evaluates I_v(w) and K_v(w) from the same series, sharing 1/w, 1/sqrt(w), the sincos of Im w and
 // exp(+-Re w) (also where the family needs K only: the series is several times cheaper than the Miller algorithm).
-SPB_FN Prep prepare(int fam, cplx z, real fnu, int kode, bool fuse = false) {
+SPB_FN Prep prepare(int fam, cplx z, real fnu, int kode, int fuse = 0) {
     const real fnul = SPB_FNUL, alim = SPB_ALIM, tol = SPB_TOL;
     Prep p;
     p.w = z;
@@ -170,7 +178,7 @@ SPB_FN Prep prepare(int fam, cplx z, real fnu, int kode, bool fuse = false) {
         prepare_geometry(fam, z, p);
         p.combine = CMB_GENERAL;
         bool simple;
-        p.ireg = iregion_simple(p.w, fnu, az, simple, kode);
+        p.ireg = iregion_simple(p.w, fnu, az, simple, kode, (fuse & FUSE_DEBYE) != 0);
         if (simple) p.combine = CMB_I_ROT;
         return p;
     }
@@ -204,19 +212,26 @@ SPB_FN Prep prepare(int fam, cplx z, real fnu, int kode, bool fuse = false) {
     p.kreg = kregion(p.w, fnu, az);
     if (left) {
         bool simple;
-        p.ireg = iregion_simple(p.w, fnu, az, simple, kode);
+        p.ireg = iregion_simple(p.w, fnu, az, simple, kode, (fuse & FUSE_DEBYE) != 0);
         if (!simple) {
             p.combine = CMB_GENERAL;
             p.ireg = -1;
             p.kreg = -1;
-        } else if (fuse && p.ireg == IREG_ASYI) {
+        } else if (((fuse & FUSE_ASYI) && p.ireg == IREG_ASYI) || p.ireg == IREG_DEBYE) {
+            p.kreg = KREG_FUSED;  // I and K from one evaluation (large-|w| series / Debye expansion)
+        }
+    } else {
+        // I_v(w) is not needed here, but the point lies in a region where one of the single-evaluation routines
+        // gives K at a fraction of the cost of the Miller algorithm + forward recurrence: same bin, the combine
+        // step ignores I
+        const int r = binu_region(p.w, fnu, 1, SPB_RL, SPB_FNUL, az);
+        if ((fuse & FUSE_ASYI) && r == IREG_ASYI) {
+            p.ireg = IREG_ASYI;
+            p.kreg = KREG_FUSED;
+        } else if ((fuse & FUSE_DEBYE) && r >= IREG_MLRI && r <= IREG_UNI2 && debye_ok(p.w, fnu)) {
+            p.ireg = IREG_DEBYE;
             p.kreg = KREG_FUSED;
         }
-    } else if (fuse && binu_region(p.w, fnu, 1, SPB_RL, SPB_FNUL, az) == IREG_ASYI) {
-        // I_v(w) is not needed here, but the point lies in the region where the fused routine takes K from the
-        // large-|w| series (a fraction of the cost of the Miller algorithm): same bin, the combine step ignores I
-        p.ireg = IREG_ASYI;
-        p.kreg = KREG_FUSED;
     }
     return p;
 }
@@ -262,7 +277,7 @@ SPB_HD FastOrder fast_order(real fnu) {
     o.kreg = (rabs(fnu - real(inu)) == real(0.5)) ? KREG_HALF : KREG_MILLER;
     return o;
 }
-SPB_HD bool fast_classify(int fam, cplx z, const FastOrder &o, int kode, bool fuse, int &ireg, int &kreg) {
+SPB_HD bool fast_classify(int fam, cplx z, const FastOrder &o, int kode, int fuse, int &ireg, int &kreg) {
     const real alim = SPB_ALIM;
     const real m2 = z.re * z.re + z.im * z.im;
     if (!o.ok || !(m2 >= o.m2_lo) || !(m2 <= o.m2_hi)) return false;  // (a NaN fails the comparisons)
@@ -292,14 +307,14 @@ SPB_HD bool fast_classify(int fam, cplx z, const FastOrder &o, int kode, bool fu
     }
     kreg = o.kreg;
     ireg = left ? IREG_ASYI : -1;
-    if (fuse) {
+    if (fuse & FUSE_ASYI) {
         // the window is the large-|w| region of I: K comes from the same series whether or not I is needed
         ireg = IREG_ASYI;
         kreg = KREG_FUSED;
     }
     return true;
 }
-SPB_HD bool fast_classify(int fam, cplx z, real fnu, int kode, bool fuse, int &ireg, int &kreg) {
+SPB_HD bool fast_classify(int fam, cplx z, real fnu, int kode, int fuse, int &ireg, int &kreg) {
     const FastOrder o = fast_order(fnu);
     return fast_classify(fam, z, o, kode, fuse, ireg, kreg);
 }
@@ -310,7 +325,7 @@ SPB_HD unsigned int class_of(int ireg, int kreg) {
     const unsigned int bk = kreg >= 0 ? (unsigned int)kreg : 3u;
     return bi | (bk << 3);
 }
-SPB_HD unsigned int class_byte(int fam, cplx z, real fnu, int kode, bool fuse, bool allow_fast = true) {
+SPB_HD unsigned int class_byte(int fam, cplx z, real fnu, int kode, int fuse, bool allow_fast = true) {
     int ireg, kreg;
     if (!(allow_fast && fast_classify(fam, z, fnu, kode, fuse, ireg, kreg))) {
         const Prep p = prepare(fam, z, fnu, kode, fuse);
@@ -403,6 +418,19 @@ SPB_FN int fused_ik_region(cplx w, real fnu, int kode, cplx &ival, int &inz, cpl
     }
     kval = coef * ksum;
     return 0;
+}
+
+// I_v(w) and / or K_v(w) of a point in the Debye-direct region (IREG_DEBYE): one evaluation of the uniform
+// expansion at the order itself (spb_debye.h).  need_i: the family needs I_v(w) at this point.
+SPB_FN int debye_region(int fam, cplx w, real fnu, int kode, bool need_i, cplx &ival, int &inz, cplx &kval, int &knz,
+                        real az, const OrderPhase *oph = nullptr) {
+    const bool need_k = !(fam == FAM_J || fam == FAM_I);
+    inz = 0;
+    knz = 0;
+    ival = cplx(0.0, 0.0);
+    kval = cplx(0.0, 0.0);
+    if (az < real(0.0)) az = cabs_(w);
+    return debye_ik(w, fnu, kode, need_i, need_k, ival, kval, az, oph);
 }
 
 // continuation K(w e^{i pi mr}) from (K(w), I(w)) for one member (acon with n = 1)
@@ -755,7 +783,7 @@ SPB_FN cplx reflect_eval(int fam, cplx z, real fnu, int kode, int &ierr, int &nz
 // Whole pipeline for one point, in the order the GPU runs it (prepare -> I pass
 // -> K pass -> finish, general path on any hand-over).  `path` reports which
 // route was taken: 0 binned, 1 general from prepare, 2 general after a pass.
-SPB_FN cplx pipeline_eval(int fam, cplx z, real fnu, int kode, int &ierr, int &nz, int &path, bool fuse = false) {
+SPB_FN cplx pipeline_eval(int fam, cplx z, real fnu, int kode, int &ierr, int &nz, int &path, int fuse = 0) {
     Prep p = prepare(fam, z, fnu, kode, fuse);
     path = 1;
     if (p.combine == CMB_GENERAL) return general_eval(fam, z, fnu, kode, ierr, nz);
@@ -766,10 +794,12 @@ SPB_FN cplx pipeline_eval(int fam, cplx z, real fnu, int kode, int &ierr, int &n
         nz = p.final_nz;
         return cplx(0.0, 0.0);
     }
+    bool geom_needs_i;
     {
         // the region passes see only the class (bins) and recompute the geometry: same thing here
         const int ireg = p.ireg, kreg = p.kreg;
         p = prepare_pass(fam, z);
+        geom_needs_i = p.ireg >= 0;
         // (cannot happen except for fused points that do not need I; would show up as a path-1 mismatch)
         if ((p.ireg >= 0) != (ireg >= 0) && kreg != KREG_FUSED) p.combine = CMB_GENERAL;
         p.ireg = ireg;
@@ -778,7 +808,11 @@ SPB_FN cplx pipeline_eval(int fam, cplx z, real fnu, int kode, int &ierr, int &n
     cplx ival(0.0, 0.0), kval(0.0, 0.0);
     int inz = 0, knz = 0;
     path = 2;
-    if (p.kreg == KREG_FUSED) {
+    if (p.ireg == IREG_DEBYE) {
+        if (debye_region(fam, p.w, fnu, kode, geom_needs_i, ival, inz, kval, knz, p.az) < 0)
+            return general_eval(fam, z, fnu, kode, ierr, nz);
+        p.kreg = -1;
+    } else if (p.kreg == KREG_FUSED) {
         if (fused_ik_region(p.w, fnu, kode, ival, inz, kval, knz, p.az) < 0)
             return general_eval(fam, z, fnu, kode, ierr, nz);
         if (knz != 0 && (p.combine == CMB_ACON || p.combine == CMB_Y_SHARED))
@@ -799,7 +833,7 @@ SPB_FN cplx pipeline_eval(int fam, cplx z, real fnu, int kode, int &ierr, int &n
 
 // J and Y together, in the order the GPU runs the FAM_JY pipeline.
 SPB_FN void pipeline_eval_jy(cplx z, real fnu, int kode, cplx &jv, int &jerr, int &jnz, cplx &yv, int &yerr,
-                             int &ynz, int &path, bool fuse = false) {
+                             int &ynz, int &path, int fuse = 0) {
     Prep p = prepare(FAM_JY, z, fnu, kode, fuse);
     path = 1;
     cplx ival(0.0, 0.0), kval(0.0, 0.0);
@@ -811,7 +845,10 @@ SPB_FN void pipeline_eval_jy(cplx z, real fnu, int kode, cplx &jv, int &jerr, in
         p.ireg = ireg;
         p.kreg = kreg;
     }
-    if (!general && p.kreg == KREG_FUSED) {
+    if (!general && p.ireg == IREG_DEBYE) {
+        path = 2;
+        if (debye_region(FAM_JY, p.w, fnu, kode, true, ival, inz, kval, knz, p.az) < 0) general = true;
+    } else if (!general && p.kreg == KREG_FUSED) {
         path = 2;
         if (fused_ik_region(p.w, fnu, kode, ival, inz, kval, knz, p.az) < 0) general = true;
         if (knz != 0 && p.combine == CMB_Y_SHARED) general = true;

@@ -7,6 +7,7 @@
 // compute entry point fails with SPB_E_NO_DEVICE when no CUDA device exists.
 #include "../../include/sciport_b200.h"
 #include "spb_kernels.cuh"
+#include "amos/spb_family.h"
 
 
 #include <cuda_runtime.h>
@@ -322,6 +323,14 @@ static int fuse_mode() {
     return mode;
 }
 
+static bool debye_enabled() {
+    static const bool on = [] {
+        const char *e = getenv("SPB_DEBYE");
+        return !(e && atoi(e) == 0);
+    }();
+    return on;
+}
+
 int enqueue_chunk(const DevJob &job_in, ScratchSet &ss, int sms, int flags, cudaStream_t st, Prof *pf = nullptr) {
     Prof dummy;
     Prof &p = pf ? *pf : dummy;
@@ -331,7 +340,10 @@ int enqueue_chunk(const DevJob &job_in, ScratchSet &ss, int sms, int flags, cuda
         // the I routine sums anyway)
         const bool ktype = !(job.fam == SPB_FN_J || job.fam == SPB_FN_I);
         const int mode = fuse_mode();
-        job.fuse = (ktype && !(flags & SPB_PATH_MONOLITHIC) && (mode >= 2 || (mode == 1 && job.v_stride == 0))) ? 1 : 0;
+        job.fuse = (ktype && !(flags & SPB_PATH_MONOLITHIC) && (mode >= 2 || (mode == 1 && job.v_stride == 0)))
+                       ? spb::FUSE_ASYI : 0;
+        // Debye-direct region (every family; SPB_DEBYE=0 in the environment switches it off)
+        if (debye_enabled() && !(flags & SPB_PATH_MONOLITHIC)) job.fuse |= spb::FUSE_DEBYE;
         job.pdl = (pdl_enabled() && job.v_stride == 0) ? 1 : 0;
     }
     if (flags & SPB_PATH_MONOLITHIC) {
@@ -347,8 +359,8 @@ int enqueue_chunk(const DevJob &job_in, ScratchSet &ss, int sms, int flags, cuda
     launch_scan_scatter(job, ss.s, st);
     launches += 3;
     const bool ktype = !(job.fam == SPB_FN_J || job.fam == SPB_FN_I);  // K, H1, H2, Y and the JY pair
-    static const int ipass_id[NB_I] = {SPB_K_IPASS_SERIES, SPB_K_IPASS_ASYI, SPB_K_IPASS_MLRI,
-                                       SPB_K_IPASS_WRSK,   SPB_K_IPASS_UNI1, SPB_K_IPASS_UNI2};
+    static const int ipass_id[NB_I] = {SPB_K_IPASS_SERIES, SPB_K_IPASS_ASYI, SPB_K_IPASS_MLRI, SPB_K_IPASS_WRSK,
+                                       SPB_K_IPASS_UNI1,   SPB_K_IPASS_UNI2, SPB_K_IPASS_DEBYE};
     for (int r = 0; r < NB_I; ++r) {
         p.mark(ipass_id[r], st);
         launch_ipass(job, ss.s, r, sms, st);
@@ -376,8 +388,10 @@ void collect_profile(Prof &p, const ScratchSet &ss, long long n) {
         cudaEventElapsedTime(&ms, p.ev[i], p.ev[i + 1]);
         long long pts = n;
         int id = p.ids[i];
-        if ((id >= SPB_K_IPASS_SERIES && id <= SPB_K_IPASS_WRSK) || id == SPB_K_IPASS_UNI1 || id == SPB_K_IPASS_UNI2) {
-            int r = id == SPB_K_IPASS_UNI1 ? 4 : id == SPB_K_IPASS_UNI2 ? 5 : id - SPB_K_IPASS_SERIES;
+        if ((id >= SPB_K_IPASS_SERIES && id <= SPB_K_IPASS_WRSK) || id == SPB_K_IPASS_UNI1 || id == SPB_K_IPASS_UNI2 ||
+            id == SPB_K_IPASS_DEBYE) {
+            int r = id == SPB_K_IPASS_UNI1 ? 4 : id == SPB_K_IPASS_UNI2 ? 5 : id == SPB_K_IPASS_DEBYE ? 6
+                                                                                : id - SPB_K_IPASS_SERIES;
             pts = (long long)bins[r + 1] - bins[r];
         } else if (id == SPB_K_KPASS) {
             pts = (long long)bins[BIN_GENERAL] - bins[BIN_K0];

@@ -26,7 +26,7 @@ void launch_ipass(const DevJob &job, const Scratch &s, int region, int sms, cuda
     switch (region) {
         case spb::IREG_SERIES: launch_ipass_region<spb::IREG_SERIES>(job, s, sms, st); break;
         case spb::IREG_ASYI:
-            if (job.fuse)
+            if (job.fuse & spb::FUSE_ASYI)
                 launch_fused(job, s, sms, st);  // I and K of these points in one kernel (k_fused.cu)
             else
                 launch_ipass_region<spb::IREG_ASYI>(job, s, sms, st);
@@ -41,6 +41,7 @@ void launch_ipass(const DevJob &job, const Scratch &s, int region, int sms, cuda
             break;
         case spb::IREG_UNI1: launch_ipass_region<spb::IREG_UNI1>(job, s, sms, st); break;
         case spb::IREG_UNI2: launch_ipass_region<spb::IREG_UNI2>(job, s, sms, st); break;
+        case spb::IREG_DEBYE: launch_debye(job, s, sms, st); break;
         default: break;
     }
 }

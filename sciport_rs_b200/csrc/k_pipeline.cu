@@ -47,10 +47,11 @@ struct Packed {
     }
 };
 
-// The three keys of a class byte land in fixed places of the two words (NB_I = 6, five fields per word):
-// I bins 0..4 -> word 0, field bi; I bin 5 -> word 1, field 0; K bins -> word 1, fields 1..3; general -> word 1,
-// field 4.  Written out so that the only variable-dependent work is one multiply and one shift per key.
-static_assert(NB_I == 6 && NB_K == 3 && FIELDS_PER_WORD == 5 && NWORDS == 2, "packed layout below assumes 6 + 3 + 1 bins");
+// The three keys of a class byte land in fixed places of the three words (NB_I = 7, five fields per word):
+// I bins 0..4 -> word 0, field bi; I bins 5, 6 -> word 1, fields 0, 1; K bins -> word 1, fields 2..4; general ->
+// word 2, field 0 (= field number bin of the generic Packed::field()).  Written out so that the only
+// variable-dependent work is one multiply and one shift per key.
+static_assert(NB_I == 7 && NB_K == 3 && FIELDS_PER_WORD == 5 && NWORDS == 3, "packed layout below assumes 7 + 3 + 1 bins");
 
 __device__ __forceinline__ void packed_add(unsigned int c, Packed &p) {
     int bi, bk;
@@ -58,21 +59,21 @@ __device__ __forceinline__ void packed_add(unsigned int c, Packed &p) {
     point_bins(c, bi, bk, gen);
     if (bi < 5)
         p.w[0] += 1ull << (FIELD_BITS * bi);
-    else if (bi == 5)
-        p.w[1] += 1ull;
-    if (bk != 3) p.w[1] += 1ull << (FIELD_BITS * (bk + 1));
-    if (gen) p.w[1] += 1ull << (FIELD_BITS * 4);
+    else if (bi != 7)
+        p.w[1] += 1ull << (FIELD_BITS * (bi - 5));
+    if (bk != 3) p.w[1] += 1ull << (FIELD_BITS * (bk + 2));
+    if (gen) p.w[2] += 1ull;
 }
 
 __device__ __forceinline__ unsigned int field_i(const Packed &p, int bi) {
-    unsigned long long x = bi < 5 ? (p.w[0] >> (FIELD_BITS * bi)) : p.w[1];
+    unsigned long long x = bi < 5 ? (p.w[0] >> (FIELD_BITS * bi)) : (p.w[1] >> (FIELD_BITS * (bi - 5)));
     return (unsigned int)x & ((1u << FIELD_BITS) - 1u);
 }
 __device__ __forceinline__ unsigned int field_k(const Packed &p, int bk) {
-    return (unsigned int)(p.w[1] >> (FIELD_BITS * (bk + 1))) & ((1u << FIELD_BITS) - 1u);
+    return (unsigned int)(p.w[1] >> (FIELD_BITS * (bk + 2))) & ((1u << FIELD_BITS) - 1u);
 }
 __device__ __forceinline__ unsigned int field_g(const Packed &p) {
-    return (unsigned int)(p.w[1] >> (FIELD_BITS * 4)) & ((1u << FIELD_BITS) - 1u);
+    return (unsigned int)p.w[2] & ((1u << FIELD_BITS) - 1u);
 }
 
 // FAM / KODE: the job's family and scaling flag as compile-time constants (dispatch_fam_kode)
@@ -114,7 +115,7 @@ __global__ void __launch_bounds__(256) k_classify(DevJob job, Scratch s) {
         for (int k = 0; k < PER_THREAD; ++k) {
             int ireg, kreg;
             if (!scalar_order) fo = spb::fast_order(vk[k]);
-            const bool ok = spb::fast_classify(job.fam, cplx(zk[k].x, zk[k].y), fo, job.kode, job.fuse != 0, ireg, kreg);
+            const bool ok = spb::fast_classify(job.fam, cplx(zk[k].x, zk[k].y), fo, job.kode, job.fuse, ireg, kreg);
             unsigned int c = 0xffu;
             if (__all_sync(0xffffffffu, ok)) c = spb::class_of(ireg, kreg);
             cls4[k / 4] |= c << (8 * (k % 4));
@@ -130,7 +131,7 @@ __global__ void __launch_bounds__(256) k_classify(DevJob job, Scratch s) {
                 cplx z;
                 double v;
                 load_point(job, i, z, v);
-                c = spb::class_byte(job.fam, z, v, job.kode, job.fuse != 0, false);
+                c = spb::class_byte(job.fam, z, v, job.kode, job.fuse, false);
             }
             s.cls[i] = (unsigned char)c;
             packed_add(c, cnt);

@@ -11,7 +11,8 @@ struct DevJob {
     int fam;   // spb::Family
     int kode;  // 1 | 2
     int sem;   // 0 raw AMOS, 1 scipy-compatible post-processing
-    int fuse;  // 1: points needing I and K with I in the large-|w| region are evaluated by the fused region kernel
+    int fuse;  // spb::FUSE_ASYI (1): points needing I and K with I in the large-|w| region are evaluated by the fused
+               // region kernel; spb::FUSE_DEBYE (2): the Debye-direct region (spb_debye.h) is carved out
     int pdl;   // 1: the kernels of this chunk are launched as programmatic dependents of each other (launch_pdl)
     int reflect;  // 1: orders v < 0 by the reflection formulae (K folds v -> |v| at load; the others on the general path)
     const double *v;
@@ -45,9 +46,9 @@ struct Scratch {
     int nblocks;            // tiles in this chunk
 };
 
-// bins: 0..5 I regions (series, asyi, mlri, wrsk, uniform form 1, uniform form 2), 6..8 K regions (series,
-// miller, half), 9 general.  The I bins index perm_i, the K bins perm_k, the general bin glist.
-constexpr int NB_I = 6;
+// bins: 0..6 I regions (series, asyi, mlri, wrsk, uniform form 1, uniform form 2, Debye-direct), 7..9 K regions
+// (series, miller, half), 10 general.  The I bins index perm_i, the K bins perm_k, the general bin glist.
+constexpr int NB_I = 7;
 constexpr int NB_K = 3;
 constexpr int BIN_K0 = NB_I;
 constexpr int BIN_GENERAL = NB_I + NB_K;
@@ -135,6 +136,7 @@ void launch_classify(const DevJob &job, const Scratch &s, cudaStream_t st);
 void launch_scan_scatter(const DevJob &job, const Scratch &s, cudaStream_t st);
 void launch_ipass(const DevJob &job, const Scratch &s, int region, int sms, cudaStream_t st);
 void launch_fused(const DevJob &job, const Scratch &s, int sms, cudaStream_t st);  // job.fuse: I + K, large-|w| region
+void launch_debye(const DevJob &job, const Scratch &s, int sms, cudaStream_t st);  // Debye-direct region (k_debye.cu)
 void launch_kpass(const DevJob &job, const Scratch &s, int sms, cudaStream_t st);
 int launch_general(const DevJob &job, const Scratch &s, int sms, cudaStream_t st);
 void launch_monolithic(const DevJob &job, cudaStream_t st);

@@ -41,6 +41,12 @@ def oracle_lib():
     return _oracle
 
 
+def _mode_bits(fuse):
+    """fuse: False / True (fused large-|w| I + K routine) or a bitmask (1 = that, 2 = Debye-direct region)."""
+    f = int(fuse)
+    return (0x10000 if f & 1 else 0) | (0x20000 if f & 2 else 0)
+
+
 def cpu_bessel(fn, kode, v, z, sem=0, pipeline=False, threads=8, fuse=False):
     lib = oracle_lib()
     z = np.ascontiguousarray(z, dtype=np.complex128)
@@ -51,7 +57,7 @@ def cpu_bessel(fn, kode, v, z, sem=0, pipeline=False, threads=8, fuse=False):
     if pipeline:
         path = np.empty(z.shape, np.int32)
         lib.spbo_bessel_pipeline(FN[fn], kode, v.ctypes.data, 1, z.ctypes.data, out.ctypes.data, ierr.ctypes.data,
-                                 nz.ctypes.data, path.ctypes.data, z.size, threads | (0x10000 if fuse else 0))
+                                 nz.ctypes.data, path.ctypes.data, z.size, threads | _mode_bits(fuse))
         return out, ierr, nz, path
     lib.spbo_bessel_sem(FN[fn], kode, sem, v.ctypes.data, 1, z.ctypes.data, out.ctypes.data, ierr.ctypes.data,
                         nz.ctypes.data, z.size, threads)
@@ -92,7 +98,7 @@ def cpu_bessel_jy(kode, v, z, threads=8, fuse=False):
     oj, oy = np.empty_like(z), np.empty_like(z)
     codes = np.empty((4, z.size), np.int32)
     lib.spbo_bessel_jy_pipeline(kode, v.ctypes.data, 1, z.ctypes.data, oj.ctypes.data, oy.ctypes.data, codes.ctypes.data,
-                                z.size, threads | (0x10000 if fuse else 0))
+                                z.size, threads | _mode_bits(fuse))
     return (oj, codes[0], codes[2]), (oy, codes[1], codes[3])
 
 

@@ -19,7 +19,8 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 from test_pipeline_cpu import gen  # noqa: E402
 
 KERNELS = ["classify", "scan_scatter", "ipass_series", "ipass_asyi", "ipass_mlri", "ipass_wrsk", "kpass", "general",
-           "monolithic", "ipass_uni1", "ipass_uni2"]
+           "monolithic", "ipass_uni1", "ipass_uni2", "ipass_debye"]
+NK = len(KERNELS)
 FN = {"J": 0, "Y": 1, "I": 2, "K": 3, "H1": 4, "H2": 5, "JY": 6}
 
 
@@ -39,26 +40,37 @@ def main():
     out = {"_rule": "add/sub/mul/div/sqrt = 1, exp/log/sin/cos/atan/sinh/cosh = 30, pow = 60; per point, "
                     "prepare + region + finish", "_sample": {}}
     rng = np.random.default_rng(1)
-    # last field: fused I + K in the large-|w| region (the library's default)
-    samples = {"cfg2": (cfg2_sample(1 << 18), ("J", "Y", "JY"), 1, 1),
-               "cfg3": (gen("cfg3", 1 << 17, rng), ("I", "K"), 2, 1),
-               "cfg4": (gen("cfg4", 1 << 17, rng), ("H1", "H2"), 1, 1)}
+    # last field: the single-evaluation routines of the library's default flow (1 = fused I + K in the large-|w|
+    # region for K-type families, 2 = Debye-direct region)
+    samples = {"cfg2": (cfg2_sample(1 << 18), ("J", "Y", "JY"), 1, 3),
+               "cfg3": (gen("cfg3", 1 << 17, rng), ("I", "K"), 2, 3),
+               "cfg4": (gen("cfg4", 1 << 17, rng), ("H1", "H2"), 1, 3)}
     for cfg, ((v, z), fams, kode, fuse) in samples.items():
         v = np.ascontiguousarray(v, dtype=np.float64)
         z = np.ascontiguousarray(z, dtype=np.complex128)
         for fn in fams:
-            ops = np.zeros(11)
-            pts = np.zeros(11, np.int64)
+            ops = np.zeros(NK)
+            pts = np.zeros(NK, np.int64)
             lib.spbo_count_ops2(FN[fn], kode, fuse, v.ctypes.data, 1, z.ctypes.data, z.size, ops.ctypes.data,
                                 pts.ctypes.data)
-            total = ops[2:8].sum() + ops[9:11].sum() + ops[0]
-            for k in range(11):
+            # J and I families: the fused large-|w| routine does not apply (bit 0 is ignored by the library too)
+            total = ops[2:8].sum() + ops[9:NK].sum() + ops[0]
+            for k in range(NK):
                 if pts[k]:
                     key = f"{fn}/{KERNELS[k]}" if cfg == "cfg2" else f"{cfg}:{fn}/{KERNELS[k]}"
                     out[key] = {"flops_per_point": ops[k] / pts[k], "points": int(pts[k])}
             key = f"{fn}/per_eval" if cfg == "cfg2" else f"{cfg}:{fn}/per_eval"
             out[key] = {"flops_per_point": total / z.size, "points": int(z.size)}
-            out["_sample"][f"{cfg}:{fn}"] = f"{z.size} points, kode={kode}, fused I+K in the large-|w| region: {bool(fuse)}"
+            out["_sample"][f"{cfg}:{fn}"] = (f"{z.size} points, kode={kode}, fused I+K in the large-|w| region: "
+                                              f"{bool(fuse & 1)}, Debye-direct region: {bool(fuse & 2)}")
+    # Airy (cfg4 distribution): the complete routine per point
+    lib.spbo_count_ops_airy.restype = ctypes.c_double
+    lib.spbo_count_ops_airy.argtypes = [ctypes.c_int, ctypes.c_int, P, ctypes.c_int64]
+    _, z4 = gen("cfg4", 1 << 16, rng)
+    z4 = np.ascontiguousarray(z4, dtype=np.complex128)
+    for which, name in ((0, "Ai"), (2, "Bi")):
+        f = lib.spbo_count_ops_airy(which, 1, z4.ctypes.data, z4.size)
+        out[f"cfg4:{name}/per_eval"] = {"flops_per_point": f, "points": int(z4.size)}
     os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
     with open(os.path.join(ROOT, "profiles", "flops_per_eval.json"), "w") as f:
         json.dump(out, f, indent=1)
