@@ -102,7 +102,7 @@ def last_timing(want_ms=True):
     return ms.value, n.value
 
 
-def last_profile(max_records=64):
+def last_profile(max_records=4096):
     import numpy as np
     ids = np.zeros(max_records, np.int32)
     ms = np.zeros(max_records, np.float64)

@@ -63,7 +63,11 @@ SPB_FN int debye_ik(cplx w, real fnu, int kode, bool need_i, bool need_k, cplx &
     // s^2 = v^2 + w^2, s = sqrt(s^2) with Re s >= 0; 1/s = conj(s)/|s|^2
     const cplx s2(v2 + (w.re - w.im) * (w.re + w.im), real(2.0) * w.re * w.im);
     const real d = cabs_(s2);  // |s|^2
-    const cplx s = csqrt_mod(s2, d);
+    cplx s = csqrt_mod(s2, d);
+    // On the imaginary axis beyond the turning point (Re w = 0, |Im w| > v: real arguments of J, Y, H) s^2 is a
+    // negative real number and its square root sits on the branch cut: s is the continuation of the values next to
+    // the axis, where Im s^2 = 2 Re w Im w has the sign of Im w (s ~ w for large |w|)
+    if (s.re == real(0.0) && w.im < real(0.0)) s.im = -rabs(s.im);
     const real rd = rcp_fast(d);
     const cplx rs(s.re * rd, -s.im * rd);
     // t^2 = v^2 / s^2 = v^2 conj(s^2) / |s|^4

@@ -210,7 +210,15 @@ SPB_HD cplx csinpi_(cplx z) {
     sincospi(x, &sx, &cx);
 #else
     sx = sinpi_(x);
-    cx = sinpi_(x + real(0.5));
+    // cos(pi x) with an exact +0 at the half-integers (the sign of that zero decides the branch of ln sin(pi z)
+    // on the lines Re z = n + 1/2: like CUDA's cospi and the oracle's, never -0)
+    real r = fmod(rabs(x), real(2.0));
+    if (r == real(0.5) || r == real(1.5))
+        cx = real(0.0);
+    else if (r < real(1.0))
+        cx = -sin(real(SPB_PI) * (r - real(0.5)));
+    else
+        cx = sin(real(SPB_PI) * (r - real(1.5)));
 #endif
     return cplx(sx * cosh(piy), cx * sinh(piy));
 }

@@ -97,3 +97,30 @@ def test_debye_region_is_used_and_bounded():
                 s2 = v * v + w * w
                 assert np.all(np.sqrt(np.abs(s2[deb])) >= 36.0 * (1 - 1e-12))
                 assert np.all(np.abs(s2[deb]) ** 1.5 / (v[deb] ** 2) >= 240.0 * (1 - 1e-12))
+
+
+def test_debye_region_on_the_axes_exactly():
+    """Real arguments of J / Y / H put the evaluation point w exactly on the imaginary axis (s^2 = v^2 + w^2 on the
+    branch cut of the square root beyond the turning point), imaginary arguments of I / K likewise; real arguments
+    of I / K sit on the real axis.  Against live scipy and against points a hair off the axis."""
+    rng = np.random.default_rng(17)
+    n = 4000
+    v = 5 + 45 * rng.random(n)
+    r = 60 + 140 * rng.random(n)
+    for fn, zs in (("J", r + 0j), ("Y", r + 0j), ("H1", r + 0j), ("H2", -r + 0j), ("I", 1j * r), ("I", -1j * r),
+                   ("K", 1j * r), ("I", r + 0j), ("K", r + 0j), ("I", -r + 0j), ("J", -r + 0j)):
+        for kode in (1, 2):
+            got, ierr, nz, path = helpers.cpu_bessel(fn, kode, v, zs, pipeline=True, fuse=FUSE_ALL)
+            _, full = helpers.cpu_classify(fn, kode, v, zs, FUSE_ALL)
+            assert ((full & 7) == 6).mean() > 0.3  # the Debye-direct region is exercised on the axis
+            want = so.evaluate(fn, kode, v, zs)
+            scale = so.scale_near_zeros(fn, kode, v, zs, want)
+            if fn in ("H1", "H2"):
+                # on the real axis (the border of the half plane where H grows) the two terms of the continuation
+                # cancel partially: |J| is the size of the terms (measured against 40-digit mpmath at v = 40.67,
+                # z = -116.05: this flow 8e-14, the classic drivers 1.7e-13, scipy 1.3e-12 relative to |H2| = 0.009)
+                scale = np.maximum(scale, np.abs(so.evaluate("J", kode, v, zs)))
+            ok = (ierr == 0) & (nz == 0) & np.isfinite(want.real) & np.isfinite(want.imag)
+            err = so.mismatch(got, want, scale)
+            bad = ok & (err > so.tolerance(want, zs, v))
+            assert not bad.any(), (fn, kode, int(bad.sum()), v[bad][:2], zs[bad][:2], err[bad][:2])
