@@ -160,6 +160,24 @@ int spb_devmath(int which, const double *x, double *out, int64_t n, const spb_ex
 int spb_kaiser(int64_t m, double beta, int sym, double *out, const spb_exec *ex);
 int spb_lanczos(int64_t m, int sym, double *out, const spb_exec *ex);
 
+/* ---- every window of signal::windows as ONE fused kernel per kind: the selector of
+ * get_window(WindowType, nx, fftbins) (windows.rs:116-152).  Index -> argument -> value -> store, nothing is read.
+ * params (n_params doubles):
+ *   GENERAL_COSINE  the coefficients a_k (<= 16); blackman / hamming / hann / flattop / blackmanharris / nuttall /
+ *                   general_hamming are general_cosine with fixed coefficients (windows.rs:220-250, 272-285, 342-356)
+ *   EXPONENTIAL     center (NaN = (m - 1)/2), tau           TUKEY  alpha (alpha <= 0: ones, alpha >= 1: hann)
+ *   TAYLOR          nbar (<= 17), sll, norm (0 / 1; the reference accepts `norm` and ignores it, windows.rs:466)
+ *   GAUSSIAN        std                                      GENERAL_GAUSSIAN  power, width
+ *   KAISER, KBD     beta                                     the others take none
+ * KBD (kaiser_bessel_derived, windows.rs:560-589) needs an even m; its running sum is a device scan. */
+enum spb_window_kind {
+    SPB_WIN_BOXCAR = 0, SPB_WIN_TRIANG = 1, SPB_WIN_GENERAL_COSINE = 2, SPB_WIN_BARTLETT = 3, SPB_WIN_PARZEN = 4,
+    SPB_WIN_BOHMAN = 5, SPB_WIN_BARTHANN = 6, SPB_WIN_COSINE = 7, SPB_WIN_EXPONENTIAL = 8, SPB_WIN_TUKEY = 9,
+    SPB_WIN_TAYLOR = 10, SPB_WIN_GAUSSIAN = 11, SPB_WIN_GENERAL_GAUSSIAN = 12, SPB_WIN_KAISER = 13,
+    SPB_WIN_LANCZOS = 14, SPB_WIN_KBD = 15
+};
+int spb_window(int kind, int64_t m, int sym, const double *params, int n_params, double *out, const spb_exec *ex);
+
 /* ---- first error in index order = `.collect::<Result<_, i32>>()` (mod.rs:11-12) ------------
  * *idx = -1, *code = 0 when every element is OK.  ierr lives where ex says. */
 int spb_first_error(const int32_t *ierr, int64_t n, int64_t *idx, int32_t *code, const spb_exec *ex);

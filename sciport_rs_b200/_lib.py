@@ -51,6 +51,7 @@ def _load():
     lib.spb_devmath.argtypes = [I, P, P, L, EX]
     lib.spb_kaiser.argtypes = [L, ctypes.c_double, I, P, EX]
     lib.spb_lanczos.argtypes = [L, I, P, EX]
+    lib.spb_window.argtypes = [I, L, I, P, I, P, EX]
     lib.spb_first_error.argtypes = [P, L, ctypes.POINTER(L), ctypes.POINTER(ctypes.c_int32), EX]
     lib.spb_last_first_error.argtypes = [I, ctypes.POINTER(L), ctypes.POINTER(ctypes.c_int32)]
     lib.spb_synth.argtypes = [I, ctypes.c_uint64, L, L, L, P, P, EX]
@@ -66,7 +67,7 @@ def _load():
 
 EXPORTS = [
     "spb_bessel", "spb_bessel_jy", "spb_bessel_real", "spb_airy", "spb_gamma", "spb_lgamma", "spb_cgamma", "spb_clgamma",
-    "spb_sinc", "spb_devmath", "spb_kaiser", "spb_lanczos", "spb_first_error", "spb_last_first_error", "spb_synth", "spb_fp64_peak", "spb_last_timing", "spb_last_profile", "spb_device_topology", "spb_device_count",
+    "spb_sinc", "spb_devmath", "spb_kaiser", "spb_lanczos", "spb_window", "spb_first_error", "spb_last_first_error", "spb_synth", "spb_fp64_peak", "spb_last_timing", "spb_last_profile", "spb_device_topology", "spb_device_count",
     "spb_version", "spb_last_error",
 ]
 

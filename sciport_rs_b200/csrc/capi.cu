@@ -1019,56 +1019,101 @@ int spb_devmath(int which, const double *x, double *out, int64_t n, const spb_ex
 }
 
 // windows: nothing is read, m doubles are written (device pointer: on the caller's stream; host pointer: staged)
-static int window_impl(int kind, int64_t m, double beta, int sym, double *out, const spb_exec *ex) {
+static int window_impl(int kind, int64_t m, int sym, const double *params, int n_params, double *out,
+                       const spb_exec *ex) {
     std::vector<int> devs;
     bool dptr;
     cudaStream_t st;
     int flags;
     int rc = check_exec(ex, devs, dptr, st, flags);
     if (rc != SPB_OK) return rc;
+    if (kind < SPB_WIN_BOXCAR || kind > SPB_WIN_KBD) return fail(SPB_E_ARG, "unknown window kind");
     if (m < 0) return fail(SPB_E_ARG, "negative window length");
+    if (n_params < 0 || n_params > SPB_WIN_MAX_PARAMS || (n_params > 0 && !params))
+        return fail(SPB_E_ARG, "bad window parameters");
+    static const int need[] = {0, 0, 1, 0, 0, 0, 0, 0, 2, 1, 3, 1, 2, 1, 0, 1};
+    if (n_params < need[kind]) return fail(SPB_E_ARG, "too few window parameters");
+    WinParams p{};
+    p.n = n_params;
+    for (int k = 0; k < n_params; ++k) p.a[k] = params[k];
+    if ((kind == SPB_WIN_KAISER || kind == SPB_WIN_KBD) && !(p.a[0] == p.a[0])) return fail(SPB_E_ARG, "beta is NaN");
+    if (kind == SPB_WIN_TAYLOR && !(p.a[0] >= 2.0 && p.a[0] <= SPB_WIN_MAX_PARAMS + 1.0))
+        return fail(SPB_E_ARG, "taylor: nbar must be 2..17");
+    if (kind == SPB_WIN_KBD && m > 1 && (m % 2) != 0)
+        return fail(SPB_E_ARG, "Kaiser-Bessel derived windows are only defined for an even number of points");
     if (m == 0) return SPB_OK;
     if (!out) return fail(SPB_E_ARG, "null buffer");
-    if (kind == 0 && !(beta == beta)) return fail(SPB_E_ARG, "beta is NaN");
+    // degenerate parameter values are other windows (windows.rs:423-427)
+    if (kind == SPB_WIN_TUKEY && p.a[0] <= 0.0) kind = SPB_WIN_BOXCAR;
+    if (kind == SPB_WIN_TUKEY && p.a[0] >= 1.0) {
+        kind = SPB_WIN_GENERAL_COSINE;
+        p.a[0] = 0.5;
+        p.a[1] = 0.5;
+        p.n = 2;
+    }
     DeviceCtx *c = get_ctx(devs[0]);
     std::lock_guard<std::mutex> lk(c->mu);
     CK(cudaSetDevice(c->dev));
     cudaStream_t s0 = dptr ? st : c->streams[0];
+    // the Kaiser kinds share the per-device scalar I0(beta) and KBD the staging buffer: order against a device-pointer
+    // call that may still be queued on another stream
+    if (dptr)
+        order_after_previous(c, s0);
+    else if (c->busy_valid)
+        cudaEventSynchronize(c->busy);
     double *dout = out;
-    if (!dptr && cudaMalloc(&dout, m * 8) != cudaSuccess) {
-        cudaGetLastError();
-        return fail(SPB_E_ALLOC, "cudaMalloc failed");
+    if (!dptr) {
+        rc = ensure_stage(c->stage[0], std::max<long long>(1024, (m + 1) / 2 + 1), false, false, false, false);
+        if (rc != SPB_OK) return rc;
+        dout = (double *)c->stage[0].out;  // 16 bytes per staged element: room for m doubles
     }
     g_last_launches = 1;
+    cudaError_t e = cudaSuccess;
     if (m <= 1) {
         // len_guards (windows.rs:624-626, 650-656): windows of length <= 1 are all ones
-        const double one = 1.0;
-        CK(cudaMemcpyAsync(dout, &one, 8, cudaMemcpyHostToDevice, s0));
+        static const double one = 1.0;
+        e = cudaMemcpyAsync(dout, &one, 8, cudaMemcpyHostToDevice, s0);
     } else {
         // periodic windows (sym = false) are the first m points of the symmetric window of length m + 1
         // (extend / truncate, windows.rs:628-647)
         const long long m_ext = sym ? m : m + 1;
-        if (kind == 0) {
-            launch_kaiser(m_ext, m, beta, c->d_scalar, dout, c->sms, s0);
+        if (kind == SPB_WIN_KAISER) {
+            launch_kaiser(m_ext, m, p.a[0], c->d_scalar, dout, c->sms, s0);
             g_last_launches = 2;
-        } else {
+        } else if (kind == SPB_WIN_LANCZOS) {
             launch_lanczos(m_ext, m, dout, s0);
+        } else if (kind == SPB_WIN_KBD) {
+            // Kaiser window of length m/2 + 1 into the z staging buffer, then the scan (sym is ignored: windows.rs:560)
+            const long long h = m / 2;
+            rc = ensure_stage(c->stage[1], std::max<long long>(1024, h + 1), false, false, false, false);
+            if (rc != SPB_OK) return rc;
+            double *kbuf = (double *)c->stage[1].z;
+            launch_kaiser(h + 1, h + 1, p.a[0], c->d_scalar, kbuf, c->sms, s0);
+            launch_kbd_finish(kbuf, h, dout, s0);
+            g_last_launches = 3;
+        } else {
+            launch_window(kind, m_ext, m, p, dout, s0);
         }
+        e = cudaGetLastError();
     }
-    CK(cudaGetLastError());
-    if (!dptr) {
-        cudaError_t e = cudaMemcpyAsync(out, dout, m * 8, cudaMemcpyDeviceToHost, s0);
+    if (e == cudaSuccess && !dptr) {
+        e = cudaMemcpyAsync(out, dout, m * 8, cudaMemcpyDeviceToHost, s0);
         if (e == cudaSuccess) e = cudaStreamSynchronize(s0);
-        cudaFree(dout);
-        if (e != cudaSuccess) return fail(SPB_E_CUDA, cudaGetErrorString(e));
     }
+    if (dptr) mark_busy(c, s0);
+    if (e != cudaSuccess) return fail(SPB_E_CUDA, cudaGetErrorString(e));
     return SPB_OK;
 }
 
 int spb_kaiser(int64_t m, double beta, int sym, double *out, const spb_exec *ex) {
-    return window_impl(0, m, beta, sym, out, ex);
+    return window_impl(SPB_WIN_KAISER, m, sym, &beta, 1, out, ex);
 }
-int spb_lanczos(int64_t m, int sym, double *out, const spb_exec *ex) { return window_impl(1, m, 0.0, sym, out, ex); }
+int spb_lanczos(int64_t m, int sym, double *out, const spb_exec *ex) {
+    return window_impl(SPB_WIN_LANCZOS, m, sym, nullptr, 0, out, ex);
+}
+int spb_window(int kind, int64_t m, int sym, const double *params, int n_params, double *out, const spb_exec *ex) {
+    return window_impl(kind, m, sym, params, n_params, out, ex);
+}
 
 int spb_first_error(const int32_t *ierr, int64_t n, int64_t *idx, int32_t *code, const spb_exec *ex) {
     if (!idx || !code) return fail(SPB_E_ARG, "null output");

@@ -154,6 +154,14 @@ void launch_sinc(const double *x, double *out, long long n, cudaStream_t st);
 void launch_devmath(int which, const double *x, double *out, long long n, cudaStream_t st);
 void launch_kaiser(long long m_ext, long long n_out, double beta, double2 *den, double *out, int sms, cudaStream_t st);
 void launch_lanczos(long long m_ext, long long n_out, double *out, cudaStream_t st);
+// elementwise windows (k_window.cu): parameters by value, at most SPB_WIN_MAX_PARAMS doubles
+constexpr int SPB_WIN_MAX_PARAMS = 16;
+struct WinParams {
+    double a[SPB_WIN_MAX_PARAMS];
+    int n;
+};
+void launch_window(int kind, long long m_ext, long long n_out, const WinParams &p, double *out, cudaStream_t st);
+void launch_kbd_finish(const double *k, long long h, double *out, cudaStream_t st);
 double run_fp64_peak(int device, double seconds, double *sm_mhz);
 
 }  // namespace spbk
