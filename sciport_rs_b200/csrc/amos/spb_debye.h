@@ -27,7 +27,27 @@
 #pragma once
 #include "spb_common.h"
 
+// Namespace-scope coefficient tables: constant memory on the device (a DFMA then reads the coefficient as a
+// constant-bank operand; as a literal it costs two moves into a register pair first: 17 % of the instructions of
+// the first version of this kernel), a plain static array on the host.
+#if defined(__CUDA_ARCH__)
+#define SPB_CONST_TABLE(name, n) static __constant__ double name[n]
+#elif defined(__CUDACC__)
+#define SPB_CONST_TABLE(name, n) static __constant__ double name[n]
+#else
+#define SPB_CONST_TABLE(name, n) static const double name[n]
+#endif
+
 namespace spb {
+namespace dby {
+#include "spb_tables_debye.inc"
+// (atan(r)/r - 1)/r^2 on r^2 <= tan(pi/8)^2, highest power first (tools/gen_tables.py --debye; fit error 2e-22)
+SPB_CONST_TABLE(ATANC, 14) = {1.19595677955128283e-02, -2.72748188162988958e-02, 3.72343513633974776e-02,
+                              -4.29426924398485510e-02, 4.75462140340531039e-02, -5.26245398479938398e-02,
+                              5.88230463938551468e-02,  -6.66666434483427356e-02, 7.69230761627277687e-02,
+                              -9.09090908929153091e-02, 1.11111111110904534e-01,  -1.42857142857141489e-01,
+                              1.99999999999999983e-01,  -3.33333333333333315e-01};
+}  // namespace dby
 
 #ifndef SPB_DEBYE_S0
 #define SPB_DEBYE_S0 36.0
@@ -35,6 +55,36 @@ namespace spb {
 #ifndef SPB_DEBYE_P0
 #define SPB_DEBYE_P0 240.0
 #endif
+
+// acc * y + q with a real q: two fused multiply-adds per component
+SPB_HD cplx horner_step(cplx acc, cplx y, real q) {
+    return cplx(fma_(acc.re, y.re, fma_(-acc.im, y.im, q)), fma_(acc.re, y.im, acc.im * y.re));
+}
+
+// atan2(y, x) for arguments on scale (neither both zero nor near the ends of the exponent range): the quotient
+// min/max through the branch-free reciprocal, one reduction at tan(pi/8) and a degree-13 polynomial in r^2
+// (<= 1 ulp of pi/4 absolute, <= 2 ulp relative near 0); quadrant by selection.  The library form on the host.
+SPB_HD real atan2_onscale(real y, real x) {
+#if defined(__CUDA_ARCH__)
+    const double ax = fabs(x), ay = fabs(y);
+    const double mx = ax > ay ? ax : ay, mn = ax > ay ? ay : ax;
+    double a = mn * rcp_onscale(mx);  // [0, 1]
+    const bool hi = a > 0.41421356237309503;
+    // (a - 1)/(a + 1) in [-0.4143, 0] for a in (tan(pi/8), 1]
+    const double r = hi ? (a - 1.0) * rcp_onscale(a + 1.0) : a;
+    const double u = r * r;
+    double p = dby::ATANC[0];
+#pragma unroll
+    for (int k = 1; k < 14; ++k) p = fma(p, u, dby::ATANC[k]);
+    double t = fma(r * u, p, r);
+    t = hi ? t + 0.78539816339744828 + 3.061616997868383e-17 : t;  // + pi/4 (head + tail)
+    t = ay > ax ? 1.5707963267948966 - t : t;
+    t = x < 0.0 ? 3.141592653589793 - t : t;
+    return y < 0.0 ? -t : t;
+#else
+    return atan2(y, x);
+#endif
+}
 
 // Is (w, v) inside the calibrated region?  Squares only: m = |v^2 + w^2|^2 = |s|^4;
 //   |s| >= S0  <=>  m >= S0^4 ;   |s|^3 / v^2 >= P0  <=>  m^3 >= (P0 v^2)^4
@@ -52,57 +102,76 @@ SPB_HD bool debye_ok(cplx w, real fnu) {
 
 // need_i / need_k: which of the two functions the caller wants (the other output is left untouched).
 // kode 1: I_v(w), K_v(w); kode 2: e^{-Re w} I_v(w), e^{w} K_v(w).  Returns 0, or < 0 when the point has to go to
-// the general path (exponent off the middle scaling level, series not converged).
+// the general path (exponent off the middle scaling level).
+//
+// Series.  sum_{k<=14} P_k(t^2)/s^k with t^2 = v^2/s^2 is regrouped by powers of 1/s (tools/gen_tables.py,
+// gen_debye_series):  sum_m Q_m(v^2)/s^m  with REAL polynomials Q_m of the real variable v^2 (119 coefficients in
+// all), summed as two Horner chains in y = 1/s^2 (even m, odd m).  Even + odd is the series of I, even - odd the
+// alternating series of K.  Against the term-by-term form (complex Horner in t^2 per term, convergence exit): a
+// third of the arithmetic, no data-dependent trip count (the lanes of a warp never part), and independent chains
+// for the pipeline to overlap.  All 14 terms are always summed; inside the calibrated region they decrease
+// monotonically, the 14th is below 3e-14.
 SPB_FN int debye_ik(cplx w, real fnu, int kode, bool need_i, bool need_k, cplx &ival, cplx &kval, real az,
                     const OrderPhase *oph = nullptr) {
-#include "spb_tables_unik.inc"
-    const real tol = SPB_TOL, alim = SPB_ALIM;
+    using dby::DQ;
+    const real alim = SPB_ALIM;
     const real rt2pi = 0.398942280401432678;   // 1/sqrt(2 pi)
     const real rthpi = 1.25331413731550025;    // sqrt(pi/2)
+    (void)az;
     const real v2 = fnu * fnu;
-    // s^2 = v^2 + w^2, s = sqrt(s^2) with Re s >= 0; 1/s = conj(s)/|s|^2
+    // s^2 = v^2 + w^2, s = sqrt(s^2) with Re s >= 0, 1/s = conj(s)/|s|^2, 1/sqrt(s): selections, no branches
     const cplx s2(v2 + (w.re - w.im) * (w.re + w.im), real(2.0) * w.re * w.im);
-    const real d = cabs_(s2);  // |s|^2
-    cplx s = csqrt_mod(s2, d);
-    // On the imaginary axis beyond the turning point (Re w = 0, |Im w| > v: real arguments of J, Y, H) s^2 is a
-    // negative real number and its square root sits on the branch cut: s is the continuation of the values next to
-    // the axis, where Im s^2 = 2 Re w Im w has the sign of Im w (s ~ w for large |w|)
-    if (s.re == real(0.0) && w.im < real(0.0)) s.im = -rabs(s.im);
-    const real rd = rcp_fast(d);
-    const cplx rs(s.re * rd, -s.im * rd);
-    // t^2 = v^2 / s^2 = v^2 conj(s^2) / |s|^4
-    const real q = v2 * rd * rd;
-    const cplx x(s2.re * q, -s2.im * q);
-    // sum of P_k(t^2) / s^k, k = 1..14 (table UK: u_k coefficients highest power of t^2 first, u_0 = 1 at UK[0]);
-    // both loops unrolled so that every table index is a compile-time constant; all-plus and alternating sums
-    cplx sp(1.0, 0.0), sm(1.0, 0.0), pw(1.0, 0.0);
-    real last = 1.0;
-    int l = 1;
-    SPB_UNROLL
-    for (int k = 1; k <= 14; ++k) {
-        cplx pk(real(UK[l]), 0.0);
-        SPB_UNROLL
-        for (int j = 1; j <= k; ++j) pk = pk * x + real(UK[l + j]);
-        l += k + 1;
-        pw = pw * rs;
-        const cplx term = pw * pk;
-        sp = sp + term;
-        sm = (k & 1) ? sm - term : sm + term;
-        last = rabs(term.re) + rabs(term.im);
-        if (last < tol) break;
+    cplx s, rs, phi;
+    {
+#if defined(__CUDA_ARCH__)
+        const double m2 = fma(s2.re, s2.re, s2.im * s2.im);       // |s|^4, on scale (>= S0^4)
+        const double mi = rsqrt_onscale(m2);
+        double d = m2 * mi;                                       // |s|^2
+        d = fma(fma(-d, d, m2), 0.5 * mi, d);
+        const double rd = fma(mi, fma(-d, mi, 1.0), mi);          // 1/|s|^2
+        const double tq = 0.5 * (d + fabs(s2.re));
+        const double ri = rsqrt_onscale(tq);
+        double r = tq * ri;
+        r = fma(fma(-r, r, tq), 0.5 * ri, r);                     // sqrt((|s^2| + |Re s^2|)/2)
+        const double q = fabs(s2.im) * (0.5 * ri);                // |Im s^2| / (2 r)
+        // Re s^2 >= 0: s = (r, +-q); Re s^2 < 0: s = (q, +-r); sign of Im s = sign of Im s^2, on the branch cut
+        // (Im s^2 = 0, real arguments of J / Y / H beyond the turning point) the sign of Im w: s ~ w for large |w|
+        const bool pos = s2.re >= 0.0;
+        const bool neg_im = (s2.im < 0.0) || (s2.im == 0.0 && w.im < 0.0);
+        const double sre = pos ? r : q, sim = pos ? q : r;
+        s = cplx(sre, neg_im ? -sim : sim);
+        rs = cplx(s.re * rd, -s.im * rd);
+        // 1/sqrt(s) = conj(sqrt s)/|s|,  sqrt s = (g, Im s/(2g)),  g = sqrt((|s| + Re s)/2),  |s| = sqrt(d)
+        const double di = rsqrt_onscale(d);                       // 1/|s|
+        double as = d * di;
+        as = fma(fma(-as, as, d), 0.5 * di, as);                  // |s|
+        const double tg = 0.5 * (as + s.re);
+        const double gi = rsqrt_onscale(tg);
+        double g = tg * gi;
+        g = fma(fma(-g, g, tg), 0.5 * gi, g);
+        phi = cplx(g * di, -(s.im * (0.5 * gi)) * di);
+#else
+        const real d = cabs_(s2);  // |s|^2
+        s = csqrt_mod(s2, d);
+        if (s.re == real(0.0) && w.im < real(0.0)) s.im = -rabs(s.im);  // branch cut: see the device form
+        const real rd = real(1.0) / d;
+        rs = cplx(s.re * rd, -s.im * rd);
+        phi = csqrt_(rs);
+#endif
     }
-    // Inside the calibrated region the 14th term is below 3e-14 (an asymptotic series: the sum is then as accurate
-    // as its last term); anything larger means the point does not belong here
-    if (!(last < real(1.0e-13))) return -2;
-    // exponent  E = v eta - w = v^2 / (s + w) - v ln((v + s) / w):  s - w without cancellation (Re s, Re w >= 0)
-    const real raz = rcp_fast(az);
-    const cplx rw = cplx(w.re * raz, -w.im * raz) * raz;
+    const cplx y = rs * rs;
+#include "spb_debye_series.inc"
+    const cplx sp = ev + od, sm = ev - od;
+    // exponent  E = v eta - w = v^2 / (s + w) - v ln((v + s) / w):  s - w without cancellation (Re s, Re w >= 0);
+    // ln|(v + s)/w| from the squared moduli, arg from (v + s) conj(w)
     const cplx den = s + w;
     const real rdd = rcp_fast(den.re * den.re + den.im * den.im);
     const cplx e1(v2 * den.re * rdd, -v2 * den.im * rdd);
-    const cplx zn = (s + fnu) * rw;
-    const cplx lg = clog_(zn);
-    const cplx e(e1.re - fnu * lg.re, e1.im - fnu * lg.im);
+    const cplx sv(s.re + fnu, s.im);
+    const real w2 = w.re * w.re + w.im * w.im;
+    const real lnm = real(0.5) * log_((sv.re * sv.re + sv.im * sv.im) * rcp_fast(w2));
+    const real ang = atan2_onscale(sv.im * w.re - sv.re * w.im, sv.re * w.re + sv.im * w.im);
+    const cplx e(e1.re - fnu * lnm, e1.im - fnu * ang);
     // exponentials: kode 2 carries e^{E.re} (I) and e^{-E.re} (K); kode 1 e^{+-(E.re + Re w)}
     const real tt = (kode == 2) ? e.re : e.re + w.re;
     if (!(rabs(tt) < alim)) return -9;  // leaves the middle scaling level: general path
@@ -113,8 +182,6 @@ SPB_FN int debye_ik(cplx w, real fnu, int kode, bool need_i, bool need_k, cplx &
     sincos_(w.im, sw, cw);
     // e^{i (E.im + Im w)}: phase of the dominant term of I in both scalings
     const cplx ph_i(ce * cw - se * sw, se * cw + ce * sw);
-    // 1/sqrt(s) = sqrt(1/s)
-    const cplx phi = csqrt_(rs);
     if (need_k) {
         // e^{-i E.im} (kode 2: e^{w} K) or e^{-i (E.im + Im w)} (kode 1)
         const cplx ph_k = (kode == 2) ? cplx(ce, -se) : conj(ph_i);

@@ -253,5 +253,115 @@ def main():
                                   table("GAMA", gama), table("ALFA", alfa), table("BETA", beta)])
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--debye" not in sys.argv:
     main()
+
+
+# ---------------------------------------------------------------- Debye-direct region (spb_debye.h)
+def gen_debye_series(kmax=14):
+    """Rearrangement of  sum_{k<=kmax} P_k(t^2) / s^k,  t^2 = v^2 / s^2  (u_k(t) = t^k P_k(t^2)),  by powers of 1/s:
+         sum_m Q_m(v^2) / s^m,   Q_m(v^2) = sum_j c_{m-2j, j} (v^2)^j   (j <= k = m - 2j <= kmax)
+    with REAL polynomials Q_m in the real variable v^2.  Writes the coefficient table DQ (Horner order per m, highest
+    power of v^2 first) and the straight-line evaluation code (even and odd m as two Horner chains in y = 1/s^2)."""
+    _, polys = gen_uk(kmax)  # polys[k] = coefficients of P_k, highest power of t^2 first (degree k)
+    c = {}
+    for k, row in enumerate(polys):
+        for pos, val in enumerate(row):
+            j = k - pos
+            if val != 0:
+                c[(k, j)] = val
+    table_vals, lines = [], []
+    mmax = 3 * kmax
+    present = {}
+    for m in range(1, mmax + 1):
+        js = sorted([j for j in range(0, m // 3 + 1) if (m - 2 * j, j) in c and m - 2 * j <= kmax], reverse=True)
+        if not js:
+            continue
+        jmin, jmax = js[-1], js[0]
+        expr = None
+        for j in range(jmax, jmin - 1, -1):
+            idx = len(table_vals)
+            table_vals.append(c.get((m - 2 * j, j), Fraction(0)))
+            expr = f"real(DQ[{idx}])" if expr is None else f"fma_({expr}, v2, real(DQ[{idx}]))"
+        if jmin > 0:
+            expr = f"({expr}) * p{jmin}"
+        present[m] = expr
+    lines.append("// GENERATED by tools/gen_tables.py (gen_debye_series); do not edit.")
+    lines.append("// in: real v2 (= v^2), cplx rs (= 1/s), cplx y (= 1/s^2); out: cplx ev (even m, incl. the leading 1), cplx od (odd m)")
+    maxj = max(j for (_, j) in c)
+    lines.append("const real p1 = v2;")
+    for j in range(2, maxj + 1):
+        a, b = j // 2, j - j // 2
+        lines.append(f"const real p{j} = p{a} * p{b};")
+    for parity, name in ((0, "ev"), (1, "od")):
+        ms = sorted([m for m in present if m % 2 == parity], reverse=True)
+        first = True
+        for m in ms:
+            if first:
+                lines.append(f"cplx {name}({present[m]}, real(0.0));")
+                prev = m
+                first = False
+                continue
+            for _ in range((prev - m) // 2 - 1):  # an absent m in between: multiply only
+                lines.append(f"{name} = {name} * y;")
+            lines.append(f"{name} = horner_step({name}, y, {present[m]});  // m = {m}")
+            prev = m
+        if parity == 0:
+            for _ in range(prev // 2 - 1):
+                lines.append(f"{name} = {name} * y;")
+            lines.append(f"{name} = horner_step({name}, y, real(1.0));  // m = 0")
+        else:
+            for _ in range((prev - 1) // 2):
+                lines.append(f"{name} = {name} * y;")
+            lines.append(f"{name} = {name} * rs;")
+    return table_vals, lines
+
+
+def write_debye():
+    vals, lines = gen_debye_series(14)
+    with open(os.path.join(OUTDIR, "spb_tables_debye.inc"), "w") as f:
+        f.write("// spb_tables_debye.inc — GENERATED by tools/gen_tables.py (gen_debye_series); do not edit.\n"
+                "// Coefficients c_{k,j} of the Debye polynomials u_k(t) = t^k sum_j c_{k,j} t^{2j} (DLMF 10.41.10-11),\n"
+                "// regrouped by m = k + 2j (Horner order in v^2 per m).  Namespace-scope table: __constant__ on the device.\n")
+        f.write("SPB_CONST_TABLE(DQ, %d) = {\n" % len(vals))
+        for i in range(0, len(vals), 3):
+            f.write("    " + ", ".join(fmt(frac_to_mp(v)) for v in vals[i:i + 3]) + ",\n")
+        f.write("};\n")
+    with open(os.path.join(OUTDIR, "spb_debye_series.inc"), "w") as f:
+        f.write("\n".join(lines) + "\n")
+    print("debye series:", len(vals), "coefficients,", len(lines), "statements")
+
+
+def gen_atan_fit(deg=13):
+    """Near-minimax fit (Chebyshev interpolation) of (atan(sqrt(u))/sqrt(u) - 1)/u on 0 <= u <= tan(pi/8)^2."""
+    hi = mp.tan(mp.pi / 8) ** 2
+
+    def f(u):
+        if u == 0:
+            return -mp.mpf(1) / 3
+        r = mp.sqrt(u)
+        return (mp.atan(r) / r - 1) / u
+    n = deg + 1
+    nodes = [hi / 2 * (1 + mp.cos(mp.pi * (2 * i + 1) / (2 * n))) for i in range(n)]
+    A = mp.matrix(n, n)
+    b = mp.matrix(n, 1)
+    for i, x in enumerate(nodes):
+        for j in range(n):
+            A[i, j] = x ** j
+        b[i] = f(x)
+    sol = mp.lu_solve(A, b)
+    coef = [sol[j] for j in range(n)]
+    # report the fit error
+    worst = 0
+    for i in range(2001):
+        u = hi * i / 2000
+        p = sum(coef[j] * u ** j for j in range(n))
+        worst = max(worst, abs(p - f(u)) * u)  # error relative to atan(r)/r ~ 1
+    return coef[::-1], worst
+
+
+if __name__ == "__main__" and "--debye" in sys.argv:
+    write_debye()
+    co, w = gen_atan_fit(int(os.environ.get("ATAN_DEG", "13")))
+    print("ATANC (highest power first), fit error %s:" % mp.nstr(w, 3))
+    print(", ".join("%.17e" % float(c) for c in co))
