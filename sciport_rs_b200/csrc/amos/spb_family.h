@@ -68,8 +68,10 @@ struct Prep {
 SPB_HD bool uoik_is_noop(real az, real gnu, real alim, real x, int kode) {
     // scaled variants test Re(zeta2 - zeta1 - w): x <= Re zeta2 <= x + gnu, so the x terms cancel
     if (kode != 1) x = real(0.0);
-    // cheap sufficient test first (covers small orders at moderate |z| without a division or logarithm):
-    // for 2^-20 <= t = az/gnu <= 2^20, ln(1 + 2/t + t) < 15.3
+    // cheap sufficient tests first (they cover the BASELINE configs without a division or a logarithm):
+    // for 1/64 <= t = az/gnu <= 64, ln(1 + 2/t + t) <= ln(129.02) < 4.8601, so b < 9.0017 gnu + x;
+    // for 2^-20 <= t <= 2^20, ln(1 + 2/t + t) < 15.3
+    if (az >= gnu * real(0.015625) && az <= gnu * real(64.0) && gnu * real(9.0017) + x < alim) return true;
     if (az >= gnu * real(9.5367431640625e-07) && az <= gnu * real(1048576.0) &&
         gnu * real(19.5) + x < alim)
         return true;

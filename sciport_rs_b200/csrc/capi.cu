@@ -268,7 +268,8 @@ int ensure_scratch(ScratchSet &ss, long long n, cudaStream_t st) {
         return o;
     };
     size_t o_cls = take(cap), o_pi = take(cap * 4), o_pk = take(cap * 4), o_gl = take(cap * 4),
-           o_it = take(cap * 16), o_ic = take(cap), o_bc = take((size_t)NBINS * nblocks_cap * 4), o_bins = take(BINS_WORDS * 4);
+           o_it = take(cap * 16), o_ic = take(cap), o_bc = take((size_t)NBINS * nblocks_cap * 4), o_bins = take(BINS_WORDS * 4),
+           o_pi2 = take(cap * 4), o_pk2 = take(cap * 4), o_cc = take((size_t)CELL_SLOTS * NCELLS * 4);
     char *base = nullptr;
     if (cudaMalloc(&base, off) != cudaSuccess) {
         cudaGetLastError();
@@ -280,6 +281,9 @@ int ensure_scratch(ScratchSet &ss, long long n, cudaStream_t st) {
     ss.s.perm_i = (unsigned int *)(base + o_pi);
     ss.s.perm_k = (unsigned int *)(base + o_pk);
     ss.s.glist = (unsigned int *)(base + o_gl);
+    ss.s.perm_i2 = (unsigned int *)(base + o_pi2);
+    ss.s.perm_k2 = (unsigned int *)(base + o_pk2);
+    ss.s.cellcnt = (unsigned int *)(base + o_cc);
     ss.s.itemp = (double2 *)(base + o_it);
     ss.s.icode = (signed char *)(base + o_ic);
     ss.s.blockcnt = (unsigned int *)(base + o_bc);
@@ -323,6 +327,14 @@ static int fuse_mode() {
     return mode;
 }
 
+static int cellsort_mode() {
+    static const int mode = [] {
+        const char *e = getenv("SPB_CELLSORT");
+        return e ? atoi(e) : 1;
+    }();
+    return mode;
+}
+
 static bool debye_enabled() {
     static const bool on = [] {
         const char *e = getenv("SPB_DEBYE");
@@ -344,6 +356,9 @@ int enqueue_chunk(const DevJob &job_in, ScratchSet &ss, int sms, int flags, cuda
                        ? spb::FUSE_ASYI : 0;
         // Debye-direct region (every family; SPB_DEBYE=0 in the environment switches it off)
         if (debye_enabled() && !(flags & SPB_PATH_MONOLITHIC)) job.fuse |= spb::FUSE_DEBYE;
+        // second-level (|z|, order) sort inside the iterative bins: SPB_CELLSORT = 0 never, 1 (default) for
+        // per-element orders, 2 always
+        job.cellsort = (cellsort_mode() == 2 || (cellsort_mode() == 1 && job.v_stride != 0)) ? 1 : 0;
         job.pdl = (pdl_enabled() && job.v_stride == 0) ? 1 : 0;
     }
     if (flags & SPB_PATH_MONOLITHIC) {
@@ -358,6 +373,7 @@ int enqueue_chunk(const DevJob &job_in, ScratchSet &ss, int sms, int flags, cuda
     p.mark(SPB_K_SCAN_SCATTER, st);
     launch_scan_scatter(job, ss.s, st);
     launches += 3;
+    if (job.cellsort) launches += launch_cellsort(job, ss.s, sms, st);
     const bool ktype = !(job.fam == SPB_FN_J || job.fam == SPB_FN_I);  // K, H1, H2, Y and the JY pair
     static const int ipass_id[NB_I] = {SPB_K_IPASS_SERIES, SPB_K_IPASS_ASYI, SPB_K_IPASS_MLRI, SPB_K_IPASS_WRSK,
                                        SPB_K_IPASS_UNI1,   SPB_K_IPASS_UNI2, SPB_K_IPASS_DEBYE};

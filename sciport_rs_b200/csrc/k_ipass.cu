@@ -33,7 +33,7 @@ void launch_ipass(const DevJob &job, const Scratch &s, int region, int sms, cuda
             break;
         case spb::IREG_MLRI: launch_ipass_region<spb::IREG_MLRI>(job, s, sms, st); break;
         case spb::IREG_WRSK:
-            if (job.v_stride != 0)
+            if (job.v_stride != 0 && !job.cellsort)
                 launch_pdl(job.pdl != 0, k_ipass_sorted<spb::IREG_WRSK>, resident_grid(k_ipass_sorted<spb::IREG_WRSK>, 128, sms), 128, st,
                            job, s);
             else

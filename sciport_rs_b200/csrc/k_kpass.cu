@@ -39,17 +39,21 @@ __device__ __forceinline__ void kpass_point(const DevJob &job, const Scratch &s,
 
 // broadcast scalar order (v_stride = 0): the order-dependent phase factors are computed once per CTA and live in
 // shared memory, not in registers of the persistent loop
-template <int FAM, int KODE>
+// SCALAR = false: per-element orders of a cell-sorted job (perm_k2: neighbours in the list are neighbours in |z| and
+// in the order), phase factors per point
+template <int FAM, int KODE, bool SCALAR = true>
 __global__ void __launch_bounds__(128, SPB_KPASS_MINB) k_kpass(DevJob job, Scratch s) {
     pdl_enter();
     job.fam = FAM;  // compile-time family and scaling flag (dispatch_fam_kode)
     job.kode = KODE;
     __shared__ spb::OrderPhase s_ph;
-    if (threadIdx.x == 0) s_ph = spb::order_phase(__ldg(job.v));
-    __syncthreads();
+    if (SCALAR) {
+        if (threadIdx.x == 0) s_ph = spb::order_phase(__ldg(job.v));
+        __syncthreads();
+    }
     const unsigned int count = s.bins[BIN_GENERAL] - s.bins[BIN_K0];
     const unsigned int stride = gridDim.x * blockDim.x;
-    const unsigned int *perm = s.perm_k;
+    const unsigned int *perm = job.cellsort ? s.perm_k2 : s.perm_k;
     unsigned int t = blockIdx.x * blockDim.x + threadIdx.x;
     bool have1 = t < count, have2 = (t + stride) < count;
     unsigned int i1 = have1 ? __ldg(perm + t) : 0u;
@@ -80,7 +84,12 @@ __global__ void __launch_bounds__(128, SPB_KPASS_MINB) k_kpass(DevJob job, Scrat
             it1 = s.itemp[i1];  // only meaningful where the point went through the I pass
             ic1 = s.icode[i1];
         }
-        kpass_point(job, s, i, z, v, itv, icv, &s_ph);
+        if (SCALAR) {
+            kpass_point(job, s, i, z, v, itv, icv, &s_ph);
+        } else {
+            const spb::OrderPhase ph = spb::order_phase(v);
+            kpass_point(job, s, i, z, v, itv, icv, &ph);
+        }
     }
 }
 
@@ -138,7 +147,10 @@ __global__ void __launch_bounds__(128, SPB_KPASS_MINB) k_kpass_sorted(DevJob job
 template <int FAM, int KODE>
 struct KpassLaunch {
     static void run(const DevJob &job, const Scratch &s, int sms, cudaStream_t st) {
-        if (job.v_stride != 0 || job.n < 2)
+        if (job.cellsort && job.v_stride != 0)
+            launch_pdl(job.pdl != 0, k_kpass<FAM, KODE, false>, resident_grid(k_kpass<FAM, KODE, false>, 128, sms), 128, st,
+                       job, s);
+        else if (job.v_stride != 0 || job.n < 2)
             launch_pdl(job.pdl != 0, k_kpass_sorted<FAM, KODE>, resident_grid(k_kpass_sorted<FAM, KODE>, 128, sms), 128, st, job, s);
         else
             launch_pdl(job.pdl != 0, k_kpass<FAM, KODE>, resident_grid(k_kpass<FAM, KODE>, 128, sms), 128, st, job, s);

@@ -93,7 +93,11 @@ __global__ void __launch_bounds__(256) k_classify(DevJob job, Scratch s) {
     // issued before the first test, so the phase runs at memory speed on batches that live in the large-|z|
     // region.  A warp keeps a fast result only if all its lanes accepted that point.
     unsigned int cls4[PER_THREAD / 4];  // class bytes, 0xff = not decided yet
-    {
+#pragma unroll
+    for (int q = 0; q < PER_THREAD / 4; ++q) cls4[q] = 0xffffffffu;
+    // (per-element orders: a warp of 32 unrelated (order, argument) pairs practically never sits in the large-|z|
+    // region as a whole, so the fast accept would only add its cost to every point)
+    if (job.v_stride == 0) {
         double2 zk[PER_THREAD];
         double vk[PER_THREAD];
 #pragma unroll
@@ -109,12 +113,10 @@ __global__ void __launch_bounds__(256) k_classify(DevJob job, Scratch s) {
         }
 #pragma unroll
         for (int q = 0; q < PER_THREAD / 4; ++q) cls4[q] = 0;
-        const bool scalar_order = job.v_stride == 0;
-        spb::FastOrder fo = spb::fast_order(vk[0]);  // a broadcast order: its half of the test once per thread
+        const spb::FastOrder fo = spb::fast_order(vk[0]);  // a broadcast order: its half of the test once per thread
 #pragma unroll
         for (int k = 0; k < PER_THREAD; ++k) {
             int ireg, kreg;
-            if (!scalar_order) fo = spb::fast_order(vk[k]);
             const bool ok = spb::fast_classify(job.fam, cplx(zk[k].x, zk[k].y), fo, job.kode, job.fuse, ireg, kreg);
             unsigned int c = 0xffu;
             if (__all_sync(0xffffffffu, ok)) c = spb::class_of(ireg, kreg);
@@ -227,6 +229,9 @@ __global__ void __launch_bounds__(1024) k_scan(Scratch s) {
 
 __global__ void __launch_bounds__(256) k_scatter(DevJob job, Scratch s) {
     pdl_enter();
+    // counters of the second-level sort of this chunk (k_cell_hist runs after this kernel, in stream order)
+    if (blockIdx.x == 0)
+        for (int c = threadIdx.x; c < CELL_SLOTS * NCELLS; c += 256) s.cellcnt[c] = 0;
     __shared__ unsigned long long warp_tot[8][NWORDS];
     __shared__ unsigned int tile_base[NBINS], lstart[NBINS], seg_total[3];
     __shared__ unsigned int stage[3][TILE];
@@ -351,6 +356,137 @@ __global__ void __launch_bounds__(256) k_scatter(DevJob job, Scratch s) {
         s.perm_k[tile_base[b] + (j - lstart[b])] = stage[1][j];
     }
     for (unsigned int j = threadIdx.x; j < seg_total[2]; j += 256) s.glist[tile_base[BIN_GENERAL] + j] = stage[2][j];
+}
+
+// ---- second-level sort inside the iterative bins: by (|z|, order) cell ------------------------------------------
+// The region routines of these bins are loops whose trip counts are smooth functions of |z| and the order (series
+// length, Miller start index, forward recurrence over the order, ratio walk).  Inside one region bin the stable
+// compaction leaves the points in index order, i.e. in random (|z|, order) order for unrelated inputs: the lanes of
+// a warp then run loops of very different lengths (measured: 20-21 of 32 lanes active in the Miller / Wronskian /
+// K kernels of config 3 even with a per-CTA batch sort of 512 points).  A counting sort of each bin segment by a
+// 9-bit cell key -- 32 levels of |z|, four per octave, times 16 levels of the order -- makes 32 consecutive
+// entries near neighbours in both variables, over the whole chunk instead of a 512-point batch:
+//   k_cell_hist    histogram of the cell keys per bin (shared-memory histograms, one global add per cell and CTA)
+//   k_cell_scan    exclusive scan of the 512 cell counters of every bin -> cell cursors
+//   k_cell_scatter batches of 1024 entries: shared-memory counts, ONE global atomic per (batch, cell) reserves the
+//                  range, entries are written to perm_i2 / perm_k2 (order inside a cell is arbitrary: results are
+//                  per point, only the memory order depends on it)
+// Bin boundaries do not move, so the region kernels only switch the index array they walk.
+__device__ __forceinline__ unsigned int cell_of(cplx z, double v) {
+    const double m2 = z.re * z.re + z.im * z.im;
+    const int hi = __double2hiint(m2);
+    int q = 2 * ((hi >> 20) - 1023) + ((hi >> 19) & 1);  // two levels per octave of |z|^2 = four per octave of |z|
+    q = q < 0 ? 0 : (q > 31 ? 31 : q);
+    int b = (int)(fabs(v) * 0.25);
+    b = b > 15 ? 15 : b;
+    return (unsigned int)(q | (b << 5));
+}
+
+// slot -> (bin, index array): I bins 0 (series), 2 (mlri), 3 (wrsk), 4, 5 (uniform forms), then the three K bins
+__device__ __forceinline__ void cell_slot(const Scratch &s, int slot, const unsigned int *&src, unsigned int *&dst,
+                                          unsigned int &count) {
+    const int bin = slot == 0 ? 0 : (slot < 5 ? slot + 1 : BIN_K0 + (slot - 5));
+    const bool kbin = slot >= 5;
+    const unsigned int start = s.bins[bin] - (kbin ? s.bins[BIN_K0] : s.bins[0]);
+    count = s.bins[bin + 1] - s.bins[bin];
+    src = (kbin ? s.perm_k : s.perm_i) + start;
+    dst = (kbin ? s.perm_k2 : s.perm_i2) + start;
+}
+
+__global__ void __launch_bounds__(256) k_cell_hist(DevJob job, Scratch s) {
+    pdl_enter();
+    __shared__ unsigned int hist[NCELLS];
+    const int slot = blockIdx.y;
+    const unsigned int *src;
+    unsigned int *dst, count;
+    cell_slot(s, slot, src, dst, count);
+    if ((unsigned long long)blockIdx.x * 256ull >= count) return;
+    for (int c = threadIdx.x; c < NCELLS; c += 256) hist[c] = 0;
+    __syncthreads();
+    for (unsigned int t = blockIdx.x * 256 + threadIdx.x; t < count; t += gridDim.x * 256) {
+        const unsigned int i = __ldg(src + t);
+        cplx z;
+        double v;
+        load_point(job, i, z, v);
+        atomicAdd(&hist[cell_of(z, v)], 1u);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < NCELLS; c += 256)
+        if (hist[c]) atomicAdd(&s.cellcnt[slot * NCELLS + c], hist[c]);
+}
+
+__global__ void __launch_bounds__(NCELLS) k_cell_scan(Scratch s) {
+    pdl_enter();
+    __shared__ unsigned int wsum[NCELLS / 32];
+    const int slot = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned int *cnt = s.cellcnt + slot * NCELLS;
+    const unsigned int x = cnt[threadIdx.x];
+    unsigned int incl = x;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned int y = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += y;
+    }
+    if (lane == 31) wsum[wid] = incl;
+    __syncthreads();
+    unsigned int off = 0;
+    for (int w = 0; w < wid; ++w) off += wsum[w];
+    cnt[threadIdx.x] = off + incl - x;  // exclusive: where the cell starts inside its bin segment
+}
+
+__global__ void __launch_bounds__(256) k_cell_scatter(DevJob job, Scratch s) {
+    pdl_enter();
+    constexpr int R = 4;  // entries per thread and batch
+    __shared__ unsigned int cnt[NCELLS], base[NCELLS];
+    const int slot = blockIdx.y;
+    const unsigned int *src;
+    unsigned int *dst, count;
+    cell_slot(s, slot, src, dst, count);
+#pragma unroll 1
+    for (unsigned int t0 = blockIdx.x * (256 * R); t0 < count; t0 += gridDim.x * (256 * R)) {
+        for (int c = threadIdx.x; c < NCELLS; c += 256) cnt[c] = 0;
+        __syncthreads();
+        unsigned int idx[R], key[R], rank[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const unsigned int t = t0 + threadIdx.x + 256 * r;
+            key[r] = 0xffffffffu;
+            if (t < count) {
+                idx[r] = __ldg(src + t);
+                cplx z;
+                double v;
+                load_point(job, idx[r], z, v);
+                key[r] = cell_of(z, v);
+                rank[r] = atomicAdd(&cnt[key[r]], 1u);
+            }
+        }
+        __syncthreads();
+        for (int c = threadIdx.x; c < NCELLS; c += 256)
+            if (cnt[c]) base[c] = atomicAdd(&s.cellcnt[slot * NCELLS + c], cnt[c]);
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            if (key[r] != 0xffffffffu) dst[base[key[r]] + rank[r]] = idx[r];
+        __syncthreads();
+    }
+}
+
+int launch_cellsort(const DevJob &job, const Scratch &s, int sms, cudaStream_t st) {
+    // (the cell counters were zeroed by k_scatter of this chunk)
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = job.pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cfg.stream = st;
+    cfg.dynamicSmemBytes = 0;
+    cfg.blockDim = dim3(256, 1, 1);
+    cfg.gridDim = dim3((unsigned int)(sms * 2), CELL_SLOTS, 1);
+    cudaLaunchKernelEx(&cfg, k_cell_hist, job, s);
+    launch_pdl(job.pdl != 0, k_cell_scan, CELL_SLOTS, NCELLS, st, s);
+    cudaLaunchKernelEx(&cfg, k_cell_scatter, job, s);
+    return 3;
 }
 
 template <int FAM, int KODE>

@@ -14,6 +14,8 @@ struct DevJob {
     int fuse;  // spb::FUSE_ASYI (1): points needing I and K with I in the large-|w| region are evaluated by the fused
                // region kernel; spb::FUSE_DEBYE (2): the Debye-direct region (spb_debye.h) is carved out
     int pdl;   // 1: the kernels of this chunk are launched as programmatic dependents of each other (launch_pdl)
+    int cellsort;  // 1: inside the iterative region bins the point indices are sorted once more, by (|z|, order) cell
+                   // (k_pipeline.cu): the bins' kernels then read perm_i2 / perm_k2
     int reflect;  // 1: orders v < 0 by the reflection formulae (K folds v -> |v| at load; the others on the general path)
     const double *v;
     long long v_stride;  // 0 = broadcast
@@ -38,6 +40,9 @@ struct Scratch {
     unsigned char *cls;     // [n] class byte: bits 0-2 I bin (7 none), 3-4 K bin (3 none), 5 general
     unsigned int *perm_i;   // [n] point indices sorted by I bin (stable)
     unsigned int *perm_k;   // [n] point indices sorted by K bin (stable)
+    unsigned int *perm_i2;  // [n] perm_i with the segments of the iterative bins re-sorted by (|z|, order) cell
+    unsigned int *perm_k2;  // [n] perm_k re-sorted likewise
+    unsigned int *cellcnt;  // [CELL_SLOTS][NCELLS] cell histogram of a chunk, then (k_cell_scan) the cell cursors
     unsigned int *glist;    // [n] general-path list
     double2 *itemp;         // [n] I(w) for families that also need K
     signed char *icode;     // [n] nz of the I pass (<0: handed to the general path)
@@ -58,6 +63,10 @@ constexpr int FIELD_BITS = 12;
 constexpr int FIELDS_PER_WORD = 5;
 constexpr int NWORDS = (NBINS + FIELDS_PER_WORD - 1) / FIELDS_PER_WORD;
 constexpr int TILE = 2048;               // points per classification tile
+// second-level sort inside a bin: 512 cells = 32 levels of |z| (four per octave, 1 <= |z| < 221) x 16 levels of the
+// order (steps of 4); slots = the bins that are sorted this way (I: series, mlri, wrsk, uni1, uni2; K: all three)
+constexpr int NCELLS = 512;
+constexpr int CELL_SLOTS = 8;
 // slots of Scratch::bins beyond the NBINS+1 start offsets
 constexpr int GLIST_LEN_SLOT = 24;  // current length of the general list (grows when a pass hands a point over)
 constexpr int SLOT_DONE = 25;       // CTAs of k_scan that have finished
@@ -134,6 +143,7 @@ inline void dispatch_fam_kode(int fam, int kode, A &&...a) {
 // kernels.cu
 void launch_classify(const DevJob &job, const Scratch &s, cudaStream_t st);
 void launch_scan_scatter(const DevJob &job, const Scratch &s, cudaStream_t st);
+int launch_cellsort(const DevJob &job, const Scratch &s, int sms, cudaStream_t st);  // returns the launches made
 void launch_ipass(const DevJob &job, const Scratch &s, int region, int sms, cudaStream_t st);
 void launch_fused(const DevJob &job, const Scratch &s, int sms, cudaStream_t st);  // job.fuse: I + K, large-|w| region
 void launch_debye(const DevJob &job, const Scratch &s, int sms, cudaStream_t st);  // Debye-direct region (k_debye.cu)

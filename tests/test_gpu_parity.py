@@ -257,10 +257,12 @@ def test_jy_pair_matches_separate_calls(special, cfg):
         ja, ya, aa, ba = to_np(j), to_np(y), to_np(a), to_np(b)
         scale = np.maximum(np.abs(aa), np.abs(ba))
         ok = (to_np(ia) == 0) & (to_np(ib) == 0) & np.isfinite(scale)
-        # a point may be binned in one family and general in the other (the pair is classified like Y); outside the
-        # BASELINE boxes that difference of route shows the algorithm's own conditioning, eps max(|z|, v)
+        # a point may take different routes in the two calls (the pair is classified like Y: binned in one family and
+        # general in the other, or the Debye-direct region in one and the Miller / Wronskian route in the other):
+        # both results are within the parity tolerance of the truth, so they agree to that tolerance, not to rounding;
+        # outside the BASELINE boxes the difference of route shows the algorithm's own conditioning, eps max(|z|, v)
         cond = 16.0 if cfg == "wide" else 0.0
-        tolj = np.maximum(2e-14, so.tolerance(aa, z, v, conditioning=cond)) if cond else np.full(z.shape, 2e-14)
+        tolj = so.tolerance(aa, z, v, conditioning=cond) if cfg in ("wide", "cfg3") else np.full(z.shape, 2e-14)
         assert np.all(so.mismatch(ja, aa, scale)[ok] <= tolj[ok])
         assert np.all(so.mismatch(ya, ba, scale)[ok] <= so.tolerance(ba, z, v, conditioning=cond)[ok])
     # host-pointer path of the pair
