@@ -5,7 +5,10 @@ Headline workload = BASELINE config[2], the configuration the metric's target is
 batches of >= 256M points at >= 60 % FP64 peak", "exponentially-scaled iv/kv with per-element order v in [0,50],
 256M points, sharded over 1/2/4/8 B200"): ONE batch of 2^28 points of the index-addressable cfg3 stream (SURVEY.md
 §8d: v = 50 u0, z = 200 u1 e^{i pi (2 u2 - 1)}), evaluated as ive(v, z) and kve(v, z) (KODE = 2).  One *step* = both
-functions over the whole batch = 2 * 2^28 evals (one eval = one complex output).  With N GPUs the batch is sliced
+functions over the whole batch = 2 * 2^28 evals (one eval = one complex output), computed by the pair entry point
+spb_bessel_ik (special.ive_kve): one classification, I and K at the shared right-half-plane point, both outputs from
+one series where a single-evaluation region applies.  `separate_calls` reports the same step as two single calls
+(spb_bessel(I) then spb_bessel(K)).  With N GPUs the batch is sliced
 contiguously, rank r owns [r n / N, (r + 1) n / N) (strong scaling; no element is shared, so there is no collective
 on the data path: torch.distributed only carries the barrier and the max-over-ranks of the device time).
 
@@ -506,11 +509,13 @@ def main():
 
     def step():
         # device-pointer calls only enqueue; nothing here synchronises with the GPU.  No per-element code arrays: the
-        # first failing element of each call is tracked in one device word (Result<Array, i32> semantics)
+        # first failing element of each output is tracked in one device word (Result<Array, i32> semantics)
+        special.bessel_ik(v, z, scaled=True, outs=[out_i, out_k], want_codes=False)
+        launches[0] += _lib.last_timing(want_ms=False)[1]
+
+    def step_separate():
         special.bessel("I", v, z, scaled=True, out=out_i, want_codes=False)
-        launches[0] += _lib.last_timing(want_ms=False)[1]
         special.bessel("K", v, z, scaled=True, out=out_k, want_codes=False)
-        launches[0] += _lib.last_timing(want_ms=False)[1]
 
     for _ in range(warmup):
         step()
@@ -547,10 +552,17 @@ def main():
     value = evals_per_step * args.steps / (ms * 1e-3)
     launches_total = int(sum_over_ranks(launches_timed, dev))
 
+    # the same step as two single calls (device-resident), for comparison
+    sep_ms = timed(torch, step_separate, 3, warm=1)
+    if world > 1:
+        sep_ms = max_over_ranks(sep_ms, dev)
+    separate_calls = {"value": evals_per_step / (sep_ms * 1e-3), "unit": UNIT, "ms_per_step": sep_ms,
+                      "note": "spb_bessel(I, kode 2) then spb_bessel(K, kode 2) over the same slices, best of 3"}
+    step()  # (the accuracy leg below reads the pair's outputs)
+
     # per-kernel times of one profiled step (events between launches; the records of all chunks summed per kernel)
-    prof = aggregate_profile(special.profile_step(lambda: (
-        special.bessel("I", v, z, scaled=True, out=out_i, want_codes=False, profile=True),
-        special.bessel("K", v, z, scaled=True, out=out_k, want_codes=False, profile=True))))
+    prof = aggregate_profile(special.profile_step(
+        lambda: special.bessel_ik(v, z, scaled=True, outs=[out_i, out_k], want_codes=False, profile=True)))
 
     # accuracy of this very run against live scipy on a strided 2^16 sample of this rank's slice
     accuracy = None
@@ -559,8 +571,7 @@ def main():
             n_acc = 1 << 16
             idx = torch.arange(0, n, max(n // n_acc, 1), device=dev)[:n_acc]
             vs, zs = v[idx].cpu().numpy(), z[idx].cpu().numpy()
-            gi, ei, _ = special.bessel("I", v[idx].contiguous(), z[idx].contiguous(), scaled=True)
-            gk, ek, _ = special.bessel("K", v[idx].contiguous(), z[idx].contiguous(), scaled=True)
+            (gi, ei, _), (gk, ek, _) = special.bessel_ik(v[idx].contiguous(), z[idx].contiguous(), scaled=True)
             same = bool(torch.equal(gi, out_i[idx]) and torch.equal(gk, out_k[idx]))
             accuracy = {"ive": scipy_accuracy("I", 2, vs, zs, out_i[idx].cpu().numpy(), ei.cpu().numpy()),
                         "kve": scipy_accuracy("K", 2, vs, zs, out_k[idx].cpu().numpy(), ek.cpu().numpy()),
@@ -589,11 +600,10 @@ def main():
         # first Err in index order is raised afterwards.  Among 2^28 cfg3 points a handful overflow for real
         # (K_v(z) e^z at |z| ~ 1e-6 with v ~ 49), so the Err is part of the workload: caught and reported here.
         sl = slice(0, m)
-        for name, f, o in (("ive", special.ive, oin), ("kve", special.kve_array, okn)):
-            try:
-                f(vn[sl], zn[sl], out=o[sl], devices=devices)
-            except special.SpecialError as err:
-                e2e_errs[name] = {"first_err_index": int(err.index), "ierr": int(err.code)}
+        try:
+            special.ive_kve(vn[sl], zn[sl], outs=[oin[sl], okn[sl]], devices=devices)
+        except special.SpecialError as err:
+            e2e_errs["ive_kve"] = {"first_err_index": int(err.index), "ierr": int(err.code)}
 
     e2e_step(m=min(n, 1 << 23))  # warm the staging buffers
     torch.cuda.synchronize()
@@ -605,15 +615,15 @@ def main():
     dt = time.perf_counter() - t0
     my_e2e = dt
     dt = max_over_ranks(dt, dev)
-    h2d = 2 * (vn.nbytes + zn.nbytes)
+    h2d = vn.nbytes + zn.nbytes
     d2h = oin.nbytes + okn.nbytes + 2 * 16
     e2e = {"value": evals_per_step * args.e2e_steps / dt, "unit": UNIT,
            "h2d_bytes_per_step": int(sum_over_ranks(h2d, dev)), "d2h_bytes_per_step": int(sum_over_ranks(d2h, dev)),
            "steps": args.e2e_steps, "ms_per_step": 1e3 * dt / args.e2e_steps, "first_errors_rank0": e2e_errs,
            "pcie_gbs_achieved": (int(sum_over_ranks(h2d + d2h, dev)) * args.e2e_steps / dt) / 1e9,
-           "note": "special.ive + special.kve_array on pinned host buffers through spb_bessel: H2D of v and z (per "
-                   "call), kernels, D2H of the results and of the 16-byte first-error words inside the timed region; "
-                   "two streams per device, chunks of 2^22 points, copies overlapped with compute"}
+           "note": "special.ive_kve on pinned host buffers through spb_bessel_ik: H2D of v and z, kernels, D2H of both "
+                   "results and of the 16-byte first-error words inside the timed region; two streams per device, "
+                   "chunks of 2^22 points, copies overlapped with compute"}
     pcie = pcie_probe(torch, dev, world)
     pcie_sum = [sum_over_ranks(x, dev) for x in pcie]
     per_rank = {"rank": rank, "gpu": local_rank, "topology": topo, "device_ms_per_step": my_ms / args.steps,
@@ -646,8 +656,8 @@ def main():
                 dt0 = time.perf_counter() - t0
                 in_process = {"n_devices": world, "points": m, "evals_per_s": 2 * m / dt1,
                               "evals_per_s_one_device": 2 * m / dt0, "speedup": dt0 / dt1,
-                              "note": "special.ive + kve_array with devices=[0..N-1] from rank 0 alone (the other "
-                                      "ranks idle at a barrier): spb_bessel slices the batch contiguously across "
+                              "note": "special.ive_kve with devices=[0..N-1] from rank 0 alone (the other "
+                                      "ranks idle at a barrier): spb_bessel_ik slices the batch contiguously across "
                                       "the devices, one host thread and two streams per device"}
             except Exception as e:
                 in_process = {"error": repr(e)}
@@ -664,17 +674,18 @@ def main():
     peaks = load_json("MEASURED_PEAKS.json")
     hbm_peak = peaks.get("hbm_gbs") or 6547.8
     # whole step by tallied algorithmic flops
-    f_i = flops.get("cfg3:I/per_eval", {}).get("flops_per_point")
-    f_k = flops.get("cfg3:K/per_eval", {}).get("flops_per_point")
+    # (the pair's own tally per POINT: both outputs from one classification / one series where that applies)
+    f_ik = flops.get("cfg3:IK/per_eval", {}).get("flops_per_point")
     step_frac = None
-    if f_i and f_k:
-        step_frac = (f_i + f_k) * n_total * args.steps / (ms * 1e-3) / 1e12 / (fp64_peak * world)
+    if f_ik:
+        step_frac = f_ik * n_total * args.steps / (ms * 1e-3) / 1e12 / (fp64_peak * world)
     # dominant kernel = the one with the largest share of the profiled step (rank 0's slice)
     roofline = None
     if prof:
         top = prof[0]
         fpe = flops.get("cfg3:" + top["name"], {}).get("flops_per_point")
         pts = top["points"]
+        out_bytes = 32.0  # the pair stores two results per point
         per_launch_ms = top["ms"] / max(top["launches"], 1)
         achieved = (fpe * pts / (top["ms"] * 1e-3) / 1e12) if (fpe and pts and top["ms"] > 0) else None
         traffic = load_json("profiles", "r2_traffic.json").get("kernels", {}).get(top["name"])
@@ -684,7 +695,7 @@ def main():
             "traffic": traffic,
             "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel from the committed "
                             "ncu --set full capture (profiles/r2_traffic.json), null if not captured",
-            "algorithmic_bytes_per_launch": BYTES_PER_EVAL * pts / max(top["launches"], 1),
+            "algorithmic_bytes_per_launch": (24.0 + out_bytes) * pts / max(top["launches"], 1),
             "peak_source": "spb_fp64_peak: DFMA microbenchmark of this library, 8 independent chains per thread, all "
                            "SMs, sustained 2 s on this GPU right before the timed region (MEASURED_PEAKS.json has no "
                            "FP64 figure); clocks while it ran: " + json.dumps(peak_clocks),
@@ -692,8 +703,8 @@ def main():
             "launch_ms": per_launch_ms, "launches_per_step": top["launches"],
             "share_of_step": top["ms"] / max(sum(r["ms"] for r in prof), 1e-9),
             "whole_step_frac": step_frac,
-            "whole_step_flops_per_point": (f_i + f_k) if (f_i and f_k) else None,
-            "hbm_view": {"achieved_gbs": BYTES_PER_EVAL * evals_per_step * args.steps / (ms * 1e-3) / 1e9,
+            "whole_step_flops_per_point": f_ik,
+            "hbm_view": {"achieved_gbs": 56.0 * n_total * args.steps / (ms * 1e-3) / 1e9,
                          "peak_gbs": hbm_peak * world},
             "kernels": [dict(r, frac=(flops.get("cfg3:" + r["name"], {}).get("flops_per_point", 0) * r["points"] /
                                       (r["ms"] * 1e-3) / 1e12 / fp64_peak) if r["ms"] > 0 else None) for r in prof],
@@ -726,12 +737,12 @@ def main():
                    "points_per_gpu": n_total // world,
                    "l2": "inputs+outputs per step 56 B/point x 2^28/N points >> 126 MB L2 (no flush needed)",
                    "timing": "CUDA events on the launching stream, max over ranks",
-                   "path": "binned pipeline, chunks of 2^24 points, spb_bessel(I, kode 2) then spb_bessel(K, kode 2)"},
+                   "path": "binned pipeline, chunks of 2^24 points, spb_bessel_ik (I and K, kode 2, one pass)"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches_total,
         "kernel_ms_per_step": sum(r["ms"] for r in prof) if prof else None,
         "host_enqueue_ms_per_step": host_enqueue_ms, "fp64_peak_tflops": fp64_peak, "fp64_peak_clocks": peak_clocks,
         "roofline": roofline, "accuracy": accuracy, "cpu_baseline": cpu_baseline, "ranks": gathered,
-        "in_process": in_process, "configs": configs,
+        "separate_calls": separate_calls, "in_process": in_process, "configs": configs,
     }
     print(json.dumps(line))
     if world > 1:

@@ -42,8 +42,10 @@ enum spb_fn {
     SPB_FN_K = 3,  /* K_v(z)   — replaces bessel_k, kv.rs:19  */
     SPB_FN_H1 = 4, /* H^(1)_v(z)                              */
     SPB_FN_H2 = 5, /* H^(2)_v(z)                              */
-    SPB_FN_JY = 6  /* J_v and Y_v together (spb_bessel_jy only): both need I_v at the same rotated point,
+    SPB_FN_JY = 6, /* J_v and Y_v together (spb_bessel_jy only): both need I_v at the same rotated point,
                       so the pair costs one I pass + one K pass instead of two + one */
+    SPB_FN_IK = 7  /* I_v and K_v together (spb_bessel_ik only): K in the left half plane is continued with I
+                      at the same point, and the large-|z| / Debye-direct regions give both from one series */
 };
 
 /* kode: 1 = unscaled (kv), 2 = exponentially scaled (kve; I,J,Y: e^{-|Re z|} resp. e^{-|Im z|};
@@ -130,6 +132,12 @@ int spb_bessel(int fn, int kode, const double *v, int64_t v_stride, const spb_c1
 /* J_v(z_i) and Y_v(z_i) in one pass (n_orders = 1).  Results equal spb_bessel(SPB_FN_J) / spb_bessel(SPB_FN_Y). */
 int spb_bessel_jy(int kode, const double *v, int64_t v_stride, const spb_c128 *z, spb_c128 *out_j, spb_c128 *out_y,
                   int32_t *ierr_j, int32_t *ierr_y, int32_t *nz_j, int32_t *nz_y, int64_t n, const spb_exec *ex);
+
+/* I_v(z_i) and K_v(z_i) in one pass (kode 2: e^{-|Re z|} I and e^{z} K, the ive / kve pair of BASELINE config 3).
+ * Results equal spb_bessel(SPB_FN_I) / spb_bessel(SPB_FN_K) to the parity tolerance (a point may take a different
+ * region routine in the pair than in the single calls). */
+int spb_bessel_ik(int kode, const double *v, int64_t v_stride, const spb_c128 *z, spb_c128 *out_i, spb_c128 *out_k,
+                  int32_t *ierr_i, int32_t *ierr_k, int32_t *nz_i, int32_t *nz_k, int64_t n, const spb_exec *ex);
 
 /* same with real arguments promoted to complex, the shape of special::i0 (mod.rs:8-13: `v.into()`) */
 int spb_bessel_real(int fn, int kode, const double *v, int64_t v_stride, const double *x, spb_c128 *out,

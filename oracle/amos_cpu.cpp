@@ -130,6 +130,29 @@ int spbo_classify(int fn, int kode, int fuse, const double *v, int64_t v_stride,
     return 0;
 }
 
+// I and K together through the FAM_IK flow (out_i, out_k as re,im pairs); codes [4][n]: ierr_i, ierr_k, nz_i, nz_k
+int spbo_bessel_ik_pipeline(int kode, const double *v, int64_t v_stride, const double *z, double *out_i, double *out_k,
+                            int32_t *codes, int64_t n, int threads_and_mode) {
+    const int threads = threads_and_mode & 0xffff;
+    const int fuse = ((threads_and_mode & 0x10000) ? FUSE_ASYI : 0) | ((threads_and_mode & 0x20000) ? FUSE_DEBYE : 0);
+    parallel_for(n, threads, [=](int64_t lo, int64_t hi) {
+        for (int64_t i = lo; i < hi; ++i) {
+            cplx a, b;
+            int ea, eb, na, nb, pth;
+            pipeline_eval_ik(cplx(z[2 * i], z[2 * i + 1]), v[i * v_stride], kode, a, ea, na, b, eb, nb, pth, fuse);
+            out_i[2 * i] = a.re;
+            out_i[2 * i + 1] = a.im;
+            out_k[2 * i] = b.re;
+            out_k[2 * i + 1] = b.im;
+            codes[i] = ea;
+            codes[n + i] = eb;
+            codes[2 * n + i] = na;
+            codes[3 * n + i] = nb;
+        }
+    });
+    return 0;
+}
+
 // J and Y together through the FAM_JY flow (out_j, out_y as re,im pairs)
 int spbo_bessel_jy_pipeline(int kode, const double *v, int64_t v_stride, const double *z, double *out_j, double *out_y,
                             int32_t *codes /* [4][n]: ierr_j, ierr_y, nz_j, nz_y */, int64_t n,

@@ -91,26 +91,27 @@ int spbo_count_ops2(int fam, int kode, int fuse, const double *v, int64_t v_stri
         ops[0] += prep_ops;
         pts[0] += 1;
         int ierr, nz;
-        if (fam == FAM_JY) {
+        if (fam == FAM_JY || fam == FAM_IK) {
+            const bool ik = (fam == FAM_IK);
             // pair family: I pass charged to its region kernel, K pass + both finishes to kpass
             bool general = (p.combine == CMB_GENERAL);
             cplx iv(0.0, 0.0), kv(0.0, 0.0), jv, yv;
             int inz = 0, knz = 0, e2, n2;
             if (!general && p.ireg == IREG_DEBYE) {
                 g_ops = prep_ops;
-                if (debye_region(FAM_JY, p.w, fnu, kode, true, iv, inz, kv, knz, p.az) < 0)
+                if (debye_region(fam, p.w, fnu, kode, true, iv, inz, kv, knz, p.az) < 0)
                     general = true;
                 else
-                    finish_jy(p, zz, fnu, kode, iv, inz, kv, knz, jv, ierr, nz, yv, e2, n2);
+                    { if (ik) finish_ik(p, zz, fnu, kode, iv, inz, kv, knz, jv, ierr, nz, yv, e2, n2); else finish_jy(p, zz, fnu, kode, iv, inz, kv, knz, jv, ierr, nz, yv, e2, n2); }
                 ops[islot(IREG_DEBYE)] += g_ops;
                 pts[islot(IREG_DEBYE)] += 1;
             } else if (!general && p.kreg == KREG_FUSED) {
                 g_ops = prep_ops;
                 if (fused_ik_region(p.w, fnu, kode, iv, inz, kv, knz, p.az) < 0 ||
-                    (knz != 0 && p.combine == CMB_Y_SHARED))
+                    (knz != 0 && (p.combine == CMB_Y_SHARED || p.combine == CMB_ACON)))
                     general = true;
                 else
-                    finish_jy(p, zz, fnu, kode, iv, inz, kv, knz, jv, ierr, nz, yv, e2, n2);
+                    { if (ik) finish_ik(p, zz, fnu, kode, iv, inz, kv, knz, jv, ierr, nz, yv, e2, n2); else finish_jy(p, zz, fnu, kode, iv, inz, kv, knz, jv, ierr, nz, yv, e2, n2); }
                 ops[islot(IREG_ASYI)] += g_ops;
                 pts[islot(IREG_ASYI)] += 1;
             } else if (!general) {
@@ -123,15 +124,15 @@ int spbo_count_ops2(int fam, int kode, int fuse, const double *v, int64_t v_stri
             if (!general && p.kreg != KREG_FUSED) {
                 g_ops = prep_ops;
                 knz = kpass_region(p.w, fnu, kode, kv);
-                if (knz < 0 || (knz != 0 && p.combine == CMB_Y_SHARED)) general = true;
-                else finish_jy(p, zz, fnu, kode, iv, inz, kv, knz, jv, ierr, nz, yv, e2, n2);
+                if (knz < 0 || (knz != 0 && (p.combine == CMB_Y_SHARED || p.combine == CMB_ACON))) general = true;
+                else { if (ik) finish_ik(p, zz, fnu, kode, iv, inz, kv, knz, jv, ierr, nz, yv, e2, n2); else finish_jy(p, zz, fnu, kode, iv, inz, kv, knz, jv, ierr, nz, yv, e2, n2); }
                 ops[6] += g_ops;
                 pts[6] += 1;
             }
             if (general) {
                 g_ops = 0;
-                general_eval(FAM_J, zz, fnu, kode, ierr, nz);
-                general_eval(FAM_Y, zz, fnu, kode, ierr, nz);
+                general_eval(ik ? FAM_I : FAM_J, zz, fnu, kode, ierr, nz);
+                general_eval(ik ? FAM_K : FAM_Y, zz, fnu, kode, ierr, nz);
                 ops[7] += g_ops;
                 pts[7] += 1;
             }

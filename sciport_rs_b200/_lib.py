@@ -45,6 +45,7 @@ def _load():
     lib.spb_bessel.argtypes = [I, I, P, L, P, P, P, P, L, I, EX]
     lib.spb_bessel_real.argtypes = [I, I, P, L, P, P, P, P, L, I, EX]
     lib.spb_bessel_jy.argtypes = [I, P, L, P, P, P, P, P, P, P, L, EX]
+    lib.spb_bessel_ik.argtypes = [I, P, L, P, P, P, P, P, P, P, L, EX]
     lib.spb_airy.argtypes = [I, I, P, P, P, P, L, EX]
     for name in ("spb_gamma", "spb_lgamma", "spb_cgamma", "spb_clgamma", "spb_sinc"):
         getattr(lib, name).argtypes = [P, P, L, EX]
@@ -66,7 +67,7 @@ def _load():
 
 
 EXPORTS = [
-    "spb_bessel", "spb_bessel_jy", "spb_bessel_real", "spb_airy", "spb_gamma", "spb_lgamma", "spb_cgamma", "spb_clgamma",
+    "spb_bessel", "spb_bessel_jy", "spb_bessel_ik", "spb_bessel_real", "spb_airy", "spb_gamma", "spb_lgamma", "spb_cgamma", "spb_clgamma",
     "spb_sinc", "spb_devmath", "spb_kaiser", "spb_lanczos", "spb_window", "spb_first_error", "spb_last_first_error", "spb_synth", "spb_fp64_peak", "spb_last_timing", "spb_last_profile", "spb_device_topology", "spb_device_count",
     "spb_version", "spb_last_error",
 ]

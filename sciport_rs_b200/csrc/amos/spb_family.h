@@ -25,7 +25,9 @@
 namespace spb {
 
 // FAM_JY evaluates J and Y together: both need I_v at the same right-half-plane point, so the I pass is shared.
-enum Family { FAM_J = 0, FAM_Y = 1, FAM_I = 2, FAM_K = 3, FAM_H1 = 4, FAM_H2 = 5, FAM_JY = 6 };
+// FAM_IK evaluates I and K together: K in the left half plane is continued with I at the same right-half-plane point,
+// and the single-evaluation routines (large-|w| series, Debye-direct region) produce both from one series.
+enum Family { FAM_J = 0, FAM_Y = 1, FAM_I = 2, FAM_K = 3, FAM_H1 = 4, FAM_H2 = 5, FAM_JY = 6, FAM_IK = 7 };
 
 // how finish() combines the pass results
 enum Combine {
@@ -123,11 +125,12 @@ SPB_HD bool prepare_geometry(int fam, cplx z, Prep &p) {
         return true;
     }
     bool left;
-    if (fam == FAM_K) {
+    if (fam == FAM_K || fam == FAM_IK) {
         left = z.re < real(0.0);
         p.w = left ? -z : z;
         p.mr = (z.im < real(0.0)) ? -1 : 1;
         p.combine = left ? CMB_ACON : CMB_K_ROT;
+        if (fam == FAM_IK) left = true;  // I_v(w) is an output everywhere
     } else if (fam == FAM_H1 || fam == FAM_H2) {
         int m = (fam == FAM_H1) ? 1 : 2;
         int mm = 3 - m - m;
@@ -291,8 +294,8 @@ SPB_HD bool fast_classify(int fam, cplx z, const FastOrder &o, int kode, int fus
     // K-type families: which half plane the evaluation point lies in, |Re w| for the pre-test
     bool left;
     real x;
-    if (fam == FAM_K) {
-        left = z.re < real(0.0);
+    if (fam == FAM_K || fam == FAM_IK) {
+        left = (fam == FAM_IK) || z.re < real(0.0);
         x = rabs(z.re);
     } else if (fam == FAM_H1 || fam == FAM_H2) {
         const real fmm = (fam == FAM_H1) ? real(1.0) : real(-1.0);
@@ -603,6 +606,15 @@ SPB_FN void finish_jy(const Prep &p, cplx z, real fnu, int kode, cplx ival, int 
     yv = y_from_hankels(z, kode, h1, h2, nz1, nz2, ynz);
 }
 
+// I and K from one (I(w), K(w)) pair.  Same arithmetic as finish(FAM_I) and finish(FAM_K).
+SPB_FN void finish_ik(const Prep &p, cplx z, real fnu, int kode, cplx ival, int inz, cplx kval, int knz, cplx &iv,
+                      int &ierr_i, int &nz_i, cplx &kv, int &ierr_k, int &nz_k, const OrderPhase *oph = nullptr) {
+    Prep pi = p;
+    pi.combine = CMB_I_ROT;
+    iv = finish(FAM_I, pi, z, fnu, kode, ival, inz, cplx(0.0, 0.0), 0, ierr_i, nz_i, oph);
+    kv = finish(FAM_K, p, z, fnu, kode, ival, inz, kval, knz, ierr_k, nz_k, oph);
+}
+
 // The general per-point path (same routine on CPU checker and GPU).
 SPB_FN cplx general_eval(int fam, cplx z, real fnu, int kode, int &ierr, int &nz) {
     cplx cy[1];
@@ -872,6 +884,43 @@ SPB_FN void pipeline_eval_jy(cplx z, real fnu, int kode, cplx &jv, int &jerr, in
     }
     path = 0;
     finish_jy(p, z, fnu, kode, ival, inz, kval, knz, jv, jerr, jnz, yv, yerr, ynz);
+}
+
+// I and K together, in the order the GPU runs the FAM_IK pipeline.
+SPB_FN void pipeline_eval_ik(cplx z, real fnu, int kode, cplx &iv, int &ierr_i, int &nz_i, cplx &kv, int &ierr_k,
+                             int &nz_k, int &path, int fuse = 0) {
+    Prep p = prepare(FAM_IK, z, fnu, kode, fuse);
+    path = 1;
+    cplx ival(0.0, 0.0), kval(0.0, 0.0);
+    int inz = 0, knz = 0;
+    bool general = (p.combine == CMB_GENERAL || p.combine == CMB_FINAL);
+    if (!general) {
+        const int ireg = p.ireg, kreg = p.kreg;
+        p = prepare_pass(FAM_IK, z);
+        p.ireg = ireg;
+        p.kreg = kreg;
+        path = 2;
+        if (p.ireg == IREG_DEBYE) {
+            if (debye_region(FAM_IK, p.w, fnu, kode, true, ival, inz, kval, knz, p.az) < 0) general = true;
+        } else if (p.kreg == KREG_FUSED) {
+            if (fused_ik_region(p.w, fnu, kode, ival, inz, kval, knz, p.az) < 0) general = true;
+            if (knz != 0 && p.combine == CMB_ACON) general = true;
+        } else {
+            inz = ipass_region(p.ireg, p.w, fnu, kode, ival, p.az);
+            if (inz < 0) general = true;
+            if (!general) {
+                knz = kpass_region(p.w, fnu, kode, kval, p.az);
+                if (knz < 0 || (knz != 0 && p.combine == CMB_ACON)) general = true;
+            }
+        }
+    }
+    if (general) {
+        iv = general_eval(FAM_I, z, fnu, kode, ierr_i, nz_i);
+        kv = general_eval(FAM_K, z, fnu, kode, ierr_k, nz_k);
+        return;
+    }
+    path = 0;
+    finish_ik(p, z, fnu, kode, ival, inz, kval, knz, iv, ierr_i, nz_i, kv, ierr_k, nz_k);
 }
 
 }  // namespace spb

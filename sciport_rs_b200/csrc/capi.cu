@@ -759,12 +759,13 @@ int run_host_slice_seq(DeviceCtx *c, const BesselArgs &a, int *launches_out) {
 int bessel_impl(int fn, int kode, const double *v, int64_t v_stride, const spb_c128 *z, const double *x,
                 spb_c128 *out, int32_t *ierr, int32_t *nz, int64_t n, int n_orders, const spb_exec *ex,
                 spb_c128 *out2 = nullptr, int32_t *ierr2 = nullptr, int32_t *nz2 = nullptr) {
-    if (fn < SPB_FN_J || fn > SPB_FN_JY) return fail(SPB_E_ARG, "unknown function selector");
-    if ((fn == SPB_FN_JY) != (out2 != nullptr) && n > 0) return fail(SPB_E_ARG, "pair family needs two result buffers");
+    if (fn < SPB_FN_J || fn > SPB_FN_IK) return fail(SPB_E_ARG, "unknown function selector");
+    const bool pair = (fn == SPB_FN_JY || fn == SPB_FN_IK);
+    if (pair != (out2 != nullptr) && n > 0) return fail(SPB_E_ARG, "pair family needs two result buffers");
     if (kode != 1 && kode != 2) return fail(SPB_E_ARG, "kode must be 1 or 2");
     if (n < 0 || v_stride < 0) return fail(SPB_E_ARG, "negative n or v_stride");
     if (n_orders < 1 || n_orders > 4096) return fail(SPB_E_ARG, "n_orders must be 1..4096");
-    if (n_orders > 1 && (fn == SPB_FN_JY)) return fail(SPB_E_ARG, "the JY pair has no order-sequence form");
+    if (n_orders > 1 && pair) return fail(SPB_E_ARG, "the pair families have no order-sequence form");
     if (n > 0 && (!v || (!z && !x) || !out)) return fail(SPB_E_ARG, "null buffer");
     std::vector<int> devs;
     bool dptr;
@@ -941,6 +942,12 @@ int spb_bessel_jy(int kode, const double *v, int64_t v_stride, const spb_c128 *z
                   int32_t *ierr_j, int32_t *ierr_y, int32_t *nz_j, int32_t *nz_y, int64_t n, const spb_exec *ex) {
     if (n > 0 && !out_y) return fail(SPB_E_ARG, "null buffer");
     return bessel_impl(SPB_FN_JY, kode, v, v_stride, z, nullptr, out_j, ierr_j, nz_j, n, 1, ex, out_y, ierr_y, nz_y);
+}
+
+int spb_bessel_ik(int kode, const double *v, int64_t v_stride, const spb_c128 *z, spb_c128 *out_i, spb_c128 *out_k,
+                  int32_t *ierr_i, int32_t *ierr_k, int32_t *nz_i, int32_t *nz_k, int64_t n, const spb_exec *ex) {
+    if (n > 0 && !out_k) return fail(SPB_E_ARG, "null buffer");
+    return bessel_impl(SPB_FN_IK, kode, v, v_stride, z, nullptr, out_i, ierr_i, nz_i, n, 1, ex, out_k, ierr_k, nz_k);
 }
 
 int spb_bessel_real(int fn, int kode, const double *v, int64_t v_stride, const double *x, spb_c128 *out,

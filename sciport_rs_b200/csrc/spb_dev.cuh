@@ -51,6 +51,14 @@ __device__ __forceinline__ void finish_store(const DevJob &job, const spb::Prep 
         store_point2(job, i, yv, yerr, ynz);
         return;
     }
+    if (job.fam == spb::FAM_IK) {
+        cplx iv, kv;
+        int kerr, kz;
+        spb::finish_ik(p, z, v, job.kode, ival, inz, kval, knz, iv, ierr, nz, kv, kerr, kz, ph);
+        store_point(job, i, iv, ierr, nz);
+        store_point2(job, i, kv, kerr, kz);
+        return;
+    }
     cplx val = spb::finish(job.fam, p, z, v, job.kode, ival, inz, kval, knz, ierr, nz, ph);
     store_point(job, i, val, ierr, nz);
 }
@@ -146,8 +154,24 @@ __device__ __forceinline__ void eval_general_store(const DevJob &j, long long i,
             store_point2(j, i, b, ierr2, nz2);
             return;
         }
+        if (j.fam == spb::FAM_IK) {
+            cplx a = spb::reflect_eval(spb::FAM_I, z, v, j.kode, ierr, nz, j.sem != 0);
+            store_point(j, i, a, ierr, nz);
+            cplx b = spb::reflect_eval(spb::FAM_K, z, v, j.kode, ierr, nz, j.sem != 0);
+            store_point2(j, i, b, ierr, nz);
+            return;
+        }
         cplx val = spb::reflect_eval(j.fam, z, v, j.kode, ierr, nz, j.sem != 0);
         store_point(j, i, val, ierr, nz);
+        return;
+    }
+    if (j.fam == spb::FAM_IK) {
+        cplx a = spb::general_eval(spb::FAM_I, z, v, j.kode, ierr, nz);
+        if (j.sem) a = spb::apply_semantics(spb::FAM_I, z, v, j.kode, a, ierr, nz);
+        store_point(j, i, a, ierr, nz);
+        cplx b = spb::general_eval(spb::FAM_K, z, v, j.kode, ierr, nz);
+        if (j.sem) b = spb::apply_semantics(spb::FAM_K, z, v, j.kode, b, ierr, nz);
+        store_point2(j, i, b, ierr, nz);
         return;
     }
     if (j.fam == spb::FAM_JY) {

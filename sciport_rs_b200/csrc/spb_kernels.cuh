@@ -24,7 +24,7 @@ struct DevJob {
     double2 *out;
     int *ierr;  // nullable
     int *nz;    // nullable
-    double2 *out2;  // second result of a pair family (FAM_JY: out = J, out2 = Y)
+    double2 *out2;  // second result of a pair family (FAM_JY: out = J, out2 = Y; FAM_IK: out = I, out2 = K)
     int *ierr2;     // nullable
     int *nz2;       // nullable
     long long n;  // points in this chunk
@@ -135,6 +135,7 @@ inline void dispatch_fam_kode(int fam, int kode, A &&...a) {
         SPB_FAM_CASE(4)
         SPB_FAM_CASE(5)
         SPB_FAM_CASE(6)
+        SPB_FAM_CASE(7)
         default: break;  // families are validated at the C ABI
     }
 #undef SPB_FAM_CASE

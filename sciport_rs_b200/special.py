@@ -153,10 +153,41 @@ def bessel(fn, v, z, scaled=False, semantics="amos", path="binned", real_input=F
     return out, ierr, nz
 
 
-def bessel_jy(v, z, scaled=False, semantics="amos", profile=False, outs=None, codes=None, want_codes=True,
+def bessel_ik(v, z, scaled=False, semantics="amos", profile=False, outs=None, codes=None, want_codes=True,
               devices=None):
+    """I_v(z) and K_v(z) in one pass (spb_bessel_ik): returns ((I, ierr_i, nz_i), (K, ierr_k, nz_k)); scaled=True
+    gives the ive / kve pair.  K in the left half plane is continued with I at the same right-half-plane point and
+    the large-|z| / Debye-direct regions produce both functions from one series, so the pair costs far less than
+    the two single calls."""
+    return bessel_jy(v, z, scaled, semantics, profile, outs, codes, want_codes, devices, _entry="ik")
+
+
+def ive_kve(v, z, outs=None, devices=None):
+    """(ive(v, z), kve(v, z)) computed together (BASELINE config 3); raises on the first Err of either."""
+    (i, _, _), (k, _, _) = bessel_ik(v, z, scaled=True, outs=outs, want_codes=False, devices=devices)
+    for which in (0, 1):
+        idx, code = last_first_error(which)
+        if idx >= 0:
+            raise SpecialError(code, idx)
+    return i, k
+
+
+def iv_kv(v, z, outs=None, devices=None):
+    """(iv(v, z), kv(v, z)) computed together; raises on the first Err of either."""
+    (i, _, _), (k, _, _) = bessel_ik(v, z, scaled=False, outs=outs, want_codes=False, devices=devices)
+    for which in (0, 1):
+        idx, code = last_first_error(which)
+        if idx >= 0:
+            raise SpecialError(code, idx)
+    return i, k
+
+
+def bessel_jy(v, z, scaled=False, semantics="amos", profile=False, outs=None, codes=None, want_codes=True,
+              devices=None, _entry="jy"):
     """J_v(z) and Y_v(z) in one pass (spb_bessel_jy): returns ((J, ierr_j, nz_j), (Y, ierr_y, nz_y)).
     Both functions need I_v at the same rotated point, so the pair shares classification and the I pass."""
+    entry = lib.spb_bessel_jy if _entry == "jy" else lib.spb_bessel_ik
+    tag = "JY" if _entry == "jy" else "IK"
     kode = 2 if scaled else 1
     flags = (SEM_SCIPY if semantics == "scipy" else SEM_AMOS) | (PROFILE if profile else 0)
     if _is_torch(z):
@@ -180,11 +211,11 @@ def bessel_jy(v, z, scaled=False, semantics="amos", profile=False, outs=None, co
         cp = [c.data_ptr() if c is not None else None for c in codes]
         with torch.cuda.device(zc.device):
             ex = make_exec(device_ptrs=True, stream=_stream_for(zc), flags=flags, devices=[zc.device.index])
-            check(lib.spb_bessel_jy(kode, vt.data_ptr(), stride, zc.data_ptr(), outs[0].data_ptr(), outs[1].data_ptr(),
-                                    cp[0], cp[1], cp[2], cp[3], n, ctypes.byref(ex)))
+            check(entry(kode, vt.data_ptr(), stride, zc.data_ptr(), outs[0].data_ptr(), outs[1].data_ptr(),
+                        cp[0], cp[1], cp[2], cp[3], n, ctypes.byref(ex)))
         if profile and _PROFILE_LOG is not None:
             for r in _lib.last_profile():
-                r["name"] = f"JY/{r['name']}"
+                r["name"] = f"{tag}/{r['name']}"
                 _PROFILE_LOG.append(r)
         return (outs[0], codes[0], codes[2]), (outs[1], codes[1], codes[3])
     za = np.ascontiguousarray(z, dtype=np.complex128)
@@ -201,8 +232,8 @@ def bessel_jy(v, z, scaled=False, semantics="amos", profile=False, outs=None, co
         codes = [np.empty(za.shape, np.int32) for _ in range(4)]
     cp = [c.ctypes.data if c is not None else None for c in codes]
     ex = make_exec(flags=flags, devices=devices)
-    check(lib.spb_bessel_jy(kode, va.ctypes.data, stride, za.ctypes.data, outs[0].ctypes.data, outs[1].ctypes.data,
-                            cp[0], cp[1], cp[2], cp[3], za.size, ctypes.byref(ex)))
+    check(entry(kode, va.ctypes.data, stride, za.ctypes.data, outs[0].ctypes.data, outs[1].ctypes.data,
+                cp[0], cp[1], cp[2], cp[3], za.size, ctypes.byref(ex)))
     return (outs[0], codes[0], codes[2]), (outs[1], codes[1], codes[3])
 
 

@@ -32,6 +32,7 @@ def oracle_lib():
         lib.spbo_bessel_pipeline.argtypes = [I, I, P, L, P, P, P, P, P, L, I]
         lib.spbo_airy.argtypes = [I, I, P, P, P, P, L, I]
         lib.spbo_bessel_jy_pipeline.argtypes = [I, P, L, P, P, P, P, L, I]
+        lib.spbo_bessel_ik_pipeline.argtypes = [I, P, L, P, P, P, P, L, I]
         lib.spbo_bessel_seq.argtypes = [I, I, P, L, P, P, P, P, L, I, I]
         lib.spbo_kaiser.argtypes = [L, ctypes.c_double, I, P]
         lib.spbo_lanczos.argtypes = [L, I, P]
@@ -100,6 +101,17 @@ def cpu_bessel_jy(kode, v, z, threads=8, fuse=False):
     lib.spbo_bessel_jy_pipeline(kode, v.ctypes.data, 1, z.ctypes.data, oj.ctypes.data, oy.ctypes.data, codes.ctypes.data,
                                 z.size, threads | _mode_bits(fuse))
     return (oj, codes[0], codes[2]), (oy, codes[1], codes[3])
+
+
+def cpu_bessel_ik(kode, v, z, threads=8, fuse=3):
+    lib = oracle_lib()
+    z = np.ascontiguousarray(z, dtype=np.complex128)
+    v = np.ascontiguousarray(np.broadcast_to(np.asarray(v, dtype=np.float64), z.shape))
+    oi, ok = np.empty_like(z), np.empty_like(z)
+    codes = np.empty((4, z.size), np.int32)
+    lib.spbo_bessel_ik_pipeline(kode, v.ctypes.data, 1, z.ctypes.data, oi.ctypes.data, ok.ctypes.data, codes.ctypes.data,
+                                z.size, threads | _mode_bits(fuse))
+    return (oi, codes[0], codes[2]), (ok, codes[1], codes[3])
 
 
 def cpu_airy(which, kode, z, threads=8):

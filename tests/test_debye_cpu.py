@@ -124,3 +124,32 @@ def test_debye_region_on_the_axes_exactly():
             err = so.mismatch(got, want, scale)
             bad = ok & (err > so.tolerance(want, zs, v))
             assert not bad.any(), (fn, kode, int(bad.sum()), v[bad][:2], zs[bad][:2], err[bad][:2])
+
+
+@pytest.mark.parametrize("fuse", [0, 3], ids=["separate", "single-evaluation routines"])
+@pytest.mark.parametrize("cfg", ["cfg2", "cfg3", "cfg4", "real", "wide", "far"])
+def test_ik_pair_matches_separate_drivers(cfg, fuse):
+    """The FAM_IK flow (spb_bessel_ik: I and K from one classification, one I pass, one K pass) against the I and K
+    drivers: bit for bit with the region passes alone, to the parity tolerance (identical error classes) with the
+    fused large-|w| routine and the Debye-direct region on."""
+    rng = np.random.default_rng(helpers.seed_of("ik", cfg))
+    v, z = gen(cfg, 20000, rng)
+    for kode in (1, 2):
+        (i_, ei, ni), (k_, ek, nk) = helpers.cpu_bessel_ik(kode, v, z, fuse=fuse)
+        a, ia, na = helpers.cpu_bessel("I", kode, v, z)
+        b, ib, nb = helpers.cpu_bessel("K", kode, v, z)
+        assert np.array_equal(ei, ia) and np.array_equal(ni, na) and np.array_equal(ek, ib) and np.array_equal(nk, nb)
+        if fuse == 0:
+            same_i = (i_.view(np.uint64) == a.view(np.uint64)).reshape(-1, 2).all(1) | (np.isnan(a.real) & np.isnan(i_.real))
+            same_k = (k_.view(np.uint64) == b.view(np.uint64)).reshape(-1, 2).all(1) | (np.isnan(b.real) & np.isnan(k_.real))
+            assert same_i.all() and same_k.all()
+            continue
+        cond = 16.0 if cfg in ("wide", "far") else 0.0
+        with np.errstate(all="ignore"):
+            si = np.maximum(np.abs(a), np.where((np.abs(z.real) <= 1) & np.isfinite(np.abs(b)), np.abs(b) / np.pi
+                                                * (np.exp(-z.real - np.abs(z.real)) if kode == 2 else 1.0), 0))
+            sk = np.maximum(np.abs(b), np.where((z.real < 0) & np.isfinite(np.abs(a)), np.pi * np.abs(a)
+                                                * (np.exp(z.real + np.abs(z.real)) if kode == 2 else 1.0), 0))
+        ok = (ia == 0) & (na == 0) & (ib == 0) & (nb == 0)
+        assert np.all(so.mismatch(i_, a, si)[ok] <= so.tolerance(a, z, v, conditioning=cond)[ok])
+        assert np.all(so.mismatch(k_, b, sk)[ok] <= so.tolerance(b, z, v, conditioning=cond)[ok])

@@ -714,3 +714,37 @@ np.savez(sys.argv[1], **{f"{fn}_{i}": a for fn, t in out.items() for i, a in enu
             res[tag] = np.load(os.path.join(d, tag + ".npz"))
         for k in res["a"].files:
             assert np.array_equal(res["a"][k], res["b"][k]), k
+
+
+@pytest.mark.parametrize("cfg", ["cfg2", "cfg3", "cfg4", "wide"])
+def test_ik_pair_matches_single_calls_and_scipy(special, cfg):
+    """spb_bessel_ik (I and K in one pass) against spb_bessel(I) / spb_bessel(K) and live scipy: identical error
+    classes, values to the parity tolerance (a point may take another region routine in the pair)."""
+    rng = np.random.default_rng(helpers.seed_of("ik-gpu", cfg))
+    v, z = gen(cfg, 200000, rng)
+    zt, vt = torch.from_numpy(z).cuda(), torch.from_numpy(v).cuda()
+    cond = 16.0 if cfg == "wide" else 0.0
+    for scaled in (False, True):
+        kode = 2 if scaled else 1
+        (i_, ei, ni), (k_, ek, nk) = special.bessel_ik(vt, zt, scaled=scaled)
+        a, ia, na = special.bessel("I", vt, zt, scaled=scaled)
+        b, ib, nb = special.bessel("K", vt, zt, scaled=scaled)
+        assert torch.equal(ei, ia) and torch.equal(ni, na) and torch.equal(ek, ib) and torch.equal(nk, nb)
+        for fn, got, single, ie, nzz in (("I", i_, a, ia, na), ("K", k_, b, ib, nb)):
+            g, sg = to_np(got), to_np(single)
+            want = so.evaluate(fn, kode, v, z)
+            scale = so.scale_near_zeros(fn, kode, v, z, want)
+            ok = (to_np(ie) == 0) & (to_np(nzz) == 0) & np.isfinite(want.real) & np.isfinite(want.imag)
+            ok &= ~scipy_kode2_defect(fn, kode, v) & (np.abs(z) < 32767.0) & (v < 32767.0)
+            tol = so.tolerance(want, z, v, conditioning=cond)
+            assert np.all(so.mismatch(g, want, scale)[ok] <= tol[ok]), (fn, scaled)
+            assert np.all(so.mismatch(g, sg, np.maximum(scale, np.abs(sg)))[ok] <= tol[ok]), (fn, scaled)
+    # host buffers (staged chunks) give the same bits as device pointers
+    (i_h, _, _), (k_h, _, _) = special.bessel_ik(v[:50000], z[:50000], scaled=True)
+    (i_d, _, _), (k_d, _, _) = special.bessel_ik(vt[:50000], zt[:50000], scaled=True)
+    for h, d in ((i_h, to_np(i_d)), (k_h, to_np(k_d))):
+        same = (h.view(np.uint64) == d.view(np.uint64)).reshape(-1, 2).all(1) | (np.isnan(h.real) & np.isnan(d.real))
+        assert same.all()
+    if cfg == "cfg2":
+        i2, k2 = special.ive_kve(v[:50000], z[:50000])  # raises like Result<_, i32>; none fails on this grid
+        assert np.array_equal(i2.view(np.uint64), i_h.view(np.uint64)) and np.array_equal(k2.view(np.uint64), k_h.view(np.uint64))

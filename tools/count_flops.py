@@ -21,7 +21,7 @@ from test_pipeline_cpu import gen  # noqa: E402
 KERNELS = ["classify", "scan_scatter", "ipass_series", "ipass_asyi", "ipass_mlri", "ipass_wrsk", "kpass", "general",
            "monolithic", "ipass_uni1", "ipass_uni2", "ipass_debye"]
 NK = len(KERNELS)
-FN = {"J": 0, "Y": 1, "I": 2, "K": 3, "H1": 4, "H2": 5, "JY": 6}
+FN = {"J": 0, "Y": 1, "I": 2, "K": 3, "H1": 4, "H2": 5, "JY": 6, "IK": 7}
 
 
 def cfg2_sample(n):
@@ -43,7 +43,7 @@ def main():
     # last field: the single-evaluation routines of the library's default flow (1 = fused I + K in the large-|w|
     # region for K-type families, 2 = Debye-direct region)
     samples = {"cfg2": (cfg2_sample(1 << 18), ("J", "Y", "JY"), 1, 3),
-               "cfg3": (gen("cfg3", 1 << 17, rng), ("I", "K"), 2, 3),
+               "cfg3": (gen("cfg3", 1 << 17, rng), ("I", "K", "IK"), 2, 3),
                "cfg4": (gen("cfg4", 1 << 17, rng), ("H1", "H2"), 1, 3)}
     for cfg, ((v, z), fams, kode, fuse) in samples.items():
         v = np.ascontiguousarray(v, dtype=np.float64)

@@ -25,6 +25,7 @@ for k in r.get("kernels", []):
                                                        ("%.3f" % k["frac"]) if k.get("frac") else "-"))
 print("accuracy:", json.dumps(d.get("accuracy")))
 print("cpu_baseline:", json.dumps(d.get("cpu_baseline")))
+print("separate_calls:", json.dumps(d.get("separate_calls")))
 print("in_process:", json.dumps(d.get("in_process")))
 for rk in d.get("ranks") or []:
     print("  rank", json.dumps(rk))
