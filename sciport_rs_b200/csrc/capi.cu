@@ -269,7 +269,7 @@ int ensure_scratch(ScratchSet &ss, long long n, cudaStream_t st) {
     };
     size_t o_cls = take(cap), o_pi = take(cap * 4), o_pk = take(cap * 4), o_gl = take(cap * 4),
            o_it = take(cap * 16), o_ic = take(cap), o_bc = take((size_t)NBINS * nblocks_cap * 4), o_bins = take(BINS_WORDS * 4),
-           o_pi2 = take(cap * 4), o_pk2 = take(cap * 4), o_cc = take((size_t)CELL_SLOTS * NCELLS * 4);
+           o_pi2 = take(cap * 4), o_pk2 = take(cap * 4), o_cc = take((size_t)CELL_SLOTS * NCELLS * 4), o_ck = take(cap * 2);
     char *base = nullptr;
     if (cudaMalloc(&base, off) != cudaSuccess) {
         cudaGetLastError();
@@ -284,6 +284,7 @@ int ensure_scratch(ScratchSet &ss, long long n, cudaStream_t st) {
     ss.s.perm_i2 = (unsigned int *)(base + o_pi2);
     ss.s.perm_k2 = (unsigned int *)(base + o_pk2);
     ss.s.cellcnt = (unsigned int *)(base + o_cc);
+    ss.s.cellkey = (unsigned short *)(base + o_ck);
     ss.s.itemp = (double2 *)(base + o_it);
     ss.s.icode = (signed char *)(base + o_ic);
     ss.s.blockcnt = (unsigned int *)(base + o_bc);

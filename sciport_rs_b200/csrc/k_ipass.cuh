@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(128, FAM >= 0 ? SPB_FUSED_MINB : SPB_IPASS_MIN
     const unsigned int count = s.bins[REGION + 1] - s.bins[REGION];
     const unsigned int stride = gridDim.x * blockDim.x;
     // iterative regions of a cell-sorted job walk the re-sorted index array (k_pipeline.cu)
-    const unsigned int *perm = ((REGION != spb::IREG_ASYI && job.cellsort) ? s.perm_i2 : s.perm_i) + start;
+    const unsigned int *perm = (job.cellsort ? s.perm_i2 : s.perm_i) + start;
     unsigned int t = blockIdx.x * blockDim.x + threadIdx.x;
     bool have1 = t < count, have2 = (t + stride) < count;
     unsigned int i1 = have1 ? __ldg(perm + t) : 0u;

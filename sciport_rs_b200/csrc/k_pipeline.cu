@@ -76,6 +76,17 @@ __device__ __forceinline__ unsigned int field_g(const Packed &p) {
     return (unsigned int)p.w[2] & ((1u << FIELD_BITS) - 1u);
 }
 
+// (|z|, order) cell of a point for the second-level sort (see k_cell_hist below): 32 levels of |z|, 16 of the order
+__device__ __forceinline__ unsigned int cell_of(cplx z, double v) {
+    const double m2 = z.re * z.re + z.im * z.im;
+    const int hi = __double2hiint(m2);
+    int q = 2 * ((hi >> 20) - 1023) + ((hi >> 19) & 1);  // two levels per octave of |z|^2 = four per octave of |z|
+    q = q < 0 ? 0 : (q > 31 ? 31 : q);
+    int b = (int)(fabs(v) * 0.25);
+    b = b > 15 ? 15 : b;
+    return (unsigned int)(q | (b << 5));
+}
+
 // FAM / KODE: the job's family and scaling flag as compile-time constants (dispatch_fam_kode)
 template <int FAM, int KODE>
 __global__ void __launch_bounds__(256) k_classify(DevJob job, Scratch s) {
@@ -134,6 +145,12 @@ __global__ void __launch_bounds__(256) k_classify(DevJob job, Scratch s) {
                 double v;
                 load_point(job, i, z, v);
                 c = spb::class_byte(job.fam, z, v, job.kode, job.fuse, false);
+                if (job.cellsort) s.cellkey[i] = (unsigned short)cell_of(z, v);
+            } else if (job.cellsort) {
+                cplx z;
+                double v;
+                load_point(job, i, z, v);
+                s.cellkey[i] = (unsigned short)cell_of(z, v);
             }
             s.cls[i] = (unsigned char)c;
             packed_add(c, cnt);
@@ -366,27 +383,18 @@ __global__ void __launch_bounds__(256) k_scatter(DevJob job, Scratch s) {
 // K kernels of config 3 even with a per-CTA batch sort of 512 points).  A counting sort of each bin segment by a
 // 9-bit cell key -- 32 levels of |z|, four per octave, times 16 levels of the order -- makes 32 consecutive
 // entries near neighbours in both variables, over the whole chunk instead of a 512-point batch:
+// The classifier of a cell-sorted job stores the key of every point (2 bytes, coalesced) next to its class byte.
 //   k_cell_hist    histogram of the cell keys per bin (shared-memory histograms, one global add per cell and CTA)
 //   k_cell_scan    exclusive scan of the 512 cell counters of every bin -> cell cursors
 //   k_cell_scatter batches of 1024 entries: shared-memory counts, ONE global atomic per (batch, cell) reserves the
 //                  range, entries are written to perm_i2 / perm_k2 (order inside a cell is arbitrary: results are
 //                  per point, only the memory order depends on it)
 // Bin boundaries do not move, so the region kernels only switch the index array they walk.
-__device__ __forceinline__ unsigned int cell_of(cplx z, double v) {
-    const double m2 = z.re * z.re + z.im * z.im;
-    const int hi = __double2hiint(m2);
-    int q = 2 * ((hi >> 20) - 1023) + ((hi >> 19) & 1);  // two levels per octave of |z|^2 = four per octave of |z|
-    q = q < 0 ? 0 : (q > 31 ? 31 : q);
-    int b = (int)(fabs(v) * 0.25);
-    b = b > 15 ? 15 : b;
-    return (unsigned int)(q | (b << 5));
-}
-
-// slot -> (bin, index array): I bins 0 (series), 2 (mlri), 3 (wrsk), 4, 5 (uniform forms), then the three K bins
+// slot -> (bin, index array): I bins 0..5 (series, asyi, mlri, wrsk, uniform forms 1 and 2), then the three K bins
 __device__ __forceinline__ void cell_slot(const Scratch &s, int slot, const unsigned int *&src, unsigned int *&dst,
                                           unsigned int &count) {
-    const int bin = slot == 0 ? 0 : (slot < 5 ? slot + 1 : BIN_K0 + (slot - 5));
-    const bool kbin = slot >= 5;
+    const int bin = slot < 6 ? slot : BIN_K0 + (slot - 6);
+    const bool kbin = slot >= 6;
     const unsigned int start = s.bins[bin] - (kbin ? s.bins[BIN_K0] : s.bins[0]);
     count = s.bins[bin + 1] - s.bins[bin];
     src = (kbin ? s.perm_k : s.perm_i) + start;
@@ -405,10 +413,7 @@ __global__ void __launch_bounds__(256) k_cell_hist(DevJob job, Scratch s) {
     __syncthreads();
     for (unsigned int t = blockIdx.x * 256 + threadIdx.x; t < count; t += gridDim.x * 256) {
         const unsigned int i = __ldg(src + t);
-        cplx z;
-        double v;
-        load_point(job, i, z, v);
-        atomicAdd(&hist[cell_of(z, v)], 1u);
+        atomicAdd(&hist[s.cellkey[i]], 1u);
     }
     __syncthreads();
     for (int c = threadIdx.x; c < NCELLS; c += 256)
@@ -453,10 +458,7 @@ __global__ void __launch_bounds__(256) k_cell_scatter(DevJob job, Scratch s) {
             key[r] = 0xffffffffu;
             if (t < count) {
                 idx[r] = __ldg(src + t);
-                cplx z;
-                double v;
-                load_point(job, idx[r], z, v);
-                key[r] = cell_of(z, v);
+                key[r] = s.cellkey[idx[r]];
                 rank[r] = atomicAdd(&cnt[key[r]], 1u);
             }
         }

@@ -43,6 +43,7 @@ struct Scratch {
     unsigned int *perm_i2;  // [n] perm_i with the segments of the iterative bins re-sorted by (|z|, order) cell
     unsigned int *perm_k2;  // [n] perm_k re-sorted likewise
     unsigned int *cellcnt;  // [CELL_SLOTS][NCELLS] cell histogram of a chunk, then (k_cell_scan) the cell cursors
+    unsigned short *cellkey;  // [n] (|z|, order) cell of every point, written by the classifier of a cell-sorted job
     unsigned int *glist;    // [n] general-path list
     double2 *itemp;         // [n] I(w) for families that also need K
     signed char *icode;     // [n] nz of the I pass (<0: handed to the general path)
@@ -64,9 +65,10 @@ constexpr int FIELDS_PER_WORD = 5;
 constexpr int NWORDS = (NBINS + FIELDS_PER_WORD - 1) / FIELDS_PER_WORD;
 constexpr int TILE = 2048;               // points per classification tile
 // second-level sort inside a bin: 512 cells = 32 levels of |z| (four per octave, 1 <= |z| < 221) x 16 levels of the
-// order (steps of 4); slots = the bins that are sorted this way (I: series, mlri, wrsk, uni1, uni2; K: all three)
+// order (steps of 4); slots = the bins that are sorted this way (every I bin but the Debye-direct one, whose routine
+// has no data-dependent loop; the three K bins)
 constexpr int NCELLS = 512;
-constexpr int CELL_SLOTS = 8;
+constexpr int CELL_SLOTS = 9;
 // slots of Scratch::bins beyond the NBINS+1 start offsets
 constexpr int GLIST_LEN_SLOT = 24;  // current length of the general list (grows when a pass hands a point over)
 constexpr int SLOT_DONE = 25;       // CTAs of k_scan that have finished
