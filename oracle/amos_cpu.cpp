@@ -99,7 +99,7 @@ int spbo_bessel_pipeline(int fn, int kode, const double *v, int64_t v_stride, co
     // fused routine (the flow of the fused region kernel)
     // bit 17: the Debye-direct region (spb_debye.h) is enabled as well
     const int threads = threads_and_mode & 0xffff;
-    const int fuse = ((threads_and_mode & 0x10000) ? FUSE_ASYI : 0) | ((threads_and_mode & 0x20000) ? FUSE_DEBYE : 0);
+    const int fuse = ((threads_and_mode & 0x10000) ? FUSE_ASYI : 0) | ((threads_and_mode & 0x20000) ? FUSE_DEBYE : 0) | ((threads_and_mode & 0x40000) ? FUSE_WRSK : 0);
     parallel_for(n, threads, [=](int64_t lo, int64_t hi) {
         for (int64_t i = lo; i < hi; ++i) {
             int ie, nzz, pth;
@@ -134,7 +134,7 @@ int spbo_classify(int fn, int kode, int fuse, const double *v, int64_t v_stride,
 int spbo_bessel_ik_pipeline(int kode, const double *v, int64_t v_stride, const double *z, double *out_i, double *out_k,
                             int32_t *codes, int64_t n, int threads_and_mode) {
     const int threads = threads_and_mode & 0xffff;
-    const int fuse = ((threads_and_mode & 0x10000) ? FUSE_ASYI : 0) | ((threads_and_mode & 0x20000) ? FUSE_DEBYE : 0);
+    const int fuse = ((threads_and_mode & 0x10000) ? FUSE_ASYI : 0) | ((threads_and_mode & 0x20000) ? FUSE_DEBYE : 0) | ((threads_and_mode & 0x40000) ? FUSE_WRSK : 0);
     parallel_for(n, threads, [=](int64_t lo, int64_t hi) {
         for (int64_t i = lo; i < hi; ++i) {
             cplx a, b;
@@ -158,7 +158,7 @@ int spbo_bessel_jy_pipeline(int kode, const double *v, int64_t v_stride, const d
                             int32_t *codes /* [4][n]: ierr_j, ierr_y, nz_j, nz_y */, int64_t n,
                             int threads_and_mode) {
     const int threads = threads_and_mode & 0xffff;
-    const int fuse = ((threads_and_mode & 0x10000) ? FUSE_ASYI : 0) | ((threads_and_mode & 0x20000) ? FUSE_DEBYE : 0);
+    const int fuse = ((threads_and_mode & 0x10000) ? FUSE_ASYI : 0) | ((threads_and_mode & 0x20000) ? FUSE_DEBYE : 0) | ((threads_and_mode & 0x40000) ? FUSE_WRSK : 0);
     parallel_for(n, threads, [=](int64_t lo, int64_t hi) {
         for (int64_t i = lo; i < hi; ++i) {
             cplx jv, yv;

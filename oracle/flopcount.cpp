@@ -107,13 +107,13 @@ int spbo_count_ops2(int fam, int kode, int fuse, const double *v, int64_t v_stri
                 pts[islot(IREG_DEBYE)] += 1;
             } else if (!general && p.kreg == KREG_FUSED) {
                 g_ops = prep_ops;
-                if (fused_ik_region(p.w, fnu, kode, iv, inz, kv, knz, p.az) < 0 ||
+                if (fused_region(p.ireg, p.w, fnu, kode, iv, inz, kv, knz, p.az) < 0 ||
                     (knz != 0 && (p.combine == CMB_Y_SHARED || p.combine == CMB_ACON)))
                     general = true;
                 else
                     { if (ik) finish_ik(p, zz, fnu, kode, iv, inz, kv, knz, jv, ierr, nz, yv, e2, n2); else finish_jy(p, zz, fnu, kode, iv, inz, kv, knz, jv, ierr, nz, yv, e2, n2); }
-                ops[islot(IREG_ASYI)] += g_ops;
-                pts[islot(IREG_ASYI)] += 1;
+                ops[islot(p.ireg)] += g_ops;
+                pts[islot(p.ireg)] += 1;
             } else if (!general) {
                 g_ops = prep_ops;
                 inz = ipass_region(p.ireg, p.w, fnu, kode, iv);
@@ -160,13 +160,13 @@ int spbo_count_ops2(int fam, int kode, int fuse, const double *v, int64_t v_stri
             pts[islot(IREG_DEBYE)] += 1;
         } else if (p.kreg == KREG_FUSED) {
             g_ops = prep_ops;
-            if (fused_ik_region(p.w, fnu, kode, ival, inz, kval, knz, p.az) < 0 ||
+            if (fused_region(p.ireg, p.w, fnu, kode, ival, inz, kval, knz, p.az) < 0 ||
                 (knz != 0 && (p.combine == CMB_ACON || p.combine == CMB_Y_SHARED)))
                 handed = true;
             else
                 finish(fam, p, zz, fnu, kode, ival, inz, kval, knz, ierr, nz);
-            ops[islot(IREG_ASYI)] += g_ops;
-            pts[islot(IREG_ASYI)] += 1;
+            ops[islot(p.ireg)] += g_ops;
+            pts[islot(p.ireg)] += 1;
         } else if (p.ireg >= 0) {
             g_ops = prep_ops;  // the region kernel recomputes prepare()
             inz = ipass_region(p.ireg, p.w, fnu, kode, ival);

@@ -140,10 +140,13 @@ SPB_FN int uoik(cplx z, real fnu, int kode, int ikflg, int n, Y y, real tol, rea
 // after all, and the caller hands it to the general path); both forms round identically.
 template <bool SIMPLE = false, class Y>
 SPB_FN int wrsk(cplx zr, real fnu, int kode, int n, Y y, real tol, real elim, real alim,
-                real az_known = real(-1.0)) {
+                real az_known = real(-1.0), cplx *k_out = nullptr) {
     cplx cw[2];
     int nw = SIMPLE ? bknu_simple2(zr, fnu, kode, cw, tol, elim, alim, az_known)
                     : bknu(zr, fnu, kode, 2, cw, tol, elim, alim, az_known);
+    // K_fnu(zr) itself, for callers that need K at the same point (K-type families: the K pass would compute the
+    // very same value again)
+    if (k_out) *k_out = cw[0];
     // a failed K evaluation is reported at the end (no return between the data-dependent loops of bknu and
     // rati, so that their exits reconverge here)
     const bool kfail = nw != 0;

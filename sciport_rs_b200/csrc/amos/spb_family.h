@@ -43,7 +43,10 @@ enum Combine {
 // `fuse` argument of prepare() / the classifier: which of the single-evaluation region routines of the binned
 // pipeline are enabled (the classic per-point drivers know neither)
 enum { FUSE_ASYI = 1,   // I and K of a K-type point in the large-|w| region of I from one Hankel series (fused_ik_region)
-       FUSE_DEBYE = 2 };  // Debye-direct region (spb_debye.h) for I, K or both
+       FUSE_DEBYE = 2,  // Debye-direct region (spb_debye.h) for I, K or both
+       FUSE_WRSK = 4 };  // K-type points whose I region is Miller + Wronskian: that routine evaluates K_v(w), K_v+1(w)
+                         // for its normalisation, so K_v(w) is taken from there instead of from a second evaluation
+                         // in the K pass (wrsk_ik_region)
 
 // K-pass regions
 enum KRegion { KREG_SERIES = 0, KREG_MILLER = 1, KREG_HALF = 2, KREG_COUNT = 3 };
@@ -222,8 +225,9 @@ SPB_FN Prep prepare(int fam, cplx z, real fnu, int kode, int fuse = 0) {
             p.combine = CMB_GENERAL;
             p.ireg = -1;
             p.kreg = -1;
-        } else if (((fuse & FUSE_ASYI) && p.ireg == IREG_ASYI) || p.ireg == IREG_DEBYE) {
-            p.kreg = KREG_FUSED;  // I and K from one evaluation (large-|w| series / Debye expansion)
+        } else if (((fuse & FUSE_ASYI) && p.ireg == IREG_ASYI) || p.ireg == IREG_DEBYE ||
+                   ((fuse & FUSE_WRSK) && p.ireg == IREG_WRSK)) {
+            p.kreg = KREG_FUSED;  // I and K from one evaluation (large-|w| series / Debye expansion / Wronskian route)
         }
     } else {
         // I_v(w) is not needed here, but the point lies in a region where one of the single-evaluation routines
@@ -423,6 +427,28 @@ SPB_FN int fused_ik_region(cplx w, real fnu, int kode, cplx &ival, int &inz, cpl
     }
     kval = coef * ksum;
     return 0;
+}
+
+// I_v(w) and K_v(w) of a K-type point whose I region is Miller + Wronskian (FUSE_WRSK): the Wronskian
+// normalisation needs K_v(w) and K_v+1(w) anyway (same lean K routine, same arguments as the K pass would use), so
+// K_v(w) is a by-product.  Returns < 0 when the point has to go to the general path.
+SPB_FN int wrsk_ik_region(cplx w, real fnu, int kode, cplx &ival, int &inz, cplx &kval, int &knz, real az) {
+    const real tol = SPB_TOL, elim = SPB_ELIM, alim = SPB_ALIM;
+    cplx y[1];
+    y[0] = cplx(0.0, 0.0);
+    kval = cplx(0.0, 0.0);
+    inz = 0;
+    knz = 0;
+    const int nw = wrsk<true>(w, fnu, kode, 1, y, tol, elim, alim, az, &kval);
+    ival = y[0];
+    return nw;
+}
+
+// both outputs of a KREG_FUSED point outside the Debye-direct region, by the routine of its I region
+SPB_FN int fused_region(int ireg, cplx w, real fnu, int kode, cplx &ival, int &inz, cplx &kval, int &knz, real az,
+                        const OrderPhase *oph = nullptr) {
+    if (ireg == IREG_WRSK) return wrsk_ik_region(w, fnu, kode, ival, inz, kval, knz, az);
+    return fused_ik_region(w, fnu, kode, ival, inz, kval, knz, az, oph);
 }
 
 // I_v(w) and / or K_v(w) of a point in the Debye-direct region (IREG_DEBYE): one evaluation of the uniform
@@ -827,7 +853,7 @@ SPB_FN cplx pipeline_eval(int fam, cplx z, real fnu, int kode, int &ierr, int &n
             return general_eval(fam, z, fnu, kode, ierr, nz);
         p.kreg = -1;
     } else if (p.kreg == KREG_FUSED) {
-        if (fused_ik_region(p.w, fnu, kode, ival, inz, kval, knz, p.az) < 0)
+        if (fused_region(p.ireg, p.w, fnu, kode, ival, inz, kval, knz, p.az) < 0)
             return general_eval(fam, z, fnu, kode, ierr, nz);
         if (knz != 0 && (p.combine == CMB_ACON || p.combine == CMB_Y_SHARED))
             return general_eval(fam, z, fnu, kode, ierr, nz);
@@ -864,7 +890,7 @@ SPB_FN void pipeline_eval_jy(cplx z, real fnu, int kode, cplx &jv, int &jerr, in
         if (debye_region(FAM_JY, p.w, fnu, kode, true, ival, inz, kval, knz, p.az) < 0) general = true;
     } else if (!general && p.kreg == KREG_FUSED) {
         path = 2;
-        if (fused_ik_region(p.w, fnu, kode, ival, inz, kval, knz, p.az) < 0) general = true;
+        if (fused_region(p.ireg, p.w, fnu, kode, ival, inz, kval, knz, p.az) < 0) general = true;
         if (knz != 0 && p.combine == CMB_Y_SHARED) general = true;
     } else {
         if (!general) {
@@ -903,7 +929,7 @@ SPB_FN void pipeline_eval_ik(cplx z, real fnu, int kode, cplx &iv, int &ierr_i, 
         if (p.ireg == IREG_DEBYE) {
             if (debye_region(FAM_IK, p.w, fnu, kode, true, ival, inz, kval, knz, p.az) < 0) general = true;
         } else if (p.kreg == KREG_FUSED) {
-            if (fused_ik_region(p.w, fnu, kode, ival, inz, kval, knz, p.az) < 0) general = true;
+            if (fused_region(p.ireg, p.w, fnu, kode, ival, inz, kval, knz, p.az) < 0) general = true;
             if (knz != 0 && p.combine == CMB_ACON) general = true;
         } else {
             inz = ipass_region(p.ireg, p.w, fnu, kode, ival, p.az);

@@ -357,6 +357,8 @@ int enqueue_chunk(const DevJob &job_in, ScratchSet &ss, int sms, int flags, cuda
                        ? spb::FUSE_ASYI : 0;
         // Debye-direct region (every family; SPB_DEBYE=0 in the environment switches it off)
         if (debye_enabled() && !(flags & SPB_PATH_MONOLITHIC)) job.fuse |= spb::FUSE_DEBYE;
+        // K of a Miller + Wronskian point from the Wronskian routine itself (with the fused large-|w| kernel)
+        if (job.fuse & spb::FUSE_ASYI) job.fuse |= spb::FUSE_WRSK;
         // second-level (|z|, order) sort inside the iterative bins: SPB_CELLSORT = 0 never, 1 (default) for
         // per-element orders, 2 always
         job.cellsort = (cellsort_mode() == 2 || (cellsort_mode() == 1 && job.v_stride != 0)) ? 1 : 0;

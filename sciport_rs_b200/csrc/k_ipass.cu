@@ -27,13 +27,15 @@ void launch_ipass(const DevJob &job, const Scratch &s, int region, int sms, cuda
         case spb::IREG_SERIES: launch_ipass_region<spb::IREG_SERIES>(job, s, sms, st); break;
         case spb::IREG_ASYI:
             if (job.fuse & spb::FUSE_ASYI)
-                launch_fused(job, s, sms, st);  // I and K of these points in one kernel (k_fused.cu)
+                launch_fused(job, s, sms, st, spb::IREG_ASYI);  // I and K of these points in one kernel (k_fused.cu)
             else
                 launch_ipass_region<spb::IREG_ASYI>(job, s, sms, st);
             break;
         case spb::IREG_MLRI: launch_ipass_region<spb::IREG_MLRI>(job, s, sms, st); break;
         case spb::IREG_WRSK:
-            if (job.v_stride != 0 && !job.cellsort)
+            if ((job.fuse & spb::FUSE_WRSK) && !(job.fam == spb::FAM_J || job.fam == spb::FAM_I))
+                launch_fused(job, s, sms, st, spb::IREG_WRSK);  // K_v(w) from the Wronskian normalisation: no K pass
+            else if (job.v_stride != 0 && !job.cellsort)
                 launch_pdl(job.pdl != 0, k_ipass_sorted<spb::IREG_WRSK>, resident_grid(k_ipass_sorted<spb::IREG_WRSK>, 128, sms), 128, st,
                            job, s);
             else

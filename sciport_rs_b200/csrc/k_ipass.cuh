@@ -22,11 +22,13 @@ template <int REGION, bool FUSED = false>
 __device__ __forceinline__ void ipass_point(const DevJob &job, const Scratch &s, long long i, cplx z, double v,
                                             const spb::OrderPhase *ph) {
     // the classifier has already established region and simplicity of this point: geometry only
-    spb::Prep p = spb::prepare_pass(job.fam, z, !FUSED);
+    spb::Prep p = spb::prepare_pass(job.fam, z, !FUSED || REGION != spb::IREG_ASYI);
     if (FUSED) {
         cplx ival, kval;
         int inz = 0, knz = 0;
-        const int rc = spb::fused_ik_region(p.w, v, job.kode, ival, inz, kval, knz, p.az, ph);
+        const int rc = (REGION == spb::IREG_WRSK)
+                           ? spb::wrsk_ik_region(p.w, v, job.kode, ival, inz, kval, knz, p.az)
+                           : spb::fused_ik_region(p.w, v, job.kode, ival, inz, kval, knz, p.az, ph);
         if (rc < 0 || (knz != 0 && (p.combine == spb::CMB_ACON || p.combine == spb::CMB_Y_SHARED))) {
             unsigned int g = atomicAdd(&s.bins[GLIST_LEN_SLOT], 1u);
             s.glist[g] = (unsigned int)i;
@@ -58,7 +60,8 @@ __device__ __forceinline__ void ipass_point(const DevJob &job, const Scratch &s,
 // memory; otherwise they are computed per point
 // FAM >= 0: the fused form of the kernel with the family and the scaling flag as compile-time constants
 template <int REGION, bool SCALAR, int FAM = -1, int KODE = 0>
-__global__ void __launch_bounds__(128, FAM >= 0 ? SPB_FUSED_MINB : SPB_IPASS_MINB(REGION)) k_ipass(DevJob job, Scratch s) {
+__global__ void __launch_bounds__(128, FAM >= 0 ? (REGION == spb::IREG_ASYI ? SPB_FUSED_MINB : 3) : SPB_IPASS_MINB(REGION))
+    k_ipass(DevJob job, Scratch s) {
     pdl_enter();
     if (FAM >= 0) {
         job.fam = FAM;

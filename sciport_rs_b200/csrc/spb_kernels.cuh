@@ -148,7 +148,8 @@ void launch_classify(const DevJob &job, const Scratch &s, cudaStream_t st);
 void launch_scan_scatter(const DevJob &job, const Scratch &s, cudaStream_t st);
 int launch_cellsort(const DevJob &job, const Scratch &s, int sms, cudaStream_t st);  // returns the launches made
 void launch_ipass(const DevJob &job, const Scratch &s, int region, int sms, cudaStream_t st);
-void launch_fused(const DevJob &job, const Scratch &s, int sms, cudaStream_t st);  // job.fuse: I + K, large-|w| region
+// job.fuse: I + K of the K-type points of one I region (large-|w| series / Miller + Wronskian) in one kernel
+void launch_fused(const DevJob &job, const Scratch &s, int sms, cudaStream_t st, int region);
 void launch_debye(const DevJob &job, const Scratch &s, int sms, cudaStream_t st);  // Debye-direct region (k_debye.cu)
 void launch_kpass(const DevJob &job, const Scratch &s, int sms, cudaStream_t st);
 int launch_general(const DevJob &job, const Scratch &s, int sms, cudaStream_t st);

@@ -43,9 +43,10 @@ def oracle_lib():
 
 
 def _mode_bits(fuse):
-    """fuse: False / True (fused large-|w| I + K routine) or a bitmask (1 = that, 2 = Debye-direct region)."""
+    """fuse: False / True (fused large-|w| I + K routine) or a bitmask (1 = that, 2 = Debye-direct region, 4 = K of
+    a Miller + Wronskian point from the Wronskian routine)."""
     f = int(fuse)
-    return (0x10000 if f & 1 else 0) | (0x20000 if f & 2 else 0)
+    return (0x10000 if f & 1 else 0) | (0x20000 if f & 2 else 0) | (0x40000 if f & 4 else 0)
 
 
 def cpu_bessel(fn, kode, v, z, sem=0, pipeline=False, threads=8, fuse=False):
@@ -86,7 +87,7 @@ def cpu_classify(fn, kode, v, z, fuse):
     v = np.ascontiguousarray(np.broadcast_to(np.asarray(v, dtype=np.float64), z.shape))
     fast = np.empty(z.shape, np.int8)
     full = np.empty(z.shape, np.int8)
-    lib.spbo_classify({**FN, "JY": 6}[fn], kode, int(fuse), ctypes.c_void_p(v.ctypes.data), ctypes.c_int64(1),
+    lib.spbo_classify({**FN, "JY": 6, "IK": 7}[fn], kode, int(fuse), ctypes.c_void_p(v.ctypes.data), ctypes.c_int64(1),
                       ctypes.c_void_p(z.ctypes.data), ctypes.c_void_p(fast.ctypes.data),
                       ctypes.c_void_p(full.ctypes.data), ctypes.c_int64(z.size))
     return fast, full
@@ -103,7 +104,7 @@ def cpu_bessel_jy(kode, v, z, threads=8, fuse=False):
     return (oj, codes[0], codes[2]), (oy, codes[1], codes[3])
 
 
-def cpu_bessel_ik(kode, v, z, threads=8, fuse=3):
+def cpu_bessel_ik(kode, v, z, threads=8, fuse=7):
     lib = oracle_lib()
     z = np.ascontiguousarray(z, dtype=np.complex128)
     v = np.ascontiguousarray(np.broadcast_to(np.asarray(v, dtype=np.float64), z.shape))

@@ -13,7 +13,7 @@ from helpers import FN
 from oracle import scipy_oracle as so
 from test_pipeline_cpu import gen
 
-FUSE_ALL = 3  # fused large-|w| routine + Debye-direct region: the library's default flow
+FUSE_ALL = 7  # fused large-|w| routine + Debye-direct region + K from the Wronskian route: the library default
 
 
 def scaled_companion_scale(fn, v, z, truth_i, truth_k):
@@ -126,7 +126,7 @@ def test_debye_region_on_the_axes_exactly():
             assert not bad.any(), (fn, kode, int(bad.sum()), v[bad][:2], zs[bad][:2], err[bad][:2])
 
 
-@pytest.mark.parametrize("fuse", [0, 3], ids=["separate", "single-evaluation routines"])
+@pytest.mark.parametrize("fuse", [0, 3, 7], ids=["separate", "single-evaluation routines", "default"])
 @pytest.mark.parametrize("cfg", ["cfg2", "cfg3", "cfg4", "real", "wide", "far"])
 def test_ik_pair_matches_separate_drivers(cfg, fuse):
     """The FAM_IK flow (spb_bessel_ik: I and K from one classification, one I pass, one K pass) against the I and K
