@@ -41,10 +41,10 @@ def main():
                     "prepare + region + finish", "_sample": {}}
     rng = np.random.default_rng(1)
     # last field: the single-evaluation routines of the library's default flow (1 = fused I + K in the large-|w|
-    # region for K-type families, 2 = Debye-direct region)
-    samples = {"cfg2": (cfg2_sample(1 << 18), ("J", "Y", "JY"), 1, 3),
-               "cfg3": (gen("cfg3", 1 << 17, rng), ("I", "K", "IK"), 2, 3),
-               "cfg4": (gen("cfg4", 1 << 17, rng), ("H1", "H2"), 1, 3)}
+    # region for K-type families, 2 = Debye-direct region, 4 = K from the Wronskian route)
+    samples = {"cfg2": (cfg2_sample(1 << 18), ("J", "Y", "JY"), 1, 7),
+               "cfg3": (gen("cfg3", 1 << 17, rng), ("I", "K", "IK"), 2, 7),
+               "cfg4": (gen("cfg4", 1 << 17, rng), ("H1", "H2"), 1, 7)}
     for cfg, ((v, z), fams, kode, fuse) in samples.items():
         v = np.ascontiguousarray(v, dtype=np.float64)
         z = np.ascontiguousarray(z, dtype=np.complex128)
