@@ -87,6 +87,10 @@ def main():
         v, z = special.synth(3, args.n, n_total=1 << 28, device=dev)
         for fn in ("I", "K"):
             bessel_case(3, f"{fn.lower()}ve per-element v", fn, v, z, True)
+        outs = [torch.empty_like(z) for _ in range(2)]
+        ms = timed(torch, lambda: special.bessel_ik(v, z, scaled=True, outs=outs, want_codes=False), args.reps)
+        prof = special.profile_step(lambda: special.bessel_ik(v, z, scaled=True, outs=outs, want_codes=False, profile=True))
+        emit(3, "ive+kve pair", 2 * args.n, ms, prof)
     if 4 in cfgs:
         v, z = special.synth(4, args.n, n_total=1 << 30, device=dev)
         for fn in ("H1", "H2"):
