@@ -323,8 +323,10 @@ SPB_FN int mlri(cplx z, real fnu, int kode, int n, Y y, real tol, real az_known 
         ck = rcz * at;
         ack = at * raz;
         tst = sqrt(ack / tol);
-        int itime = 1;
+        // two loops instead of one with a "second time" flag (see rati): the refinement of the test value runs
+        // once per point with the warp reconverged
         found = false;
+        bool first = false;
         for (k = 1; k <= 80; ++k) {
             cplx pt = p2;
             p2 = p1 - ck * pt;
@@ -332,17 +334,26 @@ SPB_FN int mlri(cplx z, real fnu, int kode, int n, Y y, real tol, real az_known 
             ck = ck + rz;
             real ap2 = p2.re * p2.re + p2.im * p2.im;
             if (ap2 < tst * tst) continue;
-            if (itime == 2) {
-                found = true;
-                break;
-            }
-            real ap = sqrt(ap2);
+            first = true;
+            break;
+        }
+        if (first) {
+            real ap = sqrt(p2.re * p2.re + p2.im * p2.im);
             ack = cabs_(ck);
             real flam = ack + sqrt(ack * ack - real(1.0));
             real fkap = ap / cabs_(p1);
             rho = rmin(flam, fkap);
             tst = tst * sqrt(rho / (rho * rho - real(1.0)));
-            itime = 2;
+            for (k = k + 1; k <= 80; ++k) {
+                cplx pt = p2;
+                p2 = p1 - ck * pt;
+                p1 = pt;
+                ck = ck + rz;
+                real ap2 = p2.re * p2.re + p2.im * p2.im;
+                if (ap2 < tst * tst) continue;
+                found = true;
+                break;
+            }
         }
         if (!found) {
             fail = true;
@@ -427,7 +438,6 @@ SPB_FN void rati(cplx z, real fnu, int n, Y cy, real tol, real az_known = real(-
     real fdnu = real(idnu);
     real fnup = rmax(amagz, fdnu);
     int id = idnu - magz - 1;
-    int itime = 1;
     int k = 1;
     cplx rz = crecip(z) * real(2.0);
     cplx t1 = rz * fnup;
@@ -445,7 +455,11 @@ SPB_FN void rati(cplx z, real fnu, int n, Y cy, real tol, real az_known = real(-
     p1 = p1 * rap1;
     p2 = p2 * rap1;
     ap2 = ap2 * rap1;
-    // the walk compares squared moduli (values stay below 1e20 here): one square root only when a test fires
+    // the walk compares squared moduli (values stay below 1e20 here): one square root only when a test fires.
+    // Two loops instead of one loop with a "second time" flag: the refinement of the test value (four square roots,
+    // two divisions) runs once per point, and inside a single loop every lane of a warp would reach it at its own
+    // iteration -- the block then executes once per DISTINCT iteration index in the warp instead of once (measured:
+    // a fifth of the instructions of the Wronskian kernel).  The exits of the first loop reconverge before it.
     real ap2s = ap2 * ap2, ap1s, tests = test * test;
     for (;;) {
         k += 1;
@@ -455,14 +469,24 @@ SPB_FN void rati(cplx z, real fnu, int n, Y cy, real tol, real az_known = real(-
         p1 = pt;
         t1 = t1 + rz;
         ap2s = p2.re * p2.re + p2.im * p2.im;
-        if (ap1s <= tests) continue;
-        if (itime == 2) break;
+        if (ap1s > tests) break;
+    }
+    {
         real ak = cabs_(t1) * real(0.5);
         real flam = ak + sqrt(ak * ak - real(1.0));
         real rho = rmin(sqrt(ap2s / ap1s), flam);
         test = test1 * sqrt(rho / (rho * rho - real(1.0)));
         tests = test * test;
-        itime = 2;
+    }
+    for (;;) {
+        k += 1;
+        ap1s = ap2s;
+        cplx pt = p2;
+        p2 = p1 - t1 * pt;
+        p1 = pt;
+        t1 = t1 + rz;
+        ap2s = p2.re * p2.re + p2.im * p2.im;
+        if (ap1s > tests) break;
     }
     ap2 = sqrt(ap2s);
     int kk = k + 1 - id;
