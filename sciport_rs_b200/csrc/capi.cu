@@ -58,6 +58,8 @@ long long env_log2(const char *name, int dflt, int lo, int hi) {
 const long long CHUNK_DEVICE = env_log2("SPB_CHUNK_LOG2", 24, 12, 27);
 const long long CHUNK_HOST = env_log2("SPB_HOST_CHUNK_LOG2", 22, 12, 26);
 
+constexpr int NSTREAM = 3;
+
 struct ScratchSet {
     Scratch s{};
     long long cap = 0;
@@ -83,9 +85,12 @@ struct DeviceCtx {
     int dev = -1;
     int sms = 148;
     std::mutex mu;
-    ScratchSet scratch[2];
-    StageSet stage[2];
-    cudaStream_t streams[2] = {nullptr, nullptr};
+    // host-buffer calls stage their chunks round-robin over NSTREAM streams, each with its own staging set and
+    // pipeline scratch: with two, the device-to-host engine idles whenever both streams are in their upload / compute
+    // phase; three keep both copy engines busy (config 3 pair, host buffers: 189 -> see DESIGN.md section 6)
+    ScratchSet scratch[NSTREAM];
+    StageSet stage[NSTREAM];
+    cudaStream_t streams[NSTREAM] = {};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     unsigned long long *d_packed = nullptr;
     unsigned long long *d_first = nullptr;         // [2] first failing element (packed) of the call in flight
@@ -134,8 +139,7 @@ DeviceCtx *get_ctx(int dev) {
         cudaSetDevice(dev);
         cudaDeviceProp p;
         if (cudaGetDeviceProperties(&p, dev) == cudaSuccess) c->sms = p.multiProcessorCount;
-        cudaStreamCreateWithFlags(&c->streams[0], cudaStreamNonBlocking);
-        cudaStreamCreateWithFlags(&c->streams[1], cudaStreamNonBlocking);
+        for (int b = 0; b < NSTREAM; ++b) cudaStreamCreateWithFlags(&c->streams[b], cudaStreamNonBlocking);
         cudaEventCreate(&c->ev0);
         cudaEventCreate(&c->ev1);
         cudaEventCreateWithFlags(&c->busy, cudaEventDisableTiming);
@@ -634,7 +638,7 @@ int run_host_slice(DeviceCtx *c, const BesselArgs &a, double *ms_out, int *launc
     }
     for (long long off = 0; off < a.n; off += CHUNK_HOST, ++k) {
         long long m = std::min(CHUNK_HOST, a.n - off);
-        int b = k & 1;
+        int b = k % NSTREAM;
         cudaStream_t st = c->streams[b];
         int rc = ensure_stage(c->stage[b], std::min(CHUNK_HOST, a.n), a.x != nullptr, a.v_stride != 0, a.ierr, a.nz);
         if (rc != SPB_OK) return rc;
@@ -678,8 +682,7 @@ int run_host_slice(DeviceCtx *c, const BesselArgs &a, double *ms_out, int *launc
         if (a.nz2) CK(cudaMemcpyAsync(a.nz2 + off, s.nz2, m * 4, cudaMemcpyDeviceToHost, st));
         // the staging set of this stream is reused two chunks later: stream order protects it
     }
-    CK(cudaStreamSynchronize(c->streams[0]));
-    CK(cudaStreamSynchronize(c->streams[1]));
+    for (int b = 0; b < NSTREAM; ++b) CK(cudaStreamSynchronize(c->streams[b]));
     CK(cudaGetLastError());
     CK(cudaMemcpy(c->h_first, c->d_first, 16, cudaMemcpyDeviceToHost));
     if (ms_out) *ms_out = 0.0;
@@ -703,7 +706,7 @@ int run_host_slice_seq(DeviceCtx *c, const BesselArgs &a, int *launches_out) {
     }
     for (long long off = 0; off < a.n; off += chunk, ++k) {
         long long m = std::min(chunk, a.n - off);
-        int b = k & 1;
+        int b = k % NSTREAM;
         cudaStream_t st = c->streams[b];
         StageSet &s = c->stage[b];
         int rc = ensure_stage(s, std::min(chunk, a.n), a.x != nullptr, a.v_stride != 0, a.ierr, a.nz);
@@ -751,8 +754,7 @@ int run_host_slice_seq(DeviceCtx *c, const BesselArgs &a, int *launches_out) {
         if (a.ierr) CK(cudaMemcpyAsync(a.ierr + off, s.ierr, m * 4, cudaMemcpyDeviceToHost, st));
         if (a.nz) CK(cudaMemcpyAsync(a.nz + off, s.nz, m * 4, cudaMemcpyDeviceToHost, st));
     }
-    CK(cudaStreamSynchronize(c->streams[0]));
-    CK(cudaStreamSynchronize(c->streams[1]));
+    for (int b = 0; b < NSTREAM; ++b) CK(cudaStreamSynchronize(c->streams[b]));
     CK(cudaGetLastError());
     CK(cudaMemcpy(c->h_first, c->d_first, 16, cudaMemcpyDeviceToHost));
     if (launches_out) *launches_out = launches;
@@ -837,7 +839,7 @@ int map_host_slice(DeviceCtx *c, const char *in, char *out, long long n, size_t 
     int k = 0, launches = 0;
     for (long long off = 0; off < n; off += CHUNK_HOST, ++k) {
         const long long m = std::min(CHUNK_HOST, n - off);
-        const int b = k & 1;
+        const int b = k % NSTREAM;
         cudaStream_t st = c->streams[b];
         int rc = ensure_stage(c->stage[b], std::min(CHUNK_HOST, n), false, false, false, false);
         if (rc != SPB_OK) return rc;
@@ -848,8 +850,7 @@ int map_host_slice(DeviceCtx *c, const char *in, char *out, long long n, size_t 
         CK(cudaMemcpyAsync(out + (size_t)off * out_bytes_per, sg.out, (size_t)m * out_bytes_per, cudaMemcpyDeviceToHost,
                            st));
     }
-    CK(cudaStreamSynchronize(c->streams[0]));
-    CK(cudaStreamSynchronize(c->streams[1]));
+    for (int b = 0; b < NSTREAM; ++b) CK(cudaStreamSynchronize(c->streams[b]));
     CK(cudaGetLastError());
     if (launches_out) *launches_out = launches;
     return SPB_OK;
@@ -910,7 +911,7 @@ int airy_host_slice(DeviceCtx *c, int which, int kode, int sem, const spb_c128 *
     }
     for (long long off = 0; off < n; off += CHUNK_HOST, ++k) {
         const long long m = std::min<long long>(CHUNK_HOST, n - off);
-        const int b = k & 1;
+        const int b = k % NSTREAM;
         cudaStream_t s0 = c->streams[b];
         int rc = ensure_stage(c->stage[b], std::min<long long>(CHUNK_HOST, n), false, false, true, true);
         if (rc != SPB_OK) return rc;
@@ -924,8 +925,7 @@ int airy_host_slice(DeviceCtx *c, int which, int kode, int sem, const spb_c128 *
         if (ierr) CK(cudaMemcpyAsync(ierr + off, sg.ierr, m * 4, cudaMemcpyDeviceToHost, s0));
         if (nz) CK(cudaMemcpyAsync(nz + off, sg.nz, m * 4, cudaMemcpyDeviceToHost, s0));
     }
-    CK(cudaStreamSynchronize(c->streams[0]));
-    CK(cudaStreamSynchronize(c->streams[1]));
+    for (int b = 0; b < NSTREAM; ++b) CK(cudaStreamSynchronize(c->streams[b]));
     CK(cudaGetLastError());
     CK(cudaMemcpy(c->h_first, c->d_first, 16, cudaMemcpyDeviceToHost));
     if (launches_out) *launches_out = launches;
