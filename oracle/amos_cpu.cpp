@@ -17,6 +17,7 @@
 
 #include "../sciport_rs_b200/csrc/amos/spb_family.h"
 #include "../sciport_rs_b200/csrc/amos/spb_gamma.h"
+#include "../sciport_rs_b200/csrc/amos/spb_airy_lean.h"
 
 using namespace spb;
 
@@ -289,6 +290,42 @@ int spbo_airy(int which, int kode, const double *z, double *out, int32_t *ierr, 
             out[2 * i + 1] = o.im;
             if (ierr) ierr[i] = ie;
             if (nz) nz[i] = nzz;
+        }
+    });
+    return 0;
+}
+
+// The flow of the Airy kernels: |zeta| = (2/3)|z|^(3/2) >= rl through the lean large-|zeta| routines
+// (spb_airy_lean.h; a declined point falls back to the complete routine like on the GPU), the rest through the
+// complete routines.  path[i] = 1 where the lean routine produced the value.
+int spbo_airy_flow(int which, int kode, const double *z, double *out, int32_t *ierr, int32_t *nz, int32_t *path,
+                   int64_t n, int threads) {
+    parallel_for(n, threads, [=](int64_t lo, int64_t hi) {
+        for (int64_t i = lo; i < hi; ++i) {
+            cplx zz(z[2 * i], z[2 * i + 1]);
+            cplx o(0.0, 0.0);
+            int ie = 0, nzz = 0;
+            const double az = cabs_(zz);
+            const double azeta = (2.0 / 3.0) * az * sqrt(az);
+            bool lean = az > 1.0 && azeta >= SPB_RL * (1.0 + 1.0e-9) && az < 1.0e300;
+            if (lean) {
+                if (which < 2)
+                    lean = airy_large(zz, which, kode, o, nzz, ie);
+                else
+                    o = biry_large(zz, which - 2, kode, ie);
+            }
+            if (!lean) {
+                nzz = 0;
+                if (which < 2)
+                    o = airy(zz, which, kode, nzz, ie);
+                else
+                    o = biry(zz, which - 2, kode, ie);
+            }
+            out[2 * i] = o.re;
+            out[2 * i + 1] = o.im;
+            if (ierr) ierr[i] = ie;
+            if (nz) nz[i] = nzz;
+            if (path) path[i] = lean ? 1 : 0;
         }
     });
     return 0;

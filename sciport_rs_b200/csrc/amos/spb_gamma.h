@@ -83,6 +83,25 @@ __device__ __forceinline__ void log_dd(double y, double &hi, double &lo) {
 }
 #endif
 
+#if defined(__CUDA_ARCH__)
+// Gamma(y) = exp((y - 1/2) ln y - y + ln sqrt(2 pi) + tail(y)) for 12 <= y <= 171.6, the exponent in double-double.
+// Straight-line: the whole of Gamma(x) for x >= 12 (fast path of k_real_map_queued).
+__device__ __forceinline__ double gamma_stirling_dev(double y) {
+    double lh, ll;
+    log_dd(y, lh, ll);
+    const double a = y - 0.5;  // exact
+    const double p = a * lh;
+    const double pe = fma(a, lh, -p) + a * ll;
+    const double t1 = p - y;  // |p| > y for y >= 12
+    const double te = -y - (t1 - p);
+    const double rest = ((te + pe) + stirling_tail(y)) + 0.9189385332046728;
+    const double th = t1 + rest;
+    const double tl = rest - (th - t1);
+    const double r = exp_(0.5 * th);
+    return r * fma(r, tl, r);
+}
+#endif
+
 SPB_FN real gamma_pos(real x) {
     // x > 0
     const real sq2pi = 2.50662827463100050242;
@@ -94,21 +113,7 @@ SPB_FN real gamma_pos(real x) {
         y += real(1.0);
     }
 #if defined(__CUDA_ARCH__)
-    {
-        // Gamma(y) = exp((y - 1/2) ln y - y + ln sqrt(2 pi) + tail(y)), the exponent in double-double
-        double lh, ll;
-        log_dd(y, lh, ll);
-        const double a = y - 0.5;  // exact
-        const double p = a * lh;
-        const double pe = fma(a, lh, -p) + a * ll;
-        const double t1 = p - y;  // |p| > y for y >= 12
-        const double te = -y - (t1 - p);
-        const double rest = ((te + pe) + stirling_tail(y)) + 0.9189385332046728;
-        const double th = t1 + rest;
-        const double tl = rest - (th - t1);
-        const double r = exp_(0.5 * th);
-        return (r * fma(r, tl, r)) * rcp_onscale(prod);  // 1 <= prod < 12^12
-    }
+    return gamma_stirling_dev(y) * rcp_onscale(prod);  // 1 <= prod < 12^12
 #endif
     real w = pow(y, real(0.5) * y - real(0.25));
     real g = sq2pi * exp(stirling_tail(y));
@@ -135,6 +140,13 @@ SPB_FN real gamma_real(real x) {
     }
     real g = gamma_pos(real(1.0) - x);
     return real(SPB_PI) / (s * g);
+}
+
+// ln Gamma(y) for y >= 12 by the Stirling series (straight-line: the fast path of k_real_map_queued)
+SPB_HD real lgamma_stirling(real y) {
+    const real hl2pi = 0.91893853320467274178;  // ln(2 pi)/2
+    const real ly = log_(y);
+    return (y - real(0.5)) * ly - y + hl2pi + (y < real(1.0e17) ? stirling_tail(y) : real(0.0));
 }
 
 SPB_FN real lgamma_pos(real x) {

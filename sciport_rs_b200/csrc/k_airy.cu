@@ -9,19 +9,23 @@
 // evaluated in a mixed warp.
 #include "spb_dev.cuh"
 #include "amos/spb_airy.h"
+#include "amos/spb_airy_lean.h"
 
 namespace spbk {
 
-// bins 0..5 of the I-bin field: 0 Maclaurin; 1 K series; 2 K Miller; 3 I series; 4 I Miller; 5 I asymptotic
+// bins 0..5 of the I-bin field: 0 Maclaurin; 1 K series; 2 K Miller; 3 I series; 4 I Miller; 5 large |zeta| (>= rl:
+// K and I from the large-|zeta| routines only, lean kernel); non-finite arguments go to the complete routine
 __device__ __forceinline__ unsigned int airy_key(bool bi, cplx z) {
     const double az = spb::cabs_(z);
-    if (!(az > 1.0)) return 0u;
+    if (az <= 1.0) return 0u;
     const double azeta = (2.0 / 3.0) * az * sqrt(az);
+    if (azeta >= SPB_RL * (1.0 + 1.0e-9) && az < 1.0e300) return 5u;  // (margin: the routine forms zeta itself)
+    if (!(azeta < SPB_RL)) return 4u;  // at the border, NaN, Inf: complete routine
     // Ai: K_{1/3}(zeta) directly when |arg z| <= pi/3 (Re zeta >= 0, Re z > 0); otherwise, and always for Bi,
     // through I_{+-1/3}(zeta)
     if (!bi && z.re >= 0.5 * az) return azeta > 2.0 ? 2u : 1u;
     if (azeta <= 2.0 || azeta * azeta * 0.25 <= 4.0 / 3.0) return 3u;
-    return azeta < SPB_RL ? 4u : 5u;
+    return 4u;
 }
 
 __global__ void __launch_bounds__(256) k_classify_airy(int which, const double2 *z, long long n, Scratch s) {
@@ -110,9 +114,9 @@ __global__ void __launch_bounds__(128) k_airy_sorted(int id, int kode, int sem, 
     __shared__ SortSmem sm;
     __shared__ unsigned int s_idx[SORT_B];
     __shared__ double2 s_z[SORT_B];
-    // keys 1..5 (key 0 is evaluated by k_airy_small)
+    // keys 1..4 (key 0 is evaluated by k_airy_small, key 5 by k_airy_large)
     const unsigned int start = s.bins[1] - s.bins[0];
-    const unsigned int count = (unsigned int)n - start;
+    const unsigned int count = s.bins[5] - s.bins[1];
     const unsigned int *perm = s.perm_i + start;
 #pragma unroll 1
     for (unsigned int t0 = blockIdx.x * SORT_B; t0 < count; t0 += gridDim.x * SORT_B) {
@@ -141,6 +145,53 @@ __global__ void __launch_bounds__(128) k_airy_sorted(int id, int kode, int sem, 
             }
         }
         __syncthreads();
+    }
+}
+
+// Key 5 (|zeta| >= rl, 43 % of a log-uniform batch): the large-|zeta| routines only (amos/spb_airy_lean.h), a
+// fraction of the registers of the complete routine.  Declined points (unscaled Ai in the rescaling bands) are
+// appended to the general list and evaluated by k_airy_list.
+template <bool BI>
+__global__ void __launch_bounds__(128, 4) k_airy_large(int id, int kode, int sem, const double2 *z, double2 *out,
+                                                       int *ierr, int *nz, Scratch s, unsigned long long *first_err,
+                                                       long long index_base) {
+    const unsigned int start = s.bins[5] - s.bins[0];
+    const unsigned int count = s.bins[6] - s.bins[5];
+    const unsigned int *perm = s.perm_i + start;
+    const unsigned int stride = gridDim.x * blockDim.x;
+#pragma unroll 1
+    for (unsigned int t = blockIdx.x * blockDim.x + threadIdx.x; t < count; t += stride) {
+        const unsigned int i = __ldg(perm + t);
+        const double2 zz = __ldg(z + i);
+        const cplx zc(zz.x, zz.y);
+        int ie = 0, nzz = 0;
+        cplx val;
+        if (BI) {
+            val = spb::biry_large(zc, id, kode, ie);
+        } else if (!spb::airy_large(zc, id, kode, val, nzz, ie)) {
+            s.glist[atomicAdd(&s.bins[GLIST_LEN_SLOT], 1u)] = i;
+            continue;
+        }
+        if (sem) val = spb::airy_semantics(zc, val, ie);
+        out[i] = make_double2(val.re, val.im);
+        if (ierr) ierr[i] = ie;
+        if (nz) nz[i] = nzz;
+        note_error(first_err, index_base + i, ie);
+    }
+}
+
+// the points k_airy_large declined, through the complete routine
+template <bool BI>
+__global__ void __launch_bounds__(128) k_airy_list(int id, int kode, int sem, const double2 *z, double2 *out, int *ierr,
+                                                   int *nz, Scratch s, unsigned long long *first_err,
+                                                   long long index_base) {
+    const unsigned int count = s.bins[GLIST_LEN_SLOT];
+    const unsigned int stride = gridDim.x * blockDim.x;
+#pragma unroll 1
+    for (unsigned int t = blockIdx.x * blockDim.x + threadIdx.x; t < count; t += stride) {
+        const unsigned int i = s.glist[t];
+        const double2 zz = __ldg(z + i);
+        airy_point<BI>(id, kode, sem, cplx(zz.x, zz.y), i, out, ierr, nz, first_err, index_base);
     }
 }
 
@@ -178,15 +229,21 @@ int launch_airy(int which, int kode, int sem, const double2 *z, double2 *out, in
     if (bi) {
         k_airy_small<true><<<resident_grid(k_airy_small<true>, 256, sms), 256, 0, st>>>(id, kode, sem, z, out, ierr, nz, *s,
                                                                                        first_err, index_base);
+        k_airy_large<true><<<resident_grid(k_airy_large<true>, 128, sms), 128, 0, st>>>(id, kode, sem, z, out, ierr, nz, *s,
+                                                                                       first_err, index_base);
         k_airy_sorted<true><<<resident_grid(k_airy_sorted<true>, 128, sms), 128, 0, st>>>(id, kode, sem, z, out, ierr, nz,
                                                                                          n, *s, first_err, index_base);
     } else {
         k_airy_small<false><<<resident_grid(k_airy_small<false>, 256, sms), 256, 0, st>>>(id, kode, sem, z, out, ierr, nz,
                                                                                          *s, first_err, index_base);
+        k_airy_large<false><<<resident_grid(k_airy_large<false>, 128, sms), 128, 0, st>>>(id, kode, sem, z, out, ierr, nz,
+                                                                                         *s, first_err, index_base);
         k_airy_sorted<false><<<resident_grid(k_airy_sorted<false>, 128, sms), 128, 0, st>>>(id, kode, sem, z, out, ierr,
                                                                                            nz, n, *s, first_err, index_base);
+        // (Bi never declines)
+        k_airy_list<false><<<148, 128, 0, st>>>(id, kode, sem, z, out, ierr, nz, *s, first_err, index_base);
     }
-    return 5;
+    return bi ? 6 : 7;
 }
 
 }  // namespace spbk

@@ -164,6 +164,80 @@ __global__ void __launch_bounds__(256) k_real_map(const double *x, double *out, 
     if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) out[n - 1] = gfun<WHICH>(x[n - 1]);
 }
 
+// gamma / ln|gamma|: fast path + in-kernel queue.
+// Both functions are a straight-line Stirling evaluation for x >= 12 and something longer and data-dependent below
+// (recurrence product of up to 12 factors, Maclaurin series around 1 and 2, reflection for x < 0).  On unrelated
+// inputs every warp holds a few such lanes, and the whole warp then walks every branch: ln|gamma| ran with 14.4 of 32
+// lanes active (ncu, 2^27 points in [0, 100]).  Here a CTA takes tiles of 2048 points: every thread evaluates the
+// fast path of its points at once and pushes the others (value + index) into a shared-memory queue; after a barrier
+// the queue is processed densely, 32 slow points per warp.  A point takes the fast or the slow routine by its own
+// value alone, so results do not depend on the neighbours.  One pass over memory: 8 B in, 8 B out per point.
+template <int WHICH>
+__device__ __forceinline__ bool gfast(double x, double &r) {
+#if defined(__CUDA_ARCH__)
+    if (WHICH == 0) {
+        if (!(x >= 12.0 && x <= 171.6243769563027)) return false;
+        r = spb::gamma_stirling_dev(x);
+        return true;
+    }
+    if (!(x >= 12.0 && x < 1.0e305)) return false;
+    r = spb::lgamma_stirling(x);
+    return true;
+#else
+    (void)x;
+    (void)r;
+    return false;  // (host pass of nvcc: never called)
+#endif
+}
+
+template <int WHICH>
+__global__ void __launch_bounds__(256) k_real_map_queued(const double *x, double *out, long long n) {
+    constexpr int IT = 4, TILE_PTS = 256 * 2 * IT;
+    __shared__ double qx[TILE_PTS];
+    __shared__ unsigned int qi[TILE_PTS];
+    __shared__ unsigned int qn;
+    const double2 *x2 = reinterpret_cast<const double2 *>(x);
+    double2 *o2 = reinterpret_cast<double2 *>(out);
+    const long long n2 = n >> 1;
+    const long long tiles = (n2 + 256 * IT - 1) / (256 * IT);
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        if (threadIdx.x == 0) qn = 0;
+        __syncthreads();
+        const long long base = tile * (256 * IT);
+        double2 a[IT];
+#pragma unroll
+        for (int k = 0; k < IT; ++k) {
+            const long long i = base + threadIdx.x + 256 * k;
+            a[k] = (i < n2) ? __ldg(x2 + i) : make_double2(20.0, 20.0);
+        }
+#pragma unroll
+        for (int k = 0; k < IT; ++k) {
+            const long long i = base + threadIdx.x + 256 * k;
+            double2 r;
+            const bool ok0 = gfast<WHICH>(a[k].x, r.x), ok1 = gfast<WHICH>(a[k].y, r.y);
+            if (i < n2) {
+                const unsigned int local = (unsigned int)(threadIdx.x + 256 * k) * 2u;
+                if (!ok0) {
+                    const unsigned int q = atomicAdd(&qn, 1u);
+                    qx[q] = a[k].x;
+                    qi[q] = local;
+                }
+                if (!ok1) {
+                    const unsigned int q = atomicAdd(&qn, 1u);
+                    qx[q] = a[k].y;
+                    qi[q] = local + 1u;
+                }
+                o2[i] = r;  // (queued positions are overwritten below, after the barrier)
+            }
+        }
+        __syncthreads();
+        const unsigned int m = qn;
+        for (unsigned int q = threadIdx.x; q < m; q += 256) out[2 * base + qi[q]] = gfun<WHICH>(qx[q]);
+        __syncthreads();
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) out[n - 1] = gfun<WHICH>(x[n - 1]);
+}
+
 template <int WHICH>
 __global__ void __launch_bounds__(256) k_real_map_unaligned(const double *x, double *out, long long n) {
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -177,7 +251,11 @@ static void launch_real_map(const double *x, double *out, long long n, cudaStrea
     if (blocks > 148 * 8) blocks = 148 * 8;
     if (blocks < 1) blocks = 1;
     bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
-    if (aligned)
+    if (aligned && (WHICH == 0 || WHICH == 1) && n >= 4096) {
+        // gamma / ln|gamma|: fast path + in-kernel queue, persistent grid of resident CTAs
+        const int grid = resident_grid(k_real_map_queued<WHICH>, 256, 148);
+        k_real_map_queued<WHICH><<<grid, 256, 0, st>>>(x, out, n);
+    } else if (aligned)
         k_real_map<WHICH><<<(int)blocks, 256, 0, st>>>(x, out, n);
     else
         k_real_map_unaligned<WHICH><<<(int)blocks, 256, 0, st>>>(x, out, n);

@@ -31,6 +31,7 @@ def oracle_lib():
         lib.spbo_bessel_sem.argtypes = [I, I, I, P, L, P, P, P, P, L, I]
         lib.spbo_bessel_pipeline.argtypes = [I, I, P, L, P, P, P, P, P, L, I]
         lib.spbo_airy.argtypes = [I, I, P, P, P, P, L, I]
+        lib.spbo_airy_flow.argtypes = [I, I, P, P, P, P, P, L, I]
         lib.spbo_bessel_jy_pipeline.argtypes = [I, P, L, P, P, P, P, L, I]
         lib.spbo_bessel_ik_pipeline.argtypes = [I, P, L, P, P, P, P, L, I]
         lib.spbo_bessel_seq.argtypes = [I, I, P, L, P, P, P, P, L, I, I]
@@ -123,6 +124,20 @@ def cpu_airy(which, kode, z, threads=8):
     nz = np.empty(z.shape, np.int32)
     lib.spbo_airy(which, kode, z.ctypes.data, out.ctypes.data, ierr.ctypes.data, nz.ctypes.data, z.size, threads)
     return out, ierr, nz
+
+
+def cpu_airy_flow(which, kode, z, threads=8):
+    """Airy through the flow of the GPU kernels (lean large-|zeta| routines where they apply): values, ierr, nz and
+    path (1 = lean routine)."""
+    lib = oracle_lib()
+    z = np.ascontiguousarray(z, dtype=np.complex128)
+    out = np.empty_like(z)
+    ierr = np.empty(z.shape, np.int32)
+    nz = np.empty(z.shape, np.int32)
+    path = np.empty(z.shape, np.int32)
+    lib.spbo_airy_flow(which, kode, z.ctypes.data, out.ctypes.data, ierr.ctypes.data, nz.ctypes.data, path.ctypes.data,
+                       z.size, threads)
+    return out, ierr, nz, path
 
 
 def cpu_gamma(which, x):
