@@ -138,6 +138,7 @@ int spbo_count_ops2(int fam, int kode, int fuse, const double *v, int64_t v_stri
             }
             continue;
         }
+        if (p.combine == CMB_FINAL) continue;  // decided (and stored) by the classifier
         if (p.combine == CMB_GENERAL) {
             g_ops = 0;
             general_eval(fam, zz, fnu, kode, ierr, nz);

@@ -334,12 +334,19 @@ SPB_HD unsigned int class_of(int ireg, int kreg) {
     const unsigned int bk = kreg >= 0 ? (unsigned int)kreg : 3u;
     return bi | (bk << 3);
 }
+// class byte of a prepared point (see class_byte); CMB_FINAL points carry no bin and no general flag
+SPB_HD unsigned int class_of_prep(const Prep &p) {
+    if (p.combine == CMB_FINAL) return 7u | (3u << 3);
+    if (p.combine == CMB_GENERAL) return 7u | (3u << 3) | (1u << 5);
+    return class_of(p.ireg, p.kreg);
+}
 SPB_HD unsigned int class_byte(int fam, cplx z, real fnu, int kode, int fuse, bool allow_fast = true) {
     int ireg, kreg;
     if (!(allow_fast && fast_classify(fam, z, fnu, kode, fuse, ireg, kreg))) {
         const Prep p = prepare(fam, z, fnu, kode, fuse);
-        // (CMB_FINAL: decided by prepare(); the general kernel stores it without running the drivers)
-        if (p.combine == CMB_GENERAL || p.combine == CMB_FINAL) return 7u | (3u << 3) | (1u << 5);
+        // (CMB_FINAL: decided by prepare() -- the classifier kernel stores the result itself, no bin at all)
+        if (p.combine == CMB_FINAL) return 7u | (3u << 3);
+        if (p.combine == CMB_GENERAL) return 7u | (3u << 3) | (1u << 5);
         ireg = p.ireg;
         kreg = p.kreg;
     }

@@ -144,7 +144,20 @@ __global__ void __launch_bounds__(256) k_classify(DevJob job, Scratch s) {
                 cplx z;
                 double v;
                 load_point(job, i, z, v);
-                c = spb::class_byte(job.fam, z, v, job.kode, job.fuse, false);
+                const spb::Prep p = spb::prepare(job.fam, z, v, job.kode, job.fuse);
+                c = spb::class_of_prep(p);
+                if (p.combine == spb::CMB_FINAL) {
+                    // decided here (a provable underflow of K / overflow of its continuation, unscaled K, H, Y far from
+                    // the real axis): stored at once, the point enters no bin and is never visited again
+                    cplx val(0.0, 0.0);
+                    if (job.sem && p.final_ierr == 2) {
+                        // scipy conventions for an overflow: +inf for K on the positive real axis, NaN otherwise
+                        const double inf = __longlong_as_double(0x7ff0000000000000ll);
+                        const bool pos_real = z.re >= 0.0 && z.im == 0.0;
+                        val = (job.fam == spb::FAM_K && pos_real) ? cplx(inf, 0.0) : cplx(inf - inf, inf - inf);
+                    }
+                    store_point(job, i, val, p.final_ierr, p.final_nz);
+                }
                 if (job.cellsort) s.cellkey[i] = (unsigned short)cell_of(z, v);
             } else if (job.cellsort) {
                 cplx z;
