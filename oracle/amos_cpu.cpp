@@ -313,6 +313,8 @@ int spbo_airy_flow(int which, int kode, const double *z, double *out, int32_t *i
                     lean = airy_large(zz, which, kode, o, nzz, ie);
                 else
                     o = biry_large(zz, which - 2, kode, ie);
+            } else if (az > 1.0 && azeta < SPB_RL) {
+                lean = (which < 2) ? airy_mid(zz, which, kode, o, nzz, ie) : biry_mid(zz, which - 2, kode, o, ie);
             }
             if (!lean) {
                 nzz = 0;

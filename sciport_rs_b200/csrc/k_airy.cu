@@ -28,7 +28,11 @@ __device__ __forceinline__ unsigned int airy_key(bool bi, cplx z) {
     return 4u;
 }
 
-__global__ void __launch_bounds__(256) k_classify_airy(int which, const double2 *z, long long n, Scratch s) {
+// Points whose result the range / overflow / underflow tests decide (amos/spb_airy_lean.h: airy_pretest) are stored
+// here and get no bin.
+__global__ void __launch_bounds__(256) k_classify_airy(int which, int kode, int sem, const double2 *z, double2 *out,
+                                                       int *ierr, int *nz, long long n, Scratch s,
+                                                       unsigned long long *first_err, long long index_base) {
     __shared__ unsigned int hist[NBINS];
     if (threadIdx.x < NBINS) hist[threadIdx.x] = 0;
     __syncthreads();
@@ -40,7 +44,20 @@ __global__ void __launch_bounds__(256) k_classify_airy(int which, const double2 
         long long i = base + k;
         if (i < n) {
             double2 t = __ldg(z + i);
-            unsigned int key = airy_key(which >= 2, cplx(t.x, t.y));
+            const cplx zc(t.x, t.y);
+            unsigned int key = airy_key(which >= 2, zc);
+            if (key == 5u && kode == 1) {
+                spb::AiryPre pre;
+                if (spb::airy_pretest(which >= 2, zc, kode, pre) == spb::AIRY_DONE) {
+                    cplx val(0.0, 0.0);
+                    if (sem) val = spb::airy_semantics(zc, val, pre.ierr);
+                    out[i] = make_double2(val.re, val.im);
+                    if (ierr) ierr[i] = pre.ierr;
+                    if (nz) nz[i] = pre.nz;
+                    note_error(first_err, index_base + i, pre.ierr);
+                    key = 7u;  // no bin
+                }
+            }
             s.cls[i] = (unsigned char)(key | (3u << 3));  // no K bin, not general
 #pragma unroll
             for (int b = 0; b < NB_I; ++b) cnt[b] += (key == (unsigned int)b);
@@ -105,18 +122,20 @@ __global__ void __launch_bounds__(256) k_airy_small(int id, int kode, int sem, c
     (void)index_base;
 }
 
-// persistent walk over the key-sorted index list: batches of SORT_B points staged in shared memory and grouped by
-// predicted work (spb_dev.cuh), so that the lanes of a warp run evaluations of similar length inside a region
-template <bool BI>
-__global__ void __launch_bounds__(128) k_airy_sorted(int id, int kode, int sem, const double2 *z, double2 *out,
-                                                     int *ierr, int *nz, long long n, Scratch s,
-                                                     unsigned long long *first_err, long long index_base) {
+// keys 1..4 (1 < |z|, |zeta| < rl): persistent walk over the key-sorted index list, batches of SORT_B points staged in
+// shared memory and grouped by predicted work (spb_dev.cuh), evaluated by the lean mid-range routines
+// LARGE: key 5 instead (|zeta| >= rl: the large-|zeta| routines; the length of their series falls with |zeta|)
+template <bool BI, bool LARGE = false>
+__global__ void __launch_bounds__(128, LARGE ? 4 : 3) k_airy_sorted(int id, int kode, int sem, const double2 *z,
+                                                                   double2 *out, int *ierr, int *nz, long long n,
+                                                                   Scratch s, unsigned long long *first_err,
+                                                                   long long index_base) {
     __shared__ SortSmem sm;
     __shared__ unsigned int s_idx[SORT_B];
     __shared__ double2 s_z[SORT_B];
     // keys 1..4 (key 0 is evaluated by k_airy_small, key 5 by k_airy_large)
-    const unsigned int start = s.bins[1] - s.bins[0];
-    const unsigned int count = s.bins[5] - s.bins[1];
+    const unsigned int start = s.bins[LARGE ? 5 : 1] - s.bins[0];
+    const unsigned int count = LARGE ? s.bins[6] - s.bins[5] : s.bins[5] - s.bins[1];
     const unsigned int *perm = s.perm_i + start;
 #pragma unroll 1
     for (unsigned int t0 = blockIdx.x * SORT_B; t0 < count; t0 += gridDim.x * SORT_B) {
@@ -141,46 +160,41 @@ __global__ void __launch_bounds__(128) k_airy_sorted(int id, int kode, int sem, 
             if (pos < m) {
                 const unsigned int slot = sm.order[pos];
                 const double2 zz = s_z[slot];
-                airy_point<BI>(id, kode, sem, cplx(zz.x, zz.y), s_idx[slot], out, ierr, nz, first_err, index_base);
+                const cplx zc(zz.x, zz.y);
+                const unsigned int i = s_idx[slot];
+                // 1 < |z|, |zeta| < rl: the lean routines (amos/spb_airy_lean.h); the border of the region,
+                // non-finite arguments and declined points go to the complete routine (k_airy_list)
+                const double az = spb::cabs_(zc);
+                const double azeta = (2.0 / 3.0) * az * sqrt(az);
+                int ie = 0, nzz = 0;
+                cplx val;
+                bool done;
+                if (LARGE) {
+                    done = true;  // (the classifier's key: |zeta| >= rl with a margin, finite)
+                    if (BI)
+                        val = spb::biry_large(zc, id, kode, ie);
+                    else
+                        done = spb::airy_large(zc, id, kode, val, nzz, ie);
+                } else {
+                    done = az > 1.0 && azeta < SPB_RL;
+                    if (done) done = BI ? spb::biry_mid(zc, id, kode, val, ie) : spb::airy_mid(zc, id, kode, val, nzz, ie);
+                }
+                if (!done) {
+                    s.glist[atomicAdd(&s.bins[GLIST_LEN_SLOT], 1u)] = i;
+                } else {
+                    if (sem) val = spb::airy_semantics(zc, val, ie);
+                    out[i] = make_double2(val.re, val.im);
+                    if (ierr) ierr[i] = ie;
+                    if (nz) nz[i] = nzz;
+                    note_error(first_err, index_base + i, ie);
+                }
             }
         }
         __syncthreads();
     }
 }
 
-// Key 5 (|zeta| >= rl, 43 % of a log-uniform batch): the large-|zeta| routines only (amos/spb_airy_lean.h), a
-// fraction of the registers of the complete routine.  Declined points (unscaled Ai in the rescaling bands) are
-// appended to the general list and evaluated by k_airy_list.
-template <bool BI>
-__global__ void __launch_bounds__(128, 4) k_airy_large(int id, int kode, int sem, const double2 *z, double2 *out,
-                                                       int *ierr, int *nz, Scratch s, unsigned long long *first_err,
-                                                       long long index_base) {
-    const unsigned int start = s.bins[5] - s.bins[0];
-    const unsigned int count = s.bins[6] - s.bins[5];
-    const unsigned int *perm = s.perm_i + start;
-    const unsigned int stride = gridDim.x * blockDim.x;
-#pragma unroll 1
-    for (unsigned int t = blockIdx.x * blockDim.x + threadIdx.x; t < count; t += stride) {
-        const unsigned int i = __ldg(perm + t);
-        const double2 zz = __ldg(z + i);
-        const cplx zc(zz.x, zz.y);
-        int ie = 0, nzz = 0;
-        cplx val;
-        if (BI) {
-            val = spb::biry_large(zc, id, kode, ie);
-        } else if (!spb::airy_large(zc, id, kode, val, nzz, ie)) {
-            s.glist[atomicAdd(&s.bins[GLIST_LEN_SLOT], 1u)] = i;
-            continue;
-        }
-        if (sem) val = spb::airy_semantics(zc, val, ie);
-        out[i] = make_double2(val.re, val.im);
-        if (ierr) ierr[i] = ie;
-        if (nz) nz[i] = nzz;
-        note_error(first_err, index_base + i, ie);
-    }
-}
-
-// the points k_airy_large declined, through the complete routine
+// the points the lean kernels declined, through the complete routine
 template <bool BI>
 __global__ void __launch_bounds__(128) k_airy_list(int id, int kode, int sem, const double2 *z, double2 *out, int *ierr,
                                                    int *nz, Scratch s, unsigned long long *first_err,
@@ -222,28 +236,28 @@ int launch_airy(int which, int kode, int sem, const double2 *z, double2 *out, in
             k_airy<false><<<(int)blocks, 128, 0, st>>>(id, kode, sem, z, out, ierr, nz, n, first_err, index_base);
         return 1;
     }
-    k_classify_airy<<<s->nblocks, 256, 0, st>>>(which, z, n, *s);
+    k_classify_airy<<<s->nblocks, 256, 0, st>>>(which, kode, sem, z, out, ierr, nz, n, *s, first_err, index_base);
     DevJob job{};
     job.n = n;
     launch_scan_scatter(job, *s, st);
     if (bi) {
         k_airy_small<true><<<resident_grid(k_airy_small<true>, 256, sms), 256, 0, st>>>(id, kode, sem, z, out, ierr, nz, *s,
                                                                                        first_err, index_base);
-        k_airy_large<true><<<resident_grid(k_airy_large<true>, 128, sms), 128, 0, st>>>(id, kode, sem, z, out, ierr, nz, *s,
-                                                                                       first_err, index_base);
+        k_airy_sorted<true, true><<<resident_grid(k_airy_sorted<true, true>, 128, sms), 128, 0, st>>>(
+            id, kode, sem, z, out, ierr, nz, n, *s, first_err, index_base);
         k_airy_sorted<true><<<resident_grid(k_airy_sorted<true>, 128, sms), 128, 0, st>>>(id, kode, sem, z, out, ierr, nz,
                                                                                          n, *s, first_err, index_base);
+        k_airy_list<true><<<148, 128, 0, st>>>(id, kode, sem, z, out, ierr, nz, *s, first_err, index_base);
     } else {
         k_airy_small<false><<<resident_grid(k_airy_small<false>, 256, sms), 256, 0, st>>>(id, kode, sem, z, out, ierr, nz,
                                                                                          *s, first_err, index_base);
-        k_airy_large<false><<<resident_grid(k_airy_large<false>, 128, sms), 128, 0, st>>>(id, kode, sem, z, out, ierr, nz,
-                                                                                         *s, first_err, index_base);
+        k_airy_sorted<false, true><<<resident_grid(k_airy_sorted<false, true>, 128, sms), 128, 0, st>>>(
+            id, kode, sem, z, out, ierr, nz, n, *s, first_err, index_base);
         k_airy_sorted<false><<<resident_grid(k_airy_sorted<false>, 128, sms), 128, 0, st>>>(id, kode, sem, z, out, ierr,
                                                                                            nz, n, *s, first_err, index_base);
-        // (Bi never declines)
         k_airy_list<false><<<148, 128, 0, st>>>(id, kode, sem, z, out, ierr, nz, *s, first_err, index_base);
     }
-    return bi ? 6 : 7;
+    return 7;
 }
 
 }  // namespace spbk
