@@ -20,9 +20,15 @@ __device__ __forceinline__ void load_point(const DevJob &j, long long i, cplx &z
     if (j.reflect && j.fam == spb::FAM_K) v = fabs(v);
 }
 
-// record a failing element in the call-wide "first error" word (rare path: one atomic per failing element)
+// record a failing element in the call-wide "first error" word (smallest (index, ierr) of the call).  Failing
+// elements need not be rare (a quarter of an unscaled log-uniform batch over- or underflows), and a million atomics
+// on one address serialise (measured: 0.7 ms per 4M points): the word is read first -- an L2 load; a stale value only
+// costs a redundant atomic, never a wrong result -- and the atomic is issued only by a candidate that would lower it.
 __device__ __forceinline__ void note_error(unsigned long long *slot, long long index, int ierr) {
-    if (ierr != 0 && slot) atomicMin(slot, ((unsigned long long)index << 8) | (unsigned long long)(ierr & 0xff));
+    if (ierr != 0 && slot) {
+        const unsigned long long cand = ((unsigned long long)index << 8) | (unsigned long long)(ierr & 0xff);
+        if (cand < __ldcg(slot)) atomicMin(slot, cand);
+    }
 }
 
 __device__ __forceinline__ void store_point(const DevJob &j, long long i, cplx val, int ierr, int nz) {
