@@ -393,7 +393,7 @@ def test_multi_device_slices_match_single_device(special):
     (j1, _, _), (y1, _, _) = special.bessel_jy(2.5, z)
     (jg, _, _), (yg, _, _) = special.bessel_jy(2.5, z, devices=devs)
     assert np.array_equal(j1.view(np.uint64), jg.view(np.uint64)) and np.array_equal(y1.view(np.uint64), yg.view(np.uint64))
-    zz = z.copy()
+    zz = z * 0.05  # |z| <= 10: no overflow of the unscaled functions anywhere
     zz[2_900_001] = -1.0e7  # beyond the argument range of the Airy routines: ierr 4 in the second slice
     for which in ("Ai", "Bi"):
         a1, ea1, na1 = special.airy_raw(which, zz)
