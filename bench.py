@@ -688,13 +688,14 @@ def main():
         out_bytes = 32.0  # the pair stores two results per point
         per_launch_ms = top["ms"] / max(top["launches"], 1)
         achieved = (fpe * pts / (top["ms"] * 1e-3) / 1e12) if (fpe and pts and top["ms"] > 0) else None
-        traffic = load_json("profiles", "r2_traffic.json").get("kernels", {}).get(top["name"])
+        traffic_rec = load_json("profiles", "r2_traffic.json").get("kernels", {}).get(top["name"]) or {}
+        traffic = traffic_rec.get("bytes")
         roofline = {
             "bound": "fp64", "kernel": top["name"], "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
             "frac": (achieved / fp64_peak) if achieved else None,
-            "traffic": traffic,
+            "traffic": traffic, "traffic_detail": traffic_rec or None,
             "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel from the committed "
-                            "ncu --set full capture (profiles/r2_traffic.json), null if not captured",
+                            "ncu --set full capture of one 2^24-point chunk (profiles/r2_traffic.json), null if not captured",
             "algorithmic_bytes_per_launch": (24.0 + out_bytes) * pts / max(top["launches"], 1),
             "peak_source": "spb_fp64_peak: DFMA microbenchmark of this library, 8 independent chains per thread, all "
                            "SMs, sustained 2 s on this GPU right before the timed region (MEASURED_PEAKS.json has no "
