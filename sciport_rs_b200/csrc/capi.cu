@@ -92,6 +92,7 @@ struct DeviceCtx {
     StageSet stage[NSTREAM];
     cudaStream_t streams[NSTREAM] = {};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};  // chunk interleaving of device-pointer calls (run_device)
     unsigned long long *d_packed = nullptr;
     unsigned long long *d_first = nullptr;         // [2] first failing element (packed) of the call in flight
     unsigned long long h_first[2] = {~0ull, ~0ull};  // host copy, valid once the call has completed
@@ -143,6 +144,8 @@ DeviceCtx *get_ctx(int dev) {
         cudaEventCreate(&c->ev0);
         cudaEventCreate(&c->ev1);
         cudaEventCreateWithFlags(&c->busy, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&c->fork, cudaEventDisableTiming);
+        for (int b = 0; b < 2; ++b) cudaEventCreateWithFlags(&c->join[b], cudaEventDisableTiming);
         cudaMalloc(&c->d_packed, sizeof(unsigned long long));
         cudaMalloc(&c->d_first, 2 * sizeof(unsigned long long));
         cudaMalloc(&c->d_scalar, sizeof(double2));
@@ -340,6 +343,33 @@ static int cellsort_mode() {
     return mode;
 }
 
+// SPB_INTERLEAVE (environment, read once): 1 (default) the chunks of a multi-chunk device-pointer call alternate
+// between two internal streams, each with its own pipeline scratch, forked from and joined back into the caller's
+// stream; 0 every chunk on the caller's stream.
+static bool interleave_enabled() {
+    static const bool on = [] {
+        const char *e = getenv("SPB_INTERLEAVE");
+        return !(e && atoi(e) == 0);
+    }();
+    return on;
+}
+
+static bool cellside_enabled() {
+    static const bool on = [] {
+        const char *e = getenv("SPB_CELLSIDE");
+        return !(e && atoi(e) == 0);
+    }();
+    return on;
+}
+
+static bool group_enabled() {
+    static const bool on = [] {
+        const char *e = getenv("SPB_GROUP");
+        return !(e && atoi(e) == 0);
+    }();
+    return on;
+}
+
 static bool debye_enabled() {
     static const bool on = [] {
         const char *e = getenv("SPB_DEBYE");
@@ -366,6 +396,10 @@ int enqueue_chunk(const DevJob &job_in, ScratchSet &ss, int sms, int flags, cuda
         // second-level (|z|, order) sort inside the iterative bins: SPB_CELLSORT = 0 never, 1 (default) for
         // per-element orders, 2 always
         job.cellsort = (cellsort_mode() == 2 || (cellsort_mode() == 1 && job.v_stride != 0)) ? 1 : 0;
+        // bit 1: the cell key carries the side of the family's continuation (SPB_CELLSIDE=0 switches it off)
+        if (job.cellsort && cellside_enabled()) job.cellsort |= 2;
+        // the stable-order bins (Debye-direct, fused large-|w|) take the same hint inside CTA batches (SPB_GROUP=0: off)
+        job.group = (ktype && job.v_stride != 0 && group_enabled()) ? 1 : 0;  // (I and J: no continuation in the combine step)
         job.pdl = (pdl_enabled() && job.v_stride == 0) ? 1 : 0;
     }
     if (flags & SPB_PATH_MONOLITHIC) {
@@ -520,9 +554,22 @@ int run_device(DeviceCtx *c, const BesselArgs &a, cudaStream_t st, double *ms_ou
     order_after_previous(c, st);
     CK(cudaMemsetAsync(c->d_first, 0xff, 16, st));
     CK(cudaEventRecord(c->ev0, st));
-    for (long long off = 0; off < a.n; off += CHUNK_DEVICE) {
+    // Chunk interleaving.  A chunk is a dozen dependent launches; several of them have next to no parallelism (the
+    // scans, the general path over a few hundred points, empty region bins) and every persistent region kernel ends
+    // in a tail.  Consecutive chunks are independent, so they alternate between two internal streams with a scratch
+    // set each: whatever one chunk leaves idle, the kernels of the next one fill.  Results are those of the
+    // one-stream order (every point is written by its own chunk; the first-error word is an atomic minimum).
+    const bool interleave = interleave_enabled() && !prof.on && a.n > CHUNK_DEVICE;
+    if (interleave) {
+        CK(cudaEventRecord(c->fork, st));
+        for (int b = 0; b < 2; ++b) CK(cudaStreamWaitEvent(c->streams[b], c->fork, 0));
+    }
+    int chunk_no = 0;
+    for (long long off = 0; off < a.n; off += CHUNK_DEVICE, ++chunk_no) {
         long long m = std::min(CHUNK_DEVICE, a.n - off);
-        int rc = ensure_scratch(c->scratch[0], m, st);
+        const int lane = interleave ? (chunk_no & 1) : 0;
+        cudaStream_t cst = interleave ? c->streams[lane] : st;
+        int rc = ensure_scratch(c->scratch[lane], m, cst);
         if (rc != SPB_OK) return rc;
         DevJob job{};
         job.fam = a.fn;
@@ -543,7 +590,7 @@ int run_device(DeviceCtx *c, const BesselArgs &a, cudaStream_t st, double *ms_ou
         job.first_err = c->d_first;
         job.first_err2 = c->d_first + 1;
         job.index_base = a.index_base + off;
-        launches += enqueue_chunk(job, c->scratch[0], c->sms, a.flags, st, &prof);
+        launches += enqueue_chunk(job, c->scratch[lane], c->sms, a.flags, cst, &prof);
         if (prof.on) {
             // profiling serialises the chunks so that the bin counters can be read back per chunk
             CK(cudaStreamSynchronize(st));
@@ -560,6 +607,12 @@ int run_device(DeviceCtx *c, const BesselArgs &a, cudaStream_t st, double *ms_ou
                 prof.ev.clear();
                 prof.ids.clear();
             }
+        }
+    }
+    if (interleave) {
+        for (int b = 0; b < 2; ++b) {
+            CK(cudaEventRecord(c->join[b], c->streams[b]));
+            CK(cudaStreamWaitEvent(st, c->join[b], 0));
         }
     }
     CK(cudaEventRecord(c->ev1, st));

@@ -65,6 +65,26 @@ __device__ __forceinline__ void packed_add(unsigned int c, Packed &p) {
     if (gen) p.w[2] += 1ull;
 }
 
+// Compaction only: an entry of a stable bin (large-|w|: bin 1, Debye-direct: bin 6) that carries the side bit is
+// counted in a field of its own (word 2, fields 1 and 2), so that inside a tile the bin's entries come out as
+// [side 0 in index order | side 1 in index order].  The bin totals of a tile are unchanged.
+__device__ __forceinline__ int side_field(int bi) { return bi == 1 ? 1 : 2; }
+__device__ __forceinline__ void packed_add_sided(unsigned int c, Packed &p) {
+    if (!(c & 0x40u)) {
+        packed_add(c, p);
+        return;
+    }
+    int bi, bk;
+    bool gen;
+    point_bins(c, bi, bk, gen);
+    p.w[2] += 1ull << (FIELD_BITS * side_field(bi));
+    if (bk != 3) p.w[1] += 1ull << (FIELD_BITS * (bk + 2));
+    if (gen) p.w[2] += 1ull;
+}
+__device__ __forceinline__ unsigned int field_side(const Packed &p, int bi) {
+    return (unsigned int)(p.w[2] >> (FIELD_BITS * side_field(bi))) & ((1u << FIELD_BITS) - 1u);
+}
+
 __device__ __forceinline__ unsigned int field_i(const Packed &p, int bi) {
     unsigned long long x = bi < 5 ? (p.w[0] >> (FIELD_BITS * bi)) : (p.w[1] >> (FIELD_BITS * (bi - 5)));
     return (unsigned int)x & ((1u << FIELD_BITS) - 1u);
@@ -76,15 +96,16 @@ __device__ __forceinline__ unsigned int field_g(const Packed &p) {
     return (unsigned int)p.w[2] & ((1u << FIELD_BITS) - 1u);
 }
 
-// (|z|, order) cell of a point for the second-level sort (see k_cell_hist below): 32 levels of |z|, 16 of the order
-__device__ __forceinline__ unsigned int cell_of(cplx z, double v) {
+// (side, |z|, order) cell of a point for the second-level sort (see k_cell_hist below): 32 levels of |z|, 16 of the
+// order, 2 sides
+__device__ __forceinline__ unsigned int cell_of(int fam, cplx z, double v, bool with_side) {
     const double m2 = z.re * z.re + z.im * z.im;
     const int hi = __double2hiint(m2);
     int q = 2 * ((hi >> 20) - 1023) + ((hi >> 19) & 1);  // two levels per octave of |z|^2 = four per octave of |z|
     q = q < 0 ? 0 : (q > 31 ? 31 : q);
     int b = (int)(fabs(v) * 0.25);
     b = b > 15 ? 15 : b;
-    return (unsigned int)(q | (b << 5));
+    return (unsigned int)(q | (b << 5)) | (with_side ? (side_of(fam, z) << 9) : 0u);
 }
 
 // FAM / KODE: the job's family and scaling flag as compile-time constants (dispatch_fam_kode)
@@ -158,12 +179,15 @@ __global__ void __launch_bounds__(256) k_classify(DevJob job, Scratch s) {
                     }
                     store_point(job, i, val, p.final_ierr, p.final_nz);
                 }
-                if (job.cellsort) s.cellkey[i] = (unsigned short)cell_of(z, v);
+                if (job.cellsort) s.cellkey[i] = (unsigned short)cell_of(FAM, z, v, (job.cellsort & 2) != 0);
+                // stable bins: ordering hint for the compaction (the histogram below ignores it)
+                if (job.group && ((c & 7u) == (unsigned int)spb::IREG_ASYI || (c & 7u) == (unsigned int)spb::IREG_DEBYE))
+                    c |= side_of(FAM, z) << 6;
             } else if (job.cellsort) {
                 cplx z;
                 double v;
                 load_point(job, i, z, v);
-                s.cellkey[i] = (unsigned short)cell_of(z, v);
+                s.cellkey[i] = (unsigned short)cell_of(FAM, z, v, (job.cellsort & 2) != 0);
             }
             s.cls[i] = (unsigned char)c;
             packed_add(c, cnt);
@@ -308,7 +332,7 @@ __global__ void __launch_bounds__(256) k_scatter(DevJob job, Scratch s) {
     mine.clear();
 #pragma unroll
     for (int k = 0; k < 8; ++k)
-        if (k < valid) packed_add((unsigned int)((cls8 >> (8 * k)) & 0xffu), mine);
+        if (k < valid) packed_add_sided((unsigned int)((cls8 >> (8 * k)) & 0xffu), mine);
     // block-wide exclusive scan of the packed counters (fields never exceed 2048)
     Packed incl = mine;
 #pragma unroll
@@ -345,10 +369,14 @@ __global__ void __launch_bounds__(256) k_scatter(DevJob job, Scratch s) {
         const int first = b < BIN_K0 ? 0 : b < BIN_GENERAL ? BIN_K0 : BIN_GENERAL;
         unsigned int st = 0;
         for (int k = first; k < b; ++k) st += total.field(k);
+        if (b < BIN_K0) {  // side-1 entries of the stable bins in front of bin b
+            if (b > 1) st += field_side(total, 1);
+            if (b > 6) st += field_side(total, 6);
+        }
         lstart[b] = st;
     }
     if (threadIdx.x == 0) {
-        unsigned int ti = 0, tk = 0;
+        unsigned int ti = field_side(total, 1) + field_side(total, 6), tk = 0;
         for (int k = 0; k < BIN_K0; ++k) ti += total.field(k);
         for (int k = BIN_K0; k < BIN_GENERAL; ++k) tk += total.field(k);
         seg_total[0] = ti;
@@ -363,10 +391,12 @@ __global__ void __launch_bounds__(256) k_scatter(DevJob job, Scratch s) {
         bool gen;
         point_bins((unsigned int)((cls8 >> (8 * k)) & 0xffu), bi, bk, gen);
         const unsigned int idx = (unsigned int)(base + k);
-        if (bi != 7) stage[0][lstart[bi] + field_i(off, bi)] = idx;
+        const unsigned int ck = (unsigned int)((cls8 >> (8 * k)) & 0xffu);
+        if (bi != 7)
+            stage[0][lstart[bi] + ((ck & 0x40u) ? field_i(total, bi) + field_side(off, bi) : field_i(off, bi))] = idx;
         if (bk != 3) stage[1][lstart[BIN_K0 + bk] + field_k(off, bk)] = idx;
         if (gen) stage[2][field_g(off)] = idx;
-        packed_add((unsigned int)((cls8 >> (8 * k)) & 0xffu), off);
+        packed_add_sided(ck, off);
     }
     __syncthreads();
     // coalesced write-out, one segment at a time; position j of a segment belongs to the last bin whose local
@@ -394,11 +424,12 @@ __global__ void __launch_bounds__(256) k_scatter(DevJob job, Scratch s) {
 // compaction leaves the points in index order, i.e. in random (|z|, order) order for unrelated inputs: the lanes of
 // a warp then run loops of very different lengths (measured: 20-21 of 32 lanes active in the Miller / Wronskian /
 // K kernels of config 3 even with a per-CTA batch sort of 512 points).  A counting sort of each bin segment by a
-// 9-bit cell key -- 32 levels of |z|, four per octave, times 16 levels of the order -- makes 32 consecutive
+// 10-bit cell key -- 32 levels of |z|, four per octave, times 16 levels of the order, times the side of the
+// family's continuation (side_of) -- makes 32 consecutive
 // entries near neighbours in both variables, over the whole chunk instead of a 512-point batch:
 // The classifier of a cell-sorted job stores the key of every point (2 bytes, coalesced) next to its class byte.
 //   k_cell_hist    histogram of the cell keys per bin (shared-memory histograms, one global add per cell and CTA)
-//   k_cell_scan    exclusive scan of the 512 cell counters of every bin -> cell cursors
+//   k_cell_scan    exclusive scan of the 1024 cell counters of every bin -> cell cursors
 //   k_cell_scatter batches of 1024 entries: shared-memory counts, ONE global atomic per (batch, cell) reserves the
 //                  range, entries are written to perm_i2 / perm_k2 (order inside a cell is arbitrary: results are
 //                  per point, only the memory order depends on it)

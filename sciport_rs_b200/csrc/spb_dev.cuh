@@ -128,6 +128,22 @@ __device__ __forceinline__ void batch_sort(SortSmem &sm, const unsigned int (&bu
     __syncthreads();
 }
 
+// Which side of the family's continuation a point lies on: the half of the z plane where the combine step takes the
+// analytic continuation (K, the I/K pair and the Hankel functions: K_v(w) plus the I_v(w) term, an exponential and
+// an underflow test) or, for Y and the J/Y pair, which of the two Hankel terms is the continued one.  A grouping
+// hint only (top bit of the cell key; bit 6 of the class byte, which orders the stable bins inside a tile): warps
+// that are uniform in it do not walk both forms of the combine step (measured on config 3: the combine step ran with
+// 16 of 32 lanes and took a quarter of the issue slots of the Debye-direct kernel).
+__device__ __forceinline__ unsigned int side_of(int fam, cplx z) {
+    switch (fam) {
+        case spb::FAM_H1: return z.im < 0.0 ? 1u : 0u;
+        case spb::FAM_H2: return z.im > 0.0 ? 1u : 0u;
+        case spb::FAM_Y:
+        case spb::FAM_JY: return z.im < 0.0 ? 1u : 0u;
+        default: return z.re < 0.0 ? 1u : 0u;  // I, K, the I/K pair (J: no branch depends on it)
+    }
+}
+
 // Work estimates (arbitrary units, only their order matters) -> bucket 0..31
 __device__ __forceinline__ unsigned int bucket_of(double est, double scale) {
     double b = est * scale;

@@ -14,8 +14,11 @@ struct DevJob {
     int fuse;  // spb::FUSE_ASYI (1): points needing I and K with I in the large-|w| region are evaluated by the fused
                // region kernel; spb::FUSE_DEBYE (2): the Debye-direct region (spb_debye.h) is carved out
     int pdl;   // 1: the kernels of this chunk are launched as programmatic dependents of each other (launch_pdl)
-    int cellsort;  // 1: inside the iterative region bins the point indices are sorted once more, by (|z|, order) cell
-                   // (k_pipeline.cu): the bins' kernels then read perm_i2 / perm_k2
+    int cellsort;  // bit 0: inside the iterative region bins the point indices are sorted once more, by (|z|, order) cell
+                   // (k_pipeline.cu): the bins' kernels then read perm_i2 / perm_k2; bit 1: the cell key also carries
+                   // the side of the family's continuation
+    int group;    // 1: inside a tile the compaction orders the entries of the stable bins (large-|w|, Debye-direct) by the
+                  // side of the family's continuation (side_of, spb_dev.cuh; bit 6 of the class byte), then by index
     int reflect;  // 1: orders v < 0 by the reflection formulae (K folds v -> |v| at load; the others on the general path)
     const double *v;
     long long v_stride;  // 0 = broadcast
@@ -37,7 +40,7 @@ struct DevJob {
 
 // Scratch of one chunk (device memory, owned by the per-device cache in capi.cu).
 struct Scratch {
-    unsigned char *cls;     // [n] class byte: bits 0-2 I bin (7 none), 3-4 K bin (3 none), 5 general
+    unsigned char *cls;     // [n] class byte: bits 0-2 I bin (7 none), 3-4 K bin (3 none), 5 general, 6 side (ordering hint)
     unsigned int *perm_i;   // [n] point indices sorted by I bin (stable)
     unsigned int *perm_k;   // [n] point indices sorted by K bin (stable)
     unsigned int *perm_i2;  // [n] perm_i with the segments of the iterative bins re-sorted by (|z|, order) cell
@@ -67,7 +70,7 @@ constexpr int TILE = 2048;               // points per classification tile
 // second-level sort inside a bin: 512 cells = 32 levels of |z| (four per octave, 1 <= |z| < 221) x 16 levels of the
 // order (steps of 4); slots = the bins that are sorted this way (every I bin but the Debye-direct one, whose routine
 // has no data-dependent loop; the three K bins)
-constexpr int NCELLS = 512;
+constexpr int NCELLS = 1024;
 constexpr int CELL_SLOTS = 9;
 // slots of Scratch::bins beyond the NBINS+1 start offsets
 constexpr int GLIST_LEN_SLOT = 24;  // current length of the general list (grows when a pass hands a point over)
