@@ -56,6 +56,94 @@ SPB_HD bool sweep_big(cplx a) {
 // both components below 2^-1011 = 4.6e-305 (the flush threshold, about exp(-elim))
 SPB_HD bool sweep_tiny(cplx a) { return expo_(a.re) < 12 && expo_(a.im) < 12; }
 
+// four steps of the backward recurrence; on entry and on exit p1 is the newest iterate (order rap - 1 on entry of
+// the first step), p2 the one before.  The two iterates swap roles from step to step.
+SPB_HD void sweep_group(cplx &p1, cplx &p2, cplx rz, real &rap) {
+    p2 = sweep_step(p1, rz * rap, p2);
+    rap -= real(1.0);
+    p1 = sweep_step(p2, rz * rap, p1);
+    rap -= real(1.0);
+    p2 = sweep_step(p1, rz * rap, p2);
+    rap -= real(1.0);
+    p1 = sweep_step(p2, rz * rap, p1);
+    rap -= real(1.0);
+}
+// rescaling test after a group: both iterates times 2^-200 when the newest has grown past 2^200; returns 1 then
+SPB_HD int sweep_rescale(cplx &a, cplx &b) {
+    const bool big = sweep_big(a);
+    const real sc = big ? real(SPB_SWEEP_SMALL) : real(1.0);
+    a = a * sc;
+    b = b * sc;
+    return big ? 1 : 0;
+}
+// scale of a member with j rescalings still to come, as two exact powers of two around the multiplication by the
+// normalising factor (|iterate| < 2^300, the factor may be as large as e^alim for unscaled values): neither stage can
+// overflow, and a stage that underflows belongs to a member far below the flush threshold anyway.
+// j = 0: 1;  j <= 5: s1 = 2^(-200 j);  5 < j <= 10: s1 = 2^-1000, s2 = 2^(-200 (j - 5));  beyond: zero
+SPB_HD void sweep_scales(int j, real &s1, real &s2) {
+    const int j1 = j < 5 ? j : 5;
+    s1 = pow2_(-200 * j1);
+    s2 = (j <= 5) ? real(1.0) : (j <= 10) ? pow2_(-200 * (j - 5)) : real(0.0);
+}
+// Where pass B puts its members: they come out top order first, one after the other, so the destination is a
+// cursor that steps down by one member per store.  The generic form indexes the result view; a view with a cheaper
+// way of stepping (the [order][point] device view: one pointer subtraction) specialises it.
+template <class Y>
+struct SweepCursor {
+    Y y;
+    int m;
+    SPB_HD SweepCursor(Y y_, int top) : y(y_), m(top) {}
+    SPB_HD void put(cplx v) {
+        y[m] = v;
+        --m;
+    }
+};
+
+#if defined(__CUDA_ARCH__)
+#define SPB_UNLIKELY(x) (__builtin_expect(!!(x), 0))
+#else
+#define SPB_UNLIKELY(x) (x)
+#endif
+
+// one member: value = iterate * scale * (rotated normalising factor), flushed to zero while it is a leading
+// (highest-order) member below the threshold: underflow concerns the leading members only, once one member is on
+// scale the lower orders are too (they grow towards the order |w| and oscillate at O(|w|^-1/2) below it)
+template <class C>
+SPB_HD void sweep_store(C &cur, cplx x, cplx qrot, int j, real s1, real s2, bool &leading, int &nz) {
+    cplx val = (x * s1) * qrot;
+    if (SPB_UNLIKELY(j > 5)) val = val * s2;
+    if (leading) {
+        if (sweep_tiny(val)) {
+            val = cplx(0.0, 0.0);
+            nz += 1;
+        } else {
+            leading = false;
+        }
+    }
+    cur.put(val);
+}
+
+// one group of pass B that holds members (PARTIAL: the top group of a sequence whose length is not a multiple of
+// four; its first steps belong to orders above the sequence)
+template <bool PARTIAL, class C>
+SPB_HD void sweep_store_group(C &cur, int it, int n, cplx &a, cplx &b, cplx rz, real &rap, cplx q0, cplx q1, cplx q2,
+                              cplx q3, int &j, real &s1, real &s2, bool &leading, int &nz) {
+    b = sweep_step(a, rz * rap, b);
+    rap -= real(1.0);
+    if (!PARTIAL || it + 3 < n) sweep_store(cur, b, q3, j, s1, s2, leading, nz);
+    a = sweep_step(b, rz * rap, a);
+    rap -= real(1.0);
+    if (!PARTIAL || it + 2 < n) sweep_store(cur, a, q2, j, s1, s2, leading, nz);
+    b = sweep_step(a, rz * rap, b);
+    rap -= real(1.0);
+    if (!PARTIAL || it + 1 < n) sweep_store(cur, b, q1, j, s1, s2, leading, nz);
+    a = sweep_step(b, rz * rap, a);
+    rap -= real(1.0);
+    // (the test of this group comes before its last member is stored: the member is the rescaled iterate)
+    if (sweep_rescale(a, b)) sweep_scales(--j, s1, s2);
+    sweep_store(cur, a, q0, j, s1, s2, leading, nz);
+}
+
 // y[k] = csgn0 * i^(dm k) * I_{fnu+k}(w),  Re w >= 0,  az = |w|.  The order-independent factor csgn0 is folded into
 // the normalising factor once; the per-order unit i^(dm k) is applied exactly (dm = +-1 for J, 2 for I continued
 // to the left half plane, 0 for none).  Returns nz >= 0, or -1 when it declines.
@@ -111,34 +199,26 @@ SPB_FN int isweep(cplx w, real fnu, int kode, int n, Y y, real az, cplx csgn0, i
         }
     }
     const int kk = k + 1 - id;
-    const int steps = kk + n - 1;
-    // Both passes count the recurrence by `it` = steps still to come after this one (it = steps-1 .. 0): step `it`
-    // produces the iterate of order fnu + it from the two above it, member it is stored when it < n, and the
-    // rescaling test is made whenever it is a multiple of 4 (one step grows the iterate by at most
-    // 2 (order + steps) / |w| < 2^24, so it stays below 2^300).  On the device the lanes of a warp enter the loops
-    // staggered by (largest steps of the warp - own steps) idle iterations: `it` is then warp-uniform, so the test
-    // schedule does not diverge and, in pass B, the 32 stores of one order go out in the same instruction as one
-    // coalesced 512-byte request.  Timing only: the arithmetic of a lane does not depend on its neighbours.
-    // The rescaling itself is branch-free (a multiplication by 1 or by 2^-200).
-    const int it0 = SPB_WARP_MAX(steps) - 1;
+    // The recurrence runs in GROUPS of four steps with the rescaling test after each group (one step grows the
+    // iterate by at most 2 (order + steps) / |w| < 2^24, so it stays below 2^300 in between); the start index is
+    // rounded up to a whole number of groups (a higher start only helps the ratio algorithm).  A group alternates
+    // the roles of its two iterates, so no value is moved between registers.  Both passes count the groups by
+    // g = groups still to come; step `it` = 4 g + 3 .. 4 g of a group produces the iterate of order fnu + it,
+    // member it is stored when it < n.  On the device the lanes of a warp enter pass B staggered by (largest
+    // group count of the warp - own group count) idle groups: g is then warp-uniform, so in pass B the 32 stores
+    // of one order go out in the same instruction as one coalesced 512-byte request.  Timing only: the arithmetic
+    // of a lane does not depend on its neighbours.  The rescaling itself is branch-free (a multiplication by 1
+    // or by 2^-200).
+    const int steps = (kk + n - 1 + 3) & ~3;
+    const int groups = steps >> 2;
     // ---- pass A: recurrence in registers, count the rescalings
     int etot = 0;
     cplx p1(1.0, 0.0), p2(0.0, 0.0);
     {
         real rap = fnu + real(steps);
-        for (int it = it0; it >= 0; --it) {
-            if (it >= steps) continue;
-            cplx pt = p1;
-            p1 = sweep_step(pt, rz * rap, p2);
-            p2 = pt;
-            rap -= real(1.0);
-            if ((it & 3) == 0) {
-                const bool big = sweep_big(p1);
-                const real sc = big ? real(SPB_SWEEP_SMALL) : real(1.0);
-                p1 = p1 * sc;
-                p2 = p2 * sc;
-                etot += big ? 1 : 0;
-            }
+        for (int g = groups - 1; g >= 0; --g) {
+            sweep_group(p1, p2, rz, rap);
+            etot += sweep_rescale(p1, p2);
         }
     }
     if (p1.re == real(0.0) && p1.im == real(0.0)) p1 = cplx(tol, tol);
@@ -163,52 +243,33 @@ SPB_FN int isweep(cplx w, real fnu, int kode, int n, Y y, real az, cplx csgn0, i
             return -1;
     }
     // ---- pass B: same recurrence, store each member once (top order first)
-    int m = (dm * (n - 1)) & 3;                  // unit of the top member
     int nz = 0;
     bool leading = true;
     {
-        int e = 0;
+        // member it carries the unit i^(dm it), which depends on it mod 4 only: four exactly rotated copies of the
+        // normalising factor (swaps and sign changes), one per step of a group
+        const cplx q0 = q, q1 = rot_i(q, dm & 3), q2 = rot_i(q, (2 * dm) & 3), q3 = rot_i(q, (3 * dm) & 3);
+        int j = etot;  // rescalings still to come: the true size of an iterate is 2^(-200 j) of its value
+        real s1, s2;
+        sweep_scales(j, s1, s2);
         real rap = fnu + real(steps);
         cplx a(1.0, 0.0), b(0.0, 0.0);
-        for (int it = it0; it >= 0; --it) {
-            if (it >= steps) continue;
-            cplx pt = a;
-            a = sweep_step(pt, rz * rap, b);
-            b = pt;
-            rap -= real(1.0);
-            if ((it & 3) == 0) {
-                const bool big = sweep_big(a);
-                const real sc = big ? real(SPB_SWEEP_SMALL) : real(1.0);
-                a = a * sc;
-                b = b * sc;
-                e += big ? 1 : 0;
+        const int gn = (n + 3) >> 2;  // groups that hold members
+        const int g_first = SPB_WARP_MAX(groups) - 1;
+        SweepCursor<Y> cur(y, n - 1);
+        SPB_NO_UNROLL
+        for (int g = g_first; g >= 0; --g) {
+            if (g >= groups) continue;  // (device: this lane's recurrence starts later)
+            if (g >= gn) {
+                sweep_group(a, b, rz, rap);
+                if (sweep_rescale(a, b)) sweep_scales(--j, s1, s2);
+                continue;
             }
-            if (it >= n) continue;
-            const int member = it;
-            const int j = etot - e;  // rescalings still to come: true size is 2^(-200 j) of the iterate
-            // scale in two exact stages around the multiplication by q (|iterate| < 2^300, |q| may be as large
-            // as e^alim for unscaled values): neither stage can overflow, and a stage that underflows belongs
-            // to a member far below the flush threshold anyway
-            cplx val;
-            if (j == 0) {
-                val = a * q;
-            } else {
-                const int j1 = j < 5 ? j : 5;
-                val = (a * pow2_(-200 * j1)) * q;
-                if (j > 5) val = (j <= 10) ? val * pow2_(-200 * (j - 5)) : cplx(0.0, 0.0);
-            }
-            // underflow concerns the leading (highest-order) members only: once one member is on scale the
-            // lower orders are too (they grow towards the order |w| and oscillate at O(|w|^-1/2) below it)
-            if (leading) {
-                if (sweep_tiny(val)) {
-                    val = cplx(0.0, 0.0);
-                    nz += 1;
-                } else {
-                    leading = false;
-                }
-            }
-            y[member] = rot_i(val, m);
-            m = (m - dm) & 3;
+            const int it = 4 * g;
+            if (it + 3 < n)
+                sweep_store_group<false>(cur, it, n, a, b, rz, rap, q0, q1, q2, q3, j, s1, s2, leading, nz);
+            else
+                sweep_store_group<true>(cur, it, n, a, b, rz, rap, q0, q1, q2, q3, j, s1, s2, leading, nz);
         }
     }
     return nz;

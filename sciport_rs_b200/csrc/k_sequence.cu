@@ -23,6 +23,22 @@ struct SeqStore {
     __device__ __forceinline__ Slot operator[](int k) const { return Slot{base + (long long)k * stride}; }
 };
 
+}  // namespace spbk
+
+// pass B of the sweep steps down the [order][point] column of its point: one pointer subtraction per member
+template <>
+struct spb::SweepCursor<spbk::SeqStore> {
+    double2 *p;
+    long long stride;
+    __device__ __forceinline__ SweepCursor(spbk::SeqStore y, int top) : p(y.base + (long long)top * y.stride), stride(y.stride) {}
+    __device__ __forceinline__ void put(spb::cplx v) {
+        *p = make_double2(v.re, v.im);
+        p -= stride;
+    }
+};
+
+namespace spbk {
+
 __global__ void __launch_bounds__(128) k_sweep(DevJob job, int n_orders, long long out_stride, unsigned int *list,
                                                unsigned int *list_len) {
     const long long stride = (long long)gridDim.x * blockDim.x;
