@@ -89,15 +89,14 @@ SPB_HD real atan2_onscale(real y, real x) {
 // Is (w, v) inside the calibrated region?  Squares only: m = |v^2 + w^2|^2 = |s|^4;
 //   |s| >= S0  <=>  m >= S0^4 ;   |s|^3 / v^2 >= P0  <=>  m^3 >= (P0 v^2)^4
 SPB_HD bool debye_ok(cplx w, real fnu) {
-    if (!(fnu > real(1.0))) return false;
+    // (straight-line: the classifier evaluates it for every point of the iterative regions)
     const real v2 = fnu * fnu;
     const real sr = v2 + (w.re - w.im) * (w.re + w.im), si = real(2.0) * w.re * w.im;
     const real m = sr * sr + si * si;
     const real s04 = real(SPB_DEBYE_S0 * SPB_DEBYE_S0 * SPB_DEBYE_S0 * SPB_DEBYE_S0);
-    if (!(m >= s04) || !(m < real(1.0e60))) return false;
     real q = real(SPB_DEBYE_P0) * v2;
     q = q * q;
-    return m * m * m >= q * q;
+    return (fnu > real(1.0)) & (m >= s04) & (m < real(1.0e60)) & (m * m * m >= q * q);
 }
 
 // need_i / need_k: which of the two functions the caller wants (the other output is left untouched).

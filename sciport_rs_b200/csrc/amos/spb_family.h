@@ -70,27 +70,53 @@ struct Prep {
 //           would exceed |Im w| and Re zeta2 Im zeta2 = x Im w could not hold);
 //   zeta1 = gnu ln((gnu + zeta2)/w):  gnu/az <= |(gnu + zeta2)/w| <= 1 + 2 gnu/az, so with t = az/gnu
 //           |Re zeta1| <= gnu ln(1 + 2/t + t);  pi gnu covers the branch bookkeeping of the Airy-type form;
-SPB_HD bool uoik_is_noop(real az, real gnu, real alim, real x, int kode) {
-    // scaled variants test Re(zeta2 - zeta1 - w): x <= Re zeta2 <= x + gnu, so the x terms cancel
-    if (kode != 1) x = real(0.0);
-    // cheap sufficient tests first (they cover the BASELINE configs without a division or a logarithm):
+// The classifier evaluates these tests for every point of a batch, in warps whose lanes hold unrelated points: they
+// are written as straight-line code (every predicate computed, combined with & and |, regions chosen by selection)
+// so that a warp does not walk the decision tree once per distinct path; only the logarithm of the full bound sits
+// behind a branch, taken by the rare lanes that need it.  (Measured on config 3 before this form: 435 warp
+// instructions per point, 24 of 32 lanes active.)
+SPB_HD bool uoik_noop_cheap(real az, real gnu, real alim, real x) {
+    // cheap sufficient tests (they cover the BASELINE configs without a division or a logarithm):
     // for 1/64 <= t = az/gnu <= 64, ln(1 + 2/t + t) <= ln(129.02) < 4.8601, so b < 9.0017 gnu + x;
     // for 2^-20 <= t <= 2^20, ln(1 + 2/t + t) < 15.3
-    if (az >= gnu * real(0.015625) && az <= gnu * real(64.0) && gnu * real(9.0017) + x < alim) return true;
-    if (az >= gnu * real(9.5367431640625e-07) && az <= gnu * real(1048576.0) &&
-        gnu * real(19.5) + x < alim)
-        return true;
+    const bool a = (az >= gnu * real(0.015625)) & (az <= gnu * real(64.0)) & (gnu * real(9.0017) + x < alim);
+    const bool b = (az >= gnu * real(9.5367431640625e-07)) & (az <= gnu * real(1048576.0)) &
+                   (gnu * real(19.5) + x < alim);
+    return a | b;
+}
+SPB_HD bool uoik_noop_full(real az, real gnu, real alim, real x) {
     real t = az / gnu;
     real b = gnu * (log(real(1.0) + real(2.0) / t + t) + real(SPB_PI) + real(1.0)) + x;
     return b < alim;
 }
+SPB_HD bool uoik_is_noop(real az, real gnu, real alim, real x, int kode) {
+    // scaled variants test Re(zeta2 - zeta1 - w): x <= Re zeta2 <= x + gnu, so the x terms cancel
+    if (kode != 1) x = real(0.0);
+    bool ok = uoik_noop_cheap(az, gnu, alim, x);
+    if (!ok) ok = uoik_noop_full(az, gnu, alim, x);
+    return ok;
+}
 
 SPB_HD int kregion(cplx w, real fnu, real az_known = real(-1.0)) {
-    int inu = (int)(fnu + real(0.5));
-    real dnu = fnu - real(inu);
-    if (rabs(dnu) == real(0.5)) return KREG_HALF;
-    if (!((az_known >= real(0.0) ? az_known : cabs_(w)) > real(2.0))) return KREG_SERIES;
-    return KREG_MILLER;
+    const int inu = (int)(fnu + real(0.5));
+    const real dnu = fnu - real(inu);
+    const real az = az_known >= real(0.0) ? az_known : cabs_(w);
+    const int r = (az > real(2.0)) ? KREG_MILLER : KREG_SERIES;
+    return (rabs(dnu) == real(0.5)) ? KREG_HALF : r;
+}
+
+// binu_region() (spb_binu.h) for a single member, by selection: same comparisons, same result
+SPB_HD int binu_region_sel(cplx z, real fnu, real rl, real fnul, real az) {
+    const bool series = (az <= real(2.0)) | !(az * az * real(0.25) > fnu + real(1.0));
+    const bool big = !(az < rl);
+    const bool low_order = fnu <= real(1.0);
+    const bool asy = big & (low_order | !(az + az < fnu * fnu));
+    const bool direct = !big & low_order;
+    const bool uni = (fnu > fnul) | (az > fnul);
+    const bool form1 = !(rabs(z.im) > rabs(z.re) * real(1.7321));
+    const int r_uni = form1 ? IREG_UNI1 : (wrsk_instead_of_uni2(az, fnu, fnul) ? IREG_WRSK : IREG_UNI2);
+    const int r_rest = (az > rl) ? IREG_WRSK : IREG_MLRI;
+    return series ? IREG_SERIES : asy ? IREG_ASYI : direct ? IREG_MLRI : uni ? r_uni : r_rest;
 }
 
 // Is the I evaluation at (w, fnu) simple, and in which region?  debye: carve the Debye-direct region out of the
@@ -98,19 +124,19 @@ SPB_HD int kregion(cplx w, real fnu, real az_known = real(-1.0)) {
 // which also keeps the exponent of the expansion on the middle scaling level).
 SPB_HD int iregion_simple(cplx w, real fnu, real az, bool &simple, int kode, bool debye = false) {
     const real rl = SPB_RL, fnul = SPB_FNUL, alim = SPB_ALIM;
-    int r = binu_region(w, fnu, 1, rl, fnul, az);
-    simple = true;
-    if (r == IREG_MLRI || r == IREG_WRSK || r == IREG_UNI1 || r == IREG_UNI2) {
-        // these are entered through uoik(ikflg=1) unless dfnu <= 1 took the direct Miller route
-        bool direct = (r == IREG_MLRI) && (az < rl) && (fnu <= real(1.0));
-        if (!direct && !uoik_is_noop(az, rmax(fnu, real(1.0)), alim, rabs(w.re), kode)) simple = false;
-    }
-    if (r == IREG_WRSK) {
-        // second pre-test on K_fnu, K_fnu+1
-        if (!uoik_is_noop(az, rmax(fnu + real(1.0), real(2.0)), alim, rabs(w.re), kode)) simple = false;
-    }
-    if (debye && simple && r >= IREG_MLRI && r <= IREG_UNI2 && debye_ok(w, fnu)) r = IREG_DEBYE;
-    return r;
+    const int r = binu_region_sel(w, fnu, rl, fnul, az);
+    const bool iterative = (r >= IREG_MLRI) & (r <= IREG_UNI2);
+    // these are entered through uoik(ikflg=1) unless dfnu <= 1 took the direct Miller route
+    const bool direct = (r == IREG_MLRI) & (az < rl) & (fnu <= real(1.0));
+    const bool need1 = iterative & !direct;
+    const bool need2 = (r == IREG_WRSK);  // second pre-test on K_fnu, K_fnu+1
+    const real x = (kode != 1) ? real(0.0) : rabs(w.re);
+    const real gnu1 = rmax(fnu, real(1.0)), gnu2 = rmax(fnu + real(1.0), real(2.0));
+    bool ok1 = uoik_noop_cheap(az, gnu1, alim, x), ok2 = uoik_noop_cheap(az, gnu2, alim, x);
+    if (need1 & !ok1) ok1 = uoik_noop_full(az, gnu1, alim, x);
+    if (need2 & !ok2) ok2 = uoik_noop_full(az, gnu2, alim, x);
+    simple = (!need1 | ok1) & (!need2 | ok2);
+    return (debye & simple & iterative & debye_ok(w, fnu)) ? IREG_DEBYE : r;
 }
 
 // Geometry of a family at z: the right-half-plane evaluation point w, the continuation direction and the way the
@@ -180,9 +206,9 @@ SPB_FN Prep prepare(int fam, cplx z, real fnu, int kode, int fuse = 0) {
     // anything unusual (invalid input, NaN, huge or tiny arguments) goes to the driver
     real az = cabs_(z);
     p.az = az;
-    if (!(fnu >= real(0.0)) || !(az == az) || !(az < real(32767.0)) || !(fnu < real(32767.0))) return p;
+    const bool odd = !(fnu >= real(0.0)) | !(az == az) | !(az < real(32767.0)) | !(fnu < real(32767.0));
     if (fam == FAM_J || fam == FAM_I) {
-        if (az == real(0.0)) return p;
+        if (odd | (az == real(0.0))) return p;
         prepare_geometry(fam, z, p);
         p.combine = CMB_GENERAL;
         bool simple;
@@ -191,11 +217,24 @@ SPB_FN Prep prepare(int fam, cplx z, real fnu, int kode, int fuse = 0) {
         return p;
     }
     // K-type families
-    if (az < real(1.0e-290) || fnu > fnul) return p;
-    if (!(fnu > real(2.0)) && fnu > real(1.0) && !(az > tol)) return p;
+    if (odd | (az < real(1.0e-290)) | (fnu > fnul) | (!(fnu > real(2.0)) & (fnu > real(1.0)) & !(az > tol))) return p;
     const bool left = prepare_geometry(fam, z, p);
     // over/underflow pre-test of the K drivers (made at the rotated point) must be a no-op
-    if (fnu > real(2.0) && !uoik_is_noop(az, rmax(fnu, real(1.0)), alim, rabs(p.w.re), kode)) {
+    const real gnu1 = rmax(fnu, real(1.0));
+    const bool final_fam = (kode == 1) & ((fam == FAM_K) | (fam == FAM_H1) | (fam == FAM_H2) | (fam == FAM_Y));
+    // Far beyond the underflow limit the outcome below is decided without the logarithm: for 2^-20 <= |w|/gnu <= 2^20
+    // ln(1 + 2/t + t) < 15.3, so |Re w| - gnu (15.3 + pi) > elim implies the provable-underflow test of the block
+    // below (and |Re w| > elim > alim makes every form of the no-op test fail, so the block is entered).  On an
+    // unscaled log-uniform batch one point in seven is of this kind.
+    if (final_fam & (fnu > real(2.0)) & (az >= gnu1 * real(9.5367431640625e-07)) & (az <= gnu1 * real(1048576.0)) &
+        (rabs(p.w.re) - gnu1 * real(18.4416) > real(SPB_ELIM))) {
+        const bool overflow = (p.combine == CMB_ACON) || fam == FAM_Y;
+        p.combine = CMB_FINAL;
+        p.final_ierr = overflow ? 2 : 0;
+        p.final_nz = overflow ? 0 : 1;
+        return p;
+    }
+    if (fnu > real(2.0) && !uoik_is_noop(az, gnu1, alim, rabs(p.w.re), kode)) {
         // ... or provably an underflow of K_v(w): Re(zeta2 - zeta1) >= |Re w| - gnu (ln(1 + 2/t + t) + pi) > elim makes
         // the pre-test zero the whole (single-member) sequence.  The K and Hankel drivers then return 0 with nz = 1
         // in the right half plane and report an overflow (ierr = 2) in the left one, where the vanished K would
@@ -217,30 +256,26 @@ SPB_FN Prep prepare(int fam, cplx z, real fnu, int kode, int fuse = 0) {
         p.combine = CMB_GENERAL;
         return p;
     }
-    p.kreg = kregion(p.w, fnu, az);
+    const int kreg = kregion(p.w, fnu, az);
+    const bool debye_on = (fuse & FUSE_DEBYE) != 0;
+    bool simple;
+    const int ri = iregion_simple(p.w, fnu, az, simple, kode, debye_on);
     if (left) {
-        bool simple;
-        p.ireg = iregion_simple(p.w, fnu, az, simple, kode, (fuse & FUSE_DEBYE) != 0);
-        if (!simple) {
-            p.combine = CMB_GENERAL;
-            p.ireg = -1;
-            p.kreg = -1;
-        } else if (((fuse & FUSE_ASYI) && p.ireg == IREG_ASYI) || p.ireg == IREG_DEBYE ||
-                   ((fuse & FUSE_WRSK) && p.ireg == IREG_WRSK)) {
-            p.kreg = KREG_FUSED;  // I and K from one evaluation (large-|w| series / Debye expansion / Wronskian route)
-        }
+        // I and K from one evaluation (large-|w| series / Debye expansion / Wronskian route): no K bin
+        const bool fused = (((fuse & FUSE_ASYI) != 0) & (ri == IREG_ASYI)) | (ri == IREG_DEBYE) |
+                           (((fuse & FUSE_WRSK) != 0) & (ri == IREG_WRSK));
+        p.combine = simple ? p.combine : (int)CMB_GENERAL;
+        p.ireg = simple ? ri : -1;
+        p.kreg = simple ? (fused ? (int)KREG_FUSED : kreg) : -1;
     } else {
         // I_v(w) is not needed here, but the point lies in a region where one of the single-evaluation routines
         // gives K at a fraction of the cost of the Miller algorithm + forward recurrence: same bin, the combine
         // step ignores I
-        const int r = binu_region(p.w, fnu, 1, SPB_RL, SPB_FNUL, az);
-        if ((fuse & FUSE_ASYI) && r == IREG_ASYI) {
-            p.ireg = IREG_ASYI;
-            p.kreg = KREG_FUSED;
-        } else if ((fuse & FUSE_DEBYE) && r >= IREG_MLRI && r <= IREG_UNI2 && debye_ok(p.w, fnu)) {
-            p.ireg = IREG_DEBYE;
-            p.kreg = KREG_FUSED;
-        }
+        const int r = binu_region_sel(p.w, fnu, SPB_RL, SPB_FNUL, az);
+        const bool asy = ((fuse & FUSE_ASYI) != 0) & (r == IREG_ASYI);
+        const bool dby = !asy & debye_on & (r >= IREG_MLRI) & (r <= IREG_UNI2) & debye_ok(p.w, fnu);
+        p.ireg = asy ? (int)IREG_ASYI : dby ? (int)IREG_DEBYE : -1;
+        p.kreg = (asy | dby) ? (int)KREG_FUSED : kreg;
     }
     return p;
 }

@@ -146,12 +146,20 @@ __global__ void __launch_bounds__(256) k_classify(DevJob job, Scratch s) {
 #pragma unroll
         for (int q = 0; q < PER_THREAD / 4; ++q) cls4[q] = 0;
         const spb::FastOrder fo = spb::fast_order(vk[0]);  // a broadcast order: its half of the test once per thread
+        // A warp whose first point is not accepted as a whole (a batch of unrelated points, not a grid) skips the
+        // fast test for its other seven points: on such batches the test practically never succeeds for 32 lanes
+        // at once and would only add its cost to every point (config 4: a quarter of the classifier's time).
+        bool try_fast = true;
 #pragma unroll
         for (int k = 0; k < PER_THREAD; ++k) {
-            int ireg, kreg;
-            const bool ok = spb::fast_classify(job.fam, cplx(zk[k].x, zk[k].y), fo, job.kode, job.fuse, ireg, kreg);
             unsigned int c = 0xffu;
-            if (__all_sync(0xffffffffu, ok)) c = spb::class_of(ireg, kreg);
+            if (try_fast) {
+                int ireg, kreg;
+                const bool ok = spb::fast_classify(job.fam, cplx(zk[k].x, zk[k].y), fo, job.kode, job.fuse, ireg, kreg);
+                const bool all = __all_sync(0xffffffffu, ok);
+                if (all) c = spb::class_of(ireg, kreg);
+                if (k == 0 && !all) try_fast = false;
+            }
             cls4[k / 4] |= c << (8 * (k % 4));
         }
     }
