@@ -234,6 +234,20 @@ static __constant__ double EXPO[6] = {1.6059043836821613e-10, 2.505210838544172e
 static __constant__ double LOGC[7] = {1.46437581696042513e-01, 1.53294900617389485e-01, 1.81829569361832921e-01,
                                       2.22222101946705108e-01, 2.85714286317930388e-01, 3.99999999998865485e-01,
                                       6.66666666666666963e-01};
+// Full-precision scalar constants of the routines below.  A 64-bit literal whose low word is not zero costs two
+// moves into a register pair in front of every instruction that uses it (measured: a quarter of the instructions of
+// the real gamma kernel, 6 % of the Debye-direct kernel); as an element of a __constant__ array it is a constant-bank
+// operand of that instruction.
+enum {
+    K_LOG2E, K_NLN2_HI, K_NLN2_LO,          // exp: 1/ln 2, -ln 2 in two parts
+    K_LN2_HEAD, K_LN2_TAIL, K_SQRT2,        // log: ln 2 as a 40-bit head + tail, the mantissa split point
+    K_TWO_O_PI, K_NPIO2_A, K_NPIO2_B, K_NPIO2_C,  // sincos: 2/pi, -pi/2 in three parts
+    K_COUNT
+};
+static __constant__ double K[K_COUNT] = {
+    1.4426950408889634, -0.6931471805599453, -2.3190468138462996e-17,
+    0.6931471805592082, 7.371002565167799e-13, 1.4142135623730951,
+    0.6366197723675814, -1.5707963267948966, -6.123233995736766e-17, 1.4973849048591698e-33};
 }  // namespace fm
 #endif
 
@@ -288,7 +302,7 @@ __device__ __forceinline__ double log_core(double f, int e) {
     const double hfsq = 0.5 * f * f;
     const double l1 = f - (hfsq - s * fma(u, p, hfsq));
     const double fe = (double)e;
-    return fma(fe, 0.6931471805592082, fma(fe, 7.371002565167799e-13, l1));  // ln 2 = 40-bit head + tail
+    return fma(fe, fm::K[fm::K_LN2_HEAD], fma(fe, fm::K[fm::K_LN2_TAIL], l1));  // ln 2 = 40-bit head + tail
 }
 #endif
 SPB_HD real log_(real x) {
@@ -297,7 +311,7 @@ SPB_HD real log_(real x) {
     if ((unsigned int)(hi - 0x00100000) >= 0x7fe00000u) return log_library(x);
     int e = (hi >> 20) - 1023;
     double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));  // [1, 2)
-    const bool upper = m > 1.4142135623730951;
+    const bool upper = m > fm::K[fm::K_SQRT2];
     m = upper ? m * 0.5 : m;
     e = upper ? e + 1 : e;
     return log_core(m - 1.0, e);
@@ -323,11 +337,11 @@ SPB_HD void sincos_(real x, real &s, real &c) {
         sincos_library(x, &s, &c);
         return;
     }
-    const int n = __double2int_rn(x * 0.6366197723675814);
+    const int n = __double2int_rn(x * fm::K[fm::K_TWO_O_PI]);
     const double fn = (double)n;
-    double r = fma(fn, -1.5707963267948966, x);
-    r = fma(fn, -6.123233995736766e-17, r);
-    r = fma(fn, 1.4973849048591698e-33, r);
+    double r = fma(fn, fm::K[fm::K_NPIO2_A], x);
+    r = fma(fn, fm::K[fm::K_NPIO2_B], r);
+    r = fma(fn, fm::K[fm::K_NPIO2_C], r);
     const double u = r * r;
     double ps = fm::SINC[0], pc = fm::COSC[0];
 #pragma unroll
@@ -360,10 +374,10 @@ SPB_HD void sincos_(real x, real &s, real &c) {
 __device__ __forceinline__ void exp_pair_dev(double x, double &ep, double &em) {
     x = x < -746.0 ? -746.0 : x;  // (comparisons, not fmin / fmax: a NaN passes through and comes out as NaN)
     x = x > 746.0 ? 746.0 : x;
-    const int k = __double2int_rn(x * 1.4426950408889634);
+    const int k = __double2int_rn(x * fm::K[fm::K_LOG2E]);
     const double fk = (double)k;
-    double r = fma(fk, -0.6931471805599453, x);
-    r = fma(fk, -2.3190468138462996e-17, r);
+    double r = fma(fk, fm::K[fm::K_NLN2_HI], x);
+    r = fma(fk, fm::K[fm::K_NLN2_LO], r);
     const double u = r * r;
     double pe = fm::EXPE[0], po = fm::EXPO[0];
 #pragma unroll

@@ -13,16 +13,50 @@
 
 namespace spb {
 
-// sum_{k>=1} B_2k / (2k(2k-1) x^(2k-1)),  x >= 12
+#if defined(__CUDACC__)
+// device copies of the constants of the real gamma / ln|gamma| kernels (constant-bank operands, see fm::K)
+namespace gm {
+enum { LN2_HI21 = 0, LN2_LO21, HL2PI, ATANH0, STIRLING0 = ATANH0 + 11, COUNT = STIRLING0 + 9 };
+static __constant__ double K[COUNT] = {
+    0.6931471803691238, 1.9082149292705877e-10,  // ln 2: head with 21 trailing zero bits, tail
+    0.91893853320467274178,                       // ln(2 pi)/2
+    // 2/(2k+1), k = 11 .. 1: series of 2 atanh(s)/s - 2 in s^2, highest power first
+    0.08695652173913043, 0.09523809523809523, 0.10526315789473684, 0.11764705882352941, 0.13333333333333333,
+    0.15384615384615385, 0.18181818181818182, 0.2222222222222222, 0.2857142857142857, 0.4, 0.6666666666666666,
+    // B_2k / (2k (2k-1)), k = 1 .. 9
+    8.33333333333333333333e-2, -2.77777777777777777778e-3, 7.93650793650793650794e-4, -5.95238095238095238095e-4,
+    8.41750841750841750842e-4, -1.91752691752691752692e-3, 6.41025641025641025641e-3, -2.95506535947712418301e-2,
+    1.79644372368830573165e-1};
+}  // namespace gm
+// the Maclaurin tables of ln Gamma(1 + t) once more at namespace scope, in constant memory
+namespace gmt {
+#pragma push_macro("SPB_TABLE")
+#undef SPB_TABLE
+#define SPB_TABLE(name, n) static __constant__ double name[n]
+#include "spb_tables_gamma.inc"
+#pragma pop_macro("SPB_TABLE")
+}  // namespace gmt
+#endif
+
+// sum_{k>=1} B_2k / (2k(2k-1) x^(2k-1)),  x >= 12.  TERMS: 9 everywhere on the host; the device kernels sum what
+// their result needs at x >= 12, where the k-th term is below 6.9e-3 / 144^(k-1): 7 terms leave 1.9e-18 (the
+// exponent of Gamma), 6 terms 6e-17 (ln|Gamma| >= 17.5 there)
+template <int TERMS = 9>
 SPB_HD real stirling_tail(real x) {
-#include "spb_tables_gln.inc"
-    (void)GLN;
     real r = rcp_fast(x);  // x >= 12
     real r2 = r * r;
-    real s = real(CF[8]);
+#if defined(__CUDA_ARCH__)
+    real s = gm::K[gm::STIRLING0 + TERMS - 1];
 #pragma unroll
+    for (int k = TERMS - 2; k >= 0; --k) s = fma(s, r2, gm::K[gm::STIRLING0 + k]);
+    return s * r;
+#else
+#include "spb_tables_gln.inc"
+    (void)GLN;
+    real s = real(CF[8]);
     for (int k = 7; k >= 0; --k) s = s * r2 + real(CF[k]);
     return s * r;
+#endif
 }
 
 SPB_HD real sinpi_(real x) {
@@ -50,10 +84,9 @@ __device__ __forceinline__ void log_dd(double y, double &hi, double &lo) {
     int e = (hx >> 20) - 1023;
     hx = (hx & 0x000fffff) | 0x3ff00000;
     double m = __hiloint2double(hx, lx);
-    if (m > 1.4142135623730951) {
-        m *= 0.5;
-        e += 1;
-    }
+    const bool upper = m > fm::K[fm::K_SQRT2];
+    m = upper ? m * 0.5 : m;
+    e = upper ? e + 1 : e;
     const double f = m - 1.0;            // exact
     const double dh = m + 1.0;           // may round: keep the residual
     const double dl = m - (dh - 1.0);
@@ -61,25 +94,17 @@ __device__ __forceinline__ void log_dd(double y, double &hi, double &lo) {
     const double sh = f * r;
     const double sl = (fma(-sh, dh, f) - sh * dl) * r;
     const double s2 = sh * sh;
-    double p = 0.08695652173913043;      // 2/23
-    p = fma(p, s2, 0.09523809523809523);
-    p = fma(p, s2, 0.10526315789473684);
-    p = fma(p, s2, 0.11764705882352941);
-    p = fma(p, s2, 0.13333333333333333);
-    p = fma(p, s2, 0.15384615384615385);
-    p = fma(p, s2, 0.18181818181818182);
-    p = fma(p, s2, 0.2222222222222222);
-    p = fma(p, s2, 0.2857142857142857);
-    p = fma(p, s2, 0.4);
-    p = fma(p, s2, 0.6666666666666666);
+    double p = gm::K[gm::ATANH0];  // 2/23
+#pragma unroll
+    for (int k = 1; k < 11; ++k) p = fma(p, s2, gm::K[gm::ATANH0 + k]);
     const double mh = sh + sh;
     const double ml = fma(sh * s2, p, sl + sl);
     const double fe = (double)e;
-    const double eh = fe * 0.6931471803691238;  // exact: 21 trailing zero bits
+    const double eh = fe * gm::K[gm::LN2_HI21];  // exact: 21 trailing zero bits
     const double t = eh + mh;                    // |eh| >= |mh| unless e == 0 (then t == mh exactly)
     const double err = mh - (t - eh);
     hi = t;
-    lo = err + fma(fe, 1.9082149292705877e-10, ml);
+    lo = err + fma(fe, gm::K[gm::LN2_LO21], ml);
 }
 #endif
 
@@ -94,7 +119,7 @@ __device__ __forceinline__ double gamma_stirling_dev(double y) {
     const double pe = fma(a, lh, -p) + a * ll;
     const double t1 = p - y;  // |p| > y for y >= 12
     const double te = -y - (t1 - p);
-    const double rest = ((te + pe) + stirling_tail(y)) + 0.9189385332046728;
+    const double rest = ((te + pe) + stirling_tail<7>(y)) + gm::K[gm::HL2PI];
     const double th = t1 + rest;
     const double tl = rest - (th - t1);
     const double r = exp_(0.5 * th);
@@ -144,13 +169,22 @@ SPB_FN real gamma_real(real x) {
 
 // ln Gamma(y) for y >= 12 by the Stirling series (straight-line: the fast path of k_real_map_queued)
 SPB_HD real lgamma_stirling(real y) {
+#if defined(__CUDA_ARCH__)
+    const real ly = log_(y);
+    return (y - real(0.5)) * ly - y + gm::K[gm::HL2PI] + (y < real(1.0e17) ? stirling_tail<6>(y) : real(0.0));
+#else
     const real hl2pi = 0.91893853320467274178;  // ln(2 pi)/2
     const real ly = log_(y);
     return (y - real(0.5)) * ly - y + hl2pi + (y < real(1.0e17) ? stirling_tail(y) : real(0.0));
+#endif
 }
 
 SPB_FN real lgamma_pos(real x) {
+#if defined(__CUDA_ARCH__)
+    using gmt::LG1;
+#else
 #include "spb_tables_gamma.inc"
+#endif
     const real euler1 = 0.42278433509846713939;  // 1 - Euler's constant
     const real hl2pi = 0.91893853320467274178;   // ln(2 pi)/2
     if (x > real(2.5)) {
