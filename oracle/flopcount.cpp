@@ -87,9 +87,13 @@ int spbo_count_ops2(int fam, int kode, int fuse, const double *v, int64_t v_stri
         counted fnu(v[i * v_stride]);
         g_ops = 0;
         Prep p = prepare(fam, zz, fnu, kode, fuse);
-        uint64_t prep_ops = g_ops;
-        ops[0] += prep_ops;
+        ops[0] += g_ops;
         pts[0] += 1;
+        // a region kernel recomputes the geometry of its point only (prepare_pass: rotation and modulus), not the
+        // region tests of the classifier: that is what it is charged with
+        g_ops = 0;
+        (void)prepare_pass(fam, zz);
+        const uint64_t prep_ops = g_ops;
         int ierr, nz;
         if (fam == FAM_JY || fam == FAM_IK) {
             const bool ik = (fam == FAM_IK);
@@ -169,7 +173,7 @@ int spbo_count_ops2(int fam, int kode, int fuse, const double *v, int64_t v_stri
             ops[islot(p.ireg)] += g_ops;
             pts[islot(p.ireg)] += 1;
         } else if (p.ireg >= 0) {
-            g_ops = prep_ops;  // the region kernel recomputes prepare()
+            g_ops = prep_ops;  // the region kernel recomputes the geometry
             inz = ipass_region(p.ireg, p.w, fnu, kode, ival);
             if (inz < 0) handed = true;
             if (!handed && p.combine == CMB_I_ROT) finish(fam, p, zz, fnu, kode, ival, inz, kval, 0, ierr, nz);

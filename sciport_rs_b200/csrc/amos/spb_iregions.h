@@ -271,6 +271,36 @@ SPB_FN int asyi(cplx z, real fnu, int kode, int n, Y y, real rl, real tol, real 
 }
 
 // ---------------------------------------------------------------------------
+// `steps` steps of the backward recurrence of the Miller algorithm with the running sum of the normalising
+// (Neumann) relation.  On entry and on exit p2 is the newest iterate, p1 the one before.  Two steps per round with
+// the iterates swapping roles (no register moves, see rati_walk); an odd count starts with one step of the plain
+// form.  Same values as the one-step loop, step for step.
+SPB_HD void mlri_back(int steps, cplx &p1, cplx &p2, cplx rz, real &fkk, real fnf, real tfnf, real &bk, cplx &sum) {
+    if (steps <= 0) return;
+    if (steps & 1) {
+        const cplx pt = p2;
+        p2 = p1 + (rz * pt) * (fkk + fnf);
+        p1 = pt;
+        const real ac = bk * (real(1.0) - tfnf * rcp_fast(fkk + tfnf));  // 1 <= fkk + tfnf < 1e5
+        sum = sum + p1 * (ac + bk);
+        bk = ac;
+        fkk -= real(1.0);
+    }
+    for (int i = steps >> 1; i > 0; --i) {
+        p1 = p1 + (rz * p2) * (fkk + fnf);  // newest p2 -> newest p1
+        real ac = bk * (real(1.0) - tfnf * rcp_fast(fkk + tfnf));
+        sum = sum + p2 * (ac + bk);
+        bk = ac;
+        fkk -= real(1.0);
+        p2 = p2 + (rz * p1) * (fkk + fnf);  // newest p1 -> newest p2
+        ac = bk * (real(1.0) - tfnf * rcp_fast(fkk + tfnf));
+        sum = sum + p1 * (ac + bk);
+        bk = ac;
+        fkk -= real(1.0);
+    }
+}
+
+// ---------------------------------------------------------------------------
 // Miller algorithm normalised by a Neumann series.  nz = -2: no convergence.
 template <class Y>
 SPB_FN int mlri(cplx z, real fnu, int kode, int n, Y y, real tol, real az_known = real(-1.0)) {
@@ -372,16 +402,7 @@ SPB_FN int mlri(cplx z, real fnu, int kode, int n, Y y, real tol, real az_known 
     bk = exp_(bk);
     cplx sum(0.0, 0.0);
     int km = kk - inu;
-    for (int j = 1; j <= km; ++j) {
-        cplx pt = p2;
-        p2 = p1 + (rz * pt) * (fkk + fnf);
-        p1 = pt;
-        real a = real(1.0) - tfnf * rcp_fast(fkk + tfnf);  // 1 <= fkk + tfnf < 1e5
-        real ac = bk * a;
-        sum = sum + p1 * (ac + bk);
-        bk = ac;
-        fkk -= real(1.0);
-    }
+    mlri_back(km, p1, p2, rz, fkk, fnf, tfnf, bk, sum);
     y[n - 1] = p2;
     for (int j = 2; j <= n; ++j) {
         cplx pt = p2;
@@ -394,16 +415,7 @@ SPB_FN int mlri(cplx z, real fnu, int kode, int n, Y y, real tol, real az_known 
         fkk -= real(1.0);
         y[n - j] = p2;
     }
-    for (int j = 1; j <= ifnu; ++j) {
-        cplx pt = p2;
-        p2 = p1 + (rz * pt) * (fkk + fnf);
-        p1 = pt;
-        real a = real(1.0) - tfnf * rcp_fast(fkk + tfnf);  // 1 <= fkk + tfnf < 1e5
-        real ac = bk * a;
-        sum = sum + p1 * (ac + bk);
-        bk = ac;
-        fkk -= real(1.0);
-    }
+    mlri_back(ifnu, p1, p2, rz, fkk, fnf, tfnf, bk, sum);
     cplx pt = z;
     if (kode == 2) pt.re = 0.0;
     cplx lrz = clog_(rz);
@@ -422,6 +434,38 @@ SPB_FN int mlri(cplx z, real fnu, int kode, int n, Y y, real tol, real az_known 
     }
     for (int j = 0; j < n; ++j) y[j] = y[j] * cnorm;
     return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Forward magnitude walk of the ratio algorithm: p_next = p1 - t1 p2, t1 += rz, until the squared modulus of the
+// iterate before the newest exceeds `tests`.  On entry and on exit p2 is the newest iterate, p1 the one before it,
+// ap2s = |p2|^2 and ap1s = |p1|^2.  Two steps per round with the iterates swapping roles: the rotation
+// (pt = p2, p2 = new, p1 = pt) of the one-step form was a fifth of the instructions of the Wronskian kernel as
+// register moves; the values are those of the one-step loop, step for step.
+SPB_HD void rati_walk(cplx &p1, cplx &p2, cplx &t1, cplx rz, real &ap1s, real &ap2s, real tests, int &k) {
+    for (;;) {
+        // newest p2 -> newest p1
+        k += 1;
+        p1 = p1 - t1 * p2;
+        t1 = t1 + rz;
+        const real a1 = p1.re * p1.re + p1.im * p1.im;
+        if (ap2s > tests) {
+            // leave with the roles restored: (previous, newest) = (p2, p1)
+            const cplx pt = p1;
+            p1 = p2;
+            p2 = pt;
+            ap1s = ap2s;
+            ap2s = a1;
+            return;
+        }
+        // newest p1 -> newest p2
+        k += 1;
+        p2 = p2 - t1 * p1;
+        t1 = t1 + rz;
+        ap1s = a1;
+        ap2s = p2.re * p2.re + p2.im * p2.im;
+        if (ap1s > tests) return;
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -461,16 +505,7 @@ SPB_FN void rati(cplx z, real fnu, int n, Y cy, real tol, real az_known = real(-
     // iteration -- the block then executes once per DISTINCT iteration index in the warp instead of once (measured:
     // a fifth of the instructions of the Wronskian kernel).  The exits of the first loop reconverge before it.
     real ap2s = ap2 * ap2, ap1s, tests = test * test;
-    for (;;) {
-        k += 1;
-        ap1s = ap2s;
-        cplx pt = p2;
-        p2 = p1 - t1 * pt;
-        p1 = pt;
-        t1 = t1 + rz;
-        ap2s = p2.re * p2.re + p2.im * p2.im;
-        if (ap1s > tests) break;
-    }
+    rati_walk(p1, p2, t1, rz, ap1s, ap2s, tests, k);
     {
         real ak = cabs_(t1) * real(0.5);
         real flam = ak + sqrt(ak * ak - real(1.0));
@@ -478,16 +513,7 @@ SPB_FN void rati(cplx z, real fnu, int n, Y cy, real tol, real az_known = real(-
         test = test1 * sqrt(rho / (rho * rho - real(1.0)));
         tests = test * test;
     }
-    for (;;) {
-        k += 1;
-        ap1s = ap2s;
-        cplx pt = p2;
-        p2 = p1 - t1 * pt;
-        p1 = pt;
-        t1 = t1 + rz;
-        ap2s = p2.re * p2.re + p2.im * p2.im;
-        if (ap1s > tests) break;
-    }
+    rati_walk(p1, p2, t1, rz, ap1s, ap2s, tests, k);
     ap2 = sqrt(ap2s);
     int kk = k + 1 - id;
     real ak = real(kk);
@@ -495,12 +521,17 @@ SPB_FN void rati(cplx z, real fnu, int n, Y cy, real tol, real az_known = real(-
     real dfnu = fnu + real(n - 1);
     p1 = cplx(real(1.0) / ap2, 0.0);
     p2 = cplx(0.0, 0.0);
-    for (int i = 1; i <= kk; ++i) {
-        cplx pt = p1;
-        real rap = dfnu + t1r;
-        cplx tt = rz * rap;
-        p1 = pt * tt + p2;
+    // two steps per round, the iterates swapping roles (no register moves); an odd step count starts with one step
+    if (kk & 1) {
+        const cplx pt = p1;
+        p1 = pt * (rz * (dfnu + t1r)) + p2;
         p2 = pt;
+        t1r -= real(1.0);
+    }
+    for (int i = kk >> 1; i > 0; --i) {
+        p2 = p1 * (rz * (dfnu + t1r)) + p2;
+        t1r -= real(1.0);
+        p1 = p2 * (rz * (dfnu + t1r)) + p1;
         t1r -= real(1.0);
     }
     if (p1.re == real(0.0) && p1.im == real(0.0)) p1 = cplx(tol, tol);

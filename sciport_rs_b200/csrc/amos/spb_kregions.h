@@ -406,23 +406,33 @@ SPB_FN int bknu_body(cplx z, real fnu, int kode, int n, Y y, real tol, real elim
             p1 = cplx(0.0, 0.0);
             p2 = cplx(tol, 0.0);
             cplx cs = p2;
-            SPB_NO_UNROLL
-            for (int i = 1; i <= k; ++i) {
-                real a1 = fks - fk;
-                // a = (fks + fk) / (a1 + fhs) and rak = 2 / (fk + 1) from ONE reciprocal (a division costs as
-                // much as a dozen multiplications on the device; the Miller iteration is self-normalising, so
-                // the two extra roundings do not matter)
-                real d1 = a1 + fhs, d2 = fk + real(1.0);
-                real rr = rcp_fast(d1 * d2);  // 1 <= d1 d2 < 1e9
-                real a = (fks + fk) * (d2 * rr);
-                real rak = real(2.0) * (d1 * rr);
-                cplx cb = cplx(fk + z.re, z.im) * rak;
-                cplx pt = p2;
-                p2 = (pt * cb - p1) * a;
-                p1 = pt;
-                cs = cs + p2;
+            // One step: a = (fks + fk) / (a1 + fhs) and rak = 2 / (fk + 1) from ONE reciprocal (a division costs as
+            // much as a dozen multiplications on the device; the Miller iteration is self-normalising, so the two
+            // extra roundings do not matter); next = (newest cb - previous) a.  Two steps per round with the
+            // iterates swapping roles (the rotation pt = p2, p2 = next, p1 = pt of the one-step loop was a fifth
+            // of the K pass as register moves); an odd count starts with one step.  Same values, step for step.
+            auto miller_step = [&](const cplx &newest, cplx &previous) {
+                const real a1 = fks - fk;
+                const real d1 = a1 + fhs, d2 = fk + real(1.0);
+                const real rr = rcp_fast(d1 * d2);  // 1 <= d1 d2 < 1e9
+                const real a = (fks + fk) * (d2 * rr);
+                const real rak = real(2.0) * (d1 * rr);
+                const cplx cb = cplx(fk + z.re, z.im) * rak;
+                previous = (newest * cb - previous) * a;  // (now the newest)
+                cs = cs + previous;
                 fks = a1 - fk + real(1.0);
                 fk -= real(1.0);
+            };
+            if (k & 1) {
+                miller_step(p2, p1);
+                const cplx pt = p1;
+                p1 = p2;
+                p2 = pt;
+            }
+            SPB_NO_UNROLL
+            for (int i = k >> 1; i > 0; --i) {
+                miller_step(p2, p1);
+                miller_step(p1, p2);
             }
             // (p2/cs) = (p2/|cs|) (conj(cs)/|cs|) for better scaling
             real tm = cabs_(cs);
@@ -518,6 +528,28 @@ SPB_FN int bknu_body(cplx z, real fnu, int kode, int n, Y y, real tol, real elim
             if (regular) {
                 real p1r = CSRR(kflag);
                 real ascle = BRY(kflag);
+                if (SIMPLE) {
+                    // middle scaling level throughout: the plain recurrence, two steps per round with s1 and s2
+                    // swapping roles (no register moves); a value that leaves the level hands the point over
+                    int left = inu - inub + 1;
+                    if (left > 0 && (left & 1)) {
+                        const cplx st = s2;
+                        s2 = ck * st + s1;
+                        s1 = st;
+                        ck = ck + rz;
+                        if (rmax(rabs(s2.re), rabs(s2.im)) > ascle) handover = true;
+                    }
+                    SPB_NO_UNROLL
+                    for (int i = left >> 1; i > 0; --i) {
+                        s1 = ck * s2 + s1;
+                        ck = ck + rz;
+                        if (rmax(rabs(s1.re), rabs(s1.im)) > ascle) handover = true;
+                        s2 = ck * s1 + s2;
+                        ck = ck + rz;
+                        if (rmax(rabs(s2.re), rabs(s2.im)) > ascle) handover = true;
+                    }
+                    inub = inu + 1;  // (the general loop below has nothing left to do)
+                }
                 SPB_NO_UNROLL
                 for (int i = inub; i <= inu; ++i) {
                     cplx st = s2;

@@ -3,7 +3,7 @@
 op-counting build oracle/libspb_flopcount.so and freeze the means into profiles/flops_per_eval.json.
 
 Counting rule (binding definition of the survey): add/sub/mul = 1, div = 1, sqrt = 1, exp/log/sin/cos/atan/
-sinh/cosh = 30, pow = 60.  Each region kernel is charged prepare() + its region routine + its share of finish().
+sinh/cosh = 30, pow = 60.  The classifier is charged prepare() as it runs it (straight-line: every region predicate), each region kernel the geometry of its point (prepare_pass) + its region routine + its share of finish().
 """
 import ctypes
 import json
