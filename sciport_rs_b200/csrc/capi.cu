@@ -92,7 +92,7 @@ struct DeviceCtx {
     StageSet stage[NSTREAM];
     cudaStream_t streams[NSTREAM] = {};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};  // chunk interleaving of device-pointer calls (run_device)
+    cudaEvent_t fork = nullptr, join[NSTREAM] = {};  // chunk interleaving of device-pointer calls (run_device)
     unsigned long long *d_packed = nullptr;
     unsigned long long *d_first = nullptr;         // [2] first failing element (packed) of the call in flight
     unsigned long long h_first[2] = {~0ull, ~0ull};  // host copy, valid once the call has completed
@@ -145,7 +145,7 @@ DeviceCtx *get_ctx(int dev) {
         cudaEventCreate(&c->ev1);
         cudaEventCreateWithFlags(&c->busy, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&c->fork, cudaEventDisableTiming);
-        for (int b = 0; b < 2; ++b) cudaEventCreateWithFlags(&c->join[b], cudaEventDisableTiming);
+        for (int b = 0; b < NSTREAM; ++b) cudaEventCreateWithFlags(&c->join[b], cudaEventDisableTiming);
         cudaMalloc(&c->d_packed, sizeof(unsigned long long));
         cudaMalloc(&c->d_first, 2 * sizeof(unsigned long long));
         cudaMalloc(&c->d_scalar, sizeof(double2));
@@ -343,15 +343,16 @@ static int cellsort_mode() {
     return mode;
 }
 
-// SPB_INTERLEAVE (environment, read once): 1 (default) the chunks of a multi-chunk device-pointer call alternate
-// between two internal streams, each with its own pipeline scratch, forked from and joined back into the caller's
-// stream; 0 every chunk on the caller's stream.
-static bool interleave_enabled() {
-    static const bool on = [] {
+// SPB_INTERLEAVE (environment, read once): number of internal streams (each with its own pipeline scratch) the
+// chunks of a multi-chunk device-pointer call rotate over, forked from and joined back into the caller's stream;
+// default 2, at most NSTREAM; 0 or 1: every chunk on the caller's stream.
+static int interleave_lanes() {
+    static const int lanes = [] {
         const char *e = getenv("SPB_INTERLEAVE");
-        return !(e && atoi(e) == 0);
+        const int v = e ? atoi(e) : 2;
+        return v < 1 ? 1 : (v > NSTREAM ? NSTREAM : v);  // 0 or 1: off
     }();
-    return on;
+    return lanes;
 }
 
 static bool cellside_enabled() {
@@ -559,15 +560,16 @@ int run_device(DeviceCtx *c, const BesselArgs &a, cudaStream_t st, double *ms_ou
     // in a tail.  Consecutive chunks are independent, so they alternate between two internal streams with a scratch
     // set each: whatever one chunk leaves idle, the kernels of the next one fill.  Results are those of the
     // one-stream order (every point is written by its own chunk; the first-error word is an atomic minimum).
-    const bool interleave = interleave_enabled() && !prof.on && a.n > CHUNK_DEVICE;
+    const int lanes = (!prof.on && a.n > CHUNK_DEVICE) ? interleave_lanes() : 1;
+    const bool interleave = lanes > 1;
     if (interleave) {
         CK(cudaEventRecord(c->fork, st));
-        for (int b = 0; b < 2; ++b) CK(cudaStreamWaitEvent(c->streams[b], c->fork, 0));
+        for (int b = 0; b < lanes; ++b) CK(cudaStreamWaitEvent(c->streams[b], c->fork, 0));
     }
     int chunk_no = 0;
     for (long long off = 0; off < a.n; off += CHUNK_DEVICE, ++chunk_no) {
         long long m = std::min(CHUNK_DEVICE, a.n - off);
-        const int lane = interleave ? (chunk_no & 1) : 0;
+        const int lane = interleave ? (chunk_no % lanes) : 0;
         cudaStream_t cst = interleave ? c->streams[lane] : st;
         int rc = ensure_scratch(c->scratch[lane], m, cst);
         if (rc != SPB_OK) return rc;
@@ -610,7 +612,7 @@ int run_device(DeviceCtx *c, const BesselArgs &a, cudaStream_t st, double *ms_ou
         }
     }
     if (interleave) {
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < lanes; ++b) {
             CK(cudaEventRecord(c->join[b], c->streams[b]));
             CK(cudaStreamWaitEvent(st, c->join[b], 0));
         }

@@ -190,18 +190,49 @@ __device__ __forceinline__ bool gfast(double x, double &r) {
 #endif
 }
 
+// Second class of points: below the Stirling range but with a straight-line evaluation of their own, the Stirling
+// form after a FIXED upward shift (no data-dependent product loop): Gamma(x) = Gamma(x + 12) / (x (x+1) ... (x+11))
+// for 1 <= x < 12, ln Gamma(x) = ln Gamma(x + 10) - ln(x (x+1) ... (x+9)) for 2.5 < x < 12 (ln Gamma >= 0.28 there:
+// the zeros at 1 and 2 belong to the Maclaurin branch of the general routine).
+template <int WHICH>
+__device__ __forceinline__ bool gmid_ok(double x) {
+    // (Gamma keeps its points below 12 in the general class: its product loop stops at the first y >= 12, about half
+    // the factors of the fixed shift -- measured 1.17 vs 1.24 ms per 2^27 points)
+    return WHICH == 0 ? false : (x > 2.5 && x < 12.0);
+}
+template <int WHICH>
+__device__ __forceinline__ double gmid(double x) {
+#if defined(__CUDA_ARCH__)
+    constexpr int SHIFT = WHICH == 0 ? 12 : 10;
+    double prod = x;
+#pragma unroll
+    for (int k = 1; k < SHIFT; ++k) prod *= x + (double)k;
+    const double y = x + (double)SHIFT;
+    if (WHICH == 0) return spb::gamma_stirling_dev(y) * spb::rcp_onscale(prod);  // 4.8e8 <= prod < 2e16
+    return spb::lgamma_stirling(y) - spb::log_(prod);
+#else
+    return x;
+#endif
+}
+
+// Three classes per tile: the fast path is evaluated in place; the two others are pushed (value + index) into one
+// shared-memory queue each -- mid-range points from the front, general points from the back of the same arrays -- and
+// processed densely after a barrier, every warp running ONE routine.
 template <int WHICH>
 __global__ void __launch_bounds__(256) k_real_map_queued(const double *x, double *out, long long n) {
     constexpr int IT = 4, TILE_PTS = 256 * 2 * IT;
     __shared__ double qx[TILE_PTS];
     __shared__ unsigned int qi[TILE_PTS];
-    __shared__ unsigned int qn;
+    __shared__ unsigned int qn_mid, qn_gen;
     const double2 *x2 = reinterpret_cast<const double2 *>(x);
     double2 *o2 = reinterpret_cast<double2 *>(out);
     const long long n2 = n >> 1;
     const long long tiles = (n2 + 256 * IT - 1) / (256 * IT);
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        if (threadIdx.x == 0) qn = 0;
+        if (threadIdx.x == 0) {
+            qn_mid = 0;
+            qn_gen = 0;
+        }
         __syncthreads();
         const long long base = tile * (256 * IT);
         double2 a[IT];
@@ -218,12 +249,14 @@ __global__ void __launch_bounds__(256) k_real_map_queued(const double *x, double
             if (i < n2) {
                 const unsigned int local = (unsigned int)(threadIdx.x + 256 * k) * 2u;
                 if (!ok0) {
-                    const unsigned int q = atomicAdd(&qn, 1u);
+                    const unsigned int q = gmid_ok<WHICH>(a[k].x) ? atomicAdd(&qn_mid, 1u)
+                                                                   : (unsigned int)TILE_PTS - 1u - atomicAdd(&qn_gen, 1u);
                     qx[q] = a[k].x;
                     qi[q] = local;
                 }
                 if (!ok1) {
-                    const unsigned int q = atomicAdd(&qn, 1u);
+                    const unsigned int q = gmid_ok<WHICH>(a[k].y) ? atomicAdd(&qn_mid, 1u)
+                                                                   : (unsigned int)TILE_PTS - 1u - atomicAdd(&qn_gen, 1u);
                     qx[q] = a[k].y;
                     qi[q] = local + 1u;
                 }
@@ -231,8 +264,12 @@ __global__ void __launch_bounds__(256) k_real_map_queued(const double *x, double
             }
         }
         __syncthreads();
-        const unsigned int m = qn;
-        for (unsigned int q = threadIdx.x; q < m; q += 256) out[2 * base + qi[q]] = gfun<WHICH>(qx[q]);
+        const unsigned int m_mid = qn_mid, m_gen = qn_gen;
+        for (unsigned int q = threadIdx.x; q < m_mid; q += 256) out[2 * base + qi[q]] = gmid<WHICH>(qx[q]);
+        for (unsigned int q = threadIdx.x; q < m_gen; q += 256) {
+            const unsigned int s = (unsigned int)TILE_PTS - 1u - q;
+            out[2 * base + qi[s]] = gfun<WHICH>(qx[s]);
+        }
         __syncthreads();
     }
     if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) out[n - 1] = gfun<WHICH>(x[n - 1]);
