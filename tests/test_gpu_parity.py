@@ -174,6 +174,50 @@ def test_airy_golden(special, which, kode):
     assert np.all(err[ok] <= tol[ok]), f"{np.max((err - tol)[ok]):.2e}"
 
 
+@pytest.mark.parametrize("kode", [1, 2])
+@pytest.mark.parametrize("which", ["Ai", "Bi"])
+def test_airy_config_scale_vs_scipy(special, which, kode):
+    """BASELINE config 4 at scale for the Airy companions: 200 000 points of the cfg4 stream (|z| log-uniform
+    1e-3..1e4, all quadrants) against LIVE scipy.special.airy / airye, values and error classes.  |z| reaches 1e4,
+    ten times beyond the golden fixture: the large-|zeta| kernels, the loss-of-significance band (ierr 3) and the
+    argument limit (ierr 4 / scipy NaN) all occur."""
+    n = 200_000
+    _, z_dev = special.synth(4, n, n_total=1 << 30, device=torch.device("cuda", 0))
+    z = to_np(z_dev)
+    got, ierr, nz = special.airy_raw(which, z_dev, scaled=(kode == 2), semantics="scipy")
+    got, ierr = to_np(got), to_np(ierr)
+    w = ("Ai", "Aip", "Bi", "Bip").index(which)
+    want = so.evaluate_airy(w, kode, z)
+    comp = so.evaluate_airy(2 - w, kode, z)
+    # error classes: the CPU port of the drivers is the reference for the codes (scipy folds them into NaN / inf)
+    _, ierr_c, _ = helpers.cpu_airy(w, kode, z)
+    assert np.array_equal(ierr, ierr_c)
+    assert set(np.unique(ierr)) >= {0}, "the stream must contain regular points"
+    lost = np.isnan(want.real)
+    assert np.all(np.isnan(got.real[lost & (ierr != 0)]))
+    # (ierr 3 = more than half of the significant digits lost to the argument reduction: a value is still returned)
+    ok = np.isfinite(want.real) & np.isfinite(want.imag) & ((ierr == 0) | (ierr == 3))
+    assert ok.mean() > 0.6 and np.any(ierr == 3)
+    zeta = (2.0 / 3.0) * np.abs(z) ** 1.5
+    tol = so.tolerance(want) + 4 * so.EPS * zeta
+    # near the zeros on the negative real axis the envelope |Ai| ~ |Bi| is the scale (north star: absolute bound there)
+    scale = np.maximum(np.abs(want), np.where((z.real < 0) & np.isfinite(np.abs(comp)), np.abs(comp), 0))
+    if which == "Bi":
+        # Bi also vanishes along the rays arg z = +-pi/3 (its complex zeros): Bi(z) = e^{i pi/6} Ai(z w) + e^{-i pi/6}
+        # Ai(z conj w), w = e^{2 pi i/3}, and the two terms cancel there; their moduli are the scale
+        om = np.exp(2j * np.pi / 3)
+        with np.errstate(all="ignore"):
+            terms = np.abs(so.evaluate_airy(0, 1, z * om)) + np.abs(so.evaluate_airy(0, 1, z * np.conj(om)))
+            if kode == 2:
+                terms = terms * np.exp(-np.abs((2.0 / 3.0 * z * np.sqrt(z)).real))
+        scale = np.maximum(scale, np.where(np.isfinite(terms), terms, 0))
+    err = so.mismatch(got, want, scale)
+    assert np.all(err[ok] <= tol[ok]), f"{which} kode {kode}: {np.max((err - tol)[ok]):.2e} over the tolerance"
+    # inside |z| <= 100 (|zeta| <= 667) the plain 1e-13 of the north star holds up to the conditioning term
+    inner = ok & (np.abs(z) <= 100.0)
+    assert np.all(err[inner] <= 1e-13 + 4 * so.EPS * zeta[inner])
+
+
 def test_gamma_family(special):
     g = helpers.load_golden("gamma_golden.npz")
     x = g["x"]
