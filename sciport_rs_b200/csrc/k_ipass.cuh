@@ -15,6 +15,10 @@ namespace spbk {
 #ifndef SPB_FUSED_MINB
 #define SPB_FUSED_MINB 5
 #endif
+// (fused Miller + Wronskian kernel: 96 registers without spills, 5 CTAs per SM; left alone it takes 104 = 4 CTAs)
+#ifndef SPB_WRSKF_MINB
+#define SPB_WRSKF_MINB 5
+#endif
 
 // one point of the I pass: I_v(w) by the region routine; J / I families finish here, the others park I(w)
 // FUSED (large-|w| region, families that need K as well): I_v(w) and K_v(w) by the fused routine, combine, store
@@ -60,7 +64,7 @@ __device__ __forceinline__ void ipass_point(const DevJob &job, const Scratch &s,
 // memory; otherwise they are computed per point
 // FAM >= 0: the fused form of the kernel with the family and the scaling flag as compile-time constants
 template <int REGION, bool SCALAR, int FAM = -1, int KODE = 0>
-__global__ void __launch_bounds__(128, FAM >= 0 ? (REGION == spb::IREG_ASYI ? SPB_FUSED_MINB : 3) : SPB_IPASS_MINB(REGION))
+__global__ void __launch_bounds__(128, FAM >= 0 ? (REGION == spb::IREG_ASYI ? SPB_FUSED_MINB : SPB_WRSKF_MINB) : SPB_IPASS_MINB(REGION))
     k_ipass(DevJob job, Scratch s) {
     pdl_enter();
     if (FAM >= 0) {
