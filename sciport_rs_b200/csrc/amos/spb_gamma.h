@@ -237,7 +237,14 @@ SPB_HD real sinc_real(real x) {
     // special::sinc, /root/reference/src/special/trig.rs:4-13: sin(pi a)/(pi a), 1 at a == 0
     if (x == real(0.0)) return real(1.0);
     real y = x * real(SPB_PI);
+#if defined(__CUDA_ARCH__)
+    // the reference's formula with the device sine (three-part reduction, <= 1 ulp; library form beyond 2^20)
+    real sn, cs;
+    sincos_(y, sn, cs);
+    return sn / y;
+#else
     return sin(y) / y;
+#endif
 }
 
 }  // namespace spb
