@@ -144,11 +144,75 @@ SPB_HD void sweep_store_group(C &cur, int it, int n, cplx &a, cplx &b, cplx rz, 
     sweep_store(cur, a, q0, j, s1, s2, leading, nz);
 }
 
+// e^w K_fnu(w) and e^w K_fnu+1(w) for |w| >= rl, Re w >= 0, by the large-|w| (Hankel) expansion
+//     e^w K_v(w) = sqrt(pi / 2w) sum_j a_j(v) / w^j,   a_j / a_j-1 = (4 v^2 - (2j-1)^2) / (8 j):
+// the all-positive form of the series the large-|w| routine of I sums (spb_iregions.h, asyi), with its term ratio
+// and its convergence test; |arg w| <= pi/2, so the remainder is bounded by twice the first neglected term
+// (DLMF 10.40(iii)).  The binned pipeline takes K of this region from the same series (DESIGN.md section 2,
+// departure 3).  Both orders advance in one loop until both have converged: ten real operations per term and
+// order with nearly equal trip counts across a warp, where the Miller algorithm of bknu() runs three
+// data-dependent loops.  Returns false when a series has not converged within the published term limit.
+SPB_FN bool sweep_k_pair_large(cplx w, real fnu, real az, real tol, cplx &k0, cplx &k1) {
+    static const double RJ[48] = {
+        0.0, 1.0, 1.0 / 2, 1.0 / 3, 1.0 / 4, 1.0 / 5, 1.0 / 6, 1.0 / 7, 1.0 / 8, 1.0 / 9, 1.0 / 10, 1.0 / 11,
+        1.0 / 12, 1.0 / 13, 1.0 / 14, 1.0 / 15, 1.0 / 16, 1.0 / 17, 1.0 / 18, 1.0 / 19, 1.0 / 20, 1.0 / 21,
+        1.0 / 22, 1.0 / 23, 1.0 / 24, 1.0 / 25, 1.0 / 26, 1.0 / 27, 1.0 / 28, 1.0 / 29, 1.0 / 30, 1.0 / 31,
+        1.0 / 32, 1.0 / 33, 1.0 / 34, 1.0 / 35, 1.0 / 36, 1.0 / 37, 1.0 / 38, 1.0 / 39, 1.0 / 40, 1.0 / 41,
+        1.0 / 42, 1.0 / 43, 1.0 / 44, 1.0 / 45, 1.0 / 46, 1.0 / 47};
+    const real rthpi = 1.25331413731550025;  // sqrt(pi/2)
+    const real raz = rcp_fast(az);
+    const cplx rcz = w_recip(w, raz);
+    const cplx coef = w_rsqrt(w, az, raz) * rthpi;
+    const cplx rez = rcz * real(0.125);  // 1/(8w)
+    const real raez = real(0.125) * raz;
+    const real s = tol * raez;
+    const int jl = (int)(real(SPB_RL) + real(SPB_RL)) + 2;
+    const real d0 = fnu + fnu, d1 = d0 + real(2.0);
+    real sq0 = d0 * d0 - real(1.0), sq1 = d1 * d1 - real(1.0);
+    const real atol0 = s * rabs(sq0), atol1 = s * rabs(sq1);
+    cplx c0(1.0, 0.0), c1(1.0, 0.0), sum0(1.0, 0.0), sum1(1.0, 0.0);
+    real aa0 = 1.0, aa1 = 1.0, ak = 0.0;
+    bool conv = false;
+    for (int j = 1; j <= jl; ++j) {
+        const real t0 = sq0 * real(RJ[j]), t1 = sq1 * real(RJ[j]);
+        c0 = (c0 * rez) * t0;
+        c1 = (c1 * rez) * t1;
+        sum0 = sum0 + c0;
+        sum1 = sum1 + c1;
+        aa0 = aa0 * (rabs(t0) * raez);
+        aa1 = aa1 * (rabs(t1) * raez);
+        ak += real(8.0);
+        sq0 -= ak;
+        sq1 -= ak;
+        if (aa0 <= atol0 && aa1 <= atol1) {
+            conv = true;
+            break;
+        }
+    }
+    k0 = coef * sum0;
+    k1 = coef * sum1;
+    return conv;
+}
+
+// The right-half-plane point w at which the sweep of family J / I evaluates I_{fnu+k}(w) for the argument z
+// (the rotation of besj_sweep / besi_sweep below; the K-pair pre-pass of the device kernels uses it too).
+SPB_HD cplx sweep_point_w(bool jfam, cplx z) {
+    if (jfam) {
+        cplx zn(z.im, -z.re);
+        return (z.im < real(0.0)) ? -zn : zn;
+    }
+    return (z.re < real(0.0)) ? -z : z;
+}
+
 // y[k] = csgn0 * i^(dm k) * I_{fnu+k}(w),  Re w >= 0,  az = |w|.  The order-independent factor csgn0 is folded into
 // the normalising factor once; the per-order unit i^(dm k) is applied exactly (dm = +-1 for J, 2 for I continued
 // to the left half plane, 0 for none).  Returns nz >= 0, or -1 when it declines.
+// kpre (device kernels): where |w| < rl, the pair e^w K_fnu(w), e^w K_fnu+1(w) evaluated beforehand by a dense pass
+// over the points that need the Miller algorithm (a few such lanes would hold their whole warp in bknu(): 19 % of the
+// sweep kernel's instructions at 12 of 32 lanes); NaN there = that evaluation failed.  With kpre the routine
+// takes K of |w| >= rl from the large-|w| series; without it (CPU drivers, classic behaviour) from bknu().
 template <class Y>
-SPB_FN int isweep(cplx w, real fnu, int kode, int n, Y y, real az, cplx csgn0, int dm) {
+SPB_FN int isweep(cplx w, real fnu, int kode, int n, Y y, real az, cplx csgn0, int dm, const cplx *kpre = nullptr) {
     const real tol = SPB_TOL, elim = SPB_ELIM, alim = SPB_ALIM;
     // short sequences stay with the classic drivers (cheap there, and a direct evaluation of so few members is
     // slightly more accurate than the ratio / Wronskian route)
@@ -159,7 +223,17 @@ SPB_FN int isweep(cplx w, real fnu, int kode, int n, Y y, real az, cplx csgn0, i
     cplx ck[2];
     ck[0] = cplx(0.0, 0.0);
     ck[1] = cplx(0.0, 0.0);
-    const int nw = bknu(w, fnu, 2, 2, ck, tol, elim, alim, az);
+    int nw = 0;
+    if (kpre) {
+        if (az >= real(SPB_RL)) {
+            if (!sweep_k_pair_large(w, fnu, az, tol, ck[0], ck[1])) return -1;  // (never observed: classic path)
+        } else {
+            ck[0] = kpre[0];
+            ck[1] = kpre[1];
+        }
+    } else {
+        nw = bknu(w, fnu, 2, 2, ck, tol, elim, alim, az);
+    }
     // ---- start index: forward magnitude walk of the ratio algorithm (squared moduli)
     const int inu = (int)fnu;
     const int idnu = inu + n - 1;
@@ -277,7 +351,7 @@ SPB_FN int isweep(cplx w, real fnu, int kode, int n, Y y, real az, cplx csgn0, i
 
 // J_{fnu+k}(z), k < n, through the sweep.  declined = true: nothing was stored, use besj().
 template <class Y>
-SPB_FN int besj_sweep(cplx z, real fnu, int kode, int n, Y cy, int &ierr, bool &declined) {
+SPB_FN int besj_sweep(cplx z, real fnu, int kode, int n, Y cy, int &ierr, bool &declined, const cplx *kpre = nullptr) {
     ierr = 0;
     declined = true;
     if (!(fnu >= real(0.0)) || !(fnu < real(32000.0)) || n < 2 || n > 100000) return 0;
@@ -293,7 +367,7 @@ SPB_FN int besj_sweep(cplx z, real fnu, int kode, int n, Y cy, int &ierr, bool &
         csgn.im = -csgn.im;
         cii = -cii;
     }
-    const int nz = isweep(zn, fnu, kode, n, cy, az, csgn, cii > real(0.0) ? 1 : -1);
+    const int nz = isweep(zn, fnu, kode, n, cy, az, csgn, cii > real(0.0) ? 1 : -1, kpre);
     if (nz < 0) return 0;
     declined = false;
     return nz;
@@ -301,7 +375,7 @@ SPB_FN int besj_sweep(cplx z, real fnu, int kode, int n, Y cy, int &ierr, bool &
 
 // I_{fnu+k}(z), k < n, through the sweep.  declined = true: nothing was stored, use besi().
 template <class Y>
-SPB_FN int besi_sweep(cplx z, real fnu, int kode, int n, Y cy, int &ierr, bool &declined) {
+SPB_FN int besi_sweep(cplx z, real fnu, int kode, int n, Y cy, int &ierr, bool &declined, const cplx *kpre = nullptr) {
     ierr = 0;
     declined = true;
     if (!(fnu >= real(0.0)) || !(fnu < real(32000.0)) || n < 2 || n > 100000) return 0;
@@ -317,7 +391,7 @@ SPB_FN int besi_sweep(cplx z, real fnu, int kode, int n, Y cy, int &ierr, bool &
         if (ph.inu % 2 != 0) csgn = -csgn;
         dm = 2;
     }
-    const int nz = isweep(zn, fnu, kode, n, cy, az, csgn, dm);
+    const int nz = isweep(zn, fnu, kode, n, cy, az, csgn, dm, kpre);
     if (nz < 0) return 0;
     declined = false;
     return nz;

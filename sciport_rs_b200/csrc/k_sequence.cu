@@ -39,6 +39,47 @@ struct spb::SweepCursor<spbk::SeqStore> {
 
 namespace spbk {
 
+// ---- K-pair pre-pass of the sweep --------------------------------------------------------------------------
+// The sweep normalises through the Wronskian with e^w K_fnu(w), e^w K_fnu+1(w).  For |w| >= rl (nine points in
+// ten of config 5) both come from the large-|w| series inside k_sweep; below, they need the Miller algorithm of
+// bknu(), whose three data-dependent loops would hold a whole warp for the three or four lanes that need it.
+// Those points are listed (k_sweep_mark) and their pairs evaluated densely (k_sweep_kpair), parked in rows 0 and 1
+// of the point's own result column -- the two rows pass B of k_sweep writes last -- where k_sweep picks them up.
+__global__ void __launch_bounds__(256) k_sweep_mark(DevJob job, unsigned int *defer, unsigned int *defer_len) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < job.n; i += stride) {
+        cplx z;
+        double v;
+        load_point(job, i, z, v);
+        if (!(spb::cabs_(z) >= SPB_RL)) defer[atomicAdd(defer_len, 1u)] = (unsigned int)i;  // (also NaN: declined later)
+    }
+}
+
+__global__ void __launch_bounds__(128) k_sweep_kpair(DevJob job, long long out_stride, const unsigned int *defer,
+                                                     const unsigned int *defer_len) {
+    const unsigned int count = *defer_len;
+    const unsigned int stride = gridDim.x * blockDim.x;
+#pragma unroll 1
+    for (unsigned int t = blockIdx.x * blockDim.x + threadIdx.x; t < count; t += stride) {
+        const long long i = defer[t];
+        cplx z;
+        double v;
+        load_point(job, i, z, v);
+        const cplx w = spb::sweep_point_w(job.fam == spb::FAM_J, z);
+        cplx ck[2];
+        ck[0] = cplx(0.0, 0.0);
+        ck[1] = cplx(0.0, 0.0);
+        const int nw = spb::bknu(w, v, 2, 2, ck, SPB_TOL, SPB_ELIM, SPB_ALIM, spb::cabs_(z));
+        if (nw != 0) {  // failed or set a member to zero: the sweep declines the point (NaN normalising factor)
+            const double nan = __longlong_as_double(0x7ff8000000000000ll);
+            ck[0] = cplx(nan, nan);
+            ck[1] = cplx(nan, nan);
+        }
+        job.out[i] = make_double2(ck[0].re, ck[0].im);
+        job.out[out_stride + i] = make_double2(ck[1].re, ck[1].im);
+    }
+}
+
 __global__ void __launch_bounds__(128) k_sweep(DevJob job, int n_orders, long long out_stride, unsigned int *list,
                                                unsigned int *list_len) {
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -48,12 +89,21 @@ __global__ void __launch_bounds__(128) k_sweep(DevJob job, int n_orders, long lo
         double v;
         load_point(job, i, z, v);
         SeqStore y{job.out + i, out_stride};
+        // the pair parked by k_sweep_kpair (same test as k_sweep_mark)
+        cplx kpre[2];
+        kpre[0] = cplx(0.0, 0.0);
+        kpre[1] = cplx(0.0, 0.0);
+        if (!(spb::cabs_(z) >= SPB_RL)) {
+            const double2 a = job.out[i], b = job.out[out_stride + i];
+            kpre[0] = cplx(a.x, a.y);
+            kpre[1] = cplx(b.x, b.y);
+        }
         int ierr = 0, nz = 0;
         bool declined = true;
         if (job.fam == spb::FAM_J)
-            nz = spb::besj_sweep(z, v, job.kode, n_orders, y, ierr, declined);
+            nz = spb::besj_sweep(z, v, job.kode, n_orders, y, ierr, declined, kpre);
         else
-            nz = spb::besi_sweep(z, v, job.kode, n_orders, y, ierr, declined);
+            nz = spb::besi_sweep(z, v, job.kode, n_orders, y, ierr, declined, kpre);
         if (declined) {
             list[atomicAdd(list_len, 1u)] = (unsigned int)i;
             continue;
@@ -114,11 +164,18 @@ __global__ void __launch_bounds__(128) k_sequence(DevJob job, int n_orders, long
 int launch_sequence(const DevJob &job, int n_orders, long long out_stride, const Scratch &s, int sms,
                     cudaStream_t st) {
     if (job.fam == spb::FAM_J || job.fam == spb::FAM_I) {
-        unsigned int *len = s.bins + GLIST_LEN_SLOT;
-        cudaMemsetAsync(len, 0, sizeof(unsigned int), st);
+        unsigned int *len = s.bins + GLIST_LEN_SLOT, *dlen = s.bins + SLOT_G2;
+        cudaMemsetAsync(len, 0, 3 * sizeof(unsigned int), st);  // GLIST_LEN_SLOT, SLOT_DONE (stays 0), SLOT_G2
+        // (perm_i is free on this path: the list of the pre-pass)
+        long long mark_blocks = (job.n + 255) / 256;
+        if (mark_blocks > (long long)sms * 8) mark_blocks = (long long)sms * 8;
+        if (n_orders >= SPB_SWEEP_MIN_ORDERS) {  // (shorter sequences: the sweep declines every point anyway)
+            k_sweep_mark<<<(int)mark_blocks, 256, 0, st>>>(job, s.perm_i, dlen);
+            k_sweep_kpair<<<resident_grid(k_sweep_kpair, 128, sms), 128, 0, st>>>(job, out_stride, s.perm_i, dlen);
+        }
         k_sweep<<<resident_grid(k_sweep, 128, sms), 128, 0, st>>>(job, n_orders, out_stride, s.glist, len);
         k_sequence<<<resident_grid(k_sequence, 128, sms), 128, 0, st>>>(job, n_orders, out_stride, s.glist, len);
-        return 2;
+        return 4;
     }
     k_sequence<<<resident_grid(k_sequence, 128, sms), 128, 0, st>>>(job, n_orders, out_stride, nullptr, nullptr);
     return 1;
