@@ -218,55 +218,91 @@ __device__ __forceinline__ double gmid(double x) {
 // Three classes per tile: the fast path is evaluated in place; the two others are pushed (value + index) into one
 // shared-memory queue each -- mid-range points from the front, general points from the back of the same arrays -- and
 // processed densely after a barrier, every warp running ONE routine.
+#ifndef SPB_GAMMA_NT
+#define SPB_GAMMA_NT 256
+#endif
 template <int WHICH>
-__global__ void __launch_bounds__(256) k_real_map_queued(const double *x, double *out, long long n) {
-    constexpr int IT = 4, TILE_PTS = 256 * 2 * IT;
+__global__ void __launch_bounds__(SPB_GAMMA_NT) k_real_map_queued(const double *x, double *out, long long n) {
+    constexpr int NT = SPB_GAMMA_NT, IT = 4, TILE_PTS = NT * 2 * IT;
     __shared__ double qx[TILE_PTS];
     __shared__ unsigned int qi[TILE_PTS];
     __shared__ unsigned int qn_mid, qn_gen;
     const double2 *x2 = reinterpret_cast<const double2 *>(x);
     double2 *o2 = reinterpret_cast<double2 *>(out);
     const long long n2 = n >> 1;
-    const long long tiles = (n2 + 256 * IT - 1) / (256 * IT);
+    const long long tiles = (n2 + NT * IT - 1) / (NT * IT);
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         if (threadIdx.x == 0) {
             qn_mid = 0;
             qn_gen = 0;
         }
         __syncthreads();
-        const long long base = tile * (256 * IT);
+        const long long base = tile * (NT * IT);
         double2 a[IT];
 #pragma unroll
         for (int k = 0; k < IT; ++k) {
-            const long long i = base + threadIdx.x + 256 * k;
+            const long long i = base + threadIdx.x + NT * k;
             a[k] = (i < n2) ? __ldg(x2 + i) : make_double2(20.0, 20.0);
         }
+        // fast path for all eight points of the thread; what it declines is recorded in two bit masks
+        unsigned int need_mid = 0, need_gen = 0;
 #pragma unroll
         for (int k = 0; k < IT; ++k) {
-            const long long i = base + threadIdx.x + 256 * k;
+            const long long i = base + threadIdx.x + NT * k;
             double2 r;
             const bool ok0 = gfast<WHICH>(a[k].x, r.x), ok1 = gfast<WHICH>(a[k].y, r.y);
             if (i < n2) {
-                const unsigned int local = (unsigned int)(threadIdx.x + 256 * k) * 2u;
-                if (!ok0) {
-                    const unsigned int q = gmid_ok<WHICH>(a[k].x) ? atomicAdd(&qn_mid, 1u)
-                                                                   : (unsigned int)TILE_PTS - 1u - atomicAdd(&qn_gen, 1u);
-                    qx[q] = a[k].x;
-                    qi[q] = local;
-                }
-                if (!ok1) {
-                    const unsigned int q = gmid_ok<WHICH>(a[k].y) ? atomicAdd(&qn_mid, 1u)
-                                                                   : (unsigned int)TILE_PTS - 1u - atomicAdd(&qn_gen, 1u);
-                    qx[q] = a[k].y;
-                    qi[q] = local + 1u;
-                }
+                if (!ok0) (gmid_ok<WHICH>(a[k].x) ? need_mid : need_gen) |= 1u << (2 * k);
+                if (!ok1) (gmid_ok<WHICH>(a[k].y) ? need_mid : need_gen) |= 1u << (2 * k + 1);
                 o2[i] = r;  // (queued positions are overwritten below, after the barrier)
+            }
+        }
+        // queue slots: the thread's counts, an exclusive scan over the warp, ONE shared atomic per warp and class
+        // (an atomic per queued point -- or the compiler's aggregated form of it inside the divergent branches --
+        // was 15 % of the kernel's instructions at two lanes active)
+        {
+            const unsigned int lane = threadIdx.x & 31u;
+            const unsigned int cm = __popc(need_mid), cg = __popc(need_gen);
+            unsigned int packed = cm | (cg << 16), incl = packed;  // (at most 8 x 32 per class and warp)
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned int y = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= (unsigned int)d) incl += y;
+            }
+            const unsigned int total = __shfl_sync(0xffffffffu, incl, 31);
+            unsigned int base_mid = 0, base_gen = 0;
+            if (lane == 0) {
+                if (total & 0xffffu) base_mid = atomicAdd(&qn_mid, total & 0xffffu);
+                if (total >> 16) base_gen = atomicAdd(&qn_gen, total >> 16);
+            }
+            base_mid = __shfl_sync(0xffffffffu, base_mid, 0);
+            base_gen = __shfl_sync(0xffffffffu, base_gen, 0);
+            unsigned int qm = base_mid + ((incl - packed) & 0xffffu);
+            unsigned int qg = base_gen + ((incl - packed) >> 16);
+#pragma unroll
+            for (int k = 0; k < IT; ++k) {
+                const unsigned int local = (unsigned int)(threadIdx.x + NT * k) * 2u;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const unsigned int bit = 1u << (2 * k + h);
+                    const double xv = h ? a[k].y : a[k].x;
+                    if (need_mid & bit) {
+                        qx[qm] = xv;
+                        qi[qm] = local + h;
+                        ++qm;
+                    } else if (need_gen & bit) {
+                        const unsigned int q = (unsigned int)TILE_PTS - 1u - qg;
+                        qx[q] = xv;
+                        qi[q] = local + h;
+                        ++qg;
+                    }
+                }
             }
         }
         __syncthreads();
         const unsigned int m_mid = qn_mid, m_gen = qn_gen;
-        for (unsigned int q = threadIdx.x; q < m_mid; q += 256) out[2 * base + qi[q]] = gmid<WHICH>(qx[q]);
-        for (unsigned int q = threadIdx.x; q < m_gen; q += 256) {
+        for (unsigned int q = threadIdx.x; q < m_mid; q += NT) out[2 * base + qi[q]] = gmid<WHICH>(qx[q]);
+        for (unsigned int q = threadIdx.x; q < m_gen; q += NT) {
             const unsigned int s = (unsigned int)TILE_PTS - 1u - q;
             out[2 * base + qi[s]] = gfun<WHICH>(qx[s]);
         }
@@ -290,8 +326,8 @@ static void launch_real_map(const double *x, double *out, long long n, cudaStrea
     bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
     if (aligned && (WHICH == 0 || WHICH == 1) && n >= 4096) {
         // gamma / ln|gamma|: fast path + in-kernel queue, persistent grid of resident CTAs
-        const int grid = resident_grid(k_real_map_queued<WHICH>, 256, 148);
-        k_real_map_queued<WHICH><<<grid, 256, 0, st>>>(x, out, n);
+        const int grid = resident_grid(k_real_map_queued<WHICH>, SPB_GAMMA_NT, 148);
+        k_real_map_queued<WHICH><<<grid, SPB_GAMMA_NT, 0, st>>>(x, out, n);
     } else if (aligned)
         k_real_map<WHICH><<<(int)blocks, 256, 0, st>>>(x, out, n);
     else
