@@ -96,16 +96,18 @@ __device__ __forceinline__ unsigned int field_g(const Packed &p) {
     return (unsigned int)p.w[2] & ((1u << FIELD_BITS) - 1u);
 }
 
-// (side, |z|, order) cell of a point for the second-level sort (see k_cell_hist below): 32 levels of |z|, 16 of the
-// order, 2 sides
+// (side, |z|, order) cell of a point for the second-level sort (see k_cell_hist below): 2^CELL_ZBITS levels of |z|
+// over [1, 256] (8 per octave with 6 bits, 4 with 5), 2^CELL_VBITS levels of the order over [0, 64), 2 sides
 __device__ __forceinline__ unsigned int cell_of(int fam, cplx z, double v, bool with_side) {
     const double m2 = z.re * z.re + z.im * z.im;
     const int hi = __double2hiint(m2);
-    int q = 2 * ((hi >> 20) - 1023) + ((hi >> 19) & 1);  // two levels per octave of |z|^2 = four per octave of |z|
-    q = q < 0 ? 0 : (q > 31 ? 31 : q);
-    int b = (int)(fabs(v) * 0.25);
-    b = b > 15 ? 15 : b;
-    return (unsigned int)(q | (b << 5)) | (with_side ? (side_of(fam, z) << 9) : 0u);
+    // levels of |z|^2 per octave = half of the levels of |z| per octave: the exponent and the top mantissa bits
+    constexpr int MB = CELL_ZBITS - 4;  // mantissa bits of |z|^2 used: 16 octaves of |z|^2 fill 4 bits
+    int q = (((hi >> 20) - 1023) << MB) + ((hi >> (20 - MB)) & ((1 << MB) - 1));
+    q = q < 0 ? 0 : (q > (1 << CELL_ZBITS) - 1 ? (1 << CELL_ZBITS) - 1 : q);
+    int b = (int)(fabs(v) * (double)(1 << CELL_VBITS) * (1.0 / 64.0));
+    b = b > (1 << CELL_VBITS) - 1 ? (1 << CELL_VBITS) - 1 : b;
+    return (unsigned int)(q | (b << CELL_ZBITS)) | (with_side ? (side_of(fam, z) << (CELL_ZBITS + CELL_VBITS)) : 0u);
 }
 
 // FAM / KODE: the job's family and scaling flag as compile-time constants (dispatch_fam_kode)
@@ -432,12 +434,13 @@ __global__ void __launch_bounds__(256) k_scatter(DevJob job, Scratch s) {
 // compaction leaves the points in index order, i.e. in random (|z|, order) order for unrelated inputs: the lanes of
 // a warp then run loops of very different lengths (measured: 20-21 of 32 lanes active in the Miller / Wronskian /
 // K kernels of config 3 even with a per-CTA batch sort of 512 points).  A counting sort of each bin segment by a
-// 10-bit cell key -- 32 levels of |z|, four per octave, times 16 levels of the order, times the side of the
-// family's continuation (side_of) -- makes 32 consecutive
+// (CELL_ZBITS + CELL_VBITS + 1)-bit cell key -- 32 levels of |z|, four per octave, times 16 levels of the order, times
+// the side of the family's continuation (side_of); 64 x 32 x 2 cells measured slower: the sort pays more than the
+// kernels gain (config 3 pair 9.67 -> 10.27 ms per 2^26 points) -- makes 32 consecutive
 // entries near neighbours in both variables, over the whole chunk instead of a 512-point batch:
 // The classifier of a cell-sorted job stores the key of every point (2 bytes, coalesced) next to its class byte.
 //   k_cell_hist    histogram of the cell keys per bin (shared-memory histograms, one global add per cell and CTA)
-//   k_cell_scan    exclusive scan of the 1024 cell counters of every bin -> cell cursors
+//   k_cell_scan    exclusive scan of the NCELLS cell counters of every bin -> cell cursors
 //   k_cell_scatter batches of 1024 entries: shared-memory counts, ONE global atomic per (batch, cell) reserves the
 //                  range, entries are written to perm_i2 / perm_k2 (order inside a cell is arbitrary: results are
 //                  per point, only the memory order depends on it)
@@ -473,13 +476,20 @@ __global__ void __launch_bounds__(256) k_cell_hist(DevJob job, Scratch s) {
         if (hist[c]) atomicAdd(&s.cellcnt[slot * NCELLS + c], hist[c]);
 }
 
-__global__ void __launch_bounds__(NCELLS) k_cell_scan(Scratch s) {
+constexpr int CSCAN_T = NCELLS < 1024 ? NCELLS : 1024;  // threads of k_cell_scan
+__global__ void __launch_bounds__(CSCAN_T) k_cell_scan(Scratch s) {
     pdl_enter();
-    __shared__ unsigned int wsum[NCELLS / 32];
+    constexpr int PER = NCELLS / CSCAN_T;  // consecutive cells per thread
+    __shared__ unsigned int wsum[CSCAN_T / 32];
     const int slot = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    unsigned int *cnt = s.cellcnt + slot * NCELLS;
-    const unsigned int x = cnt[threadIdx.x];
-    unsigned int incl = x;
+    unsigned int *cnt = s.cellcnt + slot * NCELLS + threadIdx.x * PER;
+    unsigned int x[PER], sum = 0;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        x[k] = cnt[k];
+        sum += x[k];
+    }
+    unsigned int incl = sum;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         const unsigned int y = __shfl_up_sync(0xffffffffu, incl, d);
@@ -489,7 +499,12 @@ __global__ void __launch_bounds__(NCELLS) k_cell_scan(Scratch s) {
     __syncthreads();
     unsigned int off = 0;
     for (int w = 0; w < wid; ++w) off += wsum[w];
-    cnt[threadIdx.x] = off + incl - x;  // exclusive: where the cell starts inside its bin segment
+    unsigned int running = off + incl - sum;  // exclusive: where the thread's first cell starts inside its bin segment
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        cnt[k] = running;
+        running += x[k];
+    }
 }
 
 __global__ void __launch_bounds__(256) k_cell_scatter(DevJob job, Scratch s) {
@@ -547,7 +562,7 @@ int launch_cellsort(const DevJob &job, const Scratch &s, int sms, cudaStream_t s
     cfg.blockDim = dim3(256, 1, 1);
     cfg.gridDim = dim3((unsigned int)(sms * 2), CELL_SLOTS, 1);
     cudaLaunchKernelEx(&cfg, k_cell_hist, job, s);
-    launch_pdl(job.pdl != 0, k_cell_scan, CELL_SLOTS, NCELLS, st, s);
+    launch_pdl(job.pdl != 0, k_cell_scan, CELL_SLOTS, CSCAN_T, st, s);
     cudaLaunchKernelEx(&cfg, k_cell_scatter, job, s);
     return 3;
 }

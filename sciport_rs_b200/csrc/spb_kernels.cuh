@@ -70,7 +70,15 @@ constexpr int TILE = 2048;               // points per classification tile
 // second-level sort inside a bin: 512 cells = 32 levels of |z| (four per octave, 1 <= |z| < 221) x 16 levels of the
 // order (steps of 4); slots = the bins that are sorted this way (every I bin but the Debye-direct one, whose routine
 // has no data-dependent loop; the three K bins)
-constexpr int NCELLS = 1024;
+// cell key of the second-level sort: CELL_ZBITS bits of |z| level, CELL_VBITS bits of order level, 1 bit of side
+#ifndef SPB_CELL_ZBITS
+#define SPB_CELL_ZBITS 5
+#endif
+#ifndef SPB_CELL_VBITS
+#define SPB_CELL_VBITS 4
+#endif
+constexpr int CELL_ZBITS = SPB_CELL_ZBITS, CELL_VBITS = SPB_CELL_VBITS;
+constexpr int NCELLS = 1 << (CELL_ZBITS + CELL_VBITS + 1);
 constexpr int CELL_SLOTS = 9;
 // slots of Scratch::bins beyond the NBINS+1 start offsets
 constexpr int GLIST_LEN_SLOT = 24;  // current length of the general list (grows when a pass hands a point over)
