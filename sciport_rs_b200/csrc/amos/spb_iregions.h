@@ -224,6 +224,7 @@ SPB_FN int asyi(cplx z, real fnu, int kode, int n, Y y, real rl, real tol, real 
             e2 = cplx(e2m * ((csy - sny) * (csy + sny)), -e2m * ((sny + sny) * csy));
         }
     }
+    bool noconv = false;
     for (int k = 1; k <= il; ++k) {
         real sqk = fdn - real(1.0);
         real atol = s * rabs(sqk);
@@ -245,7 +246,10 @@ SPB_FN int asyi(cplx z, real fnu, int kode, int n, Y y, real rl, real tol, real 
                 break;
             }
         }
-        if (!conv) return -2;
+        // (no return here: a `return` right after the data-dependent loop would move the reconvergence point of its
+        // exits to the end of the routine, and the lanes of a warp would run the rest of it in as many passes as
+        // they have distinct series lengths -- measured: the tail below ran with 6 of 32 lanes)
+        noconv = noconv || !conv;
         // the same terms with all signs positive are the large-|z| series of K (member of order fnu + n - 1 last)
         if (ksum) *ksum = cs2;
         cplx s2 = cs1;
@@ -253,6 +257,11 @@ SPB_FN int asyi(cplx z, real fnu, int kode, int n, Y y, real rl, real tol, real 
         fdn = fdn + real(8.0) * dfnu + real(4.0);
         p1 = -p1;
         y[n - il + k - 1] = s2 * ak1;
+    }
+    if (noconv) {
+        // a series that did not converge: no member is returned (as when the routine left at the failing series)
+        for (int i = 0; i < n; ++i) y[i] = cplx(0.0, 0.0);
+        return -2;
     }
     if (n <= 2) return 0;
     int nn = n;
