@@ -11,6 +11,7 @@
 // parallelised over contiguous chunks).  Nothing in the product path links it.
 #include <cstdint>
 #include <thread>
+#include <limits>
 #include <vector>
 #include <algorithm>
 #include <cmath>
@@ -182,9 +183,25 @@ int spbo_bessel_jy_pipeline(int kode, const double *v, int64_t v_stride, const d
 // Order sequences: out[k*n + i] = F_{v_i + k}(z_i), k < n_orders (J, I, K, H1, H2; Y through its Hankel pair).
 int spbo_bessel_seq(int fn, int kode, const double *v, int64_t v_stride, const double *z, double *out, int32_t *ierr,
                     int32_t *nz, int64_t n, int n_orders, int threads_and_mode) {
-    // bit 16 of the last argument switches the sweep off (classic sequence drivers only: cross-check)
+    // bit 16 of the last argument switches the sweep off (classic sequence drivers only: cross-check); bit 17 runs
+    // the sweep the way the CUDA kernels do (k_sequence.cu): the K pair of the Wronskian normalisation from the
+    // large-|w| series for |w| >= rl, from a bknu() evaluation handed in for the other points
     const int threads = threads_and_mode & 0xffff;
     const bool sweep = (threads_and_mode & 0x10000) == 0;
+    const bool device_flow = (threads_and_mode & 0x20000) != 0;
+    auto kpair = [](bool jfam, cplx zz, double fnu, cplx *kpre) {
+        kpre[0] = cplx(0.0, 0.0);
+        kpre[1] = cplx(0.0, 0.0);
+        const double az = cabs_(zz);
+        if (!(az >= SPB_RL)) {
+            const cplx w = sweep_point_w(jfam, zz);
+            if (bknu(w, fnu, 2, 2, kpre, SPB_TOL, SPB_ELIM, SPB_ALIM, az) != 0) {
+                const double nan = std::numeric_limits<double>::quiet_NaN();
+                kpre[0] = cplx(nan, nan);
+                kpre[1] = cplx(nan, nan);
+            }
+        }
+    };
     parallel_for(n, threads, [=](int64_t lo, int64_t hi) {
         std::vector<cplx> cy(n_orders), cw(n_orders);
         for (int64_t i = lo; i < hi; ++i) {
@@ -197,13 +214,17 @@ int spbo_bessel_seq(int fn, int kode, const double *v, int64_t v_stride, const d
                 // sequence driver where it declines — the same rule the CUDA sequence kernels follow
                 case FN_J: {
                     bool declined = true;
-                    if (sweep) nzz = besj_sweep(zz, fnu, kode, n_orders, cy.data(), ie, declined);
+                    cplx kpre[2];
+                    if (sweep && device_flow) kpair(true, zz, fnu, kpre);
+                    if (sweep) nzz = besj_sweep(zz, fnu, kode, n_orders, cy.data(), ie, declined, device_flow ? kpre : nullptr);
                     if (declined) nzz = besj(zz, fnu, kode, n_orders, cy.data(), ie);
                     break;
                 }
                 case FN_I: {
                     bool declined = true;
-                    if (sweep) nzz = besi_sweep(zz, fnu, kode, n_orders, cy.data(), ie, declined);
+                    cplx kpre[2];
+                    if (sweep && device_flow) kpair(false, zz, fnu, kpre);
+                    if (sweep) nzz = besi_sweep(zz, fnu, kode, n_orders, cy.data(), ie, declined, device_flow ? kpre : nullptr);
                     if (declined) nzz = besi(zz, fnu, kode, n_orders, cy.data(), ie);
                     break;
                 }

@@ -67,9 +67,10 @@ def cpu_bessel(fn, kode, v, z, sem=0, pipeline=False, threads=8, fuse=False):
     return out, ierr, nz
 
 
-def cpu_bessel_seq(fn, kode, v, z, n_orders, threads=8, classic=False):
+def cpu_bessel_seq(fn, kode, v, z, n_orders, threads=8, classic=False, device_flow=False):
     """Order sequence F_{v+k}(z), k < n_orders, on the CPU checker: ((n_orders, n) values, ierr[n], nz[n]).
-    classic=True forces the classic sequence drivers (no write-once sweep) for J and I."""
+    classic=True forces the classic sequence drivers (no write-once sweep) for J and I; device_flow=True runs the
+    sweep as the CUDA kernels do (K pair of the normalisation from the large-|w| series / handed in from bknu)."""
     lib = oracle_lib()
     z = np.ascontiguousarray(z, dtype=np.complex128).ravel()
     v = np.ascontiguousarray(np.broadcast_to(np.asarray(v, dtype=np.float64), z.shape))
@@ -77,7 +78,7 @@ def cpu_bessel_seq(fn, kode, v, z, n_orders, threads=8, classic=False):
     ierr = np.empty(z.size, np.int32)
     nz = np.empty(z.size, np.int32)
     lib.spbo_bessel_seq(FN[fn], kode, v.ctypes.data, 1, z.ctypes.data, out.ctypes.data, ierr.ctypes.data,
-                        nz.ctypes.data, z.size, n_orders, threads | (0x10000 if classic else 0))
+                        nz.ctypes.data, z.size, n_orders, threads | (0x10000 if classic else 0) | (0x20000 if device_flow else 0))
     return out, ierr, nz
 
 

@@ -64,6 +64,30 @@ def test_j_sweep_0_255_vs_golden(kode):
 
 
 @pytest.mark.parametrize("kode", [1, 2])
+@pytest.mark.parametrize("fn", ["J", "I"])
+def test_sweep_device_flow_matches_classic_flow(fn, kode):
+    """The CUDA sweep kernels take the K pair of the Wronskian normalisation from the large-|w| series (|w| >= rl) or
+    from a dense bknu() pre-pass (k_sequence.cu) instead of calling bknu() inside the sweep: same members to a few
+    ulp of the normalising factor, identical codes, on the config-5 stream and on fractional start orders."""
+    rng = np.random.default_rng(helpers.seed_of("sweep-device-flow", fn, kode))
+    n = 3000
+    r = 200.0 * rng.random(n)
+    th = np.pi * (2.0 * rng.random(n) - 1.0)
+    z = r * np.exp(1j * th)
+    for v0, orders in ((0.0, 256), (0.3, 64), (7.5, 40)):
+        a, ierr_a, nz_a = helpers.cpu_bessel_seq(fn, kode, v0, z, orders)
+        b, ierr_b, nz_b = helpers.cpu_bessel_seq(fn, kode, v0, z, orders, device_flow=True)
+        assert np.array_equal(ierr_a, ierr_b) and np.array_equal(nz_a, nz_b)
+        assert np.array_equal(a == 0, b == 0)
+        scale = np.maximum(np.abs(a), np.abs(a).max(axis=0, keepdims=True) * 1e-300)
+        on = np.abs(a) > 0
+        err = np.abs(a - b)[on] / scale[on]
+        assert err.max() <= 64 * so.EPS, f"{fn} kode {kode} v0 {v0}: {err.max():.2e}"
+        # both K routines are in play
+        assert (np.abs(z) < 21.7).any() and (np.abs(z) > 21.9).any()
+
+
+@pytest.mark.parametrize("kode", [1, 2])
 @pytest.mark.parametrize("fn", ["J", "Y", "I", "K", "H1", "H2"])
 def test_short_sequences_vs_golden(fn, kode):
     g = helpers.load_golden("seq_golden.npz")
