@@ -234,27 +234,31 @@ SPB_FN Prep prepare(int fam, cplx z, real fnu, int kode, int fuse = 0) {
         p.final_nz = overflow ? 0 : 1;
         return p;
     }
-    if (fnu > real(2.0) && !uoik_is_noop(az, gnu1, alim, rabs(p.w.re), kode)) {
-        // ... or provably an underflow of K_v(w): Re(zeta2 - zeta1) >= |Re w| - gnu (ln(1 + 2/t + t) + pi) > elim makes
-        // the pre-test zero the whole (single-member) sequence.  The K and Hankel drivers then return 0 with nz = 1
-        // in the right half plane and report an overflow (ierr = 2) in the left one, where the vanished K would
-        // have been continued with the growing I.  (Unscaled functions only: the scaled pre-test has no |Re w|.)
-        // Y = (H1 - H2)/2i evaluates both Hankel functions at the same |Re w|: one of them vanishes, the other one
-        // is the overflow, so Y reports ierr = 2.
-        if (kode == 1 && (fam == FAM_K || fam == FAM_H1 || fam == FAM_H2 || fam == FAM_Y)) {
-            const real gnu = rmax(fnu, real(1.0));
-            const real t = az / gnu;
-            const real b = gnu * (log(real(1.0) + real(2.0) / t + t) + real(SPB_PI));
-            if (rabs(p.w.re) - b > real(SPB_ELIM)) {
-                const bool overflow = (p.combine == CMB_ACON) || fam == FAM_Y;
-                p.combine = CMB_FINAL;
-                p.final_ierr = overflow ? 2 : 0;
-                p.final_nz = overflow ? 0 : 1;
+    if (fnu > real(2.0)) {
+        const real x = (kode != 1) ? real(0.0) : rabs(p.w.re);
+        if (!uoik_noop_cheap(az, gnu1, alim, x)) {
+            // ONE logarithm serves the full bound of the no-op test (uoik_noop_full: same expression) and the test
+            // for a provable underflow of K_v(w): Re(zeta2 - zeta1) >= |Re w| - gnu (ln(1 + 2/t + t) + pi) > elim makes
+            // the pre-test zero the whole (single-member) sequence.  The K and Hankel drivers then return 0 with
+            // nz = 1 in the right half plane and report an overflow (ierr = 2) in the left one, where the vanished K
+            // would have been continued with the growing I.  (Unscaled functions only: the scaled pre-test has no
+            // |Re w|.)  Y = (H1 - H2)/2i evaluates both Hankel functions at the same |Re w|: one of them vanishes,
+            // the other one is the overflow, so Y reports ierr = 2.
+            const real t = az / gnu1;
+            const real lt = log(real(1.0) + real(2.0) / t + t);
+            const bool noop = gnu1 * (lt + real(SPB_PI) + real(1.0)) + x < alim;
+            if (!noop) {
+                if (final_fam && rabs(p.w.re) - gnu1 * (lt + real(SPB_PI)) > real(SPB_ELIM)) {
+                    const bool overflow = (p.combine == CMB_ACON) || fam == FAM_Y;
+                    p.combine = CMB_FINAL;
+                    p.final_ierr = overflow ? 2 : 0;
+                    p.final_nz = overflow ? 0 : 1;
+                    return p;
+                }
+                p.combine = CMB_GENERAL;
                 return p;
             }
         }
-        p.combine = CMB_GENERAL;
-        return p;
     }
     const int kreg = kregion(p.w, fnu, az);
     const bool debye_on = (fuse & FUSE_DEBYE) != 0;

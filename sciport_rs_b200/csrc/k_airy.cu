@@ -15,10 +15,11 @@ namespace spbk {
 
 // bins 0..5 of the I-bin field: 0 Maclaurin; 1 K series; 2 K Miller; 3 I series; 4 I Miller; 5 large |zeta| (>= rl:
 // K and I from the large-|zeta| routines only, lean kernel); non-finite arguments go to the complete routine
-__device__ __forceinline__ unsigned int airy_key(bool bi, cplx z) {
+__device__ __forceinline__ unsigned int airy_key(bool bi, cplx z, double &azeta) {
     const double az = spb::cabs_(z);
+    azeta = 0.0;
     if (az <= 1.0) return 0u;
-    const double azeta = (2.0 / 3.0) * az * sqrt(az);
+    azeta = (2.0 / 3.0) * az * sqrt(az);
     if (azeta >= SPB_RL * (1.0 + 1.0e-9) && az < 1.0e300) return 5u;  // (margin: the routine forms zeta itself)
     if (!(azeta < SPB_RL)) return 4u;  // at the border, NaN, Inf: complete routine
     // Ai: K_{1/3}(zeta) directly when |arg z| <= pi/3 (Re zeta >= 0, Re z > 0); otherwise, and always for Bi,
@@ -45,8 +46,10 @@ __global__ void __launch_bounds__(256) k_classify_airy(int which, int kode, int 
         if (i < n) {
             double2 t = __ldg(z + i);
             const cplx zc(t.x, t.y);
-            unsigned int key = airy_key(which >= 2, zc);
-            if (key == 5u && kode == 1) {
+            double azeta;
+            unsigned int key = airy_key(which >= 2, zc, azeta);
+            // (the pre-test can only decide a point whose |Re zeta| reaches alim; |zeta| bounds it)
+            if (key == 5u && kode == 1 && azeta >= SPB_ALIM * (1.0 - 1.0e-9)) {
                 spb::AiryPre pre;
                 if (spb::airy_pretest(which >= 2, zc, kode, pre) == spb::AIRY_DONE) {
                     cplx val(0.0, 0.0);
@@ -150,7 +153,14 @@ __global__ void __launch_bounds__(128, LARGE ? 4 : 3) k_airy_sorted(int id, int 
                 const double2 zz = __ldg(z + i);
                 s_idx[slot] = i;
                 s_z[slot] = zz;
-                bucket[r] = bucket_of(airy_work(cplx(zz.x, zz.y)), 0.2);
+                unsigned int bk = bucket_of(airy_work(cplx(zz.x, zz.y)), 0.2);
+                if (LARGE && !BI) {
+                    // large-|zeta| Ai: half of an all-quadrant batch continues K through the cut (K and I combined,
+                    // an underflow test); the work estimate spans few buckets there, the sector takes the top bit
+                    const double az = spb::cabs_(cplx(zz.x, zz.y));
+                    bk = (bk > 15u ? 15u : bk) + (zz.x >= 0.5 * az ? 0u : 16u);
+                }
+                bucket[r] = bk;
             }
         }
         batch_sort(sm, bucket);
