@@ -90,8 +90,10 @@ enum spb_flags {
                            the raw behaviour                                                 */
     SPB_PATH_BINNED = 0,     /* classify -> stable compaction by region -> per-region kernels */
     SPB_PATH_MONOLITHIC = 16, /* one thread runs the whole driver per point (debug / checker) */
-    SPB_PROFILE = 32          /* device pointers only: CUDA events between the kernel launches;
+    SPB_PROFILE = 32,         /* device pointers only: CUDA events between the kernel launches;
                                  read the records back with spb_last_profile()                 */
+    SPB_PATH_NO_DIRECT = 64   /* broadcast-order jobs: every point through the classifier (the direct
+                                 large-|z| kernel that runs ahead of it is switched off; checker) */
 };
 
 /* kernel ids reported by spb_last_profile */
@@ -107,7 +109,8 @@ enum spb_kernel_id {
     SPB_K_MONOLITHIC = 8,    /* whole batch through the general path                 */
     SPB_K_IPASS_UNI1 = 9,    /* I pass: uniform (Debye-type) expansion at raised order */
     SPB_K_IPASS_UNI2 = 10,   /* I pass: uniform (Airy-type) expansion at raised order  */
-    SPB_K_IPASS_DEBYE = 11   /* I and/or K: Debye-type expansion at the order itself   */
+    SPB_K_IPASS_DEBYE = 11,  /* I and/or K: Debye-type expansion at the order itself   */
+    SPB_K_DIRECT = 12        /* broadcast order: large-|z| points in input order, ahead of the classifier */
 };
 
 /* where the buffers live and which GPUs to use */

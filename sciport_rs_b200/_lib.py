@@ -12,9 +12,9 @@ LIB_PATH = os.path.join(_HERE, "libsciport_b200.so")
 
 FN = {"J": 0, "Y": 1, "I": 2, "K": 3, "H1": 4, "H2": 5}
 AIRY = {"Ai": 0, "Aip": 1, "Bi": 2, "Bip": 3}
-SEM_AMOS, SEM_SCIPY, RAW_NEG_ORDERS, PATH_MONOLITHIC, PROFILE = 0, 1, 2, 16, 32
+SEM_AMOS, SEM_SCIPY, RAW_NEG_ORDERS, PATH_MONOLITHIC, PROFILE, PATH_NO_DIRECT = 0, 1, 2, 16, 32, 64
 KERNEL_NAMES = ["classify", "scan_scatter", "ipass_series", "ipass_asyi", "ipass_mlri", "ipass_wrsk", "kpass",
-                "general", "monolithic", "ipass_uni1", "ipass_uni2", "ipass_debye"]
+                "general", "monolithic", "ipass_uni1", "ipass_uni2", "ipass_debye", "direct_asyi"]
 E_ARG, E_NO_DEVICE, E_CUDA, E_ALLOC = -1, -2, -3, -4
 
 

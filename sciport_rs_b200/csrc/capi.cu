@@ -97,6 +97,9 @@ struct DeviceCtx {
     unsigned long long *d_first = nullptr;         // [2] first failing element (packed) of the call in flight
     unsigned long long h_first[2] = {~0ull, ~0ull};  // host copy, valid once the call has completed
     double2 *d_scalar = nullptr;                   // one complex scalar (I0(beta) of the Kaiser window)
+    // outcome of k_direct on the first chunk of a multi-chunk device-pointer call, read back without blocking
+    cudaEvent_t probe_ev = nullptr;
+    unsigned int *h_probe = nullptr;  // pinned
     // The scratch of a device is shared by all calls on it.  Device-pointer calls return while their kernels are
     // still queued, so a following call on ANOTHER stream first waits (on the device) for the event that ends the
     // previous one; calls on the same stream are ordered by the stream itself.
@@ -149,6 +152,8 @@ DeviceCtx *get_ctx(int dev) {
         cudaMalloc(&c->d_packed, sizeof(unsigned long long));
         cudaMalloc(&c->d_first, 2 * sizeof(unsigned long long));
         cudaMalloc(&c->d_scalar, sizeof(double2));
+        cudaEventCreateWithFlags(&c->probe_ev, cudaEventDisableTiming);
+        cudaMallocHost(&c->h_probe, sizeof(unsigned int));
         g_ctx[dev] = c;
     }
     return g_ctx[dev];
@@ -276,7 +281,8 @@ int ensure_scratch(ScratchSet &ss, long long n, cudaStream_t st) {
     };
     size_t o_cls = take(cap), o_pi = take(cap * 4), o_pk = take(cap * 4), o_gl = take(cap * 4),
            o_it = take(cap * 16), o_ic = take(cap), o_bc = take((size_t)NBINS * nblocks_cap * 4), o_bins = take(BINS_WORDS * 4),
-           o_pi2 = take(cap * 4), o_pk2 = take(cap * 4), o_cc = take((size_t)CELL_SLOTS * NCELLS * 4), o_ck = take(cap * 2);
+           o_pi2 = take(cap * 4), o_pk2 = take(cap * 4), o_cc = take((size_t)CELL_SLOTS * NCELLS * 4), o_ck = take(cap * 2),
+           o_dn = take((size_t)nblocks_cap * (TILE / 32));
     char *base = nullptr;
     if (cudaMalloc(&base, off) != cudaSuccess) {
         cudaGetLastError();
@@ -296,6 +302,7 @@ int ensure_scratch(ScratchSet &ss, long long n, cudaStream_t st) {
     ss.s.icode = (signed char *)(base + o_ic);
     ss.s.blockcnt = (unsigned int *)(base + o_bc);
     ss.s.bins = (unsigned int *)(base + o_bins);
+    ss.s.done = (unsigned char *)(base + o_dn);
     ss.s.nblocks = (int)((n + TILE - 1) / TILE);
     // counters of the scan's last-CTA hand-off start at zero: on the stream the pipeline kernels will run on (the
     // pipeline streams are non-blocking, so a memset on the legacy stream would not be ordered before them)
@@ -371,6 +378,15 @@ static bool group_enabled() {
     return on;
 }
 
+// SPB_DIRECT (environment, read once): 0 switches off the direct large-|z| kernel of broadcast-order jobs
+static bool direct_enabled() {
+    static const bool on = [] {
+        const char *e = getenv("SPB_DIRECT");
+        return !(e && atoi(e) == 0);
+    }();
+    return on;
+}
+
 static bool debye_enabled() {
     static const bool on = [] {
         const char *e = getenv("SPB_DEBYE");
@@ -379,7 +395,23 @@ static bool debye_enabled() {
     return on;
 }
 
-int enqueue_chunk(const DevJob &job_in, ScratchSet &ss, int sms, int flags, cudaStream_t st, Prof *pf = nullptr) {
+// Does k_direct pay on this call?  On a batch of unrelated points it finishes nothing, and although its warps give up
+// after a few groups, one more persistent grid at the head of every chunk costs the interleaved chunks of a long call
+// 0.1 ms each (config 4: 4.84 -> 5.29 ms per 2^26 points).  The first chunk of a call always runs it; the number of
+// points it finished is copied to pinned host memory right behind the kernel, and the chunks enqueued after that
+// copy has landed skip the kernel if the answer was zero.  Never blocks: while the answer is pending the kernel runs.
+struct DirectProbe {
+    cudaEvent_t ev;
+    unsigned int *h;
+    int state = 0;  // 0 nothing enqueued yet, 1 answer pending, 2 keep the kernel, 3 drop it
+    bool wanted() {
+        if (state == 1 && cudaEventQuery(ev) == cudaSuccess) state = (*h != 0) ? 2 : 3;
+        return state != 3;
+    }
+};
+
+int enqueue_chunk(const DevJob &job_in, ScratchSet &ss, int sms, int flags, cudaStream_t st, Prof *pf = nullptr,
+                  DirectProbe *probe = nullptr) {
     Prof dummy;
     Prof &p = pf ? *pf : dummy;
     DevJob job = job_in;
@@ -402,6 +434,11 @@ int enqueue_chunk(const DevJob &job_in, ScratchSet &ss, int sms, int flags, cuda
         // the stable-order bins (Debye-direct, fused large-|w|) take the same hint inside CTA batches (SPB_GROUP=0: off)
         job.group = (ktype && job.v_stride != 0 && group_enabled()) ? 1 : 0;  // (I and J: no continuation in the combine step)
         job.pdl = (pdl_enabled() && job.v_stride == 0) ? 1 : 0;
+        // broadcast order: groups of 32 consecutive points that all pass the classifier's fast accept are evaluated
+        // in input order by k_direct before anything is classified (K-type families: by the fused large-|w| routine)
+        job.direct = (job.v_stride == 0 && direct_enabled() && !(flags & (SPB_PATH_MONOLITHIC | SPB_PATH_NO_DIRECT)) &&
+                      (!ktype || (job.fuse & spb::FUSE_ASYI))) ? 1 : 0;
+        if (job.direct && probe && !probe->wanted()) job.direct = 0;
     }
     if (flags & SPB_PATH_MONOLITHIC) {
         p.mark(SPB_K_MONOLITHIC, st);
@@ -410,6 +447,16 @@ int enqueue_chunk(const DevJob &job_in, ScratchSet &ss, int sms, int flags, cuda
         return 1;
     }
     int launches = 0;
+    if (job.direct) {
+        p.mark(SPB_K_DIRECT, st);
+        launch_direct(job, ss.s, sms, st);
+        ++launches;
+        if (probe && probe->state == 0) {
+            cudaMemcpyAsync(probe->h, ss.s.bins + SLOT_DIRECT, sizeof(unsigned int), cudaMemcpyDeviceToHost, st);
+            cudaEventRecord(probe->ev, st);
+            probe->state = 1;
+        }
+    }
     p.mark(SPB_K_CLASSIFY, st);
     launch_classify(job, ss.s, st);
     p.mark(SPB_K_SCAN_SCATTER, st);
@@ -438,7 +485,7 @@ int enqueue_chunk(const DevJob &job_in, ScratchSet &ss, int sms, int flags, cuda
 // turn the recorded events into (kernel, ms, points) records; call after the stream is idle
 void collect_profile(Prof &p, const ScratchSet &ss, long long n) {
     if (!p.on) return;
-    unsigned int bins[GLIST_LEN_SLOT + 1] = {0};
+    unsigned int bins[SLOT_DIRECT_LAST + 1] = {0};
     cudaMemcpy(bins, ss.s.bins, sizeof(bins), cudaMemcpyDeviceToHost);
     for (size_t i = 0; i + 1 < p.ev.size(); ++i) {
         if (p.ids[i] < 0) continue;
@@ -455,6 +502,8 @@ void collect_profile(Prof &p, const ScratchSet &ss, long long n) {
             pts = (long long)bins[BIN_GENERAL] - bins[BIN_K0];
         } else if (id == SPB_K_GENERAL) {
             pts = bins[GLIST_LEN_SLOT];
+        } else if (id == SPB_K_DIRECT) {
+            pts = bins[SLOT_DIRECT_LAST];
         }
         g_prof.push_back({id, ms, pts});
     }
@@ -566,6 +615,7 @@ int run_device(DeviceCtx *c, const BesselArgs &a, cudaStream_t st, double *ms_ou
         CK(cudaEventRecord(c->fork, st));
         for (int b = 0; b < lanes; ++b) CK(cudaStreamWaitEvent(c->streams[b], c->fork, 0));
     }
+    DirectProbe probe{c->probe_ev, c->h_probe};
     int chunk_no = 0;
     for (long long off = 0; off < a.n; off += CHUNK_DEVICE, ++chunk_no) {
         long long m = std::min(CHUNK_DEVICE, a.n - off);
@@ -592,7 +642,8 @@ int run_device(DeviceCtx *c, const BesselArgs &a, cudaStream_t st, double *ms_ou
         job.first_err = c->d_first;
         job.first_err2 = c->d_first + 1;
         job.index_base = a.index_base + off;
-        launches += enqueue_chunk(job, c->scratch[lane], c->sms, a.flags, cst, &prof);
+        launches += enqueue_chunk(job, c->scratch[lane], c->sms, a.flags, cst, &prof,
+                                  (a.n > CHUNK_DEVICE && !prof.on) ? &probe : nullptr);
         if (prof.on) {
             // profiling serialises the chunks so that the bin counters can be read back per chunk
             CK(cudaStreamSynchronize(st));

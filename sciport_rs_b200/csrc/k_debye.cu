@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(128, SPB_DEBYE_MINB) k_debye(DevJob job, Scrat
     job.kode = KODE;
     __shared__ spb::OrderPhase s_ph;
     if (SCALAR) {
-        if (threadIdx.x == 0) s_ph = spb::order_phase(__ldg(job.v));
+        if (threadIdx.x == 0) s_ph = spb::order_phase(scalar_order(job));
         __syncthreads();
     }
     const unsigned int start = s.bins[spb::IREG_DEBYE] - s.bins[0];

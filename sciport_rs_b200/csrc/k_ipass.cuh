@@ -22,8 +22,10 @@ namespace spbk {
 
 // one point of the I pass: I_v(w) by the region routine; J / I families finish here, the others park I(w)
 // FUSED (large-|w| region, families that need K as well): I_v(w) and K_v(w) by the fused routine, combine, store
-template <int REGION, bool FUSED = false>
-__device__ __forceinline__ void ipass_point(const DevJob &job, const Scratch &s, long long i, cplx z, double v,
+// DIRECT (k_direct.cu: the point has no class byte and no list entry yet): a point the routine cannot finish is
+// reported to the caller (false) instead of being appended to the general list, and nothing is parked
+template <int REGION, bool FUSED = false, bool DIRECT = false>
+__device__ __forceinline__ bool ipass_point(const DevJob &job, const Scratch &s, long long i, cplx z, double v,
                                             const spb::OrderPhase *ph) {
     // the classifier has already established region and simplicity of this point: geometry only
     spb::Prep p = spb::prepare_pass(job.fam, z, !FUSED || REGION != spb::IREG_ASYI);
@@ -34,23 +36,25 @@ __device__ __forceinline__ void ipass_point(const DevJob &job, const Scratch &s,
                            ? spb::wrsk_ik_region(p.w, v, job.kode, ival, inz, kval, knz, p.az)
                            : spb::fused_ik_region(p.w, v, job.kode, ival, inz, kval, knz, p.az, ph);
         if (rc < 0 || (knz != 0 && (p.combine == spb::CMB_ACON || p.combine == spb::CMB_Y_SHARED))) {
+            if (DIRECT) return false;
             unsigned int g = atomicAdd(&s.bins[GLIST_LEN_SLOT], 1u);
             s.glist[g] = (unsigned int)i;
-            return;
+            return false;
         }
         finish_store(job, p, i, z, v, ival, inz, kval, knz, ph);
-        return;
+        return true;
     }
     cplx ival;
     int inz = spb::ipass_region(REGION, p.w, v, job.kode, ival, p.az, ph);
     if (inz < 0) {
+        if (DIRECT) return false;
         // the region wants to hand over: finish this point on the general path
         unsigned int g = atomicAdd(&s.bins[GLIST_LEN_SLOT], 1u);
         s.glist[g] = (unsigned int)i;
         s.icode[i] = (signed char)-1;
-        return;
+        return false;
     }
-    if (p.combine == spb::CMB_I_ROT) {
+    if (DIRECT || p.combine == spb::CMB_I_ROT) {  // (DIRECT without FUSED: the J and I families only)
         int ierr, nz;
         cplx val = spb::finish(job.fam, p, z, v, job.kode, ival, inz, cplx(0.0, 0.0), 0, ierr, nz, ph);
         store_point(job, i, val, ierr, nz);
@@ -58,6 +62,7 @@ __device__ __forceinline__ void ipass_point(const DevJob &job, const Scratch &s,
         s.itemp[i] = make_double2(ival.re, ival.im);
         s.icode[i] = (signed char)inz;
     }
+    return true;
 }
 
 // SCALAR = the order is one broadcast value (v_stride = 0): its phase factors are computed once per CTA into shared
@@ -73,7 +78,7 @@ __global__ void __launch_bounds__(128, FAM >= 0 ? (REGION == spb::IREG_ASYI ? SP
     }
     __shared__ spb::OrderPhase s_ph;
     if (SCALAR) {
-        if (threadIdx.x == 0) s_ph = spb::order_phase(__ldg(job.v));
+        if (threadIdx.x == 0) s_ph = spb::order_phase(scalar_order(job));
         __syncthreads();
     }
     const unsigned int start = s.bins[REGION] - s.bins[0];

@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(128, SPB_KPASS_MINB) k_kpass(DevJob job, Scrat
     job.kode = KODE;
     __shared__ spb::OrderPhase s_ph;
     if (SCALAR) {
-        if (threadIdx.x == 0) s_ph = spb::order_phase(__ldg(job.v));
+        if (threadIdx.x == 0) s_ph = spb::order_phase(scalar_order(job));
         __syncthreads();
     }
     const unsigned int count = s.bins[BIN_GENERAL] - s.bins[BIN_K0];

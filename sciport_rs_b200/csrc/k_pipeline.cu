@@ -110,12 +110,27 @@ __device__ __forceinline__ unsigned int cell_of(int fam, cplx z, double v, bool 
     return (unsigned int)(q | (b << CELL_ZBITS)) | (with_side ? (side_of(fam, z) << (CELL_ZBITS + CELL_VBITS)) : 0u);
 }
 
+// Direct jobs (k_direct.cu ran first): is every group of 32 points of this tile already finished?  (one flag byte
+// per group, 64 per tile; the barrier makes the answer CTA-uniform)
+constexpr int GROUPS = TILE / 32;
+__device__ __forceinline__ bool tile_done(const Scratch &s) {
+    const bool mine = threadIdx.x < GROUPS ? s.done[(size_t)blockIdx.x * GROUPS + threadIdx.x] != 0 : true;
+    return __syncthreads_and(mine) != 0;
+}
+
 // FAM / KODE: the job's family and scaling flag as compile-time constants (dispatch_fam_kode)
 template <int FAM, int KODE>
 __global__ void __launch_bounds__(256) k_classify(DevJob job, Scratch s) {
     pdl_enter();
     job.fam = FAM;
     job.kode = KODE;
+    // (k_direct finished nothing -- a batch of unrelated points: classify as if it had not run)
+    if (job.direct && s.bins[SLOT_DIRECT] == 0) job.direct = 0;
+    if (job.direct && tile_done(s)) {
+        // nothing of this tile enters a bin (k_scatter skips the tile on the same test, so no class bytes either)
+        if (threadIdx.x < NBINS) s.blockcnt[(size_t)threadIdx.x * s.nblocks + blockIdx.x] = 0;
+        return;
+    }
     __shared__ unsigned int hist[NBINS];
     if (threadIdx.x < NBINS) hist[threadIdx.x] = 0;
     __syncthreads();
@@ -131,7 +146,18 @@ __global__ void __launch_bounds__(256) k_classify(DevJob job, Scratch s) {
     for (int q = 0; q < PER_THREAD / 4; ++q) cls4[q] = 0xffffffffu;
     // (per-element orders: a warp of 32 unrelated (order, argument) pairs practically never sits in the large-|z|
     // region as a whole, so the fast accept would only add its cost to every point)
-    if (job.v_stride == 0) {
+    if (job.direct) {
+        // the fast accept has been tried by k_direct: its finished groups enter no bin (class byte of a decided
+        // point), everything else goes through prepare().  Thread t holds points t + 256 k: group (t / 32) + 8 k.
+        static_assert(GROUPS == 8 * PER_THREAD, "one group per warp and round");
+#pragma unroll
+        for (int q = 0; q < PER_THREAD / 4; ++q) cls4[q] = 0;
+#pragma unroll
+        for (int k = 0; k < PER_THREAD; ++k) {
+            const bool dn = s.done[(size_t)blockIdx.x * GROUPS + (threadIdx.x >> 5) + 8 * k] != 0;
+            cls4[k / 4] |= (dn ? (7u | (3u << 3)) : 0xffu) << (8 * (k % 4));
+        }
+    } else if (job.v_stride == 0) {
         double2 zk[PER_THREAD];
         double vk[PER_THREAD];
 #pragma unroll
@@ -287,6 +313,8 @@ __global__ void __launch_bounds__(1024) k_scan(Scratch s) {
             s.bins[GLIST_LEN_SLOT] = ((volatile unsigned int *)s.bins)[SLOT_TOTALS + BIN_GENERAL];
             s.bins[SLOT_DONE] = 0;  // re-arm for the next chunk
             s.bins[SLOT_G2] = 0;
+            s.bins[SLOT_DIRECT_LAST] = ((volatile unsigned int *)s.bins)[SLOT_DIRECT];
+            s.bins[SLOT_DIRECT] = 0;
         }
     }
 }
@@ -296,6 +324,8 @@ __global__ void __launch_bounds__(256) k_scatter(DevJob job, Scratch s) {
     // counters of the second-level sort of this chunk (k_cell_hist runs after this kernel, in stream order)
     if (blockIdx.x == 0)
         for (int c = threadIdx.x; c < CELL_SLOTS * NCELLS; c += 256) s.cellcnt[c] = 0;
+    // (k_classify wrote no class bytes for such a tile; k_scan has moved the direct counter on by now)
+    if (job.direct && s.bins[SLOT_DIRECT_LAST] != 0 && tile_done(s)) return;
     __shared__ unsigned long long warp_tot[8][NWORDS];
     __shared__ unsigned int tile_base[NBINS], lstart[NBINS], seg_total[3];
     __shared__ unsigned int stage[3][TILE];

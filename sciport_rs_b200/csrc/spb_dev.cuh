@@ -20,6 +20,13 @@ __device__ __forceinline__ void load_point(const DevJob &j, long long i, cplx &z
     if (j.reflect && j.fam == spb::FAM_K) v = fabs(v);
 }
 
+// the broadcast order of a scalar-order job (v_stride = 0), folded like load_point() folds it
+__device__ __forceinline__ double scalar_order(const DevJob &j) {
+    double v = __ldg(j.v);
+    if (j.reflect && j.fam == spb::FAM_K) v = fabs(v);
+    return v;
+}
+
 // record a failing element in the call-wide "first error" word (smallest (index, ierr) of the call).  Failing
 // elements need not be rare (a quarter of an unscaled log-uniform batch over- or underflows), and a million atomics
 // on one address serialise (measured: 0.7 ms per 4M points): the word is read first -- an L2 load; a stale value only

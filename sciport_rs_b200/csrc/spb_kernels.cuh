@@ -20,6 +20,8 @@ struct DevJob {
     int group;    // 1: inside a tile the compaction orders the entries of the stable bins (large-|w|, Debye-direct) by the
                   // side of the family's continuation (side_of, spb_dev.cuh; bit 6 of the class byte), then by index
     int reflect;  // 1: orders v < 0 by the reflection formulae (K folds v -> |v| at load; the others on the general path)
+    int direct;   // 1: k_direct (k_direct.cu) ran over this chunk first: groups of 32 consecutive points that it accepted
+                  // and finished are flagged in Scratch::done, the classifier and the compaction skip them
     const double *v;
     long long v_stride;  // 0 = broadcast
     const double2 *z;    // complex input, or
@@ -52,6 +54,7 @@ struct Scratch {
     signed char *icode;     // [n] nz of the I pass (<0: handed to the general path)
     unsigned int *blockcnt; // [NBINS][nblocks] per-tile histogram, then exclusive offsets
     unsigned int *bins;     // [NBINS+1] start offsets of bins (concatenated order); [SLOT_GLEN] = glist length
+    unsigned char *done;    // [64 * nblocks] one flag per group of 32 consecutive points: finished by k_direct
     int nblocks;            // tiles in this chunk
 };
 
@@ -84,6 +87,8 @@ constexpr int CELL_SLOTS = 9;
 constexpr int GLIST_LEN_SLOT = 24;  // current length of the general list (grows when a pass hands a point over)
 constexpr int SLOT_DONE = 25;       // CTAs of k_scan that have finished
 constexpr int SLOT_G2 = 26;         // length of the second-stage general list (points left after the shortcuts)
+constexpr int SLOT_DIRECT = 27;     // points finished by k_direct in the chunk being classified (k_scan moves it on)
+constexpr int SLOT_DIRECT_LAST = 28;  // ... in the chunk whose pipeline ran last (read by the profile)
 constexpr int SLOT_TOTALS = 32;     // [NBINS] bin totals
 constexpr int BINS_WORDS = 64;
 
@@ -157,6 +162,8 @@ inline void dispatch_fam_kode(int fam, int kode, A &&...a) {
 // kernels.cu
 void launch_classify(const DevJob &job, const Scratch &s, cudaStream_t st);
 void launch_scan_scatter(const DevJob &job, const Scratch &s, cudaStream_t st);
+// large-|w| points of a broadcast-order job straight from the input order, before classification (k_direct.cu)
+void launch_direct(const DevJob &job, const Scratch &s, int sms, cudaStream_t st);
 int launch_cellsort(const DevJob &job, const Scratch &s, int sms, cudaStream_t st);  // returns the launches made
 void launch_ipass(const DevJob &job, const Scratch &s, int region, int sms, cudaStream_t st);
 // job.fuse: I + K of the K-type points of one I region (large-|w| series / Miller + Wronskian) in one kernel

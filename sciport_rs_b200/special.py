@@ -21,7 +21,8 @@ import ctypes
 import numpy as np
 
 from . import _lib
-from ._lib import lib, check, make_exec, FN, AIRY, SEM_AMOS, SEM_SCIPY, RAW_NEG_ORDERS, PATH_MONOLITHIC, PROFILE
+from ._lib import (lib, check, make_exec, FN, AIRY, SEM_AMOS, SEM_SCIPY, RAW_NEG_ORDERS, PATH_MONOLITHIC, PROFILE,
+                   PATH_NO_DIRECT)
 
 try:  # torch is plumbing only (device memory / streams)
     import torch
@@ -82,6 +83,8 @@ def bessel(fn, v, z, scaled=False, semantics="amos", path="binned", real_input=F
     """
     kode = 2 if scaled else 1
     flags = (SEM_SCIPY if semantics == "scipy" else SEM_AMOS) | (PATH_MONOLITHIC if path == "monolithic" else 0)
+    if path == "classified":  # binned, but every point through the classifier (no direct large-|z| kernel)
+        flags |= PATH_NO_DIRECT
     if profile:
         flags |= PROFILE
     if raw_neg_orders:
@@ -154,12 +157,12 @@ def bessel(fn, v, z, scaled=False, semantics="amos", path="binned", real_input=F
 
 
 def bessel_ik(v, z, scaled=False, semantics="amos", profile=False, outs=None, codes=None, want_codes=True,
-              devices=None):
+              devices=None, path="binned"):
     """I_v(z) and K_v(z) in one pass (spb_bessel_ik): returns ((I, ierr_i, nz_i), (K, ierr_k, nz_k)); scaled=True
     gives the ive / kve pair.  K in the left half plane is continued with I at the same right-half-plane point and
     the large-|z| / Debye-direct regions produce both functions from one series, so the pair costs far less than
     the two single calls."""
-    return bessel_jy(v, z, scaled, semantics, profile, outs, codes, want_codes, devices, _entry="ik")
+    return bessel_jy(v, z, scaled, semantics, profile, outs, codes, want_codes, devices, _entry="ik", path=path)
 
 
 def ive_kve(v, z, outs=None, devices=None):
@@ -183,13 +186,15 @@ def iv_kv(v, z, outs=None, devices=None):
 
 
 def bessel_jy(v, z, scaled=False, semantics="amos", profile=False, outs=None, codes=None, want_codes=True,
-              devices=None, _entry="jy"):
+              devices=None, _entry="jy", path="binned"):
     """J_v(z) and Y_v(z) in one pass (spb_bessel_jy): returns ((J, ierr_j, nz_j), (Y, ierr_y, nz_y)).
     Both functions need I_v at the same rotated point, so the pair shares classification and the I pass."""
     entry = lib.spb_bessel_jy if _entry == "jy" else lib.spb_bessel_ik
     tag = "JY" if _entry == "jy" else "IK"
     kode = 2 if scaled else 1
     flags = (SEM_SCIPY if semantics == "scipy" else SEM_AMOS) | (PROFILE if profile else 0)
+    if path == "classified":
+        flags |= PATH_NO_DIRECT
     if _is_torch(z):
         zc = z.resolve_conj().contiguous().to(torch.complex128)
         n = zc.numel()

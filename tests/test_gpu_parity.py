@@ -792,3 +792,69 @@ def test_ik_pair_matches_single_calls_and_scipy(special, cfg):
     if cfg == "cfg2":
         i2, k2 = special.ive_kve(v[:50000], z[:50000])  # raises like Result<_, i32>; none fails on this grid
         assert np.array_equal(i2.view(np.uint64), i_h.view(np.uint64)) and np.array_equal(k2.view(np.uint64), k_h.view(np.uint64))
+
+
+@pytest.mark.parametrize("kode", [1, 2])
+@pytest.mark.parametrize("fn", ["J", "Y", "I", "K", "H1", "H2"])
+def test_direct_kernel_is_bit_identical_to_the_classified_path(special, fn, kode):
+    """Broadcast-order jobs run k_direct ahead of the classifier (k_direct.cu): groups of 32 consecutive points that
+    all pass the fast accept are evaluated in input order.  It runs the region kernel's own routine, so values AND
+    codes must be bit-identical to path='classified' (SPB_PATH_NO_DIRECT: every point through the classifier) —
+    on a grid with a ragged tail (most groups accepted, the disc around the origin declined), on long constant runs
+    mixed with unrelated points (tiles with finished and unfinished groups side by side), and on a batch of
+    unrelated points (every warp gives up after its first groups)."""
+    rng = np.random.default_rng(helpers.seed_of("direct", fn, str(kode)))
+    side = 700
+    x = np.linspace(-100.0, 100.0, side)
+    grid = (x[None, :] + 1j * x[:, None]).reshape(-1)[: side * side - 13]
+    _, mixed = gen("cfg4", 70000, rng)
+    runs = np.concatenate([np.full(5000, 150.0 + 20.0j), mixed[:3000], np.full(4111, -40.0 + 3.0j), mixed[3000:6000],
+                           np.full(33, 55.0 - 60.0j), np.array([np.nan + 0j, 0j, np.inf + 0j]), np.full(2050, 0.3 + 99.0j)])
+    for label, z in (("grid", grid), ("runs", runs), ("unrelated", mixed)):
+        zt = torch.from_numpy(np.ascontiguousarray(z)).cuda()
+        for order in (0.0, 2.5, 17.0):
+            a, ea, na = special.bessel(fn, order, zt, scaled=(kode == 2))
+            b, eb, nb = special.bessel(fn, order, zt, scaled=(kode == 2), path="classified")
+            assert torch.equal(ea, eb) and torch.equal(na, nb), (label, order)
+            assert np.array_equal(to_np(a).view(np.uint64), to_np(b).view(np.uint64)), (label, order)
+    # real arguments promoted to complex (spb_bessel_real) take the same kernel
+    xr = torch.from_numpy(np.linspace(0.0, 3000.0, 300001)).cuda()
+    a, ea, _ = special.bessel(fn, 1.0, xr, scaled=(kode == 2), real_input=True)
+    b, eb, _ = special.bessel(fn, 1.0, xr, scaled=(kode == 2), real_input=True, path="classified")
+    assert torch.equal(ea, eb) and np.array_equal(to_np(a).view(np.uint64), to_np(b).view(np.uint64))
+
+
+def test_direct_kernel_pairs_profile_and_scipy(special):
+    """The pair entry points through k_direct: bit-identical to the classified path, most of a gridded batch taken
+    by the direct kernel (profile record), values against live scipy."""
+    import scipy.special as sc
+    side = 1024
+    x = np.linspace(-120.0, 120.0, side)
+    z = (x[None, :] + 1j * x[:, None]).reshape(-1)
+    zt = torch.from_numpy(z).cuda()
+    for entry, kw in ((special.bessel_jy, {}), (special.bessel_ik, {"scaled": True})):
+        (a, ea, _), (b, eb, _) = entry(2.5, zt, **kw)
+        (c, ec, _), (d, ed, _) = entry(2.5, zt, path="classified", **kw)
+        assert torch.equal(ea, ec) and torch.equal(eb, ed)
+        assert np.array_equal(to_np(a).view(np.uint64), to_np(c).view(np.uint64))
+        assert np.array_equal(to_np(b).view(np.uint64), to_np(d).view(np.uint64))
+    prof = special.profile_step(lambda: special.bessel_jy(2.5, zt, profile=True))
+    direct = sum(r["points"] for r in prof if r["name"].endswith("direct_asyi"))
+    assert direct > 0.9 * z.size, (direct, z.size)
+    (j, _, _), (y, _, _) = special.bessel_jy(2.5, zt)
+    idx = np.arange(0, z.size, 97)
+    wj, wy = sc.jv(2.5, z[idx]), sc.yv(2.5, z[idx])
+    scale = np.maximum(np.abs(wj), np.abs(wy))
+    assert np.all(np.abs(to_np(j)[idx] - wj) <= 1e-13 * scale) and np.all(np.abs(to_np(y)[idx] - wy) <= 1e-13 * scale)
+
+
+def test_scalar_negative_order_of_k_on_the_binned_path(special):
+    """K_{-v} = K_v with a BROADCAST negative order: the order is folded where it is loaded, also for the per-CTA
+    order phase of the scalar-order kernels (left half plane: the continuation uses it)."""
+    rng = np.random.default_rng(11)
+    _, z = gen("cfg2", 150000, rng)
+    zt = torch.from_numpy(z).cuda()
+    for kode in (1, 2):
+        a, ea, _ = special.bessel("K", -3.5, zt, scaled=(kode == 2))
+        b, eb, _ = special.bessel("K", 3.5, zt, scaled=(kode == 2))
+        assert torch.equal(ea, eb) and np.array_equal(to_np(a).view(np.uint64), to_np(b).view(np.uint64))
