@@ -316,7 +316,8 @@ def other_configs(torch, special, dev, fp64_peak, hbm_peak, flops, reps=3):
     def profiled(call, prefix):
         prof = aggregate_profile(special.profile_step(call))
         for r in prof:
-            r["key"] = prefix + r["name"]
+            # (k_direct runs the large-|w| routine of the region kernel on points in input order: same tally)
+            r["key"] = prefix + r["name"].replace("direct_asyi", "ipass_asyi")
         return prof
 
     # ---- cfg1: gamma, ln|gamma| and J0/J1/Y0/Y1 (real arguments promoted to complex, mod.rs:10) on [0, 100]
@@ -352,7 +353,7 @@ def other_configs(torch, special, dev, fp64_peak, hbm_peak, flops, reps=3):
     _, z2 = special.synth(2, n2, n_total=n2, device=dev)
     outs = [torch.empty(n2, dtype=torch.complex128, device=dev) for _ in range(2)]
     ms = timed(torch, lambda: special.bessel_jy(2.5, z2, outs=outs, want_codes=False), max(reps, 5))
-    prof = profiled(lambda: special.bessel_jy(2.5, z2, outs=outs, profile=True), "")
+    prof = profiled(lambda: special.bessel_jy(2.5, z2, outs=outs, profile=True, want_codes=False), "")
     (gj, ej, _), (gy, ey, _) = special.bessel_jy(2.5, z2)
     idx, zs = sample(z2, n2)
     acc = {"J": scipy_accuracy("J", 1, 2.5, zs, gj[idx].cpu().numpy(), ej[idx].cpu().numpy()),
