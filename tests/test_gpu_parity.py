@@ -858,3 +858,16 @@ def test_scalar_negative_order_of_k_on_the_binned_path(special):
         a, ea, _ = special.bessel("K", -3.5, zt, scaled=(kode == 2))
         b, eb, _ = special.bessel("K", 3.5, zt, scaled=(kode == 2))
         assert torch.equal(ea, eb) and np.array_equal(to_np(a).view(np.uint64), to_np(b).view(np.uint64))
+
+
+def test_large_orders_and_loss_points_vs_mpmath_truth_gpu(special):
+    """The points the scipy comparison has to skip (kode-2 orders above fnul, scipy's "loss" category) against the
+    mpmath fixture tests/golden/large_order_truth2.npz, through the C ABI with device pointers."""
+    from test_oracle_golden import large_order_truth_errors
+
+    def evaluate(fn, kode, v, z):
+        got, ierr, nz = special.bessel(fn, torch.from_numpy(v).cuda(), torch.from_numpy(z).cuda(), scaled=(kode == 2))
+        return to_np(got), to_np(ierr), to_np(nz)
+
+    for label, err, tol in large_order_truth_errors(evaluate):
+        assert np.all(err <= tol), f"{label}: max {err.max():.2e} ({int((err > tol).sum())} of {err.size} above tolerance)"

@@ -61,6 +61,53 @@ def test_large_order_scaled_vs_mpmath_truth():
         assert np.all(err < 5e-13), f"{fn}: {err.max():.2e}"
 
 
+def large_order_truth_errors(evaluate):
+    """Normalised errors of `evaluate(fn, kode, v, z) -> (values, ierr, nz)` against tests/golden/large_order_truth2.npz
+    (mpmath at 50 + 0.9 |z| digits or more, generator tests/golden/make_golden_large_order.py): every order > fnul
+    point of bessel_golden.npz plus 120 seeded points with orders up to 300 (scaled functions), and the points where
+    scipy reports a loss of half the digits (both scalings).  Yields (label, err over the points both sides resolve)."""
+    g = helpers.load_golden("large_order_truth2.npz")
+    v, z = g["v"], g["z"]
+    comp_of = {"K": ("I", np.pi), "Y": ("J", 1.0), "H1": ("J", 1.0), "H2": ("J", 1.0), "J": ("Y", 1.0), "I": ("K", 1 / np.pi)}
+    for fn in ("K", "H1", "H2", "Y", "J", "I"):
+        got, ierr, nz = evaluate(fn, 2, v, z)
+        want = g[f"{fn}_2"]
+        ok = np.isfinite(want.real) & (ierr == 0) & (nz == 0)
+        assert ok.sum() >= 0.7 * len(v), (fn, int(ok.sum()))
+        # absolute bound where the function is a difference of two larger terms (continuation / Hankel combination):
+        # the companion's truth, put on the scale of fn's scaling factor, is the size of those terms
+        cname, wgt = comp_of[fn]
+        comp = np.abs(g[f"{cname}_2"]) * wgt
+        with np.errstate(all="ignore"):
+            if fn == "K":
+                comp = np.where(z.real < 0, comp * np.exp(2 * z.real), 0.0)  # e^{z} * e^{|Re z|} I
+            elif fn == "I":
+                comp = np.where(np.abs(z.real) <= 1, comp * np.exp(-2 * np.abs(z.real)), 0.0)
+            elif fn in ("H1", "H2"):
+                grow = z.imag < 0 if fn == "H1" else z.imag > 0
+                comp = np.where(grow, 0.0, comp * np.exp(-2 * np.abs(z.imag)))  # recessive side only: no cancellation
+        scale = np.maximum(np.abs(want), np.where(np.isfinite(comp), comp, 0.0))
+        with np.errstate(all="ignore"):
+            err = np.abs(got - want) / scale
+        # measured: at most 1.9e-13 for orders 86 .. 300 (the tolerance policy would allow 6e-13 .. 2.7e-12 there)
+        yield f"{fn}_2", err[ok], np.minimum(so.tolerance(want, z, v)[ok], 3e-13)
+    lv, lz = g["loss_v"], g["loss_z"]
+    for kode in (1, 2):
+        for fn in ("K", "H1", "H2", "Y", "J", "I"):
+            got, ierr, nz = evaluate(fn, kode, lv, lz)
+            want = g[f"loss_{fn}_{kode}"]
+            ok = np.isfinite(want.real) & np.isin(ierr, (0, 3)) & (nz == 0)
+            with np.errstate(all="ignore"):
+                err = np.abs(got - want) / np.abs(want)
+            yield f"loss {fn}_{kode}", err[ok], np.full(int(ok.sum()), 1e-13)
+
+
+def test_large_orders_and_loss_points_vs_mpmath_truth():
+    """The two classes of points the scipy comparison skips (scipy_kode2_defect, category "loss") against mpmath."""
+    for label, err, tol in large_order_truth_errors(lambda fn, kode, v, z: helpers.cpu_bessel(fn, kode, v, z)):
+        assert np.all(err <= tol), f"{label}: max {err.max():.2e} ({int((err > tol).sum())} of {err.size} above tolerance)"
+
+
 @pytest.mark.parametrize("kode", [1, 2])
 @pytest.mark.parametrize("which", [0, 1, 2, 3])
 def test_airy_vs_golden(which, kode):
