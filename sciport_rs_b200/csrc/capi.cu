@@ -387,6 +387,17 @@ static bool direct_enabled() {
     return on;
 }
 
+// smallest chunk the direct kernel is launched for (SPB_DIRECT_MIN_LOG2 in the environment, read once; the tests
+// lower it to exercise the kernel on small batches)
+static long long direct_min_points() {
+    static const long long n = [] {
+        const char *e = getenv("SPB_DIRECT_MIN_LOG2");
+        const int l = e ? atoi(e) : 22;
+        return 1ll << (l < 0 ? 0 : (l > 40 ? 40 : l));
+    }();
+    return n;
+}
+
 static bool debye_enabled() {
     static const bool on = [] {
         const char *e = getenv("SPB_DEBYE");
@@ -436,8 +447,10 @@ int enqueue_chunk(const DevJob &job_in, ScratchSet &ss, int sms, int flags, cuda
         job.pdl = (pdl_enabled() && job.v_stride == 0) ? 1 : 0;
         // broadcast order: groups of 32 consecutive points that all pass the classifier's fast accept are evaluated
         // in input order by k_direct before anything is classified (K-type families: by the fused large-|w| routine)
+        // (not below 2^22 points per chunk: there the kernel can win a few microseconds at most, and on a batch of
+        // unrelated points its launch, although its warps give up at once, is 4 - 9 % of a 2^20-point call: config 1)
         job.direct = (job.v_stride == 0 && direct_enabled() && !(flags & (SPB_PATH_MONOLITHIC | SPB_PATH_NO_DIRECT)) &&
-                      (!ktype || (job.fuse & spb::FUSE_ASYI))) ? 1 : 0;
+                      (!ktype || (job.fuse & spb::FUSE_ASYI)) && job.n >= direct_min_points()) ? 1 : 0;
         if (job.direct && probe && !probe->wanted()) job.direct = 0;
     }
     if (flags & SPB_PATH_MONOLITHIC) {
@@ -643,7 +656,7 @@ int run_device(DeviceCtx *c, const BesselArgs &a, cudaStream_t st, double *ms_ou
         job.first_err2 = c->d_first + 1;
         job.index_base = a.index_base + off;
         launches += enqueue_chunk(job, c->scratch[lane], c->sms, a.flags, cst, &prof,
-                                  (a.n > CHUNK_DEVICE && !prof.on) ? &probe : nullptr);
+                                  (a.n > CHUNK_DEVICE && !prof.on && c->h_probe) ? &probe : nullptr);
         if (prof.on) {
             // profiling serialises the chunks so that the bin counters can be read back per chunk
             CK(cudaStreamSynchronize(st));

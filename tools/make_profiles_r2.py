@@ -20,14 +20,14 @@ from make_profiles import launch_summary  # noqa: E402
 # bench.py's kernel names (spb profile records of the pair call) -> ncu kernel names of the same launches
 BENCH_NAMES = {
     "IK/ipass_debye": ["k_debye<"],
-    "IK/ipass_wrsk": ["k_ipass<(int)3,"],
+    "IK/ipass_wrsk": ["k_ipass<3,"],
     "IK/kpass": ["k_kpass<"],
     "IK/classify": ["k_classify<"],
-    "IK/ipass_mlri": ["k_ipass<(int)2,"],
-    "IK/ipass_asyi": ["k_ipass<(int)1,"],
-    "IK/ipass_series": ["k_ipass<(int)0,"],
-    "IK/ipass_uni1": ["k_ipass<(int)4,"],
-    "IK/ipass_uni2": ["k_ipass<(int)5,"],
+    "IK/ipass_mlri": ["k_ipass<2,"],
+    "IK/ipass_asyi": ["k_ipass<1,"],
+    "IK/ipass_series": ["k_ipass<0,"],
+    "IK/ipass_uni1": ["k_ipass<4,"],
+    "IK/ipass_uni2": ["k_ipass<5,"],
     "IK/scan_scatter": ["k_scan(", "k_scatter(", "k_cell_hist(", "k_cell_scan(", "k_cell_scatter("],
     "IK/general": ["k_general("],
 }
@@ -58,7 +58,8 @@ def main():
                          "time_us": float(r[1]) * tu}
     kernels = {}
     for name, pats in BENCH_NAMES.items():
-        hit = [(k, v) for k, v in per.items() if any(p in k for p in pats)]
+        # (kernel names with or without the (int) / (bool) casts of the demangler)
+        hit = [(k, v) for k, v in per.items() if any(p in k.replace("(int)", "").replace("(bool)", "") for p in pats)]
         if hit:
             kernels[name] = {"bytes": sum(v["dram_read_bytes"] + v["dram_write_bytes"] for _, v in hit),
                              "dram_read_bytes": sum(v["dram_read_bytes"] for _, v in hit),
