@@ -810,7 +810,11 @@ def test_direct_kernel_is_bit_identical_to_the_classified_path(special, fn, kode
     _, mixed = gen("cfg4", 70000, rng)
     runs = np.concatenate([np.full(5000, 150.0 + 20.0j), mixed[:3000], np.full(4111, -40.0 + 3.0j), mixed[3000:6000],
                            np.full(33, 55.0 - 60.0j), np.array([np.nan + 0j, 0j, np.inf + 0j]), np.full(2050, 0.3 + 99.0j)])
-    for label, z in (("grid", grid), ("runs", runs), ("unrelated", mixed)):
+    # whole groups that pass the fast accept but that the fused routine hands back (unscaled K / H beyond the
+    # exponent range of exp(-Re w), orders <= 2 have no pre-test): k_direct must leave them to the pipeline
+    far = np.concatenate([np.full(4096, -800.0 + 5.0j), np.full(4096, 900.0 + 1.0j), np.full(2048, 3.0 + 900.0j),
+                          np.full(2048, 3.0 - 900.0j), np.full(2048, -760.0 - 740.0j), np.full(1000, 30000.0 + 1.0j)])
+    for label, z in (("grid", grid), ("runs", runs), ("unrelated", mixed), ("far", far)):
         zt = torch.from_numpy(np.ascontiguousarray(z)).cuda()
         for order in (0.0, 2.5, 17.0):
             a, ea, na = special.bessel(fn, order, zt, scaled=(kode == 2))
