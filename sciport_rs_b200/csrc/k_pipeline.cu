@@ -120,7 +120,7 @@ __device__ __forceinline__ bool tile_done(const Scratch &s) {
 
 // FAM / KODE: the job's family and scaling flag as compile-time constants (dispatch_fam_kode)
 template <int FAM, int KODE>
-__global__ void __launch_bounds__(256) k_classify(DevJob job, Scratch s) {
+__global__ void __launch_bounds__(256, 4) k_classify(DevJob job, Scratch s) {
     pdl_enter();
     job.fam = FAM;
     job.kode = KODE;
