@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(256) k_airy_small(int id, int kode, int sem, c
 // shared memory and grouped by predicted work (spb_dev.cuh), evaluated by the lean mid-range routines
 // LARGE: key 5 instead (|zeta| >= rl: the large-|zeta| routines; the length of their series falls with |zeta|)
 template <bool BI, bool LARGE = false>
-__global__ void __launch_bounds__(128, LARGE ? 4 : 3) k_airy_sorted(int id, int kode, int sem, const double2 *z,
+__global__ void __launch_bounds__(128, LARGE ? 4 : 6) k_airy_sorted(int id, int kode, int sem, const double2 *z,
                                                                    double2 *out, int *ierr, int *nz, long long n,
                                                                    Scratch s, unsigned long long *first_err,
                                                                    long long index_base) {

@@ -12,7 +12,7 @@ namespace spbk {
 // leaves about ninety such points per 2^24-point chunk) is spread one point per warp over the whole machine instead
 // of filling three warps of one SM, whose lanes then walked up to 32 different branches of the driver one after the
 // other (measured: 89 us per chunk for 91 points); a long list fills all 32 lanes of every warp as before.
-__global__ void __launch_bounds__(128) k_general(DevJob job, const unsigned int *list, const unsigned int *len) {
+__global__ void __launch_bounds__(128, 4) k_general(DevJob job, const unsigned int *list, const unsigned int *len) {
     pdl_enter();
     const unsigned int count = *len;
     const unsigned int nwarps = (gridDim.x * blockDim.x) >> 5;
