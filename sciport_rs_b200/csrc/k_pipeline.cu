@@ -96,6 +96,28 @@ __device__ __forceinline__ unsigned int field_g(const Packed &p) {
     return (unsigned int)p.w[2] & ((1u << FIELD_BITS) - 1u);
 }
 
+// The increments of the three packed words for every class byte, as a shared-memory table: the if / else form above
+// ran with 15 of 32 lanes and was 45 % of the instructions of k_scatter (the bytes of a warp's points differ; in the
+// classifier, a tenth of the instructions, the table measured no gain); a branch-free arithmetic form paid as much in 64-bit variable shifts.  One table per
+// CTA, filled by its first 128 threads from the very functions above; a point then costs three 8-byte shared loads
+// (a handful of distinct addresses per warp) and three adds.  sided: bit 6 counts in the side fields (compaction).
+__device__ __forceinline__ void packed_table_init(unsigned long long (*tab)[NWORDS], bool sided) {
+    for (unsigned int c = threadIdx.x; c < 128u; c += blockDim.x) {
+        Packed p;
+        p.clear();
+        if (sided)
+            packed_add_sided(c, p);
+        else
+            packed_add(c, p);
+#pragma unroll
+        for (int k = 0; k < NWORDS; ++k) tab[c][k] = p.w[k];
+    }
+}
+__device__ __forceinline__ void packed_add_tab(const unsigned long long (*tab)[NWORDS], unsigned int c, Packed &p) {
+#pragma unroll
+    for (int k = 0; k < NWORDS; ++k) p.w[k] += tab[c & 0x7fu][k];
+}
+
 // (side, |z|, order) cell of a point for the second-level sort (see k_cell_hist below): 2^CELL_ZBITS levels of |z|
 // over [1, 256] (8 per octave with 6 bits, 4 with 5), 2^CELL_VBITS levels of the order over [0, 64), 2 sides
 __device__ __forceinline__ unsigned int cell_of(int fam, cplx z, double v, bool with_side) {
@@ -329,6 +351,8 @@ __global__ void __launch_bounds__(256) k_scatter(DevJob job, Scratch s) {
     __shared__ unsigned long long warp_tot[8][NWORDS];
     __shared__ unsigned int tile_base[NBINS], lstart[NBINS], seg_total[3];
     __shared__ unsigned int stage[3][TILE];
+    __shared__ unsigned long long ptab[128][NWORDS];
+    packed_table_init(ptab, true);  // (published by the barrier of the homogeneous-tile test below)
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const long long base = (long long)blockIdx.x * TILE + (long long)threadIdx.x * 8;
     if (threadIdx.x < NBINS) {
@@ -372,7 +396,7 @@ __global__ void __launch_bounds__(256) k_scatter(DevJob job, Scratch s) {
     mine.clear();
 #pragma unroll
     for (int k = 0; k < 8; ++k)
-        if (k < valid) packed_add_sided((unsigned int)((cls8 >> (8 * k)) & 0xffu), mine);
+        if (k < valid) packed_add_tab(ptab, (unsigned int)((cls8 >> (8 * k)) & 0xffu), mine);
     // block-wide exclusive scan of the packed counters (fields never exceed 2048)
     Packed incl = mine;
 #pragma unroll
@@ -436,7 +460,7 @@ __global__ void __launch_bounds__(256) k_scatter(DevJob job, Scratch s) {
             stage[0][lstart[bi] + ((ck & 0x40u) ? field_i(total, bi) + field_side(off, bi) : field_i(off, bi))] = idx;
         if (bk != 3) stage[1][lstart[BIN_K0 + bk] + field_k(off, bk)] = idx;
         if (gen) stage[2][field_g(off)] = idx;
-        packed_add_sided(ck, off);
+        packed_add_tab(ptab, ck, off);
     }
     __syncthreads();
     // coalesced write-out, one segment at a time; position j of a segment belongs to the last bin whose local
