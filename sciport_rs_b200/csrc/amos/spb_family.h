@@ -410,15 +410,15 @@ SPB_FN Prep prepare_pass(int fam, cplx z, bool with_modulus = true) {
 // One region of the I pass.  Returns the AMOS nz (>= 0) or < 0 when the region
 // wants to hand over (-> general path).
 SPB_FN int ipass_region(int region, cplx w, real fnu, int kode, cplx &val, real az = real(-1.0),
-                        const OrderPhase *oph = nullptr, const WShared *ws = nullptr) {
+                        const OrderPhase *oph = nullptr, const WShared *ws = nullptr, const real *gl = nullptr) {
     const real tol = SPB_TOL, elim = SPB_ELIM, alim = SPB_ALIM, rl = SPB_RL;
     cplx y[1];
     y[0] = cplx(0.0, 0.0);
     int nw;
     switch (region) {
-        case IREG_SERIES: nw = seri(w, fnu, kode, 1, y, tol, elim, alim, az); break;
+        case IREG_SERIES: nw = seri(w, fnu, kode, 1, y, tol, elim, alim, az, gl); break;
         case IREG_ASYI: nw = asyi(w, fnu, kode, 1, y, rl, tol, elim, alim, az, oph, ws); break;
-        case IREG_MLRI: nw = mlri(w, fnu, kode, 1, y, tol, az); break;
+        case IREG_MLRI: nw = mlri(w, fnu, kode, 1, y, tol, az, gl); break;
         case IREG_WRSK: nw = wrsk<true>(w, fnu, kode, 1, y, tol, elim, alim, az); break;
         case IREG_UNI1:
         case IREG_UNI2: {

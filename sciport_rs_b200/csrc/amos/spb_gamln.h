@@ -64,4 +64,14 @@ SPB_HD real gamln(real z) {
     return gamln(z, ie);
 }
 
+// ln Gamma at the arguments that depend on the order alone: which = 0: 1 + fnu (power series), 1: 1 + fnf, 2: 1 + 2 fnf
+// with fnf = fnu - int(fnu) (Neumann normalisation of the Miller routine).  A kernel of a broadcast-order job
+// evaluates them once per CTA and hands them to the routine (`gl`), where every point would otherwise evaluate them
+// again; the numbers are gamln() of the same arguments.
+SPB_FN real order_gln(real fnu, int which) {
+    const real fnf = fnu - real((int)fnu);
+    const real arg = which == 0 ? fnu + real(1.0) : which == 1 ? real(1.0) + fnf : (fnf + fnf) + real(1.0);
+    return gamln(arg);
+}
+
 }  // namespace spb

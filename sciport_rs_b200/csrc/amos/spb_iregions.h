@@ -19,7 +19,7 @@ namespace spb {
 // remaining order, so the caller must finish with another method.
 template <class Y>
 SPB_FN int seri(cplx z, real fnu, int kode, int n, Y y, real tol, real elim, real alim,
-                real az_known = real(-1.0)) {
+                real az_known = real(-1.0), const real *gl = nullptr) {
     int nz = 0;
     real az = az_known >= real(0.0) ? az_known : cabs_(z);
     if (az == real(0.0)) {
@@ -51,7 +51,7 @@ SPB_FN int seri(cplx z, real fnu, int kode, int n, Y y, real tol, real elim, rea
         real fnup = dfnu + real(1.0);
         // underflow test on the leading factor (z/2)^v / Gamma(v+1)
         cplx ak1 = ck * dfnu;
-        real ak = gamln(fnup);
+        real ak = (gl && nn == 1) ? gl[0] : gamln(fnup);  // (nn == 1: fnup = fnu + 1, see order_gln)
         ak1.re -= ak;
         if (kode == 2) ak1.re -= z.re;
         bool underflow = !(ak1.re > -elim);
@@ -312,7 +312,8 @@ SPB_HD void mlri_back(int steps, cplx &p1, cplx &p2, cplx rz, real &fkk, real fn
 // ---------------------------------------------------------------------------
 // Miller algorithm normalised by a Neumann series.  nz = -2: no convergence.
 template <class Y>
-SPB_FN int mlri(cplx z, real fnu, int kode, int n, Y y, real tol, real az_known = real(-1.0)) {
+SPB_FN int mlri(cplx z, real fnu, int kode, int n, Y y, real tol, real az_known = real(-1.0),
+                const real *gl = nullptr) {
     const real scle = SPB_D1MACH1 / tol;
     real az = az_known >= real(0.0) ? az_known : cabs_(z);
     int iaz = (int)az;
@@ -407,7 +408,7 @@ SPB_FN int mlri(cplx z, real fnu, int kode, int n, Y y, real tol, real az_known 
     p2 = cplx(scle, 0.0);  // scaled start value
     real fnf = fnu - real(ifnu);
     real tfnf = fnf + fnf;
-    real bk = gamln(fkk + tfnf + real(1.0)) - gamln(fkk + real(1.0)) - gamln(tfnf + real(1.0));
+    real bk = gamln(fkk + tfnf + real(1.0)) - gamln(fkk + real(1.0)) - (gl ? gl[2] : gamln(tfnf + real(1.0)));
     bk = exp_(bk);
     cplx sum(0.0, 0.0);
     int km = kk - inu;
@@ -429,7 +430,7 @@ SPB_FN int mlri(cplx z, real fnu, int kode, int n, Y y, real tol, real az_known 
     if (kode == 2) pt.re = 0.0;
     cplx lrz = clog_(rz);
     cplx q = pt - lrz * fnf;
-    real ap = gamln(real(1.0) + fnf);
+    real ap = gl ? gl[1] : gamln(real(1.0) + fnf);
     q.re -= ap;
     // exp(q)/(sum+p2) without squaring large magnitudes
     p2 = p2 + sum;

@@ -26,7 +26,7 @@ namespace spbk {
 // reported to the caller (false) instead of being appended to the general list, and nothing is parked
 template <int REGION, bool FUSED = false, bool DIRECT = false>
 __device__ __forceinline__ bool ipass_point(const DevJob &job, const Scratch &s, long long i, cplx z, double v,
-                                            const spb::OrderPhase *ph) {
+                                            const spb::OrderPhase *ph, const double *gl = nullptr) {
     // the classifier has already established region and simplicity of this point: geometry only
     spb::Prep p = spb::prepare_pass(job.fam, z, !FUSED || REGION != spb::IREG_ASYI);
     if (FUSED) {
@@ -45,7 +45,7 @@ __device__ __forceinline__ bool ipass_point(const DevJob &job, const Scratch &s,
         return true;
     }
     cplx ival;
-    int inz = spb::ipass_region(REGION, p.w, v, job.kode, ival, p.az, ph);
+    int inz = spb::ipass_region(REGION, p.w, v, job.kode, ival, p.az, ph, nullptr, gl);
     if (inz < 0) {
         if (DIRECT) return false;
         // the region wants to hand over: finish this point on the general path
@@ -77,8 +77,19 @@ __global__ void __launch_bounds__(128, FAM >= 0 ? (REGION == spb::IREG_ASYI ? SP
         job.kode = KODE;
     }
     __shared__ spb::OrderPhase s_ph;
+    // broadcast order, power series / Miller routine: the order-only values of ln Gamma once per CTA (order_gln; the
+    // two of the Miller routine on two warps, side by side) instead of once per point — a quarter of the
+    // instructions of the series kernel on config 4
+    constexpr bool GLN = SCALAR && FAM < 0 && (REGION == spb::IREG_SERIES || REGION == spb::IREG_MLRI);
+    __shared__ double s_gl[3];
     if (SCALAR) {
         if (threadIdx.x == 0) s_ph = spb::order_phase(scalar_order(job));
+        if (GLN) {
+            const double vs = scalar_order(job);
+            if (REGION == spb::IREG_SERIES && threadIdx.x == 0) s_gl[0] = spb::order_gln(vs, 0);
+            if (REGION == spb::IREG_MLRI && (threadIdx.x == 32 || threadIdx.x == 64))
+                s_gl[threadIdx.x >> 5] = spb::order_gln(vs, (int)(threadIdx.x >> 5));
+        }
         __syncthreads();
     }
     const unsigned int start = s.bins[REGION] - s.bins[0];
@@ -106,7 +117,7 @@ __global__ void __launch_bounds__(128, FAM >= 0 ? (REGION == spb::IREG_ASYI ? SP
         if (have2) i2 = __ldg(perm + t + stride);
         if (have1) load_point(job, i1, z1, v1);
         if (SCALAR) {
-            ipass_point<REGION, (FAM >= 0)>(job, s, i, z, v, &s_ph);
+            ipass_point<REGION, (FAM >= 0)>(job, s, i, z, v, &s_ph, GLN ? s_gl : nullptr);
         } else {
             const spb::OrderPhase ph = spb::order_phase(v);
             ipass_point<REGION, (FAM >= 0)>(job, s, i, z, v, &ph);

@@ -875,3 +875,28 @@ def test_large_orders_and_loss_points_vs_mpmath_truth_gpu(special):
 
     for label, err, tol in large_order_truth_errors(evaluate):
         assert np.all(err <= tol), f"{label}: max {err.max():.2e} ({int((err > tol).sum())} of {err.size} above tolerance)"
+
+
+@pytest.mark.parametrize("fn", ["J", "Y", "I", "K", "H1", "H2"])
+def test_broadcast_order_kernels_agree_with_per_element_orders(special, fn):
+    """The kernels of a broadcast-order job take the order-only values of ln Gamma (power series, Miller / Neumann
+    normalisation, Temme series of K) from a per-CTA cache (OrderPhase::gl_*, order_phase_scalar).  A scalar order and
+    the same order passed per element must report the same codes and agree to rounding (the two are different
+    instantiations of the same routines, so the compiler's FMA contraction may differ in the last bits) — on a batch
+    that lives in the small- and mid-|z| regions where those routines run."""
+    rng = np.random.default_rng(helpers.seed_of("glcache", fn))
+    _, z = gen("cfg4", 40000, rng)
+    zt = torch.from_numpy(z).cuda()
+    for order in (0.0, 0.3, 2.5, 7.25, 30.0):
+        v = np.full(z.size, order)
+        vt = torch.from_numpy(v).cuda()
+        for kode in (1, 2):
+            a, ea, na = special.bessel(fn, order, zt, scaled=(kode == 2))
+            b, eb, nb = special.bessel(fn, vt, zt, scaled=(kode == 2))
+            assert torch.equal(ea, eb) and torch.equal(na, nb), (order, kode)
+            a, b = to_np(a), to_np(b)
+            ok = (to_np(ea) == 0) & (to_np(na) == 0) & np.isfinite(b.real) & np.isfinite(b.imag)
+            scale = so.scale_near_zeros(fn, kode, v, z, b)
+            err = so.mismatch(a, b, scale)[ok]
+            # (a few roundings of an O(v) exponent / recurrence: measured 75 eps at v = 30)
+            assert err.max() <= max(64.0, 6.0 * order) * so.EPS, (order, kode, float(err.max()))
