@@ -416,7 +416,13 @@ struct DirectProbe {
     unsigned int *h;
     int state = 0;  // 0 nothing enqueued yet, 1 answer pending, 2 keep the kernel, 3 drop it
     bool wanted() {
-        if (state == 1 && cudaEventQuery(ev) == cudaSuccess) state = (*h != 0) ? 2 : 3;
+        if (state == 1) {
+            const cudaError_t e = cudaEventQuery(ev);
+            if (e == cudaSuccess)
+                state = (*h != 0) ? 2 : 3;
+            else if (e == cudaErrorNotReady)
+                cudaGetLastError();  // "not ready" is an answer, not an error: keep it out of the call's error check
+        }
         return state != 3;
     }
 };
