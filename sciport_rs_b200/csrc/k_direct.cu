@@ -15,7 +15,10 @@
 //
 // A batch of unrelated points (config 4) never has 32 accepting lanes at once: a warp that has declined its first
 // DIRECT_BAIL groups without a single accept stops (the flags are cleared before the launch and only ever set), and
-// when no warp has finished anything the classifier runs exactly as it does without this kernel.
+// when no warp has finished anything the classifier runs exactly as it does without this kernel.  The launcher side
+// (capi.cu) keeps the kernel away from where it cannot pay: chunks below 2^22 points never get it, and a multi-chunk
+// call reads the outcome of its first chunk back without blocking (DirectProbe) and drops it from the later chunks
+// if it finished nothing.
 #include "k_ipass.cuh"
 
 namespace spbk {
