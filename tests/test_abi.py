@@ -55,3 +55,23 @@ def test_product_does_not_import_oracle():
                 assert not re.search(r"^\s*(import|from)\s+oracle\b", text, flags=re.M), f
                 assert not re.search(r"#include\s+\"[^\"]*oracle/", text), f
                 assert "libspb_oracle" not in text, f
+
+
+def test_header_enums_match_the_python_binding():
+    """exec.flags and the kernel ids of spb_last_profile are duplicated in sciport_rs_b200/_lib.py: keep them in step
+    with include/sciport_b200.h."""
+    from sciport_rs_b200 import _lib
+    src = open(os.path.join(ROOT, "include", "sciport_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    enum = {k: int(v) for k, v in re.findall(r"\b(SPB_[A-Z0-9_]+)\s*=\s*(-?\d+)", src)}
+    assert enum["SPB_SEM_SCIPY"] == _lib.SEM_SCIPY and enum["SPB_RAW_NEG_ORDERS"] == _lib.RAW_NEG_ORDERS
+    assert enum["SPB_PATH_MONOLITHIC"] == _lib.PATH_MONOLITHIC and enum["SPB_PROFILE"] == _lib.PROFILE
+    assert enum["SPB_PATH_NO_DIRECT"] == _lib.PATH_NO_DIRECT
+    flags = [enum[k] for k in ("SPB_SEM_SCIPY", "SPB_RAW_NEG_ORDERS", "SPB_PATH_MONOLITHIC", "SPB_PROFILE", "SPB_PATH_NO_DIRECT")]
+    assert len(set(flags)) == len(flags) and all(f & (f - 1) == 0 for f in flags)  # distinct single bits
+    ids = {k[len("SPB_K_"):].lower(): v for k, v in enum.items() if k.startswith("SPB_K_")}
+    assert sorted(ids.values()) == list(range(len(_lib.KERNEL_NAMES)))
+    for name, i in ids.items():
+        want = "direct_asyi" if name == "direct" else name
+        assert _lib.KERNEL_NAMES[i] == want, (name, i, _lib.KERNEL_NAMES[i])
+    assert enum["SPB_E_NO_DEVICE"] == _lib.E_NO_DEVICE and enum["SPB_E_ARG"] == _lib.E_ARG
